@@ -1,0 +1,102 @@
+/* spnet_b200.h — C ABI of libspnet_b200.so, the sm_100a kernel library behind the
+ * B200-native SPNet hot path (Xception-SPNet forward/backward + YOLO-ellipse loss).
+ *
+ * The reference (drscotthawley/SPNet) is pure Python on Keras 2.1.3 / TF 1.14 and has no
+ * FFI of its own; this is the boundary its maintainer would bind with ctypes (see
+ * INTEGRATION.md). Each entry point names the reference code it replaces.
+ *
+ * Conventions:
+ *   - the caller owns all memory: device pointers + explicit shapes; the library never
+ *     allocates, frees or synchronises;
+ *   - every call is asynchronous on `stream`, safe to capture in a CUDA graph;
+ *   - returns 0, or a negative code (SPNET_ERR_*) with a per-thread message available from
+ *     spnet_last_error(); never throws;
+ *   - activations are NHWC; `dtype` is 0 (fp32) or 1 (bf16) for activation tensors;
+ *     parameters, BatchNorm statistics, losses and weight gradients are fp32;
+ *   - sm_100a only (spnet_check_device() reports anything else); no CPU fallback.
+ *
+ * This header is parsed by spnet_b200/_lib.py to build the ctypes signatures: keep one
+ * prototype per statement, parameters as `type name`.
+ */
+#ifndef SPNET_B200_H
+#define SPNET_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define SPNET_ERR_ARG (-1)
+#define SPNET_ERR_CUDA (-2)
+#define SPNET_ERR_ARCH (-3)
+
+/* ---- library ---- */
+int spnet_version(void);
+const char* spnet_last_error(void);
+int spnet_check_device(void);
+
+/* ---- loss / output head ----
+ * custom_loss (spnet/models.py:564-589) and my_loss (:594-633) in one launch.
+ * out6 = [total, center, size, angle, noobj, class]; grad (nullable) = dL/dy_pred.
+ * hybrid: cf.loss_type != 'same' (BCE-with-logits on noobj). sel_sigmoid: y_pred's noobj
+ * columns are pre-activations of a SelectiveSigmoid layer (:277-298). */
+int spnet_yolo_ellipse_loss(const float* y_true, const float* y_pred, int batch, int ncols, int hybrid, int sel_sigmoid, float* out6, float* grad, cudaStream_t stream);
+/* SelectiveSigmoid.call (spnet/models.py:293-295); selective_activation.py:6-9 */
+int spnet_selective_sigmoid_fwd(const float* x, float* y, int rows, int ncols, int start, int end, int skip, cudaStream_t stream);
+int spnet_selective_sigmoid_bwd(const float* y, const float* dy, float* dx, int rows, int ncols, int start, int end, int skip, cudaStream_t stream);
+/* denorm_Y (spnet/utils.py:186-188) + integer part of cleanup_antinode_vars (:56-64) +
+ * existence test (:109-118). denorm [n,ncols] f32, ints [n,ncols/8,5] i32 (cx,cy,a,b,noobj),
+ * exists [n,ncols/8] u8. */
+int spnet_decode_detections(const float* y, const float* means, const float* ranges, int n, int ncols, float* denorm, int* ints, unsigned char* exists, cudaStream_t stream);
+
+/* ---- SeparableConv2D depthwise half (keras.applications.Xception; spnet/models.py:359) ---- */
+int spnet_dwconv3x3_fwd(const void* in, const float* k, const float* in_a, const float* in_b, int relu, void* out, int dtype, int B, int H, int W, int C, cudaStream_t stream);
+int spnet_dwconv3x3_dgrad(const void* gout, const float* k, void* gin, const void* mask_src, const float* mask_a, const float* mask_b, const void* add_src, const void* add_strided, int dtype, int B, int H, int W, int C, cudaStream_t stream);
+int spnet_dwconv3x3_wgrad(const void* in, const void* gout, const float* in_a, const float* in_b, int relu, float* dk, int dtype, int B, int H, int W, int C, cudaStream_t stream);
+
+/* ---- GEMMs: pointwise 1x1, strided 1x1 residual convs, block1_conv2 (im2col), Dense head
+ *      (spnet/models.py:359,388). See gemm_tc.cu / gemm_simt.cu for operand conventions. ---- */
+int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* D, long long ldd, int out_mode, int M, int N, int K, int splits, double* colstats, cudaStream_t stream);
+int spnet_gemm_simt(const void* A, long long sa_r, long long sa_k, const void* B, long long sb_r, long long sb_k, void* D, long long ldd, int dtype, int out_mode, int M, int N, int K, int splits, double* colstats, cudaStream_t stream);
+
+/* ---- BatchNormalization (43 layers; spnet/models.py:326-336 + Xception) ---- */
+int spnet_bn_finalize(double* stats, long long count, const float* gamma, const float* beta, float eps, float momentum, int unbiased_moving_var, float* a, float* b, float* save_mean, float* save_rstd, float* moving_mean, float* moving_var, int C, cudaStream_t stream);
+int spnet_bn_inference_affine(const float* gamma, const float* beta, const float* moving_mean, const float* moving_var, float eps, float* a, float* b, int C, cudaStream_t stream);
+int spnet_bn_apply(const void* z, const float* a, const float* b, int act, const void* x, void* out, int dtype, long long rows, int C, cudaStream_t stream);
+int spnet_bn_bwd_reduce(void* g, const void* z, const float* save_mean, const float* save_rstd, const float* relu_a, const float* relu_b, int act, double* stats, int dtype, long long rows, int C, cudaStream_t stream);
+int spnet_bn_bwd_finalize(double* stats, long long count, float* dgamma, float* dbeta, float* c1, float* c2, int C, cudaStream_t stream);
+int spnet_bn_bwd_dz(const void* g, const void* z, const float* a, const float* save_mean, const float* save_rstd, const float* c1, const float* c2, void* out, int dtype, long long rows, int C, cudaStream_t stream);
+
+/* ---- MaxPooling2D(3,2,'same') + BN-apply + residual Add (Xception blocks 2-4, 13) ---- */
+int spnet_maxpool3s2_add_fwd(const void* z, const float* a, const float* b, const void* res, const float* ra, const float* rb, void* out, unsigned char* argmax, int dtype, int B, int H, int W, int C, cudaStream_t stream);
+int spnet_maxpool3s2_bwd(const void* gout, const unsigned char* argmax, void* gin, int dtype, int B, int H, int W, int C, cudaStream_t stream);
+int spnet_gather_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, cudaStream_t stream);
+
+/* ---- SPNet stem (spnet/models.py:319-340), block1_conv1, block1_conv2 im2col ---- */
+int spnet_conv_small_fwd(int which, const void* in, const float* w, const float* in_a, const float* in_b, int act, void* out, void* skip, double* stats, int dtype, int B, int H, int W, cudaStream_t stream);
+int spnet_conv_small_wgrad(int which, const void* in, const float* in_a, const float* in_b, int act, const void* g, float* dw, int dtype, int B, int H, int W, cudaStream_t stream);
+int spnet_conv_small_dgrad(int which, const void* g, const float* w, const void* mask_z, const float* mask_a, const float* mask_b, int act, void* gin, int dtype, int B, int H, int W, cudaStream_t stream);
+int spnet_stem_k3_to_k4(const float* k3, float* k4, int cout, cudaStream_t stream);
+int spnet_stem_k4grad_to_k3grad(const float* g4, float* g3, int cout, cudaStream_t stream);
+int spnet_stem_out_fwd(const void* c3, const float* a, const float* b, const void* skip, void* out, int dtype, long long pixels, float rate, const unsigned long long* seed, cudaStream_t stream);
+int spnet_stem_out_bwd(const void* g, void* gout, int dtype, long long pixels, float rate, const unsigned long long* seed, cudaStream_t stream);
+int spnet_bn3_bwd_reduce(const void* g, const void* z, const float* save_mean, const float* save_rstd, double* stats, int dtype, long long pixels, cudaStream_t stream);
+int spnet_bn3_bwd_dz(const void* g, const void* z, const float* a, const float* save_mean, const float* save_rstd, const float* c1, const float* c2, void* out, int dtype, long long pixels, cudaStream_t stream);
+int spnet_im2col3x3(const void* in, const float* a, const float* b, int relu, void* col, int dtype, int B, int H, int W, int C, cudaStream_t stream);
+int spnet_col2im3x3(const void* gcol, const void* z, const float* a, const float* b, int relu, void* gin, int dtype, int B, int H, int W, int C, cudaStream_t stream);
+
+/* ---- optimiser: keras Adam (spnet/models.py:494) + L2 of add_regularization (:47-71) ---- */
+int spnet_adam_keras_step(float* p, const float* g, float* m, float* v, long long n, long long n_l2, float l2, const float* lr_t_dev, float beta1, float beta2, float eps, float grad_scale, void* p_bf16, cudaStream_t stream);
+int spnet_sumsq(const float* p, long long n, float scale, float* out, cudaStream_t stream);
+int spnet_cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
+int spnet_cast_bf16_to_f32(const void* src, float* dst, long long n, cudaStream_t stream);
+int spnet_bias_fill(const float* bias, float* out, int rows, int cols, cudaStream_t stream);
+int spnet_colsum(const float* g, float* out, int rows, int cols, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPNET_B200_H */

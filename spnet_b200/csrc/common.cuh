@@ -1,0 +1,89 @@
+// spnet_b200 — shared device/host helpers for the sm_100a kernels.
+// Conventions: caller owns all memory, every entry point is
+// asynchronous on the given stream, returns 0 or a negative error code and
+// records a per-thread message readable through spnet_last_error().
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/spnet_b200.h"
+
+#define SPNET_OK 0
+
+#define SPNET_F32 0
+#define SPNET_BF16 1
+
+void spnet_set_error(const char* fmt, ...);
+int spnet_check_launch(const char* what);
+
+#define SPNET_REQUIRE(cond, ...)                                   \
+    do {                                                           \
+        if (!(cond)) {                                             \
+            spnet_set_error(__VA_ARGS__);                          \
+            return SPNET_ERR_ARG;                                  \
+        }                                                          \
+    } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------
+// 16-byte vector access: 4 floats or 8 bf16, always widened to fp32 registers.
+// ---------------------------------------------------------------------------
+template <typename T> struct VecN;
+template <> struct VecN<float> { static constexpr int N = 4; };
+template <> struct VecN<bf16> { static constexpr int N = 8; };
+
+__device__ __forceinline__ void load_vec(const float* p, float (&v)[4]) {
+    float4 r = *reinterpret_cast<const float4*>(p);
+    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+}
+__device__ __forceinline__ void load_vec(const bf16* p, float (&v)[8]) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ void store_vec(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void store_vec(bf16* p, const float (&v)[8]) {
+    uint4 r;
+    r.x = pack_bf16x2(v[0], v[1]);
+    r.y = pack_bf16x2(v[2], v[3]);
+    r.z = pack_bf16x2(v[4], v[5]);
+    r.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = r;
+}
+
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(bf16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f32(float x);
+template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float x) { return __float2bfloat16_rn(x); }
+// value as it will read back after being stored as T
+template <typename T> __device__ __forceinline__ float round_to(float x) { return to_f32(from_f32<T>(x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// dispatch on activation dtype code
+#define SPNET_DISPATCH_DTYPE(dtype, ...)                                   \
+    do {                                                                   \
+        if ((dtype) == SPNET_F32) { typedef float T; __VA_ARGS__; }        \
+        else if ((dtype) == SPNET_BF16) { typedef bf16 T; __VA_ARGS__; }   \
+        else { spnet_set_error("bad dtype code %d", (int)(dtype)); return SPNET_ERR_ARG; } \
+    } while (0)

@@ -1,0 +1,410 @@
+// bf16 GEMM on the 5th-generation tensor cores: TMA (cp.async.bulk.tensor) feeds a
+// shared-memory ring, one elected thread issues tcgen05.mma with the fp32 accumulator
+// in TMEM, four warps drain it with tcgen05.ld. Serves the pointwise 1x1 convolutions
+// of SeparableConv2D, the strided 1x1 residual convolutions, block1_conv2 (as an
+// im2col GEMM) and the Dense head of the reference model (spnet/models.py:359,388),
+// forward, data-gradient and weight-gradient:
+//
+//     D[M,N] (op)= A[M,K] * B[K,N]
+//
+// Each operand is described by its memory order relative to the reduction dim K:
+//   K-major  : element (r, k) at  ptr[r*ld + k]   (activations in forward/dgrad)
+//   MN-major : element (r, k) at  ptr[k*ld + r]   (keras (Cin,Cout) weights in forward,
+//                                                  both operands in weight-gradient)
+// so no transposed weight copies are needed. Out-of-range rows/cols/k are zero-filled
+// by TMA, which makes ragged M, N (728 = 5*128+88) and K (728 = 11*64+24) exact.
+//
+// Epilogue modes: store bf16, store fp32, atomic-add fp32 (split-K); optional fused
+// per-column sum / sum-of-squares (BatchNorm batch statistics) accumulated in fp64.
+#include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M (cta_group::1)
+constexpr int BK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 128;
+
+enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_ATOMIC_F32 = 2 };
+
+struct GemmEpi {
+    void* out;
+    long long ldc;
+    int mode;
+    double* colstats;  // [2*N] (sum, sumsq) or nullptr
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a lost arrive turns into a trap (reported as a launch failure) instead of a hang.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t spins = 0; !ok; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!ok && (spins & 1023u) == 1023u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) __trap();  // ~2 s at 2 GHz
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 version 1), SWIZZLE_128B.
+//  K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused.
+//  MN-major: atoms of 64 elements (128 B) x 8 k-rows; SBO = distance between 8-k-row
+//            groups (1024 B), LBO = distance between 64-element atoms along M/N.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB, GemmEpi epi,
+                                                           int M, int N, int K, int kb_per_split) {
+    constexpr uint32_t A_BYTES = BM * BK * 2;
+    constexpr uint32_t B_BYTES = BN * BK * 2;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+    __shared__ uint32_t tmem_base_holder;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.y * BM;
+    const int total_kb = (K + BK - 1) / BK;
+    const int kb_begin = blockIdx.z * kb_per_split;
+    const int kb_end = min(total_kb, kb_begin + kb_per_split);
+    const int nkb = kb_end - kb_begin;  // host guarantees >= 1
+
+    const uint32_t full0 = smem_u32(&bars[0]);
+    const uint32_t empty0 = smem_u32(&bars[STAGES]);
+    const uint32_t tfull = smem_u32(&bars[2 * STAGES]);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&tmem_base_holder)),
+                     "r"((uint32_t)BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_holder;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES;
+            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                const uint32_t sb = sa + A_BYTES;
+                const int k0 = (kb_begin + i) * BK;
+                mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+                if (A_MN) {
+#pragma unroll
+                    for (int j = 0; j < BM / 64; ++j)
+                        tma_load_2d(sa + j * (BK * 128), &tmA, full0 + 8 * s, m0 + 64 * j, k0);
+                } else {
+                    tma_load_2d(sa, &tmA, full0 + 8 * s, k0, m0);
+                }
+                if (B_MN) {
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j)
+                        tma_load_2d(sb + j * (BK * 128), &tmB, full0 + 8 * s, n0 + 64 * j, k0);
+                } else {
+                    tma_load_2d(sb, &tmB, full0 + 8 * s, k0, n0);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        // instruction descriptor: fp32 accumulate, bf16 x bf16, majors, N>>3, M>>4
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                               ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES;
+            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+            mbar_wait(full0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t ad = A_MN ? make_smem_desc(sa + k * (UMMA_K * 128), BK * 128, 1024)
+                                             : make_smem_desc(sa + k * (UMMA_K * 2), 0, 1024);
+                    const uint64_t bd = B_MN ? make_smem_desc(sb + k * (UMMA_K * 128), BK * 128, 1024)
+                                             : make_smem_desc(sb + k * (UMMA_K * 2), 0, 1024);
+                    umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(empty0 + 8 * s);          // frees the smem stage when these MMAs retire
+                if (i == nkb - 1) umma_commit(tfull);  // accumulator complete
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---------------- epilogue: all four warps ----------------
+    mbar_wait(tfull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncwarp();
+
+    const int row = m0 + warp * 32 + lane;
+    const bool row_ok = row < M;
+    float* stage_f32 = reinterpret_cast<float*>(smem);  // [BM][BN+1] fp32, reuses the (drained) ring
+    constexpr int LDS = BN + 1;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+        const int col0 = n0 + c * 32;
+        if (epi.mode == OUT_BF16) {
+            uint32_t packed[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                packed[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            if (epi.colstats) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    stage_f32[(warp * 32 + lane) * LDS + c * 32 + 2 * j] = __uint_as_float(packed[j] << 16);
+                    stage_f32[(warp * 32 + lane) * LDS + c * 32 + 2 * j + 1] =
+                        __uint_as_float(packed[j] & 0xffff0000u);
+                }
+            }
+            if (row_ok) {
+                bf16* o = reinterpret_cast<bf16*>(epi.out) + (size_t)row * epi.ldc + col0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (col0 + q * 8 < N)  // N % 8 == 0 is checked on the host
+                        *reinterpret_cast<uint4*>(o + q * 8) =
+                            make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                }
+            }
+        } else {
+            if (epi.colstats) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    stage_f32[(warp * 32 + lane) * LDS + c * 32 + j] = __uint_as_float(v[j]);
+            }
+            if (row_ok) {
+                float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldc + col0;
+                if (epi.mode == OUT_F32) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (col0 + q * 4 < N)  // N % 4 == 0 is checked on the host
+                            *reinterpret_cast<float4*>(o + q * 4) =
+                                make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                            __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < N) atomicAdd(o + j, __uint_as_float(v[j]));
+                }
+            }
+        }
+    }
+    if (epi.colstats) {
+        __syncthreads();
+        // thread t owns column t (and t+128 when BN == 256); rows past M hold exact zeros
+        for (int cc = threadIdx.x; cc < BN; cc += kThreads) {
+            if (n0 + cc < N) {
+                float s = 0.f, s2 = 0.f;
+#pragma unroll 8
+                for (int r = 0; r < BM; ++r) {
+                    const float x = stage_f32[r * LDS + cc];
+                    s += x;
+                    s2 = fmaf(x, x, s2);
+                }
+                atomicAdd(epi.colstats + (n0 + cc), (double)s);
+                atomicAdd(epi.colstats + N + (n0 + cc), (double)s2);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN)
+                     : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled get_encode() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+// operand with `rows` along M/N and `kdim` along K; ld in elements
+int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long long kdim, long long ld, bool mn_major,
+                     int tile_rows) {
+    PFN_cuTensorMapEncodeTiled enc = get_encode();
+    if (!enc) {
+        spnet_set_error("gemm_bf16: cuTensorMapEncodeTiled entry point not available");
+        return SPNET_ERR_CUDA;
+    }
+    cuuint64_t dims[2], strides[1];
+    cuuint32_t box[2], estr[2] = {1, 1};
+    if (mn_major) {
+        dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)kdim;
+        box[0] = 64; box[1] = BK;
+    } else {
+        dims[0] = (cuuint64_t)kdim; dims[1] = (cuuint64_t)rows;
+        box[0] = BK; box[1] = (cuuint32_t)tile_rows;
+    }
+    strides[0] = (cuuint64_t)ld * 2;
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        spnet_set_error("gemm_bf16: cuTensorMapEncodeTiled failed (%d) rows=%lld k=%lld ld=%lld mn=%d", (int)r, rows,
+                        kdim, ld, (int)mn_major);
+        return SPNET_ERR_CUDA;
+    }
+    return SPNET_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmEpi epi, int M, int N, int K, int splits,
+                cudaStream_t stream) {
+    constexpr int STAGES = (BN <= 128) ? 3 : 4;
+    constexpr size_t ring = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2);
+    constexpr size_t stats_tile = (size_t)BM * (BN + 1) * 4;
+    constexpr size_t smem = (ring > stats_tile ? ring : stats_tile) + 1024;
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            spnet_set_error("gemm_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return SPNET_ERR_CUDA;
+        }
+        configured = true;
+    }
+    const int total_kb = (K + BK - 1) / BK;
+    if (splits < 1) splits = 1;
+    if (splits > total_kb) splits = total_kb;
+    const int kbps = (total_kb + splits - 1) / splits;
+    splits = (total_kb + kbps - 1) / kbps;  // no empty splits
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
+    kern<<<grid, kThreads, smem, stream>>>(ta, tb, epi, M, N, K, kbps);
+    return spnet_check_launch("gemm_bf16");
+}
+
+}  // namespace
+
+extern "C" {
+
+// D[M,N] (op)= A[M,K] * B[K,N], bf16 operands, fp32 accumulation in TMEM.
+//   a_mn / b_mn : 0 = K-major (ptr[r*ld + k]), 1 = MN-major (ptr[k*ld + r])
+//   out_mode    : 0 store bf16, 1 store fp32, 2 atomic-add fp32 (required when splits > 1)
+//   colstats    : nullable fp64 [2*N]; per-column sum and sum of squares of the values as
+//                 stored (after bf16 rounding in mode 0) are atomically added
+//   Requirements: pointers 16-byte aligned, lda/ldb multiples of 8, N % 8 == 0 (bf16 out)
+//                 or N % 4 == 0 (fp32 store).
+int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* D,
+                    long long ldd, int out_mode, int M, int N, int K, int splits, double* colstats,
+                    cudaStream_t stream) {
+    SPNET_REQUIRE(A && B && D, "gemm_bf16: null pointer");
+    SPNET_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16: bad shape %d %d %d", M, N, K);
+    SPNET_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm_bf16: lda/ldb must be multiples of 8 elements");
+    SPNET_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)D % 16 == 0),
+                  "gemm_bf16: pointers must be 16-byte aligned");
+    SPNET_REQUIRE(out_mode >= 0 && out_mode <= 2, "gemm_bf16: bad out_mode %d", out_mode);
+    SPNET_REQUIRE(out_mode != OUT_BF16 || (N % 8 == 0 && ldd % 8 == 0), "gemm_bf16: bf16 output needs N, ldd %% 8 == 0");
+    SPNET_REQUIRE(out_mode != OUT_F32 || (N % 4 == 0 && ldd % 4 == 0), "gemm_bf16: fp32 output needs N, ldd %% 4 == 0");
+    SPNET_REQUIRE(splits <= 1 || out_mode == OUT_ATOMIC_F32, "gemm_bf16: split-K needs out_mode 2");
+    SPNET_REQUIRE(!(colstats && splits > 1), "gemm_bf16: column statistics are not defined for split-K partials");
+    constexpr int BN = 128;
+    CUtensorMap ta, tb;
+    int rc = make_operand_map(&ta, A, M, K, lda, a_mn != 0, BM);
+    if (rc) return rc;
+    rc = make_operand_map(&tb, B, N, K, ldb, b_mn != 0, BN);
+    if (rc) return rc;
+    GemmEpi epi = {D, ldd, out_mode, colstats};
+    if (a_mn) {
+        if (b_mn) return launch_gemm<BN, true, true>(ta, tb, epi, M, N, K, splits, stream);
+        return launch_gemm<BN, true, false>(ta, tb, epi, M, N, K, splits, stream);
+    }
+    if (b_mn) return launch_gemm<BN, false, true>(ta, tb, epi, M, N, K, splits, stream);
+    return launch_gemm<BN, false, false>(ta, tb, epi, M, N, K, splits, stream);
+}
+
+}  // extern "C"

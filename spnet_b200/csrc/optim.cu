@@ -1,0 +1,126 @@
+// Optimiser and parameter utilities.
+//  * Adam in the Keras 2.1.3 form used by the reference (spnet/models.py:494:
+//    Adam(lr=1e-5), beta=(0.9,0.999), eps=K.epsilon()=1e-7):
+//        lr_t = lr*sqrt(1-b2^t)/(1-b1^t);  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2
+//        p   -= lr_t * m / (sqrt(v) + eps)         <- eps outside the bias correction
+//    fused with the L2 regulariser gradient of add_regularization (spnet/models.py:47-71:
+//    1e-4*sum(w^2) on 10 kernels -> + 2e-4*w) and with the refresh of the bf16 working copy.
+//  * sum of squares (the L2 term of the reported loss), casts, bias fill, column sums.
+#include "common.cuh"
+
+namespace {
+
+// params live in one flat fp32 buffer; the L2-regularised tensors occupy [0, n_l2).
+__global__ void __launch_bounds__(256) adam_keras_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                         float* __restrict__ m, float* __restrict__ v,
+                                                         long long n, long long n_l2, float l2,
+                                                         const float* __restrict__ lr_t_ptr, float beta1,
+                                                         float beta2, float eps, float grad_scale,
+                                                         bf16* __restrict__ p_bf16) {
+    const float lr_t = *lr_t_ptr;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        float pi = p[i];
+        float gi = g[i] * grad_scale;
+        if (i < n_l2) gi = fmaf(2.0f * l2, pi, gi);
+        const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+        pi -= lr_t * mi / (sqrtf(vi) + eps);
+        p[i] = pi;
+        m[i] = mi;
+        v[i] = vi;
+        if (p_bf16) p_bf16[i] = __float2bfloat16_rn(pi);
+    }
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ p, long long n, float scale,
+                                                    float* __restrict__ out) {
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        s = fmaf(p[i], p[i], s);
+    __shared__ float red[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicAdd(out, t * scale);
+    }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        dst[i] = __float2bfloat16_rn(src[i]);
+}
+__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        dst[i] = __bfloat162float(src[i]);
+}
+
+// out[r, c] = bias[c]
+__global__ void bias_fill_kernel(const float* __restrict__ bias, float* __restrict__ out, int rows, int cols) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * cols) out[i] = bias[i % cols];
+}
+// out[c] = sum_r g[r, c]   (rows small: the Dense bias gradient)
+__global__ void colsum_kernel(const float* __restrict__ g, float* __restrict__ out, int rows, int cols) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += g[(size_t)r * cols + c];
+    out[c] = s;
+}
+
+int grid_for(long long n) {
+    long long g = (n + 255) / 256;
+    const long long cap = 148LL * 8;
+    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int spnet_adam_keras_step(float* p, const float* g, float* m, float* v, long long n, long long n_l2, float l2,
+                          const float* lr_t_dev, float beta1, float beta2, float eps, float grad_scale,
+                          void* p_bf16, cudaStream_t stream) {
+    SPNET_REQUIRE(p && g && m && v && lr_t_dev && n > 0 && n_l2 >= 0 && n_l2 <= n, "adam_keras_step: bad args");
+    adam_keras_kernel<<<grid_for(n), 256, 0, stream>>>(p, g, m, v, n, n_l2, l2, lr_t_dev, beta1, beta2, eps,
+                                                      grad_scale, reinterpret_cast<bf16*>(p_bf16));
+    return spnet_check_launch("adam_keras_step");
+}
+
+// *out += scale * sum(p^2)
+int spnet_sumsq(const float* p, long long n, float scale, float* out, cudaStream_t stream) {
+    SPNET_REQUIRE(p && out && n > 0, "sumsq: bad args");
+    sumsq_kernel<<<grid_for(n), 256, 0, stream>>>(p, n, scale, out);
+    return spnet_check_launch("sumsq");
+}
+
+int spnet_cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t stream) {
+    SPNET_REQUIRE(src && dst && n > 0, "cast_f32_to_bf16: bad args");
+    cast_f32_bf16_kernel<<<grid_for(n), 256, 0, stream>>>(src, reinterpret_cast<bf16*>(dst), n);
+    return spnet_check_launch("cast_f32_to_bf16");
+}
+int spnet_cast_bf16_to_f32(const void* src, float* dst, long long n, cudaStream_t stream) {
+    SPNET_REQUIRE(src && dst && n > 0, "cast_bf16_to_f32: bad args");
+    cast_bf16_f32_kernel<<<grid_for(n), 256, 0, stream>>>(reinterpret_cast<const bf16*>(src), dst, n);
+    return spnet_check_launch("cast_bf16_to_f32");
+}
+
+int spnet_bias_fill(const float* bias, float* out, int rows, int cols, cudaStream_t stream) {
+    SPNET_REQUIRE(bias && out && rows > 0 && cols > 0, "bias_fill: bad args");
+    bias_fill_kernel<<<ceil_div((long long)rows * cols, 256), 256, 0, stream>>>(bias, out, rows, cols);
+    return spnet_check_launch("bias_fill");
+}
+int spnet_colsum(const float* g, float* out, int rows, int cols, cudaStream_t stream) {
+    SPNET_REQUIRE(g && out && rows > 0 && cols > 0, "colsum: bad args");
+    colsum_kernel<<<ceil_div(cols, 128), 128, 0, stream>>>(g, out, rows, cols);
+    return spnet_check_launch("colsum");
+}
+
+}  // extern "C"

@@ -1,0 +1,208 @@
+// MaxPooling2D(3, strides 2, 'same') fused with the BatchNorm-apply of both branches and
+// the residual add of the Xception entry/exit blocks (keras.applications.Xception blocks
+// 2-4 and 13; reference call site spnet/models.py:359), its backward, and the stride-2
+// row/column subsample that feeds the 1x1 stride-2 residual convolutions.
+//
+// TF 'SAME' padding is asymmetric: out = ceil(in/2), pad_total = max((out-1)*2+3-in, 0),
+// pad_before = pad_total/2 (even sizes pad only at the end). Padded cells never win the max.
+#include "common.cuh"
+
+namespace {
+
+__host__ __device__ inline int same_pad_before(int in) {
+    const int out = (in + 1) / 2;
+    int total = (out - 1) * 2 + 3 - in;
+    if (total < 0) total = 0;
+    return total / 2;
+}
+
+// out = max_{3x3,s2}(a*z+b) + (ra*res+rb);  argmax (optional) = kh*3+kw of the first maximum
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_add_fwd_kernel(const T* __restrict__ z, const float* __restrict__ a,
+                                                              const float* __restrict__ b,
+                                                              const T* __restrict__ res,
+                                                              const float* __restrict__ ra,
+                                                              const float* __restrict__ rb, T* __restrict__ out,
+                                                              unsigned char* __restrict__ argmax, int B, int H,
+                                                              int W, int C, int OH, int OW, int pt, int pl) {
+    constexpr int V = VecN<T>::N;
+    const int CV = C / V;
+    const long long n = (long long)B * OH * OW * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int ow = (int)(r % OW);
+    r /= OW;
+    const int oh = (int)(r % OH);
+    const int bi = (int)(r / OH);
+    const int c0 = cv * V;
+    float av[V], bv[V], best[V];
+    int arg[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        av[i] = a ? a[c0 + i] : 1.f;
+        bv[i] = a ? b[c0 + i] : 0.f;
+        best[i] = -INFINITY;
+        arg[i] = 0;
+    }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const int ih = oh * 2 - pt + kh;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int iw = ow * 2 - pl + kw;
+            if (iw < 0 || iw >= W) continue;
+            float v[V];
+            load_vec(z + (((size_t)bi * H + ih) * W + iw) * C + c0, v);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const float y = fmaf(v[i], av[i], bv[i]);
+                if (y > best[i]) { best[i] = y; arg[i] = kh * 3 + kw; }
+            }
+        }
+    }
+    if (res) {
+        float v[V];
+        load_vec(res + idx * V, v);
+#pragma unroll
+        for (int i = 0; i < V; ++i) best[i] += ra ? fmaf(v[i], ra[c0 + i], rb[c0 + i]) : v[i];
+    }
+    store_vec(out + idx * V, best);
+    if (argmax) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) argmax[idx * V + i] = (unsigned char)arg[i];
+    }
+}
+
+// gin[b,h,w,c] = sum over the (<= 2x2) windows containing (h,w) whose argmax is (h,w)
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ gout,
+                                                          const unsigned char* __restrict__ argmax,
+                                                          T* __restrict__ gin, int B, int H, int W, int C, int OH,
+                                                          int OW, int pt, int pl) {
+    constexpr int V = VecN<T>::N;
+    const int CV = C / V;
+    const long long n = (long long)B * H * W * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int w = (int)(r % W);
+    r /= W;
+    const int h = (int)(r % H);
+    const int bi = (int)(r / H);
+    const int c0 = cv * V;
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const int t = h + pt - kh;  // = 2*oh
+        if (t < 0 || (t & 1)) continue;
+        const int oh = t >> 1;
+        if (oh >= OH) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int u = w + pl - kw;
+            if (u < 0 || (u & 1)) continue;
+            const int ow = u >> 1;
+            if (ow >= OW) continue;
+            const size_t o = (((size_t)bi * OH + oh) * OW + ow) * C + c0;
+            float g[V];
+            load_vec(gout + o, g);
+            const int code = kh * 3 + kw;
+            if (V == 8) {
+                const uint2 am = *reinterpret_cast<const uint2*>(argmax + o);
+                const uint32_t wds[2] = {am.x, am.y};
+#pragma unroll
+                for (int i = 0; i < V; ++i)
+                    if ((int)((wds[i >> 2] >> (8 * (i & 3))) & 0xffu) == code) acc[i] += g[i];
+            } else {
+                const uint32_t am = *reinterpret_cast<const uint32_t*>(argmax + o);
+#pragma unroll
+                for (int i = 0; i < V; ++i)
+                    if ((int)((am >> (8 * i)) & 0xffu) == code) acc[i] += g[i];
+            }
+        }
+    }
+    store_vec(gin + idx * V, acc);
+}
+
+// out[b,oh,ow,:] = in[b,2oh,2ow,:]   (what a 1x1 stride-2 'same' convolution reads)
+template <typename T>
+__global__ void __launch_bounds__(256) gather_s2_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H,
+                                                        int W, int C, int OH, int OW) {
+    constexpr int V = VecN<T>::N;
+    const int CV = C / V;
+    const long long n = (long long)B * OH * OW * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int ow = (int)(r % OW);
+    r /= OW;
+    const int oh = (int)(r % OH);
+    const int bi = (int)(r / OH);
+    float v[V];
+    load_vec(in + (((size_t)bi * H + 2 * oh) * W + 2 * ow) * C + cv * V, v);
+    store_vec(out + idx * V, v);
+}
+
+int check_pool(const char* who, int dtype, int B, int H, int W, int C) {
+    SPNET_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "%s: bad shape", who);
+    const int V = dtype == SPNET_BF16 ? 8 : 4;
+    SPNET_REQUIRE(C % V == 0, "%s: C=%d must be a multiple of %d", who, C, V);
+    return SPNET_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int spnet_maxpool3s2_add_fwd(const void* z, const float* a, const float* b, const void* res, const float* ra,
+                             const float* rb, void* out, unsigned char* argmax, int dtype, int B, int H, int W,
+                             int C, cudaStream_t stream) {
+    int rc = check_pool("maxpool3s2_add_fwd", dtype, B, H, W, C);
+    if (rc) return rc;
+    SPNET_REQUIRE(z && out, "maxpool3s2_add_fwd: null pointer");
+    SPNET_REQUIRE((a == nullptr) == (b == nullptr) && (ra == nullptr) == (rb == nullptr),
+                  "maxpool3s2_add_fwd: affine parameters come in pairs");
+    const int OH = (H + 1) / 2, OW = (W + 1) / 2;
+    const int V = dtype == SPNET_BF16 ? 8 : 4;
+    const long long n = (long long)B * OH * OW * (C / V);
+    SPNET_DISPATCH_DTYPE(dtype, (maxpool_add_fwd_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(
+                                    reinterpret_cast<const T*>(z), a, b, reinterpret_cast<const T*>(res), ra, rb,
+                                    reinterpret_cast<T*>(out), argmax, B, H, W, C, OH, OW, same_pad_before(H),
+                                    same_pad_before(W))));
+    return spnet_check_launch("maxpool3s2_add_fwd");
+}
+
+int spnet_maxpool3s2_bwd(const void* gout, const unsigned char* argmax, void* gin, int dtype, int B, int H, int W,
+                         int C, cudaStream_t stream) {
+    int rc = check_pool("maxpool3s2_bwd", dtype, B, H, W, C);
+    if (rc) return rc;
+    SPNET_REQUIRE(gout && argmax && gin, "maxpool3s2_bwd: null pointer");
+    const int OH = (H + 1) / 2, OW = (W + 1) / 2;
+    const int V = dtype == SPNET_BF16 ? 8 : 4;
+    const long long n = (long long)B * H * W * (C / V);
+    SPNET_DISPATCH_DTYPE(dtype, (maxpool_bwd_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(
+                                    reinterpret_cast<const T*>(gout), argmax, reinterpret_cast<T*>(gin), B, H, W, C,
+                                    OH, OW, same_pad_before(H), same_pad_before(W))));
+    return spnet_check_launch("maxpool3s2_bwd");
+}
+
+int spnet_gather_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, cudaStream_t stream) {
+    int rc = check_pool("gather_s2", dtype, B, H, W, C);
+    if (rc) return rc;
+    SPNET_REQUIRE(in && out, "gather_s2: null pointer");
+    const int OH = (H + 1) / 2, OW = (W + 1) / 2;
+    const int V = dtype == SPNET_BF16 ? 8 : 4;
+    const long long n = (long long)B * OH * OW * (C / V);
+    SPNET_DISPATCH_DTYPE(dtype, (gather_s2_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(
+                                    reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), B, H, W, C, OH, OW)));
+    return spnet_check_launch("gather_s2");
+}
+
+}  // extern "C"

@@ -1,0 +1,609 @@
+// Small-channel direct convolutions (Cin <= 3: no tensor-core shape exists for them) and
+// the im2col pair for block1_conv2.
+//
+//  * SPNet stem (spnet/models.py:319-340): Conv2D(3,3x3,same,no bias) -> AveragePooling2D(2)
+//    -> BN -> LeakyReLU(0.1) -> Conv2D(3) -> BN -> LeakyReLU(0.1) -> Conv2D(3) -> BN
+//    -> Add(AveragePooling2D(2)(input)) -> Dropout(0.1).
+//    conv+avgpool is evaluated as the equivalent 4x4 stride-2 convolution (pad 1) whose
+//    kernel is the 2x2 box average of the shifted 3x3 kernel, at a quarter of the work.
+//  * keras.applications.Xception block1_conv1 (3x3, stride 2, valid, 3->32).
+//  * block1_conv2 (3x3, valid, 32->64) as im2col + GEMM (gemm_tc.cu / gemm_simt.cu).
+//
+// All kernels are HBM/latency-bound (<1 % of the model's FLOPs); one thread per pixel,
+// weights in shared memory, BatchNorm statistics reduced in the epilogue.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float apply_act(float y, int act) {
+    if (act == 1) return fmaxf(y, 0.f);
+    if (act == 2) return y > 0.f ? y : 0.1f * y;
+    return y;
+}
+
+// out[b,oh,ow,:] = sum_{kh,kw,ci} act(in_a*in+in_b)[b, oh*S-pt+kh, ow*S-pl+kw, ci] * w[kh,kw,ci,:]
+// POOL_SKIP (stem conv1 only, KS=4,S=2,CIN=1): also writes skip = mean of the 2x2 centre taps.
+template <typename TI, typename TO, int CIN, int COUT, int KS, int S, bool POOL_SKIP>
+__global__ void __launch_bounds__(256) conv_direct_fwd_kernel(const TI* __restrict__ in, const float* __restrict__ w,
+                                                              const float* __restrict__ in_a,
+                                                              const float* __restrict__ in_b, int act,
+                                                              TO* __restrict__ out, TO* __restrict__ skip,
+                                                              double* __restrict__ stats, int B, int H, int W,
+                                                              int OH, int OW, int pt, int pl) {
+    __shared__ float ws[KS * KS * CIN * COUT];
+    __shared__ float sred[2][COUT];
+    __shared__ float sab[2][CIN];
+    for (int i = threadIdx.x; i < KS * KS * CIN * COUT; i += blockDim.x) ws[i] = w[i];
+    if (threadIdx.x < COUT) { sred[0][threadIdx.x] = 0.f; sred[1][threadIdx.x] = 0.f; }
+    if (threadIdx.x < CIN) {
+        sab[0][threadIdx.x] = in_a ? in_a[threadIdx.x] : 1.f;
+        sab[1][threadIdx.x] = in_a ? in_b[threadIdx.x] : 0.f;
+    }
+    __syncthreads();
+    const long long n = (long long)B * OH * OW;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = idx < n;
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+    if (valid) {
+        const int ow = (int)(idx % OW);
+        const int oh = (int)((idx / OW) % OH);
+        const int b = (int)(idx / ((long long)OW * OH));
+        float centre = 0.f;
+#pragma unroll
+        for (int kh = 0; kh < KS; ++kh) {
+            const int ih = oh * S - pt + kh;
+            if (ih < 0 || ih >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < KS; ++kw) {
+                const int iw = ow * S - pl + kw;
+                if (iw < 0 || iw >= W) continue;
+                const TI* px = in + (((size_t)b * H + ih) * W + iw) * CIN;
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) {
+                    float v = to_f32(px[ci]);
+                    if (in_a) v = apply_act(fmaf(v, sab[0][ci], sab[1][ci]), act);
+                    if (POOL_SKIP && (kh == 1 || kh == 2) && (kw == 1 || kw == 2)) centre += v;
+                    const float* wr = &ws[((kh * KS + kw) * CIN + ci) * COUT];
+#pragma unroll
+                    for (int co = 0; co < COUT; ++co) acc[co] = fmaf(v, wr[co], acc[co]);
+                }
+            }
+        }
+        TO* o = out + idx * COUT;
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+            o[co] = from_f32<TO>(acc[co]);
+            acc[co] = round_to<TO>(acc[co]);
+        }
+        if (POOL_SKIP) skip[idx] = from_f32<TO>(0.25f * centre);
+    }
+    if (stats) {
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+            const float s = warp_sum(acc[co]);
+            const float q = warp_sum(acc[co] * acc[co]);
+            if ((threadIdx.x & 31) == 0) { atomicAdd(&sred[0][co], s); atomicAdd(&sred[1][co], q); }
+        }
+        __syncthreads();
+        if (threadIdx.x < COUT) {
+            atomicAdd(stats + threadIdx.x, (double)sred[0][threadIdx.x]);
+            atomicAdd(stats + COUT + threadIdx.x, (double)sred[1][threadIdx.x]);
+        }
+    }
+}
+
+// dw[kh,kw,ci,co] += sum_pixels act(in)[.., ci] * g[b,oh,ow,co]   (small COUT: thread = output pixel)
+template <typename TI, typename TG, int CIN, int COUT, int KS, int S>
+__global__ void __launch_bounds__(256) conv_direct_wgrad_px_kernel(const TI* __restrict__ in,
+                                                                   const float* __restrict__ in_a,
+                                                                   const float* __restrict__ in_b, int act,
+                                                                   const TG* __restrict__ g, float* __restrict__ dw,
+                                                                   int B, int H, int W, int OH, int OW, int pt,
+                                                                   int pl) {
+    constexpr int NW = KS * KS * CIN * COUT;
+    __shared__ float sacc[NW];
+    for (int i = threadIdx.x; i < NW; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    float acc[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) acc[i] = 0.f;
+    float a[CIN], bb[CIN];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) { a[ci] = in_a ? in_a[ci] : 1.f; bb[ci] = in_a ? in_b[ci] : 0.f; }
+    const long long n = (long long)B * OH * OW;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int ow = (int)(idx % OW);
+        const int oh = (int)((idx / OW) % OH);
+        const int b = (int)(idx / ((long long)OW * OH));
+        float gv[COUT];
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) gv[co] = to_f32(g[idx * COUT + co]);
+#pragma unroll
+        for (int kh = 0; kh < KS; ++kh) {
+            const int ih = oh * S - pt + kh;
+            if (ih < 0 || ih >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < KS; ++kw) {
+                const int iw = ow * S - pl + kw;
+                if (iw < 0 || iw >= W) continue;
+                const TI* px = in + (((size_t)b * H + ih) * W + iw) * CIN;
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) {
+                    float v = to_f32(px[ci]);
+                    if (in_a) v = apply_act(fmaf(v, a[ci], bb[ci]), act);
+#pragma unroll
+                    for (int co = 0; co < COUT; ++co)
+                        acc[((kh * KS + kw) * CIN + ci) * COUT + co] =
+                            fmaf(v, gv[co], acc[((kh * KS + kw) * CIN + ci) * COUT + co]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        const float s = warp_sum(acc[i]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[i], s);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NW; i += blockDim.x) atomicAdd(dw + i, sacc[i]);
+}
+
+// COUT == 32: one warp per output pixel, lane = output channel, KS*KS*CIN partial sums per lane.
+template <typename TI, typename TG, int CIN, int KS, int S>
+__global__ void __launch_bounds__(256) conv_direct_wgrad_lane_kernel(const TI* __restrict__ in,
+                                                                     const float* __restrict__ in_a,
+                                                                     const float* __restrict__ in_b, int act,
+                                                                     const TG* __restrict__ g,
+                                                                     float* __restrict__ dw, int B, int H, int W,
+                                                                     int OH, int OW, int pt, int pl) {
+    constexpr int NT = KS * KS * CIN;
+    __shared__ float sacc[NT * 32];
+    for (int i = threadIdx.x; i < NT * 32; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    float acc[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) acc[i] = 0.f;
+    float a[CIN], bb[CIN];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) { a[ci] = in_a ? in_a[ci] : 1.f; bb[ci] = in_a ? in_b[ci] : 0.f; }
+    const long long n = (long long)B * OH * OW;
+    for (long long idx = warp; idx < n; idx += nwarps) {
+        const int ow = (int)(idx % OW);
+        const int oh = (int)((idx / OW) % OH);
+        const int b = (int)(idx / ((long long)OW * OH));
+        const float gv = to_f32(g[idx * 32 + lane]);
+#pragma unroll
+        for (int kh = 0; kh < KS; ++kh) {
+            const int ih = oh * S - pt + kh;
+            if (ih < 0 || ih >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < KS; ++kw) {
+                const int iw = ow * S - pl + kw;
+                if (iw < 0 || iw >= W) continue;
+                const TI* px = in + (((size_t)b * H + ih) * W + iw) * CIN;
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) {
+                    float v = to_f32(px[ci]);
+                    if (in_a) v = apply_act(fmaf(v, a[ci], bb[ci]), act);
+                    acc[(kh * KS + kw) * CIN + ci] = fmaf(v, gv, acc[(kh * KS + kw) * CIN + ci]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NT; ++i) atomicAdd(&sacc[i * 32 + lane], acc[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < NT * 32; i += blockDim.x) atomicAdd(dw + i, sacc[i]);
+}
+
+// gin[b,ih,iw,ci] = act'(pre) * sum_{kh,kw,co} g[b,oh,ow,co] * w[kh,kw,ci,co],
+//   oh*S - pt + kh = ih;  pre = mask_a*mask_z + mask_b (mask_z nullable = no activation).
+template <typename TG, typename TO, int CIN, int COUT, int KS, int S>
+__global__ void __launch_bounds__(256) conv_direct_dgrad_kernel(const TG* __restrict__ g, const float* __restrict__ w,
+                                                                const TO* __restrict__ mask_z,
+                                                                const float* __restrict__ mask_a,
+                                                                const float* __restrict__ mask_b, int act,
+                                                                TO* __restrict__ gin, int B, int H, int W, int OH,
+                                                                int OW, int pt, int pl) {
+    __shared__ float ws[KS * KS * CIN * COUT];
+    for (int i = threadIdx.x; i < KS * KS * CIN * COUT; i += blockDim.x) ws[i] = w[i];
+    __syncthreads();
+    const long long n = (long long)B * H * W;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int iw = (int)(idx % W);
+    const int ih = (int)((idx / W) % H);
+    const int b = (int)(idx / ((long long)W * H));
+    float acc[CIN];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) acc[ci] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < KS; ++kh) {
+        const int t = ih + pt - kh;
+        if (t < 0 || t % S != 0) continue;
+        const int oh = t / S;
+        if (oh >= OH) continue;
+#pragma unroll
+        for (int kw = 0; kw < KS; ++kw) {
+            const int u = iw + pl - kw;
+            if (u < 0 || u % S != 0) continue;
+            const int ow = u / S;
+            if (ow >= OW) continue;
+            const TG* gp = g + (((size_t)b * OH + oh) * OW + ow) * COUT;
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                const float gv = to_f32(gp[co]);
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci)
+                    acc[ci] = fmaf(gv, ws[((kh * KS + kw) * CIN + ci) * COUT + co], acc[ci]);
+            }
+        }
+    }
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+        float v = acc[ci];
+        if (mask_z) {
+            const float pre = fmaf(to_f32(mask_z[idx * CIN + ci]), mask_a[ci], mask_b[ci]);
+            if (!(pre > 0.f)) v = (act == 2) ? 0.1f * v : (act == 1 ? 0.f : v);
+        }
+        gin[idx * CIN + ci] = from_f32<TO>(v);
+    }
+}
+
+// ---- stem kernel folding: K4 = 2x2 box average of shifted K3; and its adjoint ----
+__global__ void stem_k3_to_k4_kernel(const float* __restrict__ k3, float* __restrict__ k4, int cout) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 16*cout
+    if (i >= 16 * cout) return;
+    const int co = i % cout, kw = (i / cout) % 4, kh = i / (4 * cout);
+    float s = 0.f;
+    for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+            const int a = kh - dy, b = kw - dx;
+            if (a >= 0 && a < 3 && b >= 0 && b < 3) s += k3[(a * 3 + b) * cout + co];
+        }
+    k4[i] = 0.25f * s;
+}
+__global__ void stem_k4grad_to_k3grad_kernel(const float* __restrict__ g4, float* __restrict__ g3, int cout) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 9*cout
+    if (i >= 9 * cout) return;
+    const int co = i % cout, b = (i / cout) % 3, a = i / (3 * cout);
+    float s = 0.f;
+    for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) s += g4[((a + dy) * 4 + (b + dx)) * cout + co];
+    g3[i] += 0.25f * s;
+}
+
+// ---- stem output: d = dropout(a*c3 + b + skip)  (C = 3, skip has 1 channel) ----
+__device__ __forceinline__ uint32_t mix32(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return (uint32_t)x;
+}
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, long long elem, float rate) {
+    const uint32_t r = mix32(seed * 0x9E3779B97F4A7C15ULL + (unsigned long long)elem);
+    return (float)(r >> 8) * (1.0f / 16777216.0f) >= rate;
+}
+
+template <typename T>
+__global__ void stem_out_fwd_kernel(const T* __restrict__ c3, const float* __restrict__ a,
+                                    const float* __restrict__ b, const T* __restrict__ skip, T* __restrict__ out,
+                                    long long pixels, float rate, const unsigned long long* __restrict__ seed) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pixels) return;
+    const float s = to_f32(skip[p]);
+    const unsigned long long sd = seed ? *seed : 0ULL;
+    const float scale = 1.0f / (1.0f - rate);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float y = fmaf(to_f32(c3[p * 3 + c]), a[c], b[c]) + s;
+        if (seed) y = dropout_keep(sd, p * 3 + c, rate) ? y * scale : 0.f;
+        out[p * 3 + c] = from_f32<T>(y);
+    }
+}
+template <typename T>
+__global__ void stem_out_bwd_kernel(const T* g, T* gout, long long pixels, float rate,
+                                    const unsigned long long* __restrict__ seed) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pixels) return;
+    const unsigned long long sd = seed ? *seed : 0ULL;
+    const float scale = 1.0f / (1.0f - rate);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float v = to_f32(g[p * 3 + c]);
+        if (seed) v = dropout_keep(sd, p * 3 + c, rate) ? v * scale : 0.f;
+        gout[p * 3 + c] = from_f32<T>(v);
+    }
+}
+
+// ---- BatchNorm backward for 3-channel tensors ----
+template <typename T>
+__global__ void __launch_bounds__(256) bn3_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ z,
+                                                             const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd,
+                                                             double* __restrict__ stats, long long pixels) {
+    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < pixels;
+         p += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float gv = to_f32(g[p * 3 + c]);
+            s[c] += gv;
+            s[3 + c] = fmaf(gv, (to_f32(z[p * 3 + c]) - mean[c]) * rstd[c], s[3 + c]);
+        }
+    }
+    __shared__ float red[6];
+    if (threadIdx.x < 6) red[threadIdx.x] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const float v = warp_sum(s[i]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&red[i], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) atomicAdd(stats + threadIdx.x, (double)red[threadIdx.x]);
+}
+template <typename T>
+__global__ void bn3_bwd_dz_kernel(const T* g, const T* __restrict__ z, const float* __restrict__ a,
+                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                  const float* __restrict__ c1, const float* __restrict__ c2, T* out,
+                                  long long pixels) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pixels) return;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float xh = (to_f32(z[p * 3 + c]) - mean[c]) * rstd[c];
+        out[p * 3 + c] = from_f32<T>(a[c] * (to_f32(g[p * 3 + c]) - c1[c] - xh * c2[c]));
+    }
+}
+
+// ---- im2col / col2im for a 3x3 'valid' stride-1 convolution ----
+// col[(b,oh,ow), (kh*3+kw)*C + c] = act(a*in+b)[b, oh+kh, ow+kw, c]
+template <typename T>
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const T* __restrict__ in, const float* __restrict__ a,
+                                                        const float* __restrict__ b, int relu, T* __restrict__ col,
+                                                        int B, int H, int W, int C) {
+    constexpr int V = VecN<T>::N;
+    const int CV = C / V, OH = H - 2, OW = W - 2;
+    const long long n = (long long)B * OH * OW * 9 * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int tap = (int)(r % 9);
+    r /= 9;
+    const int ow = (int)(r % OW);
+    r /= OW;
+    const int oh = (int)(r % OH);
+    const int bi = (int)(r / OH);
+    const int c0 = cv * V;
+    float v[V];
+    load_vec(in + (((size_t)bi * H + oh + tap / 3) * W + ow + tap % 3) * C + c0, v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        float y = v[i];
+        if (a) y = fmaf(y, a[c0 + i], b[c0 + i]);
+        if (relu) y = fmaxf(y, 0.f);
+        v[i] = y;
+    }
+    store_vec(col + idx * V, v);
+}
+// gin[b,ih,iw,c] = relu'(a*z+b) * sum_{kh,kw} gcol[(b,ih-kh,iw-kw), (kh*3+kw)*C + c]
+template <typename T>
+__global__ void __launch_bounds__(256) col2im3x3_kernel(const T* __restrict__ gcol, const T* __restrict__ z,
+                                                        const float* __restrict__ a, const float* __restrict__ b,
+                                                        int relu, T* __restrict__ gin, int B, int H, int W, int C) {
+    constexpr int V = VecN<T>::N;
+    const int CV = C / V, OH = H - 2, OW = W - 2;
+    const long long n = (long long)B * H * W * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int iw = (int)(r % W);
+    r /= W;
+    const int ih = (int)(r % H);
+    const int bi = (int)(r / H);
+    const int c0 = cv * V;
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const int oh = ih - kh;
+        if (oh < 0 || oh >= OH) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int ow = iw - kw;
+            if (ow < 0 || ow >= OW) continue;
+            float v[V];
+            load_vec(gcol + ((((size_t)bi * OH + oh) * OW + ow) * 9 + kh * 3 + kw) * C + c0, v);
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[i] += v[i];
+        }
+    }
+    if (relu) {
+        float zv[V];
+        load_vec(z + idx * V, zv);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float pre = a ? fmaf(zv[i], a[c0 + i], b[c0 + i]) : zv[i];
+            if (!(pre > 0.f)) acc[i] = 0.f;
+        }
+    }
+    store_vec(gin + idx * V, acc);
+}
+
+int persist_grid(long long n) {
+    long long g = (n + 255) / 256;
+    const long long cap = 148LL * 4;
+    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+// which: 0 = stem conv1 folded with AveragePooling2D(2): x0 fp32 [B,H,W,1] -> out [B,H/2,W/2,3], skip [B,H/2,W/2,1]
+//            (w = K4 [4,4,1,3] from spnet_stem_k3_to_k4)
+//        1 = stem conv 3->3, 3x3 same            [B,H,W,3] -> [B,H,W,3]
+//        2 = block1_conv1 3->32, 3x3 s2 valid    [B,H,W,3] -> [B,(H-3)/2+1,(W-3)/2+1,32]
+// in_a/in_b (nullable) + act (0 none, 1 relu, 2 leaky 0.1) transform the input on load.
+// stats (nullable): fp64 [2*Cout] batch-norm accumulators.
+int spnet_conv_small_fwd(int which, const void* in, const float* w, const float* in_a, const float* in_b, int act,
+                         void* out, void* skip, double* stats, int dtype, int B, int H, int W,
+                         cudaStream_t stream) {
+    SPNET_REQUIRE(in && w && out && B > 0 && H > 2 && W > 2, "conv_small_fwd: bad args");
+    SPNET_REQUIRE((in_a == nullptr) == (in_b == nullptr), "conv_small_fwd: affine parameters come in pairs");
+    if (which == 0) {
+        SPNET_REQUIRE(skip, "conv_small_fwd(0): skip output required");
+        const int OH = H / 2, OW = W / 2;
+        const long long n = (long long)B * OH * OW;
+        SPNET_DISPATCH_DTYPE(dtype, (conv_direct_fwd_kernel<float, T, 1, 3, 4, 2, true><<<ceil_div(n, 256), 256, 0, stream>>>(
+                                        reinterpret_cast<const float*>(in), w, in_a, in_b, act, reinterpret_cast<T*>(out),
+                                        reinterpret_cast<T*>(skip), stats, B, H, W, OH, OW, 1, 1)));
+    } else if (which == 1) {
+        const long long n = (long long)B * H * W;
+        SPNET_DISPATCH_DTYPE(dtype, (conv_direct_fwd_kernel<T, T, 3, 3, 3, 1, false><<<ceil_div(n, 256), 256, 0, stream>>>(
+                                        reinterpret_cast<const T*>(in), w, in_a, in_b, act, reinterpret_cast<T*>(out),
+                                        nullptr, stats, B, H, W, H, W, 1, 1)));
+    } else if (which == 2) {
+        const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
+        const long long n = (long long)B * OH * OW;
+        SPNET_DISPATCH_DTYPE(dtype, (conv_direct_fwd_kernel<T, T, 3, 32, 3, 2, false><<<ceil_div(n, 256), 256, 0, stream>>>(
+                                        reinterpret_cast<const T*>(in), w, in_a, in_b, act, reinterpret_cast<T*>(out),
+                                        nullptr, stats, B, H, W, OH, OW, 0, 0)));
+    } else {
+        spnet_set_error("conv_small_fwd: unknown conv id %d", which);
+        return SPNET_ERR_ARG;
+    }
+    return spnet_check_launch("conv_small_fwd");
+}
+
+// dw += weight gradient of the same three convolutions (dw zeroed by the caller).
+// For which == 0, dw is the K4 gradient [4,4,1,3]; fold it with spnet_stem_k4grad_to_k3grad.
+int spnet_conv_small_wgrad(int which, const void* in, const float* in_a, const float* in_b, int act, const void* g,
+                           float* dw, int dtype, int B, int H, int W, cudaStream_t stream) {
+    SPNET_REQUIRE(in && g && dw && B > 0 && H > 2 && W > 2, "conv_small_wgrad: bad args");
+    SPNET_REQUIRE((in_a == nullptr) == (in_b == nullptr), "conv_small_wgrad: affine parameters come in pairs");
+    if (which == 0) {
+        const int OH = H / 2, OW = W / 2;
+        const long long n = (long long)B * OH * OW;
+        SPNET_DISPATCH_DTYPE(dtype, (conv_direct_wgrad_px_kernel<float, T, 1, 3, 4, 2><<<persist_grid(n), 256, 0, stream>>>(
+                                        reinterpret_cast<const float*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g),
+                                        dw, B, H, W, OH, OW, 1, 1)));
+    } else if (which == 1) {
+        const long long n = (long long)B * H * W;
+        SPNET_DISPATCH_DTYPE(dtype, (conv_direct_wgrad_px_kernel<T, T, 3, 3, 3, 1><<<persist_grid(n), 256, 0, stream>>>(
+                                        reinterpret_cast<const T*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g), dw,
+                                        B, H, W, H, W, 1, 1)));
+    } else if (which == 2) {
+        const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
+        const long long n = (long long)B * OH * OW;
+        SPNET_DISPATCH_DTYPE(dtype, (conv_direct_wgrad_lane_kernel<T, T, 3, 3, 2><<<persist_grid(n * 32), 256, 0, stream>>>(
+                                        reinterpret_cast<const T*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g), dw,
+                                        B, H, W, OH, OW, 0, 0)));
+    } else {
+        spnet_set_error("conv_small_wgrad: unknown conv id %d", which);
+        return SPNET_ERR_ARG;
+    }
+    return spnet_check_launch("conv_small_wgrad");
+}
+
+// gin = data gradient (which = 1 or 2; conv 0 reads the network input, which has no gradient),
+// multiplied by act'(mask_a*mask_z+mask_b) when mask_z is given. H, W are the INPUT dims.
+int spnet_conv_small_dgrad(int which, const void* g, const float* w, const void* mask_z, const float* mask_a,
+                           const float* mask_b, int act, void* gin, int dtype, int B, int H, int W,
+                           cudaStream_t stream) {
+    SPNET_REQUIRE(g && w && gin && B > 0 && H > 2 && W > 2, "conv_small_dgrad: bad args");
+    SPNET_REQUIRE(!mask_z || (mask_a && mask_b), "conv_small_dgrad: mask needs its affine");
+    const long long n = (long long)B * H * W;
+    if (which == 1) {
+        SPNET_DISPATCH_DTYPE(dtype, (conv_direct_dgrad_kernel<T, T, 3, 3, 3, 1><<<ceil_div(n, 256), 256, 0, stream>>>(
+                                        reinterpret_cast<const T*>(g), w, reinterpret_cast<const T*>(mask_z), mask_a,
+                                        mask_b, act, reinterpret_cast<T*>(gin), B, H, W, H, W, 1, 1)));
+    } else if (which == 2) {
+        const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
+        SPNET_DISPATCH_DTYPE(dtype, (conv_direct_dgrad_kernel<T, T, 3, 32, 3, 2><<<ceil_div(n, 256), 256, 0, stream>>>(
+                                        reinterpret_cast<const T*>(g), w, reinterpret_cast<const T*>(mask_z), mask_a,
+                                        mask_b, act, reinterpret_cast<T*>(gin), B, H, W, OH, OW, 0, 0)));
+    } else {
+        spnet_set_error("conv_small_dgrad: unknown conv id %d", which);
+        return SPNET_ERR_ARG;
+    }
+    return spnet_check_launch("conv_small_dgrad");
+}
+
+int spnet_stem_k3_to_k4(const float* k3, float* k4, int cout, cudaStream_t stream) {
+    SPNET_REQUIRE(k3 && k4 && cout > 0, "stem_k3_to_k4: bad args");
+    stem_k3_to_k4_kernel<<<ceil_div(16 * cout, 64), 64, 0, stream>>>(k3, k4, cout);
+    return spnet_check_launch("stem_k3_to_k4");
+}
+// g3 += fold(g4)
+int spnet_stem_k4grad_to_k3grad(const float* g4, float* g3, int cout, cudaStream_t stream) {
+    SPNET_REQUIRE(g4 && g3 && cout > 0, "stem_k4grad_to_k3grad: bad args");
+    stem_k4grad_to_k3grad_kernel<<<ceil_div(9 * cout, 64), 64, 0, stream>>>(g4, g3, cout);
+    return spnet_check_launch("stem_k4grad_to_k3grad");
+}
+
+// d = dropout(a*c3 + b + skip);  seed nullable (= inference / rate 0: no dropout)
+int spnet_stem_out_fwd(const void* c3, const float* a, const float* b, const void* skip, void* out, int dtype,
+                       long long pixels, float rate, const unsigned long long* seed, cudaStream_t stream) {
+    SPNET_REQUIRE(c3 && a && b && skip && out && pixels > 0 && rate >= 0.f && rate < 1.f, "stem_out_fwd: bad args");
+    SPNET_DISPATCH_DTYPE(dtype, (stem_out_fwd_kernel<T><<<ceil_div(pixels, 256), 256, 0, stream>>>(
+                                    reinterpret_cast<const T*>(c3), a, b, reinterpret_cast<const T*>(skip),
+                                    reinterpret_cast<T*>(out), pixels, rate, seed)));
+    return spnet_check_launch("stem_out_fwd");
+}
+int spnet_stem_out_bwd(const void* g, void* gout, int dtype, long long pixels, float rate,
+                       const unsigned long long* seed, cudaStream_t stream) {
+    SPNET_REQUIRE(g && gout && pixels > 0 && rate >= 0.f && rate < 1.f, "stem_out_bwd: bad args");
+    SPNET_DISPATCH_DTYPE(dtype, (stem_out_bwd_kernel<T><<<ceil_div(pixels, 256), 256, 0, stream>>>(
+                                    reinterpret_cast<const T*>(g), reinterpret_cast<T*>(gout), pixels, rate, seed)));
+    return spnet_check_launch("stem_out_bwd");
+}
+
+int spnet_bn3_bwd_reduce(const void* g, const void* z, const float* save_mean, const float* save_rstd, double* stats,
+                         int dtype, long long pixels, cudaStream_t stream) {
+    SPNET_REQUIRE(g && z && save_mean && save_rstd && stats && pixels > 0, "bn3_bwd_reduce: bad args");
+    SPNET_DISPATCH_DTYPE(dtype, (bn3_bwd_reduce_kernel<T><<<persist_grid(pixels), 256, 0, stream>>>(
+                                    reinterpret_cast<const T*>(g), reinterpret_cast<const T*>(z), save_mean, save_rstd,
+                                    stats, pixels)));
+    return spnet_check_launch("bn3_bwd_reduce");
+}
+int spnet_bn3_bwd_dz(const void* g, const void* z, const float* a, const float* save_mean, const float* save_rstd,
+                     const float* c1, const float* c2, void* out, int dtype, long long pixels, cudaStream_t stream) {
+    SPNET_REQUIRE(g && z && a && save_mean && save_rstd && c1 && c2 && out && pixels > 0, "bn3_bwd_dz: bad args");
+    SPNET_DISPATCH_DTYPE(dtype, (bn3_bwd_dz_kernel<T><<<ceil_div(pixels, 256), 256, 0, stream>>>(
+                                    reinterpret_cast<const T*>(g), reinterpret_cast<const T*>(z), a, save_mean, save_rstd,
+                                    c1, c2, reinterpret_cast<T*>(out), pixels)));
+    return spnet_check_launch("bn3_bwd_dz");
+}
+
+int spnet_im2col3x3(const void* in, const float* a, const float* b, int relu, void* col, int dtype, int B, int H,
+                    int W, int C, cudaStream_t stream) {
+    SPNET_REQUIRE(in && col && B > 0 && H > 2 && W > 2, "im2col3x3: bad args");
+    const int V = dtype == SPNET_BF16 ? 8 : 4;
+    SPNET_REQUIRE(C % V == 0 && (a == nullptr) == (b == nullptr), "im2col3x3: bad channel count or affine");
+    const long long n = (long long)B * (H - 2) * (W - 2) * 9 * (C / V);
+    SPNET_DISPATCH_DTYPE(dtype, (im2col3x3_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(
+                                    reinterpret_cast<const T*>(in), a, b, relu, reinterpret_cast<T*>(col), B, H, W, C)));
+    return spnet_check_launch("im2col3x3");
+}
+int spnet_col2im3x3(const void* gcol, const void* z, const float* a, const float* b, int relu, void* gin, int dtype,
+                    int B, int H, int W, int C, cudaStream_t stream) {
+    SPNET_REQUIRE(gcol && gin && B > 0 && H > 2 && W > 2, "col2im3x3: bad args");
+    const int V = dtype == SPNET_BF16 ? 8 : 4;
+    SPNET_REQUIRE(C % V == 0 && (a == nullptr) == (b == nullptr) && (!relu || z), "col2im3x3: bad args");
+    const long long n = (long long)B * H * W * (C / V);
+    SPNET_DISPATCH_DTYPE(dtype, (col2im3x3_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(
+                                    reinterpret_cast<const T*>(gcol), reinterpret_cast<const T*>(z), a, b, relu,
+                                    reinterpret_cast<T*>(gin), B, H, W, C)));
+    return spnet_check_launch("col2im3x3");
+}
+
+}  // extern "C"

@@ -1,0 +1,310 @@
+"""Tensor-level wrappers over the C ABI (include/spnet_b200.h).
+
+PyTorch is used only as the owner of device memory and streams: every function here
+forwards raw device pointers and shapes to libspnet_b200.so on the current CUDA stream.
+Nothing in this module computes with torch ops, and nothing falls back to them.
+"""
+import torch
+
+from ._lib import lib
+
+F32, BF16 = 0, 1
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dtype_code(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError("activation tensors must be float32 or bfloat16, got %s" % t.dtype)
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.is_cuda and t.is_contiguous(), "spnet_b200 ops need contiguous CUDA tensors"
+
+
+# ----------------------------------------------------------------------------- loss / head
+def yolo_ellipse_loss(y_true, y_pred, hybrid=False, sel_sigmoid=False, out6=None, grad=None):
+    _chk(y_true, y_pred, out6, grad)
+    B, n = y_pred.shape
+    if out6 is None:
+        out6 = torch.empty(6, device=y_pred.device, dtype=torch.float32)
+    lib().yolo_ellipse_loss(_p(y_true), _p(y_pred), B, n, int(hybrid), int(sel_sigmoid), _p(out6), _p(grad), _s())
+    return out6
+
+
+def selective_sigmoid_fwd(x, start, end, skip, out=None):
+    _chk(x, out)
+    rows, n = x.shape
+    end = n if end is None else (end if end >= 0 else n + end)
+    if out is None:
+        out = torch.empty_like(x)
+    lib().selective_sigmoid_fwd(_p(x), _p(out), rows, n, start, end, skip, _s())
+    return out
+
+
+def selective_sigmoid_bwd(y, dy, start, end, skip, out=None):
+    _chk(y, dy, out)
+    rows, n = y.shape
+    end = n if end is None else (end if end >= 0 else n + end)
+    if out is None:
+        out = torch.empty_like(dy)
+    lib().selective_sigmoid_bwd(_p(y), _p(dy), _p(out), rows, n, start, end, skip, _s())
+    return out
+
+
+def decode_detections(y, means, ranges):
+    _chk(y, means, ranges)
+    n, ncols = y.shape
+    denorm = torch.empty_like(y)
+    ints = torch.empty(n, ncols // 8, 5, device=y.device, dtype=torch.int32)
+    exists = torch.empty(n, ncols // 8, device=y.device, dtype=torch.uint8)
+    lib().decode_detections(_p(y), _p(means), _p(ranges), n, ncols, _p(denorm), _p(ints), _p(exists), _s())
+    return denorm, ints, exists
+
+
+# ----------------------------------------------------------------------------- depthwise
+def dwconv3x3_fwd(x, k, in_a=None, in_b=None, relu=False, out=None):
+    _chk(x, k, in_a, in_b, out)
+    B, H, W, C = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    lib().dwconv3x3_fwd(_p(x), _p(k), _p(in_a), _p(in_b), int(relu), _p(out), dtype_code(x), B, H, W, C, _s())
+    return out
+
+
+def dwconv3x3_dgrad(gout, k, mask_src=None, mask_a=None, mask_b=None, add_src=None, add_strided=None, out=None):
+    _chk(gout, k, mask_src, mask_a, mask_b, add_src, add_strided, out)
+    B, H, W, C = gout.shape
+    if out is None:
+        out = torch.empty_like(gout)
+    lib().dwconv3x3_dgrad(_p(gout), _p(k), _p(out), _p(mask_src), _p(mask_a), _p(mask_b), _p(add_src),
+                          _p(add_strided), dtype_code(gout), B, H, W, C, _s())
+    return out
+
+
+def dwconv3x3_wgrad(x, gout, dk, in_a=None, in_b=None, relu=False):
+    """dk (fp32 [3,3,C]) is accumulated into: zero it first."""
+    _chk(x, gout, dk, in_a, in_b)
+    B, H, W, C = x.shape
+    lib().dwconv3x3_wgrad(_p(x), _p(gout), _p(in_a), _p(in_b), int(relu), _p(dk), dtype_code(x), B, H, W, C, _s())
+    return dk
+
+
+# ----------------------------------------------------------------------------- GEMM
+OUT_T, OUT_F32, OUT_ATOMIC = 0, 1, 2
+
+
+def gemm(A, a_mn, B, b_mn, D, M, N, K, out_mode=OUT_T, splits=1, colstats=None, lda=None, ldb=None, ldd=None):
+    """D[M,N] (op)= A[M,K] @ B[K,N].
+
+    a_mn / b_mn False: operand stored [rows, K] (K contiguous); True: stored [K, rows].
+    bf16 operands run on tcgen05 (gemm_tc.cu), fp32 operands on the exact FFMA kernel.
+    """
+    _chk(A, B, D, colstats)
+    lda = lda if lda is not None else (M if a_mn else K)
+    ldb = ldb if ldb is not None else (N if b_mn else K)
+    ldd = ldd if ldd is not None else N
+    if A.dtype == torch.bfloat16:
+        assert B.dtype == torch.bfloat16
+        lib().gemm_bf16(_p(A), lda, int(a_mn), _p(B), ldb, int(b_mn), _p(D), ldd, out_mode, M, N, K, splits,
+                        _p(colstats), _s())
+    else:
+        assert A.dtype == torch.float32 and B.dtype == torch.float32
+        sa = (1, lda) if a_mn else (lda, 1)
+        sb = (1, ldb) if b_mn else (ldb, 1)
+        lib().gemm_simt(_p(A), sa[0], sa[1], _p(B), sb[0], sb[1], _p(D), ldd, F32, out_mode, M, N, K, splits,
+                        _p(colstats), _s())
+    return D
+
+
+def gemm_simt(A, a_mn, B, b_mn, D, M, N, K, out_mode=OUT_T, splits=1, colstats=None, lda=None, ldb=None, ldd=None):
+    """Same contract as gemm() but always on the CUDA-core kernel (any supported dtype)."""
+    _chk(A, B, D, colstats)
+    lda = lda if lda is not None else (M if a_mn else K)
+    ldb = ldb if ldb is not None else (N if b_mn else K)
+    ldd = ldd if ldd is not None else N
+    sa = (1, lda) if a_mn else (lda, 1)
+    sb = (1, ldb) if b_mn else (ldb, 1)
+    lib().gemm_simt(_p(A), sa[0], sa[1], _p(B), sb[0], sb[1], _p(D), ldd, dtype_code(A), out_mode, M, N, K, splits,
+                    _p(colstats), _s())
+    return D
+
+
+# ----------------------------------------------------------------------------- batch norm
+def bn_finalize(stats, count, gamma, beta, a, b, save_mean, save_rstd, moving_mean=None, moving_var=None,
+                eps=1e-3, momentum=0.99, unbiased=True):
+    C = a.numel()
+    lib().bn_finalize(_p(stats), count, _p(gamma), _p(beta), eps, momentum, int(unbiased), _p(a), _p(b),
+                      _p(save_mean), _p(save_rstd), _p(moving_mean), _p(moving_var), C, _s())
+
+
+def bn_inference_affine(gamma, beta, moving_mean, moving_var, a, b, eps=1e-3):
+    lib().bn_inference_affine(_p(gamma), _p(beta), _p(moving_mean), _p(moving_var), eps, _p(a), _p(b), a.numel(), _s())
+
+
+def bn_apply(z, a, b, act=0, x=None, out=None):
+    _chk(z, a, b, x, out)
+    C = z.shape[-1]
+    rows = z.numel() // C
+    if out is None:
+        out = torch.empty_like(z)
+    lib().bn_apply(_p(z), _p(a), _p(b), act, _p(x), _p(out), dtype_code(z), rows, C, _s())
+    return out
+
+
+def bn_bwd_reduce(g, z, save_mean, save_rstd, stats, relu_a=None, relu_b=None, act=1):
+    _chk(g, z, stats)
+    C = z.shape[-1]
+    rows = z.numel() // C
+    lib().bn_bwd_reduce(_p(g), _p(z), _p(save_mean), _p(save_rstd), _p(relu_a), _p(relu_b), act, _p(stats),
+                        dtype_code(z), rows, C, _s())
+
+
+def bn_bwd_finalize(stats, count, dgamma, dbeta, c1, c2):
+    lib().bn_bwd_finalize(_p(stats), count, _p(dgamma), _p(dbeta), _p(c1), _p(c2), c1.numel(), _s())
+
+
+def bn_bwd_dz(g, z, a, save_mean, save_rstd, c1, c2, out=None):
+    _chk(g, z, out)
+    C = z.shape[-1]
+    rows = z.numel() // C
+    if out is None:
+        out = torch.empty_like(g)
+    lib().bn_bwd_dz(_p(g), _p(z), _p(a), _p(save_mean), _p(save_rstd), _p(c1), _p(c2), _p(out), dtype_code(z), rows,
+                    C, _s())
+    return out
+
+
+# ----------------------------------------------------------------------------- pooling
+def maxpool3s2_add_fwd(z, a=None, b=None, res=None, ra=None, rb=None, out=None, argmax=None):
+    _chk(z, res, out, argmax)
+    B, H, W, C = z.shape
+    if out is None:
+        out = torch.empty(B, (H + 1) // 2, (W + 1) // 2, C, device=z.device, dtype=z.dtype)
+    lib().maxpool3s2_add_fwd(_p(z), _p(a), _p(b), _p(res), _p(ra), _p(rb), _p(out), _p(argmax), dtype_code(z), B, H,
+                             W, C, _s())
+    return out
+
+
+def maxpool3s2_bwd(gout, argmax, H, W, out=None):
+    _chk(gout, argmax, out)
+    B, OH, OW, C = gout.shape
+    if out is None:
+        out = torch.empty(B, H, W, C, device=gout.device, dtype=gout.dtype)
+    lib().maxpool3s2_bwd(_p(gout), _p(argmax), _p(out), dtype_code(gout), B, H, W, C, _s())
+    return out
+
+
+def gather_s2(x, out=None):
+    _chk(x, out)
+    B, H, W, C = x.shape
+    if out is None:
+        out = torch.empty(B, (H + 1) // 2, (W + 1) // 2, C, device=x.device, dtype=x.dtype)
+    lib().gather_s2(_p(x), _p(out), dtype_code(x), B, H, W, C, _s())
+    return out
+
+
+# ----------------------------------------------------------------------------- stem / block1
+def conv_small_fwd(which, x, w, out, skip=None, in_a=None, in_b=None, act=0, stats=None):
+    _chk(x, w, out, skip, stats)
+    B, H, W = x.shape[0], x.shape[1], x.shape[2]
+    lib().conv_small_fwd(which, _p(x), _p(w), _p(in_a), _p(in_b), act, _p(out), _p(skip), _p(stats), dtype_code(out),
+                         B, H, W, _s())
+    return out
+
+
+def conv_small_wgrad(which, x, g, dw, in_a=None, in_b=None, act=0):
+    _chk(x, g, dw)
+    B, H, W = x.shape[0], x.shape[1], x.shape[2]
+    lib().conv_small_wgrad(which, _p(x), _p(in_a), _p(in_b), act, _p(g), _p(dw), dtype_code(g), B, H, W, _s())
+    return dw
+
+
+def conv_small_dgrad(which, g, w, gin, mask_z=None, mask_a=None, mask_b=None, act=0):
+    _chk(g, w, gin, mask_z)
+    B, H, W = gin.shape[0], gin.shape[1], gin.shape[2]
+    lib().conv_small_dgrad(which, _p(g), _p(w), _p(mask_z), _p(mask_a), _p(mask_b), act, _p(gin), dtype_code(g), B, H,
+                           W, _s())
+    return gin
+
+
+def stem_k3_to_k4(k3, k4):
+    lib().stem_k3_to_k4(_p(k3), _p(k4), k3.shape[-1], _s())
+
+
+def stem_k4grad_to_k3grad(g4, g3):
+    lib().stem_k4grad_to_k3grad(_p(g4), _p(g3), g3.shape[-1], _s())
+
+
+def stem_out_fwd(c3, a, b, skip, out, rate=0.0, seed=None):
+    lib().stem_out_fwd(_p(c3), _p(a), _p(b), _p(skip), _p(out), dtype_code(c3), c3.numel() // 3, rate, _p(seed), _s())
+    return out
+
+
+def stem_out_bwd(g, out, rate=0.0, seed=None):
+    lib().stem_out_bwd(_p(g), _p(out), dtype_code(g), g.numel() // 3, rate, _p(seed), _s())
+    return out
+
+
+def bn3_bwd_reduce(g, z, save_mean, save_rstd, stats):
+    lib().bn3_bwd_reduce(_p(g), _p(z), _p(save_mean), _p(save_rstd), _p(stats), dtype_code(z), z.numel() // 3, _s())
+
+
+def bn3_bwd_dz(g, z, a, save_mean, save_rstd, c1, c2, out):
+    lib().bn3_bwd_dz(_p(g), _p(z), _p(a), _p(save_mean), _p(save_rstd), _p(c1), _p(c2), _p(out), dtype_code(z),
+                     z.numel() // 3, _s())
+    return out
+
+
+def im2col3x3(x, col, a=None, b=None, relu=False):
+    _chk(x, col)
+    B, H, W, C = x.shape
+    lib().im2col3x3(_p(x), _p(a), _p(b), int(relu), _p(col), dtype_code(x), B, H, W, C, _s())
+    return col
+
+
+def col2im3x3(gcol, gin, z=None, a=None, b=None, relu=False):
+    _chk(gcol, gin, z)
+    B, H, W, C = gin.shape
+    lib().col2im3x3(_p(gcol), _p(z), _p(a), _p(b), int(relu), _p(gin), dtype_code(gin), B, H, W, C, _s())
+    return gin
+
+
+# ----------------------------------------------------------------------------- optimiser
+def adam_keras_step(p, g, m, v, lr_t_dev, n_l2=0, l2=1e-4, beta1=0.9, beta2=0.999, eps=1e-7, grad_scale=1.0,
+                    p_bf16=None):
+    lib().adam_keras_step(_p(p), _p(g), _p(m), _p(v), p.numel(), n_l2, l2, _p(lr_t_dev), beta1, beta2, eps,
+                          grad_scale, _p(p_bf16), _s())
+
+
+def sumsq(p, n, scale, out):
+    lib().sumsq(_p(p), n, scale, _p(out), _s())
+
+
+def cast_f32_to_bf16(src, dst):
+    lib().cast_f32_to_bf16(_p(src), _p(dst), src.numel(), _s())
+
+
+def cast_bf16_to_f32(src, dst):
+    lib().cast_bf16_to_f32(_p(src), _p(dst), src.numel(), _s())
+
+
+def bias_fill(bias, out):
+    rows, cols = out.shape
+    lib().bias_fill(_p(bias), _p(out), rows, cols, _s())
+
+
+def colsum(g, out):
+    rows, cols = g.shape
+    lib().colsum(_p(g), _p(out), rows, cols, _s())
