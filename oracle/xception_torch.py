@@ -1,0 +1,322 @@
+"""ORACLE — test infrastructure only (never imported by the product path).
+
+CPU restatement (PyTorch fp32 / fp64, autograd for the backward pass) of the network the
+reference builds in spnet/models.py:302-424 (create_model_functional) with cf.basemodel =
+'Xception' (spnet/config.py:52), its loss (custom_loss, :564-589), the L2 regulariser of
+add_regularization (:47-71) and the Keras-2.1.3 Adam step compiled at :494-502.
+
+The backbone is third-party: keras.applications.xception.Xception @ Keras 2.1.3
+(requirements.txt:3) with TF 1.14 semantics (requirements.txt:7); that source is NOT in the
+reference tree, so it is restated here from its published architecture:
+TF 'SAME' asymmetric padding, BatchNormalization(eps=1e-3, momentum=0.99), separable conv =
+depthwise 3x3 then pointwise 1x1 with nothing in between, pre-activation ReLU.
+
+PARITY UNPINNED for the network numerics: TensorFlow/Keras cannot run in this image and the
+reference has no golden activations. What IS pinned (tests/test_oracle_goldens.py): the
+parameter totals 50,353,481 / 50,298,935 / 54,546, the 144-layer count, the stem output
+(165,165,3) and backbone output (5,5,2048) printed in the reference's run logs
+(paper/run_logs/log_DatasetA_*.txt:94-101) and the list of the 10 L2-regularised kernels (:98).
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-3
+BN_MOMENTUM = 0.99
+L2 = 1e-4
+
+# (name, kind, shape-fn) in Keras creation order -----------------------------------------------
+
+
+def xception_spnet_spec(H, W, n_out=576):
+    """Ordered list of (keras_layer_name, weight_name, shape, trainable, l2_regularised)."""
+    spec = []
+
+    def conv(name, kh, kw, cin, cout, reg=True):
+        spec.append((name, "kernel", (kh, kw, cin, cout), True, reg))
+
+    def bn(name, c):
+        spec.append((name, "gamma", (c,), True, False))
+        spec.append((name, "beta", (c,), True, False))
+        spec.append((name, "moving_mean", (c,), False, False))
+        spec.append((name, "moving_variance", (c,), False, False))
+
+    def sep(name, cin, cout):
+        spec.append((name, "depthwise_kernel", (3, 3, cin, 1), True, False))
+        spec.append((name, "pointwise_kernel", (1, 1, cin, cout), True, False))
+
+    # stem (spnet/models.py:321-336)
+    conv("conv2d_1", 3, 3, 1, 3)
+    bn("batch_normalization_1", 3)
+    conv("conv2d_2", 3, 3, 3, 3)
+    bn("batch_normalization_2", 3)
+    conv("conv2d_3", 3, 3, 3, 3)
+    bn("batch_normalization_3", 3)
+    # Xception
+    conv("block1_conv1", 3, 3, 3, 32)
+    bn("block1_conv1_bn", 32)
+    conv("block1_conv2", 3, 3, 32, 64)
+    bn("block1_conv2_bn", 64)
+    nres = 4
+    cin = 64
+    for blk, c in ((2, 128), (3, 256), (4, 728)):
+        conv("conv2d_%d" % nres, 1, 1, cin, c)
+        bn("batch_normalization_%d" % nres, c)
+        nres += 1
+        sep("block%d_sepconv1" % blk, cin, c)
+        bn("block%d_sepconv1_bn" % blk, c)
+        sep("block%d_sepconv2" % blk, c, c)
+        bn("block%d_sepconv2_bn" % blk, c)
+        cin = c
+    for blk in range(5, 13):
+        for j in (1, 2, 3):
+            sep("block%d_sepconv%d" % (blk, j), 728, 728)
+            bn("block%d_sepconv%d_bn" % (blk, j), 728)
+    conv("conv2d_7", 1, 1, 728, 1024)
+    bn("batch_normalization_7", 1024)
+    sep("block13_sepconv1", 728, 728)
+    bn("block13_sepconv1_bn", 728)
+    sep("block13_sepconv2", 728, 1024)
+    bn("block13_sepconv2_bn", 1024)
+    sep("block14_sepconv1", 1024, 1536)
+    bn("block14_sepconv1_bn", 1536)
+    sep("block14_sepconv2", 1536, 2048)
+    bn("block14_sepconv2_bn", 2048)
+    fh, fw = feature_hw(H, W)
+    spec.append(("FinalOutput", "kernel", (fh * fw * 2048, n_out), True, True))
+    spec.append(("FinalOutput", "bias", (n_out,), True, False))
+    return spec
+
+
+def feature_hw(H, W):
+    """Spatial size after the stem (avgpool 2) and Xception (valid s2, valid, 4x same s2)."""
+    def walk(n):
+        n = n // 2              # AveragePooling2D(2), 'valid'
+        n = (n - 3) // 2 + 1    # block1_conv1 3x3 s2 valid
+        n = n - 2               # block1_conv2 3x3 valid
+        for _ in range(4):      # blocks 2,3,4,13: 'same' stride 2
+            n = (n + 1) // 2
+        return n
+    return walk(H), walk(W)
+
+
+def count_params(spec):
+    tr = sum(int(np.prod(s)) for _, _, s, t, _ in spec if t)
+    nt = sum(int(np.prod(s)) for _, _, s, t, _ in spec if not t)
+    return tr + nt, tr, nt
+
+
+def keras_layer_count(spec_unused=None):
+    """Layers of `base_model` as Keras counts them (log line 95: 144 = 1 Input + 12 stem
+    layers + 131 Xception layers after its input)."""
+    stem = 12   # conv, avgpool, bn, leaky, conv, bn, leaky, conv, bn, avgpool(inputs), add, dropout
+    xc = 0
+    xc += 6                      # block1: conv,bn,act,conv,bn,act
+    xc += 3 * (2 + 8)            # blocks 2-4: residual conv+bn (2) + act sep bn act sep bn pool add
+    xc -= 1                      # block2 has no leading activation
+    xc += 8 * 10                 # blocks 5-12: 3x(act,sep,bn) + add
+    xc += 2 + 8                  # block13: residual conv+bn + act sep bn act sep bn pool add
+    xc += 6                      # block14: sep bn act sep bn act
+    return 1 + stem + xc
+
+
+def init_weights(spec, seed=1):
+    """Keras default initialisers: glorot_uniform kernels (fan computed on the Keras kernel
+    shape, receptive field included; depthwise: fan_in = kh*kw*cin, fan_out = kh*kw*1 ... Keras
+    uses shape[-2], shape[-1] times the receptive field), zero bias, BN gamma 1 / beta 0 /
+    mean 0 / var 1."""
+    rng = np.random.default_rng(seed)
+    w = OrderedDict()
+    for layer, wname, shape, _, _ in spec:
+        key = layer + "/" + wname
+        if wname in ("kernel", "depthwise_kernel", "pointwise_kernel"):
+            if len(shape) == 2:
+                fan_in, fan_out = shape
+            else:
+                rf = shape[0] * shape[1]
+                fan_in, fan_out = shape[2] * rf, shape[3] * rf
+            lim = math.sqrt(6.0 / (fan_in + fan_out))
+            w[key] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+        elif wname in ("gamma", "moving_variance"):
+            w[key] = np.ones(shape, np.float32)
+        else:
+            w[key] = np.zeros(shape, np.float32)
+    return w
+
+
+# ---- functional pieces --------------------------------------------------------------------------
+
+def same_pads(n, k, s):
+    out = -(-n // s)
+    tot = max((out - 1) * s + k - n, 0)
+    return tot // 2, tot - tot // 2
+
+
+def conv2d_tf(x, kernel, stride=1, padding="valid", groups=1):
+    """x NCHW; kernel in Keras layout (kh,kw,cin,cout) (depthwise: (kh,kw,c,1))."""
+    kh, kw = kernel.shape[0], kernel.shape[1]
+    if groups == 1:
+        w = kernel.permute(3, 2, 0, 1)
+    else:
+        w = kernel.permute(2, 3, 0, 1)  # (c,1,kh,kw)
+    if padding == "same":
+        pt, pb = same_pads(x.shape[2], kh, stride)
+        pl, pr = same_pads(x.shape[3], kw, stride)
+        x = F.pad(x, (pl, pr, pt, pb))
+    return F.conv2d(x, w, stride=stride, groups=groups)
+
+
+def maxpool3s2_same(x):
+    pt, pb = same_pads(x.shape[2], 3, 2)
+    pl, pr = same_pads(x.shape[3], 3, 2)
+    return F.max_pool2d(F.pad(x, (pl, pr, pt, pb), value=float("-inf")), 3, 2)
+
+
+class OracleSPNet:
+    """Holds the weights as torch leaves; forward() follows the Keras graph layer by layer."""
+
+    def __init__(self, weights, H, W, n_out=576, dtype=torch.float32, unbiased_moving_var=True):
+        self.H, self.W, self.n_out, self.dtype = H, W, n_out, dtype
+        self.spec = xception_spnet_spec(H, W, n_out)
+        self.p = OrderedDict()
+        for layer, wname, shape, trainable, _ in self.spec:
+            key = layer + "/" + wname
+            t = torch.tensor(np.asarray(weights[key]), dtype=dtype)
+            assert tuple(t.shape) == tuple(shape), (key, t.shape, shape)
+            t.requires_grad_(trainable)
+            self.p[key] = t
+        self.unbiased = unbiased_moving_var
+        self.trainable = [l + "/" + w for l, w, _, t, _ in self.spec if t]
+        self.l2_keys = [l + "/" + w for l, w, _, t, r in self.spec if r]
+        self.m = {k: torch.zeros_like(self.p[k]) for k in self.trainable}
+        self.v = {k: torch.zeros_like(self.p[k]) for k in self.trainable}
+        self.t = 0
+        self.taps = {}
+
+    # -- layers
+    def bn(self, x, name, training):
+        g, b = self.p[name + "/gamma"], self.p[name + "/beta"]
+        mm, mv = self.p[name + "/moving_mean"], self.p[name + "/moving_variance"]
+        if training:
+            mean = x.mean((0, 2, 3))
+            var = x.var((0, 2, 3), unbiased=False)
+            n = x.numel() // x.shape[1]
+            with torch.no_grad():
+                uv = var * n / max(n - 1, 1) if self.unbiased else var
+                mm.mul_(BN_MOMENTUM).add_((1 - BN_MOMENTUM) * mean)
+                mv.mul_(BN_MOMENTUM).add_((1 - BN_MOMENTUM) * uv)
+        else:
+            mean, var = mm, mv
+        s = g / torch.sqrt(var + BN_EPS)
+        return x * s[None, :, None, None] + (b - mean * s)[None, :, None, None]
+
+    def sep(self, x, name):
+        x = conv2d_tf(x, self.p[name + "/depthwise_kernel"], 1, "same", groups=x.shape[1])
+        return conv2d_tf(x, self.p[name + "/pointwise_kernel"], 1, "valid")
+
+    def forward(self, x_nhwc, training=False, dropout_mask=None, taps=False):
+        """x_nhwc: (B,H,W,1) array. dropout_mask: optional (B,H/2,W/2,3) array of 0/1 keep flags
+        (training only; None = no dropout, i.e. rate 0). Returns y (B, n_out)."""
+        p = self.p
+        x0 = torch.as_tensor(np.asarray(x_nhwc), dtype=self.dtype).permute(0, 3, 1, 2)
+        tp = self.taps = {}
+        x = conv2d_tf(x0, p["conv2d_1/kernel"], 1, "same")
+        x = F.avg_pool2d(x, 2)
+        x = F.leaky_relu(self.bn(x, "batch_normalization_1", training), 0.1)
+        x = conv2d_tf(x, p["conv2d_2/kernel"], 1, "same")
+        x = F.leaky_relu(self.bn(x, "batch_normalization_2", training), 0.1)
+        x = conv2d_tf(x, p["conv2d_3/kernel"], 1, "same")
+        x = self.bn(x, "batch_normalization_3", training) + F.avg_pool2d(x0, 2)
+        if training and dropout_mask is not None:
+            m = torch.as_tensor(np.asarray(dropout_mask), dtype=self.dtype).permute(0, 3, 1, 2)
+            x = x * m / 0.9
+        if taps:
+            tp["stem"] = x
+        # block 1
+        x = torch.relu(self.bn(conv2d_tf(x, p["block1_conv1/kernel"], 2, "valid"), "block1_conv1_bn", training))
+        x = torch.relu(self.bn(conv2d_tf(x, p["block1_conv2/kernel"], 1, "valid"), "block1_conv2_bn", training))
+        if taps:
+            tp["block1"] = x
+        nres = 4
+        for blk in (2, 3, 4):
+            res = self.bn(conv2d_tf(x, p["conv2d_%d/kernel" % nres], 2, "same"), "batch_normalization_%d" % nres, training)
+            nres += 1
+            if blk != 2:
+                x = torch.relu(x)
+            x = self.bn(self.sep(x, "block%d_sepconv1" % blk), "block%d_sepconv1_bn" % blk, training)
+            x = torch.relu(x)
+            x = self.bn(self.sep(x, "block%d_sepconv2" % blk), "block%d_sepconv2_bn" % blk, training)
+            x = maxpool3s2_same(x) + res
+            if taps:
+                tp["block%d" % blk] = x
+        for blk in range(5, 13):
+            r = x
+            for j in (1, 2, 3):
+                x = torch.relu(x)
+                x = self.bn(self.sep(x, "block%d_sepconv%d" % (blk, j)), "block%d_sepconv%d_bn" % (blk, j), training)
+            x = x + r
+            if taps:
+                tp["block%d" % blk] = x
+        res = self.bn(conv2d_tf(x, p["conv2d_7/kernel"], 2, "same"), "batch_normalization_7", training)
+        x = torch.relu(x)
+        x = self.bn(self.sep(x, "block13_sepconv1"), "block13_sepconv1_bn", training)
+        x = torch.relu(x)
+        x = self.bn(self.sep(x, "block13_sepconv2"), "block13_sepconv2_bn", training)
+        x = maxpool3s2_same(x) + res
+        if taps:
+            tp["block13"] = x
+        x = torch.relu(self.bn(self.sep(x, "block14_sepconv1"), "block14_sepconv1_bn", training))
+        x = torch.relu(self.bn(self.sep(x, "block14_sepconv2"), "block14_sepconv2_bn", training))
+        if taps:
+            tp["block14"] = x
+        flat = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)  # Keras Flatten of NHWC
+        return flat @ p["FinalOutput/kernel"] + p["FinalOutput/bias"]
+
+    # -- loss (custom_loss, spnet/models.py:564-589) + L2 (:47-71)
+    @staticmethod
+    def custom_loss(y_true, y_pred, loss_type="same"):
+        v = 8
+        sq = (y_true - y_pred) ** 2
+        pobj = 1 - y_true[:, 6::v]
+        if loss_type == "same":
+            loss = 0.3 * sq[:, 6::v].sum(-1)
+        else:
+            t, z = y_true[:, 6::v], y_pred[:, 6::v]
+            loss = 0.3 * (torch.clamp(z, min=0) - z * t + torch.log1p(torch.exp(-z.abs()))).sum(-1)
+        loss = loss + 2.0 * ((pobj * sq[:, 0::v]).sum(-1) + (pobj * sq[:, 1::v]).sum(-1))
+        loss = loss + 1.0 * ((pobj * sq[:, 2::v]).sum(-1) + (pobj * sq[:, 3::v]).sum(-1))
+        d2 = (y_true[:, 2::v] - y_true[:, 3::v]) ** 2
+        loss = loss + 3.0 * ((pobj * sq[:, 4::v] * d2).sum(-1) + (pobj * sq[:, 5::v] * d2).sum(-1))
+        loss = loss + 5.0 * (pobj * sq[:, 7::v]).sum(-1)
+        return (loss / y_pred.shape[-1]).mean()
+
+    def l2_term(self):
+        return sum(L2 * (self.p[k] ** 2).sum() for k in self.l2_keys)
+
+    def loss_and_grads(self, x, y_true, loss_type="same", dropout_mask=None, with_l2=True):
+        for k in self.trainable:
+            self.p[k].grad = None
+        y = self.forward(x, training=True, dropout_mask=dropout_mask)
+        yt = torch.as_tensor(np.asarray(y_true), dtype=self.dtype)
+        data = self.custom_loss(yt, y, loss_type)
+        total = data + (self.l2_term() if with_l2 else 0.0)
+        total.backward()
+        grads = {k: self.p[k].grad.detach().clone() for k in self.trainable}
+        return float(total.detach()), float(data.detach()), y.detach(), grads
+
+    def adam_step(self, grads, lr, beta1=0.9, beta2=0.999, eps=1e-7):
+        """keras.optimizers.Adam.get_updates @ 2.1.3: eps is added to sqrt(v) un-corrected."""
+        self.t += 1
+        lr_t = lr * math.sqrt(1 - beta2 ** self.t) / (1 - beta1 ** self.t)
+        with torch.no_grad():
+            for k in self.trainable:
+                g = grads[k]
+                self.m[k] = beta1 * self.m[k] + (1 - beta1) * g
+                self.v[k] = beta2 * self.v[k] + (1 - beta2) * g * g
+                self.p[k] -= lr_t * self.m[k] / (self.v[k].sqrt() + eps)
+
+    def weights_numpy(self):
+        return OrderedDict((k, v.detach().cpu().numpy().copy()) for k, v in self.p.items())

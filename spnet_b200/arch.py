@@ -1,0 +1,116 @@
+"""Static description of the Xception-SPNet graph: parameter names/shapes in Keras layouts and
+the activation shape walk. Mirrors what the reference builds in create_model_functional
+(spnet/models.py:302-424) around keras.applications.Xception (Keras 2.1.3).
+
+Layer names follow Keras auto-naming so weights can be exchanged by name: the three stem
+convolutions are conv2d_1..3, the four residual 1x1 convolutions conv2d_4..7 (confirmed by the
+L2 list in paper/run_logs/log_DatasetA_*.txt:98), the Dense head is 'FinalOutput'.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+
+BN_EPS = 1e-3          # keras.applications.Xception uses BatchNormalization defaults
+BN_MOMENTUM = 0.99
+L2_COEF = 1e-4         # regularizers.l2(0.0001), spnet/models.py:47
+DROPOUT_RATE = 0.1     # spnet/models.py:338
+ENTRY_BLOCKS = ((2, 64, 128), (3, 128, 256), (4, 256, 728))
+MIDDLE_BLOCKS = tuple(range(5, 13))
+
+
+def same_out(n):
+    return (n + 1) // 2
+
+
+def shape_walk(H, W):
+    """Spatial sizes: dict stage -> (h, w)."""
+    s = OrderedDict()
+    s["input"] = (H, W)
+    s["stem"] = (H // 2, W // 2)
+    h, w = s["stem"]
+    s["b1c1"] = ((h - 3) // 2 + 1, (w - 3) // 2 + 1)
+    h, w = s["b1c1"]
+    s["b1c2"] = (h - 2, w - 2)
+    h, w = s["b1c2"]
+    for blk in (2, 3, 4):
+        s["in%d" % blk] = (h, w)
+        h, w = same_out(h), same_out(w)
+        s["out%d" % blk] = (h, w)
+    s["middle"] = (h, w)
+    s["in13"] = (h, w)
+    h, w = same_out(h), same_out(w)
+    s["out13"] = (h, w)
+    return s
+
+
+def param_spec(H, W, n_out=576):
+    """[(key, shape, trainable, l2_regularised)] — keys are '<keras layer>/<weight>'."""
+    spec = []
+
+    def conv(name, kh, kw, cin, cout):
+        spec.append((name + "/kernel", (kh, kw, cin, cout), True, True))
+
+    def bn(name, c):
+        spec.append((name + "/gamma", (c,), True, False))
+        spec.append((name + "/beta", (c,), True, False))
+        spec.append((name + "/moving_mean", (c,), False, False))
+        spec.append((name + "/moving_variance", (c,), False, False))
+
+    def sep(name, cin, cout):
+        spec.append((name + "/depthwise_kernel", (3, 3, cin, 1), True, False))
+        spec.append((name + "/pointwise_kernel", (1, 1, cin, cout), True, False))
+        bn(name + "_bn", cout)
+
+    for i, cin in ((1, 1), (2, 3), (3, 3)):
+        conv("conv2d_%d" % i, 3, 3, cin, 3)
+        bn("batch_normalization_%d" % i, 3)
+    conv("block1_conv1", 3, 3, 3, 32)
+    bn("block1_conv1_bn", 32)
+    conv("block1_conv2", 3, 3, 32, 64)
+    bn("block1_conv2_bn", 64)
+    for n, (blk, cin, c) in enumerate(ENTRY_BLOCKS):
+        conv("conv2d_%d" % (4 + n), 1, 1, cin, c)
+        bn("batch_normalization_%d" % (4 + n), c)
+        sep("block%d_sepconv1" % blk, cin, c)
+        sep("block%d_sepconv2" % blk, c, c)
+    for blk in MIDDLE_BLOCKS:
+        for j in (1, 2, 3):
+            sep("block%d_sepconv%d" % (blk, j), 728, 728)
+    conv("conv2d_7", 1, 1, 728, 1024)
+    bn("batch_normalization_7", 1024)
+    sep("block13_sepconv1", 728, 728)
+    sep("block13_sepconv2", 728, 1024)
+    sep("block14_sepconv1", 1024, 1536)
+    sep("block14_sepconv2", 1536, 2048)
+    fh, fw = shape_walk(H, W)["out13"]
+    spec.append(("FinalOutput/kernel", (fh * fw * 2048, n_out), True, True))
+    spec.append(("FinalOutput/bias", (n_out,), True, False))
+    return spec
+
+
+def count_params(spec):
+    tr = sum(int(np.prod(s)) for _, s, t, _ in spec if t)
+    nt = sum(int(np.prod(s)) for _, s, t, _ in spec if not t)
+    return tr + nt, tr, nt
+
+
+def glorot_init(spec, seed=1):
+    """Keras default initialisers (glorot_uniform kernels, zeros bias, BN 1/0/0/1)."""
+    rng = np.random.default_rng(seed)
+    out = OrderedDict()
+    for key, shape, _, _ in spec:
+        leaf = key.rsplit("/", 1)[1]
+        if leaf.endswith("kernel"):
+            if len(shape) == 2:
+                fan_in, fan_out = shape
+            else:
+                rf = shape[0] * shape[1]
+                fan_in, fan_out = shape[2] * rf, shape[3] * rf
+            lim = math.sqrt(6.0 / (fan_in + fan_out))
+            out[key] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+        elif leaf in ("gamma", "moving_variance"):
+            out[key] = np.ones(shape, np.float32)
+        else:
+            out[key] = np.zeros(shape, np.float32)
+    return out

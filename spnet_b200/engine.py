@@ -1,0 +1,523 @@
+"""Xception-SPNet execution engine: owns the device buffers and sequences the sm_100a kernels
+of libspnet_b200.so for inference, and for the training step
+    forward (train-mode BN, dropout) -> YOLO-ellipse loss (+L2) -> backward -> Keras Adam.
+
+This replaces what the reference gets from keras Model.predict / Model.fit's train_function
+on the graph built by create_model_functional (spnet/models.py:302-424, compiled at :494-502).
+All arithmetic happens in the CUDA kernels; torch only provides memory, streams and graphs.
+
+Data layout in HBM: activations NHWC, bf16 (or fp32 in fp32 mode); every convolution output is
+stored RAW (pre-BatchNorm) together with fp64 per-channel sum / sum-of-squares accumulated by
+the producing kernel; BatchNorm (+ReLU) is applied by the consumer on load as y = a*z + b.
+Parameters: one flat fp32 master buffer (L2-regularised kernels first, Dense head at offset 0
+so its gradient is the first all-reduce bucket), flat fp32 grad / Adam m / Adam v buffers with
+the same layout and a flat bf16 working copy refreshed by the Adam kernel.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import arch, ops
+from ._lib import lib
+
+
+class _BN:
+    __slots__ = ("name", "C", "gamma", "beta", "ggamma", "gbeta", "mm", "mv", "a", "b", "mean", "rstd", "c1", "c2",
+                 "stats")
+
+
+class _Sep:
+    __slots__ = ("name", "cin", "cout", "dwk", "gdwk", "pw", "pwl", "gpw", "bn", "t", "z", "H", "W")
+
+
+class XceptionSPNetEngine:
+    def __init__(self, H, W, batch, n_out=576, dtype="bf16", device="cuda:0", weights=None, seed=1,
+                 loss_type="same", dropout_rate=arch.DROPOUT_RATE, use_l2=True, unbiased_moving_var=True,
+                 training=True):
+        assert dtype in ("bf16", "fp32")
+        rc = lib().check_device  # noqa: F841  (resolved lazily below, after the device is selected)
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        lib().check_device()
+        self.H, self.W, self.B, self.n_out = H, W, batch, n_out
+        self.lowp = dtype == "bf16"
+        self.adt = torch.bfloat16 if self.lowp else torch.float32
+        self.loss_type = loss_type
+        self.dropout_rate = float(dropout_rate)
+        self.use_l2 = use_l2
+        self.unbiased = unbiased_moving_var
+        self.can_train = training
+        self.shapes = arch.shape_walk(H, W)
+        self.spec = arch.param_spec(H, W, n_out)
+        self._alloc_params(weights if weights is not None else arch.glorot_init(self.spec, seed))
+        self._build_layers()
+        self._alloc_activations()
+        self.step_count = 0
+        self.graph = None
+        self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self._seed_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self.lr_t_dev = torch.zeros(1, device=self.device, dtype=torch.float32)
+        self.seed_dev = torch.zeros(1, device=self.device, dtype=torch.int64)
+        self.base_seed = int(seed)
+        self.grad_hook = None  # called between backward and the optimiser (data-parallel all-reduce)
+
+    # ------------------------------------------------------------------ parameters
+    def _alloc_params(self, weights):
+        dev = self.device
+        train = [(k, s, r) for k, s, t, r in self.spec if t]
+        # Dense head first, then the other L2-regularised kernels, then everything else
+        order = ([e for e in train if e[0] == "FinalOutput/kernel"] + [e for e in train if e[2] and e[0] != "FinalOutput/kernel"]
+                 + [e for e in train if not e[2]])
+        self.offsets = OrderedDict()
+        off = 0
+        for k, s, r in order:
+            n = int(np.prod(s))
+            self.offsets[k] = (off, n, s)
+            off += (n + 7) // 8 * 8  # keep every tensor 32-byte aligned (16 B in bf16) for TMA / vector loads
+        self.n_params_padded = off
+        self.n_l2 = sum((int(np.prod(s)) + 7) // 8 * 8 for k, s, r in order if r)
+        self.params = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.w = OrderedDict((k, self.params[o:o + n].view(*s)) for k, (o, n, s) in self.offsets.items())
+        if self.can_train:
+            self.grads = torch.zeros(off, device=dev, dtype=torch.float32)
+            self.adam_m = torch.zeros(off, device=dev, dtype=torch.float32)
+            self.adam_v = torch.zeros(off, device=dev, dtype=torch.float32)
+            self.g = OrderedDict((k, self.grads[o:o + n].view(*s)) for k, (o, n, s) in self.offsets.items())
+        if self.lowp:
+            self.params_lp = torch.zeros(off, device=dev, dtype=torch.bfloat16)
+            self.wl = OrderedDict((k, self.params_lp[o:o + n].view(*s)) for k, (o, n, s) in self.offsets.items())
+        else:
+            self.params_lp, self.wl = None, self.w
+        nt = [(k, s) for k, s, t, _ in self.spec if not t]
+        self.nt_offsets = OrderedDict()
+        off = 0
+        for k, s in nt:
+            self.nt_offsets[k] = (off, int(np.prod(s)), s)
+            off += int(np.prod(s))
+        self.nontrainable = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.nt = OrderedDict((k, self.nontrainable[o:o + n].view(*s)) for k, (o, n, s) in self.nt_offsets.items())
+        self.set_weights(weights)
+
+    def set_weights(self, weights):
+        """weights: {'<layer>/<weight>': array in Keras layout}."""
+        for k, _, t, _ in self.spec:
+            src = torch.as_tensor(np.asarray(weights[k], dtype=np.float32))
+            dst = self.w[k] if t else self.nt[k]
+            assert tuple(src.shape) == tuple(dst.shape), (k, tuple(src.shape), tuple(dst.shape))
+            dst.copy_(src)
+        self.refresh_lowp()
+
+    def get_weights(self):
+        torch.cuda.synchronize(self.device)
+        out = OrderedDict()
+        for k, _, t, _ in self.spec:
+            out[k] = (self.w[k] if t else self.nt[k]).detach().cpu().numpy().copy()
+        return out
+
+    def refresh_lowp(self):
+        if self.lowp:
+            ops.cast_f32_to_bf16(self.params, self.params_lp)
+
+    # ------------------------------------------------------------------ layers
+    def _f32(self, n):
+        return torch.zeros(n, device=self.device, dtype=torch.float32)
+
+    def _mk_bn(self, name, C):
+        bn = _BN()
+        bn.name, bn.C = name, C
+        bn.gamma, bn.beta = self.w[name + "/gamma"], self.w[name + "/beta"]
+        if self.can_train:
+            bn.ggamma, bn.gbeta = self.g[name + "/gamma"], self.g[name + "/beta"]
+        else:
+            bn.ggamma = bn.gbeta = None
+        bn.mm, bn.mv = self.nt[name + "/moving_mean"], self.nt[name + "/moving_variance"]
+        bn.a, bn.b, bn.mean, bn.rstd, bn.c1, bn.c2 = (self._f32(C) for _ in range(6))
+        bn.stats = torch.zeros(2 * C, device=self.device, dtype=torch.float64)
+        self.bns.append(bn)
+        return bn
+
+    def _mk_sep(self, name, cin, cout, hw):
+        s = _Sep()
+        s.name, s.cin, s.cout = name, cin, cout
+        s.H, s.W = hw
+        s.dwk = self.w[name + "/depthwise_kernel"].view(3, 3, cin)
+        s.pw = self.w[name + "/pointwise_kernel"].view(cin, cout)
+        s.pwl = self.wl[name + "/pointwise_kernel"].view(cin, cout)
+        if self.can_train:
+            s.gdwk = self.g[name + "/depthwise_kernel"].view(3, 3, cin)
+            s.gpw = self.g[name + "/pointwise_kernel"].view(cin, cout)
+        s.bn = self._mk_bn(name + "_bn", cout)
+        return s
+
+    def _build_layers(self):
+        sh = self.shapes
+        self.bns = []
+        self.stem_bn = [self._mk_bn("batch_normalization_%d" % i, 3) for i in (1, 2, 3)]
+        self.b1_bn1 = self._mk_bn("block1_conv1_bn", 32)
+        self.b1_bn2 = self._mk_bn("block1_conv2_bn", 64)
+        self.entry = []
+        for n, (blk, cin, c) in enumerate(arch.ENTRY_BLOCKS):
+            hw = sh["in%d" % blk]
+            e = dict(blk=blk, cin=cin, c=c, hw=hw, ohw=sh["out%d" % blk], res="conv2d_%d" % (4 + n),
+                     res_bn=self._mk_bn("batch_normalization_%d" % (4 + n), c),
+                     sep1=self._mk_sep("block%d_sepconv1" % blk, cin, c, hw),
+                     sep2=self._mk_sep("block%d_sepconv2" % blk, c, c, hw), relu_in=(blk != 2))
+            self.entry.append(e)
+        self.middle = []
+        for blk in arch.MIDDLE_BLOCKS:
+            self.middle.append([self._mk_sep("block%d_sepconv%d" % (blk, j), 728, 728, sh["middle"]) for j in (1, 2, 3)])
+        hw = sh["in13"]
+        self.exit13 = dict(blk=13, cin=728, c=1024, hw=hw, ohw=sh["out13"], res="conv2d_7",
+                           res_bn=self._mk_bn("batch_normalization_7", 1024),
+                           sep1=self._mk_sep("block13_sepconv1", 728, 728, hw),
+                           sep2=self._mk_sep("block13_sepconv2", 728, 1024, hw), relu_in=True)
+        self.sep14 = [self._mk_sep("block14_sepconv1", 1024, 1536, sh["out13"]),
+                      self._mk_sep("block14_sepconv2", 1536, 2048, sh["out13"])]
+        self.k4 = self._f32(48).view(4, 4, 1, 3)
+        self.gk4 = self._f32(48).view(4, 4, 1, 3)
+        self.l2_out = self._f32(1)
+
+    def _act(self, *shape, dtype=None):
+        return torch.empty(*shape, device=self.device, dtype=dtype or self.adt)
+
+    def _alloc_activations(self):
+        B, sh, A = self.B, self.shapes, self._act
+        H, W = self.H, self.W
+        self.x0 = torch.zeros(B, H, W, 1, device=self.device, dtype=torch.float32)
+        self.y_true = torch.zeros(B, self.n_out, device=self.device, dtype=torch.float32)
+        h, w = sh["stem"]
+        self.p1, self.c2, self.c3, self.d = (A(B, h, w, 3) for _ in range(4))
+        self.s0 = A(B, h, w, 1)
+        h1, w1 = sh["b1c1"]
+        self.z11 = A(B, h1, w1, 32)
+        h2, w2 = sh["b1c2"]
+        self.col = A(B * h2 * w2, 288)
+        self.z12 = A(B, h2, w2, 64)
+        self.x2 = A(B, h2, w2, 64)
+        train = self.can_train
+        maxel = B * h2 * w2 * 128
+        for e in self.entry + [self.exit13]:
+            (eh, ew), (oh, ow) = e["hw"], e["ohw"]
+            e["xs"] = A(B, oh, ow, e["cin"])
+            e["zr"] = A(B, oh, ow, e["c"])
+            for s in (e["sep1"], e["sep2"]):
+                s.t = A(B, eh, ew, s.cin)
+                s.z = A(B, eh, ew, s.cout)
+                maxel = max(maxel, B * eh * ew * max(s.cin, s.cout))
+            e["out"] = A(B, oh, ow, e["c"])
+            e["argmax"] = A(B, oh, ow, e["c"], dtype=torch.uint8) if train else None
+        mh, mw = sh["middle"]
+        for blk in self.middle:
+            for s in blk:
+                s.t = A(B, mh, mw, 728)
+                s.z = A(B, mh, mw, 728)
+        self.mid_out = [A(B, mh, mw, 728) for _ in self.middle]
+        fh, fw = sh["out13"]
+        for s in self.sep14:
+            s.t = A(B, fh, fw, s.cin)
+            s.z = A(B, fh, fw, s.cout)
+        self.feat = A(B, fh * fw * 2048)
+        self.y_pred = torch.zeros(B, self.n_out, device=self.device, dtype=torch.float32)
+        self.loss6 = self._f32(6)
+        if train:
+            self.gy = torch.zeros(B, self.n_out, device=self.device, dtype=torch.float32)
+            self.gyl = A(B, self.n_out) if self.lowp else self.gy
+            self.gfeat = A(B, fh * fw * 2048)
+            self.gcol = A(B * h2 * w2, 288)
+            self.scratch = [A(maxel) for _ in range(6)]
+            sp = B * sh["stem"][0] * sh["stem"][1] * 3
+            self.gstem = [A(sp) for _ in range(2)]
+        self.dense_splits = max(1, min(64, (2 * 148) // max(1, -(-self.n_out // 128))))
+
+    # ------------------------------------------------------------------ helpers
+    def _view(self, buf, *shape):
+        n = int(np.prod(shape))
+        return buf[:n].view(*shape)
+
+    def _bn_ready(self, bn, count, training):
+        if training:
+            ops.bn_finalize(bn.stats, count, bn.gamma, bn.beta, bn.a, bn.b, bn.mean, bn.rstd, bn.mm, bn.mv,
+                            eps=arch.BN_EPS, momentum=arch.BN_MOMENTUM, unbiased=self.unbiased)
+        else:
+            ops.bn_inference_affine(bn.gamma, bn.beta, bn.mm, bn.mv, bn.a, bn.b, eps=arch.BN_EPS)
+
+    def _pw_fwd(self, A, Wl, D, M, K, N, bn, training):
+        ops.gemm(A, False, Wl, True, D, M, N, K, out_mode=ops.OUT_T, colstats=bn.stats if training else None)
+        self._bn_ready(bn, M, training)
+
+    def _wgrad_splits(self, rows_out, cols_out, K):
+        tile = 128 if self.lowp else 64
+        tiles = -(-rows_out // tile) * -(-cols_out // tile)
+        kb = max(1, K // (64 if self.lowp else 16))
+        return int(max(1, min(kb // 4 if kb >= 8 else 1, -(-(2 * 148) // tiles))))
+
+    def _pw_bwd(self, A, Wl, gW, gz, gA, M, K, N):
+        """gz [M,N] -> gW [K,N] += A^T gz ;  gA [M,K] = gz W^T."""
+        sp = self._wgrad_splits(K, N, M)
+        ops.gemm(A, True, gz, True, gW, K, N, M, out_mode=ops.OUT_ATOMIC, splits=sp, lda=K, ldb=N)
+        if gA is not None:
+            ops.gemm(gz, False, Wl, False, gA, M, K, N, out_mode=ops.OUT_T, ldb=N)
+
+    def _sep_fwd(self, s, x, in_bn, relu, training):
+        B = self.B
+        ops.dwconv3x3_fwd(x, s.dwk, in_bn.a if in_bn else None, in_bn.b if in_bn else None, relu, out=s.t)
+        M = B * s.H * s.W
+        self._pw_fwd(s.t, s.pwl, s.z, M, s.cin, s.cout, s.bn, training)
+
+    def _bn_bwd(self, g, z, bn, rows, relu_mask=False, out=None):
+        """g = grad wrt BN output (or wrt relu(BN output) when relu_mask) -> grad wrt z."""
+        ops.bn_bwd_reduce(g, z, bn.mean, bn.rstd, bn.stats, relu_a=bn.a if relu_mask else None,
+                          relu_b=bn.b if relu_mask else None, act=1)
+        ops.bn_bwd_finalize(bn.stats, rows, bn.ggamma, bn.gbeta, bn.c1, bn.c2)
+        return ops.bn_bwd_dz(g, z, bn.a, bn.mean, bn.rstd, bn.c1, bn.c2, out=out if out is not None else g)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, training=False):
+        """Runs the network on self.x0 (already on the device). Result in self.y_pred."""
+        B, sh = self.B, self.shapes
+        w = self.w
+        bn1, bn2, bn3 = self.stem_bn
+        H2, W2 = sh["stem"]
+        npx = B * H2 * W2
+        st = (lambda bn: bn.stats) if training else (lambda bn: None)
+        # ---- stem (spnet/models.py:321-338)
+        ops.stem_k3_to_k4(w["conv2d_1/kernel"], self.k4)
+        ops.conv_small_fwd(0, self.x0, self.k4, self.p1, skip=self.s0, stats=st(bn1))
+        self._bn_ready(bn1, npx, training)
+        ops.conv_small_fwd(1, self.p1, w["conv2d_2/kernel"], self.c2, in_a=bn1.a, in_b=bn1.b, act=2, stats=st(bn2))
+        self._bn_ready(bn2, npx, training)
+        ops.conv_small_fwd(1, self.c2, w["conv2d_3/kernel"], self.c3, in_a=bn2.a, in_b=bn2.b, act=2, stats=st(bn3))
+        self._bn_ready(bn3, npx, training)
+        drop = training and self.dropout_rate > 0
+        ops.stem_out_fwd(self.c3, bn3.a, bn3.b, self.s0, self.d, rate=self.dropout_rate if drop else 0.0,
+                         seed=self.seed_dev if drop else None)
+        # ---- block 1
+        h1, w1 = sh["b1c1"]
+        ops.conv_small_fwd(2, self.d, w["block1_conv1/kernel"], self.z11, stats=st(self.b1_bn1))
+        self._bn_ready(self.b1_bn1, B * h1 * w1, training)
+        h2, w2 = sh["b1c2"]
+        ops.im2col3x3(self.z11, self.col, self.b1_bn1.a, self.b1_bn1.b, True)
+        self._pw_fwd(self.col, self.wl["block1_conv2/kernel"].view(288, 64), self.z12.view(-1, 64), B * h2 * w2, 288,
+                     64, self.b1_bn2, training)
+        ops.bn_apply(self.z12, self.b1_bn2.a, self.b1_bn2.b, act=1, out=self.x2)
+        # ---- entry blocks 2-4, middle 5-12, exit 13
+        x = self.x2
+        for e in self.entry:
+            x = self._entry_fwd(e, x, training)
+        for blk, out in zip(self.middle, self.mid_out):
+            self._sep_fwd(blk[0], x, None, True, training)
+            self._sep_fwd(blk[1], blk[0].z, blk[0].bn, True, training)
+            self._sep_fwd(blk[2], blk[1].z, blk[1].bn, True, training)
+            ops.bn_apply(blk[2].z, blk[2].bn.a, blk[2].bn.b, act=0, x=x, out=out)
+            x = out
+        x = self._entry_fwd(self.exit13, x, training)
+        # ---- block 14 + head
+        s1, s2 = self.sep14
+        self._sep_fwd(s1, x, None, False, training)
+        self._sep_fwd(s2, s1.z, s1.bn, True, training)
+        ops.bn_apply(s2.z.view(B, -1, 2048), s2.bn.a, s2.bn.b, act=1, out=self.feat.view(B, -1, 2048))
+        F = self.feat.shape[1]
+        ops.bias_fill(w["FinalOutput/bias"], self.y_pred)
+        ops.gemm(self.feat, False, self.wl["FinalOutput/kernel"], True, self.y_pred, B, self.n_out, F,
+                 out_mode=ops.OUT_ATOMIC, splits=self.dense_splits)
+        return self.y_pred
+
+    def _entry_fwd(self, e, x, training):
+        B = self.B
+        oh, ow = e["ohw"]
+        ops.gather_s2(x, out=e["xs"])
+        self._pw_fwd(e["xs"].view(-1, e["cin"]), self.wl[e["res"] + "/kernel"].view(e["cin"], e["c"]),
+                     e["zr"].view(-1, e["c"]), B * oh * ow, e["cin"], e["c"], e["res_bn"], training)
+        s1, s2 = e["sep1"], e["sep2"]
+        self._sep_fwd(s1, x, None, e["relu_in"], training)
+        self._sep_fwd(s2, s1.z, s1.bn, True, training)
+        ops.maxpool3s2_add_fwd(s2.z, s2.bn.a, s2.bn.b, e["zr"], e["res_bn"].a, e["res_bn"].b, out=e["out"],
+                               argmax=e["argmax"] if training else None)
+        return e["out"]
+
+    # ------------------------------------------------------------------ loss
+    def loss(self, with_grad):
+        ops.yolo_ellipse_loss(self.y_true, self.y_pred, hybrid=(self.loss_type != "same"), out6=self.loss6,
+                              grad=self.gy if with_grad else None)
+        self.l2_out.zero_()
+        if self.use_l2:
+            ops.sumsq(self.params, self.n_l2, arch.L2_COEF, self.l2_out)
+
+    # ------------------------------------------------------------------ backward
+    def _sep_bwd(self, s, gz, x, in_bn, relu, g_t, g_in, add_src=None, add_strided=None):
+        """gz: grad wrt s.z [B,H,W,cout]. Produces the gradient wrt the sepconv's input tensor x
+        (before its on-load BN/ReLU transform) in g_in; for a BN'd input this is still the grad wrt
+        the BN OUTPUT (masked by relu'), to be pushed through _bn_bwd by the caller."""
+        B = self.B
+        M = B * s.H * s.W
+        self._pw_bwd(s.t, s.pwl, s.gpw, gz, g_t, M, s.cin, s.cout)
+        gt4 = g_t.view(B, s.H, s.W, s.cin)
+        ops.dwconv3x3_wgrad(x, gt4, s.gdwk, in_bn.a if in_bn else None, in_bn.b if in_bn else None, relu)
+        ops.dwconv3x3_dgrad(gt4, s.dwk, mask_src=x if relu else None, mask_a=in_bn.a if (in_bn and relu) else None,
+                            mask_b=in_bn.b if (in_bn and relu) else None, add_src=add_src, add_strided=add_strided,
+                            out=g_in.view(B, s.H, s.W, s.cin))
+
+    def _entry_bwd(self, e, x, g_out, bufs):
+        """g_out: grad wrt block output [B,oh,ow,c]. Returns grad wrt block input x."""
+        B = self.B
+        (H, W), (oh, ow) = e["hw"], e["ohw"]
+        cin, c = e["cin"], e["c"]
+        G1, G2, G3, S, R = bufs
+        Mo = B * oh * ow
+        M = B * H * W
+        s1, s2 = e["sep1"], e["sep2"]
+        # residual branch
+        g_zr = self._bn_bwd(g_out, e["zr"], e["res_bn"], Mo, out=self._view(G1, B, oh, ow, c))
+        g_xs = self._view(S, Mo, cin)
+        self._pw_bwd(e["xs"].view(Mo, cin), self.wl[e["res"] + "/kernel"].view(cin, c),
+                     self.g[e["res"] + "/kernel"].view(cin, c), g_zr.view(Mo, c), g_xs, Mo, cin, c)
+        # main branch
+        g_y2 = ops.maxpool3s2_bwd(g_out, e["argmax"], H, W, out=self._view(G1, B, H, W, c))
+        g_z2 = self._bn_bwd(g_y2, s2.z, s2.bn, M)
+        g_y1 = self._view(G3, B, H, W, c)
+        self._sep_bwd(s2, g_z2.view(M, c), s1.z, s1.bn, True, self._view(G2, M, c), g_y1)
+        g_z1 = self._bn_bwd(g_y1, s1.z, s1.bn, M)
+        g_x = self._view(R, B, H, W, cin)
+        self._sep_bwd(s1, g_z1.view(M, c), x, None, e["relu_in"], self._view(G1, M, cin), g_x,
+                      add_strided=g_xs.view(B, oh, ow, cin))
+        return g_x
+
+    def backward(self):
+        """Consumes self.gy (dL/dy_pred); accumulates into self.grads (zeroed by the caller)."""
+        B, sh, w, g = self.B, self.shapes, self.w, self.g
+        G1, G2, G3, S, R0, R1 = self.scratch
+        F = self.feat.shape[1]
+        # ---- Dense head
+        if self.lowp:
+            ops.cast_f32_to_bf16(self.gy, self.gyl)
+        ops.colsum(self.gy, g["FinalOutput/bias"])
+        ops.gemm(self.feat, True, self.gyl, True, g["FinalOutput/kernel"], F, self.n_out, B, out_mode=ops.OUT_F32,
+                 lda=F, ldb=self.n_out)
+        ops.gemm(self.gyl, False, self.wl["FinalOutput/kernel"], False, self.gfeat, B, F, self.n_out,
+                 out_mode=ops.OUT_T, ldb=self.n_out)
+        # ---- block 14
+        s1, s2 = self.sep14
+        fh, fw = sh["out13"]
+        M = B * fh * fw
+        x13 = self.exit13["out"]
+        g_z = self._bn_bwd(self.gfeat.view(B, fh, fw, 2048), s2.z, s2.bn, M, relu_mask=True)
+        g_y = self._view(G3, B, fh, fw, 1536)
+        self._sep_bwd(s2, g_z.view(M, 2048), s1.z, s1.bn, True, self._view(G2, M, 1536), g_y)
+        g_z = self._bn_bwd(g_y, s1.z, s1.bn, M)
+        g_x = self._view(R0, B, fh, fw, 1024)
+        self._sep_bwd(s1, g_z.view(M, 1536), x13, None, False, self._view(G1, M, 1024), g_x)
+        # ---- exit block 13
+        R_cur, R_nxt = R0, R1
+        x_in13 = self.mid_out[-1]
+        g_x = self._entry_bwd(self.exit13, x_in13, g_x, (G1, G2, G3, S, R_nxt))
+        R_cur, R_nxt = R_nxt, R_cur
+        # ---- middle blocks 12..5
+        mh, mw = sh["middle"]
+        M = B * mh * mw
+        for i in range(len(self.middle) - 1, -1, -1):
+            blk = self.middle[i]
+            x_in = self.mid_out[i - 1] if i > 0 else self.entry[-1]["out"]
+            g3 = self._bn_bwd(g_x, blk[2].z, blk[2].bn, M, out=self._view(G1, B, mh, mw, 728))
+            gy2 = self._view(G3, B, mh, mw, 728)
+            self._sep_bwd(blk[2], g3.view(M, 728), blk[1].z, blk[1].bn, True, self._view(G2, M, 728), gy2)
+            g2 = self._bn_bwd(gy2, blk[1].z, blk[1].bn, M)
+            gy1 = self._view(G1, B, mh, mw, 728)
+            self._sep_bwd(blk[1], g2.view(M, 728), blk[0].z, blk[0].bn, True, self._view(G2, M, 728), gy1)
+            g1 = self._bn_bwd(gy1, blk[0].z, blk[0].bn, M)
+            g_new = self._view(R_nxt, B, mh, mw, 728)
+            self._sep_bwd(blk[0], g1.view(M, 728), x_in, None, True, self._view(G2, M, 728), g_new, add_src=g_x)
+            g_x = g_new
+            R_cur, R_nxt = R_nxt, R_cur
+        # ---- entry blocks 4..2
+        for i in range(len(self.entry) - 1, -1, -1):
+            e = self.entry[i]
+            x_in = self.entry[i - 1]["out"] if i > 0 else self.x2
+            g_x = self._entry_bwd(e, x_in, g_x, (G1, G2, G3, S, R_nxt))
+            R_cur, R_nxt = R_nxt, R_cur
+        # ---- block 1
+        h2, w2 = sh["b1c2"]
+        h1, w1 = sh["b1c1"]
+        M2 = B * h2 * w2
+        g_z12 = self._bn_bwd(g_x, self.z12, self.b1_bn2, M2, relu_mask=True)
+        W2l = self.wl["block1_conv2/kernel"].view(288, 64)
+        self._pw_bwd(self.col, W2l, g["block1_conv2/kernel"].view(288, 64), g_z12.view(M2, 64), self.gcol, M2, 288, 64)
+        g_y11 = self._view(G1, B, h1, w1, 32)
+        ops.col2im3x3(self.gcol, g_y11, z=self.z11, a=self.b1_bn1.a, b=self.b1_bn1.b, relu=True)
+        g_z11 = self._bn_bwd(g_y11, self.z11, self.b1_bn1, B * h1 * w1)
+        ops.conv_small_wgrad(2, self.d, g_z11, g["block1_conv1/kernel"])
+        H2, W2 = sh["stem"]
+        npx = B * H2 * W2
+        ga, gb = (self._view(t, B, H2, W2, 3) for t in self.gstem)
+        ops.conv_small_dgrad(2, g_z11, w["block1_conv1/kernel"], ga)
+        # ---- stem
+        bn1, bn2, bn3 = self.stem_bn
+        drop = self.dropout_rate > 0
+        ops.stem_out_bwd(ga, gb, rate=self.dropout_rate if drop else 0.0, seed=self.seed_dev if drop else None)
+        self._bn3_bwd(gb, self.c3, bn3, npx)                      # gb = grad wrt c3
+        ops.conv_small_wgrad(1, self.c2, gb, g["conv2d_3/kernel"], in_a=bn2.a, in_b=bn2.b, act=2)
+        ops.conv_small_dgrad(1, gb, w["conv2d_3/kernel"], ga, mask_z=self.c2, mask_a=bn2.a, mask_b=bn2.b, act=2)
+        self._bn3_bwd(ga, self.c2, bn2, npx)                      # ga = grad wrt c2
+        ops.conv_small_wgrad(1, self.p1, ga, g["conv2d_2/kernel"], in_a=bn1.a, in_b=bn1.b, act=2)
+        ops.conv_small_dgrad(1, ga, w["conv2d_2/kernel"], gb, mask_z=self.p1, mask_a=bn1.a, mask_b=bn1.b, act=2)
+        self._bn3_bwd(gb, self.p1, bn1, npx)                      # gb = grad wrt p1
+        self.gk4.zero_()
+        ops.conv_small_wgrad(0, self.x0, gb, self.gk4)
+        ops.stem_k4grad_to_k3grad(self.gk4, g["conv2d_1/kernel"])
+
+    def _bn3_bwd(self, gbuf, z, bn, npx):
+        ops.bn3_bwd_reduce(gbuf, z, bn.mean, bn.rstd, bn.stats)
+        ops.bn_bwd_finalize(bn.stats, npx, bn.ggamma, bn.gbeta, bn.c1, bn.c2)
+        ops.bn3_bwd_dz(gbuf, z, bn.a, bn.mean, bn.rstd, bn.c1, bn.c2, gbuf)
+
+    # ------------------------------------------------------------------ optimiser / step
+    def optimizer_step(self, grad_scale=1.0):
+        ops.adam_keras_step(self.params, self.grads, self.adam_m, self.adam_v, self.lr_t_dev, n_l2=self.n_l2 if self.use_l2 else 0,
+                            l2=arch.L2_COEF, grad_scale=grad_scale, p_bf16=self.params_lp)
+
+    def _step_body(self):
+        self.grads.zero_()
+        self.forward(training=True)
+        self.loss(with_grad=True)
+        self.backward()
+        if self.grad_hook is None:
+            self.optimizer_step()
+
+    def set_lr(self, lr, beta1=0.9, beta2=0.999):
+        """Host side of Keras Adam: t += 1, lr_t = lr*sqrt(1-b2^t)/(1-b1^t) -> device scalar."""
+        self.step_count += 1
+        t = self.step_count
+        self._lr_host[0] = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+        self.lr_t_dev.copy_(self._lr_host, non_blocking=True)
+        self._seed_host[0] = (self.base_seed * 1000003 + t) & 0x7FFFFFFFFFFFFFFF
+        self.seed_dev.copy_(self._seed_host, non_blocking=True)
+
+    def capture(self):
+        """Capture fwd+loss+bwd(+Adam) into one CUDA graph (call after one eager warm-up step)."""
+        gph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gph):
+            self._step_body()
+        self.graph = gph
+
+    def train_step(self, lr):
+        """One optimiser step on the batch currently in self.x0 / self.y_true.
+        Returns the device tensor [total, center, size, angle, noobj, class] (data loss) —
+        the L2 term is in self.l2_out."""
+        self.set_lr(lr)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_body()
+        if self.grad_hook is not None:
+            self.grad_hook(self)
+            self.optimizer_step()
+        return self.loss6
+
+    def load_batch(self, x_host, y_host=None):
+        """H2D copy of one batch (numpy or pinned torch tensors)."""
+        xt = x_host if torch.is_tensor(x_host) else torch.from_numpy(np.ascontiguousarray(x_host, dtype=np.float32))
+        self.x0.copy_(xt.view(self.x0.shape), non_blocking=True)
+        if y_host is not None:
+            yt = y_host if torch.is_tensor(y_host) else torch.from_numpy(np.ascontiguousarray(y_host, dtype=np.float32))
+            self.y_true.copy_(yt.view(self.y_true.shape), non_blocking=True)
