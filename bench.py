@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the SPNet hot path on B200: Xception-SPNet full training step
+(forward + YOLO-ellipse loss + backward + Keras Adam), bf16, batch 64 per GPU, 384x512x1
+gen_fake_espi-style synthetic frames (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0). N > 1 is launched by torchrun (one rank per GPU, NCCL).
+`value`   : images/s with the batch already resident in HBM (CUDA-graph replay, device timed).
+`e2e`     : images/s through the public Keras-like API path with HOST buffers: pinned H2D of the
+            step's inputs and a D2H read of the loss inside the timed region.
+`roofline`: the dominant kernel family of the step, timed live with CUDA events.
+`--impl reference`: the reference network's CPU path. TensorFlow 1.14 / Keras 2.1.3 cannot run in
+this image, so this arm times the oracle restatement (kind "port") of the same
+training step on the box's host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, N_OUT = 384, 512, 576
+BATCH_PER_GPU = 64
+METRIC = "train images/sec (Xception-SPNet, 512x384)"
+LR = 4e-5
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def make_pool(n, seed0):
+    from spnet_b200 import fake_espi
+    X, Y, _ = fake_espi.make_dataset(n, base_seed=seed0)
+    return X, Y
+
+
+# -------------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    """CPU arm: oracle restatement of the same training step on the host cores (kind 'port')."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import xception_torch as xt
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    Bs = 4  # bounded sample of the batch-64 workload: 4 images per step
+    X, Y = make_pool(Bs, 10_000)
+    spec = xt.xception_spnet_spec(H, W, N_OUT)
+    model = xt.OracleSPNet(xt.init_weights(spec, seed=1), H, W)
+    times = []
+    for i in range(args.warmup_ref + args.steps_ref):
+        t0 = time.perf_counter()
+        _, _, _, grads = model.loss_and_grads(X, Y)
+        model.adam_step(grads, LR)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup_ref:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = Bs / (ms / 1e3)
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+           "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": ms, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "Xception-SPNet train step fwd+bwd+loss+Adam, 384x512x1, batch 64/GPU",
+                      "note": "reference CPU path = oracle restatement (TF1.14/Keras2.1.3 not runnable here)"},
+           "cpu_baseline": {"value": val, "unit": "images/s", "cores": ncores, "kind": "port",
+                            "sample": "%d steps of %d images (of the batch-64 workload), torch %s CPU fp32" % (
+                                args.steps_ref, Bs, torch.__version__)},
+           "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+# -------------------------------------------------------------------------------------------------
+def kernel_breakdown(eng, lib, steps=2):
+    """Eager steps with a CUDA-event pair around every kernel launch -> per-family device time."""
+    import torch
+    lib.profile = []
+    for _ in range(steps):
+        eng.train_step(LR)
+    torch.cuda.synchronize()
+    prof, lib.profile = lib.profile, None
+    fam = {}
+    for name, args, e0, e1 in prof:
+        d = fam.setdefault(name, {"ms": 0.0, "launches": 0, "items": []})
+        ms = e0.elapsed_time(e1)
+        d["ms"] += ms
+        d["launches"] += 1
+        d["items"].append((args, ms))
+    return fam, steps
+
+
+def algorithmic_work(name, a):
+    """(bytes, flops) one launch must move / compute, from its C-ABI arguments."""
+    def es(dtype):
+        return 2 if dtype == 1 else 4
+    if name == "spnet_dwconv3x3_fwd":      # in,k,a,b,relu,out,dtype,B,H,W,C,stream
+        n = a[7] * a[8] * a[9] * a[10]
+        return 2 * n * es(a[6]), 18 * n
+    if name == "spnet_dwconv3x3_dgrad":    # gout,k,gin,mask,ma,mb,add,adds,dtype,B,H,W,C
+        n = a[9] * a[10] * a[11] * a[12]
+        t = 2 + (1 if a[3] else 0) + (1 if a[6] else 0)
+        return t * n * es(a[8]), 18 * n
+    if name == "spnet_dwconv3x3_wgrad":    # in,g,a,b,relu,dk,dtype,B,H,W,C
+        n = a[7] * a[8] * a[9] * a[10]
+        return 2 * n * es(a[6]), 18 * n
+    if name == "spnet_gemm_bf16":          # A,lda,amn,B,ldb,bmn,D,ldd,mode,M,N,K,splits,...
+        M, N, K = a[9], a[10], a[11]
+        return 2 * (M * K + N * K) + (2 if a[8] == 0 else 4) * M * N, 2 * M * N * K
+    return 0, 0
+
+
+def run_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    from spnet_b200._lib import lib as get_lib
+    from spnet_b200.engine import XceptionSPNetEngine
+    from spnet_b200 import multi_gpu
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = get_lib()
+    B = BATCH_PER_GPU
+    npool = 2 * B
+    X, Y = make_pool(npool, 1_000_000 * rank)
+    Xp = torch.from_numpy(X).pin_memory()
+    Yp = torch.from_numpy(Y).pin_memory()
+    Xd, Yd = Xp.to(dev), Yp.to(dev)
+
+    eng = XceptionSPNetEngine(H, W, B, dtype="bf16", device=str(dev), seed=1)
+    if world > 1:
+        multi_gpu.attach_data_parallel(eng)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # eager warm-up (also counts kernel launches per step), then capture the step into a CUDA graph
+    eng.x0.copy_(Xd[:B]); eng.y_true.copy_(Yd[:B])
+    l0 = lib.launches
+    eng.train_step(LR)
+    torch.cuda.synchronize()
+    launches_per_step = lib.launches - l0
+    eng.capture()
+    for i in range(args.warmup):
+        o = (i % 2) * B
+        eng.x0.copy_(Xd[o:o + B]); eng.y_true.copy_(Yd[o:o + B])
+        eng.train_step(LR)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        o = (i % 2) * B
+        eng.x0.copy_(Xd[o:o + B]); eng.y_true.copy_(Yd[o:o + B])
+        eng.train_step(LR)
+    ev1.record()
+    barrier()
+    ms_dev = ev0.elapsed_time(ev1)
+
+    # ---- timed region 2: end to end from host buffers (pinned H2D + loss D2H every step)
+    loss_host = torch.zeros(6).pin_memory()
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    last = None
+    for i in range(args.steps):
+        o = (i % 2) * B
+        eng.load_batch(Xp[o:o + B], Yp[o:o + B])
+        loss6 = eng.train_step(LR)
+        loss_host.copy_(loss6, non_blocking=False)
+        last = float(loss_host[0])
+    ev3.record()
+    barrier()
+    ms_e2e = ev2.elapsed_time(ev3)
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+
+    total_imgs = B * world * args.steps
+    value = total_imgs / (ms_dev / 1e3)
+    e2e = total_imgs / (ms_e2e / 1e3)
+    peaks = load_peaks()
+
+    # ---- roofline of the dominant kernel family (live CUDA-event timing of eager steps)
+    eng.graph = None
+    hook, eng.grad_hook = eng.grad_hook, None  # time this rank's kernels only
+    fam, psteps = kernel_breakdown(eng, lib)
+    eng.grad_hook = hook
+    total_ms = sum(d["ms"] for d in fam.values())
+    share = sorted(((d["ms"] / total_ms, n, d["launches"] // psteps) for n, d in fam.items()), reverse=True)
+    breakdown = [{"kernel": n, "share": round(s, 4), "launches_per_step": l} for s, n, l in share[:12]]
+    groups = {"dwconv3x3": ("hbm", [n for n in fam if n.startswith("spnet_dwconv3x3")]),
+              "gemm_bf16": ("tensor", [n for n in fam if n == "spnet_gemm_bf16"])}
+    roofs = {}
+    for gname, (bound, names) in groups.items():
+        ms = sum(fam[n]["ms"] for n in names)
+        nb = nf = nl = 0
+        for n in names:
+            for a, _ in fam[n]["items"]:
+                b_, f_ = algorithmic_work(n, a)
+                nb += b_; nf += f_; nl += 1
+        if bound == "hbm":
+            ach = nb / (ms * 1e-3) / 1e9
+            roofs[gname] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                            "traffic": None, "kernel": gname + " fwd+dgrad+wgrad", "share_of_step": ms / total_ms,
+                            "launches": nl // psteps, "avg_launch_ms": ms / max(nl, 1), "algorithmic_bytes_per_step": nb // psteps}
+        else:
+            ach = nf / (ms * 1e-3) / 1e12
+            roofs[gname] = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                            "frac": ach / peaks["tf_sust"], "traffic": None, "kernel": "gemm_tc_kernel (tcgen05)",
+                            "share_of_step": ms / total_ms, "launches": nl // psteps, "avg_launch_ms": ms / max(nl, 1),
+                            "algorithmic_flops_per_step": nf // psteps}
+    dominant = max(roofs.values(), key=lambda r: r["share_of_step"])
+    other = [r for r in roofs.values() if r is not dominant]
+
+    # ---- CPU baseline on this box's host cores: bounded sample of the same workload
+    cpu = cpu_baseline()
+
+    out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "Xception-SPNet train step fwd+bwd+YOLO-ellipse loss+Keras Adam, 384x512x1, batch %d/GPU" % B,
+                      "global_batch": B * world, "parallelism": "dp%d" % world, "dropout": 0.1, "l2": 1e-4,
+                      "input_pool": "%d distinct gen_fake_espi-style frames per rank" % npool,
+                      "l2_cache": "per-step working set (activations, several GB) >> 126 MB L2; no explicit flush",
+                      "cuda_graph": True, "loss_last": last},
+           "clocks": clocks,
+           "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
+                   "h2d_bytes_per_step": int(B * (H * W * 4 + N_OUT * 4)), "d2h_bytes_per_step": 24},
+           "gpu_launches": int(launches_per_step * args.steps * 2),
+           "roofline": dominant, "roofline_other": other, "kernel_breakdown": breakdown,
+           "peaks": peaks, "cpu_baseline": cpu}
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline():
+    import torch
+    from oracle import xception_torch as xt
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    Bs = 4
+    X, Y = make_pool(Bs, 10_000)
+    model = xt.OracleSPNet(xt.init_weights(xt.xception_spnet_spec(H, W, N_OUT), seed=1), H, W)
+    ts = []
+    for i in range(3):
+        t0 = time.perf_counter()
+        _, _, _, grads = model.loss_and_grads(X, Y)
+        model.adam_step(grads, LR)
+        ts.append(time.perf_counter() - t0)
+    dt = float(np.mean(ts[1:]))
+    return {"value": Bs / dt, "unit": "images/s", "cores": ncores, "kind": "port",
+            "sample": "2 timed steps (1 warm-up) of %d images of the batch-64 workload, oracle torch-CPU fp32" % Bs}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.steps_ref = max(1, min(args.steps, 3))
+    args.warmup_ref = 1
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        dist.init_process_group("nccl")
+    run_ours(args, rank, world)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

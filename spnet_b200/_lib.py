@@ -64,6 +64,7 @@ class _Lib:
             fn.restype = restype
             fn.argtypes = argtypes
         self.launches = 0  # kernels launched through this binding (bench.py reports it)
+        self.profile = None  # list -> (name, args, start_event, end_event) per launch (bench.py)
 
     def last_error(self):
         return self._dll.spnet_last_error().decode()
@@ -76,7 +77,15 @@ class _Lib:
             return fn
 
         def call(*args):
-            rc = fn(*args)
+            if self.profile is not None:
+                import torch
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = fn(*args)
+                e1.record()
+                self.profile.append((full, args, e0, e1))
+            else:
+                rc = fn(*args)
             if rc != 0:
                 raise SpnetError("%s failed (%d): %s" % (full, rc, self.last_error()))
             self.launches += 1

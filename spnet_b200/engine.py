@@ -376,11 +376,11 @@ class XceptionSPNetEngine:
         # main branch
         g_y2 = ops.maxpool3s2_bwd(g_out, e["argmax"], H, W, out=self._view(G1, B, H, W, c))
         g_z2 = self._bn_bwd(g_y2, s2.z, s2.bn, M)
-        g_y1 = self._view(G3, B, H, W, c)
-        self._sep_bwd(s2, g_z2.view(M, c), s1.z, s1.bn, True, self._view(G2, M, c), g_y1)
+        g_y1 = self._view(G3, B, H, W, s2.cin)
+        self._sep_bwd(s2, g_z2.view(M, c), s1.z, s1.bn, True, self._view(G2, M, s2.cin), g_y1)
         g_z1 = self._bn_bwd(g_y1, s1.z, s1.bn, M)
         g_x = self._view(R, B, H, W, cin)
-        self._sep_bwd(s1, g_z1.view(M, c), x, None, e["relu_in"], self._view(G1, M, cin), g_x,
+        self._sep_bwd(s1, g_z1.view(M, s1.cout), x, None, e["relu_in"], self._view(G1, M, cin), g_x,
                       add_strided=g_xs.view(B, oh, ow, cin))
         return g_x
 
@@ -510,8 +510,10 @@ class XceptionSPNetEngine:
         else:
             self._step_body()
         if self.grad_hook is not None:
-            self.grad_hook(self)
-            self.optimizer_step()
+            self.skip_default_optimizer = False
+            self.grad_hook(self)          # e.g. multi_gpu.GradAllReduce (runs its own optimiser step)
+            if not self.skip_default_optimizer:
+                self.optimizer_step()
         return self.loss6
 
     def load_batch(self, x_host, y_host=None):
