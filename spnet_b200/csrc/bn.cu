@@ -46,34 +46,51 @@ __global__ void bn_inference_affine_kernel(const float* __restrict__ gamma, cons
     b[c] = (beta ? beta[c] : 0.0f) - mm[c] * aa;
 }
 
+// Channel-stationary mapping shared by the element-wise kernels below: a thread keeps one
+// 16-byte channel vector (its per-channel coefficients stay in registers) and walks rows with a
+// grid stride, UNROLL independent 16-byte loads in flight per tensor.
+constexpr int UNROLL = 4;
+
 // out = act(a*z + b) [+ x];  act: 0 none, 1 relu, 2 leaky-relu(0.1)
 template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* z, const float* __restrict__ a,
-                                                       const float* __restrict__ b, int act,
-                                                       const T* x, T* out,
-                                                       long long rows, int C) {
+                                                       const float* __restrict__ b, int act, const T* x, T* out,
+                                                       long long rows, int C, int cvb, int krows) {
     constexpr int V = VecN<T>::N;
     const int CV = C / V;
-    const long long n = rows * CV;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)(idx % CV) * V;
-        float v[V];
-        load_vec(z + idx * V, v);
+    const int cvl = threadIdx.x % cvb, rl = threadIdx.x / cvb;
+    const int cv = blockIdx.y * cvb + cvl;
+    if (cv >= CV) return;
+    const int c0 = cv * V;
+    float av[V], bv[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            float y = fmaf(v[i], a[c0 + i], b[c0 + i]);
-            if (act == 1) y = fmaxf(y, 0.f);
-            else if (act == 2) y = y > 0.f ? y : 0.1f * y;
-            v[i] = y;
-        }
-        if (x) {
-            float r[V];
-            load_vec(x + idx * V, r);
+    for (int i = 0; i < V; ++i) { av[i] = a[c0 + i]; bv[i] = b[c0 + i]; }
+    const long long stride = (long long)gridDim.x * krows;
+    for (long long r0 = (long long)blockIdx.x * krows + rl; r0 < rows; r0 += stride * UNROLL) {
+        float v[UNROLL][V], xr[UNROLL][V];
 #pragma unroll
-            for (int i = 0; i < V; ++i) v[i] += r[i];
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long r = r0 + u * stride;
+            if (r < rows) {
+                load_vec(z + r * C + c0, v[u]);
+                if (x) load_vec(x + r * C + c0, xr[u]);
+            }
         }
-        store_vec(out + idx * V, v);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long r = r0 + u * stride;
+            if (r < rows) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    float y = fmaf(v[u][i], av[i], bv[i]);
+                    if (act == 1) y = fmaxf(y, 0.f);
+                    else if (act == 2) y = y > 0.f ? y : 0.1f * y;
+                    if (x) y += xr[u][i];
+                    v[u][i] = y;
+                }
+                store_vec(out + r * C + c0, v[u]);
+            }
+        }
     }
 }
 
@@ -106,25 +123,37 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(T* __restrict__ g, c
             ra[i] = relu_a ? relu_a[c0 + i] : 0.f;
             rb[i] = relu_a ? relu_b[c0 + i] : 0.f;
         }
-        for (long long r = (long long)blockIdx.x * krows + rl; r < rows; r += (long long)gridDim.x * krows) {
-            float gv[V], zv[V];
-            load_vec(g + r * C + c0, gv);
-            load_vec(z + r * C + c0, zv);
-            if (relu_a) {
+        const long long stride = (long long)gridDim.x * krows;
+        for (long long r0 = (long long)blockIdx.x * krows + rl; r0 < rows; r0 += stride * UNROLL) {
+            float gv[UNROLL][V], zv[UNROLL][V];
 #pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    const float y = fmaf(zv[i], ra[i], rb[i]);
-                    if (!(y > 0.f)) gv[i] = (act == 2) ? 0.1f * gv[i] : 0.f;
+            for (int u = 0; u < UNROLL; ++u) {
+                const long long r = r0 + u * stride;
+                if (r < rows) {
+                    load_vec(g + r * C + c0, gv[u]);
+                    load_vec(z + r * C + c0, zv[u]);
                 }
-                store_vec(g + r * C + c0, gv);
-                // sums use the value as it will be re-read
-#pragma unroll
-                for (int i = 0; i < V; ++i) gv[i] = round_to<T>(gv[i]);
             }
 #pragma unroll
-            for (int i = 0; i < V; ++i) {
-                s1[i] += gv[i];
-                s2[i] = fmaf(gv[i], (zv[i] - mu[i]) * rs[i], s2[i]);
+            for (int u = 0; u < UNROLL; ++u) {
+                const long long r = r0 + u * stride;
+                if (r >= rows) continue;
+                if (relu_a) {
+#pragma unroll
+                    for (int i = 0; i < V; ++i) {
+                        const float y = fmaf(zv[u][i], ra[i], rb[i]);
+                        if (!(y > 0.f)) gv[u][i] = (act == 2) ? 0.1f * gv[u][i] : 0.f;
+                    }
+                    store_vec(g + r * C + c0, gv[u]);
+                    // sums use the value as it will be re-read
+#pragma unroll
+                    for (int i = 0; i < V; ++i) gv[u][i] = round_to<T>(gv[u][i]);
+                }
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    s1[i] += gv[u][i];
+                    s2[i] = fmaf(gv[u][i], (zv[u][i] - mu[i]) * rs[i], s2[i]);
+                }
             }
         }
     }
@@ -160,31 +189,66 @@ __global__ void bn_bwd_finalize_kernel(double* __restrict__ stats, double count,
     c2[c] = (float)(sgx / count);
 }
 
-// out = a * (g - c1 - xhat*c2)
+// out = a * (g - c1 - xhat*c2) = A*g + Bz*z + D with per-channel A = a, Bz = -a*rstd*c2,
+// D = a*(rstd*c2*mean - c1)
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const T* g, const T* __restrict__ z,
                                                         const float* __restrict__ a,
                                                         const float* __restrict__ mean,
                                                         const float* __restrict__ rstd,
                                                         const float* __restrict__ c1,
-                                                        const float* __restrict__ c2, T* out,
-                                                        long long rows, int C) {
+                                                        const float* __restrict__ c2, T* out, long long rows, int C,
+                                                        int cvb, int krows) {
     constexpr int V = VecN<T>::N;
     const int CV = C / V;
-    const long long n = rows * CV;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)(idx % CV) * V;
-        float gv[V], zv[V];
-        load_vec(g + idx * V, gv);
-        load_vec(z + idx * V, zv);
+    const int cvl = threadIdx.x % cvb, rl = threadIdx.x / cvb;
+    const int cv = blockIdx.y * cvb + cvl;
+    if (cv >= CV) return;
+    const int c0 = cv * V;
+    float A[V], Bz[V], D[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            const float xh = (zv[i] - mean[c0 + i]) * rstd[c0 + i];
-            gv[i] = a[c0 + i] * (gv[i] - c1[c0 + i] - xh * c2[c0 + i]);
-        }
-        store_vec(out + idx * V, gv);
+    for (int i = 0; i < V; ++i) {
+        const float aa = a[c0 + i], k = rstd[c0 + i] * c2[c0 + i];
+        A[i] = aa;
+        Bz[i] = -aa * k;
+        D[i] = aa * (k * mean[c0 + i] - c1[c0 + i]);
     }
+    const long long stride = (long long)gridDim.x * krows;
+    for (long long r0 = (long long)blockIdx.x * krows + rl; r0 < rows; r0 += stride * UNROLL) {
+        float gv[UNROLL][V], zv[UNROLL][V];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long r = r0 + u * stride;
+            if (r < rows) {
+                load_vec(g + r * C + c0, gv[u]);
+                load_vec(z + r * C + c0, zv[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long r = r0 + u * stride;
+            if (r < rows) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) gv[u][i] = fmaf(gv[u][i], A[i], fmaf(zv[u][i], Bz[i], D[i]));
+                store_vec(out + r * C + c0, gv[u]);
+            }
+        }
+    }
+}
+
+struct ChanGrid { int cvb, krows; dim3 grid; };
+static ChanGrid chan_grid(int CV, long long rows, int waves) {
+    ChanGrid c;
+    const int nchunks = ceil_div(CV, 128);
+    c.cvb = ceil_div(CV, nchunks);
+    c.krows = 256 / c.cvb;
+    if (c.krows < 1) c.krows = 1;
+    long long gx = (rows + c.krows - 1) / c.krows;
+    const long long cap = (148LL * waves + nchunks - 1) / nchunks;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    c.grid = dim3((unsigned)gx, nchunks);
+    return c;
 }
 
 int check_rc(const char* who, int dtype, long long rows, int C) {
@@ -192,12 +256,6 @@ int check_rc(const char* who, int dtype, long long rows, int C) {
     const int V = dtype == SPNET_BF16 ? 8 : 4;
     SPNET_REQUIRE(C % V == 0, "%s: C=%d must be a multiple of %d", who, C, V);
     return SPNET_OK;
-}
-
-int ew_grid(long long n) {
-    long long g = (n + 255) / 256;
-    const long long cap = 148LL * 16;
-    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
 }  // namespace
@@ -230,9 +288,10 @@ int spnet_bn_apply(const void* z, const float* a, const float* b, int act, const
     int rc = check_rc("bn_apply", dtype, rows, C);
     if (rc) return rc;
     SPNET_REQUIRE(z && a && b && out && act >= 0 && act <= 2, "bn_apply: bad args");
-    SPNET_DISPATCH_DTYPE(dtype, (bn_apply_kernel<T><<<ew_grid(rows * (C / VecN<T>::N)), 256, 0, stream>>>(
+    const ChanGrid cg = chan_grid(C / (dtype == SPNET_BF16 ? 8 : 4), rows, 8);
+    SPNET_DISPATCH_DTYPE(dtype, (bn_apply_kernel<T><<<cg.grid, cg.cvb * cg.krows, 0, stream>>>(
                                     reinterpret_cast<const T*>(z), a, b, act, reinterpret_cast<const T*>(x),
-                                    reinterpret_cast<T*>(out), rows, C)));
+                                    reinterpret_cast<T*>(out), rows, C, cg.cvb, cg.krows)));
     return spnet_check_launch("bn_apply");
 }
 
@@ -273,9 +332,10 @@ int spnet_bn_bwd_dz(const void* g, const void* z, const float* a, const float* s
     int rc = check_rc("bn_bwd_dz", dtype, rows, C);
     if (rc) return rc;
     SPNET_REQUIRE(g && z && a && save_mean && save_rstd && c1 && c2 && out, "bn_bwd_dz: null pointer");
-    SPNET_DISPATCH_DTYPE(dtype, (bn_bwd_dz_kernel<T><<<ew_grid(rows * (C / VecN<T>::N)), 256, 0, stream>>>(
+    const ChanGrid cg = chan_grid(C / (dtype == SPNET_BF16 ? 8 : 4), rows, 8);
+    SPNET_DISPATCH_DTYPE(dtype, (bn_bwd_dz_kernel<T><<<cg.grid, cg.cvb * cg.krows, 0, stream>>>(
                                     reinterpret_cast<const T*>(g), reinterpret_cast<const T*>(z), a, save_mean,
-                                    save_rstd, c1, c2, reinterpret_cast<T*>(out), rows, C)));
+                                    save_rstd, c1, c2, reinterpret_cast<T*>(out), rows, C, cg.cvb, cg.krows)));
     return spnet_check_launch("bn_bwd_dz");
 }
 

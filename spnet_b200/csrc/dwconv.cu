@@ -9,7 +9,7 @@
 // training the producer's BatchNorm can only be applied once its batch statistics
 // exist, so BN-apply (per-channel affine) + ReLU are fused on the LOAD side here;
 // zero padding is applied after that transform, as TF does.
-#include "common.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -22,104 +22,183 @@ struct DwEpilogue {
     const void* add_strided; // [B,ceil(H/2),ceil(W/2),C] added at even (h,w) after masking
 };
 
-template <typename T, bool AFFINE, bool RELU, bool FLIP>
-__global__ void __launch_bounds__(256) dw3x3_kernel(const T* __restrict__ in, const float* __restrict__ k,
-                                                    const float* __restrict__ in_a,
-                                                    const float* __restrict__ in_b, T* __restrict__ out, int B,
-                                                    int H, int W, int C, int R, int nstrips, DwEpilogue ep) {
-    constexpr int V = VecN<T>::N;
-    const int CV = C / V;
-    const long long total = (long long)B * nstrips * W * CV;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int cv = (int)(idx % CV);
-    long long r = idx / CV;
-    const int w = (int)(r % W);
-    r /= W;
-    const int strip = (int)(r % nstrips);
-    const int b = (int)(r / nstrips);
-    const int c0 = cv * V;
-    const int h0 = strip * R;
-    const int h1 = min(H, h0 + R);
+// ---- 4-channel group access (8 B for bf16, 16 B for fp32) --------------------------------------
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+    const float4 r = *reinterpret_cast<const float4*>(p);
+    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float (&v)[4]) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+__device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+}
 
-    float wt[9][V];
+constexpr int DW_CB = 64;   // channels per CTA (one TMA box is CB channels wide)
+constexpr int DW_G = 4;     // channels per thread
+
+// Forward / data-gradient kernel. A persistent CTA owns one 64-channel chunk (blockIdx.y) and
+// walks (image, row-tile, col-tile) tiles; each input tile INCLUDING its 1-pixel halo is fetched
+// by ONE TMA box load ({64 ch, TW+2, TH+2, 1}; out-of-image halo is zero-filled by the TMA unit)
+// into a double-buffered shared-memory stage, so the next tile streams in while the current one
+// is computed. Thread = (4-channel group, 2 adjacent output columns); it slides down the rows
+// with three running accumulators per column, reading each staged input vector once per row.
+template <typename T, bool AFFINE, bool RELU, bool FLIP>
+__global__ void __launch_bounds__(256) dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
+                                                        const float* __restrict__ k,
+                                                        const float* __restrict__ in_a,
+                                                        const float* __restrict__ in_b, T* __restrict__ out, int B,
+                                                        int H, int W, int C, int TH, int TW, int tiles_h,
+                                                        int tiles_w, DwEpilogue ep) {
+    constexpr int G = DW_G, CB = DW_CB;
+    extern __shared__ uint8_t dw_smem_raw[];
+    T* smem = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~(uintptr_t)127);
+    __shared__ __align__(8) uint64_t bars[2];
+    const int cg = threadIdx.x & 15, colg = threadIdx.x >> 4;
+    const int cbase = blockIdx.y * CB;
+    const int c0 = cbase + cg * G;
+    const bool c_ok = c0 < C;
+    const int TWH = TW + 2;
+    const int tile_elems = (TH + 2) * TWH * CB;
+    const uint32_t tile_bytes = (uint32_t)tile_elems * sizeof(T);
+    const int n_tiles = B * tiles_h * tiles_w;
+
+    float wt[9][G], av[G], bv[G];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
         const int ts = FLIP ? 8 - t : t;
 #pragma unroll
-        for (int i = 0; i < V; ++i) wt[t][i] = k[ts * C + c0 + i];
+        for (int i = 0; i < G; ++i) wt[t][i] = c_ok ? k[ts * C + c0 + i] : 0.f;
     }
-    float a[V], bb[V];
-    if (AFFINE) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) { a[i] = in_a[c0 + i]; bb[i] = in_b[c0 + i]; }
+    for (int i = 0; i < G; ++i) {
+        av[i] = (AFFINE && c_ok) ? in_a[c0 + i] : 1.f;
+        bv[i] = (AFFINE && c_ok) ? in_b[c0 + i] : 0.f;
     }
-    float accA[V], accB[V], accC[V];
-#pragma unroll
-    for (int i = 0; i < V; ++i) { accA[i] = 0.f; accB[i] = 0.f; accC[i] = 0.f; }
+    const uint32_t bar0 = smem_u32(&bars[0]);
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
 
-    const size_t img = (size_t)b * H * W;
-    for (int ih = h0 - 1; ih <= h1; ++ih) {
-        const bool rowok = ih >= 0 && ih < H;
-        float x[3][V];
+    auto issue = [&](int tile, int bufi) {
+        const int tw = tile % tiles_w;
+        const int th = (tile / tiles_w) % tiles_h;
+        const int b = tile / (tiles_w * tiles_h);
+        mbar_expect_tx(bar0 + 8 * bufi, tile_bytes);
+        tma_load_4d(smem_u32(smem + (size_t)bufi * tile_elems), &tm_in, bar0 + 8 * bufi, cbase, tw * TW - 1, th * TH - 1, b);
+    };
+    if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int cur = it & 1;
+        const int nxt = tile + gridDim.x;
+        if (threadIdx.x == 0 && nxt < n_tiles) issue(nxt, cur ^ 1);
+        mbar_wait(bar0 + 8 * cur, (uint32_t)(it >> 1) & 1u);
+
+        const int tw = tile % tiles_w;
+        const int th = (tile / tiles_w) % tiles_h;
+        const int b = tile / (tiles_w * tiles_h);
+        const int h0 = th * TH, w0 = tw * TW;
+        const int h1 = min(H, h0 + TH);
+        const int col0 = colg * 2;
+        bool colok[4];
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-            const int iw = w - 1 + kw;
-            if (rowok && iw >= 0 && iw < W) {
-                load_vec(in + (img + (size_t)ih * W + iw) * C + c0, x[kw]);
+        for (int j = 0; j < 4; ++j) {
+            const int iw = w0 - 1 + col0 + j;
+            colok[j] = iw >= 0 && iw < W;
+        }
+        const T* tb = smem + (size_t)cur * tile_elems + cg * G;
+        float acc[3][2][G];
 #pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    float v = x[kw][i];
-                    if (AFFINE) v = fmaf(v, a[i], bb[i]);
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+                for (int i = 0; i < G; ++i) acc[q][oc][i] = 0.f;
+        const size_t img = (size_t)b * H * W;
+        const int rows = min(TH, H - h0) + 2;
+        for (int r = 0; r < rows; ++r) {
+            const int ih = h0 - 1 + r;
+            const bool rowok = ih >= 0 && ih < H;
+            float x[4][G];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                load4(tb + (size_t)(r * TWH + col0 + j) * CB, x[j]);
+                const bool ok = rowok && colok[j];
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    float v = x[j][i];
+                    if (AFFINE) v = fmaf(v, av[i], bv[i]);
                     if (RELU) v = fmaxf(v, 0.f);
-                    x[kw][i] = v;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < V; ++i) x[kw][i] = 0.f;
-            }
-        }
-        // input row ih is tap row 2 of output ih-1, row 1 of output ih, row 0 of output ih+1
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-#pragma unroll
-            for (int i = 0; i < V; ++i) {
-                accA[i] = fmaf(x[kw][i], wt[6 + kw][i], accA[i]);
-                accB[i] = fmaf(x[kw][i], wt[3 + kw][i], accB[i]);
-                accC[i] = fmaf(x[kw][i], wt[0 + kw][i], accC[i]);
-            }
-        }
-        const int oh = ih - 1;
-        if (oh >= h0 && oh < h1) {
-            const size_t o = (img + (size_t)oh * W + w) * C + c0;
-            if (ep.mask_src) {
-                float m[V];
-                load_vec(reinterpret_cast<const T*>(ep.mask_src) + o, m);
-#pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    float v = m[i];
-                    if (ep.mask_a) v = fmaf(v, ep.mask_a[c0 + i], ep.mask_b[c0 + i]);
-                    if (!(v > 0.f)) accA[i] = 0.f;
+                    x[j][i] = (AFFINE && !ok) ? 0.f : v;  // zero padding applies AFTER the BN/ReLU transform
                 }
             }
-            if (ep.add_src) {
-                float m[V];
-                load_vec(reinterpret_cast<const T*>(ep.add_src) + o, m);
 #pragma unroll
-                for (int i = 0; i < V; ++i) accA[i] += m[i];
-            }
-            if (ep.add_strided && ((oh | w) & 1) == 0) {
-                const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
-                float m[V];
-                load_vec(reinterpret_cast<const T*>(ep.add_strided) +
-                             (((size_t)b * H2 + (oh >> 1)) * W2 + (w >> 1)) * C + c0, m);
+            for (int oc = 0; oc < 2; ++oc)
 #pragma unroll
-                for (int i = 0; i < V; ++i) accA[i] += m[i];
+                for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                    for (int i = 0; i < G; ++i) {
+                        acc[0][oc][i] = fmaf(x[oc + kw][i], wt[6 + kw][i], acc[0][oc][i]);
+                        acc[1][oc][i] = fmaf(x[oc + kw][i], wt[3 + kw][i], acc[1][oc][i]);
+                        acc[2][oc][i] = fmaf(x[oc + kw][i], wt[0 + kw][i], acc[2][oc][i]);
+                    }
+            const int oh = ih - 1;
+            if (oh >= h0 && oh < h1 && c_ok) {
+#pragma unroll
+                for (int oc = 0; oc < 2; ++oc) {
+                    const int ow = w0 + col0 + oc;
+                    if (ow >= W) continue;
+                    const size_t o = (img + (size_t)oh * W + ow) * C + c0;
+                    float res[G];
+#pragma unroll
+                    for (int i = 0; i < G; ++i) res[i] = acc[0][oc][i];
+                    if (ep.mask_src) {
+                        float m[G];
+                        load4(reinterpret_cast<const T*>(ep.mask_src) + o, m);
+#pragma unroll
+                        for (int i = 0; i < G; ++i) {
+                            float v = m[i];
+                            if (ep.mask_a) v = fmaf(v, ep.mask_a[c0 + i], ep.mask_b[c0 + i]);
+                            if (!(v > 0.f)) res[i] = 0.f;
+                        }
+                    }
+                    if (ep.add_src) {
+                        float m[G];
+                        load4(reinterpret_cast<const T*>(ep.add_src) + o, m);
+#pragma unroll
+                        for (int i = 0; i < G; ++i) res[i] += m[i];
+                    }
+                    if (ep.add_strided && ((oh | ow) & 1) == 0) {
+                        const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
+                        float m[G];
+                        load4(reinterpret_cast<const T*>(ep.add_strided) +
+                                  (((size_t)b * H2 + (oh >> 1)) * W2 + (ow >> 1)) * C + c0, m);
+#pragma unroll
+                        for (int i = 0; i < G; ++i) res[i] += m[i];
+                    }
+                    store4(out + o, res);
+                }
             }
-            store_vec(out + o, accA);
+#pragma unroll
+            for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    acc[0][oc][i] = acc[1][oc][i];
+                    acc[1][oc][i] = acc[2][oc][i];
+                    acc[2][oc][i] = 0.f;
+                }
         }
-#pragma unroll
-        for (int i = 0; i < V; ++i) { accA[i] = accB[i]; accB[i] = accC[i]; accC[i] = 0.f; }
+        __syncthreads();  // every thread is done with buffer `cur` before it is refilled
     }
 }
 
@@ -227,25 +306,82 @@ static void pick_strips(int B, int H, int W, int CV, int* R, int* nstrips) {
     *nstrips = ceil_div(H, r);
 }
 
+static int make_nhwc_map(CUtensorMap* map, const void* ptr, int dtype, int B, int H, int W, int C, int box_w, int box_h) {
+    PFN_cuTensorMapEncodeTiled enc = spnet_get_tensormap_encoder();
+    if (!enc) {
+        spnet_set_error("dwconv3x3: cuTensorMapEncodeTiled entry point not available");
+        return SPNET_ERR_CUDA;
+    }
+    const cuuint64_t es = dtype == SPNET_BF16 ? 2 : 4;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+    cuuint32_t box[4] = {(cuuint32_t)DW_CB, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, dtype == SPNET_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                     const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        spnet_set_error("dwconv3x3: cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d]", (int)r, B, H, W, C);
+        return SPNET_ERR_CUDA;
+    }
+    return SPNET_OK;
+}
+
+struct DwTiling { int TH, TW, tiles_h, tiles_w, threads, chunks, grid_x; size_t smem; };
+static DwTiling dw_tiling(int dtype, int B, int H, int W, int C) {
+    DwTiling t;
+    t.TW = W > 16 ? 32 : (W > 8 ? 16 : 8);
+    t.TH = H <= 12 ? H : 8;
+    t.tiles_h = ceil_div(H, t.TH);
+    t.tiles_w = ceil_div(W, t.TW);
+    t.threads = 16 * (t.TW / 2);
+    t.chunks = ceil_div(C, DW_CB);
+    const size_t es = dtype == SPNET_BF16 ? 2 : 4;
+    t.smem = 2 * (size_t)(t.TH + 2) * (t.TW + 2) * DW_CB * es + 128;
+    int per_sm = 768 / t.threads;
+    const int by_smem = (int)((220 * 1024) / t.smem);
+    if (per_sm > by_smem) per_sm = by_smem;
+    if (per_sm < 1) per_sm = 1;
+    const long long n_tiles = (long long)B * t.tiles_h * t.tiles_w;
+    long long gx = (148LL * per_sm + t.chunks - 1) / t.chunks;
+    if (gx > n_tiles) gx = n_tiles;
+    if (gx < 1) gx = 1;
+    t.grid_x = (int)gx;
+    return t;
+}
+
+template <typename T, bool AF, bool RL, bool FL>
+int launch_dw_inst(const CUtensorMap& tm, const float* k, const float* in_a, const float* in_b, T* y, int B, int H,
+                   int W, int C, const DwTiling& t, DwEpilogue ep, cudaStream_t stream) {
+    auto kern = dw3x3_tma_kernel<T, AF, RL, FL>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) {
+            spnet_set_error("dwconv3x3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return SPNET_ERR_CUDA;
+        }
+        configured = true;
+    }
+    dim3 grid(t.grid_x, t.chunks);
+    kern<<<grid, t.threads, t.smem, stream>>>(tm, k, in_a, in_b, y, B, H, W, C, t.TH, t.TW, t.tiles_h, t.tiles_w, ep);
+    return spnet_check_launch("dw3x3");
+}
+
 template <typename T>
 int launch_dw(const void* in, const float* k, const float* in_a, const float* in_b, int relu, int flip,
-              void* out, int B, int H, int W, int C, DwEpilogue ep, cudaStream_t stream) {
-    constexpr int V = VecN<T>::N;
-    int R, nstrips;
-    pick_strips(B, H, W, C / V, &R, &nstrips);
-    const long long total = (long long)B * nstrips * W * (C / V);
-    const int grid = ceil_div(total, 256);
-    const T* x = reinterpret_cast<const T*>(in);
+              void* out, int dtype, int B, int H, int W, int C, DwEpilogue ep, cudaStream_t stream) {
+    const DwTiling t = dw_tiling(dtype, B, H, W, C);
+    SPNET_REQUIRE(t.smem <= 200 * 1024, "dwconv3x3: tile does not fit shared memory");
+    CUtensorMap tm;
+    int rc = make_nhwc_map(&tm, in, dtype, B, H, W, C, t.TW + 2, t.TH + 2);
+    if (rc) return rc;
     T* y = reinterpret_cast<T*>(out);
-#define DW_LAUNCH(AF, RL, FL) \
-    dw3x3_kernel<T, AF, RL, FL><<<grid, 256, 0, stream>>>(x, k, in_a, in_b, y, B, H, W, C, R, nstrips, ep)
-    if (flip) { DW_LAUNCH(false, false, true); }
-    else if (in_a && relu) { DW_LAUNCH(true, true, false); }
-    else if (in_a) { DW_LAUNCH(true, false, false); }
-    else if (relu) { DW_LAUNCH(false, true, false); }
-    else { DW_LAUNCH(false, false, false); }
-#undef DW_LAUNCH
-    return spnet_check_launch("dw3x3");
+    if (flip) return launch_dw_inst<T, false, false, true>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
+    if (in_a && relu) return launch_dw_inst<T, true, true, false>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
+    if (in_a) return launch_dw_inst<T, true, false, false>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
+    if (relu) return launch_dw_inst<T, false, true, false>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
+    return launch_dw_inst<T, false, false, false>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
 }
 
 template <typename T>
@@ -297,7 +433,7 @@ int spnet_dwconv3x3_fwd(const void* in, const float* k, const float* in_a, const
     if (rc) return rc;
     SPNET_REQUIRE(k && ((in_a == nullptr) == (in_b == nullptr)), "dwconv3x3_fwd: bad weight/affine pointers");
     DwEpilogue ep = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    SPNET_DISPATCH_DTYPE(dtype, return launch_dw<T>(in, k, in_a, in_b, relu, 0, out, B, H, W, C, ep, stream));
+    SPNET_DISPATCH_DTYPE(dtype, return launch_dw<T>(in, k, in_a, in_b, relu, 0, out, dtype, B, H, W, C, ep, stream));
 }
 
 // gin = dw3x3^T(gout) [* (mask_a*mask_src+mask_b > 0)] [+ add_src] [+ add_strided at even (h,w)]
@@ -310,7 +446,7 @@ int spnet_dwconv3x3_dgrad(const void* gout, const float* k, void* gin, const voi
     SPNET_REQUIRE(k && ((mask_a == nullptr) == (mask_b == nullptr)), "dwconv3x3_dgrad: bad pointers");
     SPNET_REQUIRE(mask_src || !mask_a, "dwconv3x3_dgrad: mask affine without mask_src");
     DwEpilogue ep = {mask_src, mask_a, mask_b, add_src, add_strided};
-    SPNET_DISPATCH_DTYPE(dtype, return launch_dw<T>(gout, k, nullptr, nullptr, 0, 1, gin, B, H, W, C, ep, stream));
+    SPNET_DISPATCH_DTYPE(dtype, return launch_dw<T>(gout, k, nullptr, nullptr, 0, 1, gin, dtype, B, H, W, C, ep, stream));
 }
 
 // dk[3,3,C] += sum act(in) (*) gout     (dk fp32, accumulated with atomics: zero it first)

@@ -16,9 +16,7 @@
 //
 // Epilogue modes: store bf16, store fp32, atomic-add fp32 (split-K); optional fused
 // per-column sum / sum-of-squares (BatchNorm batch statistics) accumulated in fp64.
-#include "common.cuh"
-#include <cuda.h>
-#include <cudaTypedefs.h>
+#include "tma.cuh"
 
 namespace {
 
@@ -36,39 +34,6 @@ struct GemmEpi {
     double* colstats;  // [2*N] (sum, sumsq) or nullptr
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Bounded wait: a lost arrive turns into a trap (reported as a launch failure) instead of a hang.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    long long t0 = 0;
-    for (uint32_t spins = 0; !ok; ++spins) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (!ok && (spins & 1023u) == 1023u) {
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000LL) __trap();  // ~2 s at 2 GHz
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
@@ -141,8 +106,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
             mbar_init(empty0 + 8 * s, 1);
         }
         mbar_init(tfull, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_fence_init();
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -300,22 +264,10 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
-PFN_cuTensorMapEncodeTiled get_encode() {
-    static PFN_cuTensorMapEncodeTiled fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
-    }
-    return fn;
-}
-
 // operand with `rows` along M/N and `kdim` along K; ld in elements
 int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long long kdim, long long ld, bool mn_major,
                      int tile_rows) {
-    PFN_cuTensorMapEncodeTiled enc = get_encode();
+    PFN_cuTensorMapEncodeTiled enc = spnet_get_tensormap_encoder();
     if (!enc) {
         spnet_set_error("gemm_bf16: cuTensorMapEncodeTiled entry point not available");
         return SPNET_ERR_CUDA;
