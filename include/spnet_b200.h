@@ -55,6 +55,7 @@ int spnet_decode_detections(const float* y, const float* means, const float* ran
 /* ---- SeparableConv2D depthwise half (keras.applications.Xception; spnet/models.py:359) ---- */
 int spnet_dwconv3x3_fwd(const void* in, const float* k, const float* in_a, const float* in_b, int relu, void* out, int dtype, int B, int H, int W, int C, cudaStream_t stream);
 int spnet_dwconv3x3_dgrad(const void* gout, const float* k, void* gin, const void* mask_src, const float* mask_a, const float* mask_b, const void* add_src, const void* add_strided, int dtype, int B, int H, int W, int C, cudaStream_t stream);
+int spnet_dwconv3x3_bwd_fused(const void* gout, const void* in, const float* k, const float* in_a, const float* in_b, int relu, const float* bn_mean, const float* bn_rstd, double* stats, const void* add_src, const void* add_strided, void* gin, float* dk, int dtype, int B, int H, int W, int C, cudaStream_t stream);
 int spnet_dwconv3x3_wgrad(const void* in, const void* gout, const float* in_a, const float* in_b, int relu, float* dk, int dtype, int B, int H, int W, int C, cudaStream_t stream);
 
 /* ---- GEMMs: pointwise 1x1, strided 1x1 residual convs, block1_conv2 (im2col), Dense head

@@ -202,6 +202,233 @@ __global__ void __launch_bounds__(256) dw3x3_tma_kernel(const __grid_constant__ 
     }
 }
 
+// Fused backward of the depthwise stage: one pass produces
+//   gin   = dw3x3^T(gout) * relu'(in_a*in+in_b)  [+ add_src] [+ add_strided at even (h,w)]
+//   dk   += sum act(in)[h+kh-1, w+kw-1] * gout[h, w]                      (weight gradient)
+//   stats += (sum gin, sum gin * xhat),  xhat = (in - mean)*rstd          (BatchNorm backward sums
+//            of the BN that produced `in`; only when stats != nullptr)
+// so the gradient tile (TMA, with halo) and the input tensor are each read once and the masked
+// gradient is written once — 3 tensor passes instead of the 8 that separate dgrad / wgrad /
+// bn_bwd_reduce kernels need. Both gradients use the SAME 3x3 neighbourhood of gout around a
+// pixel: dgrad = sum_n gout_n * k_n,  dk_n += act(in)(pixel) * gout_n.
+template <typename T, bool AFFINE, bool RELU>
+__global__ void __launch_bounds__(256, 1) dw3x3_bwd_fused_kernel(
+    const __grid_constant__ CUtensorMap tm_g, const T* __restrict__ in, const float* __restrict__ k,
+    const float* __restrict__ in_a, const float* __restrict__ in_b, const float* __restrict__ bn_mean,
+    const float* __restrict__ bn_rstd, double* __restrict__ stats, T* __restrict__ gin, float* __restrict__ dk, int B,
+    int H, int W, int C, int TH, int TW, int tiles_h, int tiles_w, DwEpilogue ep) {
+    constexpr int G = DW_G, CB = DW_CB;
+    extern __shared__ uint8_t dw_smem_raw[];
+    T* smem = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~(uintptr_t)127);
+    __shared__ __align__(8) uint64_t bars[2];
+    const int cg = threadIdx.x & 15, colg = threadIdx.x >> 4;
+    const int ncolg = blockDim.x >> 4;
+    const int cbase = blockIdx.y * CB;
+    const int c0 = cbase + cg * G;
+    const bool c_ok = c0 < C;
+    const int TWH = TW + 2;
+    const int tile_elems = (TH + 2) * TWH * CB;
+    const uint32_t tile_bytes = (uint32_t)tile_elems * sizeof(T);
+    const int n_tiles = B * tiles_h * tiles_w;
+
+    float wt[9][G], av[G], bv[G], mu[G], rs[G];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < G; ++i) wt[t][i] = c_ok ? k[(8 - t) * C + c0 + i] : 0.f;  // flipped: data gradient
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+        av[i] = (AFFINE && c_ok) ? in_a[c0 + i] : 1.f;
+        bv[i] = (AFFINE && c_ok) ? in_b[c0 + i] : 0.f;
+        mu[i] = (stats && c_ok) ? bn_mean[c0 + i] : 0.f;
+        rs[i] = (stats && c_ok) ? bn_rstd[c0 + i] : 0.f;
+    }
+    float dkacc[9][G], s1[G], s2[G];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < G; ++i) dkacc[t][i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < G; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+
+    const uint32_t bar0 = smem_u32(&bars[0]);
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int tile, int bufi) {
+        const int tw = tile % tiles_w;
+        const int th = (tile / tiles_w) % tiles_h;
+        const int b = tile / (tiles_w * tiles_h);
+        mbar_expect_tx(bar0 + 8 * bufi, tile_bytes);
+        tma_load_4d(smem_u32(smem + (size_t)bufi * tile_elems), &tm_g, bar0 + 8 * bufi, cbase, tw * TW - 1, th * TH - 1, b);
+    };
+    if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int cur = it & 1;
+        const int nxt = tile + gridDim.x;
+        if (threadIdx.x == 0 && nxt < n_tiles) issue(nxt, cur ^ 1);
+
+        const int tw = tile % tiles_w;
+        const int th = (tile / tiles_w) % tiles_h;
+        const int b = tile / (tiles_w * tiles_h);
+        const int h0 = th * TH, w0 = tw * TW;
+        const int h1 = min(H, h0 + TH);
+        const int col0 = colg * 2;
+        const size_t img = (size_t)b * H * W;
+        bool own[2];
+#pragma unroll
+        for (int oc = 0; oc < 2; ++oc) own[oc] = c_ok && (w0 + col0 + oc) < W;
+
+        // act(in) for an owned centre pixel row (zero for rows/cols this tile does not own)
+        auto load_v = [&](int row, float (&v)[2][G]) {
+            const bool rok = row >= h0 && row < h1;
+#pragma unroll
+            for (int oc = 0; oc < 2; ++oc) {
+                if (rok && own[oc]) {
+                    load4(in + (img + (size_t)row * W + (w0 + col0 + oc)) * C + c0, v[oc]);
+#pragma unroll
+                    for (int i = 0; i < G; ++i) {
+                        float y = v[oc][i];
+                        if (AFFINE) y = fmaf(y, av[i], bv[i]);
+                        if (RELU) y = fmaxf(y, 0.f);
+                        v[oc][i] = y;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < G; ++i) v[oc][i] = 0.f;
+                }
+            }
+        };
+        // v window: rows gh-1, gh, gh+1 around the current gradient row gh (starts at gh = h0-1)
+        float vw[3][2][G];
+#pragma unroll
+        for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+            for (int i = 0; i < G; ++i) { vw[0][oc][i] = 0.f; vw[1][oc][i] = 0.f; }
+        load_v(h0, vw[2]);
+
+        mbar_wait(bar0 + 8 * cur, (uint32_t)(it >> 1) & 1u);
+        const T* tb = smem + (size_t)cur * tile_elems + cg * G;
+        float acc[3][2][G];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+                for (int i = 0; i < G; ++i) acc[q][oc][i] = 0.f;
+        const int rows = (h1 - h0) + 2;
+        for (int r = 0; r < rows; ++r) {
+            const int gh = h0 - 1 + r;
+            float vnext[2][G];
+            load_v(gh + 2, vnext);  // prefetch: needed by the next iteration
+            float x[4][G];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) load4(tb + (size_t)(r * TWH + col0 + j) * CB, x[j]);
+            // data gradient: gradient row gh feeds outputs gh-1, gh, gh+1 (flipped taps)
+#pragma unroll
+            for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                    for (int i = 0; i < G; ++i) {
+                        acc[0][oc][i] = fmaf(x[oc + kw][i], wt[6 + kw][i], acc[0][oc][i]);
+                        acc[1][oc][i] = fmaf(x[oc + kw][i], wt[3 + kw][i], acc[1][oc][i]);
+                        acc[2][oc][i] = fmaf(x[oc + kw][i], wt[0 + kw][i], acc[2][oc][i]);
+                    }
+            // weight gradient: dk[kh][kw] += v[gh+kh-1][c] * g[gh][c-kw+1]
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                    for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+                        for (int i = 0; i < G; ++i)
+                            dkacc[kh * 3 + kw][i] = fmaf(vw[kh][oc][i], x[oc + 2 - kw][i], dkacc[kh * 3 + kw][i]);
+            const int oh = gh - 1;
+            if (oh >= h0 && oh < h1) {
+#pragma unroll
+                for (int oc = 0; oc < 2; ++oc) {
+                    if (!own[oc]) continue;
+                    const int ow = w0 + col0 + oc;
+                    const size_t o = (img + (size_t)oh * W + ow) * C + c0;
+                    float res[G];
+#pragma unroll
+                    for (int i = 0; i < G; ++i) res[i] = acc[0][oc][i];
+                    if (RELU || stats) {
+                        float u[G];
+                        load4(in + o, u);  // re-read of a line fetched two rows ago (L1/L2 hit)
+#pragma unroll
+                        for (int i = 0; i < G; ++i) {
+                            if (RELU) {
+                                const float pre = AFFINE ? fmaf(u[i], av[i], bv[i]) : u[i];
+                                if (!(pre > 0.f)) res[i] = 0.f;
+                            }
+                            if (stats) {
+                                const float rr = round_to<T>(res[i]);
+                                s1[i] += rr;
+                                s2[i] = fmaf(rr, (u[i] - mu[i]) * rs[i], s2[i]);
+                            }
+                        }
+                    }
+                    if (ep.add_src) {
+                        float m[G];
+                        load4(reinterpret_cast<const T*>(ep.add_src) + o, m);
+#pragma unroll
+                        for (int i = 0; i < G; ++i) res[i] += m[i];
+                    }
+                    if (ep.add_strided && ((oh | ow) & 1) == 0) {
+                        const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
+                        float m[G];
+                        load4(reinterpret_cast<const T*>(ep.add_strided) +
+                                  (((size_t)b * H2 + (oh >> 1)) * W2 + (ow >> 1)) * C + c0, m);
+#pragma unroll
+                        for (int i = 0; i < G; ++i) res[i] += m[i];
+                    }
+                    store4(gin + o, res);
+                }
+            }
+#pragma unroll
+            for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    acc[0][oc][i] = acc[1][oc][i];
+                    acc[1][oc][i] = acc[2][oc][i];
+                    acc[2][oc][i] = 0.f;
+                    vw[0][oc][i] = vw[1][oc][i];
+                    vw[1][oc][i] = vw[2][oc][i];
+                    vw[2][oc][i] = vnext[oc][i];
+                }
+        }
+        __syncthreads();
+    }
+    // ---- CTA reduction over the column groups that share a channel group, then global atomics
+    float* red = reinterpret_cast<float*>(smem);  // [ncolg][16][NV] — the tile buffers are idle now
+    constexpr int NV = 9 * G + 2 * G;
+    float* mine = red + ((size_t)colg * 16 + cg) * NV;
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < G; ++i) mine[t * G + i] = dkacc[t][i];
+#pragma unroll
+    for (int i = 0; i < G; ++i) { mine[36 + i] = s1[i]; mine[36 + G + i] = s2[i]; }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 16 * NV; e += blockDim.x) {
+        const int g = e / NV, v = e % NV;
+        const int c = cbase + g * G + (v % G);
+        if (c >= C) continue;
+        float sum = 0.f;
+        for (int q = 0; q < ncolg; ++q) sum += red[((size_t)q * 16 + g) * NV + v];
+        if (v < 36) atomicAdd(dk + (size_t)(v / G) * C + c, sum);
+        else if (stats) atomicAdd(stats + ((v - 36) / G) * (size_t)C + c, (double)sum);
+    }
+}
+
 // Weight gradient: dk[kh,kw,c] = sum_{b,h,w} act(in)[b,h+kh-1,w+kw-1,c] * g[b,h,w,c].
 // Persistent CTAs: blockDim = cvb*kcols with a fixed channel vector per thread, so the 9*V
 // partial sums stay in registers across the whole grid-stride loop; one shared-memory
@@ -413,6 +640,51 @@ int launch_dw_wgrad(const void* in, const void* g, const float* in_a, const floa
     return spnet_check_launch("dw3x3_wgrad");
 }
 
+template <typename T, bool AF, bool RL>
+int launch_dw_bwd_inst(const CUtensorMap& tm, const T* in, const float* k, const float* in_a, const float* in_b,
+                       const float* mean, const float* rstd, double* stats, T* gin, float* dk, int B, int H, int W,
+                       int C, const DwTiling& t, int grid_x, DwEpilogue ep, cudaStream_t stream) {
+    auto kern = dw3x3_bwd_fused_kernel<T, AF, RL>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) {
+            spnet_set_error("dwconv3x3_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return SPNET_ERR_CUDA;
+        }
+        configured = true;
+    }
+    dim3 grid(grid_x, t.chunks);
+    kern<<<grid, t.threads, t.smem, stream>>>(tm, in, k, in_a, in_b, mean, rstd, stats, gin, dk, B, H, W, C, t.TH, t.TW,
+                                              t.tiles_h, t.tiles_w, ep);
+    return spnet_check_launch("dw3x3_bwd_fused");
+}
+
+template <typename T>
+int launch_dw_bwd(const void* gout, const void* in, const float* k, const float* in_a, const float* in_b, int relu,
+                  const float* mean, const float* rstd, double* stats, void* gin, float* dk, int dtype, int B, int H,
+                  int W, int C, DwEpilogue ep, cudaStream_t stream) {
+    DwTiling t = dw_tiling(dtype, B, H, W, C);
+    const size_t red_bytes = (size_t)(t.threads / 16) * 16 * 44 * 4 + 128;
+    if (t.smem < red_bytes) t.smem = red_bytes;
+    SPNET_REQUIRE(t.smem <= 200 * 1024, "dwconv3x3_bwd: tile does not fit shared memory");
+    CUtensorMap tm;
+    int rc = make_nhwc_map(&tm, gout, dtype, B, H, W, C, t.TW + 2, t.TH + 2);
+    if (rc) return rc;
+    int per_sm = 256 / t.threads;  // ~170 registers per thread: one 256-thread CTA per SM
+    if (per_sm < 1) per_sm = 1;
+    const long long n_tiles = (long long)B * t.tiles_h * t.tiles_w;
+    long long gx = (148LL * per_sm + t.chunks - 1) / t.chunks;
+    if (gx > n_tiles) gx = n_tiles;
+    if (gx < 1) gx = 1;
+    const T* x = reinterpret_cast<const T*>(in);
+    T* y = reinterpret_cast<T*>(gin);
+    if (in_a && relu) return launch_dw_bwd_inst<T, true, true>(tm, x, k, in_a, in_b, mean, rstd, stats, y, dk, B, H, W, C, t, (int)gx, ep, stream);
+    if (in_a) return launch_dw_bwd_inst<T, true, false>(tm, x, k, in_a, in_b, mean, rstd, stats, y, dk, B, H, W, C, t, (int)gx, ep, stream);
+    if (relu) return launch_dw_bwd_inst<T, false, true>(tm, x, k, in_a, in_b, mean, rstd, stats, y, dk, B, H, W, C, t, (int)gx, ep, stream);
+    return launch_dw_bwd_inst<T, false, false>(tm, x, k, in_a, in_b, mean, rstd, stats, y, dk, B, H, W, C, t, (int)gx, ep, stream);
+}
+
 int check_dw_args(const char* who, const void* in, const void* out, int dtype, int B, int H, int W, int C) {
     SPNET_REQUIRE(in && out, "%s: null pointer", who);
     SPNET_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "%s: bad shape", who);
@@ -447,6 +719,24 @@ int spnet_dwconv3x3_dgrad(const void* gout, const float* k, void* gin, const voi
     SPNET_REQUIRE(mask_src || !mask_a, "dwconv3x3_dgrad: mask affine without mask_src");
     DwEpilogue ep = {mask_src, mask_a, mask_b, add_src, add_strided};
     SPNET_DISPATCH_DTYPE(dtype, return launch_dw<T>(gout, k, nullptr, nullptr, 0, 1, gin, dtype, B, H, W, C, ep, stream));
+}
+
+// Fused backward (see dw3x3_bwd_fused_kernel): gin, dk (+=) and optional BatchNorm-backward sums.
+//   in          : the tensor the forward depthwise read (raw), transformed on load by
+//                 act(v) = relu?(in_a*v+in_b)
+//   stats       : nullable fp64 [2*C]; += (sum gin, sum gin*xhat) with xhat = (in-bn_mean)*bn_rstd
+//   add_src / add_strided : optional residual-path gradients added to gin (as in dgrad)
+int spnet_dwconv3x3_bwd_fused(const void* gout, const void* in, const float* k, const float* in_a, const float* in_b,
+                              int relu, const float* bn_mean, const float* bn_rstd, double* stats,
+                              const void* add_src, const void* add_strided, void* gin, float* dk, int dtype, int B,
+                              int H, int W, int C, cudaStream_t stream) {
+    int rc = check_dw_args("dwconv3x3_bwd_fused", gout, gin, dtype, B, H, W, C);
+    if (rc) return rc;
+    SPNET_REQUIRE(in && k && dk && ((in_a == nullptr) == (in_b == nullptr)), "dwconv3x3_bwd_fused: bad pointers");
+    SPNET_REQUIRE(!stats || (bn_mean && bn_rstd), "dwconv3x3_bwd_fused: stats need bn_mean / bn_rstd");
+    DwEpilogue ep = {nullptr, nullptr, nullptr, add_src, add_strided};
+    SPNET_DISPATCH_DTYPE(dtype, return launch_dw_bwd<T>(gout, in, k, in_a, in_b, relu, bn_mean, bn_rstd, stats, gin, dk,
+                                                        dtype, B, H, W, C, ep, stream));
 }
 
 // dk[3,3,C] += sum act(in) (*) gout     (dk fp32, accumulated with atomics: zero it first)
