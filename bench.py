@@ -153,6 +153,10 @@ def algorithmic_work(name, a):
         n = a[9] * a[10] * a[11] * a[12]
         t = 2 + (1 if a[3] else 0) + (1 if a[6] else 0)
         return t * n * es(a[8]), 18 * n
+    if name == "spnet_dwconv3x3_bwd_fused":  # gout,in,k,a,b,relu,mean,rstd,stats,add,adds,gin,dk,dtype,B,H,W,C
+        n = a[14] * a[15] * a[16] * a[17]
+        t = 3 + (1 if a[9] else 0)
+        return t * n * es(a[13]), 36 * n
     if name == "spnet_dwconv3x3_wgrad":    # in,g,a,b,relu,dk,dtype,B,H,W,C
         n = a[7] * a[8] * a[9] * a[10]
         return 2 * n * es(a[6]), 18 * n
@@ -266,7 +270,7 @@ def run_ours(args, rank, world):
         if bound == "hbm":
             ach = nb / (ms * 1e-3) / 1e9
             roofs[gname] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
-                            "traffic": None, "kernel": gname + " fwd+dgrad+wgrad", "share_of_step": ms / total_ms,
+                            "traffic": None, "kernel": gname + " fwd + fused bwd (dgrad+wgrad+mask+BN sums)", "share_of_step": ms / total_ms,
                             "launches": nl // psteps, "avg_launch_ms": ms / max(nl, 1), "algorithmic_bytes_per_step": nb // psteps}
         else:
             ach = nf / (ms * 1e-3) / 1e12

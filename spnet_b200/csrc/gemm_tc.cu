@@ -23,7 +23,7 @@ namespace {
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 128;
+constexpr int kThreads = 192;  // TMA warp, MMA warp, four epilogue warps
 
 enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_ATOMIC_F32 = 2 };
 
@@ -75,43 +75,74 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the four epilogue warps only
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Column sums of a 32x32 block held one row per lane (v[j] = element (lane, j)): after the
+// butterfly lane L holds sum_rows element(row, L). 31 shuffles instead of 32*5.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = upper ? v[i] : v[i + off];
+            const float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+// Persistent, warp-specialised kernel. One CTA per SM walks work units (split, m-tile, n-tile):
+//   warp 0      TMA producer   : fills the STAGES-deep smem ring
+//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma into one of TWO TMEM accumulators
+//   warps 2..5  epilogue       : drain the other accumulator (tcgen05.ld -> convert -> global, fused
+//                                BatchNorm column statistics) while the next unit's MMAs run
 template <int BN, bool A_MN, bool B_MN, int STAGES>
-__global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB, GemmEpi epi,
-                                                           int M, int N, int K, int kb_per_split) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmB, GemmEpi epi,
+                                                              int M, int N, int K, int kb_per_split, int tiles_m,
+                                                              int tiles_n, int n_units) {
     constexpr uint32_t A_BYTES = BM * BK * 2;
     constexpr uint32_t B_BYTES = BN * BK * 2;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
     __shared__ uint32_t tmem_base_holder;
+    __shared__ float sstat[2][4][BN];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN;
-    const int m0 = blockIdx.y * BM;
     const int total_kb = (K + BK - 1) / BK;
-    const int kb_begin = blockIdx.z * kb_per_split;
-    const int kb_end = min(total_kb, kb_begin + kb_per_split);
-    const int nkb = kb_end - kb_begin;  // host guarantees >= 1
-
     const uint32_t full0 = smem_u32(&bars[0]);
     const uint32_t empty0 = smem_u32(&bars[STAGES]);
-    const uint32_t tfull = smem_u32(&bars[2 * STAGES]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]);
+    const uint32_t tempty0 = smem_u32(&bars[2 * STAGES + 2]);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
         }
-        mbar_init(tfull, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull0 + 8 * a, 1);
+            mbar_init(tempty0 + 8 * a, 4);  // one arrive per epilogue warp
+        }
         mbar_fence_init();
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(&tmem_base_holder)),
-                     "r"((uint32_t)BN)
+                     "r"((uint32_t)(2 * BN))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -122,141 +153,162 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % STAGES;
-            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-            mbar_wait(empty0 + 8 * s, ph ^ 1u);
-            if (lane == 0) {
-                const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-                const uint32_t sb = sa + A_BYTES;
-                const int k0 = (kb_begin + i) * BK;
-                mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
-                if (A_MN) {
+        uint32_t it = 0;  // running k-block counter across units
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int n0 = (unit % tiles_n) * BN;
+            const int m0 = ((unit / tiles_n) % tiles_m) * BM;
+            const int kb_begin = (unit / (tiles_n * tiles_m)) * kb_per_split;
+            const int nkb = min(total_kb, kb_begin + kb_per_split) - kb_begin;
+            for (int i = 0; i < nkb; ++i, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
+                    const int k0 = (kb_begin + i) * BK;
+                    mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+                    if (A_MN) {
 #pragma unroll
-                    for (int j = 0; j < BM / 64; ++j)
-                        tma_load_2d(sa + j * (BK * 128), &tmA, full0 + 8 * s, m0 + 64 * j, k0);
-                } else {
-                    tma_load_2d(sa, &tmA, full0 + 8 * s, k0, m0);
-                }
-                if (B_MN) {
+                        for (int j = 0; j < BM / 64; ++j)
+                            tma_load_2d(sa + j * (BK * 128), &tmA, full0 + 8 * s, m0 + 64 * j, k0);
+                    } else {
+                        tma_load_2d(sa, &tmA, full0 + 8 * s, k0, m0);
+                    }
+                    if (B_MN) {
 #pragma unroll
-                    for (int j = 0; j < BN / 64; ++j)
-                        tma_load_2d(sb + j * (BK * 128), &tmB, full0 + 8 * s, n0 + 64 * j, k0);
-                } else {
-                    tma_load_2d(sb, &tmB, full0 + 8 * s, k0, n0);
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_2d(sb + j * (BK * 128), &tmB, full0 + 8 * s, n0 + 64 * j, k0);
+                    } else {
+                        tma_load_2d(sb, &tmB, full0 + 8 * s, k0, n0);
+                    }
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         // instruction descriptor: fp32 accumulate, bf16 x bf16, majors, N>>3, M>>4
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
                                ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % STAGES;
-            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-            mbar_wait(full0 + 8 * s, ph);
+        uint32_t it = 0, u = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++u) {
+            const int kb_begin = (unit / (tiles_n * tiles_m)) * kb_per_split;
+            const int nkb = min(total_kb, kb_begin + kb_per_split) - kb_begin;
+            const uint32_t as = u & 1u;
+            mbar_wait(tempty0 + 8 * as, ((u >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-                const uint32_t sb = sa + A_BYTES;
+            const uint32_t tacc = tmem_base + as * BN;
+            for (int i = 0; i < nkb; ++i, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
+                mbar_wait(full0 + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint64_t ad = A_MN ? make_smem_desc(sa + k * (UMMA_K * 128), BK * 128, 1024)
-                                             : make_smem_desc(sa + k * (UMMA_K * 2), 0, 1024);
-                    const uint64_t bd = B_MN ? make_smem_desc(sb + k * (UMMA_K * 128), BK * 128, 1024)
-                                             : make_smem_desc(sb + k * (UMMA_K * 2), 0, 1024);
-                    umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t ad = A_MN ? make_smem_desc(sa + k * (UMMA_K * 128), BK * 128, 1024)
+                                                 : make_smem_desc(sa + k * (UMMA_K * 2), 0, 1024);
+                        const uint64_t bd = B_MN ? make_smem_desc(sb + k * (UMMA_K * 128), BK * 128, 1024)
+                                                 : make_smem_desc(sb + k * (UMMA_K * 2), 0, 1024);
+                        umma_bf16(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty0 + 8 * s);                     // frees the smem stage when these MMAs retire
+                    if (i == nkb - 1) umma_commit(tfull0 + 8 * as);  // accumulator complete
                 }
-                umma_commit(empty0 + 8 * s);          // frees the smem stage when these MMAs retire
-                if (i == nkb - 1) umma_commit(tfull);  // accumulator complete
+                __syncwarp();
             }
-            __syncwarp();
         }
-    }
-
-    // ---------------- epilogue: all four warps ----------------
-    mbar_wait(tfull, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    __syncwarp();
-
-    const int row = m0 + warp * 32 + lane;
-    const bool row_ok = row < M;
-    float* stage_f32 = reinterpret_cast<float*>(smem);  // [BM][BN+1] fp32, reuses the (drained) ring
-    constexpr int LDS = BN + 1;
+    } else {
+        // ---------------- epilogue warps ----------------
+        const int q = warp & 3;       // TMEM lane quadrant this warp may access
+        const int et = q * 32 + lane;  // 0..127 within the epilogue group
+        uint32_t u = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++u) {
+            const int n0 = (unit % tiles_n) * BN;
+            const int m0 = ((unit / tiles_n) % tiles_m) * BM;
+            const uint32_t as = u & 1u;
+            mbar_wait(tfull0 + 8 * as, (u >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < M;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
-        const int col0 = n0 + c * 32;
-        if (epi.mode == OUT_BF16) {
-            uint32_t packed[16];
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + as * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                const int col0 = n0 + c * 32;
+                float f[32];
+                if (epi.mode == OUT_BF16) {
+                    uint32_t packed[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                packed[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-            if (epi.colstats) {
+                    for (int j = 0; j < 16; ++j) {
+                        packed[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                        f[2 * j] = __uint_as_float(packed[j] << 16);  // statistics of the values as stored
+                        f[2 * j + 1] = __uint_as_float(packed[j] & 0xffff0000u);
+                    }
+                    if (row_ok) {
+                        bf16* o = reinterpret_cast<bf16*>(epi.out) + (size_t)row * epi.ldc + col0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    stage_f32[(warp * 32 + lane) * LDS + c * 32 + 2 * j] = __uint_as_float(packed[j] << 16);
-                    stage_f32[(warp * 32 + lane) * LDS + c * 32 + 2 * j + 1] =
-                        __uint_as_float(packed[j] & 0xffff0000u);
-                }
-            }
-            if (row_ok) {
-                bf16* o = reinterpret_cast<bf16*>(epi.out) + (size_t)row * epi.ldc + col0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (col0 + q * 8 < N)  // N % 8 == 0 is checked on the host
-                        *reinterpret_cast<uint4*>(o + q * 8) =
-                            make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-                }
-            }
-        } else {
-            if (epi.colstats) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    stage_f32[(warp * 32 + lane) * LDS + c * 32 + j] = __uint_as_float(v[j]);
-            }
-            if (row_ok) {
-                float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldc + col0;
-                if (epi.mode == OUT_F32) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (col0 + q * 4 < N)  // N % 4 == 0 is checked on the host
-                            *reinterpret_cast<float4*>(o + q * 4) =
-                                make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                            __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                        for (int g = 0; g < 4; ++g) {
+                            if (col0 + g * 8 < N)  // N % 8 == 0 is checked on the host
+                                *reinterpret_cast<uint4*>(o + g * 8) =
+                                    make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+                        }
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < N) atomicAdd(o + j, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (row_ok) {
+                        float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldc + col0;
+                        if (epi.mode == OUT_F32) {
+#pragma unroll
+                            for (int g = 0; g < 8; ++g) {
+                                if (col0 + g * 4 < N)  // N % 4 == 0 is checked on the host
+                                    *reinterpret_cast<float4*>(o + g * 4) =
+                                        make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int g = 0; g < 8; ++g) {
+                                if (col0 + g * 4 < N) red_add_v4(o + g * 4, f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+                            }
+                        }
+                    }
+                }
+                if (epi.colstats) {  // rows past M hold exact zeros (TMA zero fill)
+                    float sq[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
+                    const float cs = warp_colsum32(f, lane);
+                    const float cq = warp_colsum32(sq, lane);
+                    sstat[0][q][c * 32 + lane] = cs;
+                    sstat[1][q][c * 32 + lane] = cq;
                 }
             }
-        }
-    }
-    if (epi.colstats) {
-        __syncthreads();
-        // thread t owns column t (and t+128 when BN == 256); rows past M hold exact zeros
-        for (int cc = threadIdx.x; cc < BN; cc += kThreads) {
-            if (n0 + cc < N) {
-                float s = 0.f, s2 = 0.f;
-#pragma unroll 8
-                for (int r = 0; r < BM; ++r) {
-                    const float x = stage_f32[r * LDS + cc];
-                    s += x;
-                    s2 = fmaf(x, x, s2);
+            // accumulator fully read: hand it back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+            if (epi.colstats) {
+                epi_bar_sync();
+                for (int cc = et; cc < BN; cc += 128) {
+                    if (n0 + cc < N) {
+                        const float s = sstat[0][0][cc] + sstat[0][1][cc] + sstat[0][2][cc] + sstat[0][3][cc];
+                        const float s2 = sstat[1][0][cc] + sstat[1][1][cc] + sstat[1][2][cc] + sstat[1][3][cc];
+                        atomicAdd(epi.colstats + (n0 + cc), (double)s);
+                        atomicAdd(epi.colstats + N + (n0 + cc), (double)s2);
+                    }
                 }
-                atomicAdd(epi.colstats + (n0 + cc), (double)s);
-                atomicAdd(epi.colstats + N + (n0 + cc), (double)s2);
+                epi_bar_sync();
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN))
                      : "memory");
     }
 }
@@ -296,18 +348,20 @@ int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long lon
 template <int BN, bool A_MN, bool B_MN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmEpi epi, int M, int N, int K, int splits,
                 cudaStream_t stream) {
-    constexpr int STAGES = (BN <= 128) ? 3 : 4;
-    constexpr size_t ring = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2);
-    constexpr size_t stats_tile = (size_t)BM * (BN + 1) * 4;
-    constexpr size_t smem = (ring > stats_tile ? ring : stats_tile) + 1024;
+    constexpr int STAGES = (BN <= 128) ? 6 : 4;
+    constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
     auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES>;
     static bool configured = false;
+    static int num_sms = 148;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             spnet_set_error("gemm_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return SPNET_ERR_CUDA;
         }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         configured = true;
     }
     const int total_kb = (K + BK - 1) / BK;
@@ -315,8 +369,14 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmEpi epi, int M
     if (splits > total_kb) splits = total_kb;
     const int kbps = (total_kb + splits - 1) / splits;
     splits = (total_kb + kbps - 1) / kbps;  // no empty splits
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
-    kern<<<grid, kThreads, smem, stream>>>(ta, tb, epi, M, N, K, kbps);
+    const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    const long long units = (long long)tiles_m * tiles_n * splits;
+    if (units > 0x7fffffffLL) {
+        spnet_set_error("gemm_bf16: too many tiles");
+        return SPNET_ERR_ARG;
+    }
+    const int grid = (int)(units < num_sms ? units : num_sms);
+    kern<<<grid, kThreads, smem, stream>>>(ta, tb, epi, M, N, K, kbps, tiles_m, tiles_n, (int)units);
     return spnet_check_launch("gemm_bf16");
 }
 

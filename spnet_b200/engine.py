@@ -266,10 +266,12 @@ class XceptionSPNetEngine:
         M = B * s.H * s.W
         self._pw_fwd(s.t, s.pwl, s.z, M, s.cin, s.cout, s.bn, training)
 
-    def _bn_bwd(self, g, z, bn, rows, relu_mask=False, out=None):
-        """g = grad wrt BN output (or wrt relu(BN output) when relu_mask) -> grad wrt z."""
-        ops.bn_bwd_reduce(g, z, bn.mean, bn.rstd, bn.stats, relu_a=bn.a if relu_mask else None,
-                          relu_b=bn.b if relu_mask else None, act=1)
+    def _bn_bwd(self, g, z, bn, rows, relu_mask=False, out=None, reduced=False):
+        """g = grad wrt BN output (or wrt relu(BN output) when relu_mask) -> grad wrt z.
+        reduced=True: the sums were already accumulated into bn.stats by the producer of g."""
+        if not reduced:
+            ops.bn_bwd_reduce(g, z, bn.mean, bn.rstd, bn.stats, relu_a=bn.a if relu_mask else None,
+                              relu_b=bn.b if relu_mask else None, act=1)
         ops.bn_bwd_finalize(bn.stats, rows, bn.ggamma, bn.gbeta, bn.c1, bn.c2)
         return ops.bn_bwd_dz(g, z, bn.a, bn.mean, bn.rstd, bn.c1, bn.c2, out=out if out is not None else g)
 
@@ -354,10 +356,10 @@ class XceptionSPNetEngine:
         M = B * s.H * s.W
         self._pw_bwd(s.t, s.pwl, s.gpw, gz, g_t, M, s.cin, s.cout)
         gt4 = g_t.view(B, s.H, s.W, s.cin)
-        ops.dwconv3x3_wgrad(x, gt4, s.gdwk, in_bn.a if in_bn else None, in_bn.b if in_bn else None, relu)
-        ops.dwconv3x3_dgrad(gt4, s.dwk, mask_src=x if relu else None, mask_a=in_bn.a if (in_bn and relu) else None,
-                            mask_b=in_bn.b if (in_bn and relu) else None, add_src=add_src, add_strided=add_strided,
-                            out=g_in.view(B, s.H, s.W, s.cin))
+        ops.dwconv3x3_bwd_fused(gt4, x, s.dwk, s.gdwk, in_a=in_bn.a if in_bn else None, in_b=in_bn.b if in_bn else None,
+                                relu=relu, bn_mean=in_bn.mean if in_bn else None, bn_rstd=in_bn.rstd if in_bn else None,
+                                stats=in_bn.stats if in_bn else None, add_src=add_src, add_strided=add_strided,
+                                out=g_in.view(B, s.H, s.W, s.cin))
 
     def _entry_bwd(self, e, x, g_out, bufs):
         """g_out: grad wrt block output [B,oh,ow,c]. Returns grad wrt block input x."""
@@ -378,7 +380,7 @@ class XceptionSPNetEngine:
         g_z2 = self._bn_bwd(g_y2, s2.z, s2.bn, M)
         g_y1 = self._view(G3, B, H, W, s2.cin)
         self._sep_bwd(s2, g_z2.view(M, c), s1.z, s1.bn, True, self._view(G2, M, s2.cin), g_y1)
-        g_z1 = self._bn_bwd(g_y1, s1.z, s1.bn, M)
+        g_z1 = self._bn_bwd(g_y1, s1.z, s1.bn, M, reduced=True)
         g_x = self._view(R, B, H, W, cin)
         self._sep_bwd(s1, g_z1.view(M, s1.cout), x, None, e["relu_in"], self._view(G1, M, cin), g_x,
                       add_strided=g_xs.view(B, oh, ow, cin))
@@ -405,7 +407,7 @@ class XceptionSPNetEngine:
         g_z = self._bn_bwd(self.gfeat.view(B, fh, fw, 2048), s2.z, s2.bn, M, relu_mask=True)
         g_y = self._view(G3, B, fh, fw, 1536)
         self._sep_bwd(s2, g_z.view(M, 2048), s1.z, s1.bn, True, self._view(G2, M, 1536), g_y)
-        g_z = self._bn_bwd(g_y, s1.z, s1.bn, M)
+        g_z = self._bn_bwd(g_y, s1.z, s1.bn, M, reduced=True)
         g_x = self._view(R0, B, fh, fw, 1024)
         self._sep_bwd(s1, g_z.view(M, 1536), x13, None, False, self._view(G1, M, 1024), g_x)
         # ---- exit block 13
@@ -422,10 +424,10 @@ class XceptionSPNetEngine:
             g3 = self._bn_bwd(g_x, blk[2].z, blk[2].bn, M, out=self._view(G1, B, mh, mw, 728))
             gy2 = self._view(G3, B, mh, mw, 728)
             self._sep_bwd(blk[2], g3.view(M, 728), blk[1].z, blk[1].bn, True, self._view(G2, M, 728), gy2)
-            g2 = self._bn_bwd(gy2, blk[1].z, blk[1].bn, M)
+            g2 = self._bn_bwd(gy2, blk[1].z, blk[1].bn, M, reduced=True)
             gy1 = self._view(G1, B, mh, mw, 728)
             self._sep_bwd(blk[1], g2.view(M, 728), blk[0].z, blk[0].bn, True, self._view(G2, M, 728), gy1)
-            g1 = self._bn_bwd(gy1, blk[0].z, blk[0].bn, M)
+            g1 = self._bn_bwd(gy1, blk[0].z, blk[0].bn, M, reduced=True)
             g_new = self._view(R_nxt, B, mh, mw, 728)
             self._sep_bwd(blk[0], g1.view(M, 728), x_in, None, True, self._view(G2, M, 728), g_new, add_src=g_x)
             g_x = g_new

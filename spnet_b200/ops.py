@@ -93,6 +93,19 @@ def dwconv3x3_dgrad(gout, k, mask_src=None, mask_a=None, mask_b=None, add_src=No
     return out
 
 
+def dwconv3x3_bwd_fused(gout, x, k, dk, in_a=None, in_b=None, relu=False, bn_mean=None, bn_rstd=None, stats=None,
+                        add_src=None, add_strided=None, out=None):
+    """gin, dk (+=) and optional BatchNorm-backward sums in one pass (see dwconv.cu)."""
+    _chk(gout, x, k, dk, in_a, in_b, stats, add_src, add_strided, out)
+    B, H, W, C = gout.shape
+    if out is None:
+        out = torch.empty_like(gout)
+    lib().dwconv3x3_bwd_fused(_p(gout), _p(x), _p(k), _p(in_a), _p(in_b), int(relu), _p(bn_mean), _p(bn_rstd),
+                              _p(stats), _p(add_src), _p(add_strided), _p(out), _p(dk), dtype_code(gout), B, H, W, C,
+                              _s())
+    return out
+
+
 def dwconv3x3_wgrad(x, gout, dk, in_a=None, in_b=None, relu=False):
     """dk (fp32 [3,3,C]) is accumulated into: zero it first."""
     _chk(x, gout, dk, in_a, in_b)

@@ -167,6 +167,53 @@ def test_dwconv_bwd(dtype, shape):
     torch.testing.assert_close(dk, kr.grad, **t)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 12, 16, 728), (2, 47, 63, 128), (2, 7, 9, 24), (1, 93, 125, 64), (3, 6, 8, 1024), (2, 24, 32, 256)])
+@pytest.mark.parametrize("mode", ["bn_relu", "relu_add", "plain_strided"])
+def test_dwconv_bwd_fused(dtype, shape, mode):
+    """Fused dgrad + wgrad + ReLU mask + BatchNorm-backward sums against autograd."""
+    ops = _ops()
+    torch.manual_seed(4)
+    B, H, W, C = shape
+    x = torch.randn(shape, device=dev()).to(dtype)
+    k = torch.randn(3, 3, C, device=dev()) * 0.3
+    g = torch.randn(shape, device=dev()).to(dtype)
+    a = b = mean = rstd = stats = add = sadd = None
+    relu = mode != "plain_strided"
+    if mode == "bn_relu":
+        a = torch.rand(C, device=dev()) + 0.5
+        b = torch.randn(C, device=dev()) * 0.2
+        mean = torch.randn(C, device=dev()) * 0.1
+        rstd = torch.rand(C, device=dev()) + 0.5
+        stats = torch.zeros(2 * C, device=dev(), dtype=torch.float64)
+    elif mode == "relu_add":
+        add = torch.randn(shape, device=dev()).to(dtype)
+    else:
+        sadd = torch.randn(B, (H + 1) // 2, (W + 1) // 2, C, device=dev()).to(dtype)
+    pre = x.float() * a + b if a is not None else x.float()
+    v = (torch.relu(pre) if relu else pre).detach().requires_grad_(True)
+    kr = k.clone().requires_grad_(True)
+    y = nhwc(F.conv2d(nchw(v), kr.permute(2, 0, 1).reshape(C, 1, 3, 3), padding=1, groups=C))
+    y.backward(g.float())
+    ref = v.grad * (pre > 0) if relu else v.grad.clone()
+    dk = torch.zeros(3, 3, C, device=dev())
+    gin = ops.dwconv3x3_bwd_fused(g, x, k, dk, in_a=a, in_b=b, relu=relu, bn_mean=mean, bn_rstd=rstd, stats=stats,
+                                  add_src=add, add_strided=sadd)
+    if stats is not None:
+        gq = gin.double()
+        xh = (x.double() - mean.double()) * rstd.double()
+        torch.testing.assert_close(stats[:C], gq.sum((0, 1, 2)), rtol=1e-4, atol=1e-3)
+        torch.testing.assert_close(stats[C:], (gq * xh).sum((0, 1, 2)), rtol=1e-4, atol=1e-3)
+    if add is not None:
+        ref = ref + add.float()
+    if sadd is not None:
+        ref[:, ::2, ::2, :] += sadd.float()
+    torch.testing.assert_close(gin.float(), ref, **tol(dtype))
+    scale = float(kr.grad.abs().max())
+    t = dict(rtol=2e-2, atol=2e-2 * scale) if dtype == torch.bfloat16 else dict(rtol=2e-4, atol=2e-4 * scale)
+    torch.testing.assert_close(dk, kr.grad, **t)
+
+
 # ------------------------------------------------------------------ GEMM
 def _gemm_case(M, N, K, a_mn, b_mn, out_mode, splits, stats, dtype):
     ops = _ops()
