@@ -1,0 +1,98 @@
+#! /usr/bin/env python3
+"""Batch inference + hawley_spnet.csv — same CLI and behaviour as the reference's predict_spnet.py
+(predict_network, :40-97; flags :100-115), running on the B200 engine. Extra flags (not in the
+reference): --no-png skips the per-image PNG drawing, which at B200 inference rates is where all the
+wall time goes; --dtype picks bf16 / fp32 compute."""
+import glob
+import time
+
+import numpy as np
+
+from spnet.models import *   # noqa: F401,F403  (reference: `from spnet.models import *`)
+from spnet.utils import *    # noqa: F401,F403
+import spnet.config as cf
+from spnet import models, utils
+
+default_image_dir = "/home/shawley/datasets/zooniverse_steelpan/"
+
+
+def predict_network(weights_file="spnet.model", datapath=default_image_dir, fraction=1.0, log_dir="logs/Predicting/",
+                    batch_size=16, model=None, X_pred="", draw_images=True):
+    img_file_list = None
+    if isinstance(X_pred, str) and "" == X_pred:
+        print(f"Getting data from {datapath}, fraction = {fraction}.")
+        if cf.model_type == "simple":
+            grayscale, force_dim = False, 224
+        elif cf.model_type == "big":
+            grayscale, force_dim = True, None
+        else:
+            grayscale, force_dim = True, 331
+        img_file_list = sorted(glob.glob(datapath + "/*.png"))
+        if len(img_file_list) == 0:
+            img_file_list += sorted(glob.glob(datapath + "/*.bmp"))
+        total_files = len(img_file_list)
+        total_load = int(total_files * fraction)
+        if batch_size is not None:
+            total_load = utils.nearest_multiple(total_load, batch_size)
+        print("      Total files = ", total_files, ", going to load total_load = ", total_load)
+        X_pred, img_dims = utils.build_X(total_load, img_file_list, force_dim=force_dim, grayscale=grayscale)
+        print("")
+    if model is None:
+        print("Loading model from", weights_file)
+        if ".hdf5" in weights_file:
+            print("   Defining model, then loading weights")
+            model, serial_model = models.setup_model(X_pred, try_checkpoint=True, no_cp_fatal=True,
+                                                     weights_file=weights_file, parallel=False, freeze_fac=0.0,
+                                                     quick_setup=True)
+        else:
+            print("   Loading whole model")
+            model = models.load_model(weights_file)
+    m = X_pred.shape[0]
+    print("    Predicting... (m = ", m, " frames in dataset)", sep="")
+    start_time = time.time()
+    Y_pred = model.predict(X_pred, batch_size=batch_size)
+    elapsed = time.time() - start_time
+    print("    ...elapsed time to predict = ", elapsed, "s.   FPS = ", m * 1.0 / elapsed)
+
+    print("    Drawing ellipse images...")
+    utils.make_sure_path_exists(log_dir)
+    pred_shape = [6, 6, 2, cf.vars_per_pred]
+    utils.setup_means_and_ranges(pred_shape)
+    if img_file_list is None:
+        img_file_list = ["frame_%07d.png" % i for i in range(m)]
+        draw_images = False
+    Yp, decoded = decode_on_device(Y_pred)
+    utils.show_pred_ellipses(Yp, Yp, img_file_list, num_draw=m, log_dir=log_dir, out_csv=log_dir + "hawley_spnet.csv",
+                             show_true=False, draw_images=draw_images, decoded=decoded)
+    return model
+
+
+def decode_on_device(Y_pred):
+    """denorm_Y + integer rounding + existence flags in one CUDA kernel (ops.decode_detections)."""
+    import torch
+    from spnet_b200 import ops
+    y = torch.from_numpy(np.ascontiguousarray(Y_pred, np.float32)).cuda()
+    means = torch.from_numpy(np.asarray(utils.means, np.float32)).cuda()
+    ranges = torch.from_numpy(np.asarray(utils.ranges, np.float32)).cuda()
+    denorm, ints, exists = ops.decode_detections(y, means, ranges)
+    return denorm.cpu().numpy(), (ints.cpu().numpy().astype(np.int64), exists.cpu().numpy().astype(bool))
+
+
+if __name__ == "__main__":
+    np.random.seed(1)
+    import argparse
+    parser = argparse.ArgumentParser(description="tests network on test dataset",
+                                     formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument("-w", "--weights", help="weights file in hdf5 format", default="spnet.model")
+    parser.add_argument("-d", "--datapath", help="Dataset directory with list of images", default=default_image_dir)
+    parser.add_argument("-f", "--fraction", type=float, help="Fraction of dataset to use", default=1.0)
+    parser.add_argument("-l", "--logdir", help="Directory of log/output files", default="logs/Predicting/")
+    parser.add_argument("-b", "--batch_size", type=int, help="Batch size to use", default=16)
+    parser.add_argument("--no-png", action="store_true", help="write only hawley_spnet.csv, skip the per-image PNGs")
+    parser.add_argument("--dtype", choices=["bf16", "fp32"], default=cf.compute_dtype)
+    parser.add_argument("--model_type", default=cf.model_type, help="'big' keeps 384x512 input, default resizes to 331x331")
+    args = parser.parse_args()
+    cf.compute_dtype = args.dtype
+    cf.model_type = args.model_type
+    model = predict_network(weights_file=args.weights, datapath=args.datapath, fraction=args.fraction,
+                            log_dir=args.logdir, batch_size=args.batch_size, draw_images=not args.no_png)

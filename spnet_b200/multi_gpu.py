@@ -45,13 +45,17 @@ class GradAllReduce:
         assert off == 0
         self.head = engine.grads[: (n + 7) // 8 * 8]
         self.rest = engine.grads[(n + 7) // 8 * 8:]
-        self.side = torch.cuda.Stream(device=engine.device)
-        self.head_ready = torch.cuda.Event()
-        self.head_done = torch.cuda.Event()
+        self.on_cuda = torch.device(engine.device).type == "cuda"
+        if self.on_cuda:
+            self.side = torch.cuda.Stream(device=engine.device)
+            self.head_ready = torch.cuda.Event()
+            self.head_done = torch.cuda.Event()
         self.head_in_flight = False
 
     def head_bucket_ready(self, engine):
         """Called by the engine right after the Dense-head gradient is complete."""
+        if not self.on_cuda:
+            return
         self.head_ready.record()
         with torch.cuda.stream(self.side):
             self.side.wait_event(self.head_ready)
