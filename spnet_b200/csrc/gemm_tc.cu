@@ -404,19 +404,27 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
     SPNET_REQUIRE(out_mode != OUT_F32 || (N % 4 == 0 && ldd % 4 == 0), "gemm_bf16: fp32 output needs N, ldd %% 4 == 0");
     SPNET_REQUIRE(splits <= 1 || out_mode == OUT_ATOMIC_F32, "gemm_bf16: split-K needs out_mode 2");
     SPNET_REQUIRE(!(colstats && splits > 1), "gemm_bf16: column statistics are not defined for split-K partials");
-    constexpr int BN = 128;
+    // 128x256 tiles when N is wide: one A tile then feeds 256 output columns, which cuts the
+    // L2->SM operand traffic per FLOP by a third (the 128x128 kernel is L2-bandwidth bound).
+    const bool wide = N >= 512;
     CUtensorMap ta, tb;
     int rc = make_operand_map(&ta, A, M, K, lda, a_mn != 0, BM);
     if (rc) return rc;
-    rc = make_operand_map(&tb, B, N, K, ldb, b_mn != 0, BN);
+    rc = make_operand_map(&tb, B, N, K, ldb, b_mn != 0, wide ? 256 : 128);
     if (rc) return rc;
     GemmEpi epi = {D, ldd, out_mode, colstats};
-    if (a_mn) {
-        if (b_mn) return launch_gemm<BN, true, true>(ta, tb, epi, M, N, K, splits, stream);
-        return launch_gemm<BN, true, false>(ta, tb, epi, M, N, K, splits, stream);
-    }
-    if (b_mn) return launch_gemm<BN, false, true>(ta, tb, epi, M, N, K, splits, stream);
-    return launch_gemm<BN, false, false>(ta, tb, epi, M, N, K, splits, stream);
+#define SPNET_GEMM_DISPATCH(BN_)                                                                        \
+    do {                                                                                                \
+        if (a_mn) {                                                                                     \
+            if (b_mn) return launch_gemm<BN_, true, true>(ta, tb, epi, M, N, K, splits, stream);        \
+            return launch_gemm<BN_, true, false>(ta, tb, epi, M, N, K, splits, stream);                 \
+        }                                                                                               \
+        if (b_mn) return launch_gemm<BN_, false, true>(ta, tb, epi, M, N, K, splits, stream);           \
+        return launch_gemm<BN_, false, false>(ta, tb, epi, M, N, K, splits, stream);                    \
+    } while (0)
+    if (wide) SPNET_GEMM_DISPATCH(256);
+    SPNET_GEMM_DISPATCH(128);
+#undef SPNET_GEMM_DISPATCH
 }
 
 }  // extern "C"
