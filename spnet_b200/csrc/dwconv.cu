@@ -211,8 +211,11 @@ __global__ void __launch_bounds__(256) dw3x3_tma_kernel(const __grid_constant__ 
 // gradient is written once — 3 tensor passes instead of the 8 that separate dgrad / wgrad /
 // bn_bwd_reduce kernels need. Both gradients use the SAME 3x3 neighbourhood of gout around a
 // pixel: dgrad = sum_n gout_n * k_n,  dk_n += act(in)(pixel) * gout_n.
+// Warp-specialised: the first half of the CTA computes the data gradient (+mask, +BN sums, store),
+// the second half the weight gradient, both from the same TMA-staged gradient tile. Splitting the
+// two accumulator sets over different warps halves the registers per thread (2x the resident warps).
 template <typename T, bool AFFINE, bool RELU>
-__global__ void __launch_bounds__(256, 1) dw3x3_bwd_fused_kernel(
+__global__ void __launch_bounds__(512, 1) dw3x3_bwd_fused_kernel(
     const __grid_constant__ CUtensorMap tm_g, const T* __restrict__ in, const float* __restrict__ k,
     const float* __restrict__ in_a, const float* __restrict__ in_b, const float* __restrict__ bn_mean,
     const float* __restrict__ bn_rstd, double* __restrict__ stats, T* __restrict__ gin, float* __restrict__ dk, int B,
@@ -221,8 +224,11 @@ __global__ void __launch_bounds__(256, 1) dw3x3_bwd_fused_kernel(
     extern __shared__ uint8_t dw_smem_raw[];
     T* smem = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~(uintptr_t)127);
     __shared__ __align__(8) uint64_t bars[2];
-    const int cg = threadIdx.x & 15, colg = threadIdx.x >> 4;
-    const int ncolg = blockDim.x >> 4;
+    const int half = blockDim.x >> 1;
+    const bool wg_role = (int)threadIdx.x >= half;  // warp-uniform: half is a multiple of 32
+    const int tl = threadIdx.x - (wg_role ? half : 0);
+    const int cg = tl & 15, colg = tl >> 4;
+    const int ncolg = half >> 4;
     const int cbase = blockIdx.y * CB;
     const int c0 = cbase + cg * G;
     const bool c_ok = c0 < C;
@@ -230,27 +236,14 @@ __global__ void __launch_bounds__(256, 1) dw3x3_bwd_fused_kernel(
     const int tile_elems = (TH + 2) * TWH * CB;
     const uint32_t tile_bytes = (uint32_t)tile_elems * sizeof(T);
     const int n_tiles = B * tiles_h * tiles_w;
+    const int col0 = colg * 2;
 
-    float wt[9][G], av[G], bv[G], mu[G], rs[G];
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int i = 0; i < G; ++i) wt[t][i] = c_ok ? k[(8 - t) * C + c0 + i] : 0.f;  // flipped: data gradient
+    float av[G], bv[G];
 #pragma unroll
     for (int i = 0; i < G; ++i) {
         av[i] = (AFFINE && c_ok) ? in_a[c0 + i] : 1.f;
         bv[i] = (AFFINE && c_ok) ? in_b[c0 + i] : 0.f;
-        mu[i] = (stats && c_ok) ? bn_mean[c0 + i] : 0.f;
-        rs[i] = (stats && c_ok) ? bn_rstd[c0 + i] : 0.f;
     }
-    float dkacc[9][G], s1[G], s2[G];
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int i = 0; i < G; ++i) dkacc[t][i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < G; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-
     const uint32_t bar0 = smem_u32(&bars[0]);
     if (threadIdx.x == 0) {
         mbar_init(bar0, 1);
@@ -267,156 +260,187 @@ __global__ void __launch_bounds__(256, 1) dw3x3_bwd_fused_kernel(
     };
     if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
 
+    // role-private state (only one of the two sets is live in any warp)
+    float wt[9][G];      // data-gradient role: flipped taps
+    float s1[G], s2[G];  //   BN sums: s1 = sum g, s2 = sum g*in (raw); xhat fixed up at the end
+    float dkacc[9][G];   // weight-gradient role
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            wt[t][i] = (!wg_role && c_ok) ? k[(8 - t) * C + c0 + i] : 0.f;
+            dkacc[t][i] = 0.f;
+        }
+#pragma unroll
+    for (int i = 0; i < G; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int cur = it & 1;
         const int nxt = tile + gridDim.x;
         if (threadIdx.x == 0 && nxt < n_tiles) issue(nxt, cur ^ 1);
-
         const int tw = tile % tiles_w;
         const int th = (tile / tiles_w) % tiles_h;
         const int b = tile / (tiles_w * tiles_h);
         const int h0 = th * TH, w0 = tw * TW;
         const int h1 = min(H, h0 + TH);
-        const int col0 = colg * 2;
         const size_t img = (size_t)b * H * W;
+        const int rows = (h1 - h0) + 2;
         bool own[2];
 #pragma unroll
         for (int oc = 0; oc < 2; ++oc) own[oc] = c_ok && (w0 + col0 + oc) < W;
-
-        // act(in) for an owned centre pixel row (zero for rows/cols this tile does not own)
-        auto load_v = [&](int row, float (&v)[2][G]) {
-            const bool rok = row >= h0 && row < h1;
-#pragma unroll
-            for (int oc = 0; oc < 2; ++oc) {
-                if (rok && own[oc]) {
-                    load4(in + (img + (size_t)row * W + (w0 + col0 + oc)) * C + c0, v[oc]);
-#pragma unroll
-                    for (int i = 0; i < G; ++i) {
-                        float y = v[oc][i];
-                        if (AFFINE) y = fmaf(y, av[i], bv[i]);
-                        if (RELU) y = fmaxf(y, 0.f);
-                        v[oc][i] = y;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < G; ++i) v[oc][i] = 0.f;
-                }
-            }
-        };
-        // v window: rows gh-1, gh, gh+1 around the current gradient row gh (starts at gh = h0-1)
-        float vw[3][2][G];
-#pragma unroll
-        for (int oc = 0; oc < 2; ++oc)
-#pragma unroll
-            for (int i = 0; i < G; ++i) { vw[0][oc][i] = 0.f; vw[1][oc][i] = 0.f; }
-        load_v(h0, vw[2]);
-
-        mbar_wait(bar0 + 8 * cur, (uint32_t)(it >> 1) & 1u);
         const T* tb = smem + (size_t)cur * tile_elems + cg * G;
-        float acc[3][2][G];
+
+        if (!wg_role) {
+            // ================= data gradient (+ ReLU mask, BN sums, residual adds, store) =================
+            mbar_wait(bar0 + 8 * cur, (uint32_t)(it >> 1) & 1u);
+            float acc[3][2][G];
 #pragma unroll
-        for (int q = 0; q < 3; ++q)
+            for (int q = 0; q < 3; ++q)
 #pragma unroll
-            for (int oc = 0; oc < 2; ++oc)
+                for (int oc = 0; oc < 2; ++oc)
 #pragma unroll
-                for (int i = 0; i < G; ++i) acc[q][oc][i] = 0.f;
-        const int rows = (h1 - h0) + 2;
-        for (int r = 0; r < rows; ++r) {
-            const int gh = h0 - 1 + r;
-            float vnext[2][G];
-            load_v(gh + 2, vnext);  // prefetch: needed by the next iteration
-            float x[4][G];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) load4(tb + (size_t)(r * TWH + col0 + j) * CB, x[j]);
-            // data gradient: gradient row gh feeds outputs gh-1, gh, gh+1 (flipped taps)
-#pragma unroll
-            for (int oc = 0; oc < 2; ++oc)
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-                    for (int i = 0; i < G; ++i) {
-                        acc[0][oc][i] = fmaf(x[oc + kw][i], wt[6 + kw][i], acc[0][oc][i]);
-                        acc[1][oc][i] = fmaf(x[oc + kw][i], wt[3 + kw][i], acc[1][oc][i]);
-                        acc[2][oc][i] = fmaf(x[oc + kw][i], wt[0 + kw][i], acc[2][oc][i]);
-                    }
-            // weight gradient: dk[kh][kw] += v[gh+kh-1][c] * g[gh][c-kw+1]
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw)
+                    for (int i = 0; i < G; ++i) acc[q][oc][i] = 0.f;
+            for (int r = 0; r < rows; ++r) {
+                const int oh = h0 - 2 + r;  // output row completed by gradient row gh = oh + 1
+                const bool emit = oh >= h0 && oh < h1;
+                float u[2][G];
+                if (emit && (RELU || stats)) {  // issue the loads early; consumed after the FMAs
 #pragma unroll
                     for (int oc = 0; oc < 2; ++oc)
+                        if (own[oc]) load4(in + (img + (size_t)oh * W + (w0 + col0 + oc)) * C + c0, u[oc]);
+                }
+                float x[4][G];
 #pragma unroll
-                        for (int i = 0; i < G; ++i)
-                            dkacc[kh * 3 + kw][i] = fmaf(vw[kh][oc][i], x[oc + 2 - kw][i], dkacc[kh * 3 + kw][i]);
-            const int oh = gh - 1;
-            if (oh >= h0 && oh < h1) {
+                for (int j = 0; j < 4; ++j) load4(tb + (size_t)(r * TWH + col0 + j) * CB, x[j]);
 #pragma unroll
-                for (int oc = 0; oc < 2; ++oc) {
-                    if (!own[oc]) continue;
-                    const int ow = w0 + col0 + oc;
-                    const size_t o = (img + (size_t)oh * W + ow) * C + c0;
-                    float res[G];
+                for (int oc = 0; oc < 2; ++oc)
 #pragma unroll
-                    for (int i = 0; i < G; ++i) res[i] = acc[0][oc][i];
-                    if (RELU || stats) {
-                        float u[G];
-                        load4(in + o, u);  // re-read of a line fetched two rows ago (L1/L2 hit)
+                    for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
                         for (int i = 0; i < G; ++i) {
-                            if (RELU) {
-                                const float pre = AFFINE ? fmaf(u[i], av[i], bv[i]) : u[i];
-                                if (!(pre > 0.f)) res[i] = 0.f;
-                            }
-                            if (stats) {
-                                const float rr = round_to<T>(res[i]);
-                                s1[i] += rr;
-                                s2[i] = fmaf(rr, (u[i] - mu[i]) * rs[i], s2[i]);
+                            acc[0][oc][i] = fmaf(x[oc + kw][i], wt[6 + kw][i], acc[0][oc][i]);
+                            acc[1][oc][i] = fmaf(x[oc + kw][i], wt[3 + kw][i], acc[1][oc][i]);
+                            acc[2][oc][i] = fmaf(x[oc + kw][i], wt[0 + kw][i], acc[2][oc][i]);
+                        }
+                if (emit) {
+#pragma unroll
+                    for (int oc = 0; oc < 2; ++oc) {
+                        if (!own[oc]) continue;
+                        const int ow = w0 + col0 + oc;
+                        const size_t o = (img + (size_t)oh * W + ow) * C + c0;
+                        float res[G];
+#pragma unroll
+                        for (int i = 0; i < G; ++i) res[i] = acc[0][oc][i];
+                        if (RELU || stats) {
+#pragma unroll
+                            for (int i = 0; i < G; ++i) {
+                                if (RELU) {
+                                    const float pre = AFFINE ? fmaf(u[oc][i], av[i], bv[i]) : u[oc][i];
+                                    if (!(pre > 0.f)) res[i] = 0.f;
+                                }
+                                if (stats) {
+                                    const float rr = round_to<T>(res[i]);
+                                    s1[i] += rr;
+                                    s2[i] = fmaf(rr, u[oc][i], s2[i]);
+                                }
                             }
                         }
-                    }
-                    if (ep.add_src) {
-                        float m[G];
-                        load4(reinterpret_cast<const T*>(ep.add_src) + o, m);
+                        if (ep.add_src) {
+                            float m[G];
+                            load4(reinterpret_cast<const T*>(ep.add_src) + o, m);
 #pragma unroll
-                        for (int i = 0; i < G; ++i) res[i] += m[i];
-                    }
-                    if (ep.add_strided && ((oh | ow) & 1) == 0) {
-                        const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
-                        float m[G];
-                        load4(reinterpret_cast<const T*>(ep.add_strided) +
-                                  (((size_t)b * H2 + (oh >> 1)) * W2 + (ow >> 1)) * C + c0, m);
+                            for (int i = 0; i < G; ++i) res[i] += m[i];
+                        }
+                        if (ep.add_strided && ((oh | ow) & 1) == 0) {
+                            const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
+                            float m[G];
+                            load4(reinterpret_cast<const T*>(ep.add_strided) +
+                                      (((size_t)b * H2 + (oh >> 1)) * W2 + (ow >> 1)) * C + c0, m);
 #pragma unroll
-                        for (int i = 0; i < G; ++i) res[i] += m[i];
+                            for (int i = 0; i < G; ++i) res[i] += m[i];
+                        }
+                        store4(gin + o, res);
                     }
-                    store4(gin + o, res);
                 }
+#pragma unroll
+                for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+                    for (int i = 0; i < G; ++i) {
+                        acc[0][oc][i] = acc[1][oc][i];
+                        acc[1][oc][i] = acc[2][oc][i];
+                        acc[2][oc][i] = 0.f;
+                    }
             }
+        } else {
+            // ================= weight gradient: dk[kh][kw] += act(in)[gh+kh-1][c] * g[gh][c-kw+1] =================
+            auto load_v = [&](int row, float (&v)[2][G]) {
+                const bool rok = row >= h0 && row < h1;
+#pragma unroll
+                for (int oc = 0; oc < 2; ++oc) {
+                    if (rok && own[oc]) {
+                        load4(in + (img + (size_t)row * W + (w0 + col0 + oc)) * C + c0, v[oc]);
+#pragma unroll
+                        for (int i = 0; i < G; ++i) {
+                            float y = v[oc][i];
+                            if (AFFINE) y = fmaf(y, av[i], bv[i]);
+                            if (RELU) y = fmaxf(y, 0.f);
+                            v[oc][i] = y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < G; ++i) v[oc][i] = 0.f;
+                    }
+                }
+            };
+            float vw[3][2][G];  // act(in) rows gh-1, gh, gh+1 (zero outside the rows/cols this tile owns)
 #pragma unroll
             for (int oc = 0; oc < 2; ++oc)
 #pragma unroll
-                for (int i = 0; i < G; ++i) {
-                    acc[0][oc][i] = acc[1][oc][i];
-                    acc[1][oc][i] = acc[2][oc][i];
-                    acc[2][oc][i] = 0.f;
-                    vw[0][oc][i] = vw[1][oc][i];
-                    vw[1][oc][i] = vw[2][oc][i];
-                    vw[2][oc][i] = vnext[oc][i];
-                }
+                for (int i = 0; i < G; ++i) { vw[0][oc][i] = 0.f; vw[1][oc][i] = 0.f; }
+            load_v(h0, vw[2]);
+            mbar_wait(bar0 + 8 * cur, (uint32_t)(it >> 1) & 1u);
+            for (int r = 0; r < rows; ++r) {
+                const int gh = h0 - 1 + r;
+                float vnext[2][G];
+                load_v(gh + 2, vnext);  // prefetch for the next iteration
+                float x[4][G];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) load4(tb + (size_t)(r * TWH + col0 + j) * CB, x[j]);
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                        for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+                            for (int i = 0; i < G; ++i)
+                                dkacc[kh * 3 + kw][i] = fmaf(vw[kh][oc][i], x[oc + 2 - kw][i], dkacc[kh * 3 + kw][i]);
+#pragma unroll
+                for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+                    for (int i = 0; i < G; ++i) {
+                        vw[0][oc][i] = vw[1][oc][i];
+                        vw[1][oc][i] = vw[2][oc][i];
+                        vw[2][oc][i] = vnext[oc][i];
+                    }
+            }
         }
-        __syncthreads();
+        __syncthreads();  // both roles are done with buffer `cur` before it is refilled
     }
     // ---- CTA reduction over the column groups that share a channel group, then global atomics
     float* red = reinterpret_cast<float*>(smem);  // [ncolg][16][NV] — the tile buffers are idle now
     constexpr int NV = 9 * G + 2 * G;
     float* mine = red + ((size_t)colg * 16 + cg) * NV;
+    if (wg_role) {
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
+        for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int i = 0; i < G; ++i) mine[t * G + i] = dkacc[t][i];
+            for (int i = 0; i < G; ++i) mine[t * G + i] = dkacc[t][i];
+    } else {
 #pragma unroll
-    for (int i = 0; i < G; ++i) { mine[36 + i] = s1[i]; mine[36 + G + i] = s2[i]; }
+        for (int i = 0; i < G; ++i) { mine[36 + i] = s1[i]; mine[36 + G + i] = s2[i]; }
+    }
     __syncthreads();
     for (int e = threadIdx.x; e < 16 * NV; e += blockDim.x) {
         const int g = e / NV, v = e % NV;
@@ -424,8 +448,18 @@ __global__ void __launch_bounds__(256, 1) dw3x3_bwd_fused_kernel(
         if (c >= C) continue;
         float sum = 0.f;
         for (int q = 0; q < ncolg; ++q) sum += red[((size_t)q * 16 + g) * NV + v];
-        if (v < 36) atomicAdd(dk + (size_t)(v / G) * C + c, sum);
-        else if (stats) atomicAdd(stats + ((v - 36) / G) * (size_t)C + c, (double)sum);
+        if (v < 36) {
+            atomicAdd(dk + (size_t)(v / G) * C + c, sum);
+        } else if (stats) {
+            if (v < 36 + G) {
+                atomicAdd(stats + c, (double)sum);  // sum g
+            } else {
+                // sum g*xhat = rstd * (sum g*in - mean * sum g)
+                float sg = 0.f;
+                for (int q = 0; q < ncolg; ++q) sg += red[((size_t)q * 16 + g) * NV + (v - G)];
+                atomicAdd(stats + (size_t)C + c, (double)bn_rstd[c] * ((double)sum - (double)bn_mean[c] * (double)sg));
+            }
+        }
     }
 }
 
@@ -665,13 +699,14 @@ int launch_dw_bwd(const void* gout, const void* in, const float* k, const float*
                   const float* mean, const float* rstd, double* stats, void* gin, float* dk, int dtype, int B, int H,
                   int W, int C, DwEpilogue ep, cudaStream_t stream) {
     DwTiling t = dw_tiling(dtype, B, H, W, C);
-    const size_t red_bytes = (size_t)(t.threads / 16) * 16 * 44 * 4 + 128;
+    const size_t red_bytes = (size_t)(t.threads / 16) * 16 * 44 * 4 + 128;  // per role-half colgroups
     if (t.smem < red_bytes) t.smem = red_bytes;
     SPNET_REQUIRE(t.smem <= 200 * 1024, "dwconv3x3_bwd: tile does not fit shared memory");
     CUtensorMap tm;
     int rc = make_nhwc_map(&tm, gout, dtype, B, H, W, C, t.TW + 2, t.TH + 2);
     if (rc) return rc;
-    int per_sm = 256 / t.threads;  // ~170 registers per thread: one 256-thread CTA per SM
+    t.threads *= 2;                // data-gradient warps + weight-gradient warps
+    int per_sm = 512 / t.threads;  // <= 128 registers per thread
     if (per_sm < 1) per_sm = 1;
     const long long n_tiles = (long long)B * t.tiles_h * t.tiles_w;
     long long gx = (148LL * per_sm + t.chunks - 1) / t.chunks;

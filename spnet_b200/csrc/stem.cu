@@ -15,6 +15,40 @@
 
 namespace {
 
+// N contiguous elements <-> fp32 registers, 16-byte vectors when N allows it
+template <typename T, int N>
+__device__ __forceinline__ void load_row(const T* p, float (&v)[N]) {
+    constexpr int V = VecN<T>::N;
+    if constexpr (N % V == 0) {
+#pragma unroll
+        for (int c = 0; c < N / V; ++c) {
+            float t[V];
+            load_vec(p + c * V, t);
+#pragma unroll
+            for (int i = 0; i < V; ++i) v[c * V + i] = t[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = to_f32(p[i]);
+    }
+}
+template <typename T, int N>
+__device__ __forceinline__ void store_row(T* p, const float (&v)[N]) {
+    constexpr int V = VecN<T>::N;
+    if constexpr (N % V == 0) {
+#pragma unroll
+        for (int c = 0; c < N / V; ++c) {
+            float t[V];
+#pragma unroll
+            for (int i = 0; i < V; ++i) t[i] = v[c * V + i];
+            store_vec(p + c * V, t);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = from_f32<T>(v[i]);
+    }
+}
+
 __device__ __forceinline__ float apply_act(float y, int act) {
     if (act == 1) return fmaxf(y, 0.f);
     if (act == 2) return y > 0.f ? y : 0.1f * y;
@@ -71,12 +105,9 @@ __global__ void __launch_bounds__(256) conv_direct_fwd_kernel(const TI* __restri
                 }
             }
         }
-        TO* o = out + idx * COUT;
+        store_row<TO, COUT>(out + idx * COUT, acc);
 #pragma unroll
-        for (int co = 0; co < COUT; ++co) {
-            o[co] = from_f32<TO>(acc[co]);
-            acc[co] = round_to<TO>(acc[co]);
-        }
+        for (int co = 0; co < COUT; ++co) acc[co] = round_to<TO>(acc[co]);
         if (POOL_SKIP) skip[idx] = from_f32<TO>(0.25f * centre);
     }
     if (stats) {
@@ -119,8 +150,7 @@ __global__ void __launch_bounds__(256) conv_direct_wgrad_px_kernel(const TI* __r
         const int oh = (int)((idx / OW) % OH);
         const int b = (int)(idx / ((long long)OW * OH));
         float gv[COUT];
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) gv[co] = to_f32(g[idx * COUT + co]);
+        load_row<TG, COUT>(g + idx * COUT, gv);
 #pragma unroll
         for (int kh = 0; kh < KS; ++kh) {
             const int ih = oh * S - pt + kh;
@@ -235,13 +265,13 @@ __global__ void __launch_bounds__(256) conv_direct_dgrad_kernel(const TG* __rest
             if (u < 0 || u % S != 0) continue;
             const int ow = u / S;
             if (ow >= OW) continue;
-            const TG* gp = g + (((size_t)b * OH + oh) * OW + ow) * COUT;
+            float gv[COUT];
+            load_row<TG, COUT>(g + (((size_t)b * OH + oh) * OW + ow) * COUT, gv);
 #pragma unroll
             for (int co = 0; co < COUT; ++co) {
-                const float gv = to_f32(gp[co]);
 #pragma unroll
                 for (int ci = 0; ci < CIN; ++ci)
-                    acc[ci] = fmaf(gv, ws[((kh * KS + kw) * CIN + ci) * COUT + co], acc[ci]);
+                    acc[ci] = fmaf(gv[co], ws[((kh * KS + kw) * CIN + ci) * COUT + co], acc[ci]);
             }
         }
     }
