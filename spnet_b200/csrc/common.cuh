@@ -80,6 +80,22 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Column sums of a 32x32 block held one row per lane (v[j] = element (lane, j)): after the
+// butterfly lane L holds sum_rows element(row, L). 31 shuffles instead of 32*5. Destroys v.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = upper ? v[i] : v[i + off];
+            const float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
 // dispatch on activation dtype code
 #define SPNET_DISPATCH_DTYPE(dtype, ...)                                   \
     do {                                                                   \

@@ -39,6 +39,19 @@ __device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
     *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
 }
 
+// raw (not yet widened) 4-channel group: lets a global load be issued early and consumed late —
+// the first instruction that touches the loaded register is where an in-order warp stalls
+template <typename T> struct Raw4;
+template <> struct Raw4<float> { float4 r; };
+template <> struct Raw4<bf16> { uint2 r; };
+__device__ __forceinline__ Raw4<float> load_raw4(const float* p) { Raw4<float> x; x.r = *reinterpret_cast<const float4*>(p); return x; }
+__device__ __forceinline__ Raw4<bf16> load_raw4(const bf16* p) { Raw4<bf16> x; x.r = *reinterpret_cast<const uint2*>(p); return x; }
+__device__ __forceinline__ void unpack4(const Raw4<float>& x, float (&v)[4]) { v[0] = x.r.x; v[1] = x.r.y; v[2] = x.r.z; v[3] = x.r.w; }
+__device__ __forceinline__ void unpack4(const Raw4<bf16>& x, float (&v)[4]) {
+    v[0] = __uint_as_float(x.r.x << 16); v[1] = __uint_as_float(x.r.x & 0xffff0000u);
+    v[2] = __uint_as_float(x.r.y << 16); v[3] = __uint_as_float(x.r.y & 0xffff0000u);
+}
+
 constexpr int DW_CB = 64;   // channels per CTA (one TMA box is CB channels wide)
 constexpr int DW_G = 4;     // channels per thread
 
@@ -304,11 +317,11 @@ __global__ void __launch_bounds__(512, 1) dw3x3_bwd_fused_kernel(
             for (int r = 0; r < rows; ++r) {
                 const int oh = h0 - 2 + r;  // output row completed by gradient row gh = oh + 1
                 const bool emit = oh >= h0 && oh < h1;
-                float u[2][G];
-                if (emit && (RELU || stats)) {  // issue the loads early; consumed after the FMAs
+                Raw4<T> ru[2];
+                if (emit && (RELU || stats)) {  // issued early, widened only after the FMAs below
 #pragma unroll
                     for (int oc = 0; oc < 2; ++oc)
-                        if (own[oc]) load4(in + (img + (size_t)oh * W + (w0 + col0 + oc)) * C + c0, u[oc]);
+                        if (own[oc]) ru[oc] = load_raw4(in + (img + (size_t)oh * W + (w0 + col0 + oc)) * C + c0);
                 }
                 float x[4][G];
 #pragma unroll
@@ -333,16 +346,18 @@ __global__ void __launch_bounds__(512, 1) dw3x3_bwd_fused_kernel(
 #pragma unroll
                         for (int i = 0; i < G; ++i) res[i] = acc[0][oc][i];
                         if (RELU || stats) {
+                            float u[G];
+                            unpack4(ru[oc], u);
 #pragma unroll
                             for (int i = 0; i < G; ++i) {
                                 if (RELU) {
-                                    const float pre = AFFINE ? fmaf(u[oc][i], av[i], bv[i]) : u[oc][i];
+                                    const float pre = AFFINE ? fmaf(u[i], av[i], bv[i]) : u[i];
                                     if (!(pre > 0.f)) res[i] = 0.f;
                                 }
                                 if (stats) {
                                     const float rr = round_to<T>(res[i]);
                                     s1[i] += rr;
-                                    s2[i] = fmaf(rr, u[oc][i], s2[i]);
+                                    s2[i] = fmaf(rr, u[i], s2[i]);
                                 }
                             }
                         }
@@ -374,12 +389,20 @@ __global__ void __launch_bounds__(512, 1) dw3x3_bwd_fused_kernel(
             }
         } else {
             // ================= weight gradient: dk[kh][kw] += act(in)[gh+kh-1][c] * g[gh][c-kw+1] =================
-            auto load_v = [&](int row, float (&v)[2][G]) {
+            auto fetch_v = [&](int row, Raw4<T> (&rv)[2]) -> bool {  // raw loads of an owned centre row
                 const bool rok = row >= h0 && row < h1;
+                if (rok) {
+#pragma unroll
+                    for (int oc = 0; oc < 2; ++oc)
+                        if (own[oc]) rv[oc] = load_raw4(in + (img + (size_t)row * W + (w0 + col0 + oc)) * C + c0);
+                }
+                return rok;
+            };
+            auto widen_v = [&](bool rok, const Raw4<T> (&rv)[2], float (&v)[2][G]) {  // act(in), zero if not owned
 #pragma unroll
                 for (int oc = 0; oc < 2; ++oc) {
                     if (rok && own[oc]) {
-                        load4(in + (img + (size_t)row * W + (w0 + col0 + oc)) * C + c0, v[oc]);
+                        unpack4(rv[oc], v[oc]);
 #pragma unroll
                         for (int i = 0; i < G; ++i) {
                             float y = v[oc][i];
@@ -398,12 +421,13 @@ __global__ void __launch_bounds__(512, 1) dw3x3_bwd_fused_kernel(
             for (int oc = 0; oc < 2; ++oc)
 #pragma unroll
                 for (int i = 0; i < G; ++i) { vw[0][oc][i] = 0.f; vw[1][oc][i] = 0.f; }
-            load_v(h0, vw[2]);
+            Raw4<T> rfirst[2], rnext[2];
+            const bool ok_first = fetch_v(h0, rfirst);
+            bool ok_next = fetch_v(h0 + 1, rnext);  // row needed by iteration r = 1, in flight during r = 0
+            widen_v(ok_first, rfirst, vw[2]);
             mbar_wait(bar0 + 8 * cur, (uint32_t)(it >> 1) & 1u);
             for (int r = 0; r < rows; ++r) {
                 const int gh = h0 - 1 + r;
-                float vnext[2][G];
-                load_v(gh + 2, vnext);  // prefetch for the next iteration
                 float x[4][G];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) load4(tb + (size_t)(r * TWH + col0 + j) * CB, x[j]);
@@ -416,14 +440,16 @@ __global__ void __launch_bounds__(512, 1) dw3x3_bwd_fused_kernel(
 #pragma unroll
                             for (int i = 0; i < G; ++i)
                                 dkacc[kh * 3 + kw][i] = fmaf(vw[kh][oc][i], x[oc + 2 - kw][i], dkacc[kh * 3 + kw][i]);
+                // rotate the window: row gh+2 was fetched one iteration ago, widen it only now
 #pragma unroll
                 for (int oc = 0; oc < 2; ++oc)
 #pragma unroll
                     for (int i = 0; i < G; ++i) {
                         vw[0][oc][i] = vw[1][oc][i];
                         vw[1][oc][i] = vw[2][oc][i];
-                        vw[2][oc][i] = vnext[oc][i];
                     }
+                widen_v(ok_next, rnext, vw[2]);
+                ok_next = fetch_v(gh + 3, rnext);
             }
         }
         __syncthreads();  // both roles are done with buffer `cur` before it is refilled

@@ -85,22 +85,6 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// Column sums of a 32x32 block held one row per lane (v[j] = element (lane, j)): after the
-// butterfly lane L holds sum_rows element(row, L). 31 shuffles instead of 32*5.
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < off; ++i) {
-            const float send = upper ? v[i] : v[i + off];
-            const float keep = upper ? v[i + off] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-    return v[0];
-}
-
 // Persistent, warp-specialised kernel. One CTA per SM walks work units (split, m-tile, n-tile):
 //   warp 0      TMA producer   : fills the STAGES-deep smem ring
 //   warp 1      MMA issuer     : one elected lane issues tcgen05.mma into one of TWO TMEM accumulators

@@ -30,8 +30,9 @@ __global__ void __launch_bounds__(256) maxpool_add_fwd_kernel(const T* __restric
     const long long n = (long long)B * OH * OW * CV;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
-    const int cv = (int)(idx % CV);
-    long long r = idx / CV;
+    const unsigned uidx = (unsigned)idx;  // host guarantees < 2^31 items: 32-bit div/mod only
+    const int cv = (int)(uidx % CV);
+    unsigned r = uidx / CV;
     const int ow = (int)(r % OW);
     r /= OW;
     const int oh = (int)(r % OH);
@@ -87,8 +88,9 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ 
     const long long n = (long long)B * H * W * CV;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
-    const int cv = (int)(idx % CV);
-    long long r = idx / CV;
+    const unsigned uidx = (unsigned)idx;
+    const int cv = (int)(uidx % CV);
+    unsigned r = uidx / CV;
     const int w = (int)(r % W);
     r /= W;
     const int h = (int)(r % H);
@@ -139,8 +141,9 @@ __global__ void __launch_bounds__(256) gather_s2_kernel(const T* __restrict__ in
     const long long n = (long long)B * OH * OW * CV;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
-    const int cv = (int)(idx % CV);
-    long long r = idx / CV;
+    const unsigned uidx = (unsigned)idx;  // host guarantees < 2^31 items: 32-bit div/mod only
+    const int cv = (int)(uidx % CV);
+    unsigned r = uidx / CV;
     const int ow = (int)(r % OW);
     r /= OW;
     const int oh = (int)(r % OH);
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(256) gather_s2_kernel(const T* __restrict__ in
 
 int check_pool(const char* who, int dtype, int B, int H, int W, int C) {
     SPNET_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "%s: bad shape", who);
+    SPNET_REQUIRE((long long)B * H * W * C < 0x7fffffffLL, "%s: tensor too large for 32-bit indexing", who);
     const int V = dtype == SPNET_BF16 ? 8 : 4;
     SPNET_REQUIRE(C % V == 0, "%s: C=%d must be a multiple of %d", who, C, V);
     return SPNET_OK;

@@ -81,9 +81,10 @@ __global__ void __launch_bounds__(256) conv_direct_fwd_kernel(const TI* __restri
 #pragma unroll
     for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
     if (valid) {
-        const int ow = (int)(idx % OW);
-        const int oh = (int)((idx / OW) % OH);
-        const int b = (int)(idx / ((long long)OW * OH));
+        const int pix = (int)idx;  // host guarantees < 2^31 pixels: 32-bit div/mod only
+        const int ow = pix % OW;
+        const int oh = (pix / OW) % OH;
+        const int b = pix / (OW * OH);
         float centre = 0.f;
 #pragma unroll
         for (int kh = 0; kh < KS; ++kh) {
@@ -111,11 +112,23 @@ __global__ void __launch_bounds__(256) conv_direct_fwd_kernel(const TI* __restri
         if (POOL_SKIP) skip[idx] = from_f32<TO>(0.25f * centre);
     }
     if (stats) {
+        if constexpr (COUT == 32) {
+            // lane = pixel, 32 channels per lane: 31-shuffle butterfly leaves channel `lane`'s sum in each lane
+            float sq[32];
 #pragma unroll
-        for (int co = 0; co < COUT; ++co) {
-            const float s = warp_sum(acc[co]);
-            const float q = warp_sum(acc[co] * acc[co]);
-            if ((threadIdx.x & 31) == 0) { atomicAdd(&sred[0][co], s); atomicAdd(&sred[1][co], q); }
+            for (int co = 0; co < 32; ++co) sq[co] = acc[co] * acc[co];
+            const int lane = threadIdx.x & 31;
+            const float s = warp_colsum32(acc, lane);
+            const float q = warp_colsum32(sq, lane);
+            atomicAdd(&sred[0][lane], s);
+            atomicAdd(&sred[1][lane], q);
+        } else {
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                const float s = warp_sum(acc[co]);
+                const float q = warp_sum(acc[co] * acc[co]);
+                if ((threadIdx.x & 31) == 0) { atomicAdd(&sred[0][co], s); atomicAdd(&sred[1][co], q); }
+            }
         }
         __syncthreads();
         if (threadIdx.x < COUT) {
@@ -146,9 +159,10 @@ __global__ void __launch_bounds__(256) conv_direct_wgrad_px_kernel(const TI* __r
     const long long n = (long long)B * OH * OW;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
          idx += (long long)gridDim.x * blockDim.x) {
-        const int ow = (int)(idx % OW);
-        const int oh = (int)((idx / OW) % OH);
-        const int b = (int)(idx / ((long long)OW * OH));
+        const int pix = (int)idx;  // host guarantees < 2^31 pixels: 32-bit div/mod only
+        const int ow = pix % OW;
+        const int oh = (pix / OW) % OH;
+        const int b = pix / (OW * OH);
         float gv[COUT];
         load_row<TG, COUT>(g + idx * COUT, gv);
 #pragma unroll
@@ -204,10 +218,11 @@ __global__ void __launch_bounds__(256) conv_direct_wgrad_lane_kernel(const TI* _
     for (int ci = 0; ci < CIN; ++ci) { a[ci] = in_a ? in_a[ci] : 1.f; bb[ci] = in_a ? in_b[ci] : 0.f; }
     const long long n = (long long)B * OH * OW;
     for (long long idx = warp; idx < n; idx += nwarps) {
-        const int ow = (int)(idx % OW);
-        const int oh = (int)((idx / OW) % OH);
-        const int b = (int)(idx / ((long long)OW * OH));
-        const float gv = to_f32(g[idx * 32 + lane]);
+        const int pix = (int)idx;  // host guarantees < 2^31 pixels: 32-bit div/mod only
+        const int ow = pix % OW;
+        const int oh = (pix / OW) % OH;
+        const int b = pix / (OW * OH);
+        const float gv = to_f32(g[(size_t)idx * 32 + lane]);
 #pragma unroll
         for (int kh = 0; kh < KS; ++kh) {
             const int ih = oh * S - pt + kh;
@@ -247,9 +262,10 @@ __global__ void __launch_bounds__(256) conv_direct_dgrad_kernel(const TG* __rest
     const long long n = (long long)B * H * W;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
-    const int iw = (int)(idx % W);
-    const int ih = (int)((idx / W) % H);
-    const int b = (int)(idx / ((long long)W * H));
+    const int pix = (int)idx;
+    const int iw = pix % W;
+    const int ih = (pix / W) % H;
+    const int b = pix / (W * H);
     float acc[CIN];
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) acc[ci] = 0.f;
@@ -402,8 +418,9 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const T* __restrict__ in
     const long long n = (long long)B * OH * OW * 9 * CV;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
-    const int cv = (int)(idx % CV);
-    long long r = idx / CV;
+    const unsigned uidx = (unsigned)idx;  // host guarantees < 2^31 items
+    const int cv = (int)(uidx % CV);
+    unsigned r = uidx / CV;
     const int tap = (int)(r % 9);
     r /= 9;
     const int ow = (int)(r % OW);
@@ -432,8 +449,9 @@ __global__ void __launch_bounds__(256) col2im3x3_kernel(const T* __restrict__ gc
     const long long n = (long long)B * H * W * CV;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
-    const int cv = (int)(idx % CV);
-    long long r = idx / CV;
+    const unsigned uidx = (unsigned)idx;
+    const int cv = (int)(uidx % CV);
+    unsigned r = uidx / CV;
     const int iw = (int)(r % W);
     r /= W;
     const int ih = (int)(r % H);
