@@ -278,6 +278,16 @@ def run_ours(args, rank, world):
                             "frac": ach / peaks["tf_sust"], "traffic": None, "kernel": "gemm_tc_kernel (tcgen05)",
                             "share_of_step": ms / total_ms, "launches": nl // psteps, "avg_launch_ms": ms / max(nl, 1),
                             "algorithmic_flops_per_step": nf // psteps}
+    # per-shape view of the GEMMs (M,N,K,a_mn,b_mn): time, TFLOP/s
+    shapes = {}
+    for a, ms in fam.get("spnet_gemm_bf16", {"items": []})["items"]:
+        key = (a[9], a[10], a[11], a[2], a[5])
+        d = shapes.setdefault(key, [0, 0.0])
+        d[0] += 1
+        d[1] += ms
+    gemm_shapes = [{"M": k[0], "N": k[1], "K": k[2], "a_mn": k[3], "b_mn": k[4], "launches_per_step": v[0] // psteps,
+                    "us_each": round(1e3 * v[1] / v[0], 1), "tflops": round(2.0 * k[0] * k[1] * k[2] / (v[1] / v[0] * 1e-3) / 1e12, 1)}
+                   for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:10]]
     dominant = max(roofs.values(), key=lambda r: r["share_of_step"])
     other = [r for r in roofs.values() if r is not dominant]
 
@@ -296,7 +306,7 @@ def run_ours(args, rank, world):
            "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                    "h2d_bytes_per_step": int(B * (H * W * 4 + N_OUT * 4)), "d2h_bytes_per_step": 24},
            "gpu_launches": int(launches_per_step * args.steps * 2),
-           "roofline": dominant, "roofline_other": other, "kernel_breakdown": breakdown,
+           "roofline": dominant, "roofline_other": other, "kernel_breakdown": breakdown, "gemm_shapes": gemm_shapes,
            "peaks": peaks, "cpu_baseline": cpu}
     print(json.dumps(out), flush=True)
 
@@ -335,6 +345,10 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    # keep stdout clean for the single JSON line (NCCL prints its version banner to stdout)
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if world > 1:
         import torch
         import torch.distributed as dist

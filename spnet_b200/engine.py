@@ -386,12 +386,12 @@ class XceptionSPNetEngine:
                       add_strided=g_xs.view(B, oh, ow, cin))
         return g_x
 
-    def backward(self):
-        """Consumes self.gy (dL/dy_pred); accumulates into self.grads (zeroed by the caller)."""
-        B, sh, w, g = self.B, self.shapes, self.w, self.g
-        G1, G2, G3, S, R0, R1 = self.scratch
+    def backward_head(self):
+        """Dense head: consumes self.gy (dL/dy_pred) -> FinalOutput gradients + dL/dfeatures.
+        Its weight gradient is 73 % of all gradient bytes and is complete first: under data
+        parallelism its all-reduce is launched right after this and overlaps backward_body()."""
+        B, g = self.B, self.g
         F = self.feat.shape[1]
-        # ---- Dense head
         if self.lowp:
             ops.cast_f32_to_bf16(self.gy, self.gyl)
         ops.colsum(self.gy, g["FinalOutput/bias"])
@@ -399,6 +399,15 @@ class XceptionSPNetEngine:
                  lda=F, ldb=self.n_out)
         ops.gemm(self.gyl, False, self.wl["FinalOutput/kernel"], False, self.gfeat, B, F, self.n_out,
                  out_mode=ops.OUT_T, ldb=self.n_out)
+
+    def backward(self):
+        """Consumes self.gy; accumulates into self.grads (zeroed by the caller)."""
+        self.backward_head()
+        self.backward_body()
+
+    def backward_body(self):
+        B, sh, w, g = self.B, self.shapes, self.w, self.g
+        G1, G2, G3, S, R0, R1 = self.scratch
         # ---- block 14
         s1, s2 = self.sep14
         fh, fw = sh["out13"]
@@ -478,13 +487,26 @@ class XceptionSPNetEngine:
         ops.adam_keras_step(self.params, self.grads, self.adam_m, self.adam_v, self.lr_t_dev, n_l2=self.n_l2 if self.use_l2 else 0,
                             l2=arch.L2_COEF, grad_scale=grad_scale, p_bf16=self.params_lp)
 
-    def _step_body(self):
+    def _step_part1(self):
         self.grads.zero_()
         self.forward(training=True)
         self.loss(with_grad=True)
-        self.backward()
+        self.backward_head()
+
+    def _step_part2(self):
+        self.backward_body()
         if self.grad_hook is None:
             self.optimizer_step()
+
+    def _step_body(self):
+        self._step_part1()
+        self._head_ready()
+        self._step_part2()
+
+    def _head_ready(self):
+        fn = getattr(self.grad_hook, "head_bucket_ready", None)
+        if fn is not None:
+            fn(self)
 
     def set_lr(self, lr, beta1=0.9, beta2=0.999):
         """Host side of Keras Adam: t += 1, lr_t = lr*sqrt(1-b2^t)/(1-b1^t) -> device scalar."""
@@ -497,10 +519,19 @@ class XceptionSPNetEngine:
 
     def capture(self):
         """Capture fwd+loss+bwd(+Adam) into one CUDA graph (call after one eager warm-up step)."""
-        gph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gph):
-            self._step_body()
-        self.graph = gph
+        if getattr(self.grad_hook, "head_bucket_ready", None) is None:
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                self._step_body()
+            self.graph = (gph,)
+        else:
+            # two graphs so that the Dense-head all-reduce can be launched between them
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._step_part1()
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                self._step_part2()
+            self.graph = (g1, g2)
 
     def train_step(self, lr):
         """One optimiser step on the batch currently in self.x0 / self.y_true.
@@ -508,7 +539,10 @@ class XceptionSPNetEngine:
         the L2 term is in self.l2_out."""
         self.set_lr(lr)
         if self.graph is not None:
-            self.graph.replay()
+            self.graph[0].replay()
+            if len(self.graph) > 1:
+                self._head_ready()
+                self.graph[1].replay()
         else:
             self._step_body()
         if self.grad_hook is not None:
