@@ -17,6 +17,7 @@
 // Epilogue modes: store bf16, store fp32, atomic-add fp32 (split-K); optional fused
 // per-column sum / sum-of-squares (BatchNorm batch statistics) accumulated in fp64.
 #include "tma.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -75,6 +76,28 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;
 }
 
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -90,7 +113,10 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 //   warp 1      MMA issuer     : one elected lane issues tcgen05.mma into one of TWO TMEM accumulators
 //   warps 2..5  epilogue       : drain the other accumulator (tcgen05.ld -> convert -> global, fused
 //                                BatchNorm column statistics) while the next unit's MMAs run
-template <int BN, bool A_MN, bool B_MN, int STAGES>
+// CL = 2: CTA pairs (thread-block cluster of 2 along M). Both CTAs of a pair work on the same
+// n-tile and k-range with adjacent m-tiles; each loads its own A tile and HALF of the shared B tile,
+// multicast by TMA into both CTAs' shared memory, so the pair reads B from L2 once.
+template <int BN, bool A_MN, bool B_MN, int STAGES, int CL>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB, GemmEpi epi,
                                                               int M, int N, int K, int kb_per_split, int tiles_m,
@@ -107,6 +133,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_kb = (K + BK - 1) / BK;
+    const uint32_t crank = CL > 1 ? cluster_cta_rank() : 0u;
+    const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
     const uint32_t full0 = smem_u32(&bars[0]);
     const uint32_t empty0 = smem_u32(&bars[STAGES]);
     const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]);
@@ -115,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, CL);  // every CTA of the cluster must have consumed the stage
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull0 + 8 * a, 1);
@@ -131,21 +160,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();  // barrier inits visible cluster-wide
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_holder;
+    // with CL = 2, tiles_m counts m-tile PAIRS; this CTA owns m-tile 2*pair + rank
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
-        uint32_t it = 0;  // running k-block counter across units
-        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        uint32_t ps = 0, pph = 0;  // running stage / phase across units
+        for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
             const int n0 = (unit % tiles_n) * BN;
-            const int m0 = ((unit / tiles_n) % tiles_m) * BM;
+            const int m0 = (((unit / tiles_n) % tiles_m) * CL + (int)crank) * BM;
             const int kb_begin = (unit / (tiles_n * tiles_m)) * kb_per_split;
             const int nkb = min(total_kb, kb_begin + kb_per_split) - kb_begin;
-            for (int i = 0; i < nkb; ++i, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1u;
+            for (int i = 0; i < nkb; ++i) {
+                const uint32_t s = ps, ph = pph;
+                if (++ps == STAGES) { ps = 0; pph ^= 1u; }
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
@@ -159,12 +189,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     } else {
                         tma_load_2d(sa, &tmA, full0 + 8 * s, k0, m0);
                     }
-                    if (B_MN) {
+                    if (CL == 1) {
+                        if (B_MN) {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j)
-                            tma_load_2d(sb + j * (BK * 128), &tmB, full0 + 8 * s, n0 + 64 * j, k0);
+                            for (int j = 0; j < BN / 64; ++j)
+                                tma_load_2d(sb + j * (BK * 128), &tmB, full0 + 8 * s, n0 + 64 * j, k0);
+                        } else {
+                            tma_load_2d(sb, &tmB, full0 + 8 * s, k0, n0);
+                        }
                     } else {
-                        tma_load_2d(sb, &tmB, full0 + 8 * s, k0, n0);
+                        // this CTA's half of the B tile, written into BOTH CTAs' stage (same smem offset,
+                        // completing on the same barrier offset in each destination CTA)
+                        if (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < BN / 64 / CL; ++j) {
+                                const int jj = (int)crank * (BN / 64 / CL) + j;
+                                tma_load_2d_mc(sb + jj * (BK * 128), &tmB, full0 + 8 * s, n0 + 64 * jj, k0, kMask);
+                            }
+                        } else {
+                            const int r0 = (int)crank * (BN / CL);
+                            tma_load_2d_mc(sb + r0 * 128, &tmB, full0 + 8 * s, k0, n0 + r0, kMask);
+                        }
                     }
                 }
                 __syncwarp();
@@ -175,34 +220,40 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         // instruction descriptor: fp32 accumulate, bf16 x bf16, majors, N>>3, M>>4
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
                                ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        uint32_t it = 0, u = 0;
-        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++u) {
+        // Shared-memory descriptors differ between stages / k-steps only in the 14-bit address field of
+        // the low word: build the constant parts once so the per-MMA issue cost is a couple of adds.
+        const uint32_t a_lbo = A_MN ? (uint32_t)(BK * 128) : 0u, b_lbo = B_MN ? (uint32_t)(BK * 128) : 0u;
+        const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B, version 1, SWIZZLE_128B
+        const uint32_t a_lo_base = ((a_lbo >> 4) << 16) + ((smem_u32(smem) & 0x3ffffu) >> 4);
+        const uint32_t b_lo_base = ((b_lbo >> 4) << 16) + (((smem_u32(smem) + A_BYTES) & 0x3ffffu) >> 4);
+        constexpr uint32_t A_KSTEP = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+        constexpr uint32_t B_KSTEP = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+        constexpr uint32_t STAGE_STEP = STAGE_BYTES >> 4;
+        uint32_t s = 0, ph = 0, u = 0;
+        for (int unit = cluster_id; unit < n_units; unit += n_clusters, ++u) {
             const int kb_begin = (unit / (tiles_n * tiles_m)) * kb_per_split;
             const int nkb = min(total_kb, kb_begin + kb_per_split) - kb_begin;
             const uint32_t as = u & 1u;
             mbar_wait(tempty0 + 8 * as, ((u >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tacc = tmem_base + as * BN;
-            for (int i = 0; i < nkb; ++i, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1u;
+            for (int i = 0; i < nkb; ++i) {
                 mbar_wait(full0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
-                    const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-                    const uint32_t sb = sa + A_BYTES;
+                    const uint32_t a_lo = a_lo_base + s * STAGE_STEP, b_lo = b_lo_base + s * STAGE_STEP;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t ad = A_MN ? make_smem_desc(sa + k * (UMMA_K * 128), BK * 128, 1024)
-                                                 : make_smem_desc(sa + k * (UMMA_K * 2), 0, 1024);
-                        const uint64_t bd = B_MN ? make_smem_desc(sb + k * (UMMA_K * 128), BK * 128, 1024)
-                                                 : make_smem_desc(sb + k * (UMMA_K * 2), 0, 1024);
+                        const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * A_KSTEP);
+                        const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * B_KSTEP);
                         umma_bf16(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(empty0 + 8 * s);                     // frees the smem stage when these MMAs retire
+                    // frees the smem stage (in every CTA of the cluster) when these MMAs retire
+                    if (CL > 1) umma_commit_mc(empty0 + 8 * s, kMask); else umma_commit(empty0 + 8 * s);
                     if (i == nkb - 1) umma_commit(tfull0 + 8 * as);  // accumulator complete
                 }
                 __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
     } else {
@@ -210,9 +261,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int q = warp & 3;       // TMEM lane quadrant this warp may access
         const int et = q * 32 + lane;  // 0..127 within the epilogue group
         uint32_t u = 0;
-        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++u) {
+        for (int unit = cluster_id; unit < n_units; unit += n_clusters, ++u) {
             const int n0 = (unit % tiles_n) * BN;
-            const int m0 = ((unit / tiles_n) % tiles_m) * BM;
+            const int m0 = (((unit / tiles_n) % tiles_m) * CL + (int)crank) * BM;
             const uint32_t as = u & 1u;
             mbar_wait(tfull0 + 8 * as, (u >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -290,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();  // no CTA may exit while its peer still multicasts into it
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN))
                      : "memory");
@@ -329,12 +380,12 @@ int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long lon
     return SPNET_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CL>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmEpi epi, int M, int N, int K, int splits,
                 cudaStream_t stream) {
     constexpr int STAGES = (BN <= 128) ? 6 : 4;
     constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
-    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES>;
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, CL>;
     static bool configured = false;
     static int num_sms = 148;
     if (!configured) {
@@ -353,14 +404,36 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmEpi epi, int M
     if (splits > total_kb) splits = total_kb;
     const int kbps = (total_kb + splits - 1) / splits;
     splits = (total_kb + kbps - 1) / kbps;  // no empty splits
-    const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    const int tiles_m = ((M + BM - 1) / BM + CL - 1) / CL;  // m-tile groups of CL
+    const int tiles_n = (N + BN - 1) / BN;
     const long long units = (long long)tiles_m * tiles_n * splits;
     if (units > 0x7fffffffLL) {
         spnet_set_error("gemm_bf16: too many tiles");
         return SPNET_ERR_ARG;
     }
-    const int grid = (int)(units < num_sms ? units : num_sms);
-    kern<<<grid, kThreads, smem, stream>>>(ta, tb, epi, M, N, K, kbps, tiles_m, tiles_n, (int)units);
+    const int max_clusters = num_sms / CL;
+    const int grid = (int)(units < max_clusters ? units : max_clusters) * CL;
+    if (CL == 1) {
+        kern<<<grid, kThreads, smem, stream>>>(ta, tb, epi, M, N, K, kbps, tiles_m, tiles_n, (int)units);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, epi, M, N, K, kbps, tiles_m, tiles_n, (int)units);
+        if (e != cudaSuccess) {
+            spnet_set_error("gemm_bf16: cluster launch: %s", cudaGetErrorString(e));
+            return SPNET_ERR_CUDA;
+        }
+    }
     return spnet_check_launch("gemm_bf16");
 }
 
@@ -391,23 +464,26 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
     // 128x256 tiles when N is wide: one A tile then feeds 256 output columns, which cuts the
     // L2->SM operand traffic per FLOP by a third (the 128x128 kernel is L2-bandwidth bound).
     const bool wide = N >= 512;
+    // CTA pairs (B tile multicast) when there are at least two m-tiles to pair up
+    const bool pair = wide && M > BM && getenv("SPNET_B200_NO_CLUSTER") == nullptr;
     CUtensorMap ta, tb;
     int rc = make_operand_map(&ta, A, M, K, lda, a_mn != 0, BM);
     if (rc) return rc;
-    rc = make_operand_map(&tb, B, N, K, ldb, b_mn != 0, wide ? 256 : 128);
+    rc = make_operand_map(&tb, B, N, K, ldb, b_mn != 0, wide ? (pair ? 128 : 256) : 128);
     if (rc) return rc;
     GemmEpi epi = {D, ldd, out_mode, colstats};
-#define SPNET_GEMM_DISPATCH(BN_)                                                                        \
-    do {                                                                                                \
-        if (a_mn) {                                                                                     \
-            if (b_mn) return launch_gemm<BN_, true, true>(ta, tb, epi, M, N, K, splits, stream);        \
-            return launch_gemm<BN_, true, false>(ta, tb, epi, M, N, K, splits, stream);                 \
-        }                                                                                               \
-        if (b_mn) return launch_gemm<BN_, false, true>(ta, tb, epi, M, N, K, splits, stream);           \
-        return launch_gemm<BN_, false, false>(ta, tb, epi, M, N, K, splits, stream);                    \
+#define SPNET_GEMM_DISPATCH(BN_, CL_)                                                                    \
+    do {                                                                                                 \
+        if (a_mn) {                                                                                      \
+            if (b_mn) return launch_gemm<BN_, true, true, CL_>(ta, tb, epi, M, N, K, splits, stream);    \
+            return launch_gemm<BN_, true, false, CL_>(ta, tb, epi, M, N, K, splits, stream);             \
+        }                                                                                                \
+        if (b_mn) return launch_gemm<BN_, false, true, CL_>(ta, tb, epi, M, N, K, splits, stream);       \
+        return launch_gemm<BN_, false, false, CL_>(ta, tb, epi, M, N, K, splits, stream);                \
     } while (0)
-    if (wide) SPNET_GEMM_DISPATCH(256);
-    SPNET_GEMM_DISPATCH(128);
+    if (pair) SPNET_GEMM_DISPATCH(256, 2);
+    if (wide) SPNET_GEMM_DISPATCH(256, 1);
+    SPNET_GEMM_DISPATCH(128, 1);
 #undef SPNET_GEMM_DISPATCH
 }
 
