@@ -55,31 +55,72 @@ __device__ __forceinline__ void unpack4(const Raw4<bf16>& x, float (&v)[4]) {
 constexpr int DW_CB = 64;   // channels per CTA (one TMA box is CB channels wide)
 constexpr int DW_G = 4;     // channels per thread
 
+// ---- shared-memory reads through 32-bit shared-window addresses (LDS, no generic-address math) ----
+__device__ __forceinline__ void lds4(uint32_t addr, float (&v)[4], const float*) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ void lds4(uint32_t addr, float (&v)[4], const bf16*) {
+    uint32_t a, b;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
+    v[0] = __uint_as_float(a << 16); v[1] = __uint_as_float(a & 0xffff0000u);
+    v[2] = __uint_as_float(b << 16); v[3] = __uint_as_float(b & 0xffff0000u);
+}
+
+// One gradient/input row (4 staged columns x 4 channels) into three running accumulators:
+// P completes with tap row 2, Q gets tap row 1, R starts with tap row 0.
+__device__ __forceinline__ void dw_row_fma(const float (&x)[4][DW_G], const float (&wt)[9][DW_G], float (&P)[2][DW_G],
+                                           float (&Q)[2][DW_G], float (&R)[2][DW_G]) {
+#pragma unroll
+    for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int i = 0; i < DW_G; ++i) {
+                P[oc][i] = fmaf(x[oc + kw][i], wt[6 + kw][i], P[oc][i]);
+                Q[oc][i] = fmaf(x[oc + kw][i], wt[3 + kw][i], Q[oc][i]);
+                R[oc][i] = fmaf(x[oc + kw][i], wt[0 + kw][i], R[oc][i]);
+            }
+}
+
+struct DwTileCoord { int b, h0, w0; };
+__device__ __forceinline__ DwTileCoord dw_tile_coord(int tile, int tiles_w, int tiles_h, int TH, int TW) {
+    DwTileCoord t;
+    const int tw = tile % tiles_w;
+    const int q = tile / tiles_w;
+    t.w0 = tw * TW;
+    t.h0 = (q % tiles_h) * TH;
+    t.b = q / tiles_h;
+    return t;
+}
+
 // Forward / data-gradient kernel. A persistent CTA owns one 64-channel chunk (blockIdx.y) and
 // walks (image, row-tile, col-tile) tiles; each input tile INCLUDING its 1-pixel halo is fetched
 // by ONE TMA box load ({64 ch, TW+2, TH+2, 1}; out-of-image halo is zero-filled by the TMA unit)
 // into a double-buffered shared-memory stage, so the next tile streams in while the current one
 // is computed. Thread = (4-channel group, 2 adjacent output columns); it slides down the rows
-// with three running accumulators per column, reading each staged input vector once per row.
-template <typename T, bool AFFINE, bool RELU, bool FLIP>
-__global__ void __launch_bounds__(256) dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
-                                                        const float* __restrict__ k,
-                                                        const float* __restrict__ in_a,
-                                                        const float* __restrict__ in_b, T* __restrict__ out, int B,
-                                                        int H, int W, int C, int TH, int TW, int tiles_h,
-                                                        int tiles_w, DwEpilogue ep) {
+// with three running accumulators per column (rotated by a 3x unrolled loop, no register moves),
+// reading each staged input vector once per row. EPI enables the optional mask / residual-add epilogue.
+template <typename T, bool AFFINE, bool RELU, bool FLIP, bool EPI>
+__global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
+                                                           const float* __restrict__ k,
+                                                           const float* __restrict__ in_a,
+                                                           const float* __restrict__ in_b, T* __restrict__ out, int B,
+                                                           int H, int W, int C, int TH, int TW, int tiles_h,
+                                                           int tiles_w, DwEpilogue ep) {
     constexpr int G = DW_G, CB = DW_CB;
+    constexpr uint32_t ES = sizeof(T);
     extern __shared__ uint8_t dw_smem_raw[];
-    T* smem = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~(uintptr_t)127);
     __shared__ __align__(8) uint64_t bars[2];
+    const uint32_t sbase = (smem_u32(dw_smem_raw) + 127u) & ~127u;
     const int cg = threadIdx.x & 15, colg = threadIdx.x >> 4;
     const int cbase = blockIdx.y * CB;
     const int c0 = cbase + cg * G;
     const bool c_ok = c0 < C;
     const int TWH = TW + 2;
-    const int tile_elems = (TH + 2) * TWH * CB;
-    const uint32_t tile_bytes = (uint32_t)tile_elems * sizeof(T);
+    const uint32_t tile_bytes = (uint32_t)((TH + 2) * TWH * CB) * ES;
+    const uint32_t row_bytes = (uint32_t)(TWH * CB) * ES;
     const int n_tiles = B * tiles_h * tiles_w;
+    const int col0 = colg * 2;
 
     float wt[9][G], av[G], bv[G];
 #pragma unroll
@@ -100,117 +141,108 @@ __global__ void __launch_bounds__(256) dw3x3_tma_kernel(const __grid_constant__ 
         mbar_fence_init();
     }
     __syncthreads();
-
-    auto issue = [&](int tile, int bufi) {
-        const int tw = tile % tiles_w;
-        const int th = (tile / tiles_w) % tiles_h;
-        const int b = tile / (tiles_w * tiles_h);
-        mbar_expect_tx(bar0 + 8 * bufi, tile_bytes);
-        tma_load_4d(smem_u32(smem + (size_t)bufi * tile_elems), &tm_in, bar0 + 8 * bufi, cbase, tw * TW - 1, th * TH - 1, b);
-    };
-    if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+    if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) {
+        const DwTileCoord t = dw_tile_coord(blockIdx.x, tiles_w, tiles_h, TH, TW);
+        mbar_expect_tx(bar0, tile_bytes);
+        tma_load_4d(sbase, &tm_in, bar0, cbase, t.w0 - 1, t.h0 - 1, t.b);
+    }
+    const size_t rowC = (size_t)W * C;
 
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int cur = it & 1;
         const int nxt = tile + gridDim.x;
-        if (threadIdx.x == 0 && nxt < n_tiles) issue(nxt, cur ^ 1);
-        mbar_wait(bar0 + 8 * cur, (uint32_t)(it >> 1) & 1u);
-
-        const int tw = tile % tiles_w;
-        const int th = (tile / tiles_w) % tiles_h;
-        const int b = tile / (tiles_w * tiles_h);
-        const int h0 = th * TH, w0 = tw * TW;
-        const int h1 = min(H, h0 + TH);
-        const int col0 = colg * 2;
+        if (threadIdx.x == 0 && nxt < n_tiles) {
+            const DwTileCoord t = dw_tile_coord(nxt, tiles_w, tiles_h, TH, TW);
+            mbar_expect_tx(bar0 + 8 * (cur ^ 1), tile_bytes);
+            tma_load_4d(sbase + (cur ^ 1) * tile_bytes, &tm_in, bar0 + 8 * (cur ^ 1), cbase, t.w0 - 1, t.h0 - 1, t.b);
+        }
+        const DwTileCoord tc = dw_tile_coord(tile, tiles_w, tiles_h, TH, TW);
+        const int h0 = tc.h0, w0 = tc.w0;
+        const int rows = min(TH, H - h0) + 2;
         bool colok[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int iw = w0 - 1 + col0 + j;
             colok[j] = iw >= 0 && iw < W;
         }
-        const T* tb = smem + (size_t)cur * tile_elems + cg * G;
-        float acc[3][2][G];
+        const bool st0 = c_ok && (w0 + col0) < W, st1 = c_ok && (w0 + col0 + 1) < W;
+        uint32_t s_row = sbase + cur * tile_bytes + (uint32_t)(col0 * CB + cg * G) * ES;
+        T* o_ptr = out + ((size_t)tc.b * H + h0) * rowC + (size_t)(w0 + col0) * C + c0;
+        float A_[2][G], B_[2][G], C_[2][G];
 #pragma unroll
-        for (int q = 0; q < 3; ++q)
+        for (int oc = 0; oc < 2; ++oc)
 #pragma unroll
-            for (int oc = 0; oc < 2; ++oc)
-#pragma unroll
-                for (int i = 0; i < G; ++i) acc[q][oc][i] = 0.f;
-        const size_t img = (size_t)b * H * W;
-        const int rows = min(TH, H - h0) + 2;
-        for (int r = 0; r < rows; ++r) {
+            for (int i = 0; i < G; ++i) { A_[oc][i] = 0.f; B_[oc][i] = 0.f; C_[oc][i] = 0.f; }
+        mbar_wait(bar0 + 8 * cur, (uint32_t)(it >> 1) & 1u);
+
+        int r = 0;
+        auto step = [&](float (&P)[2][G], float (&Q)[2][G], float (&R)[2][G]) {
             const int ih = h0 - 1 + r;
             const bool rowok = ih >= 0 && ih < H;
             float x[4][G];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                load4(tb + (size_t)(r * TWH + col0 + j) * CB, x[j]);
-                const bool ok = rowok && colok[j];
-#pragma unroll
-                for (int i = 0; i < G; ++i) {
-                    float v = x[j][i];
-                    if (AFFINE) v = fmaf(v, av[i], bv[i]);
-                    if (RELU) v = fmaxf(v, 0.f);
-                    x[j][i] = (AFFINE && !ok) ? 0.f : v;  // zero padding applies AFTER the BN/ReLU transform
-                }
-            }
-#pragma unroll
-            for (int oc = 0; oc < 2; ++oc)
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw)
+                lds4(s_row + j * (CB * ES), x[j], (const T*)nullptr);
+                if (AFFINE || RELU) {
+                    const bool ok = rowok && colok[j];
 #pragma unroll
                     for (int i = 0; i < G; ++i) {
-                        acc[0][oc][i] = fmaf(x[oc + kw][i], wt[6 + kw][i], acc[0][oc][i]);
-                        acc[1][oc][i] = fmaf(x[oc + kw][i], wt[3 + kw][i], acc[1][oc][i]);
-                        acc[2][oc][i] = fmaf(x[oc + kw][i], wt[0 + kw][i], acc[2][oc][i]);
+                        float v = x[j][i];
+                        if (AFFINE) v = fmaf(v, av[i], bv[i]);
+                        if (RELU) v = fmaxf(v, 0.f);
+                        x[j][i] = (AFFINE && !ok) ? 0.f : v;  // zero padding applies AFTER the BN/ReLU transform
                     }
-            const int oh = ih - 1;
-            if (oh >= h0 && oh < h1 && c_ok) {
+                }
+            }
+            dw_row_fma(x, wt, P, Q, R);
+            if (r >= 2) {  // P now holds output row h0 + r - 2
+                if (EPI) {
+                    const int oh = h0 + r - 2;
 #pragma unroll
-                for (int oc = 0; oc < 2; ++oc) {
-                    const int ow = w0 + col0 + oc;
-                    if (ow >= W) continue;
-                    const size_t o = (img + (size_t)oh * W + ow) * C + c0;
-                    float res[G];
+                    for (int oc = 0; oc < 2; ++oc) {
+                        if (!(oc ? st1 : st0)) continue;
+                        const int ow = w0 + col0 + oc;
+                        const size_t o = (size_t)(o_ptr - out) + (size_t)oc * C;
+                        if (ep.mask_src) {
+                            float m[G];
+                            load4(reinterpret_cast<const T*>(ep.mask_src) + o, m);
 #pragma unroll
-                    for (int i = 0; i < G; ++i) res[i] = acc[0][oc][i];
-                    if (ep.mask_src) {
-                        float m[G];
-                        load4(reinterpret_cast<const T*>(ep.mask_src) + o, m);
+                            for (int i = 0; i < G; ++i) {
+                                float v = m[i];
+                                if (ep.mask_a) v = fmaf(v, ep.mask_a[c0 + i], ep.mask_b[c0 + i]);
+                                if (!(v > 0.f)) P[oc][i] = 0.f;
+                            }
+                        }
+                        if (ep.add_src) {
+                            float m[G];
+                            load4(reinterpret_cast<const T*>(ep.add_src) + o, m);
 #pragma unroll
-                        for (int i = 0; i < G; ++i) {
-                            float v = m[i];
-                            if (ep.mask_a) v = fmaf(v, ep.mask_a[c0 + i], ep.mask_b[c0 + i]);
-                            if (!(v > 0.f)) res[i] = 0.f;
+                            for (int i = 0; i < G; ++i) P[oc][i] += m[i];
+                        }
+                        if (ep.add_strided && ((oh | ow) & 1) == 0) {
+                            const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
+                            float m[G];
+                            load4(reinterpret_cast<const T*>(ep.add_strided) +
+                                      (((size_t)tc.b * H2 + (oh >> 1)) * W2 + (ow >> 1)) * C + c0, m);
+#pragma unroll
+                            for (int i = 0; i < G; ++i) P[oc][i] += m[i];
                         }
                     }
-                    if (ep.add_src) {
-                        float m[G];
-                        load4(reinterpret_cast<const T*>(ep.add_src) + o, m);
-#pragma unroll
-                        for (int i = 0; i < G; ++i) res[i] += m[i];
-                    }
-                    if (ep.add_strided && ((oh | ow) & 1) == 0) {
-                        const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
-                        float m[G];
-                        load4(reinterpret_cast<const T*>(ep.add_strided) +
-                                  (((size_t)b * H2 + (oh >> 1)) * W2 + (ow >> 1)) * C + c0, m);
-#pragma unroll
-                        for (int i = 0; i < G; ++i) res[i] += m[i];
-                    }
-                    store4(out + o, res);
                 }
+                if (st0) store4(o_ptr, P[0]);
+                if (st1) store4(o_ptr + C, P[1]);
+                o_ptr += rowC;
             }
 #pragma unroll
             for (int oc = 0; oc < 2; ++oc)
 #pragma unroll
-                for (int i = 0; i < G; ++i) {
-                    acc[0][oc][i] = acc[1][oc][i];
-                    acc[1][oc][i] = acc[2][oc][i];
-                    acc[2][oc][i] = 0.f;
-                }
-        }
+                for (int i = 0; i < G; ++i) P[oc][i] = 0.f;
+            s_row += row_bytes;
+            ++r;
+        };
+        while (r + 3 <= rows) { step(A_, B_, C_); step(B_, C_, A_); step(C_, A_, B_); }
+        if (r < rows) { step(A_, B_, C_); if (r < rows) step(B_, C_, A_); }
         __syncthreads();  // every thread is done with buffer `cur` before it is refilled
     }
 }
@@ -225,18 +257,18 @@ __global__ void __launch_bounds__(256) dw3x3_tma_kernel(const __grid_constant__ 
 // bn_bwd_reduce kernels need. Both gradients use the SAME 3x3 neighbourhood of gout around a
 // pixel: dgrad = sum_n gout_n * k_n,  dk_n += act(in)(pixel) * gout_n.
 // Warp-specialised: the first half of the CTA computes the data gradient (+mask, +BN sums, store),
-// the second half the weight gradient, both from the same TMA-staged gradient tile. Splitting the
-// two accumulator sets over different warps halves the registers per thread (2x the resident warps).
-template <typename T, bool AFFINE, bool RELU>
+// the second half the weight gradient, both from the same TMA-staged gradient tile.
+template <typename T, bool AFFINE, bool RELU, bool EPI>
 __global__ void __launch_bounds__(512, 1) dw3x3_bwd_fused_kernel(
     const __grid_constant__ CUtensorMap tm_g, const T* __restrict__ in, const float* __restrict__ k,
     const float* __restrict__ in_a, const float* __restrict__ in_b, const float* __restrict__ bn_mean,
     const float* __restrict__ bn_rstd, double* __restrict__ stats, T* __restrict__ gin, float* __restrict__ dk, int B,
     int H, int W, int C, int TH, int TW, int tiles_h, int tiles_w, DwEpilogue ep) {
     constexpr int G = DW_G, CB = DW_CB;
+    constexpr uint32_t ES = sizeof(T);
     extern __shared__ uint8_t dw_smem_raw[];
-    T* smem = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~(uintptr_t)127);
     __shared__ __align__(8) uint64_t bars[2];
+    const uint32_t sbase = (smem_u32(dw_smem_raw) + 127u) & ~127u;
     const int half = blockDim.x >> 1;
     const bool wg_role = (int)threadIdx.x >= half;  // warp-uniform: half is a multiple of 32
     const int tl = threadIdx.x - (wg_role ? half : 0);
@@ -246,10 +278,11 @@ __global__ void __launch_bounds__(512, 1) dw3x3_bwd_fused_kernel(
     const int c0 = cbase + cg * G;
     const bool c_ok = c0 < C;
     const int TWH = TW + 2;
-    const int tile_elems = (TH + 2) * TWH * CB;
-    const uint32_t tile_bytes = (uint32_t)tile_elems * sizeof(T);
+    const uint32_t tile_bytes = (uint32_t)((TH + 2) * TWH * CB) * ES;
+    const uint32_t row_bytes = (uint32_t)(TWH * CB) * ES;
     const int n_tiles = B * tiles_h * tiles_w;
     const int col0 = colg * 2;
+    const size_t rowC = (size_t)W * C;
 
     float av[G], bv[G];
 #pragma unroll
@@ -264,26 +297,19 @@ __global__ void __launch_bounds__(512, 1) dw3x3_bwd_fused_kernel(
         mbar_fence_init();
     }
     __syncthreads();
-    auto issue = [&](int tile, int bufi) {
-        const int tw = tile % tiles_w;
-        const int th = (tile / tiles_w) % tiles_h;
-        const int b = tile / (tiles_w * tiles_h);
-        mbar_expect_tx(bar0 + 8 * bufi, tile_bytes);
-        tma_load_4d(smem_u32(smem + (size_t)bufi * tile_elems), &tm_g, bar0 + 8 * bufi, cbase, tw * TW - 1, th * TH - 1, b);
-    };
-    if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+    if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) {
+        const DwTileCoord t = dw_tile_coord(blockIdx.x, tiles_w, tiles_h, TH, TW);
+        mbar_expect_tx(bar0, tile_bytes);
+        tma_load_4d(sbase, &tm_g, bar0, cbase, t.w0 - 1, t.h0 - 1, t.b);
+    }
 
     // role-private state (only one of the two sets is live in any warp)
-    float wt[9][G];      // data-gradient role: flipped taps
-    float s1[G], s2[G];  //   BN sums: s1 = sum g, s2 = sum g*in (raw); xhat fixed up at the end
-    float dkacc[9][G];   // weight-gradient role
+    float wt[9][G];      // data-gradient role: flipped taps;  weight-gradient role: dk accumulators
+    float s1[G], s2[G];  // BN sums: s1 = sum g, s2 = sum g*in (raw); xhat is fixed up at the end
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int i = 0; i < G; ++i) {
-            wt[t][i] = (!wg_role && c_ok) ? k[(8 - t) * C + c0 + i] : 0.f;
-            dkacc[t][i] = 0.f;
-        }
+        for (int i = 0; i < G; ++i) wt[t][i] = (!wg_role && c_ok) ? k[(8 - t) * C + c0 + i] : 0.f;
 #pragma unroll
     for (int i = 0; i < G; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
 
@@ -291,118 +317,114 @@ __global__ void __launch_bounds__(512, 1) dw3x3_bwd_fused_kernel(
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int cur = it & 1;
         const int nxt = tile + gridDim.x;
-        if (threadIdx.x == 0 && nxt < n_tiles) issue(nxt, cur ^ 1);
-        const int tw = tile % tiles_w;
-        const int th = (tile / tiles_w) % tiles_h;
-        const int b = tile / (tiles_w * tiles_h);
-        const int h0 = th * TH, w0 = tw * TW;
-        const int h1 = min(H, h0 + TH);
-        const size_t img = (size_t)b * H * W;
-        const int rows = (h1 - h0) + 2;
-        bool own[2];
-#pragma unroll
-        for (int oc = 0; oc < 2; ++oc) own[oc] = c_ok && (w0 + col0 + oc) < W;
-        const T* tb = smem + (size_t)cur * tile_elems + cg * G;
+        if (threadIdx.x == 0 && nxt < n_tiles) {
+            const DwTileCoord t = dw_tile_coord(nxt, tiles_w, tiles_h, TH, TW);
+            mbar_expect_tx(bar0 + 8 * (cur ^ 1), tile_bytes);
+            tma_load_4d(sbase + (cur ^ 1) * tile_bytes, &tm_g, bar0 + 8 * (cur ^ 1), cbase, t.w0 - 1, t.h0 - 1, t.b);
+        }
+        const DwTileCoord tc = dw_tile_coord(tile, tiles_w, tiles_h, TH, TW);
+        const int h0 = tc.h0, w0 = tc.w0;
+        const int nrow = min(TH, H - h0);  // centre rows owned by this tile
+        const int rows = nrow + 2;
+        const bool own0 = c_ok && (w0 + col0) < W, own1 = c_ok && (w0 + col0 + 1) < W;
+        uint32_t s_row = sbase + cur * tile_bytes + (uint32_t)(col0 * CB + cg * G) * ES;
+        const size_t pix0 = ((size_t)tc.b * H + h0) * rowC + (size_t)(w0 + col0) * C + c0;  // centre row h0
 
         if (!wg_role) {
             // ================= data gradient (+ ReLU mask, BN sums, residual adds, store) =================
+            const T* u_ptr = in + pix0;
+            T* o_ptr = gin + pix0;
+            float A_[2][G], B_[2][G], C_[2][G];
+#pragma unroll
+            for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+                for (int i = 0; i < G; ++i) { A_[oc][i] = 0.f; B_[oc][i] = 0.f; C_[oc][i] = 0.f; }
             mbar_wait(bar0 + 8 * cur, (uint32_t)(it >> 1) & 1u);
-            float acc[3][2][G];
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-#pragma unroll
-                for (int oc = 0; oc < 2; ++oc)
-#pragma unroll
-                    for (int i = 0; i < G; ++i) acc[q][oc][i] = 0.f;
-            for (int r = 0; r < rows; ++r) {
-                const int oh = h0 - 2 + r;  // output row completed by gradient row gh = oh + 1
-                const bool emit = oh >= h0 && oh < h1;
-                Raw4<T> ru[2];
+            int r = 0;
+            auto step = [&](float (&P)[2][G], float (&Q)[2][G], float (&R)[2][G]) {
+                const bool emit = r >= 2;  // P completes output row h0 + r - 2
+                Raw4<T> ru0, ru1;
                 if (emit && (RELU || stats)) {  // issued early, widened only after the FMAs below
-#pragma unroll
-                    for (int oc = 0; oc < 2; ++oc)
-                        if (own[oc]) ru[oc] = load_raw4(in + (img + (size_t)oh * W + (w0 + col0 + oc)) * C + c0);
+                    if (own0) ru0 = load_raw4(u_ptr);
+                    if (own1) ru1 = load_raw4(u_ptr + C);
                 }
                 float x[4][G];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) load4(tb + (size_t)(r * TWH + col0 + j) * CB, x[j]);
-#pragma unroll
-                for (int oc = 0; oc < 2; ++oc)
-#pragma unroll
-                    for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-                        for (int i = 0; i < G; ++i) {
-                            acc[0][oc][i] = fmaf(x[oc + kw][i], wt[6 + kw][i], acc[0][oc][i]);
-                            acc[1][oc][i] = fmaf(x[oc + kw][i], wt[3 + kw][i], acc[1][oc][i]);
-                            acc[2][oc][i] = fmaf(x[oc + kw][i], wt[0 + kw][i], acc[2][oc][i]);
-                        }
+                for (int j = 0; j < 4; ++j) lds4(s_row + j * (CB * ES), x[j], (const T*)nullptr);
+                dw_row_fma(x, wt, P, Q, R);
                 if (emit) {
 #pragma unroll
                     for (int oc = 0; oc < 2; ++oc) {
-                        if (!own[oc]) continue;
-                        const int ow = w0 + col0 + oc;
-                        const size_t o = (img + (size_t)oh * W + ow) * C + c0;
-                        float res[G];
-#pragma unroll
-                        for (int i = 0; i < G; ++i) res[i] = acc[0][oc][i];
+                        if (!(oc ? own1 : own0)) continue;
                         if (RELU || stats) {
                             float u[G];
-                            unpack4(ru[oc], u);
+                            unpack4(oc ? ru1 : ru0, u);
 #pragma unroll
                             for (int i = 0; i < G; ++i) {
                                 if (RELU) {
                                     const float pre = AFFINE ? fmaf(u[i], av[i], bv[i]) : u[i];
-                                    if (!(pre > 0.f)) res[i] = 0.f;
+                                    if (!(pre > 0.f)) P[oc][i] = 0.f;
                                 }
                                 if (stats) {
-                                    const float rr = round_to<T>(res[i]);
+                                    const float rr = round_to<T>(P[oc][i]);
                                     s1[i] += rr;
                                     s2[i] = fmaf(rr, u[i], s2[i]);
                                 }
                             }
                         }
-                        if (ep.add_src) {
-                            float m[G];
-                            load4(reinterpret_cast<const T*>(ep.add_src) + o, m);
+                        if (EPI) {
+                            const int oh = h0 + r - 2, ow = w0 + col0 + oc;
+                            const size_t o = (size_t)(o_ptr - gin) + (size_t)oc * C;
+                            if (ep.add_src) {
+                                float m[G];
+                                load4(reinterpret_cast<const T*>(ep.add_src) + o, m);
 #pragma unroll
-                            for (int i = 0; i < G; ++i) res[i] += m[i];
-                        }
-                        if (ep.add_strided && ((oh | ow) & 1) == 0) {
-                            const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
-                            float m[G];
-                            load4(reinterpret_cast<const T*>(ep.add_strided) +
-                                      (((size_t)b * H2 + (oh >> 1)) * W2 + (ow >> 1)) * C + c0, m);
+                                for (int i = 0; i < G; ++i) P[oc][i] += m[i];
+                            }
+                            if (ep.add_strided && ((oh | ow) & 1) == 0) {
+                                const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
+                                float m[G];
+                                load4(reinterpret_cast<const T*>(ep.add_strided) +
+                                          (((size_t)tc.b * H2 + (oh >> 1)) * W2 + (ow >> 1)) * C + c0, m);
 #pragma unroll
-                            for (int i = 0; i < G; ++i) res[i] += m[i];
+                                for (int i = 0; i < G; ++i) P[oc][i] += m[i];
+                            }
                         }
-                        store4(gin + o, res);
+                        store4(o_ptr + (size_t)oc * C, P[oc]);
                     }
+                    o_ptr += rowC;
+                    u_ptr += rowC;
                 }
 #pragma unroll
                 for (int oc = 0; oc < 2; ++oc)
 #pragma unroll
-                    for (int i = 0; i < G; ++i) {
-                        acc[0][oc][i] = acc[1][oc][i];
-                        acc[1][oc][i] = acc[2][oc][i];
-                        acc[2][oc][i] = 0.f;
-                    }
-            }
+                    for (int i = 0; i < G; ++i) P[oc][i] = 0.f;
+                s_row += row_bytes;
+                ++r;
+            };
+            while (r + 3 <= rows) { step(A_, B_, C_); step(B_, C_, A_); step(C_, A_, B_); }
+            if (r < rows) { step(A_, B_, C_); if (r < rows) step(B_, C_, A_); }
         } else {
             // ================= weight gradient: dk[kh][kw] += act(in)[gh+kh-1][c] * g[gh][c-kw+1] =================
-            auto fetch_v = [&](int row, Raw4<T> (&rv)[2]) -> bool {  // raw loads of an owned centre row
-                const bool rok = row >= h0 && row < h1;
-                if (rok) {
-#pragma unroll
-                    for (int oc = 0; oc < 2; ++oc)
-                        if (own[oc]) rv[oc] = load_raw4(in + (img + (size_t)row * W + (w0 + col0 + oc)) * C + c0);
+            // (dk accumulators live in wt[][]). Window V0,V1,V2 = act(in) rows gh-1, gh, gh+1, zero outside
+            // the rows/cols this tile owns; rotated by the 3x unrolled loop.
+            const T* v_ptr = in + pix0;  // next centre row to fetch
+            int vrow = 0;                // its index within the tile's centre rows
+            auto fetch = [&](Raw4<T>& r0, Raw4<T>& r1) -> bool {
+                const bool ok = vrow < nrow;
+                if (ok) {
+                    if (own0) r0 = load_raw4(v_ptr);
+                    if (own1) r1 = load_raw4(v_ptr + C);
+                    v_ptr += rowC;
                 }
-                return rok;
+                ++vrow;
+                return ok;
             };
-            auto widen_v = [&](bool rok, const Raw4<T> (&rv)[2], float (&v)[2][G]) {  // act(in), zero if not owned
+            auto widen = [&](bool ok, const Raw4<T>& r0, const Raw4<T>& r1, float (&v)[2][G]) {
 #pragma unroll
                 for (int oc = 0; oc < 2; ++oc) {
-                    if (rok && own[oc]) {
-                        unpack4(rv[oc], v[oc]);
+                    if (ok && (oc ? own1 : own0)) {
+                        unpack4(oc ? r1 : r0, v[oc]);
 #pragma unroll
                         for (int i = 0; i < G; ++i) {
                             float y = v[oc][i];
@@ -416,53 +438,51 @@ __global__ void __launch_bounds__(512, 1) dw3x3_bwd_fused_kernel(
                     }
                 }
             };
-            float vw[3][2][G];  // act(in) rows gh-1, gh, gh+1 (zero outside the rows/cols this tile owns)
+            float V0[2][G], V1[2][G], V2[2][G];
 #pragma unroll
             for (int oc = 0; oc < 2; ++oc)
 #pragma unroll
-                for (int i = 0; i < G; ++i) { vw[0][oc][i] = 0.f; vw[1][oc][i] = 0.f; }
-            Raw4<T> rfirst[2], rnext[2];
-            const bool ok_first = fetch_v(h0, rfirst);
-            bool ok_next = fetch_v(h0 + 1, rnext);  // row needed by iteration r = 1, in flight during r = 0
-            widen_v(ok_first, rfirst, vw[2]);
+                for (int i = 0; i < G; ++i) { V0[oc][i] = 0.f; V1[oc][i] = 0.f; }
+            Raw4<T> ra0, ra1, rb0, rb1;
+            const bool ok_a = fetch(ra0, ra1);  // centre row h0   (= gh+1 of the first gradient row gh = h0-1)
+            bool ok_b = fetch(rb0, rb1);        // centre row h0+1 (needed one iteration later)
+            widen(ok_a, ra0, ra1, V2);
             mbar_wait(bar0 + 8 * cur, (uint32_t)(it >> 1) & 1u);
-            for (int r = 0; r < rows; ++r) {
-                const int gh = h0 - 1 + r;
+            int r = 0;
+            auto step = [&](float (&Vm)[2][G], float (&Vc)[2][G], float (&Vp)[2][G]) {
                 float x[4][G];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) load4(tb + (size_t)(r * TWH + col0 + j) * CB, x[j]);
+                for (int j = 0; j < 4; ++j) lds4(s_row + j * (CB * ES), x[j], (const T*)nullptr);
 #pragma unroll
-                for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-                    for (int kw = 0; kw < 3; ++kw)
+                    for (int oc = 0; oc < 2; ++oc)
 #pragma unroll
-                        for (int oc = 0; oc < 2; ++oc)
-#pragma unroll
-                            for (int i = 0; i < G; ++i)
-                                dkacc[kh * 3 + kw][i] = fmaf(vw[kh][oc][i], x[oc + 2 - kw][i], dkacc[kh * 3 + kw][i]);
-                // rotate the window: row gh+2 was fetched one iteration ago, widen it only now
-#pragma unroll
-                for (int oc = 0; oc < 2; ++oc)
-#pragma unroll
-                    for (int i = 0; i < G; ++i) {
-                        vw[0][oc][i] = vw[1][oc][i];
-                        vw[1][oc][i] = vw[2][oc][i];
-                    }
-                widen_v(ok_next, rnext, vw[2]);
-                ok_next = fetch_v(gh + 3, rnext);
-            }
+                        for (int i = 0; i < G; ++i) {
+                            wt[0 + kw][i] = fmaf(Vm[oc][i], x[oc + 2 - kw][i], wt[0 + kw][i]);
+                            wt[3 + kw][i] = fmaf(Vc[oc][i], x[oc + 2 - kw][i], wt[3 + kw][i]);
+                            wt[6 + kw][i] = fmaf(Vp[oc][i], x[oc + 2 - kw][i], wt[6 + kw][i]);
+                        }
+                // Vm (row gh-1) is dead: refill it with row gh+2 (fetched one iteration ago), fetch gh+3
+                widen(ok_b, rb0, rb1, Vm);
+                ok_b = fetch(rb0, rb1);
+                s_row += row_bytes;
+                ++r;
+            };
+            while (r + 3 <= rows) { step(V0, V1, V2); step(V1, V2, V0); step(V2, V0, V1); }
+            if (r < rows) { step(V0, V1, V2); if (r < rows) step(V1, V2, V0); }
         }
         __syncthreads();  // both roles are done with buffer `cur` before it is refilled
     }
     // ---- CTA reduction over the column groups that share a channel group, then global atomics
-    float* red = reinterpret_cast<float*>(smem);  // [ncolg][16][NV] — the tile buffers are idle now
+    float* red = reinterpret_cast<float*>(dw_smem_raw + (sbase - smem_u32(dw_smem_raw)));  // tile buffers are idle now
     constexpr int NV = 9 * G + 2 * G;
     float* mine = red + ((size_t)colg * 16 + cg) * NV;
     if (wg_role) {
 #pragma unroll
         for (int t = 0; t < 9; ++t)
 #pragma unroll
-            for (int i = 0; i < G; ++i) mine[t * G + i] = dkacc[t][i];
+            for (int i = 0; i < G; ++i) mine[t * G + i] = wt[t][i];
     } else {
 #pragma unroll
         for (int i = 0; i < G; ++i) { mine[36 + i] = s1[i]; mine[36 + G + i] = s2[i]; }
@@ -637,10 +657,10 @@ static DwTiling dw_tiling(int dtype, int B, int H, int W, int C) {
     return t;
 }
 
-template <typename T, bool AF, bool RL, bool FL>
+template <typename T, bool AF, bool RL, bool FL, bool EP>
 int launch_dw_inst(const CUtensorMap& tm, const float* k, const float* in_a, const float* in_b, T* y, int B, int H,
                    int W, int C, const DwTiling& t, DwEpilogue ep, cudaStream_t stream) {
-    auto kern = dw3x3_tma_kernel<T, AF, RL, FL>;
+    auto kern = dw3x3_tma_kernel<T, AF, RL, FL, EP>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -664,11 +684,11 @@ int launch_dw(const void* in, const float* k, const float* in_a, const float* in
     int rc = make_nhwc_map(&tm, in, dtype, B, H, W, C, t.TW + 2, t.TH + 2);
     if (rc) return rc;
     T* y = reinterpret_cast<T*>(out);
-    if (flip) return launch_dw_inst<T, false, false, true>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
-    if (in_a && relu) return launch_dw_inst<T, true, true, false>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
-    if (in_a) return launch_dw_inst<T, true, false, false>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
-    if (relu) return launch_dw_inst<T, false, true, false>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
-    return launch_dw_inst<T, false, false, false>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
+    if (flip) return launch_dw_inst<T, false, false, true, true>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
+    if (in_a && relu) return launch_dw_inst<T, true, true, false, false>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
+    if (in_a) return launch_dw_inst<T, true, false, false, false>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
+    if (relu) return launch_dw_inst<T, false, true, false, false>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
+    return launch_dw_inst<T, false, false, false, false>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
 }
 
 template <typename T>
@@ -700,11 +720,11 @@ int launch_dw_wgrad(const void* in, const void* g, const float* in_a, const floa
     return spnet_check_launch("dw3x3_wgrad");
 }
 
-template <typename T, bool AF, bool RL>
+template <typename T, bool AF, bool RL, bool EP>
 int launch_dw_bwd_inst(const CUtensorMap& tm, const T* in, const float* k, const float* in_a, const float* in_b,
                        const float* mean, const float* rstd, double* stats, T* gin, float* dk, int B, int H, int W,
                        int C, const DwTiling& t, int grid_x, DwEpilogue ep, cudaStream_t stream) {
-    auto kern = dw3x3_bwd_fused_kernel<T, AF, RL>;
+    auto kern = dw3x3_bwd_fused_kernel<T, AF, RL, EP>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -740,10 +760,19 @@ int launch_dw_bwd(const void* gout, const void* in, const float* k, const float*
     if (gx < 1) gx = 1;
     const T* x = reinterpret_cast<const T*>(in);
     T* y = reinterpret_cast<T*>(gin);
-    if (in_a && relu) return launch_dw_bwd_inst<T, true, true>(tm, x, k, in_a, in_b, mean, rstd, stats, y, dk, B, H, W, C, t, (int)gx, ep, stream);
-    if (in_a) return launch_dw_bwd_inst<T, true, false>(tm, x, k, in_a, in_b, mean, rstd, stats, y, dk, B, H, W, C, t, (int)gx, ep, stream);
-    if (relu) return launch_dw_bwd_inst<T, false, true>(tm, x, k, in_a, in_b, mean, rstd, stats, y, dk, B, H, W, C, t, (int)gx, ep, stream);
-    return launch_dw_bwd_inst<T, false, false>(tm, x, k, in_a, in_b, mean, rstd, stats, y, dk, B, H, W, C, t, (int)gx, ep, stream);
+#define DWB(AF, RL)                                                                                              \
+    do {                                                                                                         \
+        if (ep.add_src || ep.add_strided)                                                                        \
+            return launch_dw_bwd_inst<T, AF, RL, true>(tm, x, k, in_a, in_b, mean, rstd, stats, y, dk, B, H, W, C, t, \
+                                                       (int)gx, ep, stream);                                     \
+        return launch_dw_bwd_inst<T, AF, RL, false>(tm, x, k, in_a, in_b, mean, rstd, stats, y, dk, B, H, W, C, t,   \
+                                                    (int)gx, ep, stream);                                        \
+    } while (0)
+    if (in_a && relu) DWB(true, true);
+    if (in_a) DWB(true, false);
+    if (relu) DWB(false, true);
+    DWB(false, false);
+#undef DWB
 }
 
 int check_dw_args(const char* who, const void* in, const void* out, int dtype, int B, int H, int W, int C) {
