@@ -291,6 +291,33 @@ def run_ours(args, rank, world):
     dominant = max(roofs.values(), key=lambda r: r["share_of_step"])
     other = [r for r in roofs.values() if r is not dominant]
 
+    # ---- inference throughput (forward only, moving-stat BN), same batch / shape, CUDA-graph replay
+    infer = None
+    try:
+        del eng
+        torch.cuda.empty_cache()
+        ieng = XceptionSPNetEngine(H, W, B, dtype="bf16", device=str(dev), seed=1, training=False)
+        ieng.x0.copy_(Xd[:B])
+        ieng.forward(training=False)
+        torch.cuda.synchronize()
+        ig = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ig):
+            ieng.forward(training=False)
+        for _ in range(3):
+            ig.replay()
+        torch.cuda.synchronize()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record()
+        for i in range(args.steps):
+            ieng.x0.copy_(Xd[(i % 2) * B:(i % 2) * B + B])
+            ig.replay()
+        i1.record()
+        torch.cuda.synchronize()
+        ims = i0.elapsed_time(i1) / args.steps
+        infer = {"value": B / (ims / 1e3), "unit": "images/s (per GPU)", "ms_per_batch": ims, "batch": B}
+    except Exception as e:  # the training numbers above stay valid
+        infer = {"error": str(e)[:200]}
+
     # ---- CPU baseline on this box's host cores: bounded sample of the same workload
     cpu = cpu_baseline()
 
@@ -307,7 +334,7 @@ def run_ours(args, rank, world):
                    "h2d_bytes_per_step": int(B * (H * W * 4 + N_OUT * 4)), "d2h_bytes_per_step": 24},
            "gpu_launches": int(launches_per_step * args.steps * 2),
            "roofline": dominant, "roofline_other": other, "kernel_breakdown": breakdown, "gemm_shapes": gemm_shapes,
-           "peaks": peaks, "cpu_baseline": cpu}
+           "peaks": peaks, "inference": infer, "cpu_baseline": cpu}
     print(json.dumps(out), flush=True)
 
 

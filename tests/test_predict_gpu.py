@@ -1,0 +1,69 @@
+"""predict_spnet end to end on the GPU: PNGs on disk -> build_X -> engine forward -> device decode ->
+hawley_spnet.csv, compared with the host numpy decode and with the oracle's CSV text for the same outputs."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_predict_cli_path_writes_reference_format_csv(tmp_path):
+    from PIL import Image
+    import spnet.config as cf
+    from spnet import models, utils
+    import predict_spnet
+    from spnet_b200 import fake_espi
+    from oracle import numpy_side as ns
+
+    cf.model_type = "big"          # native 384x512 input (predict_spnet.py:50-52)
+    cf.compute_dtype = "bf16"
+    n = 6
+    for i in range(n):
+        img, _ = fake_espi.make_frame(100 + i)
+        Image.fromarray(img).save(tmp_path / ("steelpan_%07d.png" % i))
+    X = np.zeros((2, 384, 512, 1), np.float32)
+    model, _ = models.setup_model(X, 576, try_checkpoint=False, freeze_fac=0.0, quick_setup=True)
+    wpath = str(tmp_path / "weights.hdf5")
+    model.save_weights(wpath)
+    log_dir = str(tmp_path / "out") + "/"
+    m2 = predict_spnet.predict_network(weights_file=wpath, datapath=str(tmp_path), fraction=1.0, log_dir=log_dir,
+                                       batch_size=2, draw_images=True)
+    text = open(log_dir + "hawley_spnet.csv").read()
+    files = sorted(str(p) for p in tmp_path.glob("*.png"))
+    assert len(text.strip().splitlines()) >= n
+    for f in files:
+        assert os.path.basename(f) in text
+    assert os.path.exists(log_dir + "steelpan_pred_00000.png")
+    # same network outputs through the oracle's row formatter and the host decode
+    Xp, _ = utils.build_X(n, files, force_dim=None, grayscale=True)
+    Y = m2.predict(Xp, batch_size=2)
+    means, ranges = ns.setup_means_and_ranges([6, 6, 2, 8])[7:9]
+    assert ns.pred_csv_text(ns.denorm_Y(Y, means, ranges), files) == text
+    Yp_dev, (ints, exists) = predict_spnet.decode_on_device(Y)
+    np.testing.assert_array_equal(Yp_dev, utils.denorm_Y(Y))
+    hi, he = utils.decode_host(Yp_dev)
+    np.testing.assert_array_equal(ints, hi)
+    np.testing.assert_array_equal(exists, he)
+    cf.model_type = "monolithic"
+
+
+def test_fit_loop_reduces_loss_and_checkpoints(tmp_path):
+    import spnet.config as cf
+    from spnet import callbacks, models
+    from spnet_b200 import fake_espi
+    cf.model_type = "big"
+    X, Y, _ = fake_espi.make_dataset(16, base_seed=7)
+    model, serial = models.setup_model(X, 576, try_checkpoint=False, freeze_fac=0.0)
+    sched = callbacks.OneCycleScheduler(lr_max=2e-4, n_data_points=16, epochs=6, batch_size=8)
+    ck = callbacks.ParallelCheckpointCallback(model, filepath="weights.hdf5", save_every=5, dir=str(tmp_path))
+    prog = callbacks.MyProgressCallback(X_val=X[:8], Y_val=Y[:8], log_dir=str(tmp_path), batch_size=8)
+    hist = model.fit(X, Y, batch_size=8, epochs=6, shuffle=True, verbose=0, validation_data=(X[:8], Y[:8]),
+                     callbacks=[prog, ck, sched])
+    loss = hist.history["loss"]
+    assert len(loss) == 6 and np.isfinite(loss).all() and loss[-1] < loss[0]
+    assert os.path.exists(tmp_path / "weights.hdf5") and os.path.exists(tmp_path / "losses.dat")
+    again, _ = models.setup_model(X, 576, try_checkpoint=True, no_cp_fatal=True, weights_file=str(tmp_path / "weights.hdf5"),
+                                  freeze_fac=0.0)
+    assert len(again.get_weights()) == len(model.get_weights())
+    cf.model_type = "monolithic"
