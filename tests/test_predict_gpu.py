@@ -35,12 +35,18 @@ def test_predict_cli_path_writes_reference_format_csv(tmp_path):
     for f in files:
         assert os.path.basename(f) in text
     assert os.path.exists(log_dir + "steelpan_pred_00000.png")
-    # same network outputs through the oracle's row formatter and the host decode
+    # one set of network outputs through (a) device decode + product CSV writer, (b) the oracle's row
+    # formatter, (c) the host numpy decode. (The Dense head accumulates split-K partials with fp32 atomics,
+    # so two predict() calls may differ in the last bits: every path below consumes the SAME Y.)
     Xp, _ = utils.build_X(n, files, force_dim=None, grayscale=True)
     Y = m2.predict(Xp, batch_size=2)
-    means, ranges = ns.setup_means_and_ranges([6, 6, 2, 8])[7:9]
-    assert ns.pred_csv_text(ns.denorm_Y(Y, means, ranges), files) == text
+    utils.setup_means_and_ranges([6, 6, 2, 8])
     Yp_dev, (ints, exists) = predict_spnet.decode_on_device(Y)
+    out2 = str(tmp_path / "again.csv")
+    utils.show_pred_ellipses(Yp_dev, Yp_dev, files, num_draw=n, log_dir=log_dir, out_csv=out2, show_true=False,
+                             draw_images=False, decoded=(ints, exists))
+    means, ranges = ns.setup_means_and_ranges([6, 6, 2, 8])[7:9]
+    assert ns.pred_csv_text(ns.denorm_Y(Y, means, ranges), files) == open(out2).read()
     np.testing.assert_array_equal(Yp_dev, utils.denorm_Y(Y))
     hi, he = utils.decode_host(Yp_dev)
     np.testing.assert_array_equal(ints, hi)
