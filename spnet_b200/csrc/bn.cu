@@ -65,13 +65,17 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* z, const float* 
     float av[V], bv[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) { av[i] = a[c0 + i]; bv[i] = b[c0 + i]; }
-    const long long stride = (long long)gridDim.x * krows;
-    for (long long r0 = (long long)blockIdx.x * krows + rl; r0 < rows; r0 += stride * UNROLL) {
+    // each CTA walks a CONTIGUOUS range of rows (sequential DRAM pages), UNROLL*krows rows per iteration
+    const long long per_cta = (rows + gridDim.x - 1) / gridDim.x;
+    const long long r_begin = (long long)blockIdx.x * per_cta;
+    const long long r_end = r_begin + per_cta < rows ? r_begin + per_cta : rows;
+    const long long stride = krows;
+    for (long long r0 = r_begin + rl; r0 < r_end; r0 += stride * UNROLL) {
         float v[UNROLL][V], xr[UNROLL][V];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const long long r = r0 + u * stride;
-            if (r < rows) {
+            if (r < r_end) {
                 load_vec(z + r * C + c0, v[u]);
                 if (x) load_vec(x + r * C + c0, xr[u]);
             }
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* z, const float* 
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const long long r = r0 + u * stride;
-            if (r < rows) {
+            if (r < r_end) {
 #pragma unroll
                 for (int i = 0; i < V; ++i) {
                     float y = fmaf(v[u][i], av[i], bv[i]);
@@ -123,13 +127,16 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(T* __restrict__ g, c
             ra[i] = relu_a ? relu_a[c0 + i] : 0.f;
             rb[i] = relu_a ? relu_b[c0 + i] : 0.f;
         }
-        const long long stride = (long long)gridDim.x * krows;
-        for (long long r0 = (long long)blockIdx.x * krows + rl; r0 < rows; r0 += stride * UNROLL) {
+        const long long per_cta = (rows + gridDim.x - 1) / gridDim.x;
+        const long long r_begin = (long long)blockIdx.x * per_cta;
+        const long long r_end = r_begin + per_cta < rows ? r_begin + per_cta : rows;
+        const long long stride = krows;
+        for (long long r0 = r_begin + rl; r0 < r_end; r0 += stride * UNROLL) {
             float gv[UNROLL][V], zv[UNROLL][V];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const long long r = r0 + u * stride;
-                if (r < rows) {
+                if (r < r_end) {
                     load_vec(g + r * C + c0, gv[u]);
                     load_vec(z + r * C + c0, zv[u]);
                 }
@@ -137,7 +144,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(T* __restrict__ g, c
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const long long r = r0 + u * stride;
-                if (r >= rows) continue;
+                if (r >= r_end) continue;
                 if (relu_a) {
 #pragma unroll
                     for (int i = 0; i < V; ++i) {
@@ -213,13 +220,17 @@ __global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const T* g, const T* __r
         Bz[i] = -aa * k;
         D[i] = aa * (k * mean[c0 + i] - c1[c0 + i]);
     }
-    const long long stride = (long long)gridDim.x * krows;
-    for (long long r0 = (long long)blockIdx.x * krows + rl; r0 < rows; r0 += stride * UNROLL) {
+    // each CTA walks a CONTIGUOUS range of rows (sequential DRAM pages), UNROLL*krows rows per iteration
+    const long long per_cta = (rows + gridDim.x - 1) / gridDim.x;
+    const long long r_begin = (long long)blockIdx.x * per_cta;
+    const long long r_end = r_begin + per_cta < rows ? r_begin + per_cta : rows;
+    const long long stride = krows;
+    for (long long r0 = r_begin + rl; r0 < r_end; r0 += stride * UNROLL) {
         float gv[UNROLL][V], zv[UNROLL][V];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const long long r = r0 + u * stride;
-            if (r < rows) {
+            if (r < r_end) {
                 load_vec(g + r * C + c0, gv[u]);
                 load_vec(z + r * C + c0, zv[u]);
             }
@@ -227,7 +238,7 @@ __global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const T* g, const T* __r
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const long long r = r0 + u * stride;
-            if (r < rows) {
+            if (r < r_end) {
 #pragma unroll
                 for (int i = 0; i < V; ++i) gv[u][i] = fmaf(gv[u][i], A[i], fmaf(zv[u][i], Bz[i], D[i]));
                 store_vec(out + r * C + c0, gv[u]);
