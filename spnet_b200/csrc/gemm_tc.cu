@@ -24,7 +24,8 @@ namespace {
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;  // TMA warp, MMA warp, four epilogue warps
+constexpr int kEpiWarps = 8;    // two per TMEM lane quadrant, each draining half of the columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA warp, MMA warp, epilogue warps
 
 enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_ATOMIC_F32 = 2 };
 
@@ -102,7 +103,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the four epilogue warps only
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
 }
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull0 + 8 * a, 1);
-            mbar_init(tempty0 + 8 * a, 4);  // one arrive per epilogue warp
+            mbar_init(tempty0 + 8 * a, kEpiWarps);  // one arrive per epilogue warp
         }
         mbar_fence_init();
     }
@@ -258,8 +259,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
     } else {
         // ---------------- epilogue warps ----------------
-        const int q = warp & 3;       // TMEM lane quadrant this warp may access
-        const int et = q * 32 + lane;  // 0..127 within the epilogue group
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int chalf = (warp - 2) >> 2;      // which half of the column chunks this warp drains
+        const int et = (warp - 2) * 32 + lane;  // 0..255 within the epilogue group
         uint32_t u = 0;
         for (int unit = cluster_id; unit < n_units; unit += n_clusters, ++u) {
             const int n0 = (unit % tiles_n) * BN;
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < M;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = chalf; c < BN / 32; c += kEpiWarps / 4) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + as * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
                 const int col0 = n0 + c * 32;
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             if (lane == 0) mbar_arrive(tempty0 + 8 * as);
             if (epi.colstats) {
                 epi_bar_sync();
-                for (int cc = et; cc < BN; cc += 128) {
+                for (int cc = et; cc < BN; cc += 32 * kEpiWarps) {
                     if (n0 + cc < N) {
                         const float s = sstat[0][0][cc] + sstat[0][1][cc] + sstat[0][2][cc] + sstat[0][3][cc];
                         const float s2 = sstat[1][0][cc] + sstat[1][1][cc] + sstat[1][2][cc] + sstat[1][3][cc];
@@ -459,13 +461,28 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
     SPNET_REQUIRE(out_mode >= 0 && out_mode <= 2, "gemm_bf16: bad out_mode %d", out_mode);
     SPNET_REQUIRE(out_mode != OUT_BF16 || (N % 8 == 0 && ldd % 8 == 0), "gemm_bf16: bf16 output needs N, ldd %% 8 == 0");
     SPNET_REQUIRE(out_mode != OUT_F32 || (N % 4 == 0 && ldd % 4 == 0), "gemm_bf16: fp32 output needs N, ldd %% 4 == 0");
+    const bool wide_ = N >= 512, pair_ = wide_ && M > BM && getenv("SPNET_B200_NO_CLUSTER") == nullptr;
+    if (splits <= 0) {
+        // auto split-K (atomic output only): fill the SMs (or SM pairs) once without spilling into a
+        // second, nearly empty round; keep at least 4 k-blocks per split
+        splits = 1;
+        if (out_mode == OUT_ATOMIC_F32) {
+            const int bn = wide_ ? 256 : 128, cl = pair_ ? 2 : 1;
+            const long long tiles = (long long)(((M + BM - 1) / BM + cl - 1) / cl) * ((N + bn - 1) / bn);
+            const long long slots = 148 / cl;
+            long long sp = tiles >= slots ? 1 : slots / tiles;
+            const long long kb = (K + BK - 1) / BK;
+            if (sp > kb / 4) sp = kb / 4;
+            splits = (int)(sp < 1 ? 1 : sp);
+        }
+    }
     SPNET_REQUIRE(splits <= 1 || out_mode == OUT_ATOMIC_F32, "gemm_bf16: split-K needs out_mode 2");
     SPNET_REQUIRE(!(colstats && splits > 1), "gemm_bf16: column statistics are not defined for split-K partials");
     // 128x256 tiles when N is wide: one A tile then feeds 256 output columns, which cuts the
     // L2->SM operand traffic per FLOP by a third (the 128x128 kernel is L2-bandwidth bound).
-    const bool wide = N >= 512;
+    const bool wide = wide_;
     // CTA pairs (B tile multicast) when there are at least two m-tiles to pair up
-    const bool pair = wide && M > BM && getenv("SPNET_B200_NO_CLUSTER") == nullptr;
+    const bool pair = pair_;
     CUtensorMap ta, tb;
     int rc = make_operand_map(&ta, A, M, K, lda, a_mn != 0, BM);
     if (rc) return rc;

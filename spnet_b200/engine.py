@@ -255,7 +255,7 @@ class XceptionSPNetEngine:
 
     def _pw_bwd(self, A, Wl, gW, gz, gA, M, K, N):
         """gz [M,N] -> gW [K,N] += A^T gz ;  gA [M,K] = gz W^T."""
-        sp = self._wgrad_splits(K, N, M)
+        sp = 0 if self.lowp else self._wgrad_splits(K, N, M)  # 0 = let the tcgen05 GEMM pick (fills the SMs once)
         ops.gemm(A, True, gz, True, gW, K, N, M, out_mode=ops.OUT_ATOMIC, splits=sp, lda=K, ldb=N)
         if gA is not None:
             ops.gemm(gz, False, Wl, False, gA, M, K, N, out_mode=ops.OUT_T, ldb=N)
