@@ -1,5 +1,6 @@
-// Depthwise 3x3, stride 1, 'same' padding, NHWC — forward, data-gradient and
-// weight-gradient. This is the depthwise half of keras SeparableConv2D as used by
+// Depthwise 3x3, stride 1, 'same' padding, NHWC — stand-alone data-gradient and
+// weight-gradient entry points (the forward and the fused backward the engine runs are in
+// dwconv_packed.cu). This is the depthwise half of keras SeparableConv2D as used by
 // keras.applications.Xception (reference call site spnet/models.py:359).
 //
 // HBM-bound: every thread owns one 16-byte channel vector (8 bf16 / 4 fp32) of one
@@ -247,268 +248,6 @@ __global__ void __launch_bounds__(256, 2) dw3x3_tma_kernel(const __grid_constant
     }
 }
 
-// Fused backward of the depthwise stage: one pass produces
-//   gin   = dw3x3^T(gout) * relu'(in_a*in+in_b)  [+ add_src] [+ add_strided at even (h,w)]
-//   dk   += sum act(in)[h+kh-1, w+kw-1] * gout[h, w]                      (weight gradient)
-//   stats += (sum gin, sum gin * xhat),  xhat = (in - mean)*rstd          (BatchNorm backward sums
-//            of the BN that produced `in`; only when stats != nullptr)
-// so the gradient tile (TMA, with halo) and the input tensor are each read once and the masked
-// gradient is written once — 3 tensor passes instead of the 8 that separate dgrad / wgrad /
-// bn_bwd_reduce kernels need. Both gradients use the SAME 3x3 neighbourhood of gout around a
-// pixel: dgrad = sum_n gout_n * k_n,  dk_n += act(in)(pixel) * gout_n.
-// Warp-specialised: the first half of the CTA computes the data gradient (+mask, +BN sums, store),
-// the second half the weight gradient, both from the same TMA-staged gradient tile.
-template <typename T, bool AFFINE, bool RELU, bool EPI>
-__global__ void __launch_bounds__(512, 1) dw3x3_bwd_fused_kernel(
-    const __grid_constant__ CUtensorMap tm_g, const T* __restrict__ in, const float* __restrict__ k,
-    const float* __restrict__ in_a, const float* __restrict__ in_b, const float* __restrict__ bn_mean,
-    const float* __restrict__ bn_rstd, double* __restrict__ stats, T* __restrict__ gin, float* __restrict__ dk, int B,
-    int H, int W, int C, int TH, int TW, int tiles_h, int tiles_w, DwEpilogue ep) {
-    constexpr int G = DW_G, CB = DW_CB;
-    constexpr uint32_t ES = sizeof(T);
-    extern __shared__ uint8_t dw_smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2];
-    const uint32_t sbase = (smem_u32(dw_smem_raw) + 127u) & ~127u;
-    const int half = blockDim.x >> 1;
-    const bool wg_role = (int)threadIdx.x >= half;  // warp-uniform: half is a multiple of 32
-    const int tl = threadIdx.x - (wg_role ? half : 0);
-    const int cg = tl & 15, colg = tl >> 4;
-    const int ncolg = half >> 4;
-    const int cbase = blockIdx.y * CB;
-    const int c0 = cbase + cg * G;
-    const bool c_ok = c0 < C;
-    const int TWH = TW + 2;
-    const uint32_t tile_bytes = (uint32_t)((TH + 2) * TWH * CB) * ES;
-    const uint32_t row_bytes = (uint32_t)(TWH * CB) * ES;
-    const int n_tiles = B * tiles_h * tiles_w;
-    const int col0 = colg * 2;
-    const size_t rowC = (size_t)W * C;
-
-    float av[G], bv[G];
-#pragma unroll
-    for (int i = 0; i < G; ++i) {
-        av[i] = (AFFINE && c_ok) ? in_a[c0 + i] : 1.f;
-        bv[i] = (AFFINE && c_ok) ? in_b[c0 + i] : 0.f;
-    }
-    const uint32_t bar0 = smem_u32(&bars[0]);
-    if (threadIdx.x == 0) {
-        mbar_init(bar0, 1);
-        mbar_init(bar0 + 8, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) {
-        const DwTileCoord t = dw_tile_coord(blockIdx.x, tiles_w, tiles_h, TH, TW);
-        mbar_expect_tx(bar0, tile_bytes);
-        tma_load_4d(sbase, &tm_g, bar0, cbase, t.w0 - 1, t.h0 - 1, t.b);
-    }
-
-    // role-private state (only one of the two sets is live in any warp)
-    float wt[9][G];      // data-gradient role: flipped taps;  weight-gradient role: dk accumulators
-    float s1[G], s2[G];  // BN sums: s1 = sum g, s2 = sum g*in (raw); xhat is fixed up at the end
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int i = 0; i < G; ++i) wt[t][i] = (!wg_role && c_ok) ? k[(8 - t) * C + c0 + i] : 0.f;
-#pragma unroll
-    for (int i = 0; i < G; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int cur = it & 1;
-        const int nxt = tile + gridDim.x;
-        if (threadIdx.x == 0 && nxt < n_tiles) {
-            const DwTileCoord t = dw_tile_coord(nxt, tiles_w, tiles_h, TH, TW);
-            mbar_expect_tx(bar0 + 8 * (cur ^ 1), tile_bytes);
-            tma_load_4d(sbase + (cur ^ 1) * tile_bytes, &tm_g, bar0 + 8 * (cur ^ 1), cbase, t.w0 - 1, t.h0 - 1, t.b);
-        }
-        const DwTileCoord tc = dw_tile_coord(tile, tiles_w, tiles_h, TH, TW);
-        const int h0 = tc.h0, w0 = tc.w0;
-        const int nrow = min(TH, H - h0);  // centre rows owned by this tile
-        const int rows = nrow + 2;
-        const bool own0 = c_ok && (w0 + col0) < W, own1 = c_ok && (w0 + col0 + 1) < W;
-        uint32_t s_row = sbase + cur * tile_bytes + (uint32_t)(col0 * CB + cg * G) * ES;
-        const size_t pix0 = ((size_t)tc.b * H + h0) * rowC + (size_t)(w0 + col0) * C + c0;  // centre row h0
-
-        if (!wg_role) {
-            // ================= data gradient (+ ReLU mask, BN sums, residual adds, store) =================
-            const T* u_ptr = in + pix0;
-            T* o_ptr = gin + pix0;
-            float A_[2][G], B_[2][G], C_[2][G];
-#pragma unroll
-            for (int oc = 0; oc < 2; ++oc)
-#pragma unroll
-                for (int i = 0; i < G; ++i) { A_[oc][i] = 0.f; B_[oc][i] = 0.f; C_[oc][i] = 0.f; }
-            mbar_wait(bar0 + 8 * cur, (uint32_t)(it >> 1) & 1u);
-            int r = 0;
-            auto step = [&](float (&P)[2][G], float (&Q)[2][G], float (&R)[2][G]) {
-                const bool emit = r >= 2;  // P completes output row h0 + r - 2
-                Raw4<T> ru0, ru1;
-                if (emit && (RELU || stats)) {  // issued early, widened only after the FMAs below
-                    if (own0) ru0 = load_raw4(u_ptr);
-                    if (own1) ru1 = load_raw4(u_ptr + C);
-                }
-                float x[4][G];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) lds4(s_row + j * (CB * ES), x[j], (const T*)nullptr);
-                dw_row_fma(x, wt, P, Q, R);
-                if (emit) {
-#pragma unroll
-                    for (int oc = 0; oc < 2; ++oc) {
-                        if (!(oc ? own1 : own0)) continue;
-                        if (RELU || stats) {
-                            float u[G];
-                            unpack4(oc ? ru1 : ru0, u);
-#pragma unroll
-                            for (int i = 0; i < G; ++i) {
-                                if (RELU) {
-                                    const float pre = AFFINE ? fmaf(u[i], av[i], bv[i]) : u[i];
-                                    if (!(pre > 0.f)) P[oc][i] = 0.f;
-                                }
-                                if (stats) {
-                                    const float rr = round_to<T>(P[oc][i]);
-                                    s1[i] += rr;
-                                    s2[i] = fmaf(rr, u[i], s2[i]);
-                                }
-                            }
-                        }
-                        if (EPI) {
-                            const int oh = h0 + r - 2, ow = w0 + col0 + oc;
-                            const size_t o = (size_t)(o_ptr - gin) + (size_t)oc * C;
-                            if (ep.add_src) {
-                                float m[G];
-                                load4(reinterpret_cast<const T*>(ep.add_src) + o, m);
-#pragma unroll
-                                for (int i = 0; i < G; ++i) P[oc][i] += m[i];
-                            }
-                            if (ep.add_strided && ((oh | ow) & 1) == 0) {
-                                const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
-                                float m[G];
-                                load4(reinterpret_cast<const T*>(ep.add_strided) +
-                                          (((size_t)tc.b * H2 + (oh >> 1)) * W2 + (ow >> 1)) * C + c0, m);
-#pragma unroll
-                                for (int i = 0; i < G; ++i) P[oc][i] += m[i];
-                            }
-                        }
-                        store4(o_ptr + (size_t)oc * C, P[oc]);
-                    }
-                    o_ptr += rowC;
-                    u_ptr += rowC;
-                }
-#pragma unroll
-                for (int oc = 0; oc < 2; ++oc)
-#pragma unroll
-                    for (int i = 0; i < G; ++i) P[oc][i] = 0.f;
-                s_row += row_bytes;
-                ++r;
-            };
-            while (r + 3 <= rows) { step(A_, B_, C_); step(B_, C_, A_); step(C_, A_, B_); }
-            if (r < rows) { step(A_, B_, C_); if (r < rows) step(B_, C_, A_); }
-        } else {
-            // ================= weight gradient: dk[kh][kw] += act(in)[gh+kh-1][c] * g[gh][c-kw+1] =================
-            // (dk accumulators live in wt[][]). Window V0,V1,V2 = act(in) rows gh-1, gh, gh+1, zero outside
-            // the rows/cols this tile owns; rotated by the 3x unrolled loop.
-            const T* v_ptr = in + pix0;  // next centre row to fetch
-            int vrow = 0;                // its index within the tile's centre rows
-            auto fetch = [&](Raw4<T>& r0, Raw4<T>& r1) -> bool {
-                const bool ok = vrow < nrow;
-                if (ok) {
-                    if (own0) r0 = load_raw4(v_ptr);
-                    if (own1) r1 = load_raw4(v_ptr + C);
-                    v_ptr += rowC;
-                }
-                ++vrow;
-                return ok;
-            };
-            auto widen = [&](bool ok, const Raw4<T>& r0, const Raw4<T>& r1, float (&v)[2][G]) {
-#pragma unroll
-                for (int oc = 0; oc < 2; ++oc) {
-                    if (ok && (oc ? own1 : own0)) {
-                        unpack4(oc ? r1 : r0, v[oc]);
-#pragma unroll
-                        for (int i = 0; i < G; ++i) {
-                            float y = v[oc][i];
-                            if (AFFINE) y = fmaf(y, av[i], bv[i]);
-                            if (RELU) y = fmaxf(y, 0.f);
-                            v[oc][i] = y;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < G; ++i) v[oc][i] = 0.f;
-                    }
-                }
-            };
-            float V0[2][G], V1[2][G], V2[2][G];
-#pragma unroll
-            for (int oc = 0; oc < 2; ++oc)
-#pragma unroll
-                for (int i = 0; i < G; ++i) { V0[oc][i] = 0.f; V1[oc][i] = 0.f; }
-            Raw4<T> ra0, ra1, rb0, rb1;
-            const bool ok_a = fetch(ra0, ra1);  // centre row h0   (= gh+1 of the first gradient row gh = h0-1)
-            bool ok_b = fetch(rb0, rb1);        // centre row h0+1 (needed one iteration later)
-            widen(ok_a, ra0, ra1, V2);
-            mbar_wait(bar0 + 8 * cur, (uint32_t)(it >> 1) & 1u);
-            int r = 0;
-            auto step = [&](float (&Vm)[2][G], float (&Vc)[2][G], float (&Vp)[2][G]) {
-                float x[4][G];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) lds4(s_row + j * (CB * ES), x[j], (const T*)nullptr);
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-                    for (int oc = 0; oc < 2; ++oc)
-#pragma unroll
-                        for (int i = 0; i < G; ++i) {
-                            wt[0 + kw][i] = fmaf(Vm[oc][i], x[oc + 2 - kw][i], wt[0 + kw][i]);
-                            wt[3 + kw][i] = fmaf(Vc[oc][i], x[oc + 2 - kw][i], wt[3 + kw][i]);
-                            wt[6 + kw][i] = fmaf(Vp[oc][i], x[oc + 2 - kw][i], wt[6 + kw][i]);
-                        }
-                // Vm (row gh-1) is dead: refill it with row gh+2 (fetched one iteration ago), fetch gh+3
-                widen(ok_b, rb0, rb1, Vm);
-                ok_b = fetch(rb0, rb1);
-                s_row += row_bytes;
-                ++r;
-            };
-            while (r + 3 <= rows) { step(V0, V1, V2); step(V1, V2, V0); step(V2, V0, V1); }
-            if (r < rows) { step(V0, V1, V2); if (r < rows) step(V1, V2, V0); }
-        }
-        __syncthreads();  // both roles are done with buffer `cur` before it is refilled
-    }
-    // ---- CTA reduction over the column groups that share a channel group, then global atomics
-    float* red = reinterpret_cast<float*>(dw_smem_raw + (sbase - smem_u32(dw_smem_raw)));  // tile buffers are idle now
-    constexpr int NV = 9 * G + 2 * G;
-    float* mine = red + ((size_t)colg * 16 + cg) * NV;
-    if (wg_role) {
-#pragma unroll
-        for (int t = 0; t < 9; ++t)
-#pragma unroll
-            for (int i = 0; i < G; ++i) mine[t * G + i] = wt[t][i];
-    } else {
-#pragma unroll
-        for (int i = 0; i < G; ++i) { mine[36 + i] = s1[i]; mine[36 + G + i] = s2[i]; }
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < 16 * NV; e += blockDim.x) {
-        const int g = e / NV, v = e % NV;
-        const int c = cbase + g * G + (v % G);
-        if (c >= C) continue;
-        float sum = 0.f;
-        for (int q = 0; q < ncolg; ++q) sum += red[((size_t)q * 16 + g) * NV + v];
-        if (v < 36) {
-            atomicAdd(dk + (size_t)(v / G) * C + c, sum);
-        } else if (stats) {
-            if (v < 36 + G) {
-                atomicAdd(stats + c, (double)sum);  // sum g
-            } else {
-                // sum g*xhat = rstd * (sum g*in - mean * sum g)
-                float sg = 0.f;
-                for (int q = 0; q < ncolg; ++q) sg += red[((size_t)q * 16 + g) * NV + (v - G)];
-                atomicAdd(stats + (size_t)C + c, (double)bn_rstd[c] * ((double)sum - (double)bn_mean[c] * (double)sg));
-            }
-        }
-    }
-}
-
 // Weight gradient: dk[kh,kw,c] = sum_{b,h,w} act(in)[b,h+kh-1,w+kw-1,c] * g[b,h,w,c].
 // Persistent CTAs: blockDim = cvb*kcols with a fixed channel vector per thread, so the 9*V
 // partial sums stay in registers across the whole grid-stride loop; one shared-memory
@@ -684,11 +423,10 @@ int launch_dw(const void* in, const float* k, const float* in_a, const float* in
     int rc = make_nhwc_map(&tm, in, dtype, B, H, W, C, t.TW + 2, t.TH + 2);
     if (rc) return rc;
     T* y = reinterpret_cast<T*>(out);
-    if (flip) return launch_dw_inst<T, false, false, true, true>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
-    if (in_a && relu) return launch_dw_inst<T, true, true, false, false>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
-    if (in_a) return launch_dw_inst<T, true, false, false, false>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
-    if (relu) return launch_dw_inst<T, false, true, false, false>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
-    return launch_dw_inst<T, false, false, false, false>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
+    // only the stand-alone data-gradient entry point still runs on this kernel (forward and the
+    // fused backward live in dwconv_packed.cu)
+    SPNET_REQUIRE(flip && !in_a && !relu, "dwconv3x3: internal: unexpected variant");
+    return launch_dw_inst<T, false, false, true, true>(tm, k, in_a, in_b, y, B, H, W, C, t, ep, stream);
 }
 
 template <typename T>
@@ -720,61 +458,6 @@ int launch_dw_wgrad(const void* in, const void* g, const float* in_a, const floa
     return spnet_check_launch("dw3x3_wgrad");
 }
 
-template <typename T, bool AF, bool RL, bool EP>
-int launch_dw_bwd_inst(const CUtensorMap& tm, const T* in, const float* k, const float* in_a, const float* in_b,
-                       const float* mean, const float* rstd, double* stats, T* gin, float* dk, int B, int H, int W,
-                       int C, const DwTiling& t, int grid_x, DwEpilogue ep, cudaStream_t stream) {
-    auto kern = dw3x3_bwd_fused_kernel<T, AF, RL, EP>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) {
-            spnet_set_error("dwconv3x3_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return SPNET_ERR_CUDA;
-        }
-        configured = true;
-    }
-    dim3 grid(grid_x, t.chunks);
-    kern<<<grid, t.threads, t.smem, stream>>>(tm, in, k, in_a, in_b, mean, rstd, stats, gin, dk, B, H, W, C, t.TH, t.TW,
-                                              t.tiles_h, t.tiles_w, ep);
-    return spnet_check_launch("dw3x3_bwd_fused");
-}
-
-template <typename T>
-int launch_dw_bwd(const void* gout, const void* in, const float* k, const float* in_a, const float* in_b, int relu,
-                  const float* mean, const float* rstd, double* stats, void* gin, float* dk, int dtype, int B, int H,
-                  int W, int C, DwEpilogue ep, cudaStream_t stream) {
-    DwTiling t = dw_tiling(dtype, B, H, W, C);
-    const size_t red_bytes = (size_t)(t.threads / 16) * 16 * 44 * 4 + 128;  // per role-half colgroups
-    if (t.smem < red_bytes) t.smem = red_bytes;
-    SPNET_REQUIRE(t.smem <= 200 * 1024, "dwconv3x3_bwd: tile does not fit shared memory");
-    CUtensorMap tm;
-    int rc = make_nhwc_map(&tm, gout, dtype, B, H, W, C, t.TW + 2, t.TH + 2);
-    if (rc) return rc;
-    t.threads *= 2;                // data-gradient warps + weight-gradient warps
-    int per_sm = 512 / t.threads;  // <= 128 registers per thread
-    if (per_sm < 1) per_sm = 1;
-    const long long n_tiles = (long long)B * t.tiles_h * t.tiles_w;
-    long long gx = (148LL * per_sm + t.chunks - 1) / t.chunks;
-    if (gx > n_tiles) gx = n_tiles;
-    if (gx < 1) gx = 1;
-    const T* x = reinterpret_cast<const T*>(in);
-    T* y = reinterpret_cast<T*>(gin);
-#define DWB(AF, RL)                                                                                              \
-    do {                                                                                                         \
-        if (ep.add_src || ep.add_strided)                                                                        \
-            return launch_dw_bwd_inst<T, AF, RL, true>(tm, x, k, in_a, in_b, mean, rstd, stats, y, dk, B, H, W, C, t, \
-                                                       (int)gx, ep, stream);                                     \
-        return launch_dw_bwd_inst<T, AF, RL, false>(tm, x, k, in_a, in_b, mean, rstd, stats, y, dk, B, H, W, C, t,   \
-                                                    (int)gx, ep, stream);                                        \
-    } while (0)
-    if (in_a && relu) DWB(true, true);
-    if (in_a) DWB(true, false);
-    if (relu) DWB(false, true);
-    DWB(false, false);
-#undef DWB
-}
-
 int check_dw_args(const char* who, const void* in, const void* out, int dtype, int B, int H, int W, int C) {
     SPNET_REQUIRE(in && out, "%s: null pointer", who);
     SPNET_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "%s: bad shape", who);
@@ -787,17 +470,6 @@ int check_dw_args(const char* who, const void* in, const void* out, int dtype, i
 
 extern "C" {
 
-// out = dw3x3(act(in)),  act(v) = relu?(in_a*v + in_b)   (in_a/in_b nullable, fp32 [C])
-// k: [3,3,C] fp32 (keras depthwise_kernel (3,3,C,1) flattened)
-int spnet_dwconv3x3_fwd(const void* in, const float* k, const float* in_a, const float* in_b, int relu,
-                        void* out, int dtype, int B, int H, int W, int C, cudaStream_t stream) {
-    int rc = check_dw_args("dwconv3x3_fwd", in, out, dtype, B, H, W, C);
-    if (rc) return rc;
-    SPNET_REQUIRE(k && ((in_a == nullptr) == (in_b == nullptr)), "dwconv3x3_fwd: bad weight/affine pointers");
-    DwEpilogue ep = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    SPNET_DISPATCH_DTYPE(dtype, return launch_dw<T>(in, k, in_a, in_b, relu, 0, out, dtype, B, H, W, C, ep, stream));
-}
-
 // gin = dw3x3^T(gout) [* (mask_a*mask_src+mask_b > 0)] [+ add_src] [+ add_strided at even (h,w)]
 int spnet_dwconv3x3_dgrad(const void* gout, const float* k, void* gin, const void* mask_src,
                           const float* mask_a, const float* mask_b, const void* add_src,
@@ -809,24 +481,6 @@ int spnet_dwconv3x3_dgrad(const void* gout, const float* k, void* gin, const voi
     SPNET_REQUIRE(mask_src || !mask_a, "dwconv3x3_dgrad: mask affine without mask_src");
     DwEpilogue ep = {mask_src, mask_a, mask_b, add_src, add_strided};
     SPNET_DISPATCH_DTYPE(dtype, return launch_dw<T>(gout, k, nullptr, nullptr, 0, 1, gin, dtype, B, H, W, C, ep, stream));
-}
-
-// Fused backward (see dw3x3_bwd_fused_kernel): gin, dk (+=) and optional BatchNorm-backward sums.
-//   in          : the tensor the forward depthwise read (raw), transformed on load by
-//                 act(v) = relu?(in_a*v+in_b)
-//   stats       : nullable fp64 [2*C]; += (sum gin, sum gin*xhat) with xhat = (in-bn_mean)*bn_rstd
-//   add_src / add_strided : optional residual-path gradients added to gin (as in dgrad)
-int spnet_dwconv3x3_bwd_fused(const void* gout, const void* in, const float* k, const float* in_a, const float* in_b,
-                              int relu, const float* bn_mean, const float* bn_rstd, double* stats,
-                              const void* add_src, const void* add_strided, void* gin, float* dk, int dtype, int B,
-                              int H, int W, int C, cudaStream_t stream) {
-    int rc = check_dw_args("dwconv3x3_bwd_fused", gout, gin, dtype, B, H, W, C);
-    if (rc) return rc;
-    SPNET_REQUIRE(in && k && dk && ((in_a == nullptr) == (in_b == nullptr)), "dwconv3x3_bwd_fused: bad pointers");
-    SPNET_REQUIRE(!stats || (bn_mean && bn_rstd), "dwconv3x3_bwd_fused: stats need bn_mean / bn_rstd");
-    DwEpilogue ep = {nullptr, nullptr, nullptr, add_src, add_strided};
-    SPNET_DISPATCH_DTYPE(dtype, return launch_dw_bwd<T>(gout, in, k, in_a, in_b, relu, bn_mean, bn_rstd, stats, gin, dk,
-                                                        dtype, B, H, W, C, ep, stream));
 }
 
 // dk[3,3,C] += sum act(in) (*) gout     (dk fp32, accumulated with atomics: zero it first)

@@ -114,7 +114,7 @@ def test_decode_matches_numpy():
 # ------------------------------------------------------------------ depthwise
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(2, 12, 16, 728), (3, 47, 63, 128), (1, 6, 8, 2048), (2, 5, 5, 40), (1, 93, 125, 64)])
-@pytest.mark.parametrize("mode", ["plain", "relu", "affine_relu"])
+@pytest.mark.parametrize("mode", ["plain", "relu", "affine_relu", "affine"])
 def test_dwconv_fwd(dtype, shape, mode):
     ops = _ops()
     torch.manual_seed(1)
@@ -122,10 +122,10 @@ def test_dwconv_fwd(dtype, shape, mode):
     x = torch.randn(shape, device=dev()).to(dtype)
     k = torch.randn(3, 3, C, device=dev()) * 0.3
     a = b = None
-    if mode == "affine_relu":
+    if mode in ("affine_relu", "affine"):
         a = torch.rand(C, device=dev()) + 0.5
-        b = torch.randn(C, device=dev()) * 0.2
-    relu = mode != "plain"
+        b = torch.randn(C, device=dev()) * 0.2 + 0.3  # a non-zero shift makes the padding order visible
+    relu = mode in ("relu", "affine_relu")
     out = ops.dwconv3x3_fwd(x, k, a, b, relu)
     ref = dw_ref(x, k, a, b, relu)
     torch.testing.assert_close(out.float(), ref, **tol(dtype))
