@@ -47,52 +47,124 @@ __global__ void bn_inference_affine_kernel(const float* __restrict__ gamma, cons
 }
 
 // Channel-stationary mapping shared by the element-wise kernels below: a thread keeps one
-// 16-byte channel vector (its per-channel coefficients stay in registers) and walks rows with a
-// grid stride, UNROLL independent 16-byte loads in flight per tensor.
+// 16-byte channel vector (its per-channel coefficients stay in registers as fp32 pairs, fetched
+// with 16-byte loads) and walks a contiguous range of rows, UNROLL independent 16-byte loads in
+// flight per tensor. Tensor values stay in their raw 16-byte form until they are used and all
+// arithmetic is packed fp32 (fma.rn.f32x2), which keeps the kernels at ~64 registers so that a
+// whole grid is resident in ONE wave — these launches are short (tens of microseconds), a second
+// wave would pay the prologue latency again.
 constexpr int UNROLL = 4;
+
+__device__ __forceinline__ uint64_t pk2(float2 v) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+    return r;
+}
+__device__ __forceinline__ float2 upk2(uint64_t r) {
+    float2 v;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
+    return v;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
+    return upk2(d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+    return upk2(d);
+}
+
+// A 16-byte vector of activations as NP fp32 pairs (bf16: 4 pairs, fp32: 2 pairs).
+template <typename T> struct RawVec;
+template <> struct RawVec<bf16> {
+    static constexpr int NP = 4;
+    uint4 r;
+    __device__ __forceinline__ float2 get(int i) const {
+        const uint32_t w = i == 0 ? r.x : (i == 1 ? r.y : (i == 2 ? r.z : r.w));
+        return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+    }
+    __device__ __forceinline__ void set(int i, float2 v) {
+        const uint32_t w = pack_bf16x2(v.x, v.y);
+        if (i == 0) r.x = w; else if (i == 1) r.y = w; else if (i == 2) r.z = w; else r.w = w;
+    }
+};
+template <> struct RawVec<float> {
+    static constexpr int NP = 2;
+    float4 r;
+    __device__ __forceinline__ float2 get(int i) const { return i == 0 ? make_float2(r.x, r.y) : make_float2(r.z, r.w); }
+    __device__ __forceinline__ void set(int i, float2 v) {
+        if (i == 0) { r.x = v.x; r.y = v.y; } else { r.z = v.x; r.w = v.y; }
+    }
+};
+template <typename T> __device__ __forceinline__ RawVec<T> ld_raw(const T* p) {
+    RawVec<T> v;
+    v.r = *reinterpret_cast<const decltype(v.r)*>(p);
+    return v;
+}
+template <typename T> __device__ __forceinline__ void st_raw(T* p, const RawVec<T>& v) {
+    *reinterpret_cast<decltype(v.r)*>(p) = v.r;
+}
+// per-channel fp32 coefficients of one channel vector as pairs (c0 is a multiple of 4)
+template <int NP> __device__ __forceinline__ void ld_coef(const float* __restrict__ p, int c0, float2 (&v)[NP]) {
+#pragma unroll
+    for (int i = 0; i < NP; i += 2) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p + c0 + 2 * i));
+        v[i] = make_float2(q.x, q.y);
+        v[i + 1] = make_float2(q.z, q.w);
+    }
+}
+
+struct RowRange { long long begin, end; };
+__device__ __forceinline__ RowRange cta_rows(long long rows) {
+    // each CTA walks a CONTIGUOUS range of rows (sequential DRAM pages)
+    const long long per_cta = (rows + gridDim.x - 1) / gridDim.x;
+    RowRange r;
+    r.begin = (long long)blockIdx.x * per_cta;
+    r.end = r.begin + per_cta < rows ? r.begin + per_cta : rows;
+    return r;
+}
 
 // out = act(a*z + b) [+ x];  act: 0 none, 1 relu, 2 leaky-relu(0.1)
 template <typename T>
-__global__ void __launch_bounds__(256) bn_apply_kernel(const T* z, const float* __restrict__ a,
-                                                       const float* __restrict__ b, int act, const T* x, T* out,
-                                                       long long rows, int C, int cvb, int krows) {
-    constexpr int V = VecN<T>::N;
+__global__ void __launch_bounds__(256, 3) bn_apply_kernel(const T* z, const float* __restrict__ a,
+                                                          const float* __restrict__ b, int act, const T* x, T* out,
+                                                          long long rows, int C, int cvb, int krows) {
+    constexpr int V = VecN<T>::N, NP = RawVec<T>::NP;
     const int CV = C / V;
     const int cvl = threadIdx.x % cvb, rl = threadIdx.x / cvb;
     const int cv = blockIdx.y * cvb + cvl;
     if (cv >= CV) return;
     const int c0 = cv * V;
-    float av[V], bv[V];
-#pragma unroll
-    for (int i = 0; i < V; ++i) { av[i] = a[c0 + i]; bv[i] = b[c0 + i]; }
-    // each CTA walks a CONTIGUOUS range of rows (sequential DRAM pages), UNROLL*krows rows per iteration
-    const long long per_cta = (rows + gridDim.x - 1) / gridDim.x;
-    const long long r_begin = (long long)blockIdx.x * per_cta;
-    const long long r_end = r_begin + per_cta < rows ? r_begin + per_cta : rows;
+    float2 av[NP], bv[NP];
+    ld_coef<NP>(a, c0, av);
+    ld_coef<NP>(b, c0, bv);
+    const RowRange rr = cta_rows(rows);
     const long long stride = krows;
-    for (long long r0 = r_begin + rl; r0 < r_end; r0 += stride * UNROLL) {
-        float v[UNROLL][V], xr[UNROLL][V];
+    for (long long r0 = rr.begin + rl; r0 < rr.end; r0 += stride * UNROLL) {
+        RawVec<T> v[UNROLL], xr[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const long long r = r0 + u * stride;
-            if (r < r_end) {
-                load_vec(z + r * C + c0, v[u]);
-                if (x) load_vec(x + r * C + c0, xr[u]);
+            if (r < rr.end) {
+                v[u] = ld_raw(z + r * C + c0);
+                if (x) xr[u] = ld_raw(x + r * C + c0);
             }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const long long r = r0 + u * stride;
-            if (r < r_end) {
+            if (r < rr.end) {
 #pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    float y = fmaf(v[u][i], av[i], bv[i]);
-                    if (act == 1) y = fmaxf(y, 0.f);
-                    else if (act == 2) y = y > 0.f ? y : 0.1f * y;
-                    if (x) y += xr[u][i];
-                    v[u][i] = y;
+                for (int i = 0; i < NP; ++i) {
+                    float2 y = ffma2(v[u].get(i), av[i], bv[i]);
+                    if (act == 1) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); }
+                    else if (act == 2) { y.x = y.x > 0.f ? y.x : 0.1f * y.x; y.y = y.y > 0.f ? y.y : 0.1f * y.y; }
+                    if (x) y = fadd2(y, xr[u].get(i));
+                    v[u].set(i, y);
                 }
-                store_vec(out + r * C + c0, v[u]);
+                st_raw(out + r * C + c0, v[u]);
             }
         }
     }
@@ -101,72 +173,78 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* z, const float* 
 // stats[c] += sum g, stats[C+c] += sum g*xhat, xhat = (z-mean)*rstd.
 // If relu_a is given, g is first masked in place by (relu_a*z+relu_b > 0) (act 1) or scaled
 // by the leaky slope (act 2): the gradient of the activation that followed this BN.
-template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(T* __restrict__ g, const T* __restrict__ z,
-                                                            const float* __restrict__ mean,
-                                                            const float* __restrict__ rstd,
-                                                            const float* __restrict__ relu_a,
-                                                            const float* __restrict__ relu_b, int act,
-                                                            double* __restrict__ stats, long long rows, int C,
-                                                            int cvb, int krows) {
-    constexpr int V = VecN<T>::N;
+template <typename T, bool MASKED>
+__global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(T* __restrict__ g, const T* __restrict__ z,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd,
+                                                               const float* __restrict__ relu_a,
+                                                               const float* __restrict__ relu_b, int act,
+                                                               double* __restrict__ stats, long long rows, int C,
+                                                               int cvb, int krows) {
+    constexpr int V = VecN<T>::N, NP = RawVec<T>::NP;
     const int CV = C / V;
     const int cvl = threadIdx.x % cvb, rl = threadIdx.x / cvb;
     const int cv = blockIdx.y * cvb + cvl;
     const bool active = cv < CV;
     const int c0 = cv * V;
-    float s1[V], s2[V];
+    float2 s1[NP], s2[NP];
 #pragma unroll
-    for (int i = 0; i < V; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+    for (int i = 0; i < NP; ++i) s1[i] = s2[i] = make_float2(0.f, 0.f);
     if (active) {
-        float mu[V], rs[V], ra[V], rb[V];
+        float2 rs[NP], nm[NP], ra[NP], rb[NP];  // xhat = z*rs + nm,  nm = -mean*rs
+        ld_coef<NP>(rstd, c0, rs);
+        ld_coef<NP>(mean, c0, nm);
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            mu[i] = mean[c0 + i];
-            rs[i] = rstd[c0 + i];
-            ra[i] = relu_a ? relu_a[c0 + i] : 0.f;
-            rb[i] = relu_a ? relu_b[c0 + i] : 0.f;
+        for (int i = 0; i < NP; ++i) {
+            nm[i] = make_float2(-nm[i].x * rs[i].x, -nm[i].y * rs[i].y);
+            ra[i] = rb[i] = make_float2(0.f, 0.f);
         }
-        const long long per_cta = (rows + gridDim.x - 1) / gridDim.x;
-        const long long r_begin = (long long)blockIdx.x * per_cta;
-        const long long r_end = r_begin + per_cta < rows ? r_begin + per_cta : rows;
+        if (MASKED) {
+            ld_coef<NP>(relu_a, c0, ra);
+            ld_coef<NP>(relu_b, c0, rb);
+        }
+        const RowRange rr = cta_rows(rows);
         const long long stride = krows;
-        for (long long r0 = r_begin + rl; r0 < r_end; r0 += stride * UNROLL) {
-            float gv[UNROLL][V], zv[UNROLL][V];
+        for (long long r0 = rr.begin + rl; r0 < rr.end; r0 += stride * UNROLL) {
+            RawVec<T> gv[UNROLL], zv[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const long long r = r0 + u * stride;
-                if (r < r_end) {
-                    load_vec(g + r * C + c0, gv[u]);
-                    load_vec(z + r * C + c0, zv[u]);
+                if (r < rr.end) {
+                    gv[u] = ld_raw(g + r * C + c0);
+                    zv[u] = ld_raw(z + r * C + c0);
                 }
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const long long r = r0 + u * stride;
-                if (r >= r_end) continue;
-                if (relu_a) {
+                if (r >= rr.end) continue;
+                if (MASKED) {
 #pragma unroll
-                    for (int i = 0; i < V; ++i) {
-                        const float y = fmaf(zv[u][i], ra[i], rb[i]);
-                        if (!(y > 0.f)) gv[u][i] = (act == 2) ? 0.1f * gv[u][i] : 0.f;
+                    for (int i = 0; i < NP; ++i) {
+                        const float2 y = ffma2(zv[u].get(i), ra[i], rb[i]);
+                        float2 gg = gv[u].get(i);
+                        if (!(y.x > 0.f)) gg.x = (act == 2) ? 0.1f * gg.x : 0.f;
+                        if (!(y.y > 0.f)) gg.y = (act == 2) ? 0.1f * gg.y : 0.f;
+                        gv[u].set(i, gg);  // re-rounded to T: the sums below use the value as it will be re-read
                     }
-                    store_vec(g + r * C + c0, gv[u]);
-                    // sums use the value as it will be re-read
-#pragma unroll
-                    for (int i = 0; i < V; ++i) gv[u][i] = round_to<T>(gv[u][i]);
+                    st_raw(g + r * C + c0, gv[u]);
                 }
 #pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    s1[i] += gv[u][i];
-                    s2[i] = fmaf(gv[u][i], (zv[u][i] - mu[i]) * rs[i], s2[i]);
+                for (int i = 0; i < NP; ++i) {
+                    const float2 gg = gv[u].get(i);
+                    s1[i] = fadd2(s1[i], gg);
+                    s2[i] = ffma2(gg, ffma2(zv[u].get(i), rs[i], nm[i]), s2[i]);
                 }
             }
         }
     }
     __shared__ float red[2][256 * 8];
 #pragma unroll
-    for (int i = 0; i < V; ++i) { red[0][threadIdx.x * V + i] = s1[i]; red[1][threadIdx.x * V + i] = s2[i]; }
+    for (int i = 0; i < NP; ++i) {
+        red[0][threadIdx.x * V + 2 * i] = s1[i].x; red[0][threadIdx.x * V + 2 * i + 1] = s1[i].y;
+        red[1][threadIdx.x * V + 2 * i] = s2[i].x; red[1][threadIdx.x * V + 2 * i + 1] = s2[i].y;
+    }
     __syncthreads();
     if (rl == 0 && active) {
 #pragma unroll
@@ -199,63 +277,68 @@ __global__ void bn_bwd_finalize_kernel(double* __restrict__ stats, double count,
 // out = a * (g - c1 - xhat*c2) = A*g + Bz*z + D with per-channel A = a, Bz = -a*rstd*c2,
 // D = a*(rstd*c2*mean - c1)
 template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const T* g, const T* __restrict__ z,
-                                                        const float* __restrict__ a,
-                                                        const float* __restrict__ mean,
-                                                        const float* __restrict__ rstd,
-                                                        const float* __restrict__ c1,
-                                                        const float* __restrict__ c2, T* out, long long rows, int C,
-                                                        int cvb, int krows) {
-    constexpr int V = VecN<T>::N;
+__global__ void __launch_bounds__(256, 3) bn_bwd_dz_kernel(const T* g, const T* __restrict__ z,
+                                                           const float* __restrict__ a,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd,
+                                                           const float* __restrict__ c1,
+                                                           const float* __restrict__ c2, T* out, long long rows,
+                                                           int C, int cvb, int krows) {
+    constexpr int V = VecN<T>::N, NP = RawVec<T>::NP;
     const int CV = C / V;
     const int cvl = threadIdx.x % cvb, rl = threadIdx.x / cvb;
     const int cv = blockIdx.y * cvb + cvl;
     if (cv >= CV) return;
     const int c0 = cv * V;
-    float A[V], Bz[V], D[V];
+    float2 A[NP], Bz[NP], D[NP];
+    {
+        float2 mu[NP], rs[NP], k1[NP], k2[NP];
+        ld_coef<NP>(a, c0, A);
+        ld_coef<NP>(mean, c0, mu);
+        ld_coef<NP>(rstd, c0, rs);
+        ld_coef<NP>(c1, c0, k1);
+        ld_coef<NP>(c2, c0, k2);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-        const float aa = a[c0 + i], k = rstd[c0 + i] * c2[c0 + i];
-        A[i] = aa;
-        Bz[i] = -aa * k;
-        D[i] = aa * (k * mean[c0 + i] - c1[c0 + i]);
+        for (int i = 0; i < NP; ++i) {
+            const float kx = rs[i].x * k2[i].x, ky = rs[i].y * k2[i].y;
+            Bz[i] = make_float2(-A[i].x * kx, -A[i].y * ky);
+            D[i] = make_float2(A[i].x * (kx * mu[i].x - k1[i].x), A[i].y * (ky * mu[i].y - k1[i].y));
+        }
     }
-    // each CTA walks a CONTIGUOUS range of rows (sequential DRAM pages), UNROLL*krows rows per iteration
-    const long long per_cta = (rows + gridDim.x - 1) / gridDim.x;
-    const long long r_begin = (long long)blockIdx.x * per_cta;
-    const long long r_end = r_begin + per_cta < rows ? r_begin + per_cta : rows;
+    const RowRange rr = cta_rows(rows);
     const long long stride = krows;
-    for (long long r0 = r_begin + rl; r0 < r_end; r0 += stride * UNROLL) {
-        float gv[UNROLL][V], zv[UNROLL][V];
+    for (long long r0 = rr.begin + rl; r0 < rr.end; r0 += stride * UNROLL) {
+        RawVec<T> gv[UNROLL], zv[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const long long r = r0 + u * stride;
-            if (r < r_end) {
-                load_vec(g + r * C + c0, gv[u]);
-                load_vec(z + r * C + c0, zv[u]);
+            if (r < rr.end) {
+                gv[u] = ld_raw(g + r * C + c0);
+                zv[u] = ld_raw(z + r * C + c0);
             }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const long long r = r0 + u * stride;
-            if (r < r_end) {
+            if (r < rr.end) {
 #pragma unroll
-                for (int i = 0; i < V; ++i) gv[u][i] = fmaf(gv[u][i], A[i], fmaf(zv[u][i], Bz[i], D[i]));
-                store_vec(out + r * C + c0, gv[u]);
+                for (int i = 0; i < NP; ++i) gv[u].set(i, ffma2(gv[u].get(i), A[i], ffma2(zv[u].get(i), Bz[i], D[i])));
+                st_raw(out + r * C + c0, gv[u]);
             }
         }
     }
 }
 
 struct ChanGrid { int cvb, krows; dim3 grid; };
-static ChanGrid chan_grid(int CV, long long rows, int waves) {
+static ChanGrid chan_grid(int CV, long long rows, int ctas_per_sm) {
     ChanGrid c;
     const int nchunks = ceil_div(CV, 128);
     c.cvb = ceil_div(CV, nchunks);
     c.krows = 256 / c.cvb;
     if (c.krows < 1) c.krows = 1;
-    long long gx = (rows + c.krows - 1) / c.krows;
-    const long long cap = (148LL * waves + nchunks - 1) / nchunks;
+    // one resident wave; at least 2*UNROLL rows per thread so the coefficient prologue is amortised
+    long long gx = (rows + (long long)c.krows * 2 * UNROLL - 1) / ((long long)c.krows * 2 * UNROLL);
+    const long long cap = (148LL * ctas_per_sm) / nchunks;
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     c.grid = dim3((unsigned)gx, nchunks);
@@ -299,7 +382,7 @@ int spnet_bn_apply(const void* z, const float* a, const float* b, int act, const
     int rc = check_rc("bn_apply", dtype, rows, C);
     if (rc) return rc;
     SPNET_REQUIRE(z && a && b && out && act >= 0 && act <= 2, "bn_apply: bad args");
-    const ChanGrid cg = chan_grid(C / (dtype == SPNET_BF16 ? 8 : 4), rows, 8);
+    const ChanGrid cg = chan_grid(C / (dtype == SPNET_BF16 ? 8 : 4), rows, 3);
     SPNET_DISPATCH_DTYPE(dtype, (bn_apply_kernel<T><<<cg.grid, cg.cvb * cg.krows, 0, stream>>>(
                                     reinterpret_cast<const T*>(z), a, b, act, reinterpret_cast<const T*>(x),
                                     reinterpret_cast<T*>(out), rows, C, cg.cvb, cg.krows)));
@@ -313,19 +396,16 @@ int spnet_bn_bwd_reduce(void* g, const void* z, const float* save_mean, const fl
     if (rc) return rc;
     SPNET_REQUIRE(g && z && save_mean && save_rstd && stats, "bn_bwd_reduce: null pointer");
     SPNET_REQUIRE((relu_a == nullptr) == (relu_b == nullptr), "bn_bwd_reduce: mask affine comes in pairs");
-    const int V = dtype == SPNET_BF16 ? 8 : 4;
-    const int CV = C / V;
-    const int nchunks = ceil_div(CV, 128);
-    const int cvb = ceil_div(CV, nchunks);
-    int krows = 256 / cvb;
-    if (krows < 1) krows = 1;
-    int gx = ceil_div(rows, krows);
-    const int cap = (4 * 148 + nchunks - 1) / nchunks;
-    if (gx > cap) gx = cap;
-    dim3 grid(gx, nchunks);
-    SPNET_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T><<<grid, cvb * krows, 0, stream>>>(
-                                    reinterpret_cast<T*>(g), reinterpret_cast<const T*>(z), save_mean, save_rstd,
-                                    relu_a, relu_b, act, stats, rows, C, cvb, krows)));
+    const ChanGrid cg = chan_grid(C / (dtype == SPNET_BF16 ? 8 : 4), rows, 3);
+    if (relu_a) {
+        SPNET_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T, true><<<cg.grid, cg.cvb * cg.krows, 0, stream>>>(
+                                        reinterpret_cast<T*>(g), reinterpret_cast<const T*>(z), save_mean, save_rstd,
+                                        relu_a, relu_b, act, stats, rows, C, cg.cvb, cg.krows)));
+    } else {
+        SPNET_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T, false><<<cg.grid, cg.cvb * cg.krows, 0, stream>>>(
+                                        reinterpret_cast<T*>(g), reinterpret_cast<const T*>(z), save_mean, save_rstd,
+                                        relu_a, relu_b, act, stats, rows, C, cg.cvb, cg.krows)));
+    }
     return spnet_check_launch("bn_bwd_reduce");
 }
 
@@ -343,7 +423,7 @@ int spnet_bn_bwd_dz(const void* g, const void* z, const float* a, const float* s
     int rc = check_rc("bn_bwd_dz", dtype, rows, C);
     if (rc) return rc;
     SPNET_REQUIRE(g && z && a && save_mean && save_rstd && c1 && c2 && out, "bn_bwd_dz: null pointer");
-    const ChanGrid cg = chan_grid(C / (dtype == SPNET_BF16 ? 8 : 4), rows, 8);
+    const ChanGrid cg = chan_grid(C / (dtype == SPNET_BF16 ? 8 : 4), rows, 3);
     SPNET_DISPATCH_DTYPE(dtype, (bn_bwd_dz_kernel<T><<<cg.grid, cg.cvb * cg.krows, 0, stream>>>(
                                     reinterpret_cast<const T*>(g), reinterpret_cast<const T*>(z), a, save_mean,
                                     save_rstd, c1, c2, reinterpret_cast<T*>(out), rows, C, cg.cvb, cg.krows)));

@@ -19,6 +19,7 @@
 // TMA map fills the halo with NaN, which the affine keeps and fmaxf(NaN, 0) turns into the exact
 // zero the padding needs — no per-element masking in the hot loop.
 #include "tma.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -473,21 +474,33 @@ Tiling pick_tiling(int kind, int dtype, int B, int H, int W, int C) {
     t.threads = ncons * 32;
     // resident CTAs per SM this kernel is sized for (registers: <= 64K / threads per thread)
     int ctas = kind == 0 ? (t.TW == 32 ? 2 : (t.TW == 16 ? 4 : 6)) : (t.TW == 32 ? 1 : (t.TW == 16 ? 2 : 3));
+    int force_th = 0, force_s = 0;
+    if (const char* e = getenv("SPNET_DW_TUNE")) {  // "ctas,TH,S" (0 = automatic): tuning sweeps only
+        int a = 0, b = 0, c = 0;
+        if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3) {
+            if (a > 0) ctas = a;
+            force_th = b;
+            force_s = c;
+        }
+    }
     const size_t budget = (size_t)216 * 1024 / ctas - 1024;
     double best = 1e30;
     t.TH = 0;
     const int cands[] = {2, 3, 4, 6, 8, 12, 16};
     for (int th : cands) {
         if (th > H && th != 2) continue;
+        if (force_th && th != force_th) continue;
         const size_t stage = (size_t)(th + 2) * (t.TW + 2) * pix + (kind ? (size_t)th * t.TW * pix * (kind == 2 ? 2 : 1) : 0);
         int S = (int)(budget / stage);
-        if (S > 4) S = 4;
+        if (S > MAX_STAGES) S = MAX_STAGES;
+        if (force_s && S > force_s) S = force_s;
         if (S < 2) continue;
         const long long n = (long long)B * ceil_div(H, th) * t.tiles_w;
         long long gx = (148LL * ctas) / t.chunks;
         if (gx < 1) gx = 1;
         if (gx > n) gx = n;
         const long long per = (n + gx - 1) / gx;
+        if (S > per + 1) S = (int)per + 1;
         // rows a CTA walks (+2 halo rows and ~1 row of per-tile overhead each), scaled by the share of an SM it gets
         const double waves = (double)ceil_div(gx * t.chunks, 148LL * ctas);
         const double cost = (double)per * ((th < H ? th : H) + 3.0) * waves;
