@@ -15,6 +15,8 @@ __global__ void bn_finalize_kernel(double* __restrict__ stats, double count, con
                                    float* __restrict__ a, float* __restrict__ b, float* __restrict__ save_mean,
                                    float* __restrict__ save_rstd, float* __restrict__ moving_mean,
                                    float* __restrict__ moving_var, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double mean = stats[c] / count;
@@ -132,6 +134,8 @@ __global__ void __launch_bounds__(256, 3) bn_apply_kernel(const T* z, const floa
                                                           const float* __restrict__ b, int act, const T* x, T* out,
                                                           long long rows, int C, int cvb, int krows) {
     constexpr int V = VecN<T>::N, NP = RawVec<T>::NP;
+    pdl_trigger();
+    pdl_wait();
     const int CV = C / V;
     const int cvl = threadIdx.x % cvb, rl = threadIdx.x / cvb;
     const int cv = blockIdx.y * cvb + cvl;
@@ -182,6 +186,8 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(T* __restrict__ g
                                                                double* __restrict__ stats, long long rows, int C,
                                                                int cvb, int krows) {
     constexpr int V = VecN<T>::N, NP = RawVec<T>::NP;
+    pdl_trigger();
+    pdl_wait();
     const int CV = C / V;
     const int cvl = threadIdx.x % cvb, rl = threadIdx.x / cvb;
     const int cv = blockIdx.y * cvb + cvl;
@@ -263,6 +269,8 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(T* __restrict__ g
 __global__ void bn_bwd_finalize_kernel(double* __restrict__ stats, double count, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ c1, float* __restrict__ c2,
                                        int C) {
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double sg = stats[c], sgx = stats[C + c];
@@ -285,6 +293,8 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_dz_kernel(const T* g, const T* 
                                                            const float* __restrict__ c2, T* out, long long rows,
                                                            int C, int cvb, int krows) {
     constexpr int V = VecN<T>::N, NP = RawVec<T>::NP;
+    pdl_trigger();
+    pdl_wait();
     const int CV = C / V;
     const int cvl = threadIdx.x % cvb, rl = threadIdx.x / cvb;
     const int cv = blockIdx.y * cvb + cvl;
@@ -361,9 +371,10 @@ int spnet_bn_finalize(double* stats, long long count, const float* gamma, const 
                       float* save_rstd, float* moving_mean, float* moving_var, int C, cudaStream_t stream) {
     SPNET_REQUIRE(stats && a && b && save_mean && save_rstd && C > 0 && count > 0, "bn_finalize: bad args");
     SPNET_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr), "bn_finalize: moving stats come in pairs");
-    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(stats, (double)count, gamma, beta, eps, momentum,
-                                                             unbiased_moving_var, a, b, save_mean, save_rstd,
-                                                             moving_mean, moving_var, C);
+    cudaError_t e = spnet_launch_pdl(bn_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, stream, 1, stats,
+                                     (double)count, gamma, beta, eps, momentum, unbiased_moving_var, a, b, save_mean,
+                                     save_rstd, moving_mean, moving_var, C);
+    SPNET_REQUIRE(e == cudaSuccess, "bn_finalize: launch: %s", cudaGetErrorString(e));
     return spnet_check_launch("bn_finalize");
 }
 
@@ -383,9 +394,9 @@ int spnet_bn_apply(const void* z, const float* a, const float* b, int act, const
     if (rc) return rc;
     SPNET_REQUIRE(z && a && b && out && act >= 0 && act <= 2, "bn_apply: bad args");
     const ChanGrid cg = chan_grid(C / (dtype == SPNET_BF16 ? 8 : 4), rows, 3);
-    SPNET_DISPATCH_DTYPE(dtype, (bn_apply_kernel<T><<<cg.grid, cg.cvb * cg.krows, 0, stream>>>(
-                                    reinterpret_cast<const T*>(z), a, b, act, reinterpret_cast<const T*>(x),
-                                    reinterpret_cast<T*>(out), rows, C, cg.cvb, cg.krows)));
+    SPNET_DISPATCH_DTYPE(dtype, (spnet_launch_pdl(bn_apply_kernel<T>, cg.grid, dim3(cg.cvb * cg.krows), 0, stream, 1,
+                                                  reinterpret_cast<const T*>(z), a, b, act, reinterpret_cast<const T*>(x),
+                                                  reinterpret_cast<T*>(out), rows, C, cg.cvb, cg.krows)));
     return spnet_check_launch("bn_apply");
 }
 
@@ -398,13 +409,15 @@ int spnet_bn_bwd_reduce(void* g, const void* z, const float* save_mean, const fl
     SPNET_REQUIRE((relu_a == nullptr) == (relu_b == nullptr), "bn_bwd_reduce: mask affine comes in pairs");
     const ChanGrid cg = chan_grid(C / (dtype == SPNET_BF16 ? 8 : 4), rows, 3);
     if (relu_a) {
-        SPNET_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T, true><<<cg.grid, cg.cvb * cg.krows, 0, stream>>>(
-                                        reinterpret_cast<T*>(g), reinterpret_cast<const T*>(z), save_mean, save_rstd,
-                                        relu_a, relu_b, act, stats, rows, C, cg.cvb, cg.krows)));
+        SPNET_DISPATCH_DTYPE(dtype, (spnet_launch_pdl(bn_bwd_reduce_kernel<T, true>, cg.grid, dim3(cg.cvb * cg.krows), 0,
+                                                      stream, 1, reinterpret_cast<T*>(g), reinterpret_cast<const T*>(z),
+                                                      save_mean, save_rstd, relu_a, relu_b, act, stats, rows, C, cg.cvb,
+                                                      cg.krows)));
     } else {
-        SPNET_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T, false><<<cg.grid, cg.cvb * cg.krows, 0, stream>>>(
-                                        reinterpret_cast<T*>(g), reinterpret_cast<const T*>(z), save_mean, save_rstd,
-                                        relu_a, relu_b, act, stats, rows, C, cg.cvb, cg.krows)));
+        SPNET_DISPATCH_DTYPE(dtype, (spnet_launch_pdl(bn_bwd_reduce_kernel<T, false>, cg.grid, dim3(cg.cvb * cg.krows), 0,
+                                                      stream, 1, reinterpret_cast<T*>(g), reinterpret_cast<const T*>(z),
+                                                      save_mean, save_rstd, relu_a, relu_b, act, stats, rows, C, cg.cvb,
+                                                      cg.krows)));
     }
     return spnet_check_launch("bn_bwd_reduce");
 }
@@ -412,7 +425,9 @@ int spnet_bn_bwd_reduce(void* g, const void* z, const float* save_mean, const fl
 int spnet_bn_bwd_finalize(double* stats, long long count, float* dgamma, float* dbeta, float* c1, float* c2,
                           int C, cudaStream_t stream) {
     SPNET_REQUIRE(stats && c1 && c2 && C > 0 && count > 0, "bn_bwd_finalize: bad args");
-    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(stats, (double)count, dgamma, dbeta, c1, c2, C);
+    cudaError_t e = spnet_launch_pdl(bn_bwd_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, stream, 1, stats,
+                                     (double)count, dgamma, dbeta, c1, c2, C);
+    SPNET_REQUIRE(e == cudaSuccess, "bn_bwd_finalize: launch: %s", cudaGetErrorString(e));
     return spnet_check_launch("bn_bwd_finalize");
 }
 
@@ -424,9 +439,9 @@ int spnet_bn_bwd_dz(const void* g, const void* z, const float* a, const float* s
     if (rc) return rc;
     SPNET_REQUIRE(g && z && a && save_mean && save_rstd && c1 && c2 && out, "bn_bwd_dz: null pointer");
     const ChanGrid cg = chan_grid(C / (dtype == SPNET_BF16 ? 8 : 4), rows, 3);
-    SPNET_DISPATCH_DTYPE(dtype, (bn_bwd_dz_kernel<T><<<cg.grid, cg.cvb * cg.krows, 0, stream>>>(
-                                    reinterpret_cast<const T*>(g), reinterpret_cast<const T*>(z), a, save_mean,
-                                    save_rstd, c1, c2, reinterpret_cast<T*>(out), rows, C, cg.cvb, cg.krows)));
+    SPNET_DISPATCH_DTYPE(dtype, (spnet_launch_pdl(bn_bwd_dz_kernel<T>, cg.grid, dim3(cg.cvb * cg.krows), 0, stream, 1,
+                                                  reinterpret_cast<const T*>(g), reinterpret_cast<const T*>(z), a, save_mean,
+                                                  save_rstd, c1, c2, reinterpret_cast<T*>(out), rows, C, cg.cvb, cg.krows)));
     return spnet_check_launch("bn_bwd_dz");
 }
 

@@ -96,6 +96,46 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
     return v[0];
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// The step is a chain of ~400 short kernels; with PDL (opt-in: SPNET_B200_PDL=1) a kernel's CTAs are
+// scheduled and run their prologue (barrier init, TMEM allocation, index math) while the previous
+// kernel drains, and block in pdl_wait() until that kernel has completed and flushed its memory.
+// Without the launch attribute both instructions are no-ops. Rules used throughout:
+// pdl_trigger() first thing, pdl_wait() before the FIRST global-memory access of any kind.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool spnet_pdl_enabled();
+
+// Launch with the programmatic-stream-serialization attribute (and an optional cluster size).
+// Only for kernels that follow the rules above.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t spnet_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                           cudaStream_t stream, int cluster, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cluster > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = cluster;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (spnet_pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // dispatch on activation dtype code
 #define SPNET_DISPATCH_DTYPE(dtype, ...)                                   \
     do {                                                                   \

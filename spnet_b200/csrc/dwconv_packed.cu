@@ -131,7 +131,9 @@ dw3x3_fwd_packed_kernel(const __grid_constant__ CUtensorMap tm_in, const float* 
         }
         mbar_fence_init();
     }
+    pdl_trigger();
     __syncthreads();
+    pdl_wait();  // everything below touches global memory
 
     // Producer duty: lane 0 of warp 0 keeps S-1 tiles in flight. Stage (it-1)%S is refilled at the
     // start of tile `it`, once every warp has released it (empty barrier).
@@ -275,7 +277,9 @@ dw3x3_bwd_packed_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_c
         }
         mbar_fence_init();
     }
+    pdl_trigger();
     __syncthreads();
+    pdl_wait();  // everything below touches global memory
 
     auto issue = [&](int tile, int s) {
         const TileCoord t = tile_coord(tile, tiles_w, tiles_h, TH, TW);
@@ -526,8 +530,9 @@ int launch_fwd_inst(const CUtensorMap& tm, const float* k, const float* a, const
         }
         configured = true;
     }
-    kern<<<dim3(t.grid_x, t.chunks), t.threads, t.smem, stream>>>(tm, k, a, b, y, B, H, W, C, t.TH, t.TW, t.tiles_h,
-                                                                 t.tiles_w, t.S);
+    cudaError_t e = spnet_launch_pdl(kern, dim3(t.grid_x, t.chunks), dim3(t.threads), t.smem, stream, 1, tm, k, a, b, y, B,
+                                     H, W, C, t.TH, t.TW, t.tiles_h, t.tiles_w, t.S);
+    SPNET_REQUIRE(e == cudaSuccess, "dwconv3x3_fwd: launch: %s", cudaGetErrorString(e));
     return spnet_check_launch("dw3x3_fwd");
 }
 
@@ -560,8 +565,10 @@ int launch_bwd_inst(const CUtensorMap& tg, const CUtensorMap& tx, const CUtensor
         }
         configured = true;
     }
-    kern<<<dim3(t.grid_x, t.chunks), t.threads, t.smem, stream>>>(tg, tx, ta, k, a, b, mean, rstd, stats, sadd, gin, dk, B,
-                                                                 H, W, C, t.TH, t.TW, t.tiles_h, t.tiles_w, t.S);
+    cudaError_t e = spnet_launch_pdl(kern, dim3(t.grid_x, t.chunks), dim3(t.threads), t.smem, stream, 1, tg, tx, ta, k, a,
+                                     b, mean, rstd, stats, sadd, gin, dk, B, H, W, C, t.TH, t.TW, t.tiles_h, t.tiles_w,
+                                     t.S);
+    SPNET_REQUIRE(e == cudaSuccess, "dwconv3x3_bwd_fused: launch: %s", cudaGetErrorString(e));
     return spnet_check_launch("dw3x3_bwd_fused");
 }
 

@@ -161,9 +161,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    pdl_trigger();
     if (CL > 1) cluster_sync_all(); else __syncthreads();  // barrier inits visible cluster-wide
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_holder;
+    pdl_wait();  // the set-up above overlapped the previous kernel's tail; global memory from here on
     // with CL = 2, tiles_m counts m-tile PAIRS; this CTA owns m-tile 2*pair + rank
 
     if (warp == 0) {
@@ -415,26 +417,11 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmEpi epi, int M
     }
     const int max_clusters = num_sms / CL;
     const int grid = (int)(units < max_clusters ? units : max_clusters) * CL;
-    if (CL == 1) {
-        kern<<<grid, kThreads, smem, stream>>>(ta, tb, epi, M, N, K, kbps, tiles_m, tiles_n, (int)units);
-    } else {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = CL;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, epi, M, N, K, kbps, tiles_m, tiles_n, (int)units);
-        if (e != cudaSuccess) {
-            spnet_set_error("gemm_bf16: cluster launch: %s", cudaGetErrorString(e));
-            return SPNET_ERR_CUDA;
-        }
+    cudaError_t e = spnet_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, CL, ta, tb, epi, M, N, K, kbps,
+                                     tiles_m, tiles_n, (int)units);
+    if (e != cudaSuccess) {
+        spnet_set_error("gemm_bf16: launch: %s", cudaGetErrorString(e));
+        return SPNET_ERR_CUDA;
     }
     return spnet_check_launch("gemm_bf16");
 }
