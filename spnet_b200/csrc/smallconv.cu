@@ -1,0 +1,704 @@
+// Small-channel direct convolutions of the SPNet stem and of Xception's block1_conv1
+// (spnet/models.py:319-340; keras.applications.Xception block1_conv1): Cin <= 3, so there is no
+// tensor-core shape for them and they are HBM/latency-bound (<1 % of the model's FLOPs).
+//
+//   which 0 : stem conv1 folded with AveragePooling2D(2): 4x4 stride-2 (pad 1), 1 -> 3, fp32 input
+//   which 1 : stem conv2 / conv3: 3x3 'same', 3 -> 3, BN + LeakyReLU(0.1) applied on load
+//   which 2 : block1_conv1: 3x3 stride 2 'valid', 3 -> 32
+//
+// All kernels share one structure: a persistent CTA walks output tiles; the input window of a tile
+// is loaded cooperatively (contiguous, coalesced element loads), transformed ONCE (BN affine +
+// activation, zero padding applied after it) and parked in shared memory as planar fp32, so the
+// per-pixel work is conflict-free LDS + FMA with no address arithmetic; 3-channel outputs go back
+// through shared memory so that global stores are contiguous too. BatchNorm statistics and weight
+// gradients are accumulated in registers across all tiles of a CTA and reduced once at the end.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float apply_act(float y, int act) {
+    if (act == 1) return fmaxf(y, 0.f);
+    if (act == 2) return y > 0.f ? y : 0.1f * y;
+    return y;
+}
+
+constexpr int kThreads = 256;
+
+// Input window of an output tile -> planar fp32 shared memory sm[ci][r][c] (row pitch IWP),
+// transformed by act(a*v+b); out-of-image elements are zero (padding follows the activation).
+// Two phases so that the global loads of the NEXT tile are in flight while the current tile is
+// computed: fetch() = coalesced element loads into registers, commit() = transform + park in smem.
+template <typename TI, int CIN, int IH_T, int IW_T, int IWP>
+struct Window {
+    static constexpr int ROW_E = IW_T * CIN, N = IH_T * ROW_E, PER = (N + kThreads - 1) / kThreads;
+    TI raw[PER];
+    unsigned ok;
+    __device__ __forceinline__ void fetch(const TI* __restrict__ img, int H, int W, int ih0, int iw0) {
+        ok = 0u;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int idx = threadIdx.x + k * kThreads;
+            const int r = idx / ROW_E, e = idx - r * ROW_E;
+            const int c = e / CIN;
+            const int ih = ih0 + r, iw = iw0 + c;
+            if (idx < N && ih >= 0 && ih < H && iw >= 0 && iw < W) {
+                raw[k] = img[((size_t)ih * W + iw0) * CIN + e];
+                ok |= 1u << k;
+            }
+        }
+    }
+    __device__ __forceinline__ void commit(float* __restrict__ sm, const float* sab, bool affine, int act) const {
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int idx = threadIdx.x + k * kThreads;
+            if (idx >= N) break;
+            const int r = idx / ROW_E, e = idx - r * ROW_E;
+            const int c = e / CIN, ci = e - c * CIN;
+            float v = 0.f;
+            if (ok & (1u << k)) {
+                v = to_f32(raw[k]);
+                if (affine) v = apply_act(fmaf(v, sab[ci], sab[CIN + ci]), act);
+            }
+            sm[(ci * IH_T + r) * IWP + c] = v;
+        }
+    }
+};
+
+struct TileXY { int b, r0, c0; };
+__device__ __forceinline__ TileXY tile_xy(int tile, int tiles_h, int tiles_w, int TH, int TW) {
+    TileXY t;
+    const int tw = tile % tiles_w, q = tile / tiles_w;
+    t.c0 = tw * TW;
+    t.r0 = (q % tiles_h) * TH;
+    t.b = q / tiles_h;
+    return t;
+}
+
+// =================================================================================================
+// Forward-type pass, 3 output channels (which 0, which 1, and the data gradient of which 1, which
+// is the same convolution with the flipped + transposed kernel followed by the activation mask).
+// Tile = 16 x 64 output pixels, thread = 4 pixels (rows ty, ty+4, ty+8, ty+12).
+//   MODE 0: plain   MODE 1: + skip = mean of the 2x2 centre taps (which 0)   MODE 2: data gradient
+// =================================================================================================
+constexpr int C3_TH = 16, C3_TW = 64;
+constexpr int C3W_TH = 8;  // weight-gradient tiles: 81 partial sums + the prefetch stage must fit 128 registers
+
+template <typename TI, typename TO, int CIN, int KS, int S, int MODE>
+__global__ void __launch_bounds__(kThreads, 2) conv3out_kernel(const TI* __restrict__ in, const float* __restrict__ w,
+                                                               const float* __restrict__ in_a,
+                                                               const float* __restrict__ in_b, int act,
+                                                               TO* __restrict__ out, TO* __restrict__ skip,
+                                                               double* __restrict__ stats,
+                                                               const TO* __restrict__ mask_z,
+                                                               const float* __restrict__ mask_a,
+                                                               const float* __restrict__ mask_b, int B, int H, int W,
+                                                               int OH, int OW, int pt, int pl, int tiles_h, int tiles_w) {
+    constexpr int COUT = 3, TH = C3_TH, TW = C3_TW;
+    constexpr int IH_T = (TH - 1) * S + KS, IW_T = (TW - 1) * S + KS, IWP = IW_T + 1;
+    constexpr int NW = KS * KS * CIN * COUT;
+    __shared__ float s_in[CIN * IH_T * IWP];
+    __shared__ float ws[NW];
+    __shared__ float sab[2 * CIN + 2 * COUT];
+    __shared__ TO s_out[TH * TW * COUT];
+    __shared__ TO s_skip[MODE == 1 ? TH * TW : 1];
+    __shared__ float sred[2 * COUT];
+    for (int i = threadIdx.x; i < NW; i += kThreads) {
+        if (MODE == 2) {
+            // data gradient: out channel = forward ci, in channel = forward co, taps flipped
+            const int t = i / (CIN * COUT), rem = i % (CIN * COUT);
+            const int cin_here = rem / COUT, cout_here = rem % COUT;  // (forward co, forward ci)
+            ws[i] = w[((KS * KS - 1 - t) * COUT + cout_here) * CIN + cin_here];
+        } else {
+            ws[i] = w[i];
+        }
+    }
+    if (threadIdx.x < CIN) {
+        sab[threadIdx.x] = in_a ? in_a[threadIdx.x] : 1.f;
+        sab[CIN + threadIdx.x] = in_a ? in_b[threadIdx.x] : 0.f;
+    }
+    if (MODE == 2 && threadIdx.x < COUT) {
+        sab[2 * CIN + threadIdx.x] = mask_z ? mask_a[threadIdx.x] : 1.f;
+        sab[2 * CIN + COUT + threadIdx.x] = mask_z ? mask_b[threadIdx.x] : 0.f;
+    }
+    if (threadIdx.x < 2 * COUT) sred[threadIdx.x] = 0.f;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    float ssum[COUT] = {0.f, 0.f, 0.f}, ssq[COUT] = {0.f, 0.f, 0.f};
+    const int n_tiles = B * tiles_h * tiles_w;
+    Window<TI, CIN, IH_T, IW_T, IWP> win;
+    if ((int)blockIdx.x < n_tiles) {
+        const TileXY t = tile_xy(blockIdx.x, tiles_h, tiles_w, TH, TW);
+        win.fetch(in + (size_t)t.b * H * W * CIN, H, W, t.r0 * S - pt, t.c0 * S - pl);
+    }
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const TileXY tc = tile_xy(tile, tiles_h, tiles_w, TH, TW);
+        const int oh0 = tc.r0, ow0 = tc.c0, b = tc.b;
+        __syncthreads();  // previous tile: compute is done with s_in, copy-out is done with s_out
+        win.commit(s_in, sab, in_a != nullptr, act);
+        __syncthreads();
+        if (tile + (int)gridDim.x < n_tiles) {  // next tile's loads fly during this tile's compute
+            const TileXY t = tile_xy(tile + gridDim.x, tiles_h, tiles_w, TH, TW);
+            win.fetch(in + (size_t)t.b * H * W * CIN, H, W, t.r0 * S - pt, t.c0 * S - pl);
+        }
+#pragma unroll 1
+        for (int pp = 0; pp < TH / 4; ++pp) {
+            const int r = ty + 4 * pp;
+            const int oh = oh0 + r, ow = ow0 + tx;
+            float acc[COUT] = {0.f, 0.f, 0.f};
+            float centre = 0.f;
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < KS; ++kw) {
+                        const float v = s_in[(ci * IH_T + r * S + kh) * IWP + tx * S + kw];
+                        if (MODE == 1 && (kh == 1 || kh == 2) && (kw == 1 || kw == 2)) centre += v;
+                        const float* wr = &ws[((kh * KS + kw) * CIN + ci) * COUT];
+#pragma unroll
+                        for (int co = 0; co < COUT; ++co) acc[co] = fmaf(v, wr[co], acc[co]);
+                    }
+            const bool valid = oh < OH && ow < OW;
+            if (MODE == 2 && mask_z && valid) {
+                const TO* mz = mask_z + (((size_t)b * OH + oh) * OW + ow) * COUT;
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+                    const float pre = fmaf(to_f32(mz[co]), sab[2 * CIN + co], sab[2 * CIN + COUT + co]);
+                    if (!(pre > 0.f)) acc[co] = (act == 2) ? 0.1f * acc[co] : (act == 1 ? 0.f : acc[co]);
+                }
+            }
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                const TO o = from_f32<TO>(acc[co]);
+                s_out[(r * TW + tx) * COUT + co] = o;
+                if (valid) {
+                    const float rr = to_f32(o);
+                    ssum[co] += rr;
+                    ssq[co] = fmaf(rr, rr, ssq[co]);
+                }
+            }
+            if (MODE == 1) s_skip[r * TW + tx] = from_f32<TO>(0.25f * centre);
+        }
+        __syncthreads();
+        // contiguous row segments of the output tile
+        const int vw = min(TW, OW - ow0), vh = min(TH, OH - oh0);
+        const int row_e = vw * COUT;
+        for (int idx = threadIdx.x; idx < vh * row_e; idx += kThreads) {
+            const int r = idx / row_e, e = idx - r * row_e;
+            out[(((size_t)b * OH + oh0 + r) * OW + ow0) * COUT + e] = s_out[r * TW * COUT + e];
+        }
+        if (MODE == 1) {
+            for (int idx = threadIdx.x; idx < vh * vw; idx += kThreads) {
+                const int r = idx / vw, e = idx - r * vw;
+                skip[((size_t)b * OH + oh0 + r) * OW + ow0 + e] = s_skip[r * TW + e];
+            }
+        }
+    }
+    if (stats) {
+        __syncthreads();
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+            const float s = warp_sum(ssum[co]), q = warp_sum(ssq[co]);
+            if ((threadIdx.x & 31) == 0) { atomicAdd(&sred[co], s); atomicAdd(&sred[COUT + co], q); }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * COUT) atomicAdd(stats + threadIdx.x, (double)sred[threadIdx.x]);
+    }
+}
+
+// =================================================================================================
+// block1_conv1 forward: 3x3 stride 2 valid, 3 -> 32. Tile = 4 x 64 output pixels, thread = pixel,
+// 32 accumulators per thread, weights read from shared memory as float4.
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2) conv_b1c1_fwd_kernel(const T* __restrict__ in, const float* __restrict__ w,
+                                                                    const float* __restrict__ in_a,
+                                                                    const float* __restrict__ in_b, int act,
+                                                                    T* __restrict__ out, double* __restrict__ stats,
+                                                                    int B, int H, int W, int OH, int OW, int tiles_h,
+                                                                    int tiles_w) {
+    constexpr int CIN = 3, COUT = 32, KS = 3, S = 2, TH = 4, TW = 64;
+    constexpr int IH_T = (TH - 1) * S + KS, IW_T = (TW - 1) * S + KS, IWP = IW_T + 2;
+    __shared__ float s_in[CIN * IH_T * IWP];
+    __shared__ __align__(16) float ws[KS * KS * CIN * COUT];
+    __shared__ float sab[2 * CIN];
+    __shared__ float sred[2 * COUT];
+    for (int i = threadIdx.x; i < KS * KS * CIN * COUT; i += kThreads) ws[i] = w[i];
+    if (threadIdx.x < CIN) {
+        sab[threadIdx.x] = in_a ? in_a[threadIdx.x] : 1.f;
+        sab[CIN + threadIdx.x] = in_a ? in_b[threadIdx.x] : 0.f;
+    }
+    if (threadIdx.x < 2 * COUT) sred[threadIdx.x] = 0.f;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6, lane = threadIdx.x & 31;
+    float cs = 0.f, cq = 0.f;  // running per-channel sums: channel = lane
+    const int n_tiles = B * tiles_h * tiles_w;
+    Window<T, CIN, IH_T, IW_T, IWP> win;
+    if ((int)blockIdx.x < n_tiles) {
+        const TileXY t = tile_xy(blockIdx.x, tiles_h, tiles_w, TH, TW);
+        win.fetch(in + (size_t)t.b * H * W * CIN, H, W, t.r0 * S, t.c0 * S);
+    }
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const TileXY tc = tile_xy(tile, tiles_h, tiles_w, TH, TW);
+        const int oh0 = tc.r0, ow0 = tc.c0, b = tc.b;
+        __syncthreads();  // previous tile's readers are done with s_in
+        win.commit(s_in, sab, in_a != nullptr, act);
+        __syncthreads();
+        if (tile + (int)gridDim.x < n_tiles) {
+            const TileXY t = tile_xy(tile + gridDim.x, tiles_h, tiles_w, TH, TW);
+            win.fetch(in + (size_t)t.b * H * W * CIN, H, W, t.r0 * S, t.c0 * S);
+        }
+        const int oh = oh0 + ty, ow = ow0 + tx;
+        const bool valid = oh < OH && ow < OW;
+        float acc[COUT];
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+#pragma unroll
+        for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < KS; ++kw)
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) {
+                    const float v = s_in[(ci * IH_T + ty * S + kh) * IWP + tx * S + kw];
+                    const float4* wr = reinterpret_cast<const float4*>(&ws[((kh * KS + kw) * CIN + ci) * COUT]);
+#pragma unroll
+                    for (int c4 = 0; c4 < COUT / 4; ++c4) {
+                        const float4 ww = wr[c4];
+                        acc[4 * c4 + 0] = fmaf(v, ww.x, acc[4 * c4 + 0]);
+                        acc[4 * c4 + 1] = fmaf(v, ww.y, acc[4 * c4 + 1]);
+                        acc[4 * c4 + 2] = fmaf(v, ww.z, acc[4 * c4 + 2]);
+                        acc[4 * c4 + 3] = fmaf(v, ww.w, acc[4 * c4 + 3]);
+                    }
+                }
+        if (valid) {
+            T* o = out + (((size_t)b * OH + oh) * OW + ow) * COUT;
+            if constexpr (sizeof(T) == 2) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    *reinterpret_cast<uint4*>(o + 8 * g) =
+                        make_uint4(pack_bf16x2(acc[8 * g], acc[8 * g + 1]), pack_bf16x2(acc[8 * g + 2], acc[8 * g + 3]),
+                                   pack_bf16x2(acc[8 * g + 4], acc[8 * g + 5]), pack_bf16x2(acc[8 * g + 6], acc[8 * g + 7]));
+            } else {
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    *reinterpret_cast<float4*>(o + 4 * g) = make_float4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
+            }
+        }
+        if (stats) {
+            // lane = pixel, 32 channels per lane: the butterfly leaves channel `lane`'s sum over the warp's pixels
+            float sq[32];
+#pragma unroll
+            for (int co = 0; co < 32; ++co) {
+                acc[co] = valid ? round_to<T>(acc[co]) : 0.f;
+                sq[co] = acc[co] * acc[co];
+            }
+            cs += warp_colsum32(acc, lane);
+            cq += warp_colsum32(sq, lane);
+        }
+    }
+    if (stats) {
+        __syncthreads();
+        atomicAdd(&sred[lane], cs);
+        atomicAdd(&sred[COUT + lane], cq);
+        __syncthreads();
+        if (threadIdx.x < 2 * COUT) atomicAdd(stats + threadIdx.x, (double)sred[threadIdx.x]);
+    }
+}
+
+// 4 consecutive channels of a gradient pixel, widened to fp32, with a register prefetch stage
+template <typename T> struct G4;
+template <> struct G4<bf16> {
+    uint2 r;
+    __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint2*>(p); }
+    __device__ __forceinline__ void zero() { r = make_uint2(0u, 0u); }
+    __device__ __forceinline__ float4 get() const {
+        return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                           __uint_as_float(r.y & 0xffff0000u));
+    }
+};
+template <> struct G4<float> {
+    float4 r;
+    __device__ __forceinline__ void load(const float* p) { r = *reinterpret_cast<const float4*>(p); }
+    __device__ __forceinline__ void zero() { r = make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ float4 get() const { return r; }
+};
+
+// =================================================================================================
+// block1_conv1 data gradient: gin[ih,iw,ci] = sum_{kh,kw,co} g[(ih-kh)/2, (iw-kw)/2, co] w[kh,kw,ci,co]
+// over the taps whose (ih-kh, iw-kw) are even and inside the output. Tile = 8 x 64 INPUT pixels;
+// warp = one row, lane = column pair (2*lane, 2*lane+1) processed one parity at a time, so that
+// the set of contributing taps is warp-uniform.
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2) conv_b1c1_dgrad_kernel(const T* __restrict__ g, const float* __restrict__ w,
+                                                                      T* __restrict__ gin, int B, int H, int W, int OH,
+                                                                      int OW, int tiles_h, int tiles_w) {
+    constexpr int CIN = 3, COUT = 32, KS = 3, TH = 8, TW = 64;
+    constexpr int GH_T = TH / 2 + 1, GW_T = TW / 2 + 1, GP = COUT + 4;  // padded pixel pitch: conflict-free LDS.128
+    constexpr int NV = GH_T * GW_T * (COUT / 4), PER = (NV + kThreads - 1) / kThreads;
+    __shared__ __align__(16) float s_g[GH_T * GW_T * GP];
+    __shared__ __align__(16) float ws[KS * KS * CIN * COUT];
+    __shared__ T s_out[TH * TW * CIN];
+    for (int i = threadIdx.x; i < KS * KS * CIN * COUT; i += kThreads) ws[i] = w[i];
+    const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
+    const int n_tiles = B * tiles_h * tiles_w;
+    G4<T> pre[PER];
+    auto fetch = [&](int tile) {
+        const TileXY t = tile_xy(tile, tiles_h, tiles_w, TH, TW);
+        // g window: oh in [ih0/2 - 1, ih0/2 + TH/2), ow likewise (ih0, iw0 are even)
+        const int goh0 = t.r0 / 2 - 1, gow0 = t.c0 / 2 - 1;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int idx = threadIdx.x + k * kThreads;
+            const int v4 = idx % (COUT / 4), p = idx / (COUT / 4);
+            const int gr = p / GW_T, gc = p - gr * GW_T;
+            const int oh = goh0 + gr, ow = gow0 + gc;
+            pre[k].zero();
+            if (idx < NV && oh >= 0 && oh < OH && ow >= 0 && ow < OW)
+                pre[k].load(g + (((size_t)t.b * OH + oh) * OW + ow) * COUT + 4 * v4);
+        }
+    };
+    if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const TileXY tc = tile_xy(tile, tiles_h, tiles_w, TH, TW);
+        const int ih0 = tc.r0, iw0 = tc.c0, b = tc.b;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int idx = threadIdx.x + k * kThreads;
+            if (idx < NV) *reinterpret_cast<float4*>(&s_g[(idx / (COUT / 4)) * GP + 4 * (idx % (COUT / 4))]) = pre[k].get();
+        }
+        __syncthreads();
+        if (tile + (int)gridDim.x < n_tiles) fetch(tile + gridDim.x);
+#pragma unroll
+        for (int pw = 0; pw < 2; ++pw) {
+            const int cl = 2 * lane + pw;  // column inside the tile
+            float acc[CIN] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int kh = 0; kh < KS; ++kh) {
+                if (((row - kh) & 1) != 0) continue;  // ih0 even: parity of ih-kh = parity of row-kh (warp-uniform)
+                const int gr = (row - kh + 2) / 2;     // (ih - kh)/2 - goh0
+#pragma unroll
+                for (int kw = 0; kw < KS; ++kw) {
+                    if (((pw - kw) & 1) != 0) continue;  // compile-time after unrolling
+                    const int gc = (cl - kw + 2) / 2;
+                    const float4* gp = reinterpret_cast<const float4*>(&s_g[(gr * GW_T + gc) * GP]);
+                    const float4* wp = reinterpret_cast<const float4*>(&ws[(kh * KS + kw) * CIN * COUT]);
+#pragma unroll
+                    for (int c4 = 0; c4 < COUT / 4; ++c4) {
+                        const float4 gv = gp[c4];
+#pragma unroll
+                        for (int ci = 0; ci < CIN; ++ci) {
+                            const float4 ww = wp[ci * (COUT / 4) + c4];
+                            acc[ci] = fmaf(gv.x, ww.x, acc[ci]);
+                            acc[ci] = fmaf(gv.y, ww.y, acc[ci]);
+                            acc[ci] = fmaf(gv.z, ww.z, acc[ci]);
+                            acc[ci] = fmaf(gv.w, ww.w, acc[ci]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) s_out[(row * TW + cl) * CIN + ci] = from_f32<T>(acc[ci]);
+        }
+        __syncthreads();
+        const int vw = min(TW, W - iw0), vh = min(TH, H - ih0);
+        const int row_e = vw * CIN;
+        for (int idx = threadIdx.x; idx < vh * row_e; idx += kThreads) {
+            const int r = idx / row_e, e = idx - r * row_e;
+            gin[(((size_t)b * H + ih0 + r) * W + iw0) * CIN + e] = s_out[r * TW * CIN + e];
+        }
+    }
+}
+
+// =================================================================================================
+// Weight gradients with 3 output channels (which 0: 48 weights, which 1: 81 weights): thread = pixel,
+// all weight partial sums in registers across the CTA's tiles, one reduction at the end.
+// =================================================================================================
+template <typename TI, typename TG, int CIN, int KS, int S>
+__global__ void __launch_bounds__(kThreads, 2) conv3out_wgrad_kernel(const TI* __restrict__ in,
+                                                                     const float* __restrict__ in_a,
+                                                                     const float* __restrict__ in_b, int act,
+                                                                     const TG* __restrict__ g, float* __restrict__ dw,
+                                                                     int B, int H, int W, int OH, int OW, int pt,
+                                                                     int pl, int tiles_h, int tiles_w) {
+    constexpr int COUT = 3, TH = C3W_TH, TW = C3_TW;
+    constexpr int IH_T = (TH - 1) * S + KS, IW_T = (TW - 1) * S + KS, IWP = IW_T + 1;
+    constexpr int NW = KS * KS * CIN * COUT;
+    constexpr int NG = TH * TW * COUT, GPER = NG / kThreads;
+    __shared__ float s_in[CIN * IH_T * IWP];
+    __shared__ float s_g[COUT * TH * TW];
+    __shared__ float sab[2 * CIN];
+    __shared__ float sacc[NW];
+    if (threadIdx.x < CIN) {
+        sab[threadIdx.x] = in_a ? in_a[threadIdx.x] : 1.f;
+        sab[CIN + threadIdx.x] = in_a ? in_b[threadIdx.x] : 0.f;
+    }
+    for (int i = threadIdx.x; i < NW; i += kThreads) sacc[i] = 0.f;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    float acc[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) acc[i] = 0.f;
+    const int n_tiles = B * tiles_h * tiles_w;
+    Window<TI, CIN, IH_T, IW_T, IWP> win;
+    TG graw[GPER];
+    auto fetch = [&](int tile) {
+        const TileXY t = tile_xy(tile, tiles_h, tiles_w, TH, TW);
+        win.fetch(in + (size_t)t.b * H * W * CIN, H, W, t.r0 * S - pt, t.c0 * S - pl);
+#pragma unroll
+        for (int k = 0; k < GPER; ++k) {
+            const int idx = threadIdx.x + k * kThreads;
+            const int r = idx / (TW * COUT), e = idx - r * (TW * COUT);
+            const int oh = t.r0 + r, ow = t.c0 + e / COUT;
+            graw[k] = from_f32<TG>(0.f);
+            if (oh < OH && ow < OW) graw[k] = g[(((size_t)t.b * OH + oh) * OW + t.c0) * COUT + e];
+        }
+    };
+    if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();
+        win.commit(s_in, sab, in_a != nullptr, act);
+#pragma unroll
+        for (int k = 0; k < GPER; ++k) {  // gradient tile, planar
+            const int idx = threadIdx.x + k * kThreads;
+            const int r = idx / (TW * COUT), e = idx - r * (TW * COUT);
+            const int c = e / COUT, co = e - c * COUT;
+            s_g[(co * TH + r) * TW + c] = to_f32(graw[k]);
+        }
+        __syncthreads();
+        if (tile + (int)gridDim.x < n_tiles) fetch(tile + gridDim.x);
+#pragma unroll 1
+        for (int pp = 0; pp < TH / 4; ++pp) {
+            const int r = ty + 4 * pp;
+            float gv[COUT];
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) gv[co] = s_g[(co * TH + r) * TW + tx];
+#pragma unroll
+            for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < KS; ++kw)
+#pragma unroll
+                    for (int ci = 0; ci < CIN; ++ci) {
+                        const float v = s_in[(ci * IH_T + r * S + kh) * IWP + tx * S + kw];
+#pragma unroll
+                        for (int co = 0; co < COUT; ++co)
+                            acc[((kh * KS + kw) * CIN + ci) * COUT + co] =
+                                fmaf(v, gv[co], acc[((kh * KS + kw) * CIN + ci) * COUT + co]);
+                    }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        const float s = warp_sum(acc[i]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[i], s);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NW; i += kThreads) atomicAdd(dw + i, sacc[i]);
+}
+
+// =================================================================================================
+// block1_conv1 weight gradient (3x3 s2 valid, 3 -> 32; 864 weights): a warp covers 4 output pixels x
+// 8 groups of 4 output channels; a thread keeps 27 x 4 partial sums in registers.
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1) conv_b1c1_wgrad_kernel(const T* __restrict__ in,
+                                                                      const float* __restrict__ in_a,
+                                                                      const float* __restrict__ in_b, int act,
+                                                                      const T* __restrict__ g, float* __restrict__ dw,
+                                                                      int B, int H, int W, int OH, int OW, int tiles_h,
+                                                                      int tiles_w) {
+    constexpr int CIN = 3, COUT = 32, KS = 3, S = 2, TH = 4, TW = 32;
+    constexpr int IH_T = (TH - 1) * S + KS, IW_T = (TW - 1) * S + KS, IWP = IW_T + 2;
+    constexpr int GP = COUT + 4;
+    constexpr int NT = KS * KS * CIN;  // 27
+    constexpr int NV = TH * TW * (COUT / 4), GPER = NV / kThreads;
+    __shared__ float s_in[CIN * IH_T * IWP];
+    __shared__ __align__(16) float s_g[TH * TW * GP];
+    __shared__ float sab[2 * CIN];
+    __shared__ float sacc[NT * COUT];
+    if (threadIdx.x < CIN) {
+        sab[threadIdx.x] = in_a ? in_a[threadIdx.x] : 1.f;
+        sab[CIN + threadIdx.x] = in_a ? in_b[threadIdx.x] : 0.f;
+    }
+    for (int i = threadIdx.x; i < NT * COUT; i += kThreads) sacc[i] = 0.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cg = lane & 7, ps = lane >> 3;  // channel group (4 channels), pixel slot within the warp
+    float acc[NT][4];
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+    const int n_tiles = B * tiles_h * tiles_w;
+    Window<T, CIN, IH_T, IW_T, IWP> win;
+    G4<T> graw[GPER];
+    auto fetch = [&](int tile) {
+        const TileXY t = tile_xy(tile, tiles_h, tiles_w, TH, TW);
+        win.fetch(in + (size_t)t.b * H * W * CIN, H, W, t.r0 * S, t.c0 * S);
+#pragma unroll
+        for (int k = 0; k < GPER; ++k) {
+            const int idx = threadIdx.x + k * kThreads;
+            const int v4 = idx % (COUT / 4), p = idx / (COUT / 4);
+            const int r = p / TW, c = p - r * TW;
+            const int oh = t.r0 + r, ow = t.c0 + c;
+            graw[k].zero();
+            if (oh < OH && ow < OW) graw[k].load(g + (((size_t)t.b * OH + oh) * OW + ow) * COUT + 4 * v4);
+        }
+    };
+    if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();
+        win.commit(s_in, sab, in_a != nullptr, act);
+#pragma unroll
+        for (int k = 0; k < GPER; ++k) {
+            const int idx = threadIdx.x + k * kThreads;
+            *reinterpret_cast<float4*>(&s_g[(idx / (COUT / 4)) * GP + 4 * (idx % (COUT / 4))]) = graw[k].get();
+        }
+        __syncthreads();
+        if (tile + (int)gridDim.x < n_tiles) fetch(tile + gridDim.x);
+        // 128 pixels per tile, 32 per pass (8 warps x 4 slots)
+#pragma unroll 1
+        for (int pass = 0; pass < TH * TW / 32; ++pass) {
+            const int p = pass * 32 + warp * 4 + ps;
+            const int r = p / TW, c = p - r * TW;
+            const float4 gv = *reinterpret_cast<const float4*>(&s_g[p * GP + 4 * cg]);
+#pragma unroll
+            for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < KS; ++kw)
+#pragma unroll
+                    for (int ci = 0; ci < CIN; ++ci) {
+                        const float v = s_in[(ci * IH_T + r * S + kh) * IWP + c * S + kw];
+                        const int t = (kh * KS + kw) * CIN + ci;
+                        acc[t][0] = fmaf(v, gv.x, acc[t][0]);
+                        acc[t][1] = fmaf(v, gv.y, acc[t][1]);
+                        acc[t][2] = fmaf(v, gv.z, acc[t][2]);
+                        acc[t][3] = fmaf(v, gv.w, acc[t][3]);
+                    }
+        }
+    }
+    __syncthreads();
+    // reduce the 4 pixel slots of a warp, then the 8 warps through shared memory
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float s = acc[t][j];
+            s += __shfl_xor_sync(0xffffffffu, s, 8);
+            s += __shfl_xor_sync(0xffffffffu, s, 16);
+            if (ps == 0) atomicAdd(&sacc[t * COUT + 4 * cg + j], s);
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NT * COUT; i += kThreads) atomicAdd(dw + i, sacc[i]);
+}
+
+int persist_grid_tiles(long long n_tiles, int ctas_per_sm) {
+    const long long cap = 148LL * ctas_per_sm;
+    return (int)(n_tiles < cap ? n_tiles : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+// which: 0 = stem conv1 folded with AveragePooling2D(2): x0 fp32 [B,H,W,1] -> out [B,H/2,W/2,3], skip [B,H/2,W/2,1]
+//            (w = K4 [4,4,1,3] from spnet_stem_k3_to_k4)
+//        1 = stem conv 3->3, 3x3 same            [B,H,W,3] -> [B,H,W,3]
+//        2 = block1_conv1 3->32, 3x3 s2 valid    [B,H,W,3] -> [B,(H-3)/2+1,(W-3)/2+1,32]
+// in_a/in_b (nullable) + act (0 none, 1 relu, 2 leaky 0.1) transform the input on load.
+// stats (nullable): fp64 [2*Cout] batch-norm accumulators.
+int spnet_conv_small_fwd(int which, const void* in, const float* w, const float* in_a, const float* in_b, int act,
+                         void* out, void* skip, double* stats, int dtype, int B, int H, int W, cudaStream_t stream) {
+    SPNET_REQUIRE(in && w && out && B > 0 && H > 2 && W > 2, "conv_small_fwd: bad args");
+    SPNET_REQUIRE((in_a == nullptr) == (in_b == nullptr), "conv_small_fwd: affine parameters come in pairs");
+    if (which == 0) {
+        SPNET_REQUIRE(skip, "conv_small_fwd(0): needs the skip output");
+        const int OH = H / 2, OW = W / 2;
+        const int th = ceil_div(OH, C3_TH), tw = ceil_div(OW, C3_TW);
+        const int grid = persist_grid_tiles((long long)B * th * tw, 2);
+        SPNET_DISPATCH_DTYPE(dtype, (conv3out_kernel<float, T, 1, 4, 2, 1><<<grid, kThreads, 0, stream>>>(
+                                        reinterpret_cast<const float*>(in), w, in_a, in_b, act, reinterpret_cast<T*>(out),
+                                        reinterpret_cast<T*>(skip), stats, nullptr, nullptr, nullptr, B, H, W, OH, OW, 1,
+                                        1, th, tw)));
+    } else if (which == 1) {
+        const int th = ceil_div(H, C3_TH), tw = ceil_div(W, C3_TW);
+        const int grid = persist_grid_tiles((long long)B * th * tw, 2);
+        SPNET_DISPATCH_DTYPE(dtype, (conv3out_kernel<T, T, 3, 3, 1, 0><<<grid, kThreads, 0, stream>>>(
+                                        reinterpret_cast<const T*>(in), w, in_a, in_b, act, reinterpret_cast<T*>(out),
+                                        nullptr, stats, nullptr, nullptr, nullptr, B, H, W, H, W, 1, 1, th, tw)));
+    } else if (which == 2) {
+        const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
+        const int th = ceil_div(OH, 4), tw = ceil_div(OW, 64);
+        const int grid = persist_grid_tiles((long long)B * th * tw, 2);
+        SPNET_DISPATCH_DTYPE(dtype, (conv_b1c1_fwd_kernel<T><<<grid, kThreads, 0, stream>>>(
+                                        reinterpret_cast<const T*>(in), w, in_a, in_b, act, reinterpret_cast<T*>(out),
+                                        stats, B, H, W, OH, OW, th, tw)));
+    } else {
+        spnet_set_error("conv_small_fwd: unknown conv id %d", which);
+        return SPNET_ERR_ARG;
+    }
+    return spnet_check_launch("conv_small_fwd");
+}
+
+// dw += weight gradient of the same three convolutions (dw zeroed by the caller).
+// For which == 0, dw is the K4 gradient [4,4,1,3]; fold it with spnet_stem_k4grad_to_k3grad.
+int spnet_conv_small_wgrad(int which, const void* in, const float* in_a, const float* in_b, int act, const void* g,
+                           float* dw, int dtype, int B, int H, int W, cudaStream_t stream) {
+    SPNET_REQUIRE(in && g && dw && B > 0 && H > 2 && W > 2, "conv_small_wgrad: bad args");
+    SPNET_REQUIRE((in_a == nullptr) == (in_b == nullptr), "conv_small_wgrad: affine parameters come in pairs");
+    if (which == 0) {
+        const int OH = H / 2, OW = W / 2;
+        const int th = ceil_div(OH, C3W_TH), tw = ceil_div(OW, C3_TW);
+        const int grid = persist_grid_tiles((long long)B * th * tw, 2);
+        SPNET_DISPATCH_DTYPE(dtype, (conv3out_wgrad_kernel<float, T, 1, 4, 2><<<grid, kThreads, 0, stream>>>(
+                                        reinterpret_cast<const float*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g),
+                                        dw, B, H, W, OH, OW, 1, 1, th, tw)));
+    } else if (which == 1) {
+        const int th = ceil_div(H, C3W_TH), tw = ceil_div(W, C3_TW);
+        const int grid = persist_grid_tiles((long long)B * th * tw, 2);
+        SPNET_DISPATCH_DTYPE(dtype, (conv3out_wgrad_kernel<T, T, 3, 3, 1><<<grid, kThreads, 0, stream>>>(
+                                        reinterpret_cast<const T*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g), dw,
+                                        B, H, W, H, W, 1, 1, th, tw)));
+    } else if (which == 2) {
+        const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
+        const int th = ceil_div(OH, 4), tw = ceil_div(OW, 32);
+        const int grid = persist_grid_tiles((long long)B * th * tw, 1);  // 134 registers x 256 threads: one CTA per SM
+        SPNET_DISPATCH_DTYPE(dtype, (conv_b1c1_wgrad_kernel<T><<<grid, kThreads, 0, stream>>>(
+                                        reinterpret_cast<const T*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g), dw,
+                                        B, H, W, OH, OW, th, tw)));
+    } else {
+        spnet_set_error("conv_small_wgrad: unknown conv id %d", which);
+        return SPNET_ERR_ARG;
+    }
+    return spnet_check_launch("conv_small_wgrad");
+}
+
+// gin = data gradient (which = 1 or 2; conv 0 reads the network input, which has no gradient),
+// multiplied by act'(mask_a*mask_z+mask_b) when mask_z is given. H, W are the INPUT dims.
+int spnet_conv_small_dgrad(int which, const void* g, const float* w, const void* mask_z, const float* mask_a,
+                           const float* mask_b, int act, void* gin, int dtype, int B, int H, int W,
+                           cudaStream_t stream) {
+    SPNET_REQUIRE(g && w && gin && B > 0 && H > 2 && W > 2, "conv_small_dgrad: bad args");
+    SPNET_REQUIRE(!mask_z || (mask_a && mask_b), "conv_small_dgrad: mask needs its affine");
+    if (which == 1) {
+        // 'same' 3x3 stride 1: the data gradient is the convolution of g with the flipped, transposed kernel
+        const int th = ceil_div(H, C3_TH), tw = ceil_div(W, C3_TW);
+        const int grid = persist_grid_tiles((long long)B * th * tw, 2);
+        SPNET_DISPATCH_DTYPE(dtype, (conv3out_kernel<T, T, 3, 3, 1, 2><<<grid, kThreads, 0, stream>>>(
+                                        reinterpret_cast<const T*>(g), w, nullptr, nullptr, act, reinterpret_cast<T*>(gin),
+                                        nullptr, nullptr, reinterpret_cast<const T*>(mask_z), mask_a, mask_b, B, H, W, H, W,
+                                        1, 1, th, tw)));
+    } else if (which == 2) {
+        SPNET_REQUIRE(!mask_z, "conv_small_dgrad(2): block1_conv1 reads the stem output directly (no activation mask)");
+        const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
+        const int th = ceil_div(H, 8), tw = ceil_div(W, 64);
+        const int grid = persist_grid_tiles((long long)B * th * tw, 2);
+        SPNET_DISPATCH_DTYPE(dtype, (conv_b1c1_dgrad_kernel<T><<<grid, kThreads, 0, stream>>>(
+                                        reinterpret_cast<const T*>(g), w, reinterpret_cast<T*>(gin), B, H, W, OH, OW, th,
+                                        tw)));
+    } else {
+        spnet_set_error("conv_small_dgrad: unknown conv id %d", which);
+        return SPNET_ERR_ARG;
+    }
+    return spnet_check_launch("conv_small_dgrad");
+}
+
+}  // extern "C"

@@ -1,5 +1,5 @@
-// Small-channel direct convolutions (Cin <= 3: no tensor-core shape exists for them) and
-// the im2col pair for block1_conv2.
+// Stem glue kernels and the im2col pair for block1_conv2 (the small-channel convolutions
+// themselves are in smallconv.cu).
 //
 //  * SPNet stem (spnet/models.py:319-340): Conv2D(3,3x3,same,no bias) -> AveragePooling2D(2)
 //    -> BN -> LeakyReLU(0.1) -> Conv2D(3) -> BN -> LeakyReLU(0.1) -> Conv2D(3) -> BN
@@ -53,253 +53,6 @@ __device__ __forceinline__ float apply_act(float y, int act) {
     if (act == 1) return fmaxf(y, 0.f);
     if (act == 2) return y > 0.f ? y : 0.1f * y;
     return y;
-}
-
-// out[b,oh,ow,:] = sum_{kh,kw,ci} act(in_a*in+in_b)[b, oh*S-pt+kh, ow*S-pl+kw, ci] * w[kh,kw,ci,:]
-// POOL_SKIP (stem conv1 only, KS=4,S=2,CIN=1): also writes skip = mean of the 2x2 centre taps.
-template <typename TI, typename TO, int CIN, int COUT, int KS, int S, bool POOL_SKIP>
-__global__ void __launch_bounds__(256) conv_direct_fwd_kernel(const TI* __restrict__ in, const float* __restrict__ w,
-                                                              const float* __restrict__ in_a,
-                                                              const float* __restrict__ in_b, int act,
-                                                              TO* __restrict__ out, TO* __restrict__ skip,
-                                                              double* __restrict__ stats, int B, int H, int W,
-                                                              int OH, int OW, int pt, int pl) {
-    __shared__ float ws[KS * KS * CIN * COUT];
-    __shared__ float sred[2][COUT];
-    __shared__ float sab[2][CIN];
-    for (int i = threadIdx.x; i < KS * KS * CIN * COUT; i += blockDim.x) ws[i] = w[i];
-    if (threadIdx.x < COUT) { sred[0][threadIdx.x] = 0.f; sred[1][threadIdx.x] = 0.f; }
-    if (threadIdx.x < CIN) {
-        sab[0][threadIdx.x] = in_a ? in_a[threadIdx.x] : 1.f;
-        sab[1][threadIdx.x] = in_a ? in_b[threadIdx.x] : 0.f;
-    }
-    __syncthreads();
-    const long long n = (long long)B * OH * OW;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = idx < n;
-    float acc[COUT];
-#pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
-    if (valid) {
-        const int pix = (int)idx;  // host guarantees < 2^31 pixels: 32-bit div/mod only
-        const int ow = pix % OW;
-        const int oh = (pix / OW) % OH;
-        const int b = pix / (OW * OH);
-        float centre = 0.f;
-#pragma unroll
-        for (int kh = 0; kh < KS; ++kh) {
-            const int ih = oh * S - pt + kh;
-            if (ih < 0 || ih >= H) continue;
-#pragma unroll
-            for (int kw = 0; kw < KS; ++kw) {
-                const int iw = ow * S - pl + kw;
-                if (iw < 0 || iw >= W) continue;
-                const TI* px = in + (((size_t)b * H + ih) * W + iw) * CIN;
-#pragma unroll
-                for (int ci = 0; ci < CIN; ++ci) {
-                    float v = to_f32(px[ci]);
-                    if (in_a) v = apply_act(fmaf(v, sab[0][ci], sab[1][ci]), act);
-                    if (POOL_SKIP && (kh == 1 || kh == 2) && (kw == 1 || kw == 2)) centre += v;
-                    const float* wr = &ws[((kh * KS + kw) * CIN + ci) * COUT];
-#pragma unroll
-                    for (int co = 0; co < COUT; ++co) acc[co] = fmaf(v, wr[co], acc[co]);
-                }
-            }
-        }
-        store_row<TO, COUT>(out + idx * COUT, acc);
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) acc[co] = round_to<TO>(acc[co]);
-        if (POOL_SKIP) skip[idx] = from_f32<TO>(0.25f * centre);
-    }
-    if (stats) {
-        if constexpr (COUT == 32) {
-            // lane = pixel, 32 channels per lane: 31-shuffle butterfly leaves channel `lane`'s sum in each lane
-            float sq[32];
-#pragma unroll
-            for (int co = 0; co < 32; ++co) sq[co] = acc[co] * acc[co];
-            const int lane = threadIdx.x & 31;
-            const float s = warp_colsum32(acc, lane);
-            const float q = warp_colsum32(sq, lane);
-            atomicAdd(&sred[0][lane], s);
-            atomicAdd(&sred[1][lane], q);
-        } else {
-#pragma unroll
-            for (int co = 0; co < COUT; ++co) {
-                const float s = warp_sum(acc[co]);
-                const float q = warp_sum(acc[co] * acc[co]);
-                if ((threadIdx.x & 31) == 0) { atomicAdd(&sred[0][co], s); atomicAdd(&sred[1][co], q); }
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x < COUT) {
-            atomicAdd(stats + threadIdx.x, (double)sred[0][threadIdx.x]);
-            atomicAdd(stats + COUT + threadIdx.x, (double)sred[1][threadIdx.x]);
-        }
-    }
-}
-
-// dw[kh,kw,ci,co] += sum_pixels act(in)[.., ci] * g[b,oh,ow,co]   (small COUT: thread = output pixel)
-template <typename TI, typename TG, int CIN, int COUT, int KS, int S>
-__global__ void __launch_bounds__(256) conv_direct_wgrad_px_kernel(const TI* __restrict__ in,
-                                                                   const float* __restrict__ in_a,
-                                                                   const float* __restrict__ in_b, int act,
-                                                                   const TG* __restrict__ g, float* __restrict__ dw,
-                                                                   int B, int H, int W, int OH, int OW, int pt,
-                                                                   int pl) {
-    constexpr int NW = KS * KS * CIN * COUT;
-    __shared__ float sacc[NW];
-    for (int i = threadIdx.x; i < NW; i += blockDim.x) sacc[i] = 0.f;
-    __syncthreads();
-    float acc[NW];
-#pragma unroll
-    for (int i = 0; i < NW; ++i) acc[i] = 0.f;
-    float a[CIN], bb[CIN];
-#pragma unroll
-    for (int ci = 0; ci < CIN; ++ci) { a[ci] = in_a ? in_a[ci] : 1.f; bb[ci] = in_a ? in_b[ci] : 0.f; }
-    const long long n = (long long)B * OH * OW;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int pix = (int)idx;  // host guarantees < 2^31 pixels: 32-bit div/mod only
-        const int ow = pix % OW;
-        const int oh = (pix / OW) % OH;
-        const int b = pix / (OW * OH);
-        float gv[COUT];
-        load_row<TG, COUT>(g + idx * COUT, gv);
-#pragma unroll
-        for (int kh = 0; kh < KS; ++kh) {
-            const int ih = oh * S - pt + kh;
-            if (ih < 0 || ih >= H) continue;
-#pragma unroll
-            for (int kw = 0; kw < KS; ++kw) {
-                const int iw = ow * S - pl + kw;
-                if (iw < 0 || iw >= W) continue;
-                const TI* px = in + (((size_t)b * H + ih) * W + iw) * CIN;
-#pragma unroll
-                for (int ci = 0; ci < CIN; ++ci) {
-                    float v = to_f32(px[ci]);
-                    if (in_a) v = apply_act(fmaf(v, a[ci], bb[ci]), act);
-#pragma unroll
-                    for (int co = 0; co < COUT; ++co)
-                        acc[((kh * KS + kw) * CIN + ci) * COUT + co] =
-                            fmaf(v, gv[co], acc[((kh * KS + kw) * CIN + ci) * COUT + co]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < NW; ++i) {
-        const float s = warp_sum(acc[i]);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[i], s);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < NW; i += blockDim.x) atomicAdd(dw + i, sacc[i]);
-}
-
-// COUT == 32: one warp per output pixel, lane = output channel, KS*KS*CIN partial sums per lane.
-template <typename TI, typename TG, int CIN, int KS, int S>
-__global__ void __launch_bounds__(256) conv_direct_wgrad_lane_kernel(const TI* __restrict__ in,
-                                                                     const float* __restrict__ in_a,
-                                                                     const float* __restrict__ in_b, int act,
-                                                                     const TG* __restrict__ g,
-                                                                     float* __restrict__ dw, int B, int H, int W,
-                                                                     int OH, int OW, int pt, int pl) {
-    constexpr int NT = KS * KS * CIN;
-    __shared__ float sacc[NT * 32];
-    for (int i = threadIdx.x; i < NT * 32; i += blockDim.x) sacc[i] = 0.f;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    float acc[NT];
-#pragma unroll
-    for (int i = 0; i < NT; ++i) acc[i] = 0.f;
-    float a[CIN], bb[CIN];
-#pragma unroll
-    for (int ci = 0; ci < CIN; ++ci) { a[ci] = in_a ? in_a[ci] : 1.f; bb[ci] = in_a ? in_b[ci] : 0.f; }
-    const long long n = (long long)B * OH * OW;
-    for (long long idx = warp; idx < n; idx += nwarps) {
-        const int pix = (int)idx;  // host guarantees < 2^31 pixels: 32-bit div/mod only
-        const int ow = pix % OW;
-        const int oh = (pix / OW) % OH;
-        const int b = pix / (OW * OH);
-        const float gv = to_f32(g[(size_t)idx * 32 + lane]);
-#pragma unroll
-        for (int kh = 0; kh < KS; ++kh) {
-            const int ih = oh * S - pt + kh;
-            if (ih < 0 || ih >= H) continue;
-#pragma unroll
-            for (int kw = 0; kw < KS; ++kw) {
-                const int iw = ow * S - pl + kw;
-                if (iw < 0 || iw >= W) continue;
-                const TI* px = in + (((size_t)b * H + ih) * W + iw) * CIN;
-#pragma unroll
-                for (int ci = 0; ci < CIN; ++ci) {
-                    float v = to_f32(px[ci]);
-                    if (in_a) v = apply_act(fmaf(v, a[ci], bb[ci]), act);
-                    acc[(kh * KS + kw) * CIN + ci] = fmaf(v, gv, acc[(kh * KS + kw) * CIN + ci]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < NT; ++i) atomicAdd(&sacc[i * 32 + lane], acc[i]);
-    __syncthreads();
-    for (int i = threadIdx.x; i < NT * 32; i += blockDim.x) atomicAdd(dw + i, sacc[i]);
-}
-
-// gin[b,ih,iw,ci] = act'(pre) * sum_{kh,kw,co} g[b,oh,ow,co] * w[kh,kw,ci,co],
-//   oh*S - pt + kh = ih;  pre = mask_a*mask_z + mask_b (mask_z nullable = no activation).
-template <typename TG, typename TO, int CIN, int COUT, int KS, int S>
-__global__ void __launch_bounds__(256) conv_direct_dgrad_kernel(const TG* __restrict__ g, const float* __restrict__ w,
-                                                                const TO* __restrict__ mask_z,
-                                                                const float* __restrict__ mask_a,
-                                                                const float* __restrict__ mask_b, int act,
-                                                                TO* __restrict__ gin, int B, int H, int W, int OH,
-                                                                int OW, int pt, int pl) {
-    __shared__ float ws[KS * KS * CIN * COUT];
-    for (int i = threadIdx.x; i < KS * KS * CIN * COUT; i += blockDim.x) ws[i] = w[i];
-    __syncthreads();
-    const long long n = (long long)B * H * W;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
-    const int pix = (int)idx;
-    const int iw = pix % W;
-    const int ih = (pix / W) % H;
-    const int b = pix / (W * H);
-    float acc[CIN];
-#pragma unroll
-    for (int ci = 0; ci < CIN; ++ci) acc[ci] = 0.f;
-#pragma unroll
-    for (int kh = 0; kh < KS; ++kh) {
-        const int t = ih + pt - kh;
-        if (t < 0 || t % S != 0) continue;
-        const int oh = t / S;
-        if (oh >= OH) continue;
-#pragma unroll
-        for (int kw = 0; kw < KS; ++kw) {
-            const int u = iw + pl - kw;
-            if (u < 0 || u % S != 0) continue;
-            const int ow = u / S;
-            if (ow >= OW) continue;
-            float gv[COUT];
-            load_row<TG, COUT>(g + (((size_t)b * OH + oh) * OW + ow) * COUT, gv);
-#pragma unroll
-            for (int co = 0; co < COUT; ++co) {
-#pragma unroll
-                for (int ci = 0; ci < CIN; ++ci)
-                    acc[ci] = fmaf(gv[co], ws[((kh * KS + kw) * CIN + ci) * COUT + co], acc[ci]);
-            }
-        }
-    }
-#pragma unroll
-    for (int ci = 0; ci < CIN; ++ci) {
-        float v = acc[ci];
-        if (mask_z) {
-            const float pre = fmaf(to_f32(mask_z[idx * CIN + ci]), mask_a[ci], mask_b[ci]);
-            if (!(pre > 0.f)) v = (act == 2) ? 0.1f * v : (act == 1 ? 0.f : v);
-        }
-        gin[idx * CIN + ci] = from_f32<TO>(v);
-    }
 }
 
 // ---- stem kernel folding: K4 = 2x2 box average of shifted K3; and its adjoint ----
@@ -495,96 +248,6 @@ int persist_grid(long long n) {
 }  // namespace
 
 extern "C" {
-
-// which: 0 = stem conv1 folded with AveragePooling2D(2): x0 fp32 [B,H,W,1] -> out [B,H/2,W/2,3], skip [B,H/2,W/2,1]
-//            (w = K4 [4,4,1,3] from spnet_stem_k3_to_k4)
-//        1 = stem conv 3->3, 3x3 same            [B,H,W,3] -> [B,H,W,3]
-//        2 = block1_conv1 3->32, 3x3 s2 valid    [B,H,W,3] -> [B,(H-3)/2+1,(W-3)/2+1,32]
-// in_a/in_b (nullable) + act (0 none, 1 relu, 2 leaky 0.1) transform the input on load.
-// stats (nullable): fp64 [2*Cout] batch-norm accumulators.
-int spnet_conv_small_fwd(int which, const void* in, const float* w, const float* in_a, const float* in_b, int act,
-                         void* out, void* skip, double* stats, int dtype, int B, int H, int W,
-                         cudaStream_t stream) {
-    SPNET_REQUIRE(in && w && out && B > 0 && H > 2 && W > 2, "conv_small_fwd: bad args");
-    SPNET_REQUIRE((in_a == nullptr) == (in_b == nullptr), "conv_small_fwd: affine parameters come in pairs");
-    if (which == 0) {
-        SPNET_REQUIRE(skip, "conv_small_fwd(0): skip output required");
-        const int OH = H / 2, OW = W / 2;
-        const long long n = (long long)B * OH * OW;
-        SPNET_DISPATCH_DTYPE(dtype, (conv_direct_fwd_kernel<float, T, 1, 3, 4, 2, true><<<ceil_div(n, 256), 256, 0, stream>>>(
-                                        reinterpret_cast<const float*>(in), w, in_a, in_b, act, reinterpret_cast<T*>(out),
-                                        reinterpret_cast<T*>(skip), stats, B, H, W, OH, OW, 1, 1)));
-    } else if (which == 1) {
-        const long long n = (long long)B * H * W;
-        SPNET_DISPATCH_DTYPE(dtype, (conv_direct_fwd_kernel<T, T, 3, 3, 3, 1, false><<<ceil_div(n, 256), 256, 0, stream>>>(
-                                        reinterpret_cast<const T*>(in), w, in_a, in_b, act, reinterpret_cast<T*>(out),
-                                        nullptr, stats, B, H, W, H, W, 1, 1)));
-    } else if (which == 2) {
-        const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
-        const long long n = (long long)B * OH * OW;
-        SPNET_DISPATCH_DTYPE(dtype, (conv_direct_fwd_kernel<T, T, 3, 32, 3, 2, false><<<ceil_div(n, 256), 256, 0, stream>>>(
-                                        reinterpret_cast<const T*>(in), w, in_a, in_b, act, reinterpret_cast<T*>(out),
-                                        nullptr, stats, B, H, W, OH, OW, 0, 0)));
-    } else {
-        spnet_set_error("conv_small_fwd: unknown conv id %d", which);
-        return SPNET_ERR_ARG;
-    }
-    return spnet_check_launch("conv_small_fwd");
-}
-
-// dw += weight gradient of the same three convolutions (dw zeroed by the caller).
-// For which == 0, dw is the K4 gradient [4,4,1,3]; fold it with spnet_stem_k4grad_to_k3grad.
-int spnet_conv_small_wgrad(int which, const void* in, const float* in_a, const float* in_b, int act, const void* g,
-                           float* dw, int dtype, int B, int H, int W, cudaStream_t stream) {
-    SPNET_REQUIRE(in && g && dw && B > 0 && H > 2 && W > 2, "conv_small_wgrad: bad args");
-    SPNET_REQUIRE((in_a == nullptr) == (in_b == nullptr), "conv_small_wgrad: affine parameters come in pairs");
-    if (which == 0) {
-        const int OH = H / 2, OW = W / 2;
-        const long long n = (long long)B * OH * OW;
-        SPNET_DISPATCH_DTYPE(dtype, (conv_direct_wgrad_px_kernel<float, T, 1, 3, 4, 2><<<persist_grid(n), 256, 0, stream>>>(
-                                        reinterpret_cast<const float*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g),
-                                        dw, B, H, W, OH, OW, 1, 1)));
-    } else if (which == 1) {
-        const long long n = (long long)B * H * W;
-        SPNET_DISPATCH_DTYPE(dtype, (conv_direct_wgrad_px_kernel<T, T, 3, 3, 3, 1><<<persist_grid(n), 256, 0, stream>>>(
-                                        reinterpret_cast<const T*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g), dw,
-                                        B, H, W, H, W, 1, 1)));
-    } else if (which == 2) {
-        const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
-        const long long n = (long long)B * OH * OW;
-        SPNET_DISPATCH_DTYPE(dtype, (conv_direct_wgrad_lane_kernel<T, T, 3, 3, 2><<<persist_grid(n * 32), 256, 0, stream>>>(
-                                        reinterpret_cast<const T*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g), dw,
-                                        B, H, W, OH, OW, 0, 0)));
-    } else {
-        spnet_set_error("conv_small_wgrad: unknown conv id %d", which);
-        return SPNET_ERR_ARG;
-    }
-    return spnet_check_launch("conv_small_wgrad");
-}
-
-// gin = data gradient (which = 1 or 2; conv 0 reads the network input, which has no gradient),
-// multiplied by act'(mask_a*mask_z+mask_b) when mask_z is given. H, W are the INPUT dims.
-int spnet_conv_small_dgrad(int which, const void* g, const float* w, const void* mask_z, const float* mask_a,
-                           const float* mask_b, int act, void* gin, int dtype, int B, int H, int W,
-                           cudaStream_t stream) {
-    SPNET_REQUIRE(g && w && gin && B > 0 && H > 2 && W > 2, "conv_small_dgrad: bad args");
-    SPNET_REQUIRE(!mask_z || (mask_a && mask_b), "conv_small_dgrad: mask needs its affine");
-    const long long n = (long long)B * H * W;
-    if (which == 1) {
-        SPNET_DISPATCH_DTYPE(dtype, (conv_direct_dgrad_kernel<T, T, 3, 3, 3, 1><<<ceil_div(n, 256), 256, 0, stream>>>(
-                                        reinterpret_cast<const T*>(g), w, reinterpret_cast<const T*>(mask_z), mask_a,
-                                        mask_b, act, reinterpret_cast<T*>(gin), B, H, W, H, W, 1, 1)));
-    } else if (which == 2) {
-        const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
-        SPNET_DISPATCH_DTYPE(dtype, (conv_direct_dgrad_kernel<T, T, 3, 32, 3, 2><<<ceil_div(n, 256), 256, 0, stream>>>(
-                                        reinterpret_cast<const T*>(g), w, reinterpret_cast<const T*>(mask_z), mask_a,
-                                        mask_b, act, reinterpret_cast<T*>(gin), B, H, W, OH, OW, 0, 0)));
-    } else {
-        spnet_set_error("conv_small_dgrad: unknown conv id %d", which);
-        return SPNET_ERR_ARG;
-    }
-    return spnet_check_launch("conv_small_dgrad");
-}
 
 int spnet_stem_k3_to_k4(const float* k3, float* k4, int cout, cudaStream_t stream) {
     SPNET_REQUIRE(k3 && k4 && cout > 0, "stem_k3_to_k4: bad args");
