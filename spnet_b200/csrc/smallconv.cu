@@ -97,20 +97,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_kernel(const TI* __restr
     constexpr int IH_T = (TH - 1) * S + KS, IW_T = (TW - 1) * S + KS, IWP = IW_T + 1;
     constexpr int NW = KS * KS * CIN * COUT;
     __shared__ float s_in[CIN * IH_T * IWP];
-    __shared__ float ws[NW];
+    __shared__ __align__(16) float ws[KS * KS * CIN * 4];  // [tap][ci][co padded to 4]
     __shared__ float sab[2 * CIN + 2 * COUT];
     __shared__ TO s_out[TH * TW * COUT];
     __shared__ TO s_skip[MODE == 1 ? TH * TW : 1];
     __shared__ float sred[2 * COUT];
     for (int i = threadIdx.x; i < NW; i += kThreads) {
-        if (MODE == 2) {
-            // data gradient: out channel = forward ci, in channel = forward co, taps flipped
-            const int t = i / (CIN * COUT), rem = i % (CIN * COUT);
-            const int cin_here = rem / COUT, cout_here = rem % COUT;  // (forward co, forward ci)
-            ws[i] = w[((KS * KS - 1 - t) * COUT + cout_here) * CIN + cin_here];
-        } else {
-            ws[i] = w[i];
-        }
+        const int t = i / (CIN * COUT), rem = i % (CIN * COUT);
+        const int cin_here = rem / COUT, cout_here = rem % COUT;
+        // data gradient: out channel = forward ci, in channel = forward co, taps flipped
+        ws[(t * CIN + cin_here) * 4 + cout_here] =
+            MODE == 2 ? w[((KS * KS - 1 - t) * COUT + cout_here) * CIN + cin_here] : w[i];
     }
     if (threadIdx.x < CIN) {
         sab[threadIdx.x] = in_a ? in_a[threadIdx.x] : 1.f;
@@ -139,36 +136,47 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_kernel(const TI* __restr
             const TileXY t = tile_xy(tile + gridDim.x, tiles_h, tiles_w, TH, TW);
             win.fetch(in + (size_t)t.b * H * W * CIN, H, W, t.r0 * S - pt, t.c0 * S - pl);
         }
-#pragma unroll 1
-        for (int pp = 0; pp < TH / 4; ++pp) {
+        // 4 pixels per thread (rows ty + 4*pp) share every weight triple: one LDS.128 per (tap, ci)
+        constexpr int PP = TH / 4;
+        float acc[PP][COUT], centre[PP];
+#pragma unroll
+        for (int pp = 0; pp < PP; ++pp) {
+            centre[pp] = 0.f;
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) acc[pp][co] = 0.f;
+        }
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+            for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < KS; ++kw) {
+                    const float4 wv = *reinterpret_cast<const float4*>(&ws[((kh * KS + kw) * CIN + ci) * 4]);
+#pragma unroll
+                    for (int pp = 0; pp < PP; ++pp) {
+                        const float v = s_in[(ci * IH_T + (ty + 4 * pp) * S + kh) * IWP + tx * S + kw];
+                        if (MODE == 1 && (kh == 1 || kh == 2) && (kw == 1 || kw == 2)) centre[pp] += v;
+                        acc[pp][0] = fmaf(v, wv.x, acc[pp][0]);
+                        acc[pp][1] = fmaf(v, wv.y, acc[pp][1]);
+                        acc[pp][2] = fmaf(v, wv.z, acc[pp][2]);
+                    }
+                }
+#pragma unroll
+        for (int pp = 0; pp < PP; ++pp) {
             const int r = ty + 4 * pp;
             const int oh = oh0 + r, ow = ow0 + tx;
-            float acc[COUT] = {0.f, 0.f, 0.f};
-            float centre = 0.f;
-#pragma unroll
-            for (int ci = 0; ci < CIN; ++ci)
-#pragma unroll
-                for (int kh = 0; kh < KS; ++kh)
-#pragma unroll
-                    for (int kw = 0; kw < KS; ++kw) {
-                        const float v = s_in[(ci * IH_T + r * S + kh) * IWP + tx * S + kw];
-                        if (MODE == 1 && (kh == 1 || kh == 2) && (kw == 1 || kw == 2)) centre += v;
-                        const float* wr = &ws[((kh * KS + kw) * CIN + ci) * COUT];
-#pragma unroll
-                        for (int co = 0; co < COUT; ++co) acc[co] = fmaf(v, wr[co], acc[co]);
-                    }
             const bool valid = oh < OH && ow < OW;
             if (MODE == 2 && mask_z && valid) {
                 const TO* mz = mask_z + (((size_t)b * OH + oh) * OW + ow) * COUT;
 #pragma unroll
                 for (int co = 0; co < COUT; ++co) {
                     const float pre = fmaf(to_f32(mz[co]), sab[2 * CIN + co], sab[2 * CIN + COUT + co]);
-                    if (!(pre > 0.f)) acc[co] = (act == 2) ? 0.1f * acc[co] : (act == 1 ? 0.f : acc[co]);
+                    if (!(pre > 0.f)) acc[pp][co] = (act == 2) ? 0.1f * acc[pp][co] : (act == 1 ? 0.f : acc[pp][co]);
                 }
             }
 #pragma unroll
             for (int co = 0; co < COUT; ++co) {
-                const TO o = from_f32<TO>(acc[co]);
+                const TO o = from_f32<TO>(acc[pp][co]);
                 s_out[(r * TW + tx) * COUT + co] = o;
                 if (valid) {
                     const float rr = to_f32(o);
@@ -176,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_kernel(const TI* __restr
                     ssq[co] = fmaf(rr, rr, ssq[co]);
                 }
             }
-            if (MODE == 1) s_skip[r * TW + tx] = from_f32<TO>(0.25f * centre);
+            if (MODE == 1) s_skip[r * TW + tx] = from_f32<TO>(0.25f * centre[pp]);
         }
         __syncthreads();
         // contiguous row segments of the output tile
