@@ -68,13 +68,15 @@ int spnet_bn_finalize(double* stats, long long count, const float* gamma, const 
 int spnet_bn_inference_affine(const float* gamma, const float* beta, const float* moving_mean, const float* moving_var, float eps, float* a, float* b, int C, cudaStream_t stream);
 int spnet_bn_apply(const void* z, const float* a, const float* b, int act, const void* x, void* out, int dtype, long long rows, int C, cudaStream_t stream);
 int spnet_bn_bwd_reduce(void* g, const void* z, const float* save_mean, const float* save_rstd, const float* relu_a, const float* relu_b, int act, double* stats, int dtype, long long rows, int C, cudaStream_t stream);
+int spnet_colstats(const void* z, double* stats, int dtype, long long rows, int C, cudaStream_t stream);
 int spnet_bn_bwd_finalize(double* stats, long long count, float* dgamma, float* dbeta, float* c1, float* c2, int C, cudaStream_t stream);
 int spnet_bn_bwd_dz(const void* g, const void* z, const float* a, const float* save_mean, const float* save_rstd, const float* c1, const float* c2, void* out, int dtype, long long rows, int C, cudaStream_t stream);
 
 /* ---- MaxPooling2D(3,2,'same') + BN-apply + residual Add (Xception blocks 2-4, 13) ---- */
 int spnet_maxpool3s2_add_fwd(const void* z, const float* a, const float* b, const void* res, const float* ra, const float* rb, void* out, unsigned char* argmax, int dtype, int B, int H, int W, int C, cudaStream_t stream);
 int spnet_maxpool3s2_bwd(const void* gout, const unsigned char* argmax, void* gin, int dtype, int B, int H, int W, int C, cudaStream_t stream);
-int spnet_gather_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, cudaStream_t stream);
+int spnet_gather_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, int off, cudaStream_t stream);
+int spnet_scatter_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, int off, cudaStream_t stream);
 
 /* ---- SPNet stem (spnet/models.py:319-340), block1_conv1, block1_conv2 im2col ---- */
 int spnet_conv_small_fwd(int which, const void* in, const float* w, const float* in_a, const float* in_b, int act, void* out, void* skip, double* stats, int dtype, int B, int H, int W, cudaStream_t stream);

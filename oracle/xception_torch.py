@@ -178,9 +178,12 @@ def maxpool3s2_same(x):
 class OracleSPNet:
     """Holds the weights as torch leaves; forward() follows the Keras graph layer by layer."""
 
+    def make_spec(self, H, W, n_out):
+        return xception_spnet_spec(H, W, n_out)
+
     def __init__(self, weights, H, W, n_out=576, dtype=torch.float32, unbiased_moving_var=True):
         self.H, self.W, self.n_out, self.dtype = H, W, n_out, dtype
-        self.spec = xception_spnet_spec(H, W, n_out)
+        self.spec = self.make_spec(H, W, n_out)
         self.p = OrderedDict()
         for layer, wname, shape, trainable, _ in self.spec:
             key = layer + "/" + wname
@@ -235,11 +238,18 @@ class OracleSPNet:
             x = x * m / 0.9
         if taps:
             tp["stem"] = x
+        x = self.backbone(x, training, taps)
+        flat = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)  # Keras Flatten of NHWC
+        return flat @ p["FinalOutput/kernel"] + p["FinalOutput/bias"]
+
+    def backbone(self, x, training, taps=False):
+        """keras.applications.Xception(include_top=False) on the stem output (NCHW)."""
+        p = self.p
         # block 1
         x = torch.relu(self.bn(conv2d_tf(x, p["block1_conv1/kernel"], 2, "valid"), "block1_conv1_bn", training))
         x = torch.relu(self.bn(conv2d_tf(x, p["block1_conv2/kernel"], 1, "valid"), "block1_conv2_bn", training))
         if taps:
-            tp["block1"] = x
+            self.taps["block1"] = x
         nres = 4
         for blk in (2, 3, 4):
             res = self.bn(conv2d_tf(x, p["conv2d_%d/kernel" % nres], 2, "same"), "batch_normalization_%d" % nres, training)
@@ -251,7 +261,7 @@ class OracleSPNet:
             x = self.bn(self.sep(x, "block%d_sepconv2" % blk), "block%d_sepconv2_bn" % blk, training)
             x = maxpool3s2_same(x) + res
             if taps:
-                tp["block%d" % blk] = x
+                self.taps["block%d" % blk] = x
         for blk in range(5, 13):
             r = x
             for j in (1, 2, 3):
@@ -259,7 +269,7 @@ class OracleSPNet:
                 x = self.bn(self.sep(x, "block%d_sepconv%d" % (blk, j)), "block%d_sepconv%d_bn" % (blk, j), training)
             x = x + r
             if taps:
-                tp["block%d" % blk] = x
+                self.taps["block%d" % blk] = x
         res = self.bn(conv2d_tf(x, p["conv2d_7/kernel"], 2, "same"), "batch_normalization_7", training)
         x = torch.relu(x)
         x = self.bn(self.sep(x, "block13_sepconv1"), "block13_sepconv1_bn", training)
@@ -267,13 +277,12 @@ class OracleSPNet:
         x = self.bn(self.sep(x, "block13_sepconv2"), "block13_sepconv2_bn", training)
         x = maxpool3s2_same(x) + res
         if taps:
-            tp["block13"] = x
+            self.taps["block13"] = x
         x = torch.relu(self.bn(self.sep(x, "block14_sepconv1"), "block14_sepconv1_bn", training))
         x = torch.relu(self.bn(self.sep(x, "block14_sepconv2"), "block14_sepconv2_bn", training))
         if taps:
-            tp["block14"] = x
-        flat = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)  # Keras Flatten of NHWC
-        return flat @ p["FinalOutput/kernel"] + p["FinalOutput/bias"]
+            self.taps["block14"] = x
+        return x
 
     # -- loss (custom_loss, spnet/models.py:564-589) + L2 (:47-71)
     @staticmethod
@@ -320,3 +329,67 @@ class OracleSPNet:
 
     def weights_numpy(self):
         return OrderedDict((k, v.detach().cpu().numpy().copy()) for k, v in self.p.items())
+
+
+# =================================================================================================
+# MobileNet backbone (BASELINE configs[2]): keras.applications.mobilenet.MobileNet @ Keras 2.1.3,
+# alpha = 1, depth_multiplier = 1, include_top=False (reference call site spnet/models.py:349-355).
+# Not in the reference tree either; restated from its published architecture:
+# conv1 3x3 s2 'same' -> BN -> relu6, then 13 x [DepthwiseConv2D 3x3 'same' stride s -> BN -> relu6
+# -> Conv 1x1 -> BN -> relu6]. Pinned structurally by the no-top parameter total 3,228,864.
+# =================================================================================================
+MOBILENET_BLOCKS = ((32, 64, 1), (64, 128, 2), (128, 128, 1), (128, 256, 2), (256, 256, 1), (256, 512, 2),
+                    (512, 512, 1), (512, 512, 1), (512, 512, 1), (512, 512, 1), (512, 512, 1), (512, 1024, 2),
+                    (1024, 1024, 1))
+
+
+def mobilenet_feature_hw(H, W):
+    def walk(n):
+        n = n // 2            # AveragePooling2D(2)
+        for _ in range(5):    # conv1 and four stride-2 depthwise stages, all 'same'
+            n = -(-n // 2)
+        return n
+    return walk(H), walk(W)
+
+
+def mobilenet_spnet_spec(H, W, n_out=576):
+    spec = []
+
+    def bn(name, c):
+        spec.append((name, "gamma", (c,), True, False))
+        spec.append((name, "beta", (c,), True, False))
+        spec.append((name, "moving_mean", (c,), False, False))
+        spec.append((name, "moving_variance", (c,), False, False))
+
+    for i, cin in ((1, 1), (2, 3), (3, 3)):
+        spec.append(("conv2d_%d" % i, "kernel", (3, 3, cin, 3), True, True))
+        bn("batch_normalization_%d" % i, 3)
+    spec.append(("conv1", "kernel", (3, 3, 3, 32), True, True))
+    bn("conv1_bn", 32)
+    for i, (cin, cout, _) in enumerate(MOBILENET_BLOCKS, start=1):
+        spec.append(("conv_dw_%d" % i, "depthwise_kernel", (3, 3, cin, 1), True, False))
+        bn("conv_dw_%d_bn" % i, cin)
+        spec.append(("conv_pw_%d" % i, "kernel", (1, 1, cin, cout), True, True))
+        bn("conv_pw_%d_bn" % i, cout)
+    fh, fw = mobilenet_feature_hw(H, W)
+    spec.append(("FinalOutput", "kernel", (fh * fw * 1024, n_out), True, True))
+    spec.append(("FinalOutput", "bias", (n_out,), True, False))
+    return spec
+
+
+class OracleMobileNetSPNet(OracleSPNet):
+    def make_spec(self, H, W, n_out):
+        return mobilenet_spnet_spec(H, W, n_out)
+
+    def backbone(self, x, training, taps=False):
+        p = self.p
+        relu6 = lambda v: torch.clamp(v, 0.0, 6.0)  # noqa: E731
+        x = relu6(self.bn(conv2d_tf(x, p["conv1/kernel"], 2, "same"), "conv1_bn", training))
+        for i, (cin, cout, stride) in enumerate(MOBILENET_BLOCKS, start=1):
+            x = conv2d_tf(x, p["conv_dw_%d/depthwise_kernel" % i], stride, "same", groups=cin)
+            x = relu6(self.bn(x, "conv_dw_%d_bn" % i, training))
+            x = conv2d_tf(x, p["conv_pw_%d/kernel" % i], 1, "valid")
+            x = relu6(self.bn(x, "conv_pw_%d_bn" % i, training))
+            if taps:
+                self.taps["block%d" % i] = x
+        return x

@@ -89,6 +89,57 @@ def param_spec(H, W, n_out=576):
     return spec
 
 
+# keras.applications.mobilenet.MobileNet (alpha=1, depth_multiplier=1) @ Keras 2.1.3: (cin, cout, stride)
+MOBILENET_BLOCKS = ((32, 64, 1), (64, 128, 2), (128, 128, 1), (128, 256, 2), (256, 256, 1), (256, 512, 2),
+                    (512, 512, 1), (512, 512, 1), (512, 512, 1), (512, 512, 1), (512, 512, 1), (512, 1024, 2),
+                    (1024, 1024, 1))
+
+
+def mobilenet_shape_walk(H, W):
+    s = OrderedDict()
+    s["input"] = (H, W)
+    s["stem"] = (H // 2, W // 2)
+    h, w = s["stem"]
+    if h % 32 or w % 32:
+        raise NotImplementedError("MobileNet backbone: the stem output (%d x %d) must be divisible by 32 "
+                                  "(stride-2 'same' stages are built for even sizes)" % (h, w))
+    h, w = h // 2, w // 2
+    s["conv1"] = (h, w)
+    for i, (_, _, stride) in enumerate(MOBILENET_BLOCKS, start=1):
+        s["in%d" % i] = (h, w)
+        h, w = h // stride, w // stride
+        s["out%d" % i] = (h, w)
+    return s
+
+
+def mobilenet_param_spec(H, W, n_out=576):
+    """MobileNet-SPNet: [(key, shape, trainable, l2_regularised)]. DepthwiseConv2D drops
+    kernel_regularizer from its config, so (as for SeparableConv2D) only the dense convolutions
+    and the head are L2-regularised after add_regularization's JSON round trip (spnet/models.py:47-71)."""
+    spec = []
+
+    def bn(name, c):
+        spec.append((name + "/gamma", (c,), True, False))
+        spec.append((name + "/beta", (c,), True, False))
+        spec.append((name + "/moving_mean", (c,), False, False))
+        spec.append((name + "/moving_variance", (c,), False, False))
+
+    for i, cin in ((1, 1), (2, 3), (3, 3)):
+        spec.append(("conv2d_%d/kernel" % i, (3, 3, cin, 3), True, True))
+        bn("batch_normalization_%d" % i, 3)
+    spec.append(("conv1/kernel", (3, 3, 3, 32), True, True))
+    bn("conv1_bn", 32)
+    for i, (cin, cout, _) in enumerate(MOBILENET_BLOCKS, start=1):
+        spec.append(("conv_dw_%d/depthwise_kernel" % i, (3, 3, cin, 1), True, False))
+        bn("conv_dw_%d_bn" % i, cin)
+        spec.append(("conv_pw_%d/kernel" % i, (1, 1, cin, cout), True, True))
+        bn("conv_pw_%d_bn" % i, cout)
+    fh, fw = mobilenet_shape_walk(H, W)["out13"]
+    spec.append(("FinalOutput/kernel", (fh * fw * 1024, n_out), True, True))
+    spec.append(("FinalOutput/bias", (n_out,), True, False))
+    return spec
+
+
 def count_params(spec):
     tr = sum(int(np.prod(s)) for _, s, t, _ in spec if t)
     nt = sum(int(np.prod(s)) for _, s, t, _ in spec if not t)

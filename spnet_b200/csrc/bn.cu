@@ -128,7 +128,7 @@ __device__ __forceinline__ RowRange cta_rows(long long rows) {
     return r;
 }
 
-// out = act(a*z + b) [+ x];  act: 0 none, 1 relu, 2 leaky-relu(0.1)
+// out = act(a*z + b) [+ x];  act: 0 none, 1 relu, 2 leaky-relu(0.1), 3 relu6
 template <typename T>
 __global__ void __launch_bounds__(256, 3) bn_apply_kernel(const T* z, const float* __restrict__ a,
                                                           const float* __restrict__ b, int act, const T* x, T* out,
@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(256, 3) bn_apply_kernel(const T* z, const floa
                     float2 y = ffma2(v[u].get(i), av[i], bv[i]);
                     if (act == 1) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); }
                     else if (act == 2) { y.x = y.x > 0.f ? y.x : 0.1f * y.x; y.y = y.y > 0.f ? y.y : 0.1f * y.y; }
+                    else if (act == 3) { y.x = fminf(fmaxf(y.x, 0.f), 6.f); y.y = fminf(fmaxf(y.y, 0.f), 6.f); }
                     if (x) y = fadd2(y, xr[u].get(i));
                     v[u].set(i, y);
                 }
@@ -230,8 +231,13 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(T* __restrict__ g
                     for (int i = 0; i < NP; ++i) {
                         const float2 y = ffma2(zv[u].get(i), ra[i], rb[i]);
                         float2 gg = gv[u].get(i);
-                        if (!(y.x > 0.f)) gg.x = (act == 2) ? 0.1f * gg.x : 0.f;
-                        if (!(y.y > 0.f)) gg.y = (act == 2) ? 0.1f * gg.y : 0.f;
+                        if (act == 3) {  // relu6: open only inside (0, 6)
+                            if (!(y.x > 0.f && y.x < 6.f)) gg.x = 0.f;
+                            if (!(y.y > 0.f && y.y < 6.f)) gg.y = 0.f;
+                        } else {
+                            if (!(y.x > 0.f)) gg.x = (act == 2) ? 0.1f * gg.x : 0.f;
+                            if (!(y.y > 0.f)) gg.y = (act == 2) ? 0.1f * gg.y : 0.f;
+                        }
                         gv[u].set(i, gg);  // re-rounded to T: the sums below use the value as it will be re-read
                     }
                     st_raw(g + r * C + c0, gv[u]);
@@ -241,6 +247,66 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(T* __restrict__ g
                     const float2 gg = gv[u].get(i);
                     s1[i] = fadd2(s1[i], gg);
                     s2[i] = ffma2(gg, ffma2(zv[u].get(i), rs[i], nm[i]), s2[i]);
+                }
+            }
+        }
+    }
+    __shared__ float red[2][256 * 8];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        red[0][threadIdx.x * V + 2 * i] = s1[i].x; red[0][threadIdx.x * V + 2 * i + 1] = s1[i].y;
+        red[1][threadIdx.x * V + 2 * i] = s2[i].x; red[1][threadIdx.x * V + 2 * i + 1] = s2[i].y;
+    }
+    __syncthreads();
+    if (rl == 0 && active) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            float t1 = 0.f, t2 = 0.f;
+            for (int j = 0; j < krows; ++j) {
+                t1 += red[0][(j * cvb + cvl) * V + i];
+                t2 += red[1][(j * cvb + cvl) * V + i];
+            }
+            atomicAdd(stats + c0 + i, (double)t1);
+            atomicAdd(stats + C + c0 + i, (double)t2);
+        }
+    }
+}
+
+// stats[c] += sum z, stats[C+c] += sum z^2 over the rows (batch statistics of a tensor whose producer
+// has no statistics epilogue)
+template <typename T>
+__global__ void __launch_bounds__(256, 3) colstats_kernel(const T* __restrict__ z, double* __restrict__ stats,
+                                                          long long rows, int C, int cvb, int krows) {
+    constexpr int V = VecN<T>::N, NP = RawVec<T>::NP;
+    pdl_trigger();
+    pdl_wait();
+    const int CV = C / V;
+    const int cvl = threadIdx.x % cvb, rl = threadIdx.x / cvb;
+    const int cv = blockIdx.y * cvb + cvl;
+    const bool active = cv < CV;
+    const int c0 = cv * V;
+    float2 s1[NP], s2[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) s1[i] = s2[i] = make_float2(0.f, 0.f);
+    if (active) {
+        const RowRange rr = cta_rows(rows);
+        const long long stride = krows;
+        for (long long r0 = rr.begin + rl; r0 < rr.end; r0 += stride * UNROLL) {
+            RawVec<T> zv[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const long long r = r0 + u * stride;
+                if (r < rr.end) zv[u] = ld_raw(z + r * C + c0);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const long long r = r0 + u * stride;
+                if (r >= rr.end) continue;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    const float2 v = zv[u].get(i);
+                    s1[i] = fadd2(s1[i], v);
+                    s2[i] = ffma2(v, v, s2[i]);
                 }
             }
         }
@@ -392,7 +458,7 @@ int spnet_bn_apply(const void* z, const float* a, const float* b, int act, const
                    long long rows, int C, cudaStream_t stream) {
     int rc = check_rc("bn_apply", dtype, rows, C);
     if (rc) return rc;
-    SPNET_REQUIRE(z && a && b && out && act >= 0 && act <= 2, "bn_apply: bad args");
+    SPNET_REQUIRE(z && a && b && out && act >= 0 && act <= 3, "bn_apply: bad args");
     const ChanGrid cg = chan_grid(C / (dtype == SPNET_BF16 ? 8 : 4), rows, 3);
     SPNET_DISPATCH_DTYPE(dtype, (spnet_launch_pdl(bn_apply_kernel<T>, cg.grid, dim3(cg.cvb * cg.krows), 0, stream, 1,
                                                   reinterpret_cast<const T*>(z), a, b, act, reinterpret_cast<const T*>(x),
@@ -420,6 +486,17 @@ int spnet_bn_bwd_reduce(void* g, const void* z, const float* save_mean, const fl
                                                       cg.krows)));
     }
     return spnet_check_launch("bn_bwd_reduce");
+}
+
+// stats[2*C] += (sum, sum of squares) per channel of z [rows, C]
+int spnet_colstats(const void* z, double* stats, int dtype, long long rows, int C, cudaStream_t stream) {
+    int rc = check_rc("colstats", dtype, rows, C);
+    if (rc) return rc;
+    SPNET_REQUIRE(z && stats, "colstats: null pointer");
+    const ChanGrid cg = chan_grid(C / (dtype == SPNET_BF16 ? 8 : 4), rows, 3);
+    SPNET_DISPATCH_DTYPE(dtype, (spnet_launch_pdl(colstats_kernel<T>, cg.grid, dim3(cg.cvb * cg.krows), 0, stream, 1,
+                                                  reinterpret_cast<const T*>(z), stats, rows, C, cg.cvb, cg.krows)));
+    return spnet_check_launch("colstats");
 }
 
 int spnet_bn_bwd_finalize(double* stats, long long count, float* dgamma, float* dbeta, float* c1, float* c2,

@@ -53,6 +53,17 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
     return upk(d);
 }
 __device__ __forceinline__ float2 relu2(float2 v) { return make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)); }
+// activation applied on load: RELU = 0 none, 1 ReLU (Xception), 2 ReLU6 (MobileNet). NaN (the padding fill) maps to 0.
+template <int RELU> __device__ __forceinline__ float2 act2(float2 v) {
+    if (RELU == 1) return relu2(v);
+    if (RELU == 2) return make_float2(fminf(fmaxf(v.x, 0.f), 6.f), fminf(fmaxf(v.y, 0.f), 6.f));
+    return v;
+}
+template <int RELU> __device__ __forceinline__ bool act_open(float pre) {  // derivative of the activation is 1
+    if (RELU == 1) return pre > 0.f;
+    if (RELU == 2) return pre > 0.f && pre < 6.f;
+    return true;
+}
 
 // ---- one channel pair of one pixel: raw (as stored) and widened (fp32) forms --------------------
 template <typename T> struct PairOf;
@@ -104,13 +115,13 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_w, int tiles
 // CTA = TW/NC warps; blockIdx.y = 64-channel chunk, blockIdx.x walks
 // (image, row-tile, col-tile) tiles round-robin.
 // =================================================================================================
-template <typename T, int NC, bool AFFINE, bool RELU>
+template <typename T, int NC, bool AFFINE, int RELU>
 __global__ void __launch_bounds__(256, 2)
 dw3x3_fwd_packed_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ k,
                         const float* __restrict__ in_a, const float* __restrict__ in_b, T* __restrict__ out, int B,
                         int H, int W, int C, int TH, int TW, int tiles_h, int tiles_w, int S) {
     constexpr uint32_t PB = PairOf<T>::bytes, PIX = 32 * PB;  // bytes of one pixel's 64-channel slice
-    constexpr bool MASK = AFFINE && !RELU;                    // explicit padding mask (no NaN trick without ReLU)
+    constexpr bool MASK = AFFINE && RELU == 0;                // explicit padding mask (no NaN trick without ReLU)
     typedef typename PairOf<T>::raw raw_t;
     extern __shared__ uint8_t dwp_smem[];
     __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES];
@@ -196,7 +207,7 @@ dw3x3_fwd_packed_kernel(const __grid_constant__ CUtensorMap tm_in, const float* 
                 for (int j = 0; j < NC + 2; ++j) {
                     float2 v = widen(cur[j]);
                     if (AFFINE) v = ffma2(v, av, bv);
-                    if (RELU) v = relu2(v);
+                    v = act2<RELU>(v);
                     if (MASK && !(rowok && colok[j])) v = make_float2(0.f, 0.f);
                     x[j] = v;
                 }
@@ -244,7 +255,7 @@ dw3x3_fwd_packed_kernel(const __grid_constant__ CUtensorMap tm_in, const float* 
 // Stage = gout tile with halo (zero-filled) + in tile (+ add_src tile), one mbarrier.
 // EPI: 0 none, 1 add_src (TMA-staged), 2 add_strided (global loads at even rows/columns).
 // =================================================================================================
-template <typename T, bool AFFINE, bool RELU, int EPI>
+template <typename T, bool AFFINE, int RELU, int EPI>
 __global__ void __launch_bounds__(512, 1)
 dw3x3_bwd_packed_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x,
                         const __grid_constant__ CUtensorMap tm_add, const float* __restrict__ k,
@@ -365,7 +376,7 @@ dw3x3_bwd_packed_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_c
                         if (oc == 1 && !own1) continue;  // warp-uniform
                         const float2 u = widen(xr[oc]);
                         const float2 pre = AFFINE ? ffma2(u, av, bv) : u;
-                        const float2 act = RELU ? relu2(pre) : pre;
+                        const float2 act = act2<RELU>(pre);
                         float2 d = fmul2(Ga[oc], kf[0]);
                         d = ffma2(Ga[oc + 1], kf[1], d);
                         d = ffma2(Ga[oc + 2], kf[2], d);
@@ -381,8 +392,8 @@ dw3x3_bwd_packed_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_c
                             dkf[6 + b] = ffma2(act, Gc[oc + b], dkf[6 + b]);
                         }
                         if (RELU) {
-                            if (!(pre.x > 0.f)) d.x = 0.f;
-                            if (!(pre.y > 0.f)) d.y = 0.f;
+                            if (!act_open<RELU>(pre.x)) d.x = 0.f;
+                            if (!act_open<RELU>(pre.y)) d.y = 0.f;
                         }
                         if (stats) {
                             const float2 rr = round_pair(d, (const T*)nullptr);
@@ -517,7 +528,7 @@ Tiling pick_tiling(int kind, int dtype, int B, int H, int W, int C) {
     return t;
 }
 
-template <typename T, int NC, bool AF, bool RL>
+template <typename T, int NC, bool AF, int RL>
 int launch_fwd_inst(const CUtensorMap& tm, const float* k, const float* a, const float* b, T* y, int B, int H, int W,
                     int C, const Tiling& t, cudaStream_t stream) {
     auto kern = dw3x3_fwd_packed_kernel<T, NC, AF, RL>;
@@ -545,13 +556,15 @@ int launch_fwd(const void* in, const float* k, const float* a, const float* b, i
     int rc = make_map(&tm, in, dtype, B, H, W, C, t.TW + 2, t.TH + 2, a && relu);
     if (rc) return rc;
     T* y = reinterpret_cast<T*>(out);
-    if (a && relu) return launch_fwd_inst<T, 4, true, true>(tm, k, a, b, y, B, H, W, C, t, stream);
-    if (a) return launch_fwd_inst<T, 4, true, false>(tm, k, a, b, y, B, H, W, C, t, stream);
-    if (relu) return launch_fwd_inst<T, 4, false, true>(tm, k, a, b, y, B, H, W, C, t, stream);
-    return launch_fwd_inst<T, 4, false, false>(tm, k, a, b, y, B, H, W, C, t, stream);
+    if (a && relu == 2) return launch_fwd_inst<T, 4, true, 2>(tm, k, a, b, y, B, H, W, C, t, stream);
+    if (a && relu) return launch_fwd_inst<T, 4, true, 1>(tm, k, a, b, y, B, H, W, C, t, stream);
+    if (a) return launch_fwd_inst<T, 4, true, 0>(tm, k, a, b, y, B, H, W, C, t, stream);
+    if (relu == 2) return launch_fwd_inst<T, 4, false, 2>(tm, k, a, b, y, B, H, W, C, t, stream);
+    if (relu) return launch_fwd_inst<T, 4, false, 1>(tm, k, a, b, y, B, H, W, C, t, stream);
+    return launch_fwd_inst<T, 4, false, 0>(tm, k, a, b, y, B, H, W, C, t, stream);
 }
 
-template <typename T, bool AF, bool RL, int EPI>
+template <typename T, bool AF, int RL, int EPI>
 int launch_bwd_inst(const CUtensorMap& tg, const CUtensorMap& tx, const CUtensorMap& ta, const float* k, const float* a,
                     const float* b, const float* mean, const float* rstd, double* stats, const T* sadd, T* gin,
                     float* dk, int B, int H, int W, int C, const Tiling& t, cudaStream_t stream) {
@@ -596,10 +609,12 @@ int launch_bwd(const void* gout, const void* in, const float* k, const float* a,
         if (epi == 2) return launch_bwd_inst<T, AF, RL, 2>(tg, tx, ta, k, a, b, mean, rstd, stats, sadd, y, dk, B, H, W, C, t, stream); \
         return launch_bwd_inst<T, AF, RL, 0>(tg, tx, ta, k, a, b, mean, rstd, stats, sadd, y, dk, B, H, W, C, t, stream);   \
     } while (0)
-    if (a && relu) DWB(true, true);
-    if (a) DWB(true, false);
-    if (relu) DWB(false, true);
-    DWB(false, false);
+    if (a && relu == 2) DWB(true, 2);
+    if (a && relu) DWB(true, 1);
+    if (a) DWB(true, 0);
+    if (relu == 2) DWB(false, 2);
+    if (relu) DWB(false, 1);
+    DWB(false, 0);
 #undef DWB
 }
 
@@ -615,13 +630,13 @@ int check_args(const char* who, const void* in, const void* out, int dtype, int 
 
 extern "C" {
 
-// out = dw3x3(act(in)),  act(v) = relu?(in_a*v + in_b)   (in_a/in_b nullable, fp32 [C])
+// out = dw3x3(act(in)),  act(v) = relu?(in_a*v + in_b)   (in_a/in_b nullable, fp32 [C]; relu: 0 none, 1 ReLU, 2 ReLU6)
 // k: [3,3,C] fp32 (keras depthwise_kernel (3,3,C,1) flattened)
 int spnet_dwconv3x3_fwd(const void* in, const float* k, const float* in_a, const float* in_b, int relu, void* out,
                         int dtype, int B, int H, int W, int C, cudaStream_t stream) {
     int rc = check_args("dwconv3x3_fwd", in, out, dtype, B, H, W, C);
     if (rc) return rc;
-    SPNET_REQUIRE(k && ((in_a == nullptr) == (in_b == nullptr)), "dwconv3x3_fwd: bad weight/affine pointers");
+    SPNET_REQUIRE(k && ((in_a == nullptr) == (in_b == nullptr)) && relu >= 0 && relu <= 2, "dwconv3x3_fwd: bad weight/affine pointers or relu code");
     SPNET_DISPATCH_DTYPE(dtype, return launch_fwd<T>(in, k, in_a, in_b, relu, out, dtype, B, H, W, C, stream));
 }
 
@@ -636,7 +651,7 @@ int spnet_dwconv3x3_bwd_fused(const void* gout, const void* in, const float* k, 
                               cudaStream_t stream) {
     int rc = check_args("dwconv3x3_bwd_fused", gout, gin, dtype, B, H, W, C);
     if (rc) return rc;
-    SPNET_REQUIRE(in && k && dk && ((in_a == nullptr) == (in_b == nullptr)), "dwconv3x3_bwd_fused: bad pointers");
+    SPNET_REQUIRE(in && k && dk && ((in_a == nullptr) == (in_b == nullptr)) && relu >= 0 && relu <= 2, "dwconv3x3_bwd_fused: bad pointers or relu code");
     SPNET_REQUIRE(!stats || (bn_mean && bn_rstd), "dwconv3x3_bwd_fused: stats need bn_mean / bn_rstd");
     SPNET_REQUIRE(!(add_src && add_strided), "dwconv3x3_bwd_fused: add_src and add_strided are exclusive");
     SPNET_DISPATCH_DTYPE(dtype, return launch_bwd<T>(gout, in, k, in_a, in_b, relu, bn_mean, bn_rstd, stats, add_src,

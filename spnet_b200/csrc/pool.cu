@@ -132,10 +132,11 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ 
     store_vec(gin + idx * V, acc);
 }
 
-// out[b,oh,ow,:] = in[b,2oh,2ow,:]   (what a 1x1 stride-2 'same' convolution reads)
+// out[b,oh,ow,:] = in[b,2oh+off,2ow+off,:]   (off 0: what a 1x1 stride-2 'same' convolution reads;
+// off 1: a 3x3 stride-2 'same' convolution on an even-sized input = its stride-1 result at odd positions)
 template <typename T>
 __global__ void __launch_bounds__(256) gather_s2_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H,
-                                                        int W, int C, int OH, int OW) {
+                                                        int W, int C, int OH, int OW, int off) {
     constexpr int V = VecN<T>::N;
     const int CV = C / V;
     const long long n = (long long)B * OH * OW * CV;
@@ -149,7 +150,32 @@ __global__ void __launch_bounds__(256) gather_s2_kernel(const T* __restrict__ in
     const int oh = (int)(r % OH);
     const int bi = (int)(r / OH);
     float v[V];
-    load_vec(in + (((size_t)bi * H + 2 * oh) * W + 2 * ow) * C + cv * V, v);
+    load_vec(in + (((size_t)bi * H + 2 * oh + off) * W + 2 * ow + off) * C + cv * V, v);
+    store_vec(out + idx * V, v);
+}
+
+// adjoint of gather_s2: out[b,h,w,:] = in[b,(h-off)/2,(w-off)/2,:] where both are integral, else 0
+template <typename T>
+__global__ void __launch_bounds__(256) scatter_s2_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H,
+                                                         int W, int C, int OH, int OW, int off) {
+    constexpr int V = VecN<T>::N;
+    const int CV = C / V;
+    const long long n = (long long)B * H * W * CV;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const unsigned uidx = (unsigned)idx;
+    const int cv = (int)(uidx % CV);
+    unsigned r = uidx / CV;
+    const int w = (int)(r % W);
+    r /= W;
+    const int h = (int)(r % H);
+    const int bi = (int)(r / H);
+    float v[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = 0.f;
+    const int th = h - off, tw = w - off;
+    if (th >= 0 && tw >= 0 && !(th & 1) && !(tw & 1) && (th >> 1) < OH && (tw >> 1) < OW)
+        load_vec(in + (((size_t)bi * OH + (th >> 1)) * OW + (tw >> 1)) * C + cv * V, v);
     store_vec(out + idx * V, v);
 }
 
@@ -197,16 +223,30 @@ int spnet_maxpool3s2_bwd(const void* gout, const unsigned char* argmax, void* gi
     return spnet_check_launch("maxpool3s2_bwd");
 }
 
-int spnet_gather_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, cudaStream_t stream) {
+// off = 0: rows/cols 0,2,4,... -> out [B,ceil(H/2),ceil(W/2),C];  off = 1: rows/cols 1,3,5,... -> [B,H/2,W/2,C]
+int spnet_gather_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, int off, cudaStream_t stream) {
     int rc = check_pool("gather_s2", dtype, B, H, W, C);
     if (rc) return rc;
-    SPNET_REQUIRE(in && out, "gather_s2: null pointer");
-    const int OH = (H + 1) / 2, OW = (W + 1) / 2;
+    SPNET_REQUIRE(in && out && (off == 0 || off == 1), "gather_s2: bad args");
+    const int OH = (H + 1 - off) / 2, OW = (W + 1 - off) / 2;
     const int V = dtype == SPNET_BF16 ? 8 : 4;
     const long long n = (long long)B * OH * OW * (C / V);
     SPNET_DISPATCH_DTYPE(dtype, (gather_s2_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(
-                                    reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), B, H, W, C, OH, OW)));
+                                    reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), B, H, W, C, OH, OW, off)));
     return spnet_check_launch("gather_s2");
+}
+
+// adjoint of spnet_gather_s2: in [B,OH,OW,C] (OH, OW as above) -> out [B,H,W,C], zero elsewhere
+int spnet_scatter_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, int off, cudaStream_t stream) {
+    int rc = check_pool("scatter_s2", dtype, B, H, W, C);
+    if (rc) return rc;
+    SPNET_REQUIRE(in && out && (off == 0 || off == 1), "scatter_s2: bad args");
+    const int OH = (H + 1 - off) / 2, OW = (W + 1 - off) / 2;
+    const int V = dtype == SPNET_BF16 ? 8 : 4;
+    const long long n = (long long)B * H * W * (C / V);
+    SPNET_DISPATCH_DTYPE(dtype, (scatter_s2_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(
+                                    reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), B, H, W, C, OH, OW, off)));
+    return spnet_check_launch("scatter_s2");
 }
 
 }  // extern "C"

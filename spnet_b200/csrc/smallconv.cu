@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_kernel(const TI* __restr
 #pragma unroll
             for (int co = 0; co < COUT; ++co) acc[pp][co] = 0.f;
         }
-#pragma unroll
+#pragma unroll 1
         for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
             for (int kh = 0; kh < KS; ++kh)
@@ -611,6 +611,7 @@ extern "C" {
 //            (w = K4 [4,4,1,3] from spnet_stem_k3_to_k4)
 //        1 = stem conv 3->3, 3x3 same            [B,H,W,3] -> [B,H,W,3]
 //        2 = block1_conv1 3->32, 3x3 s2 valid    [B,H,W,3] -> [B,(H-3)/2+1,(W-3)/2+1,32]
+//        3 = MobileNet conv1 3->32, 3x3 s2 'same' (TF pads only at the end for even H, W) -> [B,H/2,W/2,32]
 // in_a/in_b (nullable) + act (0 none, 1 relu, 2 leaky 0.1) transform the input on load.
 // stats (nullable): fp64 [2*Cout] batch-norm accumulators.
 int spnet_conv_small_fwd(int which, const void* in, const float* w, const float* in_a, const float* in_b, int act,
@@ -632,8 +633,9 @@ int spnet_conv_small_fwd(int which, const void* in, const float* w, const float*
         SPNET_DISPATCH_DTYPE(dtype, (conv3out_kernel<T, T, 3, 3, 1, 0><<<grid, kThreads, 0, stream>>>(
                                         reinterpret_cast<const T*>(in), w, in_a, in_b, act, reinterpret_cast<T*>(out),
                                         nullptr, stats, nullptr, nullptr, nullptr, B, H, W, H, W, 1, 1, th, tw)));
-    } else if (which == 2) {
-        const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
+    } else if (which == 2 || which == 3) {
+        SPNET_REQUIRE(which == 2 || (H % 2 == 0 && W % 2 == 0), "conv_small_fwd(3): 'same' stride 2 is built for even H, W");
+        const int OH = which == 2 ? (H - 3) / 2 + 1 : H / 2, OW = which == 2 ? (W - 3) / 2 + 1 : W / 2;
         const int th = ceil_div(OH, 4), tw = ceil_div(OW, 64);
         const int grid = persist_grid_tiles((long long)B * th * tw, 2);
         SPNET_DISPATCH_DTYPE(dtype, (conv_b1c1_fwd_kernel<T><<<grid, kThreads, 0, stream>>>(
@@ -665,8 +667,9 @@ int spnet_conv_small_wgrad(int which, const void* in, const float* in_a, const f
         SPNET_DISPATCH_DTYPE(dtype, (conv3out_wgrad_kernel<T, T, 3, 3, 1><<<grid, kThreads, 0, stream>>>(
                                         reinterpret_cast<const T*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g), dw,
                                         B, H, W, H, W, 1, 1, th, tw)));
-    } else if (which == 2) {
-        const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
+    } else if (which == 2 || which == 3) {
+        SPNET_REQUIRE(which == 2 || (H % 2 == 0 && W % 2 == 0), "conv_small_wgrad(3): 'same' stride 2 is built for even H, W");
+        const int OH = which == 2 ? (H - 3) / 2 + 1 : H / 2, OW = which == 2 ? (W - 3) / 2 + 1 : W / 2;
         const int th = ceil_div(OH, 4), tw = ceil_div(OW, 32);
         const int grid = persist_grid_tiles((long long)B * th * tw, 1);  // 134 registers x 256 threads: one CTA per SM
         SPNET_DISPATCH_DTYPE(dtype, (conv_b1c1_wgrad_kernel<T><<<grid, kThreads, 0, stream>>>(
@@ -694,9 +697,10 @@ int spnet_conv_small_dgrad(int which, const void* g, const float* w, const void*
                                         reinterpret_cast<const T*>(g), w, nullptr, nullptr, act, reinterpret_cast<T*>(gin),
                                         nullptr, nullptr, reinterpret_cast<const T*>(mask_z), mask_a, mask_b, B, H, W, H, W,
                                         1, 1, th, tw)));
-    } else if (which == 2) {
-        SPNET_REQUIRE(!mask_z, "conv_small_dgrad(2): block1_conv1 reads the stem output directly (no activation mask)");
-        const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
+    } else if (which == 2 || which == 3) {
+        SPNET_REQUIRE(!mask_z, "conv_small_dgrad(2|3): these convolutions read the stem output directly (no activation mask)");
+        SPNET_REQUIRE(which == 2 || (H % 2 == 0 && W % 2 == 0), "conv_small_dgrad(3): 'same' stride 2 is built for even H, W");
+        const int OH = which == 2 ? (H - 3) / 2 + 1 : H / 2, OW = which == 2 ? (W - 3) / 2 + 1 : W / 2;
         const int th = ceil_div(H, 8), tw = ceil_div(W, 64);
         const int grid = persist_grid_tiles((long long)B * th * tw, 2);
         SPNET_DISPATCH_DTYPE(dtype, (conv_b1c1_dgrad_kernel<T><<<grid, kThreads, 0, stream>>>(

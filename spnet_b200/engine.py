@@ -32,7 +32,12 @@ class _Sep:
     __slots__ = ("name", "cin", "cout", "dwk", "gdwk", "pw", "pwl", "gpw", "bn", "t", "z", "H", "W")
 
 
-class XceptionSPNetEngine:
+class SPNetEngineBase:
+    """Stem, Dense head, loss, optimiser and step plumbing shared by the backbones. A backbone
+    subclass provides: _arch() -> (shapes, param spec), _build_backbone(), _alloc_backbone()
+    (must set self.feat_dims = (fh, fw, C)), _backbone_fwd(training) (stem output self.d ->
+    self.feat) and _backbone_bwd(ga) (self.gfeat -> gradient w.r.t. self.d in ga)."""
+
     def __init__(self, H, W, batch, n_out=576, dtype="bf16", device="cuda:0", weights=None, seed=1,
                  loss_type="same", dropout_rate=arch.DROPOUT_RATE, use_l2=True, unbiased_moving_var=True,
                  training=True):
@@ -49,8 +54,7 @@ class XceptionSPNetEngine:
         self.use_l2 = use_l2
         self.unbiased = unbiased_moving_var
         self.can_train = training
-        self.shapes = arch.shape_walk(H, W)
-        self.spec = arch.param_spec(H, W, n_out)
+        self.shapes, self.spec = self._arch()
         self._alloc_params(weights if weights is not None else arch.glorot_init(self.spec, seed))
         self._build_layers()
         self._alloc_activations()
@@ -152,29 +156,9 @@ class XceptionSPNetEngine:
         return s
 
     def _build_layers(self):
-        sh = self.shapes
         self.bns = []
         self.stem_bn = [self._mk_bn("batch_normalization_%d" % i, 3) for i in (1, 2, 3)]
-        self.b1_bn1 = self._mk_bn("block1_conv1_bn", 32)
-        self.b1_bn2 = self._mk_bn("block1_conv2_bn", 64)
-        self.entry = []
-        for n, (blk, cin, c) in enumerate(arch.ENTRY_BLOCKS):
-            hw = sh["in%d" % blk]
-            e = dict(blk=blk, cin=cin, c=c, hw=hw, ohw=sh["out%d" % blk], res="conv2d_%d" % (4 + n),
-                     res_bn=self._mk_bn("batch_normalization_%d" % (4 + n), c),
-                     sep1=self._mk_sep("block%d_sepconv1" % blk, cin, c, hw),
-                     sep2=self._mk_sep("block%d_sepconv2" % blk, c, c, hw), relu_in=(blk != 2))
-            self.entry.append(e)
-        self.middle = []
-        for blk in arch.MIDDLE_BLOCKS:
-            self.middle.append([self._mk_sep("block%d_sepconv%d" % (blk, j), 728, 728, sh["middle"]) for j in (1, 2, 3)])
-        hw = sh["in13"]
-        self.exit13 = dict(blk=13, cin=728, c=1024, hw=hw, ohw=sh["out13"], res="conv2d_7",
-                           res_bn=self._mk_bn("batch_normalization_7", 1024),
-                           sep1=self._mk_sep("block13_sepconv1", 728, 728, hw),
-                           sep2=self._mk_sep("block13_sepconv2", 728, 1024, hw), relu_in=True)
-        self.sep14 = [self._mk_sep("block14_sepconv1", 1024, 1536, sh["out13"]),
-                      self._mk_sep("block14_sepconv2", 1536, 2048, sh["out13"])]
+        self._build_backbone()
         self.k4 = self._f32(48).view(4, 4, 1, 3)
         self.gk4 = self._f32(48).view(4, 4, 1, 3)
         self.l2_out = self._f32(1)
@@ -190,43 +174,15 @@ class XceptionSPNetEngine:
         h, w = sh["stem"]
         self.p1, self.c2, self.c3, self.d = (A(B, h, w, 3) for _ in range(4))
         self.s0 = A(B, h, w, 1)
-        h1, w1 = sh["b1c1"]
-        self.z11 = A(B, h1, w1, 32)
-        h2, w2 = sh["b1c2"]
-        self.col = A(B * h2 * w2, 288)
-        self.z12 = A(B, h2, w2, 64)
-        self.x2 = A(B, h2, w2, 64)
-        train = self.can_train
-        maxel = B * h2 * w2 * 128
-        for e in self.entry + [self.exit13]:
-            (eh, ew), (oh, ow) = e["hw"], e["ohw"]
-            e["xs"] = A(B, oh, ow, e["cin"])
-            e["zr"] = A(B, oh, ow, e["c"])
-            for s in (e["sep1"], e["sep2"]):
-                s.t = A(B, eh, ew, s.cin)
-                s.z = A(B, eh, ew, s.cout)
-                maxel = max(maxel, B * eh * ew * max(s.cin, s.cout))
-            e["out"] = A(B, oh, ow, e["c"])
-            e["argmax"] = A(B, oh, ow, e["c"], dtype=torch.uint8) if train else None
-        mh, mw = sh["middle"]
-        for blk in self.middle:
-            for s in blk:
-                s.t = A(B, mh, mw, 728)
-                s.z = A(B, mh, mw, 728)
-        self.mid_out = [A(B, mh, mw, 728) for _ in self.middle]
-        fh, fw = sh["out13"]
-        for s in self.sep14:
-            s.t = A(B, fh, fw, s.cin)
-            s.z = A(B, fh, fw, s.cout)
-        self.feat = A(B, fh * fw * 2048)
+        self._alloc_backbone()
+        fh, fw, fc = self.feat_dims
+        self.feat = A(B, fh * fw * fc)
         self.y_pred = torch.zeros(B, self.n_out, device=self.device, dtype=torch.float32)
         self.loss6 = self._f32(6)
-        if train:
+        if self.can_train:
             self.gy = torch.zeros(B, self.n_out, device=self.device, dtype=torch.float32)
             self.gyl = A(B, self.n_out) if self.lowp else self.gy
-            self.gfeat = A(B, fh * fw * 2048)
-            self.gcol = A(B * h2 * w2, 288)
-            self.scratch = [A(maxel) for _ in range(6)]
+            self.gfeat = A(B, fh * fw * fc)
             sp = B * sh["stem"][0] * sh["stem"][1] * 3
             self.gstem = [A(sp) for _ in range(2)]
         self.dense_splits = max(1, min(64, (2 * 148) // max(1, -(-self.n_out // 128))))
@@ -295,31 +251,7 @@ class XceptionSPNetEngine:
         drop = training and self.dropout_rate > 0
         ops.stem_out_fwd(self.c3, bn3.a, bn3.b, self.s0, self.d, rate=self.dropout_rate if drop else 0.0,
                          seed=self.seed_dev if drop else None)
-        # ---- block 1
-        h1, w1 = sh["b1c1"]
-        ops.conv_small_fwd(2, self.d, w["block1_conv1/kernel"], self.z11, stats=st(self.b1_bn1))
-        self._bn_ready(self.b1_bn1, B * h1 * w1, training)
-        h2, w2 = sh["b1c2"]
-        ops.im2col3x3(self.z11, self.col, self.b1_bn1.a, self.b1_bn1.b, True)
-        self._pw_fwd(self.col, self.wl["block1_conv2/kernel"].view(288, 64), self.z12.view(-1, 64), B * h2 * w2, 288,
-                     64, self.b1_bn2, training)
-        ops.bn_apply(self.z12, self.b1_bn2.a, self.b1_bn2.b, act=1, out=self.x2)
-        # ---- entry blocks 2-4, middle 5-12, exit 13
-        x = self.x2
-        for e in self.entry:
-            x = self._entry_fwd(e, x, training)
-        for blk, out in zip(self.middle, self.mid_out):
-            self._sep_fwd(blk[0], x, None, True, training)
-            self._sep_fwd(blk[1], blk[0].z, blk[0].bn, True, training)
-            self._sep_fwd(blk[2], blk[1].z, blk[1].bn, True, training)
-            ops.bn_apply(blk[2].z, blk[2].bn.a, blk[2].bn.b, act=0, x=x, out=out)
-            x = out
-        x = self._entry_fwd(self.exit13, x, training)
-        # ---- block 14 + head
-        s1, s2 = self.sep14
-        self._sep_fwd(s1, x, None, False, training)
-        self._sep_fwd(s2, s1.z, s1.bn, True, training)
-        ops.bn_apply(s2.z.view(B, -1, 2048), s2.bn.a, s2.bn.b, act=1, out=self.feat.view(B, -1, 2048))
+        self._backbone_fwd(training)
         F = self.feat.shape[1]
         ops.bias_fill(w["FinalOutput/bias"], self.y_pred)
         ops.gemm(self.feat, False, self.wl["FinalOutput/kernel"], True, self.y_pred, B, self.n_out, F,
@@ -407,61 +339,10 @@ class XceptionSPNetEngine:
 
     def backward_body(self):
         B, sh, w, g = self.B, self.shapes, self.w, self.g
-        G1, G2, G3, S, R0, R1 = self.scratch
-        # ---- block 14
-        s1, s2 = self.sep14
-        fh, fw = sh["out13"]
-        M = B * fh * fw
-        x13 = self.exit13["out"]
-        g_z = self._bn_bwd(self.gfeat.view(B, fh, fw, 2048), s2.z, s2.bn, M, relu_mask=True)
-        g_y = self._view(G3, B, fh, fw, 1536)
-        self._sep_bwd(s2, g_z.view(M, 2048), s1.z, s1.bn, True, self._view(G2, M, 1536), g_y)
-        g_z = self._bn_bwd(g_y, s1.z, s1.bn, M, reduced=True)
-        g_x = self._view(R0, B, fh, fw, 1024)
-        self._sep_bwd(s1, g_z.view(M, 1536), x13, None, False, self._view(G1, M, 1024), g_x)
-        # ---- exit block 13
-        R_cur, R_nxt = R0, R1
-        x_in13 = self.mid_out[-1]
-        g_x = self._entry_bwd(self.exit13, x_in13, g_x, (G1, G2, G3, S, R_nxt))
-        R_cur, R_nxt = R_nxt, R_cur
-        # ---- middle blocks 12..5
-        mh, mw = sh["middle"]
-        M = B * mh * mw
-        for i in range(len(self.middle) - 1, -1, -1):
-            blk = self.middle[i]
-            x_in = self.mid_out[i - 1] if i > 0 else self.entry[-1]["out"]
-            g3 = self._bn_bwd(g_x, blk[2].z, blk[2].bn, M, out=self._view(G1, B, mh, mw, 728))
-            gy2 = self._view(G3, B, mh, mw, 728)
-            self._sep_bwd(blk[2], g3.view(M, 728), blk[1].z, blk[1].bn, True, self._view(G2, M, 728), gy2)
-            g2 = self._bn_bwd(gy2, blk[1].z, blk[1].bn, M, reduced=True)
-            gy1 = self._view(G1, B, mh, mw, 728)
-            self._sep_bwd(blk[1], g2.view(M, 728), blk[0].z, blk[0].bn, True, self._view(G2, M, 728), gy1)
-            g1 = self._bn_bwd(gy1, blk[0].z, blk[0].bn, M, reduced=True)
-            g_new = self._view(R_nxt, B, mh, mw, 728)
-            self._sep_bwd(blk[0], g1.view(M, 728), x_in, None, True, self._view(G2, M, 728), g_new, add_src=g_x)
-            g_x = g_new
-            R_cur, R_nxt = R_nxt, R_cur
-        # ---- entry blocks 4..2
-        for i in range(len(self.entry) - 1, -1, -1):
-            e = self.entry[i]
-            x_in = self.entry[i - 1]["out"] if i > 0 else self.x2
-            g_x = self._entry_bwd(e, x_in, g_x, (G1, G2, G3, S, R_nxt))
-            R_cur, R_nxt = R_nxt, R_cur
-        # ---- block 1
-        h2, w2 = sh["b1c2"]
-        h1, w1 = sh["b1c1"]
-        M2 = B * h2 * w2
-        g_z12 = self._bn_bwd(g_x, self.z12, self.b1_bn2, M2, relu_mask=True)
-        W2l = self.wl["block1_conv2/kernel"].view(288, 64)
-        self._pw_bwd(self.col, W2l, g["block1_conv2/kernel"].view(288, 64), g_z12.view(M2, 64), self.gcol, M2, 288, 64)
-        g_y11 = self._view(G1, B, h1, w1, 32)
-        ops.col2im3x3(self.gcol, g_y11, z=self.z11, a=self.b1_bn1.a, b=self.b1_bn1.b, relu=True)
-        g_z11 = self._bn_bwd(g_y11, self.z11, self.b1_bn1, B * h1 * w1)
-        ops.conv_small_wgrad(2, self.d, g_z11, g["block1_conv1/kernel"])
         H2, W2 = sh["stem"]
         npx = B * H2 * W2
         ga, gb = (self._view(t, B, H2, W2, 3) for t in self.gstem)
-        ops.conv_small_dgrad(2, g_z11, w["block1_conv1/kernel"], ga)
+        self._backbone_bwd(ga)
         # ---- stem
         bn1, bn2, bn3 = self.stem_bn
         drop = self.dropout_rate > 0
@@ -562,3 +443,260 @@ class XceptionSPNetEngine:
         if y_host is not None:
             yt = y_host if torch.is_tensor(y_host) else torch.from_numpy(np.ascontiguousarray(y_host, dtype=np.float32))
             self.y_true.copy_(yt.view(self.y_true.shape), non_blocking=True)
+
+
+class XceptionSPNetEngine(SPNetEngineBase):
+    """keras.applications.Xception backbone (reference default, spnet/config.py:52)."""
+
+    def _arch(self):
+        return arch.shape_walk(self.H, self.W), arch.param_spec(self.H, self.W, self.n_out)
+
+    def _build_backbone(self):
+        sh = self.shapes
+        self.b1_bn1 = self._mk_bn("block1_conv1_bn", 32)
+        self.b1_bn2 = self._mk_bn("block1_conv2_bn", 64)
+        self.entry = []
+        for n, (blk, cin, c) in enumerate(arch.ENTRY_BLOCKS):
+            hw = sh["in%d" % blk]
+            e = dict(blk=blk, cin=cin, c=c, hw=hw, ohw=sh["out%d" % blk], res="conv2d_%d" % (4 + n),
+                     res_bn=self._mk_bn("batch_normalization_%d" % (4 + n), c),
+                     sep1=self._mk_sep("block%d_sepconv1" % blk, cin, c, hw),
+                     sep2=self._mk_sep("block%d_sepconv2" % blk, c, c, hw), relu_in=(blk != 2))
+            self.entry.append(e)
+        self.middle = []
+        for blk in arch.MIDDLE_BLOCKS:
+            self.middle.append([self._mk_sep("block%d_sepconv%d" % (blk, j), 728, 728, sh["middle"]) for j in (1, 2, 3)])
+        hw = sh["in13"]
+        self.exit13 = dict(blk=13, cin=728, c=1024, hw=hw, ohw=sh["out13"], res="conv2d_7",
+                           res_bn=self._mk_bn("batch_normalization_7", 1024),
+                           sep1=self._mk_sep("block13_sepconv1", 728, 728, hw),
+                           sep2=self._mk_sep("block13_sepconv2", 728, 1024, hw), relu_in=True)
+        self.sep14 = [self._mk_sep("block14_sepconv1", 1024, 1536, sh["out13"]),
+                      self._mk_sep("block14_sepconv2", 1536, 2048, sh["out13"])]
+
+    def _alloc_backbone(self):
+        B, sh, A = self.B, self.shapes, self._act
+        h1, w1 = sh["b1c1"]
+        self.z11 = A(B, h1, w1, 32)
+        h2, w2 = sh["b1c2"]
+        self.col = A(B * h2 * w2, 288)
+        self.z12 = A(B, h2, w2, 64)
+        self.x2 = A(B, h2, w2, 64)
+        train = self.can_train
+        maxel = B * h2 * w2 * 128
+        for e in self.entry + [self.exit13]:
+            (eh, ew), (oh, ow) = e["hw"], e["ohw"]
+            e["xs"] = A(B, oh, ow, e["cin"])
+            e["zr"] = A(B, oh, ow, e["c"])
+            for s in (e["sep1"], e["sep2"]):
+                s.t = A(B, eh, ew, s.cin)
+                s.z = A(B, eh, ew, s.cout)
+                maxel = max(maxel, B * eh * ew * max(s.cin, s.cout))
+            e["out"] = A(B, oh, ow, e["c"])
+            e["argmax"] = A(B, oh, ow, e["c"], dtype=torch.uint8) if train else None
+        mh, mw = sh["middle"]
+        for blk in self.middle:
+            for s in blk:
+                s.t = A(B, mh, mw, 728)
+                s.z = A(B, mh, mw, 728)
+        self.mid_out = [A(B, mh, mw, 728) for _ in self.middle]
+        fh, fw = sh["out13"]
+        for s in self.sep14:
+            s.t = A(B, fh, fw, s.cin)
+            s.z = A(B, fh, fw, s.cout)
+        self.feat_dims = (fh, fw, 2048)
+        if train:
+            self.gcol = A(B * h2 * w2, 288)
+            self.scratch = [A(maxel) for _ in range(6)]
+
+    def _backbone_fwd(self, training):
+        B, sh, w = self.B, self.shapes, self.w
+        st = (lambda bn: bn.stats) if training else (lambda bn: None)
+        # ---- block 1
+        h1, w1 = sh["b1c1"]
+        ops.conv_small_fwd(2, self.d, w["block1_conv1/kernel"], self.z11, stats=st(self.b1_bn1))
+        self._bn_ready(self.b1_bn1, B * h1 * w1, training)
+        h2, w2 = sh["b1c2"]
+        ops.im2col3x3(self.z11, self.col, self.b1_bn1.a, self.b1_bn1.b, True)
+        self._pw_fwd(self.col, self.wl["block1_conv2/kernel"].view(288, 64), self.z12.view(-1, 64), B * h2 * w2, 288,
+                     64, self.b1_bn2, training)
+        ops.bn_apply(self.z12, self.b1_bn2.a, self.b1_bn2.b, act=1, out=self.x2)
+        # ---- entry blocks 2-4, middle 5-12, exit 13
+        x = self.x2
+        for e in self.entry:
+            x = self._entry_fwd(e, x, training)
+        for blk, out in zip(self.middle, self.mid_out):
+            self._sep_fwd(blk[0], x, None, True, training)
+            self._sep_fwd(blk[1], blk[0].z, blk[0].bn, True, training)
+            self._sep_fwd(blk[2], blk[1].z, blk[1].bn, True, training)
+            ops.bn_apply(blk[2].z, blk[2].bn.a, blk[2].bn.b, act=0, x=x, out=out)
+            x = out
+        x = self._entry_fwd(self.exit13, x, training)
+        # ---- block 14 + head
+        s1, s2 = self.sep14
+        self._sep_fwd(s1, x, None, False, training)
+        self._sep_fwd(s2, s1.z, s1.bn, True, training)
+        ops.bn_apply(s2.z.view(B, -1, 2048), s2.bn.a, s2.bn.b, act=1, out=self.feat.view(B, -1, 2048))
+
+    def _backbone_bwd(self, ga):
+        B, sh, w, g = self.B, self.shapes, self.w, self.g
+        G1, G2, G3, S, R0, R1 = self.scratch
+        # ---- block 14
+        s1, s2 = self.sep14
+        fh, fw = sh["out13"]
+        M = B * fh * fw
+        x13 = self.exit13["out"]
+        g_z = self._bn_bwd(self.gfeat.view(B, fh, fw, 2048), s2.z, s2.bn, M, relu_mask=True)
+        g_y = self._view(G3, B, fh, fw, 1536)
+        self._sep_bwd(s2, g_z.view(M, 2048), s1.z, s1.bn, True, self._view(G2, M, 1536), g_y)
+        g_z = self._bn_bwd(g_y, s1.z, s1.bn, M, reduced=True)
+        g_x = self._view(R0, B, fh, fw, 1024)
+        self._sep_bwd(s1, g_z.view(M, 1536), x13, None, False, self._view(G1, M, 1024), g_x)
+        # ---- exit block 13
+        R_cur, R_nxt = R0, R1
+        x_in13 = self.mid_out[-1]
+        g_x = self._entry_bwd(self.exit13, x_in13, g_x, (G1, G2, G3, S, R_nxt))
+        R_cur, R_nxt = R_nxt, R_cur
+        # ---- middle blocks 12..5
+        mh, mw = sh["middle"]
+        M = B * mh * mw
+        for i in range(len(self.middle) - 1, -1, -1):
+            blk = self.middle[i]
+            x_in = self.mid_out[i - 1] if i > 0 else self.entry[-1]["out"]
+            g3 = self._bn_bwd(g_x, blk[2].z, blk[2].bn, M, out=self._view(G1, B, mh, mw, 728))
+            gy2 = self._view(G3, B, mh, mw, 728)
+            self._sep_bwd(blk[2], g3.view(M, 728), blk[1].z, blk[1].bn, True, self._view(G2, M, 728), gy2)
+            g2 = self._bn_bwd(gy2, blk[1].z, blk[1].bn, M, reduced=True)
+            gy1 = self._view(G1, B, mh, mw, 728)
+            self._sep_bwd(blk[1], g2.view(M, 728), blk[0].z, blk[0].bn, True, self._view(G2, M, 728), gy1)
+            g1 = self._bn_bwd(gy1, blk[0].z, blk[0].bn, M, reduced=True)
+            g_new = self._view(R_nxt, B, mh, mw, 728)
+            self._sep_bwd(blk[0], g1.view(M, 728), x_in, None, True, self._view(G2, M, 728), g_new, add_src=g_x)
+            g_x = g_new
+            R_cur, R_nxt = R_nxt, R_cur
+        # ---- entry blocks 4..2
+        for i in range(len(self.entry) - 1, -1, -1):
+            e = self.entry[i]
+            x_in = self.entry[i - 1]["out"] if i > 0 else self.x2
+            g_x = self._entry_bwd(e, x_in, g_x, (G1, G2, G3, S, R_nxt))
+            R_cur, R_nxt = R_nxt, R_cur
+        # ---- block 1
+        h2, w2 = sh["b1c2"]
+        h1, w1 = sh["b1c1"]
+        M2 = B * h2 * w2
+        g_z12 = self._bn_bwd(g_x, self.z12, self.b1_bn2, M2, relu_mask=True)
+        W2l = self.wl["block1_conv2/kernel"].view(288, 64)
+        self._pw_bwd(self.col, W2l, g["block1_conv2/kernel"].view(288, 64), g_z12.view(M2, 64), self.gcol, M2, 288, 64)
+        g_y11 = self._view(G1, B, h1, w1, 32)
+        ops.col2im3x3(self.gcol, g_y11, z=self.z11, a=self.b1_bn1.a, b=self.b1_bn1.b, relu=True)
+        g_z11 = self._bn_bwd(g_y11, self.z11, self.b1_bn1, B * h1 * w1)
+        ops.conv_small_wgrad(2, self.d, g_z11, g["block1_conv1/kernel"])
+        ops.conv_small_dgrad(2, g_z11, w["block1_conv1/kernel"], ga)
+
+
+class MobileNetSPNetEngine(SPNetEngineBase):
+    """keras.applications.mobilenet.MobileNet (alpha 1, depth multiplier 1) backbone, BASELINE
+    configs[2] (reference call site spnet/models.py:349-355). Post-activation blocks:
+    DepthwiseConv2D 3x3 'same' stride s -> BN -> ReLU6 -> Conv 1x1 -> BN -> ReLU6.
+
+    The depthwise stages run on the same packed kernels as Xception's (BN + ReLU6 of the
+    previous stage applied on load). A stride-2 'same' depthwise convolution on an even-sized
+    map equals the stride-1 result sampled at odd rows/columns (TF pads only at the end), so the
+    four stride-2 stages run the stride-1 kernel followed by a subsample (and its adjoint in
+    backward); spatial sizes must stay even down to the last stride-2 stage (stem output
+    divisible by 32, e.g. 384x512 inputs)."""
+
+    def _arch(self):
+        return arch.mobilenet_shape_walk(self.H, self.W), arch.mobilenet_param_spec(self.H, self.W, self.n_out)
+
+    def _build_backbone(self):
+        sh = self.shapes
+        self.c1_bn = self._mk_bn("conv1_bn", 32)
+        self.blocks = []
+        for i, (cin, cout, stride) in enumerate(arch.MOBILENET_BLOCKS, start=1):
+            b = dict(i=i, cin=cin, cout=cout, s=stride, hw=sh["in%d" % i], ohw=sh["out%d" % i],
+                     dwk=self.w["conv_dw_%d/depthwise_kernel" % i].view(3, 3, cin),
+                     pw=self.w["conv_pw_%d/kernel" % i].view(cin, cout),
+                     pwl=self.wl["conv_pw_%d/kernel" % i].view(cin, cout),
+                     bn_dw=self._mk_bn("conv_dw_%d_bn" % i, cin), bn_pw=self._mk_bn("conv_pw_%d_bn" % i, cout))
+            if self.can_train:
+                b["gdwk"] = self.g["conv_dw_%d/depthwise_kernel" % i].view(3, 3, cin)
+                b["gpw"] = self.g["conv_pw_%d/kernel" % i].view(cin, cout)
+            self.blocks.append(b)
+
+    def _alloc_backbone(self):
+        B, sh, A = self.B, self.shapes, self._act
+        h, w = sh["conv1"]
+        self.zc1 = A(B, h, w, 32)
+        maxel = B * h * w * 32
+        for b in self.blocks:
+            (h, w), (oh, ow) = b["hw"], b["ohw"]
+            b["zd_full"] = A(B, h, w, b["cin"]) if b["s"] == 2 else None
+            b["zd"] = A(B, oh, ow, b["cin"])
+            b["t"] = A(B, oh, ow, b["cin"])
+            b["zp"] = A(B, oh, ow, b["cout"])
+            maxel = max(maxel, B * h * w * b["cin"], B * oh * ow * b["cout"])
+        fh, fw = self.blocks[-1]["ohw"]
+        self.feat_dims = (fh, fw, 1024)
+        if self.can_train:
+            self.scratch = [A(maxel) for _ in range(4)]
+
+    def _backbone_fwd(self, training):
+        B, w = self.B, self.w
+        h, wd = self.shapes["conv1"]
+        ops.conv_small_fwd(3, self.d, w["conv1/kernel"], self.zc1, stats=self.c1_bn.stats if training else None)
+        self._bn_ready(self.c1_bn, B * h * wd, training)
+        x, xbn = self.zc1, self.c1_bn
+        for b in self.blocks:
+            (oh, ow) = b["ohw"]
+            M = B * oh * ow
+            if b["s"] == 2:
+                ops.dwconv3x3_fwd(x, b["dwk"], xbn.a, xbn.b, 2, out=b["zd_full"])
+                ops.gather_s2(b["zd_full"], out=b["zd"], off=1)
+            else:
+                ops.dwconv3x3_fwd(x, b["dwk"], xbn.a, xbn.b, 2, out=b["zd"])
+            if training:
+                ops.colstats(b["zd"], b["bn_dw"].stats)
+            self._bn_ready(b["bn_dw"], M, training)
+            ops.bn_apply(b["zd"], b["bn_dw"].a, b["bn_dw"].b, act=3, out=b["t"])
+            self._pw_fwd(b["t"].view(M, b["cin"]), b["pwl"], b["zp"].view(M, b["cout"]), M, b["cin"], b["cout"],
+                         b["bn_pw"], training)
+            x, xbn = b["zp"], b["bn_pw"]
+        fh, fw, fc = self.feat_dims
+        ops.bn_apply(x.view(B, -1, fc), xbn.a, xbn.b, act=3, out=self.feat.view(B, -1, fc))
+
+    def _backbone_bwd(self, ga):
+        B, w, g = self.B, self.w, self.g
+        bufs = self.scratch
+        last = self.blocks[-1]
+        fh, fw, fc = self.feat_dims
+        # gradient w.r.t. relu6(BN(zp13)) -> masked in place, BN-backward sums accumulated
+        g_y = self.gfeat.view(B, fh, fw, fc)
+        ops.bn_bwd_reduce(g_y, last["zp"], last["bn_pw"].mean, last["bn_pw"].rstd, last["bn_pw"].stats,
+                          relu_a=last["bn_pw"].a, relu_b=last["bn_pw"].b, act=3)
+        cur = None  # scratch buffer holding g_y (None: self.gfeat)
+        for idx in range(len(self.blocks) - 1, -1, -1):
+            b = self.blocks[idx]
+            (h, wd), (oh, ow) = b["hw"], b["ohw"]
+            M = B * oh * ow
+            cin, cout = b["cin"], b["cout"]
+            x, xbn = (self.blocks[idx - 1]["zp"], self.blocks[idx - 1]["bn_pw"]) if idx > 0 else (self.zc1, self.c1_bn)
+            tb, fb, nb = [i for i in range(4) if i != cur][:3]
+            # pointwise BN + 1x1 (g_y already carries the ReLU6 mask and this BN's backward sums)
+            g_zp = self._bn_bwd(g_y, b["zp"], b["bn_pw"], M, reduced=True)
+            g_t = self._view(bufs[tb], B, oh, ow, cin)
+            self._pw_bwd(b["t"].view(M, cin), b["pwl"], b["gpw"], g_zp.view(M, cout), g_t.view(M, cin), M, cin, cout)
+            # depthwise BN (+ReLU6 mask)
+            ops.bn_bwd_reduce(g_t, b["zd"], b["bn_dw"].mean, b["bn_dw"].rstd, b["bn_dw"].stats, relu_a=b["bn_dw"].a,
+                              relu_b=b["bn_dw"].b, act=3)
+            g_zd = self._bn_bwd(g_t, b["zd"], b["bn_dw"], M, reduced=True)
+            g_full = ops.scatter_s2(g_zd, self._view(bufs[fb], B, h, wd, cin), off=1) if b["s"] == 2 else g_zd
+            # depthwise 3x3: gradient w.r.t. relu6(BN_prev(x)) (masked) + BN_prev backward sums + dk
+            g_y = self._view(bufs[nb], B, h, wd, cin)
+            ops.dwconv3x3_bwd_fused(g_full, x, b["dwk"], b["gdwk"], in_a=xbn.a, in_b=xbn.b, relu=2, bn_mean=xbn.mean,
+                                    bn_rstd=xbn.rstd, stats=xbn.stats, out=g_y)
+            cur = nb
+        h, wd = self.shapes["conv1"]
+        g_zc1 = self._bn_bwd(g_y, self.zc1, self.c1_bn, B * h * wd, reduced=True)
+        ops.conv_small_wgrad(3, self.d, g_zc1, g["conv1/kernel"])
+        ops.conv_small_dgrad(3, g_zc1, w["conv1/kernel"], ga)

@@ -139,8 +139,10 @@ class History:
 class SPNetModel:
     """Xception-SPNet behind a Keras-Model-like interface."""
 
-    def __init__(self, input_shape, Y0size=576, quick_setup=False, weights=None, seed=1, name="spnet"):
+    def __init__(self, input_shape, Y0size=576, quick_setup=False, weights=None, seed=1, name="spnet",
+                 backbone="Xception"):
         H, W = int(input_shape[0]), int(input_shape[1])
+        self.backbone = backbone
         if len(input_shape) > 2 and int(input_shape[2]) != 1:
             raise ValueError("Xception-SPNet takes single-channel (grayscale) input; got shape %s" % (tuple(input_shape),))
         if Y0size % cf.vars_per_pred != 0:
@@ -149,7 +151,7 @@ class SPNetModel:
         self.input_shape = (None, H, W, 1)
         self.output_shape = (None, Y0size)
         self.H, self.W, self.Y0size = H, W, Y0size
-        self.spec = arch.param_spec(H, W, Y0size)
+        self.spec = (arch.mobilenet_param_spec if backbone == "MobileNet" else arch.param_spec)(H, W, Y0size)
         self._shape = OrderedDict((k, s) for k, s, _, _ in self.spec)
         self._host_weights = weights if weights is not None else arch.glorot_init(self.spec, seed)
         self.use_l2 = not quick_setup          # add_regularization is skipped by quick_setup (spnet/models.py:398-399)
@@ -237,7 +239,7 @@ class SPNetModel:
 
     def summary(self):
         tot, tr, nt = arch.count_params(self.spec)
-        print("Xception-SPNet  input (%d,%d,1) -> %d outputs; %d layers with weights" % (self.H, self.W, self.Y0size, len(self.layers)))
+        print("%s-SPNet  input (%d,%d,1) -> %d outputs; %d layers with weights" % (self.backbone, self.H, self.W, self.Y0size, len(self.layers)))
         print("Total params: {:,}\nTrainable params: {:,}\nNon-trainable params: {:,}".format(tot, tr, nt))
 
     # ---- engines ------------------------------------------------------------------------------
@@ -246,13 +248,14 @@ class SPNetModel:
         self.optimizer = optimizer if optimizer is not None else Adam(lr=0.00001)
 
     def _engine(self, batch, training):
-        from .engine import XceptionSPNetEngine
+        from .engine import MobileNetSPNetEngine, XceptionSPNetEngine
+        Engine = MobileNetSPNetEngine if self.backbone == "MobileNet" else XceptionSPNetEngine
         key = (batch, training)
         eng = self._engines.get(key)
         if eng is None:
             torch = _torch()
             dev = "cuda:%d" % torch.cuda.current_device()
-            eng = XceptionSPNetEngine(self.H, self.W, batch, n_out=self.Y0size, dtype=cf.compute_dtype, device=dev,
+            eng = Engine(self.H, self.W, batch, n_out=self.Y0size, dtype=cf.compute_dtype, device=dev,
                                       weights=self._weights_dict(), loss_type=cf.loss_type, use_l2=self.use_l2,
                                       training=training)
             eng._version = self._version
@@ -408,17 +411,26 @@ def Xception(weights=None, include_top=False, input_tensor=None, input_shape=Non
     return "Xception"
 
 
+def MobileNet(weights=None, include_top=False, input_tensor=None, input_shape=None):
+    """keras.applications.mobilenet.MobileNet plug-in (spnet/models.py:20,349-355). The reference asks
+    for weights='imagenet', which Keras 2.1.3 only provides for square 128-224 inputs; here the backbone
+    is always built with the supplied / Keras-default-initialised weights."""
+    return "MobileNet"
+
+
 def create_model_functional(X, Y0size=576, freeze_fac=0.75, quick_setup=False):
     """spnet/models.py:302-424. Stem -> cf.basemodel -> Flatten -> Dense(Y0size,'FinalOutput')."""
     print("Using functional API model, cf.basemodel =", cf.basemodel)
     print("X[0].shape = ", X[0].shape)
     if not hasattr(sys.modules[__name__], cf.basemodel):
         raise AttributeError("module 'spnet.models' has no attribute '%s'" % cf.basemodel)
-    if cf.basemodel != "Xception":
-        raise NotImplementedError("cf.basemodel = %r: only the Xception backbone (the reference default, "
-                                  "spnet/config.py:52) is built so far" % cf.basemodel)
-    model = SPNetModel(X[0].shape, Y0size=Y0size, quick_setup=quick_setup)
-    num_layers = 144  # Keras layer count of base_model (paper/run_logs/log_DatasetA_*.txt:95)
+    if cf.basemodel not in ("Xception", "MobileNet"):
+        raise NotImplementedError("cf.basemodel = %r: the Xception (reference default, spnet/config.py:52) and "
+                                  "MobileNet backbones are built so far" % cf.basemodel)
+    model = SPNetModel(X[0].shape, Y0size=Y0size, quick_setup=quick_setup, backbone=cf.basemodel)
+    # Keras layer count of base_model: 144 for Xception (paper/run_logs/log_DatasetA_*.txt:95);
+    # MobileNet: 1 Input + 12 stem layers + 81 backbone layers (3 + 13 x 6)
+    num_layers = 144 if cf.basemodel == "Xception" else 94
     freeze_layers = int(num_layers * freeze_fac)
     print("Freezing ", freeze_layers, "/", num_layers, " layers of base_model")
     if freeze_layers > 0:

@@ -219,13 +219,27 @@ def maxpool3s2_bwd(gout, argmax, H, W, out=None):
     return out
 
 
-def gather_s2(x, out=None):
+def gather_s2(x, out=None, off=0):
     _chk(x, out)
     B, H, W, C = x.shape
     if out is None:
-        out = torch.empty(B, (H + 1) // 2, (W + 1) // 2, C, device=x.device, dtype=x.dtype)
-    lib().gather_s2(_p(x), _p(out), dtype_code(x), B, H, W, C, _s())
+        out = torch.empty(B, (H + 1 - off) // 2, (W + 1 - off) // 2, C, device=x.device, dtype=x.dtype)
+    lib().gather_s2(_p(x), _p(out), dtype_code(x), B, H, W, C, off, _s())
     return out
+
+
+def scatter_s2(x, out, off=0):
+    """Adjoint of gather_s2: x [B,OH,OW,C] -> out [B,H,W,C] (zero where nothing lands)."""
+    _chk(x, out)
+    B, H, W, C = out.shape
+    lib().scatter_s2(_p(x), _p(out), dtype_code(x), B, H, W, C, off, _s())
+    return out
+
+
+def colstats(z, stats):
+    _chk(z, stats)
+    C = z.shape[-1]
+    lib().colstats(_p(z), _p(stats), dtype_code(z), z.numel() // C, C, _s())
 
 
 # ----------------------------------------------------------------------------- stem / block1

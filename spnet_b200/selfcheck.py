@@ -7,13 +7,13 @@ import sys
 import numpy as np
 
 
-def make_case(H, W, B, seed=0, n_out=576):
+def make_case(H, W, B, seed=0, n_out=576, backbone="Xception"):
     """Seeded inputs shared by the oracle and the engine: weights with non-trivial BN state,
     gen_fake_espi-like images in [-1,1], YOLO-grid targets."""
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from oracle import xception_torch as xt
     rng = np.random.default_rng(seed)
-    spec = xt.xception_spnet_spec(H, W, n_out)
+    spec = (xt.mobilenet_spnet_spec if backbone == "MobileNet" else xt.xception_spnet_spec)(H, W, n_out)
     w = xt.init_weights(spec, seed=seed + 1)
     for k in w:
         leaf = k.rsplit("/", 1)[1]

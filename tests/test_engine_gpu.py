@@ -152,3 +152,82 @@ def test_dropout_statistics_and_smoke():
     frac = float((eng.d == 0).float().mean())
     assert 0.07 < frac < 0.13, frac
     selfcheck.smoke()
+
+
+# ------------------------------------------------------------------ MobileNet backbone (BASELINE configs[2])
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_mobilenet_inference_forward(dtype, tol):
+    from spnet_b200.engine import MobileNetSPNetEngine
+    H, W, B = 128, 192, 3
+    w, x, yt = make_case(H, W, B, seed=13, backbone="MobileNet")
+    ref = xt.OracleMobileNetSPNet(w, H, W)
+    with torch.no_grad():
+        y_ref = ref.forward(x, training=False).numpy()
+    eng = MobileNetSPNetEngine(H, W, B, dtype=dtype, weights=w, training=False)
+    eng.load_batch(x)
+    y = eng.forward(training=False).cpu().numpy()
+    assert rel_err(y, y_ref) < tol, rel_err(y, y_ref)
+
+
+@pytest.mark.parametrize("loss_type", ["same", "hybrid"])
+def test_mobilenet_train_step_fp32(loss_type):
+    from spnet_b200.engine import MobileNetSPNetEngine
+    H, W, B = 128, 192, 4
+    w, x, yt = make_case(H, W, B, seed=15, backbone="MobileNet")
+    ref = xt.OracleMobileNetSPNet(w, H, W)
+    total, data, y_ref, grads = ref.loss_and_grads(x, yt, loss_type=loss_type)
+    eng = MobileNetSPNetEngine(H, W, B, dtype="fp32", weights=w, dropout_rate=0.0, loss_type=loss_type)
+    eng.load_batch(x, yt)
+    eng.grad_hook = lambda e: None
+    loss6 = eng.train_step(lr=1e-3)
+    torch.cuda.synchronize()
+    got_total = float(loss6[0]) + float(eng.l2_out[0])
+    assert abs(float(loss6[0]) - data) / abs(data) < 1e-4
+    assert abs(got_total - total) / abs(total) < 1e-4
+    assert rel_err(eng.y_pred.cpu().numpy(), y_ref.numpy()) < 1e-4
+    gnorms = [float(np.linalg.norm(grads[k].numpy().astype(np.float64))) / np.sqrt(grads[k].numel()) for k in ref.trainable]
+    floor_rms = 1e-3 * float(np.median(gnorms))
+    bad = []
+    for k in ref.trainable:
+        g_ref = grads[k].numpy().copy()
+        if k in ref.l2_keys:
+            g_ref -= 2 * xt.L2 * w[k]
+        if k == "batch_normalization_3/beta":
+            continue  # a per-channel shift in front of a train-mode BN: mathematically zero on both sides
+        e = l2_err(eng.g[k].cpu().numpy(), g_ref, floor=floor_rms * np.sqrt(g_ref.size))
+        if e > 3e-2:
+            bad.append((k, e))
+    assert not bad, bad[:10]
+    ref.adam_step(grads, 1e-3)
+    w_ref, w_got = ref.weights_numpy(), eng.get_weights()
+    for k in w_ref:
+        if "moving" in k:
+            assert rel_err(w_got[k], w_ref[k]) < 1e-4, k
+
+
+def test_mobilenet_train_step_bf16():
+    """MobileNet has no residual paths: on random-init weights with train-mode BatchNorm a relative
+    perturbation grows ~1.4x per block (the fp32 engine ends at 2.4e-5 from 1e-7 rounding, the bf16 one
+    at ~0.37 from 4e-3; tests/debug_mobilenet_errors.py prints the per-block curve). So the bf16 check
+    here is behavioural: the error stays inside that amplification envelope, the head gradient points
+    the right way, and the loss goes down over a few optimiser steps."""
+    from spnet_b200.engine import MobileNetSPNetEngine
+    H, W, B = 192, 256, 8
+    w, x, yt = make_case(H, W, B, seed=17, backbone="MobileNet")
+    ref = xt.OracleMobileNetSPNet(w, H, W)
+    total, data, y_ref, grads = ref.loss_and_grads(x, yt)
+    eng = MobileNetSPNetEngine(H, W, B, dtype="bf16", weights=w, dropout_rate=0.0)
+    eng.load_batch(x, yt)
+    eng.grad_hook = lambda e: None
+    loss6 = eng.train_step(lr=1e-4)
+    torch.cuda.synchronize()
+    assert l2_err(eng.y_pred.cpu().numpy(), y_ref.numpy()) < 0.6
+    assert abs(float(loss6[0]) - data) / abs(data) < 0.5
+    a = eng.g["FinalOutput/kernel"].cpu().numpy().ravel().astype(np.float64)
+    b = (grads["FinalOutput/kernel"].numpy() - 2 * xt.L2 * w["FinalOutput/kernel"]).ravel().astype(np.float64)
+    assert float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30)) > 0.5
+    eng.grad_hook = None
+    losses = [float(eng.train_step(lr=1e-4)[0]) for _ in range(6)]
+    torch.cuda.synchronize()
+    assert all(np.isfinite(losses)), losses
+    assert losses[-1] < losses[0], losses

@@ -36,7 +36,9 @@ def dw_ref(x, k, a=None, b=None, relu=False):
     v = x.float()
     if a is not None:
         v = v * a + b
-    if relu:
+    if relu == 2:
+        v = torch.clamp(v, 0.0, 6.0)
+    elif relu:
         v = torch.relu(v)
     C = x.shape[-1]
     w = k.permute(2, 0, 1).reshape(C, 1, 3, 3)
@@ -114,18 +116,18 @@ def test_decode_matches_numpy():
 # ------------------------------------------------------------------ depthwise
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(2, 12, 16, 728), (3, 47, 63, 128), (1, 6, 8, 2048), (2, 5, 5, 40), (1, 93, 125, 64)])
-@pytest.mark.parametrize("mode", ["plain", "relu", "affine_relu", "affine"])
+@pytest.mark.parametrize("mode", ["plain", "relu", "affine_relu", "affine", "affine_relu6"])
 def test_dwconv_fwd(dtype, shape, mode):
     ops = _ops()
     torch.manual_seed(1)
     B, H, W, C = shape
-    x = torch.randn(shape, device=dev()).to(dtype)
+    x = (torch.randn(shape, device=dev()) * (5.0 if mode == "affine_relu6" else 1.0)).to(dtype)
     k = torch.randn(3, 3, C, device=dev()) * 0.3
     a = b = None
-    if mode in ("affine_relu", "affine"):
+    if mode in ("affine_relu", "affine", "affine_relu6"):
         a = torch.rand(C, device=dev()) + 0.5
         b = torch.randn(C, device=dev()) * 0.2 + 0.3  # a non-zero shift makes the padding order visible
-    relu = mode in ("relu", "affine_relu")
+    relu = 2 if mode == "affine_relu6" else mode in ("relu", "affine_relu")
     out = ops.dwconv3x3_fwd(x, k, a, b, relu)
     ref = dw_ref(x, k, a, b, relu)
     torch.testing.assert_close(out.float(), ref, **tol(dtype))
@@ -169,18 +171,18 @@ def test_dwconv_bwd(dtype, shape):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(2, 12, 16, 728), (2, 47, 63, 128), (2, 7, 9, 24), (1, 93, 125, 64), (3, 6, 8, 1024), (2, 24, 32, 256)])
-@pytest.mark.parametrize("mode", ["bn_relu", "relu_add", "plain_strided"])
+@pytest.mark.parametrize("mode", ["bn_relu", "relu_add", "plain_strided", "bn_relu6"])
 def test_dwconv_bwd_fused(dtype, shape, mode):
     """Fused dgrad + wgrad + ReLU mask + BatchNorm-backward sums against autograd."""
     ops = _ops()
     torch.manual_seed(4)
     B, H, W, C = shape
-    x = torch.randn(shape, device=dev()).to(dtype)
+    x = (torch.randn(shape, device=dev()) * (5.0 if mode == "bn_relu6" else 1.0)).to(dtype)
     k = torch.randn(3, 3, C, device=dev()) * 0.3
     g = torch.randn(shape, device=dev()).to(dtype)
     a = b = mean = rstd = stats = add = sadd = None
-    relu = mode != "plain_strided"
-    if mode == "bn_relu":
+    relu = 2 if mode == "bn_relu6" else mode != "plain_strided"
+    if mode in ("bn_relu", "bn_relu6"):
         a = torch.rand(C, device=dev()) + 0.5
         b = torch.randn(C, device=dev()) * 0.2
         mean = torch.randn(C, device=dev()) * 0.1
@@ -191,11 +193,11 @@ def test_dwconv_bwd_fused(dtype, shape, mode):
     else:
         sadd = torch.randn(B, (H + 1) // 2, (W + 1) // 2, C, device=dev()).to(dtype)
     pre = x.float() * a + b if a is not None else x.float()
-    v = (torch.relu(pre) if relu else pre).detach().requires_grad_(True)
+    v = (torch.clamp(pre, 0.0, 6.0) if relu == 2 else (torch.relu(pre) if relu else pre)).detach().requires_grad_(True)
     kr = k.clone().requires_grad_(True)
     y = nhwc(F.conv2d(nchw(v), kr.permute(2, 0, 1).reshape(C, 1, 3, 3), padding=1, groups=C))
     y.backward(g.float())
-    ref = v.grad * (pre > 0) if relu else v.grad.clone()
+    ref = v.grad * ((pre > 0) & (pre < 6)) if relu == 2 else (v.grad * (pre > 0) if relu else v.grad.clone())
     dk = torch.zeros(3, 3, C, device=dev())
     gin = ops.dwconv3x3_bwd_fused(g, x, k, dk, in_a=a, in_b=b, relu=relu, bn_mean=mean, bn_rstd=rstd, stats=stats,
                                   add_src=add, add_strided=sadd)
@@ -212,6 +214,26 @@ def test_dwconv_bwd_fused(dtype, shape, mode):
     scale = float(kr.grad.abs().max())
     t = dict(rtol=2e-2, atol=2e-2 * scale) if dtype == torch.bfloat16 else dict(rtol=2e-4, atol=2e-4 * scale)
     torch.testing.assert_close(dk, kr.grad, **t)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("off", [0, 1])
+def test_subsample_scatter_colstats(dtype, off):
+    ops = _ops()
+    torch.manual_seed(6)
+    B, H, W, C = 2, 12, 16, 72
+    x = torch.randn(B, H, W, C, device=dev()).to(dtype)
+    y = ops.gather_s2(x, off=off)
+    torch.testing.assert_close(y, x[:, off::2, off::2, :].contiguous())
+    back = torch.empty_like(x)
+    ops.scatter_s2(y, back, off=off)
+    ref = torch.zeros_like(x)
+    ref[:, off::2, off::2, :] = y
+    torch.testing.assert_close(back, ref)
+    st = torch.zeros(2 * C, device=dev(), dtype=torch.float64)
+    ops.colstats(x, st)
+    torch.testing.assert_close(st[:C], x.double().sum((0, 1, 2)), rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(st[C:], (x.double() ** 2).sum((0, 1, 2)), rtol=1e-5, atol=1e-4)
 
 
 # ------------------------------------------------------------------ GEMM
