@@ -9,7 +9,8 @@ Prints ONE JSON line (rank 0). N > 1 is launched by torchrun (one rank per GPU, 
 `value`   : images/s with the batch already resident in HBM (CUDA-graph replay, device timed).
 `e2e`     : images/s through the public Keras-like API path with HOST buffers: pinned H2D of the
             step's inputs and a D2H read of the loss inside the timed region.
-`roofline`: the dominant kernel family of the step, timed live with CUDA events.
+`roofline`: the dominant kernel family of the step (its launches of one step replayed as a CUDA graph
+            and timed with CUDA events); `roofline_other` holds the other families.
 `--impl reference`: the reference network's CPU path. TensorFlow 1.14 / Keras 2.1.3 cannot run in
 this image, so this arm times the oracle restatement (kind "port") of the same
 training step on the box's host cores.
@@ -146,6 +147,7 @@ def algorithmic_work(name, a):
     """(bytes, flops) one launch must move / compute, from its C-ABI arguments."""
     def es(dtype):
         return 2 if dtype == 1 else 4
+    a = tuple(a)
     if name == "spnet_dwconv3x3_fwd":      # in,k,a,b,relu,out,dtype,B,H,W,C,stream
         n = a[7] * a[8] * a[9] * a[10]
         return 2 * n * es(a[6]), 18 * n
@@ -249,36 +251,72 @@ def run_ours(args, rank, world):
     e2e = total_imgs / (ms_e2e / 1e3)
     peaks = load_peaks()
 
-    # ---- roofline of the dominant kernel family (live CUDA-event timing of eager steps)
+    # ---- per-family view of the step: eager steps with a CUDA-event pair around every launch give the
+    #      share of each kernel family; the roofline numbers come from replaying each family's launches
+    #      (same arguments, same buffers, step order) as one CUDA graph timed with CUDA events, so that
+    #      the ~4 us per-launch cost of eager event pairs does not deflate kernels that run 10-30 us
     eng.graph = None
     hook, eng.grad_hook = eng.grad_hook, None  # time this rank's kernels only
     fam, psteps = kernel_breakdown(eng, lib)
     eng.grad_hook = hook
     total_ms = sum(d["ms"] for d in fam.values())
     share = sorted(((d["ms"] / total_ms, n, d["launches"] // psteps) for n, d in fam.items()), reverse=True)
-    breakdown = [{"kernel": n, "share": round(s, 4), "launches_per_step": l} for s, n, l in share[:12]]
-    groups = {"dwconv3x3": ("hbm", [n for n in fam if n.startswith("spnet_dwconv3x3")]),
-              "gemm_bf16": ("tensor", [n for n in fam if n == "spnet_gemm_bf16"])}
+    breakdown = [{"kernel": n, "share": round(s, 4), "launches_per_step": l} for s, n, l in share[:14]]
+
+    def graph_us(calls, reps=4):
+        """Average device time per launch of `calls` [(name, args)] replayed as one CUDA graph."""
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            st = torch.cuda.current_stream().cuda_stream
+            for name, a in calls:
+                rc = getattr(lib._dll, name)(*(tuple(a[:-1]) + (st,)))
+                if rc != 0:
+                    raise RuntimeError("%s failed in the family replay: %s" % (name, lib.last_error()))
+        g.replay()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(reps):
+            g.replay()
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1) * 1e3 / (reps * len(calls))
+
+    RIDGE = peaks["tf_sust"] * 1e12 / (peaks["hbm"] * 1e9)  # FLOP/B above which a GEMM is tensor-bound
+    one_step = {n: d["items"][:len(d["items"]) // psteps] for n, d in fam.items()}
+    fams = {"gemm_tensor": ("tensor", "gemm_tc_kernel (tcgen05), shapes above the ridge (%.0f FLOP/B)" % RIDGE, []),
+            "gemm_hbm": ("hbm", "gemm_tc_kernel (tcgen05), shapes below the ridge", []),
+            "dwconv_fwd": ("hbm", "dw3x3_fwd_packed_kernel (+BN/ReLU on load)", []),
+            "dwconv_bwd": ("hbm", "dw3x3_bwd_packed_kernel (dgrad+wgrad+mask+BN sums)", [])}
+    for a, _ in one_step.get("spnet_gemm_bf16", []):
+        b_, f_ = algorithmic_work("spnet_gemm_bf16", a)
+        fams["gemm_tensor" if f_ / b_ >= RIDGE else "gemm_hbm"][2].append(("spnet_gemm_bf16", a))
+    for a, _ in one_step.get("spnet_dwconv3x3_fwd", []):
+        fams["dwconv_fwd"][2].append(("spnet_dwconv3x3_fwd", a))
+    for a, _ in one_step.get("spnet_dwconv3x3_bwd_fused", []):
+        fams["dwconv_bwd"][2].append(("spnet_dwconv3x3_bwd_fused", a))
     roofs = {}
-    for gname, (bound, names) in groups.items():
-        ms = sum(fam[n]["ms"] for n in names)
-        nb = nf = nl = 0
-        for n in names:
-            for a, _ in fam[n]["items"]:
-                b_, f_ = algorithmic_work(n, a)
-                nb += b_; nf += f_; nl += 1
+    for key, (bound, label, calls) in fams.items():
+        if not calls:
+            continue
+        us = graph_us(calls)
+        nb = sum(algorithmic_work(n, a)[0] for n, a in calls)
+        nf = sum(algorithmic_work(n, a)[1] for n, a in calls)
+        r = {"bound": bound, "kernel": label, "launches": len(calls), "avg_launch_ms": us * 1e-3,
+             "traffic": None, "timing": "CUDA-graph replay of the family's launches of one step, CUDA events"}
+        t_s = us * 1e-6 * len(calls)
         if bound == "hbm":
-            ach = nb / (ms * 1e-3) / 1e9
-            roofs[gname] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
-                            "traffic": None, "kernel": gname + " fwd + fused bwd (dgrad+wgrad+mask+BN sums)", "share_of_step": ms / total_ms,
-                            "launches": nl // psteps, "avg_launch_ms": ms / max(nl, 1), "algorithmic_bytes_per_step": nb // psteps}
+            ach = nb / t_s / 1e9
+            r.update({"achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                      "algorithmic_bytes_per_step": nb})
         else:
-            ach = nf / (ms * 1e-3) / 1e12
-            roofs[gname] = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                            "frac": ach / peaks["tf_sust"], "traffic": None, "kernel": "gemm_tc_kernel (tcgen05)",
-                            "share_of_step": ms / total_ms, "launches": nl // psteps, "avg_launch_ms": ms / max(nl, 1),
-                            "algorithmic_flops_per_step": nf // psteps}
-    # per-shape view of the GEMMs (M,N,K,a_mn,b_mn): time, TFLOP/s
+            ach = nf / t_s / 1e12
+            r.update({"achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sust"],
+                      "algorithmic_flops_per_step": nf})
+        r["share_of_step"] = t_s * 1e3 / (ms_dev / args.steps)
+        roofs[key] = r
+    # per-shape view of the GEMMs (M,N,K,a_mn,b_mn): eager-event time, TFLOP/s
     shapes = {}
     for a, ms in fam.get("spnet_gemm_bf16", {"items": []})["items"]:
         key = (a[9], a[10], a[11], a[2], a[5])
@@ -286,7 +324,7 @@ def run_ours(args, rank, world):
         d[0] += 1
         d[1] += ms
     gemm_shapes = [{"M": k[0], "N": k[1], "K": k[2], "a_mn": k[3], "b_mn": k[4], "launches_per_step": v[0] // psteps,
-                    "us_each": round(1e3 * v[1] / v[0], 1), "tflops": round(2.0 * k[0] * k[1] * k[2] / (v[1] / v[0] * 1e-3) / 1e12, 1)}
+                    "us_each_eager": round(1e3 * v[1] / v[0], 1), "tflops": round(2.0 * k[0] * k[1] * k[2] / (v[1] / v[0] * 1e-3) / 1e12, 1)}
                    for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:10]]
     dominant = max(roofs.values(), key=lambda r: r["share_of_step"])
     other = [r for r in roofs.values() if r is not dominant]
@@ -333,7 +371,7 @@ def run_ours(args, rank, world):
            "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                    "h2d_bytes_per_step": int(B * (H * W * 4 + N_OUT * 4)), "d2h_bytes_per_step": 24},
            "gpu_launches": int(launches_per_step * args.steps * 2),
-           "roofline": dominant, "roofline_other": other, "kernel_breakdown": breakdown, "gemm_shapes": gemm_shapes,
+           "roofline": dominant, "roofline_other": other, "kernel_breakdown": breakdown, "eager_step_ms": total_ms / psteps, "gemm_shapes": gemm_shapes,
            "peaks": peaks, "inference": infer, "cpu_baseline": cpu}
     print(json.dumps(out), flush=True)
 
