@@ -119,7 +119,8 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // multicast by TMA into both CTAs' shared memory, so the pair reads B from L2 once.
 template <int BN, bool A_MN, bool B_MN, int STAGES, int CL>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                              const __grid_constant__ CUtensorMap tmB, GemmEpi epi,
+                                                              const __grid_constant__ CUtensorMap tmB,
+                                                              const __grid_constant__ CUtensorMap tmD, GemmEpi epi,
                                                               int M, int N, int K, int kb_per_split, int tiles_m,
                                                               int tiles_n, int n_units) {
     constexpr uint32_t A_BYTES = BM * BK * 2;
@@ -130,9 +131,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
     __shared__ uint32_t tmem_base_holder;
-    __shared__ float sstat[2][4][BN];
+    __shared__ float sstat[2][2][4][BN];  // [accumulator parity][sum | sumsq][lane quadrant][column]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // bf16 output staging for the TMA-store epilogue: one 32 x 32 (64-byte rows, SWIZZLE_64B) box per epilogue warp
+    const uint32_t stage_out0 = smem_u32(smem) + STAGES * STAGE_BYTES;
     const int total_kb = (K + BK - 1) / BK;
     const uint32_t crank = CL > 1 ? cluster_cta_rank() : 0u;
     const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
@@ -264,6 +267,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
         const int chalf = (warp - 2) >> 2;      // which half of the column chunks this warp drains
         const int et = (warp - 2) * 32 + lane;  // 0..255 within the epilogue group
+        // BatchNorm column statistics: thread `et` owns column `et` of the tile and keeps fp64 running
+        // sums across the units this CTA walks; they go to global memory (fp64 atomics) only when the
+        // n-tile changes or the CTA is done. Per-unit atomics to the same few addresses from every CTA
+        // were 36 % of a skinny GEMM (744000 x 128 x 128: 125 us -> 80 us without them).
+        double acc_s = 0.0, acc_q = 0.0;
+        int acc_n0 = -1;
+        auto flush_stats = [&]() {
+            if (acc_n0 >= 0 && et < BN && acc_n0 + et < N) {
+                atomicAdd(epi.colstats + (acc_n0 + et), acc_s);
+                atomicAdd(epi.colstats + N + (acc_n0 + et), acc_q);
+            }
+            acc_s = 0.0;
+            acc_q = 0.0;
+        };
         uint32_t u = 0;
         for (int unit = cluster_id; unit < n_units; unit += n_clusters, ++u) {
             const int n0 = (unit % tiles_n) * BN;
@@ -287,13 +304,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         f[2 * j] = __uint_as_float(packed[j] << 16);  // statistics of the values as stored
                         f[2 * j + 1] = __uint_as_float(packed[j] & 0xffff0000u);
                     }
-                    if (row_ok) {
-                        bf16* o = reinterpret_cast<bf16*>(epi.out) + (size_t)row * epi.ldc + col0;
+                    // registers -> swizzled staging box -> one TMA store per 32 x 32 chunk: the row-per-lane
+                    // global stores this replaces cost 32 LSU cycles each (32 different lines per instruction);
+                    // rows >= M and columns >= N are clipped by the TMA unit
+                    if (col0 < N && m0 + q * 32 < M) {  // warp-uniform
+                        const uint32_t stg = stage_out0 + (uint32_t)(warp - 2) * 2048u;
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous box read out
+                        __syncwarp();
+                        const uint32_t rowaddr = stg + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            if (col0 + g * 8 < N)  // N % 8 == 0 is checked on the host
-                                *reinterpret_cast<uint4*>(o + g * 8) =
-                                    make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+                        for (int g = 0; g < 4; ++g)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (((uint32_t)g ^ sw) << 4)),
+                                         "r"(packed[4 * g]), "r"(packed[4 * g + 1]), "r"(packed[4 * g + 2]),
+                                         "r"(packed[4 * g + 3])
+                                         : "memory");
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmD),
+                                         "r"(stg), "r"(col0), "r"(m0 + q * 32)
+                                         : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
                     }
                 } else {
@@ -322,8 +353,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
                     const float cs = warp_colsum32(f, lane);
                     const float cq = warp_colsum32(sq, lane);
-                    sstat[0][q][c * 32 + lane] = cs;
-                    sstat[1][q][c * 32 + lane] = cq;
+                    sstat[as][0][q][c * 32 + lane] = cs;
+                    sstat[as][1][q][c * 32 + lane] = cq;
                 }
             }
             // accumulator fully read: hand it back to the MMA warp
@@ -331,18 +362,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * as);
             if (epi.colstats) {
+                // partial sums of this unit are visible after the barrier; the buffer alternates with the
+                // accumulator parity, so the next unit's writers never race with these reads
                 epi_bar_sync();
-                for (int cc = et; cc < BN; cc += 32 * kEpiWarps) {
-                    if (n0 + cc < N) {
-                        const float s = sstat[0][0][cc] + sstat[0][1][cc] + sstat[0][2][cc] + sstat[0][3][cc];
-                        const float s2 = sstat[1][0][cc] + sstat[1][1][cc] + sstat[1][2][cc] + sstat[1][3][cc];
-                        atomicAdd(epi.colstats + (n0 + cc), (double)s);
-                        atomicAdd(epi.colstats + N + (n0 + cc), (double)s2);
-                    }
+                if (n0 != acc_n0) {
+                    flush_stats();
+                    acc_n0 = n0;
                 }
-                epi_bar_sync();
+                if (et < BN) {
+                    acc_s += (double)(sstat[as][0][0][et] + sstat[as][0][1][et] + sstat[as][0][2][et] + sstat[as][0][3][et]);
+                    acc_q += (double)(sstat[as][1][0][et] + sstat[as][1][1][et] + sstat[as][1][2][et] + sstat[as][1][3][et]);
+                }
             }
         }
+        if (epi.colstats) flush_stats();
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging may not die under a store
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     if (CL > 1) cluster_sync_all(); else __syncthreads();  // no CTA may exit while its peer still multicasts into it
@@ -385,10 +419,10 @@ int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long lon
 }
 
 template <int BN, bool A_MN, bool B_MN, int CL>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmEpi epi, int M, int N, int K, int splits,
-                cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, GemmEpi epi, int M, int N, int K,
+                int splits, cudaStream_t stream) {
     constexpr int STAGES = (BN <= 128) ? 6 : 4;
-    constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
+    constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + kEpiWarps * 2048;
     auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, CL>;
     static bool configured = false;
     static int num_sms = 148;
@@ -417,7 +451,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmEpi epi, int M
     }
     const int max_clusters = num_sms / CL;
     const int grid = (int)(units < max_clusters ? units : max_clusters) * CL;
-    cudaError_t e = spnet_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, CL, ta, tb, epi, M, N, K, kbps,
+    cudaError_t e = spnet_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, CL, ta, tb, td, epi, M, N, K, kbps,
                                      tiles_m, tiles_n, (int)units);
     if (e != cudaSuccess) {
         spnet_set_error("gemm_bf16: launch: %s", cudaGetErrorString(e));
@@ -475,15 +509,24 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
     if (rc) return rc;
     rc = make_operand_map(&tb, B, N, K, ldb, b_mn != 0, wide ? (pair ? 128 : 256) : 128);
     if (rc) return rc;
+    CUtensorMap td = ta;  // only read by the bf16-output epilogue
+    if (out_mode == OUT_BF16) {
+        PFN_cuTensorMapEncodeTiled enc = spnet_get_tensormap_encoder();
+        cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M}, strides[1] = {(cuuint64_t)ldd * 2};
+        cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+        CUresult r = enc(&td, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SPNET_REQUIRE(r == CUDA_SUCCESS, "gemm_bf16: cuTensorMapEncodeTiled (output) failed (%d) M=%d N=%d ldd=%lld", (int)r, M, N, ldd);
+    }
     GemmEpi epi = {D, ldd, out_mode, colstats};
 #define SPNET_GEMM_DISPATCH(BN_, CL_)                                                                    \
     do {                                                                                                 \
         if (a_mn) {                                                                                      \
-            if (b_mn) return launch_gemm<BN_, true, true, CL_>(ta, tb, epi, M, N, K, splits, stream);    \
-            return launch_gemm<BN_, true, false, CL_>(ta, tb, epi, M, N, K, splits, stream);             \
+            if (b_mn) return launch_gemm<BN_, true, true, CL_>(ta, tb, td, epi, M, N, K, splits, stream);    \
+            return launch_gemm<BN_, true, false, CL_>(ta, tb, td, epi, M, N, K, splits, stream);             \
         }                                                                                                \
-        if (b_mn) return launch_gemm<BN_, false, true, CL_>(ta, tb, epi, M, N, K, splits, stream);       \
-        return launch_gemm<BN_, false, false, CL_>(ta, tb, epi, M, N, K, splits, stream);                \
+        if (b_mn) return launch_gemm<BN_, false, true, CL_>(ta, tb, td, epi, M, N, K, splits, stream);       \
+        return launch_gemm<BN_, false, false, CL_>(ta, tb, td, epi, M, N, K, splits, stream);                \
     } while (0)
     if (pair) SPNET_GEMM_DISPATCH(256, 2);
     if (wide) SPNET_GEMM_DISPATCH(256, 1);
