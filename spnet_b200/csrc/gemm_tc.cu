@@ -105,9 +105,6 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the four epilogue warps only
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
 }
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 // Persistent, warp-specialised kernel. One CTA per SM walks work units (split, m-tile, n-tile):
 //   warp 0      TMA producer   : fills the STAGES-deep smem ring
@@ -288,8 +285,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const uint32_t as = u & 1u;
             mbar_wait(tfull0 + 8 * as, (u >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < M;
 #pragma unroll 1
             for (int c = chalf; c < BN / 32; c += kEpiWarps / 4) {
                 uint32_t v[32];
@@ -330,19 +325,34 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    if (row_ok) {
-                        float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldc + col0;
-                        if (epi.mode == OUT_F32) {
+                    // fp32 store / split-K accumulation through the same 2 KB staging box, 16 columns (64-byte
+                    // rows) at a time: TMA store, or TMA reduce-add into the fp32 gradient for OUT_ATOMIC_F32
+                    if (m0 + q * 32 < M) {  // warp-uniform
+                        const uint32_t stg = stage_out0 + (uint32_t)(warp - 2) * 2048u;
+                        const uint32_t rowaddr = stg + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
 #pragma unroll
-                            for (int g = 0; g < 8; ++g) {
-                                if (col0 + g * 4 < N)  // N % 4 == 0 is checked on the host
-                                    *reinterpret_cast<float4*>(o + g * 4) =
-                                        make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
-                            }
-                        } else {
+                        for (int h = 0; h < 2; ++h) {
+                            if (col0 + 16 * h >= N) break;  // warp-uniform
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            __syncwarp();
 #pragma unroll
-                            for (int g = 0; g < 8; ++g) {
-                                if (col0 + g * 4 < N) red_add_v4(o + g * 4, f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+                            for (int g = 0; g < 4; ++g)
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (((uint32_t)g ^ sw) << 4)),
+                                             "r"(v[16 * h + 4 * g]), "r"(v[16 * h + 4 * g + 1]), "r"(v[16 * h + 4 * g + 2]),
+                                             "r"(v[16 * h + 4 * g + 3])
+                                             : "memory");
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) {
+                                if (epi.mode == OUT_F32)
+                                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmD),
+                                                 "r"(stg), "r"(col0 + 16 * h), "r"(m0 + q * 32)
+                                                 : "memory");
+                                else
+                                    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmD),
+                                                 "r"(stg), "r"(col0 + 16 * h), "r"(m0 + q * 32)
+                                                 : "memory");
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                             }
                         }
                     }
@@ -509,7 +519,7 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
                   "gemm_bf16: pointers must be 16-byte aligned");
     SPNET_REQUIRE(out_mode >= 0 && out_mode <= 2, "gemm_bf16: bad out_mode %d", out_mode);
     SPNET_REQUIRE(out_mode != OUT_BF16 || (N % 8 == 0 && ldd % 8 == 0), "gemm_bf16: bf16 output needs N, ldd %% 8 == 0");
-    SPNET_REQUIRE(out_mode != OUT_F32 || (N % 4 == 0 && ldd % 4 == 0), "gemm_bf16: fp32 output needs N, ldd %% 4 == 0");
+    SPNET_REQUIRE(out_mode == OUT_BF16 || ldd % 4 == 0, "gemm_bf16: fp32 output needs ldd %% 4 == 0");
     const bool wide_ = N >= 512, pair_ = wide_ && M > BM && getenv("SPNET_B200_NO_CLUSTER") == nullptr;
     if (splits <= 0) {
         // auto split-K (atomic output only): fill the SMs (or SM pairs) once without spilling into a
@@ -537,13 +547,15 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
     if (rc) return rc;
     rc = make_operand_map(&tb, B, N, K, ldb, b_mn != 0, wide ? (pair ? 128 : 256) : 128);
     if (rc) return rc;
-    CUtensorMap td = ta;  // only read by the bf16-output epilogue
-    if (out_mode == OUT_BF16) {
+    CUtensorMap td;  // output boxes of the TMA-store epilogue: 32 x 32 bf16 or 32 x 16 fp32 (64-byte rows, SWIZZLE_64B)
+    {
         PFN_cuTensorMapEncodeTiled enc = spnet_get_tensormap_encoder();
-        cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M}, strides[1] = {(cuuint64_t)ldd * 2};
-        cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
-        CUresult r = enc(&td, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        const bool ob = out_mode == OUT_BF16;
+        cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M}, strides[1] = {(cuuint64_t)ldd * (ob ? 2 : 4)};
+        cuuint32_t box[2] = {ob ? 32u : 16u, 32u}, estr[2] = {1, 1};
+        CUresult r = enc(&td, ob ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, D, dims, strides, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SPNET_REQUIRE(r == CUDA_SUCCESS, "gemm_bf16: cuTensorMapEncodeTiled (output) failed (%d) M=%d N=%d ldd=%lld", (int)r, M, N, ldd);
     }
     GemmEpi epi = {D, ldd, out_mode, colstats};
