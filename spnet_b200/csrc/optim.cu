@@ -11,6 +11,18 @@
 namespace {
 
 // params live in one flat fp32 buffer; the L2-regularised tensors occupy [0, n_l2).
+// HBM-bound (28 B read+written per parameter + 2 B bf16 copy): 16-byte accesses, two independent
+// vectors per thread in flight. Buffers must be 16-byte aligned (8-byte for the bf16 copy).
+__device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v, bool reg, float l2x2, float lr_t,
+                                          float beta1, float beta2, float eps, float grad_scale) {
+    float gi = g * grad_scale;
+    if (reg) gi = fmaf(l2x2, p, gi);
+    m = beta1 * m + (1.0f - beta1) * gi;
+    v = beta2 * v + (1.0f - beta2) * gi * gi;
+    p -= lr_t * m / (sqrtf(v) + eps);
+    return p;
+}
+
 __global__ void __launch_bounds__(256) adam_keras_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                          float* __restrict__ m, float* __restrict__ v,
                                                          long long n, long long n_l2, float l2,
@@ -18,17 +30,44 @@ __global__ void __launch_bounds__(256) adam_keras_kernel(float* __restrict__ p, 
                                                          float beta2, float eps, float grad_scale,
                                                          bf16* __restrict__ p_bf16) {
     const float lr_t = *lr_t_ptr;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x) {
-        float pi = p[i];
-        float gi = g[i] * grad_scale;
-        if (i < n_l2) gi = fmaf(2.0f * l2, pi, gi);
-        const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
-        const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
-        pi -= lr_t * mi / (sqrtf(vi) + eps);
-        p[i] = pi;
-        m[i] = mi;
-        v[i] = vi;
+    const float l2x2 = 2.0f * l2;
+    const long long nv = n >> 2;  // float4 vectors
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < nv; i0 += 2 * stride) {
+        float4 pv[2], gv[2], mv[2], vv[2];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const long long i = i0 + u * stride;
+            ok[u] = i < nv;
+            if (ok[u]) {
+                pv[u] = reinterpret_cast<const float4*>(p)[i];
+                gv[u] = __ldcs(reinterpret_cast<const float4*>(g) + i);  // gradients are dead after this read
+                mv[u] = reinterpret_cast<const float4*>(m)[i];
+                vv[u] = reinterpret_cast<const float4*>(v)[i];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!ok[u]) continue;
+            const long long i = i0 + u * stride;
+            const long long e = 4 * i;
+            adam_one(pv[u].x, gv[u].x, mv[u].x, vv[u].x, e < n_l2, l2x2, lr_t, beta1, beta2, eps, grad_scale);
+            adam_one(pv[u].y, gv[u].y, mv[u].y, vv[u].y, e + 1 < n_l2, l2x2, lr_t, beta1, beta2, eps, grad_scale);
+            adam_one(pv[u].z, gv[u].z, mv[u].z, vv[u].z, e + 2 < n_l2, l2x2, lr_t, beta1, beta2, eps, grad_scale);
+            adam_one(pv[u].w, gv[u].w, mv[u].w, vv[u].w, e + 3 < n_l2, l2x2, lr_t, beta1, beta2, eps, grad_scale);
+            reinterpret_cast<float4*>(p)[i] = pv[u];
+            reinterpret_cast<float4*>(m)[i] = mv[u];
+            reinterpret_cast<float4*>(v)[i] = vv[u];
+            if (p_bf16)
+                reinterpret_cast<uint2*>(p_bf16)[i] = make_uint2(pack_bf16x2(pv[u].x, pv[u].y), pack_bf16x2(pv[u].z, pv[u].w));
+        }
+    }
+    // tail (n not a multiple of 4: never the case for the engine's padded buffers)
+    for (long long i = 4 * nv + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float pi = p[i], mi = m[i], vi = v[i];
+        adam_one(pi, g[i], mi, vi, i < n_l2, l2x2, lr_t, beta1, beta2, eps, grad_scale);
+        p[i] = pi; m[i] = mi; v[i] = vi;
         if (p_bf16) p_bf16[i] = __float2bfloat16_rn(pi);
     }
 }
@@ -36,7 +75,12 @@ __global__ void __launch_bounds__(256) adam_keras_kernel(float* __restrict__ p, 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ p, long long n, float scale,
                                                     float* __restrict__ out) {
     float s = 0.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+    const long long nv = n >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+        const float4 q = reinterpret_cast<const float4*>(p)[i];
+        s = fmaf(q.x, q.x, s); s = fmaf(q.y, q.y, s); s = fmaf(q.z, q.z, s); s = fmaf(q.w, q.w, s);
+    }
+    for (long long i = 4 * nv + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x)
         s = fmaf(p[i], p[i], s);
     __shared__ float red[8];
@@ -89,6 +133,8 @@ int spnet_adam_keras_step(float* p, const float* g, float* m, float* v, long lon
                           const float* lr_t_dev, float beta1, float beta2, float eps, float grad_scale,
                           void* p_bf16, cudaStream_t stream) {
     SPNET_REQUIRE(p && g && m && v && lr_t_dev && n > 0 && n_l2 >= 0 && n_l2 <= n, "adam_keras_step: bad args");
+    SPNET_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0 && ((uintptr_t)p_bf16 & 7) == 0,
+                  "adam_keras_step: buffers must be 16-byte aligned");
     adam_keras_kernel<<<grid_for(n), 256, 0, stream>>>(p, g, m, v, n, n_l2, l2, lr_t_dev, beta1, beta2, eps,
                                                       grad_scale, reinterpret_cast<bf16*>(p_bf16));
     return spnet_check_launch("adam_keras_step");
@@ -96,7 +142,7 @@ int spnet_adam_keras_step(float* p, const float* g, float* m, float* v, long lon
 
 // *out += scale * sum(p^2)
 int spnet_sumsq(const float* p, long long n, float scale, float* out, cudaStream_t stream) {
-    SPNET_REQUIRE(p && out && n > 0, "sumsq: bad args");
+    SPNET_REQUIRE(p && out && n > 0 && ((uintptr_t)p & 15) == 0, "sumsq: bad args (p must be 16-byte aligned)");
     sumsq_kernel<<<grid_for(n), 256, 0, stream>>>(p, n, scale, out);
     return spnet_check_launch("sumsq");
 }
