@@ -8,7 +8,7 @@
 //
 // All kernels share one structure: a persistent CTA walks output tiles; the input window of a tile
 // is loaded cooperatively (contiguous, coalesced element loads), transformed ONCE (BN affine +
-// activation, zero padding applied after it) and parked in shared memory as planar fp32, so the
+// activation, zero padding applied after it) and parked in shared memory as fp32, so the
 // per-pixel work is conflict-free LDS + FMA with no address arithmetic; 3-channel outputs go back
 // through shared memory so that global stores are contiguous too. BatchNorm statistics and weight
 // gradients are accumulated in registers across all tiles of a CTA and reduced once at the end.
@@ -24,45 +24,67 @@ __device__ __forceinline__ float apply_act(float y, int act) {
 
 constexpr int kThreads = 256;
 
-// Input window of an output tile -> planar fp32 shared memory sm[ci][r][c] (row pitch IWP),
-// transformed by act(a*v+b); out-of-image elements are zero (padding follows the activation).
-// Two phases so that the global loads of the NEXT tile are in flight while the current tile is
-// computed: fetch() = coalesced element loads into registers, commit() = transform + park in smem.
-template <typename TI, int CIN, int IH_T, int IW_T, int IWP>
+// Input window of an output tile -> fp32 shared memory sm[r][c*CIN + ci] (row pitch ROWP, the same
+// interleaved order as global memory), transformed by act(a*v+b); out-of-image elements are zero
+// (padding follows the activation). Two phases so that the global loads of the NEXT tile are in
+// flight while the current tile is computed: fetch() = coalesced element loads into registers,
+// commit() = transform + park in smem. Warp w owns rows w, w+8, ..., a lane owns every 32nd element
+// of a row, so no per-element division is needed and all predicates are compares.
+template <typename TI, int CIN, int IH_T, int IW_T>
 struct Window {
-    static constexpr int ROW_E = IW_T * CIN, N = IH_T * ROW_E, PER = (N + kThreads - 1) / kThreads;
-    TI raw[PER];
-    unsigned ok;
+    static constexpr int ROW_E = IW_T * CIN, ROWP = ROW_E + 1;
+    static constexpr int RPW = (IH_T + 7) / 8, EPL = (ROW_E + 31) / 32;
+    TI raw[RPW * EPL];
     __device__ __forceinline__ void fetch(const TI* __restrict__ img, int H, int W, int ih0, int iw0) {
-        ok = 0u;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int e_lo = max(0, -iw0) * CIN, e_hi = min(IW_T, W - iw0) * CIN;
 #pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            const int idx = threadIdx.x + k * kThreads;
-            const int r = idx / ROW_E, e = idx - r * ROW_E;
-            const int c = e / CIN;
-            const int ih = ih0 + r, iw = iw0 + c;
-            if (idx < N && ih >= 0 && ih < H && iw >= 0 && iw < W) {
-                raw[k] = img[((size_t)ih * W + iw0) * CIN + e];
-                ok |= 1u << k;
+        for (int i = 0; i < RPW; ++i) {
+            const int r = warp + 8 * i, ih = ih0 + r;
+            const bool rowok = r < IH_T && ih >= 0 && ih < H;
+            const TI* rowp = img + ((long long)ih * W + iw0) * CIN;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) {
+                const int e = lane + 32 * j;
+                if (rowok && e >= e_lo && e < e_hi) raw[i * EPL + j] = rowp[e];
             }
         }
     }
-    __device__ __forceinline__ void commit(float* __restrict__ sm, const float* sab, bool affine, int act) const {
+    __device__ __forceinline__ void commit(float* __restrict__ sm, const float* sab, bool affine, int act, int H, int W,
+                                           int ih0, int iw0) const {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int e_lo = max(0, -iw0) * CIN, e_hi = min(IW_T, W - iw0) * CIN;
+        const int l3 = lane % CIN;
 #pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            const int idx = threadIdx.x + k * kThreads;
-            if (idx >= N) break;
-            const int r = idx / ROW_E, e = idx - r * ROW_E;
-            const int c = e / CIN, ci = e - c * CIN;
-            float v = 0.f;
-            if (ok & (1u << k)) {
-                v = to_f32(raw[k]);
-                if (affine) v = apply_act(fmaf(v, sab[ci], sab[CIN + ci]), act);
+        for (int i = 0; i < RPW; ++i) {
+            const int r = warp + 8 * i, ih = ih0 + r;
+            if (r >= IH_T) break;
+            const bool rowok = ih >= 0 && ih < H;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) {
+                const int e = lane + 32 * j;
+                if (e >= ROW_E) break;
+                int ci = l3 + (32 * j) % CIN;
+                if (ci >= CIN) ci -= CIN;
+                float v = 0.f;
+                if (rowok && e >= e_lo && e < e_hi) {
+                    v = to_f32(raw[i * EPL + j]);
+                    if (affine) v = apply_act(fmaf(v, sab[ci], sab[CIN + ci]), act);
+                }
+                sm[r * ROWP + e] = v;
             }
-            sm[(ci * IH_T + r) * IWP + c] = v;
         }
     }
 };
+
+// rows of a tile -> global memory: warp w copies rows w, w+8, ... (row_e contiguous elements each)
+template <typename T>
+__device__ __forceinline__ void copy_rows_out(T* __restrict__ dst, long long dst_pitch, const T* __restrict__ src, int src_pitch,
+                                              int rows, int row_e) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < rows; r += 8)
+        for (int e = lane; e < row_e; e += 32) dst[r * dst_pitch + e] = src[r * src_pitch + e];
+}
 
 struct TileXY { int b, r0, c0; };
 __device__ __forceinline__ TileXY tile_xy(int tile, int tiles_h, int tiles_w, int TH, int TW) {
@@ -94,9 +116,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_kernel(const TI* __restr
                                                                const float* __restrict__ mask_b, int B, int H, int W,
                                                                int OH, int OW, int pt, int pl, int tiles_h, int tiles_w) {
     constexpr int COUT = 3, TH = C3_TH, TW = C3_TW;
-    constexpr int IH_T = (TH - 1) * S + KS, IW_T = (TW - 1) * S + KS, IWP = IW_T + 1;
+    constexpr int IH_T = (TH - 1) * S + KS, IW_T = (TW - 1) * S + KS;
+    typedef Window<TI, CIN, IH_T, IW_T> Win;
+    constexpr int ROWP = Win::ROWP;
     constexpr int NW = KS * KS * CIN * COUT;
-    __shared__ float s_in[CIN * IH_T * IWP];
+    __shared__ float s_in[IH_T * ROWP];
     __shared__ __align__(16) float ws[KS * KS * CIN * 4];  // [tap][ci][co padded to 4]
     __shared__ float sab[2 * CIN + 2 * COUT];
     __shared__ TO s_out[TH * TW * COUT];
@@ -121,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_kernel(const TI* __restr
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     float ssum[COUT] = {0.f, 0.f, 0.f}, ssq[COUT] = {0.f, 0.f, 0.f};
     const int n_tiles = B * tiles_h * tiles_w;
-    Window<TI, CIN, IH_T, IW_T, IWP> win;
+    Win win;
     if ((int)blockIdx.x < n_tiles) {
         const TileXY t = tile_xy(blockIdx.x, tiles_h, tiles_w, TH, TW);
         win.fetch(in + (size_t)t.b * H * W * CIN, H, W, t.r0 * S - pt, t.c0 * S - pl);
@@ -130,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_kernel(const TI* __restr
         const TileXY tc = tile_xy(tile, tiles_h, tiles_w, TH, TW);
         const int oh0 = tc.r0, ow0 = tc.c0, b = tc.b;
         __syncthreads();  // previous tile: compute is done with s_in, copy-out is done with s_out
-        win.commit(s_in, sab, in_a != nullptr, act);
+        win.commit(s_in, sab, in_a != nullptr, act, H, W, oh0 * S - pt, ow0 * S - pl);
         __syncthreads();
         if (tile + (int)gridDim.x < n_tiles) {  // next tile's loads fly during this tile's compute
             const TileXY t = tile_xy(tile + gridDim.x, tiles_h, tiles_w, TH, TW);
@@ -154,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_kernel(const TI* __restr
                     const float4 wv = *reinterpret_cast<const float4*>(&ws[((kh * KS + kw) * CIN + ci) * 4]);
 #pragma unroll
                     for (int pp = 0; pp < PP; ++pp) {
-                        const float v = s_in[(ci * IH_T + (ty + 4 * pp) * S + kh) * IWP + tx * S + kw];
+                        const float v = s_in[((ty + 4 * pp) * S + kh) * ROWP + (tx * S + kw) * CIN + ci];
                         if (MODE == 1 && (kh == 1 || kh == 2) && (kw == 1 || kw == 2)) centre[pp] += v;
                         acc[pp][0] = fmaf(v, wv.x, acc[pp][0]);
                         acc[pp][1] = fmaf(v, wv.y, acc[pp][1]);
@@ -189,17 +213,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_kernel(const TI* __restr
         __syncthreads();
         // contiguous row segments of the output tile
         const int vw = min(TW, OW - ow0), vh = min(TH, OH - oh0);
-        const int row_e = vw * COUT;
-        for (int idx = threadIdx.x; idx < vh * row_e; idx += kThreads) {
-            const int r = idx / row_e, e = idx - r * row_e;
-            out[(((size_t)b * OH + oh0 + r) * OW + ow0) * COUT + e] = s_out[r * TW * COUT + e];
-        }
-        if (MODE == 1) {
-            for (int idx = threadIdx.x; idx < vh * vw; idx += kThreads) {
-                const int r = idx / vw, e = idx - r * vw;
-                skip[((size_t)b * OH + oh0 + r) * OW + ow0 + e] = s_skip[r * TW + e];
-            }
-        }
+        copy_rows_out(out + (((size_t)b * OH + oh0) * OW + ow0) * COUT, (long long)OW * COUT, s_out, TW * COUT, vh, vw * COUT);
+        if (MODE == 1) copy_rows_out(skip + ((size_t)b * OH + oh0) * OW + ow0, (long long)OW, s_skip, TW, vh, vw);
     }
     if (stats) {
         __syncthreads();
@@ -225,8 +240,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_b1c1_fwd_kernel(const T* __r
                                                                     int B, int H, int W, int OH, int OW, int tiles_h,
                                                                     int tiles_w) {
     constexpr int CIN = 3, COUT = 32, KS = 3, S = 2, TH = 4, TW = 64;
-    constexpr int IH_T = (TH - 1) * S + KS, IW_T = (TW - 1) * S + KS, IWP = IW_T + 2;
-    __shared__ float s_in[CIN * IH_T * IWP];
+    constexpr int IH_T = (TH - 1) * S + KS, IW_T = (TW - 1) * S + KS;
+    typedef Window<T, CIN, IH_T, IW_T> Win;
+    constexpr int ROWP = Win::ROWP;
+    __shared__ float s_in[IH_T * ROWP];
     __shared__ __align__(16) float ws[KS * KS * CIN * COUT];
     __shared__ float sab[2 * CIN];
     __shared__ float sred[2 * COUT];
@@ -239,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_b1c1_fwd_kernel(const T* __r
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6, lane = threadIdx.x & 31;
     float cs = 0.f, cq = 0.f;  // running per-channel sums: channel = lane
     const int n_tiles = B * tiles_h * tiles_w;
-    Window<T, CIN, IH_T, IW_T, IWP> win;
+    Win win;
     if ((int)blockIdx.x < n_tiles) {
         const TileXY t = tile_xy(blockIdx.x, tiles_h, tiles_w, TH, TW);
         win.fetch(in + (size_t)t.b * H * W * CIN, H, W, t.r0 * S, t.c0 * S);
@@ -248,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_b1c1_fwd_kernel(const T* __r
         const TileXY tc = tile_xy(tile, tiles_h, tiles_w, TH, TW);
         const int oh0 = tc.r0, ow0 = tc.c0, b = tc.b;
         __syncthreads();  // previous tile's readers are done with s_in
-        win.commit(s_in, sab, in_a != nullptr, act);
+        win.commit(s_in, sab, in_a != nullptr, act, H, W, oh0 * S, ow0 * S);
         __syncthreads();
         if (tile + (int)gridDim.x < n_tiles) {
             const TileXY t = tile_xy(tile + gridDim.x, tiles_h, tiles_w, TH, TW);
@@ -265,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_b1c1_fwd_kernel(const T* __r
             for (int kw = 0; kw < KS; ++kw)
 #pragma unroll
                 for (int ci = 0; ci < CIN; ++ci) {
-                    const float v = s_in[(ci * IH_T + ty * S + kh) * IWP + tx * S + kw];
+                    const float v = s_in[(ty * S + kh) * ROWP + (tx * S + kw) * CIN + ci];
                     const float4* wr = reinterpret_cast<const float4*>(&ws[((kh * KS + kw) * CIN + ci) * COUT]);
 #pragma unroll
                     for (int c4 = 0; c4 < COUT / 4; ++c4) {
@@ -409,11 +426,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_b1c1_dgrad_kernel(const T* _
         }
         __syncthreads();
         const int vw = min(TW, W - iw0), vh = min(TH, H - ih0);
-        const int row_e = vw * CIN;
-        for (int idx = threadIdx.x; idx < vh * row_e; idx += kThreads) {
-            const int r = idx / row_e, e = idx - r * row_e;
-            gin[(((size_t)b * H + ih0 + r) * W + iw0) * CIN + e] = s_out[r * TW * CIN + e];
-        }
+        copy_rows_out(gin + (((size_t)b * H + ih0) * W + iw0) * CIN, (long long)W * CIN, s_out, TW * CIN, vh, vw * CIN);
     }
 }
 
@@ -429,11 +442,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_wgrad_kernel(const TI* _
                                                                      int B, int H, int W, int OH, int OW, int pt,
                                                                      int pl, int tiles_h, int tiles_w) {
     constexpr int COUT = 3, TH = C3W_TH, TW = C3_TW;
-    constexpr int IH_T = (TH - 1) * S + KS, IW_T = (TW - 1) * S + KS, IWP = IW_T + 1;
+    constexpr int IH_T = (TH - 1) * S + KS, IW_T = (TW - 1) * S + KS;
+    typedef Window<TI, CIN, IH_T, IW_T> Win;
+    constexpr int ROWP = Win::ROWP;
     constexpr int NW = KS * KS * CIN * COUT;
-    constexpr int NG = TH * TW * COUT, GPER = NG / kThreads;
-    __shared__ float s_in[CIN * IH_T * IWP];
-    __shared__ float s_g[COUT * TH * TW];
+    constexpr int GROW = TW * COUT, GPITCH = GROW + 1, GEPL = GROW / 32;  // gradient tile: one row per warp (TH == 8)
+    static_assert(TH == 8 && GROW % 32 == 0, "gradient tile mapping");
+    __shared__ float s_in[IH_T * ROWP];
+    __shared__ float s_g[TH * GPITCH];
     __shared__ float sab[2 * CIN];
     __shared__ float sacc[NW];
     if (threadIdx.x < CIN) {
@@ -442,35 +458,33 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_wgrad_kernel(const TI* _
     }
     for (int i = threadIdx.x; i < NW; i += kThreads) sacc[i] = 0.f;
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float acc[NW];
 #pragma unroll
     for (int i = 0; i < NW; ++i) acc[i] = 0.f;
     const int n_tiles = B * tiles_h * tiles_w;
-    Window<TI, CIN, IH_T, IW_T, IWP> win;
-    TG graw[GPER];
+    Win win;
+    TG graw[GEPL];
     auto fetch = [&](int tile) {
         const TileXY t = tile_xy(tile, tiles_h, tiles_w, TH, TW);
         win.fetch(in + (size_t)t.b * H * W * CIN, H, W, t.r0 * S - pt, t.c0 * S - pl);
+        const int oh = t.r0 + warp;  // gradient row of this warp
+        const int e_hi = min(TW, OW - t.c0) * COUT;
+        const TG* rowp = g + (((size_t)t.b * OH + oh) * OW + t.c0) * COUT;
 #pragma unroll
-        for (int k = 0; k < GPER; ++k) {
-            const int idx = threadIdx.x + k * kThreads;
-            const int r = idx / (TW * COUT), e = idx - r * (TW * COUT);
-            const int oh = t.r0 + r, ow = t.c0 + e / COUT;
-            graw[k] = from_f32<TG>(0.f);
-            if (oh < OH && ow < OW) graw[k] = g[(((size_t)t.b * OH + oh) * OW + t.c0) * COUT + e];
+        for (int j = 0; j < GEPL; ++j) {
+            const int e = lane + 32 * j;
+            graw[j] = from_f32<TG>(0.f);
+            if (oh < OH && e < e_hi) graw[j] = rowp[e];
         }
     };
     if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const TileXY tc = tile_xy(tile, tiles_h, tiles_w, TH, TW);
         __syncthreads();
-        win.commit(s_in, sab, in_a != nullptr, act);
+        win.commit(s_in, sab, in_a != nullptr, act, H, W, tc.r0 * S - pt, tc.c0 * S - pl);
 #pragma unroll
-        for (int k = 0; k < GPER; ++k) {  // gradient tile, planar
-            const int idx = threadIdx.x + k * kThreads;
-            const int r = idx / (TW * COUT), e = idx - r * (TW * COUT);
-            const int c = e / COUT, co = e - c * COUT;
-            s_g[(co * TH + r) * TW + c] = to_f32(graw[k]);
-        }
+        for (int j = 0; j < GEPL; ++j) s_g[warp * GPITCH + lane + 32 * j] = to_f32(graw[j]);  // zero outside the output
         __syncthreads();
         if (tile + (int)gridDim.x < n_tiles) fetch(tile + gridDim.x);
 #pragma unroll 1
@@ -478,14 +492,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_wgrad_kernel(const TI* _
             const int r = ty + 4 * pp;
             float gv[COUT];
 #pragma unroll
-            for (int co = 0; co < COUT; ++co) gv[co] = s_g[(co * TH + r) * TW + tx];
+            for (int co = 0; co < COUT; ++co) gv[co] = s_g[r * GPITCH + tx * COUT + co];
 #pragma unroll
             for (int kh = 0; kh < KS; ++kh)
 #pragma unroll
                 for (int kw = 0; kw < KS; ++kw)
 #pragma unroll
                     for (int ci = 0; ci < CIN; ++ci) {
-                        const float v = s_in[(ci * IH_T + r * S + kh) * IWP + tx * S + kw];
+                        const float v = s_in[(r * S + kh) * ROWP + (tx * S + kw) * CIN + ci];
 #pragma unroll
                         for (int co = 0; co < COUT; ++co)
                             acc[((kh * KS + kw) * CIN + ci) * COUT + co] =
@@ -515,11 +529,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_b1c1_wgrad_kernel(const T* _
                                                                       int B, int H, int W, int OH, int OW, int tiles_h,
                                                                       int tiles_w) {
     constexpr int CIN = 3, COUT = 32, KS = 3, S = 2, TH = 4, TW = 32;
-    constexpr int IH_T = (TH - 1) * S + KS, IW_T = (TW - 1) * S + KS, IWP = IW_T + 2;
+    constexpr int IH_T = (TH - 1) * S + KS, IW_T = (TW - 1) * S + KS;
+    typedef Window<T, CIN, IH_T, IW_T> Win;
+    constexpr int ROWP = Win::ROWP;
     constexpr int GP = COUT + 4;
     constexpr int NT = KS * KS * CIN;  // 27
     constexpr int NV = TH * TW * (COUT / 4), GPER = NV / kThreads;
-    __shared__ float s_in[CIN * IH_T * IWP];
+    __shared__ float s_in[IH_T * ROWP];
     __shared__ __align__(16) float s_g[TH * TW * GP];
     __shared__ float sab[2 * CIN];
     __shared__ float sacc[NT * COUT];
@@ -536,7 +552,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_b1c1_wgrad_kernel(const T* _
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
     const int n_tiles = B * tiles_h * tiles_w;
-    Window<T, CIN, IH_T, IW_T, IWP> win;
+    Win win;
     G4<T> graw[GPER];
     auto fetch = [&](int tile) {
         const TileXY t = tile_xy(tile, tiles_h, tiles_w, TH, TW);
@@ -553,8 +569,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_b1c1_wgrad_kernel(const T* _
     };
     if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const TileXY tc = tile_xy(tile, tiles_h, tiles_w, TH, TW);
         __syncthreads();
-        win.commit(s_in, sab, in_a != nullptr, act);
+        win.commit(s_in, sab, in_a != nullptr, act, H, W, tc.r0 * S, tc.c0 * S);
 #pragma unroll
         for (int k = 0; k < GPER; ++k) {
             const int idx = threadIdx.x + k * kThreads;
@@ -574,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_b1c1_wgrad_kernel(const T* _
                 for (int kw = 0; kw < KS; ++kw)
 #pragma unroll
                     for (int ci = 0; ci < CIN; ++ci) {
-                        const float v = s_in[(ci * IH_T + r * S + kh) * IWP + c * S + kw];
+                        const float v = s_in[(r * S + kh) * ROWP + (c * S + kw) * CIN + ci];
                         const int t = (kh * KS + kw) * CIN + ci;
                         acc[t][0] = fmaf(v, gv.x, acc[t][0]);
                         acc[t][1] = fmaf(v, gv.y, acc[t][1]);
