@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256, 3) bn_apply_kernel(const T* z, const floa
 // If relu_a is given, g is first masked in place by (relu_a*z+relu_b > 0) (act 1) or scaled
 // by the leaky slope (act 2): the gradient of the activation that followed this BN.
 template <typename T, bool MASKED>
-__global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(T* __restrict__ g, const T* __restrict__ z,
+__global__ void __launch_bounds__(512, 1) bn_bwd_reduce_kernel(T* __restrict__ g, const T* __restrict__ z,
                                                                const float* __restrict__ mean,
                                                                const float* __restrict__ rstd,
                                                                const float* __restrict__ relu_a,
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(T* __restrict__ g
             }
         }
     }
-    __shared__ float red[2][256 * 8];
+    __shared__ float red[2][512 * 8];
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
         red[0][threadIdx.x * V + 2 * i] = s1[i].x; red[0][threadIdx.x * V + 2 * i + 1] = s1[i].y;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(T* __restrict__ g
 // stats[c] += sum z, stats[C+c] += sum z^2 over the rows (batch statistics of a tensor whose producer
 // has no statistics epilogue)
 template <typename T>
-__global__ void __launch_bounds__(256, 3) colstats_kernel(const T* __restrict__ z, double* __restrict__ stats,
+__global__ void __launch_bounds__(512, 1) colstats_kernel(const T* __restrict__ z, double* __restrict__ stats,
                                                           long long rows, int C, int cvb, int krows) {
     constexpr int V = VecN<T>::N, NP = RawVec<T>::NP;
     pdl_trigger();
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256, 3) colstats_kernel(const T* __restrict__ 
             }
         }
     }
-    __shared__ float red[2][256 * 8];
+    __shared__ float red[2][512 * 8];
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
         red[0][threadIdx.x * V + 2 * i] = s1[i].x; red[0][threadIdx.x * V + 2 * i + 1] = s1[i].y;
@@ -421,6 +421,23 @@ static ChanGrid chan_grid(int CV, long long rows, int ctas_per_sm) {
     return c;
 }
 
+// Reductions end with fp64 atomics per channel from every CTA, and that tail is serialised per address:
+// one fat CTA per SM (up to 512 threads) keeps the chains 148 deep instead of 444 (the 12288 x 728
+// reduce took 29 us next to 12 us for the dz kernel that moves more bytes).
+static ChanGrid chan_grid_reduce(int CV, long long rows) {
+    ChanGrid c;
+    const int nchunks = ceil_div(CV, 128);
+    c.cvb = ceil_div(CV, nchunks);
+    c.krows = 512 / c.cvb;
+    if (c.krows < 1) c.krows = 1;
+    long long gx = (rows + (long long)c.krows * 2 * UNROLL - 1) / ((long long)c.krows * 2 * UNROLL);
+    const long long cap = 148 / nchunks > 0 ? 148 / nchunks : 1;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    c.grid = dim3((unsigned)gx, nchunks);
+    return c;
+}
+
 int check_rc(const char* who, int dtype, long long rows, int C) {
     SPNET_REQUIRE(rows > 0 && C > 0, "%s: bad shape", who);
     const int V = dtype == SPNET_BF16 ? 8 : 4;
@@ -473,7 +490,7 @@ int spnet_bn_bwd_reduce(void* g, const void* z, const float* save_mean, const fl
     if (rc) return rc;
     SPNET_REQUIRE(g && z && save_mean && save_rstd && stats, "bn_bwd_reduce: null pointer");
     SPNET_REQUIRE((relu_a == nullptr) == (relu_b == nullptr), "bn_bwd_reduce: mask affine comes in pairs");
-    const ChanGrid cg = chan_grid(C / (dtype == SPNET_BF16 ? 8 : 4), rows, 3);
+    const ChanGrid cg = chan_grid_reduce(C / (dtype == SPNET_BF16 ? 8 : 4), rows);
     if (relu_a) {
         SPNET_DISPATCH_DTYPE(dtype, (spnet_launch_pdl(bn_bwd_reduce_kernel<T, true>, cg.grid, dim3(cg.cvb * cg.krows), 0,
                                                       stream, 1, reinterpret_cast<T*>(g), reinterpret_cast<const T*>(z),
@@ -493,7 +510,7 @@ int spnet_colstats(const void* z, double* stats, int dtype, long long rows, int 
     int rc = check_rc("colstats", dtype, rows, C);
     if (rc) return rc;
     SPNET_REQUIRE(z && stats, "colstats: null pointer");
-    const ChanGrid cg = chan_grid(C / (dtype == SPNET_BF16 ? 8 : 4), rows, 3);
+    const ChanGrid cg = chan_grid_reduce(C / (dtype == SPNET_BF16 ? 8 : 4), rows);
     SPNET_DISPATCH_DTYPE(dtype, (spnet_launch_pdl(colstats_kernel<T>, cg.grid, dim3(cg.cvb * cg.krows), 0, stream, 1,
                                                   reinterpret_cast<const T*>(z), stats, rows, C, cg.cvb, cg.krows)));
     return spnet_check_launch("colstats");

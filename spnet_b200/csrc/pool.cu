@@ -47,21 +47,29 @@ __global__ void __launch_bounds__(256) maxpool_add_fwd_kernel(const T* __restric
         best[i] = -INFINITY;
         arg[i] = 0;
     }
+    // all nine loads are issued before the first compare (clamped addresses + validity flags): the
+    // kernel is latency-bound, branches around the loads would serialise them
+    float v[9][V];
+    bool ok[9];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
         const int ih = oh * 2 - pt + kh;
-        if (ih < 0 || ih >= H) continue;
+        const int ihc = min(max(ih, 0), H - 1);
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
             const int iw = ow * 2 - pl + kw;
-            if (iw < 0 || iw >= W) continue;
-            float v[V];
-            load_vec(z + (((size_t)bi * H + ih) * W + iw) * C + c0, v);
+            const int iwc = min(max(iw, 0), W - 1);
+            ok[kh * 3 + kw] = ih == ihc && iw == iwc;
+            load_vec(z + (((size_t)bi * H + ihc) * W + iwc) * C + c0, v[kh * 3 + kw]);
+        }
+    }
 #pragma unroll
-            for (int i = 0; i < V; ++i) {
-                const float y = fmaf(v[i], av[i], bv[i]);
-                if (y > best[i]) { best[i] = y; arg[i] = kh * 3 + kw; }
-            }
+    for (int t = 0; t < 9; ++t) {
+        if (!ok[t]) continue;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float y = fmaf(v[t][i], av[i], bv[i]);
+            if (y > best[i]) { best[i] = y; arg[i] = t; }
         }
     }
     if (res) {
@@ -99,35 +107,45 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ 
     float acc[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    // candidate windows: oh in {(h+pt-kh)/2} for the kh that make it integral (at most two), same for ow;
+    // loads first (clamped, flagged), compares after
+    float g[4][V];
+    uint32_t am[4][2];
+    int code[4];
+    bool ok[4];
+    int nc = 0;
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-        const int t = h + pt - kh;  // = 2*oh
-        if (t < 0 || (t & 1)) continue;
+    for (int a = 0; a < 2; ++a) {
+        // kh candidates with (h + pt - kh) even: kh = (h+pt)&1, and that + 2 (if <= 2)
+        const int kh = ((h + pt) & 1) + 2 * a;
+        const int t = h + pt - kh;
         const int oh = t >> 1;
-        if (oh >= OH) continue;
+        const bool okh = kh <= 2 && t >= 0 && oh < OH;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
+        for (int bb = 0; bb < 2; ++bb) {
+            const int kw = ((w + pl) & 1) + 2 * bb;
             const int u = w + pl - kw;
-            if (u < 0 || (u & 1)) continue;
             const int ow = u >> 1;
-            if (ow >= OW) continue;
-            const size_t o = (((size_t)bi * OH + oh) * OW + ow) * C + c0;
-            float g[V];
-            load_vec(gout + o, g);
-            const int code = kh * 3 + kw;
+            const bool okw = kw <= 2 && u >= 0 && ow < OW;
+            ok[nc] = okh && okw;
+            code[nc] = kh * 3 + kw;
+            const size_t o = (((size_t)bi * OH + (okh ? oh : 0)) * OW + (okw ? ow : 0)) * C + c0;
+            load_vec(gout + o, g[nc]);
             if (V == 8) {
-                const uint2 am = *reinterpret_cast<const uint2*>(argmax + o);
-                const uint32_t wds[2] = {am.x, am.y};
-#pragma unroll
-                for (int i = 0; i < V; ++i)
-                    if ((int)((wds[i >> 2] >> (8 * (i & 3))) & 0xffu) == code) acc[i] += g[i];
+                const uint2 q = *reinterpret_cast<const uint2*>(argmax + o);
+                am[nc][0] = q.x; am[nc][1] = q.y;
             } else {
-                const uint32_t am = *reinterpret_cast<const uint32_t*>(argmax + o);
-#pragma unroll
-                for (int i = 0; i < V; ++i)
-                    if ((int)((am >> (8 * i)) & 0xffu) == code) acc[i] += g[i];
+                am[nc][0] = *reinterpret_cast<const uint32_t*>(argmax + o); am[nc][1] = 0;
             }
+            ++nc;
         }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!ok[k]) continue;
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+            if ((int)((am[k][i >> 2] >> (8 * (i & 3))) & 0xffu) == code[k]) acc[i] += g[k][i];
     }
     store_vec(gin + idx * V, acc);
 }
