@@ -296,6 +296,10 @@ def run_ours(args, rank, world):
         fams["dwconv_fwd"][2].append(("spnet_dwconv3x3_fwd", a))
     for a, _ in one_step.get("spnet_dwconv3x3_bwd_fused", []):
         fams["dwconv_bwd"][2].append(("spnet_dwconv3x3_bwd_fused", a))
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1", "traffic.json")))
+    except Exception:
+        traffic = {}
     roofs = {}
     for key, (bound, label, calls) in fams.items():
         if not calls:
@@ -304,7 +308,8 @@ def run_ours(args, rank, world):
         nb = sum(algorithmic_work(n, a)[0] for n, a in calls)
         nf = sum(algorithmic_work(n, a)[1] for n, a in calls)
         r = {"bound": bound, "kernel": label, "launches": len(calls), "avg_launch_ms": us * 1e-3,
-             "traffic": None, "timing": "CUDA-graph replay of the family's launches of one step, CUDA events"}
+             "traffic": traffic.get(key, {}).get("bytes_per_launch"), "traffic_source": traffic.get(key, {}).get("source"),
+             "timing": "CUDA-graph replay of the family's launches of one step, CUDA events"}
         t_s = us * 1e-6 * len(calls)
         if bound == "hbm":
             ach = nb / t_s / 1e9
