@@ -141,6 +141,29 @@ def test_network_structure_pins():
     assert 0.09 < 1e-4 * float((wd.astype(np.float64) ** 2).sum()) < 0.13
 
 
+def test_mobilenet_structure_pins():
+    """keras.applications.mobilenet.MobileNet(alpha=1, include_top=False) @ Keras 2.1.3: 3,228,864 parameters
+    (SURVEY.md section 2.2); the engine's spec and the oracle's spec must describe the same tensors."""
+    from spnet_b200 import arch
+    spec = xt.mobilenet_spnet_spec(384, 512)
+    bb = [int(np.prod(s)) for l, w, s, t, r in spec if l.startswith(("conv1", "conv_dw", "conv_pw"))]
+    assert sum(bb) == 3228864
+    assert xt.mobilenet_feature_hw(384, 512) == (6, 8)
+    eng = arch.mobilenet_param_spec(384, 512)
+    assert [(k, tuple(s)) for k, s, _, _ in eng] == [(l + "/" + w, tuple(s)) for l, w, s, _, _ in spec]
+    assert [k for k, _, _, r in eng if r] == [l + "/" + w for l, w, _, _, r in spec if r]
+    assert arch.count_params(eng) == xt.count_params(spec)
+    l2 = sorted(l for l, w, s, t, r in spec if r)
+    assert l2 == sorted(["conv2d_1", "conv2d_2", "conv2d_3", "conv1", "FinalOutput"] + ["conv_pw_%d" % i for i in range(1, 14)])
+    import torch
+    m = xt.OracleMobileNetSPNet(xt.init_weights(xt.mobilenet_spnet_spec(64, 64)), 64, 64)
+    with torch.no_grad():
+        y = m.forward(np.zeros((1, 64, 64, 1), np.float32))
+    assert tuple(y.shape) == (1, 576)
+    with pytest.raises(NotImplementedError):
+        arch.mobilenet_shape_walk(331, 331)  # stem output 165 x 165: not divisible by 32
+
+
 def test_custom_loss_equals_my_loss(gold):
     import torch
     a, _ = gold
