@@ -337,12 +337,30 @@ class SPNetEngineBase:
         self.backward_head()
         self.backward_body()
 
+    # Backward of the backbone in two parts, so that under data parallelism the gradients that are
+    # final after part A (everything from `tail_param_key` to the end of the flat buffer) can be
+    # all-reduced while part B and the stem still run. Backbones without such a split do all of it in B.
+    tail_param_key = None
+
+    def _backbone_bwd_a(self):
+        pass
+
+    def _backbone_bwd_b(self, ga):
+        self._backbone_bwd(ga)
+
     def backward_body(self):
+        self.backward_body_a()
+        self.backward_body_b()
+
+    def backward_body_a(self):
+        self._backbone_bwd_a()
+
+    def backward_body_b(self):
         B, sh, w, g = self.B, self.shapes, self.w, self.g
         H2, W2 = sh["stem"]
         npx = B * H2 * W2
         ga, gb = (self._view(t, B, H2, W2, 3) for t in self.gstem)
-        self._backbone_bwd(ga)
+        self._backbone_bwd_b(ga)
         # ---- stem
         bn1, bn2, bn3 = self.stem_bn
         drop = self.dropout_rate > 0
@@ -377,20 +395,25 @@ class SPNetEngineBase:
         self.loss(with_grad=True)
         self.backward_head()
 
-    def _step_part2(self):
-        self.backward_body()
+    def _step_part2a(self):
+        self.backward_body_a()
+
+    def _step_part2b(self):
+        self.backward_body_b()
         if self.grad_hook is None:
             self.optimizer_step()
 
     def _step_body(self):
         self._step_part1()
-        self._head_ready()
-        self._step_part2()
+        self._bucket_ready("head")
+        self._step_part2a()
+        self._bucket_ready("tail")
+        self._step_part2b()
 
-    def _head_ready(self):
-        fn = getattr(self.grad_hook, "head_bucket_ready", None)
+    def _bucket_ready(self, which):
+        fn = getattr(self.grad_hook, "bucket_ready", None)
         if fn is not None:
-            fn(self)
+            fn(self, which)
 
     def set_lr(self, lr, beta1=0.9, beta2=0.999):
         """Host side of Keras Adam: t += 1, lr_t = lr*sqrt(1-b2^t)/(1-b1^t) -> device scalar."""
@@ -403,19 +426,21 @@ class SPNetEngineBase:
 
     def capture(self):
         """Capture fwd+loss+bwd(+Adam) into one CUDA graph (call after one eager warm-up step)."""
-        if getattr(self.grad_hook, "head_bucket_ready", None) is None:
+        if getattr(self.grad_hook, "bucket_ready", None) is None:
             gph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gph):
                 self._step_body()
             self.graph = (gph,)
         else:
-            # two graphs so that the Dense-head all-reduce can be launched between them
-            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            # three graphs so that the Dense-head and the tail-bucket all-reduces can be launched between them
+            g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
                 self._step_part1()
             with torch.cuda.graph(g2, pool=g1.pool()):
-                self._step_part2()
-            self.graph = (g1, g2)
+                self._step_part2a()
+            with torch.cuda.graph(g3, pool=g1.pool()):
+                self._step_part2b()
+            self.graph = (g1, g2, g3)
 
     def train_step(self, lr):
         """One optimiser step on the batch currently in self.x0 / self.y_true.
@@ -425,8 +450,10 @@ class SPNetEngineBase:
         if self.graph is not None:
             self.graph[0].replay()
             if len(self.graph) > 1:
-                self._head_ready()
+                self._bucket_ready("head")
                 self.graph[1].replay()
+                self._bucket_ready("tail")
+                self.graph[2].replay()
         else:
             self._step_body()
         if self.grad_hook is not None:
@@ -538,7 +565,10 @@ class XceptionSPNetEngine(SPNetEngineBase):
         self._sep_fwd(s2, s1.z, s1.bn, True, training)
         ops.bn_apply(s2.z.view(B, -1, 2048), s2.bn.a, s2.bn.b, act=1, out=self.feat.view(B, -1, 2048))
 
-    def _backbone_bwd(self, ga):
+    tail_param_key = "block5_sepconv1/depthwise_kernel"  # flat-buffer suffix that is final after part A
+
+    def _backbone_bwd_a(self):
+        """Block 14, exit block 13, middle blocks 12..5."""
         B, sh, w, g = self.B, self.shapes, self.w, self.g
         G1, G2, G3, S, R0, R1 = self.scratch
         # ---- block 14
@@ -574,6 +604,13 @@ class XceptionSPNetEngine(SPNetEngineBase):
             self._sep_bwd(blk[0], g1.view(M, 728), x_in, None, True, self._view(G2, M, 728), g_new, add_src=g_x)
             g_x = g_new
             R_cur, R_nxt = R_nxt, R_cur
+        self._bwd_state = (g_x, R_cur, R_nxt)
+
+    def _backbone_bwd_b(self, ga):
+        """Entry blocks 4..2 and block 1."""
+        B, sh, w, g = self.B, self.shapes, self.w, self.g
+        G1, G2, G3, S, R0, R1 = self.scratch
+        g_x, R_cur, R_nxt = self._bwd_state
         # ---- entry blocks 4..2
         for i in range(len(self.entry) - 1, -1, -1):
             e = self.entry[i]

@@ -7,9 +7,9 @@ Here: one process per GPU (torchrun), every rank holds a full replica and takes 
 [r*B/n, (r+1)*B/n) of the global batch (the reference's get_slice: shape[0]//parts, remainder
 dropped, spnet/multi_gpu.py:49-54), BatchNorm statistics stay per replica exactly as in the tower
 scheme (:61-79 calls the shared-weight model once per slice), and the gradients are averaged with
-one NCCL all-reduce per step over NVLink 5 / NVSwitch: the Dense-head bucket (73 % of the bytes,
-first to be produced by backward, offset 0 of the flat gradient buffer) is reduced on a side
-stream while the backbone backward is still running.
+one NCCL all-reduce per step over NVLink 5 / NVSwitch, issued as buckets in the order backward
+completes them: the Dense-head bucket (73 % of the bytes, offset 0 of the flat gradient buffer) and
+the exit + middle-flow bucket are reduced on a side stream while backward is still running.
 """
 import torch
 
@@ -35,7 +35,11 @@ def batch_slice(n_rows, rank, parts):
 
 
 class GradAllReduce:
-    """engine.grad_hook: average the flat gradient buffer over ranks in two buckets."""
+    """engine.grad_hook: average the flat gradient buffer over ranks in three buckets, in the order
+    backward completes them: the Dense head (offset 0, 73 % of the bytes, final after the head's
+    backward), the tail of the buffer (exit + middle flow, final after part A of the backbone
+    backward) — both reduced on a side stream while backward continues — and the small remainder
+    (stem, block 1, entry flow, residual convolutions) once backward is done."""
 
     def __init__(self, engine, group=None):
         import torch.distributed as dist
@@ -43,33 +47,37 @@ class GradAllReduce:
         self.world = dist.get_world_size(group)
         off, n, _ = engine.offsets["FinalOutput/kernel"]
         assert off == 0
-        self.head = engine.grads[: (n + 7) // 8 * 8]
-        self.rest = engine.grads[(n + 7) // 8 * 8:]
+        n_head = (n + 7) // 8 * 8
+        t0 = engine.offsets[engine.tail_param_key][0] if engine.tail_param_key else engine.grads.numel()
+        self.buckets = {"head": engine.grads[:n_head], "tail": engine.grads[t0:]}
+        self.rest = engine.grads[n_head:t0]
         self.on_cuda = torch.device(engine.device).type == "cuda"
         if self.on_cuda:
             self.side = torch.cuda.Stream(device=engine.device)
-            self.head_ready = torch.cuda.Event()
-            self.head_done = torch.cuda.Event()
-        self.head_in_flight = False
+            self.ready = {k: torch.cuda.Event() for k in self.buckets}
+            self.done = {k: torch.cuda.Event() for k in self.buckets}
+        self.in_flight = set()
 
-    def head_bucket_ready(self, engine):
-        """Called by the engine right after the Dense-head gradient is complete."""
-        if not self.on_cuda:
+    def bucket_ready(self, engine, which):
+        """Called by the engine right after the gradients of bucket `which` are complete."""
+        if not self.on_cuda or self.buckets[which].numel() == 0:
             return
-        self.head_ready.record()
+        self.ready[which].record()
         with torch.cuda.stream(self.side):
-            self.side.wait_event(self.head_ready)
-            self.dist.all_reduce(self.head, group=self.group)
-            self.head_done.record(self.side)
-        self.head_in_flight = True
+            self.side.wait_event(self.ready[which])
+            self.dist.all_reduce(self.buckets[which], group=self.group)
+            self.done[which].record(self.side)
+        self.in_flight.add(which)
 
     def __call__(self, engine):
-        if self.head_in_flight:
-            torch.cuda.current_stream().wait_event(self.head_done)
-            self.head_in_flight = False
-        else:
-            self.dist.all_reduce(self.head, group=self.group)
-        self.dist.all_reduce(self.rest, group=self.group)
+        for which, buf in self.buckets.items():
+            if which in self.in_flight:
+                torch.cuda.current_stream().wait_event(self.done[which])
+            elif buf.numel():
+                self.dist.all_reduce(buf, group=self.group)
+        self.in_flight.clear()
+        if self.rest.numel():
+            self.dist.all_reduce(self.rest, group=self.group)
         engine.optimizer_step(grad_scale=1.0 / self.world)
         engine.skip_default_optimizer = True
 

@@ -209,19 +209,24 @@ lo, hi = multi_gpu.batch_slice(10, rank, world)      # get_slice: size = shape[0
 assert (lo, hi) == (rank * 5, rank * 5 + 5)
 class FakeEngine:
     device = "cpu"
-    def __init__(self):
-        self.offsets = OrderedDict([("FinalOutput/kernel", (0, 20, (4, 5))), ("rest", (24, 8, (8,)))])
-        self.grads = torch.arange(32, dtype=torch.float32) * (rank + 1)
+    def __init__(self, tail_key):
+        self.offsets = OrderedDict([("FinalOutput/kernel", (0, 20, (4, 5))), ("entry", (24, 8, (8,))), ("middle", (32, 16, (16,)))])
+        self.tail_param_key = tail_key
+        self.grads = torch.arange(48, dtype=torch.float32) * (rank + 1)
         self.scale = None
     def optimizer_step(self, grad_scale=1.0):
         self.scale = grad_scale
-eng = FakeEngine()
-hook = multi_gpu.attach_data_parallel(eng)
-hook.head_bucket_ready(eng)
-hook(eng)
-expect = torch.arange(32, dtype=torch.float32) * sum(r + 1 for r in range(world))
-assert torch.equal(eng.grads, expect), (eng.grads, expect)
-assert eng.scale == 1.0 / world
+for tail_key in ("middle", None):        # with and without a tail bucket (Xception / MobileNet engines)
+    eng = FakeEngine(tail_key)
+    hook = multi_gpu.attach_data_parallel(eng)
+    assert hook.buckets["head"].numel() == 24 and hook.buckets["tail"].numel() == (16 if tail_key else 0)
+    assert hook.rest.numel() == (8 if tail_key else 24)
+    hook.bucket_ready(eng, "head")       # on CPU the buckets are reduced in the final call
+    hook.bucket_ready(eng, "tail")
+    hook(eng)
+    expect = torch.arange(48, dtype=torch.float32) * sum(r + 1 for r in range(world))
+    assert torch.equal(eng.grads, expect), (eng.grads, expect)
+    assert eng.scale == 1.0 / world
 dist.barrier()
 if rank == 0:
     print("DP_OK")
