@@ -463,6 +463,44 @@ class SPNetEngineBase:
                 self.optimizer_step()
         return self.loss6
 
+    # ---- asynchronous input path: the NEXT batch travels host -> device on a copy stream into a staging
+    #      buffer while the current step computes; take_prefetched() moves it into the step's (graph-captured)
+    #      input buffers with a device-to-device copy.
+    def _ensure_stage(self):
+        if getattr(self, "_copy_stream", None) is None:
+            self._xs = torch.empty_like(self.x0)
+            self._ys = torch.empty_like(self.y_true)
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage_ready = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record()
+            self._h2d_done = torch.cuda.Event()
+
+    def prefetch_batch(self, x_host, y_host=None):
+        """Start the H2D copy of a batch (pinned torch tensors) without blocking the compute stream.
+        Returns an event that fires when the host buffers may be reused."""
+        self._ensure_stage()
+        cs = self._copy_stream
+        with torch.cuda.stream(cs):
+            cs.wait_event(self._stage_free)  # the previous staged batch has been taken
+            self._xs.copy_(x_host.view(self._xs.shape), non_blocking=True)
+            if y_host is not None:
+                self._ys.copy_(y_host.view(self._ys.shape), non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(cs)
+            self._stage_ready.record(cs)
+        self._has_y = y_host is not None
+        return done
+
+    def take_prefetched(self):
+        """Make the staged batch the current one (compute stream waits for its H2D copy only)."""
+        main = torch.cuda.current_stream()
+        main.wait_event(self._stage_ready)
+        self.x0.copy_(self._xs)
+        if self._has_y:
+            self.y_true.copy_(self._ys)
+        self._stage_free.record(main)
+
     def load_batch(self, x_host, y_host=None):
         """H2D copy of one batch (numpy or pinned torch tensors)."""
         xt = x_host if torch.is_tensor(x_host) else torch.from_numpy(np.ascontiguousarray(x_host, dtype=np.float32))

@@ -354,17 +354,25 @@ class SPNetModel:
             t0 = time.time()
             order = rng.permutation(n) if shuffle else np.arange(n)
             loss_acc.zero_()
-            for b in range(steps):
-                _call(callbacks, "on_batch_begin", b, {"batch": b, "size": batch_size})
+            def stage(b):
+                """Gather batch b into pinned buffer b % 2 and start its H2D copy on the copy stream."""
                 idx = order[b * batch_size:(b + 1) * batch_size]
                 lo, hi = multi_gpu.batch_slice(batch_size, rank, world)
                 idx = np.sort(idx[lo:hi]) if not shuffle else idx[lo:hi]
                 k = b % 2
-                if b >= 2:
-                    torch.cuda.current_stream().synchronize()  # staging buffer k was consumed two steps ago
+                if pin_free[k] is not None:
+                    pin_free[k].synchronize()  # the H2D copy that last read this pinned buffer is done
                 xpin[k].copy_(torch.from_numpy(X[idx]))
                 ypin[k].copy_(torch.from_numpy(Y[idx]))
-                eng.load_batch(xpin[k], ypin[k])
+                pin_free[k] = eng.prefetch_batch(xpin[k], ypin[k])
+
+            pin_free = [None, None]
+            stage(0)
+            for b in range(steps):
+                _call(callbacks, "on_batch_begin", b, {"batch": b, "size": batch_size})
+                eng.take_prefetched()
+                if b + 1 < steps:
+                    stage(b + 1)  # host gather + H2D of the next batch overlap this step's kernels
                 loss6 = eng.train_step(float(self.optimizer.lr))
                 loss_acc += loss6
                 if not captured and b == 0 and epoch == initial_epoch and os.environ.get("SPNET_B200_NO_GRAPH") is None:
