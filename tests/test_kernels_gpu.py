@@ -536,3 +536,46 @@ def test_adam_keras_and_helpers():
     gy = torch.randn(5, 576, device=dev())
     ops.colsum(gy, cs)
     torch.testing.assert_close(cs, gy.sum(0), rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ full-size, size-independent properties
+# (BASELINE.json configs[1] shapes: batch 64, 384x512 -> layer shapes below; no CPU oracle at these sizes)
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(12288, 728, 728, False, True), (744000, 128, 64, False, True),
+                                              (728, 728, 12288, True, True), (49152, 728, 256, False, False)])
+def test_fullsize_gemm_two_implementations_agree(M, N, K, a_mn, b_mn):
+    """tcgen05 GEMM vs the independent fp32 FFMA GEMM on the same bf16-rounded operands."""
+    ops = _ops()
+    torch.manual_seed(M % 1000 + N + K)
+    A = (torch.randn((K, M) if a_mn else (M, K), device=dev()) * 0.5).to(torch.bfloat16)
+    B = (torch.randn((K, N) if b_mn else (N, K), device=dev()) * 0.5).to(torch.bfloat16)
+    mode = ops.OUT_ATOMIC if a_mn else ops.OUT_F32
+    D1 = torch.zeros(M, N, device=dev())
+    ops.gemm(A, a_mn, B, b_mn, D1, M, N, K, out_mode=mode, splits=0 if a_mn else 1)
+    D2 = torch.zeros(M, N, device=dev())
+    ops.gemm_simt(A.float(), a_mn, B.float(), b_mn, D2, M, N, K, out_mode=ops.OUT_F32)
+    scale = float(D2.abs().max())
+    torch.testing.assert_close(D1, D2, rtol=1e-3, atol=2e-4 * scale)
+
+
+@pytest.mark.parametrize("shape", [(64, 93, 125, 128), (64, 12, 16, 728)])
+def test_fullsize_depthwise_adjoint_identities(shape):
+    """<dw_k(x), g> = <x, dw_k^T(g)> = <k, dk>: forward, data gradient and weight gradient of the packed
+    kernels are mutually consistent at the benchmark's layer shapes (fp32, no activation)."""
+    ops = _ops()
+    torch.manual_seed(21)
+    B, H, W, C = shape
+    x = torch.randn(shape, device=dev())
+    g = torch.randn(shape, device=dev())
+    k = torch.randn(3, 3, C, device=dev()) * 0.3
+    y = ops.dwconv3x3_fwd(x, k)
+    dk = torch.zeros(3, 3, C, device=dev())
+    gin = ops.dwconv3x3_bwd_fused(g, x, k, dk)
+    lhs = float((y.double() * g.double()).sum())
+    mid = float((x.double() * gin.double()).sum())
+    rhs = float((k.double() * dk.double()).sum())
+    assert abs(lhs - mid) / abs(lhs) < 1e-4, (lhs, mid)
+    assert abs(lhs - rhs) / abs(lhs) < 1e-4, (lhs, rhs)
+    # linearity in the input
+    y2 = ops.dwconv3x3_fwd(2.0 * x + 1.0, k)
+    ones = ops.dwconv3x3_fwd(torch.ones_like(x), k)
+    torch.testing.assert_close(y2, 2.0 * y + ones, rtol=1e-4, atol=1e-4)
