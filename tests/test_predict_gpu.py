@@ -73,3 +73,33 @@ def test_fit_loop_reduces_loss_and_checkpoints(tmp_path):
                                   freeze_fac=0.0)
     assert len(again.get_weights()) == len(model.get_weights())
     cf.model_type = "monolithic"
+
+
+def test_mobilenet_backbone_through_the_model_surface(tmp_path):
+    """cf.basemodel = 'MobileNet' (BASELINE configs[2]; reference plug-in point spnet/models.py:43-44,349-355):
+    setup_model -> fit -> save_weights -> load -> predict through the same Keras-like surface."""
+    import spnet.config as cf
+    from spnet import models
+    from spnet_b200 import fake_espi
+    cf.model_type = "big"
+    cf.basemodel = "MobileNet"
+    try:
+        X, Y, _ = fake_espi.make_dataset(16, base_seed=9)
+        model, _ = models.setup_model(X, 576, try_checkpoint=False, freeze_fac=0.0)
+        assert model.backbone == "MobileNet" and model.count_params() == 31541217
+        hist = model.fit(X, Y, batch_size=8, epochs=8, shuffle=True, verbose=0)
+        loss = hist.history["loss"]
+        assert np.isfinite(loss).all() and min(loss[4:]) < loss[0], loss
+        wpath = str(tmp_path / "mobilenet.hdf5")
+        model.save_weights(wpath)
+        again, _ = models.setup_model(X, 576, try_checkpoint=True, no_cp_fatal=True, weights_file=wpath, freeze_fac=0.0)
+        y1 = model.predict(X[:8], batch_size=8)
+        y2 = again.predict(X[:8], batch_size=8)
+        assert y1.shape == (8, 576) and np.isfinite(y1).all()
+        np.testing.assert_allclose(y1, y2, rtol=2e-2, atol=2e-2)  # split-K atomics reorder the Dense sums
+        cf.basemodel = "InceptionResNetV2"
+        with pytest.raises((NotImplementedError, AttributeError)):
+            models.setup_model(X, 576, try_checkpoint=False, freeze_fac=0.0)
+    finally:
+        cf.basemodel = "Xception"
+        cf.model_type = "monolithic"
