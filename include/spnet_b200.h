@@ -75,8 +75,8 @@ int spnet_bn_bwd_dz(const void* g, const void* z, const float* a, const float* s
 /* ---- MaxPooling2D(3,2,'same') + BN-apply + residual Add (Xception blocks 2-4, 13) ---- */
 int spnet_maxpool3s2_add_fwd(const void* z, const float* a, const float* b, const void* res, const float* ra, const float* rb, void* out, unsigned char* argmax, int dtype, int B, int H, int W, int C, cudaStream_t stream);
 int spnet_maxpool3s2_bwd(const void* gout, const unsigned char* argmax, void* gin, int dtype, int B, int H, int W, int C, cudaStream_t stream);
-int spnet_gather_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, int off, cudaStream_t stream);
-int spnet_scatter_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, int off, cudaStream_t stream);
+int spnet_gather_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, int off_h, int off_w, cudaStream_t stream);
+int spnet_scatter_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, int off_h, int off_w, cudaStream_t stream);
 
 /* ---- SPNet stem (spnet/models.py:319-340), block1_conv1, block1_conv2 im2col ---- */
 int spnet_conv_small_fwd(int which, const void* in, const float* w, const float* in_a, const float* in_b, int act, void* out, void* skip, double* stats, int dtype, int B, int H, int W, cudaStream_t stream);

@@ -96,18 +96,17 @@ MOBILENET_BLOCKS = ((32, 64, 1), (64, 128, 2), (128, 128, 1), (128, 256, 2), (25
 
 
 def mobilenet_shape_walk(H, W):
+    """Spatial sizes; every stride-2 stage is 'same': out = ceil(n / 2)."""
     s = OrderedDict()
     s["input"] = (H, W)
     s["stem"] = (H // 2, W // 2)
     h, w = s["stem"]
-    if h % 32 or w % 32:
-        raise NotImplementedError("MobileNet backbone: the stem output (%d x %d) must be divisible by 32 "
-                                  "(stride-2 'same' stages are built for even sizes)" % (h, w))
-    h, w = h // 2, w // 2
+    h, w = same_out(h), same_out(w)
     s["conv1"] = (h, w)
     for i, (_, _, stride) in enumerate(MOBILENET_BLOCKS, start=1):
         s["in%d" % i] = (h, w)
-        h, w = h // stride, w // stride
+        if stride == 2:
+            h, w = same_out(h), same_out(w)
         s["out%d" % i] = (h, w)
     return s
 

@@ -150,11 +150,12 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ 
     store_vec(gin + idx * V, acc);
 }
 
-// out[b,oh,ow,:] = in[b,2oh+off,2ow+off,:]   (off 0: what a 1x1 stride-2 'same' convolution reads;
-// off 1: a 3x3 stride-2 'same' convolution on an even-sized input = its stride-1 result at odd positions)
+// out[b,oh,ow,:] = in[b,2oh+off_h,2ow+off_w,:]   (off 0: what a 1x1 stride-2 'same' convolution reads, and a 3x3
+// stride-2 'same' convolution on an ODD-sized dimension = its stride-1 result at even positions; off 1: the
+// same on an EVEN-sized dimension = the stride-1 result at odd positions, because TF pads only at the end)
 template <typename T>
 __global__ void __launch_bounds__(256) gather_s2_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H,
-                                                        int W, int C, int OH, int OW, int off) {
+                                                        int W, int C, int OH, int OW, int off_h, int off_w) {
     constexpr int V = VecN<T>::N;
     const int CV = C / V;
     const long long n = (long long)B * OH * OW * CV;
@@ -168,14 +169,14 @@ __global__ void __launch_bounds__(256) gather_s2_kernel(const T* __restrict__ in
     const int oh = (int)(r % OH);
     const int bi = (int)(r / OH);
     float v[V];
-    load_vec(in + (((size_t)bi * H + 2 * oh + off) * W + 2 * ow + off) * C + cv * V, v);
+    load_vec(in + (((size_t)bi * H + 2 * oh + off_h) * W + 2 * ow + off_w) * C + cv * V, v);
     store_vec(out + idx * V, v);
 }
 
 // adjoint of gather_s2: out[b,h,w,:] = in[b,(h-off)/2,(w-off)/2,:] where both are integral, else 0
 template <typename T>
 __global__ void __launch_bounds__(256) scatter_s2_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H,
-                                                         int W, int C, int OH, int OW, int off) {
+                                                         int W, int C, int OH, int OW, int off_h, int off_w) {
     constexpr int V = VecN<T>::N;
     const int CV = C / V;
     const long long n = (long long)B * H * W * CV;
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(256) scatter_s2_kernel(const T* __restrict__ i
     float v[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) v[i] = 0.f;
-    const int th = h - off, tw = w - off;
+    const int th = h - off_h, tw = w - off_w;
     if (th >= 0 && tw >= 0 && !(th & 1) && !(tw & 1) && (th >> 1) < OH && (tw >> 1) < OW)
         load_vec(in + (((size_t)bi * OH + (th >> 1)) * OW + (tw >> 1)) * C + cv * V, v);
     store_vec(out + idx * V, v);
@@ -241,29 +242,31 @@ int spnet_maxpool3s2_bwd(const void* gout, const unsigned char* argmax, void* gi
     return spnet_check_launch("maxpool3s2_bwd");
 }
 
-// off = 0: rows/cols 0,2,4,... -> out [B,ceil(H/2),ceil(W/2),C];  off = 1: rows/cols 1,3,5,... -> [B,H/2,W/2,C]
-int spnet_gather_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, int off, cudaStream_t stream) {
+// per dimension: off = 0 takes positions 0,2,4,... (ceil(n/2) of them), off = 1 takes 1,3,5,... (n/2 of them)
+int spnet_gather_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, int off_h, int off_w,
+                    cudaStream_t stream) {
     int rc = check_pool("gather_s2", dtype, B, H, W, C);
     if (rc) return rc;
-    SPNET_REQUIRE(in && out && (off == 0 || off == 1), "gather_s2: bad args");
-    const int OH = (H + 1 - off) / 2, OW = (W + 1 - off) / 2;
+    SPNET_REQUIRE(in && out && (off_h == 0 || off_h == 1) && (off_w == 0 || off_w == 1), "gather_s2: bad args");
+    const int OH = (H + 1 - off_h) / 2, OW = (W + 1 - off_w) / 2;
     const int V = dtype == SPNET_BF16 ? 8 : 4;
     const long long n = (long long)B * OH * OW * (C / V);
     SPNET_DISPATCH_DTYPE(dtype, (gather_s2_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(
-                                    reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), B, H, W, C, OH, OW, off)));
+                                    reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), B, H, W, C, OH, OW, off_h, off_w)));
     return spnet_check_launch("gather_s2");
 }
 
 // adjoint of spnet_gather_s2: in [B,OH,OW,C] (OH, OW as above) -> out [B,H,W,C], zero elsewhere
-int spnet_scatter_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, int off, cudaStream_t stream) {
+int spnet_scatter_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, int off_h, int off_w,
+                     cudaStream_t stream) {
     int rc = check_pool("scatter_s2", dtype, B, H, W, C);
     if (rc) return rc;
-    SPNET_REQUIRE(in && out && (off == 0 || off == 1), "scatter_s2: bad args");
-    const int OH = (H + 1 - off) / 2, OW = (W + 1 - off) / 2;
+    SPNET_REQUIRE(in && out && (off_h == 0 || off_h == 1) && (off_w == 0 || off_w == 1), "scatter_s2: bad args");
+    const int OH = (H + 1 - off_h) / 2, OW = (W + 1 - off_w) / 2;
     const int V = dtype == SPNET_BF16 ? 8 : 4;
     const long long n = (long long)B * H * W * (C / V);
     SPNET_DISPATCH_DTYPE(dtype, (scatter_s2_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(
-                                    reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), B, H, W, C, OH, OW, off)));
+                                    reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), B, H, W, C, OH, OW, off_h, off_w)));
     return spnet_check_launch("scatter_s2");
 }
 

@@ -237,8 +237,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_b1c1_fwd_kernel(const T* __r
                                                                     const float* __restrict__ in_a,
                                                                     const float* __restrict__ in_b, int act,
                                                                     T* __restrict__ out, double* __restrict__ stats,
-                                                                    int B, int H, int W, int OH, int OW, int tiles_h,
-                                                                    int tiles_w) {
+                                                                    int B, int H, int W, int OH, int OW, int pt, int pl,
+                                                                    int tiles_h, int tiles_w) {
     constexpr int CIN = 3, COUT = 32, KS = 3, S = 2, TH = 4, TW = 64;
     constexpr int IH_T = (TH - 1) * S + KS, IW_T = (TW - 1) * S + KS;
     typedef Window<T, CIN, IH_T, IW_T> Win;
@@ -259,17 +259,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv_b1c1_fwd_kernel(const T* __r
     Win win;
     if ((int)blockIdx.x < n_tiles) {
         const TileXY t = tile_xy(blockIdx.x, tiles_h, tiles_w, TH, TW);
-        win.fetch(in + (size_t)t.b * H * W * CIN, H, W, t.r0 * S, t.c0 * S);
+        win.fetch(in + (size_t)t.b * H * W * CIN, H, W, t.r0 * S - pt, t.c0 * S - pl);
     }
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const TileXY tc = tile_xy(tile, tiles_h, tiles_w, TH, TW);
         const int oh0 = tc.r0, ow0 = tc.c0, b = tc.b;
         __syncthreads();  // previous tile's readers are done with s_in
-        win.commit(s_in, sab, in_a != nullptr, act, H, W, oh0 * S, ow0 * S);
+        win.commit(s_in, sab, in_a != nullptr, act, H, W, oh0 * S - pt, ow0 * S - pl);
         __syncthreads();
         if (tile + (int)gridDim.x < n_tiles) {
             const TileXY t = tile_xy(tile + gridDim.x, tiles_h, tiles_w, TH, TW);
-            win.fetch(in + (size_t)t.b * H * W * CIN, H, W, t.r0 * S, t.c0 * S);
+            win.fetch(in + (size_t)t.b * H * W * CIN, H, W, t.r0 * S - pt, t.c0 * S - pl);
         }
         const int oh = oh0 + ty, ow = ow0 + tx;
         const bool valid = oh < OH && ow < OW;
@@ -347,17 +347,17 @@ template <> struct G4<float> {
 };
 
 // =================================================================================================
-// block1_conv1 data gradient: gin[ih,iw,ci] = sum_{kh,kw,co} g[(ih-kh)/2, (iw-kw)/2, co] w[kh,kw,ci,co]
-// over the taps whose (ih-kh, iw-kw) are even and inside the output. Tile = 8 x 64 INPUT pixels;
+// block1_conv1 / MobileNet conv1 data gradient: gin[ih,iw,ci] = sum_{kh,kw,co} g[(ih+pt-kh)/2, (iw+pl-kw)/2, co] w[kh,kw,ci,co]
+// over the taps whose (ih+pt-kh, iw+pl-kw) are even and inside the output (pt, pl = leading padding, 0 or 1). Tile = 8 x 64 INPUT pixels;
 // warp = one row, lane = column pair (2*lane, 2*lane+1) processed one parity at a time, so that
 // the set of contributing taps is warp-uniform.
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2) conv_b1c1_dgrad_kernel(const T* __restrict__ g, const float* __restrict__ w,
                                                                       T* __restrict__ gin, int B, int H, int W, int OH,
-                                                                      int OW, int tiles_h, int tiles_w) {
+                                                                      int OW, int pt, int pl, int tiles_h, int tiles_w) {
     constexpr int CIN = 3, COUT = 32, KS = 3, TH = 8, TW = 64;
-    constexpr int GH_T = TH / 2 + 1, GW_T = TW / 2 + 1, GP = COUT + 4;  // padded pixel pitch: conflict-free LDS.128
+    constexpr int GH_T = TH / 2 + 2, GW_T = TW / 2 + 2, GP = COUT + 4;  // padded pixel pitch: conflict-free LDS.128
     constexpr int NV = GH_T * GW_T * (COUT / 4), PER = (NV + kThreads - 1) / kThreads;
     __shared__ __align__(16) float s_g[GH_T * GW_T * GP];
     __shared__ __align__(16) float ws[KS * KS * CIN * COUT];
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_b1c1_dgrad_kernel(const T* _
     G4<T> pre[PER];
     auto fetch = [&](int tile) {
         const TileXY t = tile_xy(tile, tiles_h, tiles_w, TH, TW);
-        // g window: oh in [ih0/2 - 1, ih0/2 + TH/2), ow likewise (ih0, iw0 are even)
+        // g window: oh in [ih0/2 - 1, ih0/2 + TH/2] (oh = (ih + pt - kh)/2, pt in {0,1}), ow likewise (ih0, iw0 even)
         const int goh0 = t.r0 / 2 - 1, gow0 = t.c0 / 2 - 1;
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
@@ -399,12 +399,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_b1c1_dgrad_kernel(const T* _
             float acc[CIN] = {0.f, 0.f, 0.f};
 #pragma unroll
             for (int kh = 0; kh < KS; ++kh) {
-                if (((row - kh) & 1) != 0) continue;  // ih0 even: parity of ih-kh = parity of row-kh (warp-uniform)
-                const int gr = (row - kh + 2) / 2;     // (ih - kh)/2 - goh0
+                if (((row + pt - kh) & 1) != 0) continue;  // ih0 even: parity of ih+pt-kh = parity of row+pt-kh (warp-uniform)
+                const int gr = (row + pt - kh + 2) / 2;     // (ih + pt - kh)/2 - goh0
 #pragma unroll
                 for (int kw = 0; kw < KS; ++kw) {
-                    if (((pw - kw) & 1) != 0) continue;  // compile-time after unrolling
-                    const int gc = (cl - kw + 2) / 2;
+                    if (((pw + pl - kw) & 1) != 0) continue;  // warp-uniform
+                    const int gc = (cl + pl - kw + 2) / 2;
                     const float4* gp = reinterpret_cast<const float4*>(&s_g[(gr * GW_T + gc) * GP]);
                     const float4* wp = reinterpret_cast<const float4*>(&ws[(kh * KS + kw) * CIN * COUT]);
 #pragma unroll
@@ -526,8 +526,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_b1c1_wgrad_kernel(const T* _
                                                                       const float* __restrict__ in_a,
                                                                       const float* __restrict__ in_b, int act,
                                                                       const T* __restrict__ g, float* __restrict__ dw,
-                                                                      int B, int H, int W, int OH, int OW, int tiles_h,
-                                                                      int tiles_w) {
+                                                                      int B, int H, int W, int OH, int OW, int pt, int pl,
+                                                                      int tiles_h, int tiles_w) {
     constexpr int CIN = 3, COUT = 32, KS = 3, S = 2, TH = 4, TW = 32;
     constexpr int IH_T = (TH - 1) * S + KS, IW_T = (TW - 1) * S + KS;
     typedef Window<T, CIN, IH_T, IW_T> Win;
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_b1c1_wgrad_kernel(const T* _
     G4<T> graw[GPER];
     auto fetch = [&](int tile) {
         const TileXY t = tile_xy(tile, tiles_h, tiles_w, TH, TW);
-        win.fetch(in + (size_t)t.b * H * W * CIN, H, W, t.r0 * S, t.c0 * S);
+        win.fetch(in + (size_t)t.b * H * W * CIN, H, W, t.r0 * S - pt, t.c0 * S - pl);
 #pragma unroll
         for (int k = 0; k < GPER; ++k) {
             const int idx = threadIdx.x + k * kThreads;
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_b1c1_wgrad_kernel(const T* _
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const TileXY tc = tile_xy(tile, tiles_h, tiles_w, TH, TW);
         __syncthreads();
-        win.commit(s_in, sab, in_a != nullptr, act, H, W, tc.r0 * S, tc.c0 * S);
+        win.commit(s_in, sab, in_a != nullptr, act, H, W, tc.r0 * S - pt, tc.c0 * S - pl);
 #pragma unroll
         for (int k = 0; k < GPER; ++k) {
             const int idx = threadIdx.x + k * kThreads;
@@ -628,7 +628,8 @@ extern "C" {
 //            (w = K4 [4,4,1,3] from spnet_stem_k3_to_k4)
 //        1 = stem conv 3->3, 3x3 same            [B,H,W,3] -> [B,H,W,3]
 //        2 = block1_conv1 3->32, 3x3 s2 valid    [B,H,W,3] -> [B,(H-3)/2+1,(W-3)/2+1,32]
-//        3 = MobileNet conv1 3->32, 3x3 s2 'same' (TF pads only at the end for even H, W) -> [B,H/2,W/2,32]
+//        3 = MobileNet conv1 3->32, 3x3 s2 'same' (TF: no leading pad for an even size, one for an odd size)
+//            -> [B,ceil(H/2),ceil(W/2),32]
 // in_a/in_b (nullable) + act (0 none, 1 relu, 2 leaky 0.1) transform the input on load.
 // stats (nullable): fp64 [2*Cout] batch-norm accumulators.
 int spnet_conv_small_fwd(int which, const void* in, const float* w, const float* in_a, const float* in_b, int act,
@@ -651,13 +652,14 @@ int spnet_conv_small_fwd(int which, const void* in, const float* w, const float*
                                         reinterpret_cast<const T*>(in), w, in_a, in_b, act, reinterpret_cast<T*>(out),
                                         nullptr, stats, nullptr, nullptr, nullptr, B, H, W, H, W, 1, 1, th, tw)));
     } else if (which == 2 || which == 3) {
-        SPNET_REQUIRE(which == 2 || (H % 2 == 0 && W % 2 == 0), "conv_small_fwd(3): 'same' stride 2 is built for even H, W");
-        const int OH = which == 2 ? (H - 3) / 2 + 1 : H / 2, OW = which == 2 ? (W - 3) / 2 + 1 : W / 2;
+        // 'same' stride 2 (which 3): out = ceil(n/2); TF pads (k - s)=1 at the end for even n, 1 + 1 for odd n
+        const int OH = which == 2 ? (H - 3) / 2 + 1 : (H + 1) / 2, OW = which == 2 ? (W - 3) / 2 + 1 : (W + 1) / 2;
+        const int pt = which == 3 ? (H & 1) : 0, pl = which == 3 ? (W & 1) : 0;
         const int th = ceil_div(OH, 4), tw = ceil_div(OW, 64);
         const int grid = persist_grid_tiles((long long)B * th * tw, 2);
         SPNET_DISPATCH_DTYPE(dtype, (conv_b1c1_fwd_kernel<T><<<grid, kThreads, 0, stream>>>(
                                         reinterpret_cast<const T*>(in), w, in_a, in_b, act, reinterpret_cast<T*>(out),
-                                        stats, B, H, W, OH, OW, th, tw)));
+                                        stats, B, H, W, OH, OW, pt, pl, th, tw)));
     } else {
         spnet_set_error("conv_small_fwd: unknown conv id %d", which);
         return SPNET_ERR_ARG;
@@ -685,13 +687,13 @@ int spnet_conv_small_wgrad(int which, const void* in, const float* in_a, const f
                                         reinterpret_cast<const T*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g), dw,
                                         B, H, W, H, W, 1, 1, th, tw)));
     } else if (which == 2 || which == 3) {
-        SPNET_REQUIRE(which == 2 || (H % 2 == 0 && W % 2 == 0), "conv_small_wgrad(3): 'same' stride 2 is built for even H, W");
-        const int OH = which == 2 ? (H - 3) / 2 + 1 : H / 2, OW = which == 2 ? (W - 3) / 2 + 1 : W / 2;
+        const int OH = which == 2 ? (H - 3) / 2 + 1 : (H + 1) / 2, OW = which == 2 ? (W - 3) / 2 + 1 : (W + 1) / 2;
+        const int pt = which == 3 ? (H & 1) : 0, pl = which == 3 ? (W & 1) : 0;
         const int th = ceil_div(OH, 4), tw = ceil_div(OW, 32);
         const int grid = persist_grid_tiles((long long)B * th * tw, 1);  // 134 registers x 256 threads: one CTA per SM
         SPNET_DISPATCH_DTYPE(dtype, (conv_b1c1_wgrad_kernel<T><<<grid, kThreads, 0, stream>>>(
                                         reinterpret_cast<const T*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g), dw,
-                                        B, H, W, OH, OW, th, tw)));
+                                        B, H, W, OH, OW, pt, pl, th, tw)));
     } else {
         spnet_set_error("conv_small_wgrad: unknown conv id %d", which);
         return SPNET_ERR_ARG;
@@ -716,13 +718,13 @@ int spnet_conv_small_dgrad(int which, const void* g, const float* w, const void*
                                         1, 1, th, tw)));
     } else if (which == 2 || which == 3) {
         SPNET_REQUIRE(!mask_z, "conv_small_dgrad(2|3): these convolutions read the stem output directly (no activation mask)");
-        SPNET_REQUIRE(which == 2 || (H % 2 == 0 && W % 2 == 0), "conv_small_dgrad(3): 'same' stride 2 is built for even H, W");
-        const int OH = which == 2 ? (H - 3) / 2 + 1 : H / 2, OW = which == 2 ? (W - 3) / 2 + 1 : W / 2;
+        const int OH = which == 2 ? (H - 3) / 2 + 1 : (H + 1) / 2, OW = which == 2 ? (W - 3) / 2 + 1 : (W + 1) / 2;
+        const int pt = which == 3 ? (H & 1) : 0, pl = which == 3 ? (W & 1) : 0;
         const int th = ceil_div(H, 8), tw = ceil_div(W, 64);
         const int grid = persist_grid_tiles((long long)B * th * tw, 2);
         SPNET_DISPATCH_DTYPE(dtype, (conv_b1c1_dgrad_kernel<T><<<grid, kThreads, 0, stream>>>(
-                                        reinterpret_cast<const T*>(g), w, reinterpret_cast<T*>(gin), B, H, W, OH, OW, th,
-                                        tw)));
+                                        reinterpret_cast<const T*>(g), w, reinterpret_cast<T*>(gin), B, H, W, OH, OW, pt, pl,
+                                        th, tw)));
     } else {
         spnet_set_error("conv_small_dgrad: unknown conv id %d", which);
         return SPNET_ERR_ARG;

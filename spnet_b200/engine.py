@@ -675,11 +675,10 @@ class MobileNetSPNetEngine(SPNetEngineBase):
     DepthwiseConv2D 3x3 'same' stride s -> BN -> ReLU6 -> Conv 1x1 -> BN -> ReLU6.
 
     The depthwise stages run on the same packed kernels as Xception's (BN + ReLU6 of the
-    previous stage applied on load). A stride-2 'same' depthwise convolution on an even-sized
-    map equals the stride-1 result sampled at odd rows/columns (TF pads only at the end), so the
-    four stride-2 stages run the stride-1 kernel followed by a subsample (and its adjoint in
-    backward); spatial sizes must stay even down to the last stride-2 stage (stem output
-    divisible by 32, e.g. 384x512 inputs)."""
+    previous stage applied on load). A stride-2 'same' depthwise convolution equals the stride-1
+    'same' result sampled at odd positions of an even-sized dimension (TF pads only at the end)
+    and at even positions of an odd-sized one (TF pads one on each side), so the four stride-2
+    stages run the stride-1 kernel followed by a subsample (and its adjoint in backward)."""
 
     def _arch(self):
         return arch.mobilenet_shape_walk(self.H, self.W), arch.mobilenet_param_spec(self.H, self.W, self.n_out)
@@ -689,7 +688,9 @@ class MobileNetSPNetEngine(SPNetEngineBase):
         self.c1_bn = self._mk_bn("conv1_bn", 32)
         self.blocks = []
         for i, (cin, cout, stride) in enumerate(arch.MOBILENET_BLOCKS, start=1):
-            b = dict(i=i, cin=cin, cout=cout, s=stride, hw=sh["in%d" % i], ohw=sh["out%d" % i],
+            hw = sh["in%d" % i]
+            b = dict(i=i, cin=cin, cout=cout, s=stride, hw=hw, ohw=sh["out%d" % i],
+                     off=(1 - hw[0] % 2, 1 - hw[1] % 2),  # even size: odd positions; odd size: even positions
                      dwk=self.w["conv_dw_%d/depthwise_kernel" % i].view(3, 3, cin),
                      pw=self.w["conv_pw_%d/kernel" % i].view(cin, cout),
                      pwl=self.wl["conv_pw_%d/kernel" % i].view(cin, cout),
@@ -727,7 +728,7 @@ class MobileNetSPNetEngine(SPNetEngineBase):
             M = B * oh * ow
             if b["s"] == 2:
                 ops.dwconv3x3_fwd(x, b["dwk"], xbn.a, xbn.b, 2, out=b["zd_full"])
-                ops.gather_s2(b["zd_full"], out=b["zd"], off=1)
+                ops.gather_s2(b["zd_full"], out=b["zd"], off=b["off"])
             else:
                 ops.dwconv3x3_fwd(x, b["dwk"], xbn.a, xbn.b, 2, out=b["zd"])
             if training:
@@ -765,7 +766,7 @@ class MobileNetSPNetEngine(SPNetEngineBase):
             ops.bn_bwd_reduce(g_t, b["zd"], b["bn_dw"].mean, b["bn_dw"].rstd, b["bn_dw"].stats, relu_a=b["bn_dw"].a,
                               relu_b=b["bn_dw"].b, act=3)
             g_zd = self._bn_bwd(g_t, b["zd"], b["bn_dw"], M, reduced=True)
-            g_full = ops.scatter_s2(g_zd, self._view(bufs[fb], B, h, wd, cin), off=1) if b["s"] == 2 else g_zd
+            g_full = ops.scatter_s2(g_zd, self._view(bufs[fb], B, h, wd, cin), off=b["off"]) if b["s"] == 2 else g_zd
             # depthwise 3x3: gradient w.r.t. relu6(BN_prev(x)) (masked) + BN_prev backward sums + dk
             g_y = self._view(bufs[nb], B, h, wd, cin)
             ops.dwconv3x3_bwd_fused(g_full, x, b["dwk"], b["gdwk"], in_a=xbn.a, in_b=xbn.b, relu=2, bn_mean=xbn.mean,

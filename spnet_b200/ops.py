@@ -219,12 +219,18 @@ def maxpool3s2_bwd(gout, argmax, H, W, out=None):
     return out
 
 
+def _off2(off):
+    return (off, off) if isinstance(off, int) else (int(off[0]), int(off[1]))
+
+
 def gather_s2(x, out=None, off=0):
+    """out[b,oh,ow] = x[b, 2*oh+off_h, 2*ow+off_w]; off = int or (off_h, off_w)."""
     _chk(x, out)
     B, H, W, C = x.shape
+    oh, ow = _off2(off)
     if out is None:
-        out = torch.empty(B, (H + 1 - off) // 2, (W + 1 - off) // 2, C, device=x.device, dtype=x.dtype)
-    lib().gather_s2(_p(x), _p(out), dtype_code(x), B, H, W, C, off, _s())
+        out = torch.empty(B, (H + 1 - oh) // 2, (W + 1 - ow) // 2, C, device=x.device, dtype=x.dtype)
+    lib().gather_s2(_p(x), _p(out), dtype_code(x), B, H, W, C, oh, ow, _s())
     return out
 
 
@@ -232,7 +238,8 @@ def scatter_s2(x, out, off=0):
     """Adjoint of gather_s2: x [B,OH,OW,C] -> out [B,H,W,C] (zero where nothing lands)."""
     _chk(x, out)
     B, H, W, C = out.shape
-    lib().scatter_s2(_p(x), _p(out), dtype_code(x), B, H, W, C, off, _s())
+    oh, ow = _off2(off)
+    lib().scatter_s2(_p(x), _p(out), dtype_code(x), B, H, W, C, oh, ow, _s())
     return out
 
 

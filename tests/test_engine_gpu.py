@@ -155,10 +155,10 @@ def test_dropout_statistics_and_smoke():
 
 
 # ------------------------------------------------------------------ MobileNet backbone (BASELINE configs[2])
+@pytest.mark.parametrize("H,W,B", [(128, 192, 3), (131, 163, 2), (150, 100, 2)])
 @pytest.mark.parametrize("dtype,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
-def test_mobilenet_inference_forward(dtype, tol):
+def test_mobilenet_inference_forward(dtype, tol, H, W, B):
     from spnet_b200.engine import MobileNetSPNetEngine
-    H, W, B = 128, 192, 3
     w, x, yt = make_case(H, W, B, seed=13, backbone="MobileNet")
     ref = xt.OracleMobileNetSPNet(w, H, W)
     with torch.no_grad():
@@ -169,10 +169,10 @@ def test_mobilenet_inference_forward(dtype, tol):
     assert rel_err(y, y_ref) < tol, rel_err(y, y_ref)
 
 
+@pytest.mark.parametrize("H,W,B", [(128, 192, 4), (131, 163, 3), (150, 100, 3)])
 @pytest.mark.parametrize("loss_type", ["same", "hybrid"])
-def test_mobilenet_train_step_fp32(loss_type):
+def test_mobilenet_train_step_fp32(loss_type, H, W, B):
     from spnet_b200.engine import MobileNetSPNetEngine
-    H, W, B = 128, 192, 4
     w, x, yt = make_case(H, W, B, seed=15, backbone="MobileNet")
     ref = xt.OracleMobileNetSPNet(w, H, W)
     total, data, y_ref, grads = ref.loss_and_grads(x, yt, loss_type=loss_type)

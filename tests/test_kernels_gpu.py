@@ -217,18 +217,18 @@ def test_dwconv_bwd_fused(dtype, shape, mode):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("off", [0, 1])
+@pytest.mark.parametrize("off", [(0, 0), (1, 1), (0, 1), (1, 0)])
 def test_subsample_scatter_colstats(dtype, off):
     ops = _ops()
     torch.manual_seed(6)
-    B, H, W, C = 2, 12, 16, 72
+    B, H, W, C = 2, 12 + (1 - off[0]), 16 + (1 - off[1]), 72  # odd sizes go with offset 0
     x = torch.randn(B, H, W, C, device=dev()).to(dtype)
     y = ops.gather_s2(x, off=off)
-    torch.testing.assert_close(y, x[:, off::2, off::2, :].contiguous())
+    torch.testing.assert_close(y, x[:, off[0]::2, off[1]::2, :].contiguous())
     back = torch.empty_like(x)
     ops.scatter_s2(y, back, off=off)
     ref = torch.zeros_like(x)
-    ref[:, off::2, off::2, :] = y
+    ref[:, off[0]::2, off[1]::2, :] = y
     torch.testing.assert_close(back, ref)
     st = torch.zeros(2 * C, device=dev(), dtype=torch.float64)
     ops.colstats(x, st)

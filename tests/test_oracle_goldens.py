@@ -160,8 +160,7 @@ def test_mobilenet_structure_pins():
     with torch.no_grad():
         y = m.forward(np.zeros((1, 64, 64, 1), np.float32))
     assert tuple(y.shape) == (1, 576)
-    with pytest.raises(NotImplementedError):
-        arch.mobilenet_shape_walk(331, 331)  # stem output 165 x 165: not divisible by 32
+    assert arch.mobilenet_shape_walk(331, 331)["out13"] == xt.mobilenet_feature_hw(331, 331) == (6, 6)
 
 
 def test_custom_loss_equals_my_loss(gold):
