@@ -131,8 +131,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     __shared__ float sstat[2][2][4][BN];  // [accumulator parity][sum | sumsq][lane quadrant][column]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // bf16 output staging for the TMA-store epilogue: one 32 x 32 (64-byte rows, SWIZZLE_64B) box per epilogue warp
+    // output staging for the TMA-store epilogue: SD boxes of 32 rows x 64 bytes (SWIZZLE_64B) per epilogue warp;
+    // two where shared memory allows (BN = 128: the HBM-bound shapes), so a box is filled while the previous
+    // one is still being read out
+    constexpr int SD = BN <= 128 ? 2 : 1;
     const uint32_t stage_out0 = smem_u32(smem) + STAGES * STAGE_BYTES;
+    uint32_t sbox = 0, last_box = 0;  // staging box this warp fills next; address of the one it filled last
     const int total_kb = (K + BK - 1) / BK;
     const uint32_t crank = CL > 1 ? cluster_cta_rank() : 0u;
     const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
@@ -303,8 +307,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     // global stores this replaces cost 32 LSU cycles each (32 different lines per instruction);
                     // rows >= M and columns >= N are clipped by the TMA unit
                     if (col0 < N && m0 + q * 32 < M) {  // warp-uniform
-                        const uint32_t stg = stage_out0 + (uint32_t)(warp - 2) * 2048u;
-                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous box read out
+                        const uint32_t stg = stage_out0 + ((uint32_t)(warp - 2) * SD + sbox) * 2048u;
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SD - 1) : "memory");  // this box was read out
                         __syncwarp();
                         const uint32_t rowaddr = stg + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
 #pragma unroll
@@ -321,6 +325,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                                          : "memory");
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
+                        last_box = stg;
+                        if (SD > 1) sbox ^= 1u;
                     }
                 } else {
 #pragma unroll
@@ -328,12 +334,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     // fp32 store / split-K accumulation through the same 2 KB staging box, 16 columns (64-byte
                     // rows) at a time: TMA store, or TMA reduce-add into the fp32 gradient for OUT_ATOMIC_F32
                     if (m0 + q * 32 < M) {  // warp-uniform
-                        const uint32_t stg = stage_out0 + (uint32_t)(warp - 2) * 2048u;
-                        const uint32_t rowaddr = stg + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
+                        const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             if (col0 + 16 * h >= N) break;  // warp-uniform
-                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            const uint32_t stg = stage_out0 + ((uint32_t)(warp - 2) * SD + sbox) * 2048u;
+                            const uint32_t rowaddr = stg + (uint32_t)lane * 64u;
+                            if (SD > 1) sbox ^= 1u;
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SD - 1) : "memory");
                             __syncwarp();
 #pragma unroll
                             for (int g = 0; g < 4; ++g)
@@ -367,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         float sx = 0.f, sy = 0.f, qx = 0.f, qy = 0.f;
                         if (col0 < N && m0 + q * 32 < M) {
                             const uint32_t half = (uint32_t)lane >> 4, p = (uint32_t)lane & 15u;
-                            const uint32_t base = stage_out0 + (uint32_t)(warp - 2) * 2048u + half * 1024u + (p & 3u) * 4u;
+                            const uint32_t base = last_box + half * 1024u + (p & 3u) * 4u;
                             const uint32_t jb = (p >> 2) << 4;
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
@@ -459,8 +467,8 @@ int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long lon
 template <int BN, bool A_MN, bool B_MN, int CL>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, GemmEpi epi, int M, int N, int K,
                 int splits, cudaStream_t stream) {
-    constexpr int STAGES = (BN <= 128) ? 6 : 4;
-    constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + kEpiWarps * 2048;
+    constexpr int STAGES = (BN <= 128) ? 5 : 4;  // BN = 128: one ring stage traded for the second staging box
+    constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + kEpiWarps * 2048 * (BN <= 128 ? 2 : 1);
     auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, CL>;
     static bool configured = false;
     static int num_sms = 148;
@@ -520,7 +528,7 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
     SPNET_REQUIRE(out_mode >= 0 && out_mode <= 2, "gemm_bf16: bad out_mode %d", out_mode);
     SPNET_REQUIRE(out_mode != OUT_BF16 || (N % 8 == 0 && ldd % 8 == 0), "gemm_bf16: bf16 output needs N, ldd %% 8 == 0");
     SPNET_REQUIRE(out_mode == OUT_BF16 || ldd % 4 == 0, "gemm_bf16: fp32 output needs ldd %% 4 == 0");
-    const bool wide_ = N >= 512, pair_ = wide_ && M > BM && getenv("SPNET_B200_NO_CLUSTER") == nullptr;
+    const bool wide_ = N >= 512 && getenv("SPNET_GEMM_FORCE_NARROW") == nullptr, pair_ = wide_ && M > BM && getenv("SPNET_B200_NO_CLUSTER") == nullptr;
     if (splits <= 0) {
         // auto split-K (atomic output only): fill the SMs (or SM pairs) once without spilling into a
         // second, nearly empty round; keep at least 4 k-blocks per split
