@@ -91,6 +91,19 @@ int spnet_bn3_bwd_dz(const void* g, const void* z, const float* a, const float* 
 int spnet_im2col3x3(const void* in, const float* a, const float* b, int relu, void* col, int dtype, int B, int H, int W, int C, cudaStream_t stream);
 int spnet_col2im3x3(const void* gcol, const void* z, const float* a, const float* b, int relu, void* gin, int dtype, int B, int H, int W, int C, cudaStream_t stream);
 
+/* ---- dense-convolution backbone pieces (keras.applications.InceptionResNetV2 via spnet/models.py:18,357-359):
+ *      generic im2col / col2im around the GEMMs, 'valid' max-pool, AveragePooling2D(3,1,'same'), channel-slice
+ *      copies (Concatenate), the scaled residual of the Inception-ResNet blocks, bias gradient ---- */
+int spnet_im2col(const void* in, void* col, int dtype, int B, int H, int W, int C, int KH, int KW, int sh, int sw, int pt, int pl, int OH, int OW, cudaStream_t stream);
+int spnet_col2im(const void* gcol, void* gin, int accumulate, int dtype, int B, int H, int W, int C, int KH, int KW, int sh, int sw, int pt, int pl, int OH, int OW, cudaStream_t stream);
+int spnet_maxpool3s2_valid_fwd(const void* z, void* out, unsigned char* argmax, int dtype, int B, int H, int W, int C, cudaStream_t stream);
+int spnet_maxpool3s2_valid_bwd(const void* gout, const unsigned char* argmax, void* gin, int dtype, int B, int H, int W, int C, cudaStream_t stream);
+int spnet_avgpool3s1(const void* in, void* out, int bwd, int accumulate, int dtype, int B, int H, int W, int C, cudaStream_t stream);
+int spnet_copy2d(const void* src, long long ld_src, void* dst, long long ld_dst, int accumulate, int dtype, long long rows, int cols, cudaStream_t stream);
+int spnet_residual_fwd(const void* x, const void* u, const float* bias, float scale, int relu, void* y, int dtype, long long rows, int C, cudaStream_t stream);
+int spnet_residual_bwd(const void* gy, const void* y, float scale, int relu, void* gx, int accumulate_gx, void* gu, int dtype, long long rows, int C, cudaStream_t stream);
+int spnet_colsum_rows(const void* g, float* out, int dtype, long long rows, int C, cudaStream_t stream);
+
 /* ---- optimiser: keras Adam (spnet/models.py:494) + L2 of add_regularization (:47-71) ---- */
 int spnet_adam_keras_step(float* p, const float* g, float* m, float* v, long long n, long long n_l2, float l2, const float* lr_t_dev, float beta1, float beta2, float eps, float grad_scale, void* p_bf16, cudaStream_t stream);
 int spnet_sumsq(const float* p, long long n, float scale, float* out, cudaStream_t stream);

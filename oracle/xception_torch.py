@@ -393,3 +393,157 @@ class OracleMobileNetSPNet(OracleSPNet):
             if taps:
                 self.taps["block%d" % i] = x
         return x
+
+
+# =================================================================================================
+# InceptionResNetV2 backbone (BASELINE configs[3]): keras.applications.inception_resnet_v2 @ Keras 2.1.3,
+# include_top=False (reference call site spnet/models.py:18,357-359). Not in the reference tree; restated
+# from its published architecture. conv2d_bn = Conv2D(use_bias=False) ->
+# BatchNormalization(scale=False) -> ReLU; Inception-ResNet blocks end in a 1x1 convolution WITH bias and
+# no BN/activation, `x + scale * up`, then ReLU. Pinned structurally by the no-top total 54,336,736.
+# =================================================================================================
+class _IRv2Walker:
+    """Walks the Keras construction code once; `emit` decides what a layer does (spec or tensor math)."""
+
+    def __init__(self, conv_bn, conv_bias, maxpool, avgpool, concat, residual):
+        self.conv_bn, self.conv_bias, self.maxpool, self.avgpool = conv_bn, conv_bias, maxpool, avgpool
+        self.concat, self.residual = concat, residual
+
+    def run(self, x):
+        cb = self.conv_bn
+        x = cb(x, 32, 3, 2, "valid")
+        x = cb(x, 32, 3, 1, "valid")
+        x = cb(x, 64, 3, 1, "same")
+        x = self.maxpool(x)
+        x = cb(x, 80, 1, 1, "valid")
+        x = cb(x, 192, 3, 1, "valid")
+        x = self.maxpool(x)
+        b0 = cb(x, 96, 1, 1, "same")
+        b1 = cb(cb(x, 48, 1, 1, "same"), 64, 5, 1, "same")
+        b2 = cb(cb(cb(x, 64, 1, 1, "same"), 96, 3, 1, "same"), 96, 3, 1, "same")
+        bp = cb(self.avgpool(x), 64, 1, 1, "same")
+        x = self.concat([b0, b1, b2, bp])
+        for i in range(1, 11):
+            x = self.block(x, 0.17, "block35", i, True)
+        b0 = cb(x, 384, 3, 2, "valid")
+        b1 = cb(cb(cb(x, 256, 1, 1, "same"), 256, 3, 1, "same"), 384, 3, 2, "valid")
+        x = self.concat([b0, b1, self.maxpool(x)])
+        for i in range(1, 21):
+            x = self.block(x, 0.1, "block17", i, True)
+        b0 = cb(cb(x, 256, 1, 1, "same"), 384, 3, 2, "valid")
+        b1 = cb(cb(x, 256, 1, 1, "same"), 288, 3, 2, "valid")
+        b2 = cb(cb(cb(x, 256, 1, 1, "same"), 288, 3, 1, "same"), 320, 3, 2, "valid")
+        x = self.concat([b0, b1, b2, self.maxpool(x)])
+        for i in range(1, 10):
+            x = self.block(x, 0.2, "block8", i, True)
+        x = self.block(x, 1.0, "block8", 10, False)
+        return cb(x, 1536, 1, 1, "same", name="conv_7b")
+
+    def block(self, x, scale, kind, idx, relu):
+        cb = self.conv_bn
+        if kind == "block35":
+            br = [cb(x, 32, 1, 1, "same"), cb(cb(x, 32, 1, 1, "same"), 32, 3, 1, "same"),
+                  cb(cb(cb(x, 32, 1, 1, "same"), 48, 3, 1, "same"), 64, 3, 1, "same")]
+        elif kind == "block17":
+            br = [cb(x, 192, 1, 1, "same"), cb(cb(cb(x, 128, 1, 1, "same"), 160, (1, 7), 1, "same"), 192, (7, 1), 1, "same")]
+        else:
+            br = [cb(x, 192, 1, 1, "same"), cb(cb(cb(x, 192, 1, 1, "same"), 224, (1, 3), 1, "same"), 256, (3, 1), 1, "same")]
+        up = self.conv_bias(self.concat(br), "%s_%d_conv" % (kind, idx))
+        return self.residual(x, up, scale, relu)
+
+
+def irv2_spnet_spec(H, W, n_out=576):
+    """Ordered (layer, weight, shape, trainable, l2) list; shapes are propagated symbolically as (h, w, c)."""
+    spec = []
+    cnt = [4, 4]  # next auto index for Conv2D / BatchNormalization (1..3 belong to the SPNet stem)
+
+    def bn(name, c, scale=True):
+        if scale:
+            spec.append((name, "gamma", (c,), True, False))
+        spec.append((name, "beta", (c,), True, False))
+        spec.append((name, "moving_mean", (c,), False, False))
+        spec.append((name, "moving_variance", (c,), False, False))
+
+    def osz(n, k, s, pad):
+        return (n - k) // s + 1 if pad == "valid" else -(-n // s)
+
+    def conv_bn(x, cout, k, s, pad, name=None):
+        kh, kw = (k, k) if isinstance(k, int) else k
+        if name is None:
+            name, bname = "conv2d_%d" % cnt[0], "batch_normalization_%d" % cnt[1]
+            cnt[0] += 1
+            cnt[1] += 1
+        else:
+            bname = name + "_bn"
+        spec.append((name, "kernel", (kh, kw, x[2], cout), True, True))
+        bn(bname, cout, scale=False)
+        return (osz(x[0], kh, s, pad), osz(x[1], kw, s, pad), cout)
+
+    def conv_bias(x, name):
+        return ("pending", x, name)
+
+    def residual(x, up, scale, relu):
+        _, m, name = up
+        spec.append((name, "kernel", (1, 1, m[2], x[2]), True, True))
+        spec.append((name, "bias", (x[2],), True, False))
+        return x
+
+    for i, cin in ((1, 1), (2, 3), (3, 3)):
+        spec.append(("conv2d_%d" % i, "kernel", (3, 3, cin, 3), True, True))
+        bn("batch_normalization_%d" % i, 3)
+    w = _IRv2Walker(conv_bn, conv_bias, lambda x: (osz(x[0], 3, 2, "valid"), osz(x[1], 3, 2, "valid"), x[2]), lambda x: x,
+                    lambda xs: (xs[0][0], xs[0][1], sum(t[2] for t in xs)), residual)
+    o = w.run((H // 2, W // 2, 3))
+    spec.append(("FinalOutput", "kernel", (o[0] * o[1] * o[2], n_out), True, True))
+    spec.append(("FinalOutput", "bias", (n_out,), True, False))
+    return spec
+
+
+class OracleIRv2SPNet(OracleSPNet):
+    def make_spec(self, H, W, n_out):
+        return irv2_spnet_spec(H, W, n_out)
+
+    def bn(self, x, name, training):
+        if (name + "/gamma") in self.p:
+            return super().bn(x, name, training)
+        b = self.p[name + "/beta"]                      # BatchNormalization(scale=False): gamma == 1
+        mm, mv = self.p[name + "/moving_mean"], self.p[name + "/moving_variance"]
+        if training:
+            mean = x.mean((0, 2, 3))
+            var = x.var((0, 2, 3), unbiased=False)
+            n = x.numel() // x.shape[1]
+            with torch.no_grad():
+                uv = var * n / max(n - 1, 1) if self.unbiased else var
+                mm.mul_(BN_MOMENTUM).add_((1 - BN_MOMENTUM) * mean)
+                mv.mul_(BN_MOMENTUM).add_((1 - BN_MOMENTUM) * uv)
+        else:
+            mean, var = mm, mv
+        s = 1.0 / torch.sqrt(var + BN_EPS)
+        return x * s[None, :, None, None] + (b - mean * s)[None, :, None, None]
+
+    def backbone(self, x, training, taps=False):
+        p = self.p
+        cnt = [4, 4]
+
+        def conv_bn(t, cout, k, s, pad, name=None):
+            if name is None:
+                name, bname = "conv2d_%d" % cnt[0], "batch_normalization_%d" % cnt[1]
+                cnt[0] += 1
+                cnt[1] += 1
+            else:
+                bname = name + "_bn"
+            return torch.relu(self.bn(conv2d_tf(t, p[name + "/kernel"], s, pad), bname, training))
+
+        def conv_bias(t, name):
+            return conv2d_tf(t, p[name + "/kernel"], 1, "valid") + p[name + "/bias"][None, :, None, None]
+
+        def avgpool(t):
+            # AveragePooling2D(3, 1, 'same'): TF averages over the in-image cells only
+            return F.avg_pool2d(t, 3, 1, padding=1, count_include_pad=False)
+
+        def residual(t, up, scale, relu):
+            y = t + scale * up
+            return torch.relu(y) if relu else y
+
+        w = _IRv2Walker(conv_bn, conv_bias, lambda t: F.max_pool2d(t, 3, 2), avgpool, lambda ts: torch.cat(ts, 1), residual)
+        return w.run(x)

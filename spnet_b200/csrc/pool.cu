@@ -242,6 +242,36 @@ int spnet_maxpool3s2_bwd(const void* gout, const unsigned char* argmax, void* gi
     return spnet_check_launch("maxpool3s2_bwd");
 }
 
+// MaxPooling2D(3, strides 2, 'valid') (Inception-ResNet stem / reductions): the same kernels with no
+// padding and OH = (H-3)/2+1. out [B,OH,OW,C]; argmax nullable (inference).
+int spnet_maxpool3s2_valid_fwd(const void* z, void* out, unsigned char* argmax, int dtype, int B, int H, int W, int C,
+                               cudaStream_t stream) {
+    int rc = check_pool("maxpool3s2_valid_fwd", dtype, B, H, W, C);
+    if (rc) return rc;
+    SPNET_REQUIRE(z && out && H >= 3 && W >= 3, "maxpool3s2_valid_fwd: bad args");
+    const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
+    const int V = dtype == SPNET_BF16 ? 8 : 4;
+    const long long n = (long long)B * OH * OW * (C / V);
+    SPNET_DISPATCH_DTYPE(dtype, (maxpool_add_fwd_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(
+                                    reinterpret_cast<const T*>(z), nullptr, nullptr, nullptr, nullptr, nullptr,
+                                    reinterpret_cast<T*>(out), argmax, B, H, W, C, OH, OW, 0, 0)));
+    return spnet_check_launch("maxpool3s2_valid_fwd");
+}
+
+int spnet_maxpool3s2_valid_bwd(const void* gout, const unsigned char* argmax, void* gin, int dtype, int B, int H, int W,
+                               int C, cudaStream_t stream) {
+    int rc = check_pool("maxpool3s2_valid_bwd", dtype, B, H, W, C);
+    if (rc) return rc;
+    SPNET_REQUIRE(gout && argmax && gin && H >= 3 && W >= 3, "maxpool3s2_valid_bwd: bad args");
+    const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
+    const int V = dtype == SPNET_BF16 ? 8 : 4;
+    const long long n = (long long)B * H * W * (C / V);
+    SPNET_DISPATCH_DTYPE(dtype, (maxpool_bwd_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(
+                                    reinterpret_cast<const T*>(gout), argmax, reinterpret_cast<T*>(gin), B, H, W, C, OH, OW,
+                                    0, 0)));
+    return spnet_check_launch("maxpool3s2_valid_bwd");
+}
+
 // per dimension: off = 0 takes positions 0,2,4,... (ceil(n/2) of them), off = 1 takes 1,3,5,... (n/2 of them)
 int spnet_gather_s2(const void* in, void* out, int dtype, int B, int H, int W, int C, int off_h, int off_w,
                     cudaStream_t stream) {

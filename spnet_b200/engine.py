@@ -19,7 +19,7 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
-from . import arch, ops
+from . import arch, irv2, ops
 from ._lib import lib
 
 
@@ -128,12 +128,12 @@ class SPNetEngineBase:
     def _f32(self, n):
         return torch.zeros(n, device=self.device, dtype=torch.float32)
 
-    def _mk_bn(self, name, C):
+    def _mk_bn(self, name, C, scale=True):
         bn = _BN()
         bn.name, bn.C = name, C
-        bn.gamma, bn.beta = self.w[name + "/gamma"], self.w[name + "/beta"]
+        bn.gamma, bn.beta = (self.w[name + "/gamma"] if scale else None), self.w[name + "/beta"]
         if self.can_train:
-            bn.ggamma, bn.gbeta = self.g[name + "/gamma"], self.g[name + "/beta"]
+            bn.ggamma, bn.gbeta = (self.g[name + "/gamma"] if scale else None), self.g[name + "/beta"]
         else:
             bn.ggamma = bn.gbeta = None
         bn.mm, bn.mv = self.nt[name + "/moving_mean"], self.nt[name + "/moving_variance"]
@@ -776,3 +776,178 @@ class MobileNetSPNetEngine(SPNetEngineBase):
         g_zc1 = self._bn_bwd(g_y, self.zc1, self.c1_bn, B * h * wd, reduced=True)
         ops.conv_small_wgrad(3, self.d, g_zc1, g["conv1/kernel"])
         ops.conv_small_dgrad(3, g_zc1, w["conv1/kernel"], ga)
+
+
+class InceptionResNetV2SPNetEngine(SPNetEngineBase):
+    """keras.applications.InceptionResNetV2 backbone, BASELINE configs[3] (reference: the generic backbone
+    branch, spnet/models.py:18,357-359). The architecture is a static program of layer records
+    (spnet_b200/irv2.py); this class allocates one buffer per activation (+ its gradient) and walks the
+    program forwards / backwards. Every convolution is a GEMM on the tcgen05 kernel (1x1: directly on the
+    NHWC activation; k x k: through a generic im2col, recomputed in backward) with the BatchNorm
+    statistics in its epilogue; BN(scale=False)+ReLU outputs are materialised because they are GEMM
+    operands."""
+
+    def _arch(self):
+        return irv2.shape_walk(self.H, self.W), irv2.param_spec(self.H, self.W, self.n_out)
+
+    def _build_backbone(self):
+        h, w = self.shapes["stem"]
+        self.prog = irv2.build_program(h, w)
+        for op in self.prog.ops:
+            if op["kind"] == "conv_bn":
+                op["bnrec"] = self._mk_bn(op["bn"], op["cout"], scale=False)
+        for op in self.prog.ops:
+            if op["kind"] == "residual":  # the bias of the 1x1 "up" convolution is added here
+                op["bias_name"] = next(p_ for p_ in self.prog.ops if p_["out"] is op["inputs"][1])["name"] + "/bias"
+        # which backward contribution to an activation's gradient comes first (writes) vs later (accumulates)
+        seen = set()
+        for op in reversed(self.prog.ops):
+            op["first"] = []
+            for x in op["inputs"]:
+                op["first"].append(x.idx not in seen)
+                seen.add(x.idx)
+
+    def _alloc_backbone(self):
+        B, A, prog = self.B, self._act, self.prog
+        train = self.can_train
+        self.data, self.grad = {}, {}
+        out = prog.output
+        self.feat_dims = (out.h, out.w, out.c)
+        for sy in prog.syms:
+            if sy is prog.input or sy is out:
+                continue
+            self.data[sy.idx] = A(B, sy.h, sy.w, sy.c)
+            if train:
+                self.grad[sy.idx] = A(B, sy.h, sy.w, sy.c)
+        col_el, tmp_el = 8, 8
+        for op in prog.ops:
+            o = op["out"]
+            if op["kind"] == "conv_bn":
+                op["z"] = A(B, o.h, o.w, o.c)
+                if not (op["kh"] == 1 and op["kw"] == 1 and op["stride"] == 1) and op["cin"] != 3:
+                    col_el = max(col_el, B * o.h * o.w * op["kh"] * op["kw"] * op["cin"])
+            elif op["kind"] == "maxpool":
+                op["argmax"] = A(B, o.h, o.w, o.c, dtype=torch.uint8) if train else None
+            for x in op["inputs"]:
+                tmp_el = max(tmp_el, B * x.h * x.w * x.c)
+        self.col = A(col_el)
+        if train:
+            self.gcol = A(col_el)
+            self.tmp = A(tmp_el)
+
+    def _alloc_activations(self):
+        super()._alloc_activations()
+        B, out = self.B, self.prog.output
+        self.data[self.prog.input.idx] = self.d
+        self.data[out.idx] = self.feat.view(B, out.h, out.w, out.c)
+        if self.can_train:
+            self.grad[out.idx] = self.gfeat.view(B, out.h, out.w, out.c)
+
+    # ---- helpers
+    def _conv_operand(self, op, x):
+        """GEMM A operand [M, K] of a convolution: the activation itself for 1x1, an im2col buffer otherwise."""
+        o = op["out"]
+        M, K = self.B * o.h * o.w, op["kh"] * op["kw"] * op["cin"]
+        if op["kh"] == 1 and op["kw"] == 1 and op["stride"] == 1:
+            return x.view(M, K), M, K
+        col = self.col[:M * K].view(M, K)
+        ops.im2col(x, col, op["kh"], op["kw"], op["stride"], op["pt"], op["pl"], o.h, o.w)
+        return col, M, K
+
+    def _backbone_fwd(self, training):
+        B, w, wl = self.B, self.w, self.wl
+        for op in self.prog.ops:
+            kind, o = op["kind"], op["out"]
+            xs = [self.data[x.idx] for x in op["inputs"]]
+            y = self.data[o.idx]
+            if kind == "conv_bn":
+                bn, z = op["bnrec"], op["z"]
+                M = B * o.h * o.w
+                if op["cin"] == 3:  # first convolution: 3x3 stride 2 'valid' on the 3-channel stem output
+                    ops.conv_small_fwd(2, xs[0], w[op["name"] + "/kernel"], z, stats=bn.stats if training else None)
+                    self._bn_ready(bn, M, training)
+                else:
+                    A_, M, K = self._conv_operand(op, xs[0])
+                    self._pw_fwd(A_, wl[op["name"] + "/kernel"].view(K, o.c), z.view(M, o.c), M, K, o.c, bn, training)
+                ops.bn_apply(z, bn.a, bn.b, act=1 if op["act"] else 0, out=y)
+            elif kind == "conv_bias":
+                M = B * o.h * o.w
+                ops.gemm(xs[0].view(M, op["cin"]), False, wl[op["name"] + "/kernel"].view(op["cin"], o.c), True, y.view(M, o.c),
+                         M, o.c, op["cin"], out_mode=ops.OUT_T)
+            elif kind == "maxpool":
+                ops.maxpool3s2_valid_fwd(xs[0], y, op["argmax"] if training else None)
+            elif kind == "avgpool":
+                ops.avgpool3s1(xs[0], y)
+            elif kind == "concat":
+                M, off = B * o.h * o.w, 0
+                for x, t in zip(op["inputs"], xs):
+                    ops.copy2d(t, 0, x.c, y, off, o.c, M, x.c)
+                    off += x.c
+            elif kind == "residual":
+                ops.residual_fwd(xs[0], xs[1], w[op["bias_name"]], op["scale"], op["relu"], y)
+
+    def _into(self, x, first):
+        """Where a full-tensor gradient contribution for activation x goes: its gradient buffer when it is the
+        first contribution, a temporary (added afterwards by _merge) otherwise."""
+        g = self.grad[x.idx]
+        return g if first else self.tmp[:g.numel()].view(g.shape)
+
+    def _merge(self, x, first):
+        if not first:
+            g = self.grad[x.idx]
+            n = g.numel()
+            ops.copy2d(self.tmp, 0, x.c, g, 0, x.c, n // x.c, x.c, accumulate=True)
+
+    def _backbone_bwd(self, ga):
+        B, w, wl, g_ = self.B, self.w, self.wl, self.g
+        self.grad[self.prog.input.idx] = ga
+        for op in reversed(self.prog.ops):
+            kind, o = op["kind"], op["out"]
+            ins = op["inputs"]
+            xs = [self.data[x.idx] for x in ins]
+            gy = self.grad[o.idx]
+            M = B * o.h * o.w
+            if kind == "conv_bn":
+                bn, z = op["bnrec"], op["z"]
+                if op["act"]:
+                    ops.bn_bwd_reduce(gy, z, bn.mean, bn.rstd, bn.stats, relu_a=bn.a, relu_b=bn.b, act=1)
+                else:
+                    ops.bn_bwd_reduce(gy, z, bn.mean, bn.rstd, bn.stats)
+                dz = self._bn_bwd(gy, z, bn, M, reduced=True)
+                gW = g_[op["name"] + "/kernel"]
+                if op["cin"] == 3:
+                    ops.conv_small_wgrad(2, xs[0], dz, gW)
+                    ops.conv_small_dgrad(2, dz, w[op["name"] + "/kernel"], ga)
+                    continue
+                A_, M, K = self._conv_operand(op, xs[0])
+                Wl = wl[op["name"] + "/kernel"].view(K, o.c)
+                if K == op["cin"]:  # 1x1: the data gradient is the input gradient itself
+                    tgt = self._into(ins[0], op["first"][0])
+                    self._pw_bwd(A_, Wl, gW.view(K, o.c), dz.view(M, o.c), tgt.view(M, K), M, K, o.c)
+                    self._merge(ins[0], op["first"][0])
+                else:
+                    gcol = self.gcol[:M * K].view(M, K)
+                    self._pw_bwd(A_, Wl, gW.view(K, o.c), dz.view(M, o.c), gcol, M, K, o.c)
+                    ops.col2im(gcol, self.grad[ins[0].idx], op["kh"], op["kw"], op["stride"], op["pt"], op["pl"], o.h, o.w,
+                               accumulate=not op["first"][0])
+            elif kind == "conv_bias":
+                K = op["cin"]
+                tgt = self._into(ins[0], op["first"][0])
+                self._pw_bwd(xs[0].view(M, K), wl[op["name"] + "/kernel"].view(K, o.c), g_[op["name"] + "/kernel"].view(K, o.c),
+                             gy.view(M, o.c), tgt.view(M, K), M, K, o.c)
+                self._merge(ins[0], op["first"][0])
+                ops.colsum_rows(gy.view(M, o.c), g_[op["name"] + "/bias"])
+            elif kind == "maxpool":
+                tgt = self._into(ins[0], op["first"][0])
+                ops.maxpool3s2_valid_bwd(gy, op["argmax"], tgt)
+                self._merge(ins[0], op["first"][0])
+            elif kind == "avgpool":
+                ops.avgpool3s1(gy, self.grad[ins[0].idx], bwd=True, accumulate=not op["first"][0])
+            elif kind == "concat":
+                off = 0
+                for x, first in zip(ins, op["first"]):
+                    ops.copy2d(gy, off, o.c, self.grad[x.idx], 0, x.c, M, x.c, accumulate=not first)
+                    off += x.c
+            elif kind == "residual":
+                ops.residual_bwd(gy, self.data[o.idx], op["scale"], op["relu"], self.grad[ins[0].idx],
+                                 not op["first"][0], self.grad[ins[1].idx])

@@ -151,7 +151,8 @@ class SPNetModel:
         self.input_shape = (None, H, W, 1)
         self.output_shape = (None, Y0size)
         self.H, self.W, self.Y0size = H, W, Y0size
-        self.spec = (arch.mobilenet_param_spec if backbone == "MobileNet" else arch.param_spec)(H, W, Y0size)
+        from . import irv2
+        self.spec = {"MobileNet": arch.mobilenet_param_spec, "InceptionResNetV2": irv2.param_spec}.get(backbone, arch.param_spec)(H, W, Y0size)
         self._shape = OrderedDict((k, s) for k, s, _, _ in self.spec)
         self._host_weights = weights if weights is not None else arch.glorot_init(self.spec, seed)
         self.use_l2 = not quick_setup          # add_regularization is skipped by quick_setup (spnet/models.py:398-399)
@@ -248,8 +249,8 @@ class SPNetModel:
         self.optimizer = optimizer if optimizer is not None else Adam(lr=0.00001)
 
     def _engine(self, batch, training):
-        from .engine import MobileNetSPNetEngine, XceptionSPNetEngine
-        Engine = MobileNetSPNetEngine if self.backbone == "MobileNet" else XceptionSPNetEngine
+        from .engine import InceptionResNetV2SPNetEngine, MobileNetSPNetEngine, XceptionSPNetEngine
+        Engine = {"MobileNet": MobileNetSPNetEngine, "InceptionResNetV2": InceptionResNetV2SPNetEngine}.get(self.backbone, XceptionSPNetEngine)
         key = (batch, training)
         eng = self._engines.get(key)
         if eng is None:
@@ -426,19 +427,26 @@ def MobileNet(weights=None, include_top=False, input_tensor=None, input_shape=No
     return "MobileNet"
 
 
+def InceptionResNetV2(weights=None, include_top=False, input_tensor=None, input_shape=None):
+    """keras.applications.inception_resnet_v2.InceptionResNetV2 plug-in (spnet/models.py:18, built through
+    the generic backbone branch :357-359 with weights=None)."""
+    return "InceptionResNetV2"
+
+
 def create_model_functional(X, Y0size=576, freeze_fac=0.75, quick_setup=False):
     """spnet/models.py:302-424. Stem -> cf.basemodel -> Flatten -> Dense(Y0size,'FinalOutput')."""
     print("Using functional API model, cf.basemodel =", cf.basemodel)
     print("X[0].shape = ", X[0].shape)
     if not hasattr(sys.modules[__name__], cf.basemodel):
         raise AttributeError("module 'spnet.models' has no attribute '%s'" % cf.basemodel)
-    if cf.basemodel not in ("Xception", "MobileNet"):
-        raise NotImplementedError("cf.basemodel = %r: the Xception (reference default, spnet/config.py:52) and "
-                                  "MobileNet backbones are built so far" % cf.basemodel)
+    if cf.basemodel not in ("Xception", "MobileNet", "InceptionResNetV2"):
+        raise NotImplementedError("cf.basemodel = %r: the Xception (reference default, spnet/config.py:52), MobileNet and "
+                                  "InceptionResNetV2 backbones are built" % cf.basemodel)
     model = SPNetModel(X[0].shape, Y0size=Y0size, quick_setup=quick_setup, backbone=cf.basemodel)
     # Keras layer count of base_model: 144 for Xception (paper/run_logs/log_DatasetA_*.txt:95);
     # MobileNet: 1 Input + 12 stem layers + 81 backbone layers (3 + 13 x 6)
-    num_layers = 144 if cf.basemodel == "Xception" else 94
+    # InceptionResNetV2: 1 Input + 12 stem layers + 779 backbone layers after its input
+    num_layers = {"Xception": 144, "MobileNet": 94}.get(cf.basemodel, 792)
     freeze_layers = int(num_layers * freeze_fac)
     print("Freezing ", freeze_layers, "/", num_layers, " layers of base_model")
     if freeze_layers > 0:

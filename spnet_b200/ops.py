@@ -342,3 +342,66 @@ def bias_fill(bias, out):
 def colsum(g, out):
     rows, cols = g.shape
     lib().colsum(_p(g), _p(out), rows, cols, _s())
+
+
+# ----------------------------------------------------------------------------- dense-convolution backbone pieces
+def im2col(x, col, kh, kw, stride, pt, pl, oh, ow):
+    _chk(x, col)
+    B, H, W, C = x.shape
+    lib().im2col(_p(x), _p(col), dtype_code(x), B, H, W, C, kh, kw, stride, stride, pt, pl, oh, ow, _s())
+    return col
+
+
+def col2im(gcol, gin, kh, kw, stride, pt, pl, oh, ow, accumulate=False):
+    _chk(gcol, gin)
+    B, H, W, C = gin.shape
+    lib().col2im(_p(gcol), _p(gin), int(accumulate), dtype_code(gin), B, H, W, C, kh, kw, stride, stride, pt, pl, oh, ow, _s())
+    return gin
+
+
+def maxpool3s2_valid_fwd(x, out, argmax=None):
+    _chk(x, out, argmax)
+    B, H, W, C = x.shape
+    lib().maxpool3s2_valid_fwd(_p(x), _p(out), _p(argmax), dtype_code(x), B, H, W, C, _s())
+    return out
+
+
+def maxpool3s2_valid_bwd(gout, argmax, gin):
+    _chk(gout, argmax, gin)
+    B, H, W, C = gin.shape
+    lib().maxpool3s2_valid_bwd(_p(gout), _p(argmax), _p(gin), dtype_code(gin), B, H, W, C, _s())
+    return gin
+
+
+def avgpool3s1(x, out, bwd=False, accumulate=False):
+    _chk(x, out)
+    B, H, W, C = x.shape
+    lib().avgpool3s1(_p(x), _p(out), int(bwd), int(accumulate), dtype_code(x), B, H, W, C, _s())
+    return out
+
+
+def copy2d(src, src_col, ld_src, dst, dst_col, ld_dst, rows, cols, accumulate=False):
+    """dst[r, dst_col:dst_col+cols] (+)= src[r, src_col:src_col+cols] on row-major buffers with pitches ld_*."""
+    es = src.element_size()
+    lib().copy2d(src.data_ptr() + src_col * es, ld_src, dst.data_ptr() + dst_col * es, ld_dst, int(accumulate),
+                 dtype_code(src), rows, cols, _s())
+
+
+def residual_fwd(x, u, bias, scale, relu, out):
+    _chk(x, u, out)
+    C = x.shape[-1]
+    lib().residual_fwd(_p(x), _p(u), _p(bias), float(scale), int(relu), _p(out), dtype_code(x), x.numel() // C, C, _s())
+    return out
+
+
+def residual_bwd(gy, y, scale, relu, gx, accumulate_gx, gu):
+    _chk(gy, y, gx, gu)
+    C = y.shape[-1]
+    lib().residual_bwd(_p(gy), _p(y), float(scale), int(relu), _p(gx), int(accumulate_gx), _p(gu), dtype_code(y),
+                       y.numel() // C, C, _s())
+
+
+def colsum_rows(g, out):
+    _chk(g, out)
+    C = g.shape[-1]
+    lib().colsum_rows(_p(g), _p(out), dtype_code(g), g.numel() // C, C, _s())

@@ -13,7 +13,7 @@ def make_case(H, W, B, seed=0, n_out=576, backbone="Xception"):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from oracle import xception_torch as xt
     rng = np.random.default_rng(seed)
-    spec = (xt.mobilenet_spnet_spec if backbone == "MobileNet" else xt.xception_spnet_spec)(H, W, n_out)
+    spec = {"MobileNet": xt.mobilenet_spnet_spec, "InceptionResNetV2": xt.irv2_spnet_spec}.get(backbone, xt.xception_spnet_spec)(H, W, n_out)
     w = xt.init_weights(spec, seed=seed + 1)
     for k in w:
         leaf = k.rsplit("/", 1)[1]

@@ -269,3 +269,82 @@ def test_fullsize_step_properties():
     np.testing.assert_allclose([l0, l1], losses_e, rtol=2e-2)
     more = [float(eng2.train_step(4e-5)[0]) for _ in range(6)]
     assert all(np.isfinite(more)) and more[-1] < l0, (l0, more)
+
+
+# ------------------------------------------------------------------ InceptionResNetV2 backbone (BASELINE configs[3])
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_irv2_inference_forward(dtype, tol):
+    from spnet_b200.engine import InceptionResNetV2SPNetEngine
+    H, W, B = 260, 330, 2
+    w, x, yt = make_case(H, W, B, seed=19, backbone="InceptionResNetV2")
+    ref = xt.OracleIRv2SPNet(w, H, W)
+    with torch.no_grad():
+        y_ref = ref.forward(x, training=False).numpy()
+    eng = InceptionResNetV2SPNetEngine(H, W, B, dtype=dtype, weights=w, training=False)
+    eng.load_batch(x)
+    y = eng.forward(training=False).cpu().numpy()
+    assert rel_err(y, y_ref) < tol, rel_err(y, y_ref)
+
+
+def test_irv2_train_step_fp32():
+    from spnet_b200.engine import InceptionResNetV2SPNetEngine
+    H, W, B = 260, 330, 3
+    w, x, yt = make_case(H, W, B, seed=23, backbone="InceptionResNetV2")
+    ref = xt.OracleIRv2SPNet(w, H, W)
+    total, data, y_ref, grads = ref.loss_and_grads(x, yt)
+    eng = InceptionResNetV2SPNetEngine(H, W, B, dtype="fp32", weights=w, dropout_rate=0.0)
+    eng.load_batch(x, yt)
+    eng.grad_hook = lambda e: None
+    loss6 = eng.train_step(lr=1e-3)
+    torch.cuda.synchronize()
+    got_total = float(loss6[0]) + float(eng.l2_out[0])
+    assert abs(float(loss6[0]) - data) / abs(data) < 1e-4
+    assert abs(got_total - total) / abs(total) < 1e-4
+    assert rel_err(eng.y_pred.cpu().numpy(), y_ref.numpy()) < 1e-4
+    gnorms = [float(np.linalg.norm(grads[k].numpy().astype(np.float64))) / np.sqrt(grads[k].numel()) for k in ref.trainable]
+    floor_rms = 1e-3 * float(np.median(gnorms))
+    bad = []
+    for k in ref.trainable:
+        g_ref = grads[k].numpy().copy()
+        if k in ref.l2_keys:
+            g_ref -= 2 * xt.L2 * w[k]
+        if k == "batch_normalization_3/beta":
+            continue
+        e = l2_err(eng.g[k].cpu().numpy(), g_ref, floor=floor_rms * np.sqrt(g_ref.size))
+        # the last stage is 2x3 pixels x 3 images at this input size: one ReLU decision flip moves a BN-beta
+        # gradient by several per cent, hence 6e-2 here instead of the 3e-2 of the other backbones
+        if e > 6e-2:
+            bad.append((k, e))
+    assert not bad, bad[:10]
+    ref.adam_step(grads, 1e-3)
+    w_ref, w_got = ref.weights_numpy(), eng.get_weights()
+    for k in w_ref:
+        if "moving" in k:
+            assert rel_err(w_got[k], w_ref[k]) < 1e-4, k
+
+
+def test_irv2_train_steps_bf16():
+    """bf16 training on the dense-convolution backbone: error envelope against the fp32 oracle, head-gradient
+    direction, finite and decreasing loss over a few optimiser steps (CUDA-graph replay)."""
+    from spnet_b200.engine import InceptionResNetV2SPNetEngine
+    H, W, B = 260, 330, 4
+    w, x, yt = make_case(H, W, B, seed=29, backbone="InceptionResNetV2")
+    ref = xt.OracleIRv2SPNet(w, H, W)
+    total, data, y_ref, grads = ref.loss_and_grads(x, yt)
+    eng = InceptionResNetV2SPNetEngine(H, W, B, dtype="bf16", weights=w, dropout_rate=0.0)
+    eng.load_batch(x, yt)
+    eng.grad_hook = lambda e: None
+    loss6 = eng.train_step(lr=1e-4)
+    torch.cuda.synchronize()
+    assert l2_err(eng.y_pred.cpu().numpy(), y_ref.numpy()) < 0.3
+    assert abs(float(loss6[0]) - data) / abs(data) < 0.3
+    a = eng.g["FinalOutput/kernel"].cpu().numpy().ravel().astype(np.float64)
+    b = (grads["FinalOutput/kernel"].numpy() - 2 * xt.L2 * w["FinalOutput/kernel"]).ravel().astype(np.float64)
+    assert float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30)) > 0.7
+    eng.grad_hook = None
+    l0 = float(eng.train_step(lr=1e-4)[0])
+    torch.cuda.synchronize()
+    eng.capture()
+    losses = [float(eng.train_step(lr=1e-4)[0]) for _ in range(6)]
+    torch.cuda.synchronize()
+    assert all(np.isfinite(losses)) and losses[-1] < l0, (l0, losses)

@@ -163,6 +163,22 @@ def test_mobilenet_structure_pins():
     assert arch.mobilenet_shape_walk(331, 331)["out13"] == xt.mobilenet_feature_hw(331, 331) == (6, 6)
 
 
+def test_irv2_structure_pins():
+    """keras.applications.InceptionResNetV2(include_top=False) @ Keras 2.1.3: 54,336,736 parameters (SURVEY.md
+    section 2.2), backbone output (4,6,1536) at 384x512; the oracle's walk of the Keras construction code and
+    the engine's layer program must produce the same tensors, names and order."""
+    from spnet_b200 import irv2
+    spec = xt.irv2_spnet_spec(384, 512)
+    stem = ("conv2d_1", "conv2d_2", "conv2d_3", "batch_normalization_1", "batch_normalization_2", "batch_normalization_3", "FinalOutput")
+    assert sum(int(np.prod(s)) for l, w, s, t, r in spec if l not in stem) == 54336736
+    eng = irv2.param_spec(384, 512)
+    assert [(k, tuple(s), t, r) for k, s, t, r in eng] == [(l + "/" + w, tuple(s), t, r) for l, w, s, t, r in spec]
+    prog = irv2.build_program(192, 256)
+    assert (prog.output.h, prog.output.w, prog.output.c) == (4, 6, 1536)
+    assert sum(1 for o in prog.ops if o["kind"] == "conv_bn") == 204 and sum(1 for o in prog.ops if o["kind"] == "conv_bias") == 40
+    assert xt.count_params(spec)[0] == 75571201
+
+
 def test_custom_loss_equals_my_loss(gold):
     import torch
     a, _ = gold

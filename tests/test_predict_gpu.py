@@ -97,9 +97,31 @@ def test_mobilenet_backbone_through_the_model_surface(tmp_path):
         y2 = again.predict(X[:8], batch_size=8)
         assert y1.shape == (8, 576) and np.isfinite(y1).all()
         np.testing.assert_allclose(y1, y2, rtol=2e-2, atol=2e-2)  # split-K atomics reorder the Dense sums
-        cf.basemodel = "InceptionResNetV2"
+        cf.basemodel = "NASNetLarge"
         with pytest.raises((NotImplementedError, AttributeError)):
             models.setup_model(X, 576, try_checkpoint=False, freeze_fac=0.0)
+    finally:
+        cf.basemodel = "Xception"
+        cf.model_type = "monolithic"
+
+
+def test_irv2_backbone_through_the_model_surface(tmp_path):
+    """cf.basemodel = 'InceptionResNetV2' (BASELINE configs[3]; the reference's generic backbone branch,
+    spnet/models.py:357-359) through setup_model -> fit -> predict at the native 384x512 input."""
+    import spnet.config as cf
+    from spnet import models
+    from spnet_b200 import fake_espi
+    cf.model_type = "big"
+    cf.basemodel = "InceptionResNetV2"
+    try:
+        X, Y, _ = fake_espi.make_dataset(8, base_seed=11)
+        model, _ = models.setup_model(X, 576, try_checkpoint=False, freeze_fac=0.0)
+        assert model.backbone == "InceptionResNetV2" and model.count_params() == 75571201
+        hist = model.fit(X, Y, batch_size=4, epochs=6, shuffle=True, verbose=0)
+        loss = hist.history["loss"]
+        assert np.isfinite(loss).all() and min(loss[3:]) < loss[0], loss
+        y = model.predict(X[:4], batch_size=4)
+        assert y.shape == (4, 576) and np.isfinite(y).all()
     finally:
         cf.basemodel = "Xception"
         cf.model_type = "monolithic"
