@@ -173,8 +173,14 @@ def run_ours(args, rank, world):
     import torch
     import torch.distributed as dist
     from spnet_b200._lib import lib as get_lib
-    from spnet_b200.engine import XceptionSPNetEngine
+    from spnet_b200 import engine as engine_mod
     from spnet_b200 import multi_gpu
+    # the headline workload is Xception (BASELINE configs[1]); --backbone runs the same step on the other
+    # backbones of BASELINE configs[2] / [3] for the record (profiles/README.md), not as the bench line
+    Engine = {"Xception": engine_mod.XceptionSPNetEngine, "MobileNet": engine_mod.MobileNetSPNetEngine,
+              "InceptionResNetV2": engine_mod.InceptionResNetV2SPNetEngine}[args.backbone]
+    global METRIC
+    METRIC = METRIC.replace("Xception", args.backbone)
 
     local = int(os.environ.get("LOCAL_RANK", 0))
     dev = torch.device("cuda", local)
@@ -187,7 +193,7 @@ def run_ours(args, rank, world):
     Yp = torch.from_numpy(Y).pin_memory()
     Xd, Yd = Xp.to(dev), Yp.to(dev)
 
-    eng = XceptionSPNetEngine(H, W, B, dtype="bf16", device=str(dev), seed=1)
+    eng = Engine(H, W, B, dtype="bf16", device=str(dev), seed=1)
     if world > 1:
         multi_gpu.attach_data_parallel(eng)
 
@@ -343,7 +349,7 @@ def run_ours(args, rank, world):
     try:
         del eng
         torch.cuda.empty_cache()
-        ieng = XceptionSPNetEngine(H, W, B, dtype="bf16", device=str(dev), seed=1, training=False)
+        ieng = Engine(H, W, B, dtype="bf16", device=str(dev), seed=1, training=False)
         ieng.x0.copy_(Xd[:B])
         ieng.forward(training=False)
         torch.cuda.synchronize()
@@ -371,7 +377,7 @@ def run_ours(args, rank, world):
     out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-           "config": {"workload": "Xception-SPNet train step fwd+bwd+YOLO-ellipse loss+Keras Adam, 384x512x1, batch %d/GPU" % B,
+           "config": {"workload": "%s-SPNet train step fwd+bwd+YOLO-ellipse loss+Keras Adam, 384x512x1, batch %d/GPU" % (args.backbone, B),
                       "global_batch": B * world, "parallelism": "dp%d" % world, "dropout": 0.1, "l2": 1e-4,
                       "input_pool": "%d distinct gen_fake_espi-style frames per rank" % npool,
                       "l2_cache": "per-step working set (activations, several GB) >> 126 MB L2; no explicit flush",
@@ -410,6 +416,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--backbone", default="Xception", choices=["Xception", "MobileNet", "InceptionResNetV2"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     args.steps_ref = max(1, min(args.steps, 3))

@@ -321,8 +321,9 @@ int spnet_colsum_rows(const void* g, float* out, int dtype, long long rows, int 
     const int chunks = ceil_div(CV, 128);
     const int cvb = ceil_div(CV, chunks);
     const int per = kT / cvb;
-    long long gx = (rows + per - 1) / per;
-    if (gx > 296) gx = 296;
+    long long gx = (rows + (long long)per * 32 - 1) / ((long long)per * 32);  // >= 32 rows per thread: the float atomics at the
+    if (gx > 64) gx = 64;                                                    // end serialise per address (64-deep at most)
+    if (gx < 1) gx = 1;
     SPNET_DISPATCH_DTYPE(dtype, (colsum_rows_kernel<T><<<dim3((unsigned)gx, chunks), kT, 0, stream>>>(
                                     reinterpret_cast<const T*>(g), out, rows, C, cvb, per)));
     return spnet_check_launch("colsum_rows");
