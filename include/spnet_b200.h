@@ -63,6 +63,15 @@ int spnet_dwconv3x3_wgrad(const void* in, const void* gout, const float* in_a, c
 int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* D, long long ldd, int out_mode, int M, int N, int K, int splits, double* colstats, cudaStream_t stream);
 int spnet_gemm_simt(const void* A, long long sa_r, long long sa_k, const void* B, long long sb_r, long long sb_k, void* D, long long ldd, int dtype, int out_mode, int M, int N, int K, int splits, double* colstats, cudaStream_t stream);
 
+/* ---- Conv2D k x k, stride 1, as implicit GEMM on tcgen05 (gemm_tc.cu, no im2col buffer): Xception
+ *      block1_conv2 (keras.applications.Xception; spnet/models.py:359) and the InceptionResNetV2 branch
+ *      convolutions (spnet/models.py:18,357-359). NHWC bf16 activations with pixel stride ld (a channel slice
+ *      of a wider buffer is fine), Keras kernel [KH,KW,Cin,Cout] bf16; pt / pl = top / left zero padding.
+ *      fwd: optional fused BatchNorm column statistics; wgrad: fp32 reduce-add into dW. ---- */
+int spnet_conv_tc_fwd(const void* X, long long ldx, int NB, int H, int W, int Cin, const void* Wt, void* Y, long long ldy, int OH, int OW, int Cout, int KH, int KW, int pt, int pl, double* colstats, cudaStream_t stream);
+int spnet_conv_tc_dgrad(const void* dY, long long ldy, int NB, int OH, int OW, int Cout, const void* Wt, void* dX, long long ldx, int H, int W, int Cin, int KH, int KW, int pt, int pl, cudaStream_t stream);
+int spnet_conv_tc_wgrad(const void* X, long long ldx, int NB, int H, int W, int Cin, const void* dY, long long ldy, int OH, int OW, int Cout, float* dW, int KH, int KW, int pt, int pl, cudaStream_t stream);
+
 /* ---- BatchNormalization (43 layers; spnet/models.py:326-336 + Xception) ---- */
 int spnet_bn_finalize(double* stats, long long count, const float* gamma, const float* beta, float eps, float momentum, int unbiased_moving_var, float* a, float* b, float* save_mean, float* save_rstd, float* moving_mean, float* moving_var, int C, cudaStream_t stream);
 int spnet_bn_inference_affine(const float* gamma, const float* beta, const float* moving_mean, const float* moving_var, float eps, float* a, float* b, int C, cudaStream_t stream);

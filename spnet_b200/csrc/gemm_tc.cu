@@ -36,6 +36,25 @@ struct GemmEpi {
     double* colstats;  // [2*N] (sum, sumsq) or nullptr
 };
 
+// Implicit-GEMM convolution on the same kernel (template parameter CONV). The activation operand is a 4-D
+// NHWC tensor map; a "row" of the GEMM is an output pixel and the rows of one tile are a
+// (2^lw x 2^lh x images) box of pixels, so the A tile of filter tap (ky, kx) is ONE TMA box at the tile's
+// origin shifted by the tap (out-of-image pixels and channels past Cin are zero-filled by the TMA unit:
+// 'same' padding and ragged channel counts cost nothing, and there is no im2col buffer).
+//   CONV 1 (forward / data gradient): k-block = (tap, 64-channel block); 128-pixel tiles.
+//   CONV 2 (weight gradient)        : one unit = one tap; k-blocks = 64-pixel boxes of the batch, both
+//                                     operands MN-major; output rows are offset by tap * Cin.
+struct ConvGeom {
+    int lw, lh;            // log2 of the pixel box's width / height (images per box = rows >> (lw + lh))
+    int tiles_w, tiles_h;  // pixel boxes per image along W / H
+    int OW, OH, NB;        // extent of the output pixels (CONV 1: masks the fused statistics)
+    int KW, cin_blocks, ntaps;
+    int pt, pl, sign;      // A-box origin = pixel + sign * (tap - pad)
+    int b_tap_stride;      // rows between taps in the 2-D weight map
+    int b_tap_on_k;        // 1: taps advance B's K coordinate (forward), 0: its N coordinate (data gradient)
+    int split_a;
+};
+
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
@@ -114,12 +133,13 @@ __device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the four e
 // CL = 2: CTA pairs (thread-block cluster of 2 along M). Both CTAs of a pair work on the same
 // n-tile and k-range with adjacent m-tiles; each loads its own A tile and HALF of the shared B tile,
 // multicast by TMA into both CTAs' shared memory, so the pair reads B from L2 once.
-template <int BN, bool A_MN, bool B_MN, int STAGES, int CL>
+template <int BN, bool A_MN, bool B_MN, int STAGES, int CL, int CONV>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmD, GemmEpi epi,
                                                               int M, int N, int K, int kb_per_split, int tiles_m,
-                                                              int tiles_n, int n_units) {
+                                                              int tiles_n, int n_units, ConvGeom cg) {
+    static_assert(CONV == 0 || CL == 1, "convolution modes run without CTA pairs");
     constexpr uint32_t A_BYTES = BM * BK * 2;
     constexpr uint32_t B_BYTES = BN * BK * 2;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -177,9 +197,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         uint32_t ps = 0, pph = 0;  // running stage / phase across units
         for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
             const int n0 = (unit % tiles_n) * BN;
-            const int m0 = (((unit / tiles_n) % tiles_m) * CL + (int)crank) * BM;
-            const int kb_begin = (unit / (tiles_n * tiles_m)) * kb_per_split;
+            const int mt = (unit / tiles_n) % tiles_m;
+            const int m0 = (mt * CL + (int)crank) * BM;
+            int rest = unit / (tiles_n * tiles_m), tap = 0;
+            if (CONV == 2) { tap = rest % cg.ntaps; rest /= cg.ntaps; }
+            const int kb_begin = rest * kb_per_split;
             const int nkb = min(total_kb, kb_begin + kb_per_split) - kb_begin;
+            int px0 = 0, py0 = 0, pimg = 0;  // CONV 1: origin of this tile's pixel box
+            if (CONV == 1) {
+                const int t2 = mt / cg.tiles_w;
+                px0 = (mt - t2 * cg.tiles_w) << cg.lw;
+                py0 = (t2 % cg.tiles_h) << cg.lh;
+                pimg = (t2 / cg.tiles_h) << (7 - cg.lw - cg.lh);
+            }
             for (int i = 0; i < nkb; ++i) {
                 const uint32_t s = ps, ph = pph;
                 if (++ps == STAGES) { ps = 0; pph ^= 1u; }
@@ -189,6 +219,39 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     const uint32_t sb = sa + A_BYTES;
                     const int k0 = (kb_begin + i) * BK;
                     mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+                    if (CONV == 1) {
+                        const int kb = kb_begin + i, tp = kb / cg.cin_blocks, cb = kb - tp * cg.cin_blocks;
+                        const int ky = tp / cg.KW, kx = tp - ky * cg.KW;
+                        if (cg.split_a) {  // experiment: the pixel box as two half-boxes
+                            tma_load_4d(sa, &tmA, full0 + 8 * s, cb * BK, px0 + cg.sign * (kx - cg.pl),
+                                        py0 + cg.sign * (ky - cg.pt), pimg);
+                            tma_load_4d(sa + A_BYTES / 2, &tmA, full0 + 8 * s, cb * BK, px0 + 64 + cg.sign * (kx - cg.pl),
+                                        py0 + cg.sign * (ky - cg.pt), pimg);
+                        } else
+                        tma_load_4d(sa, &tmA, full0 + 8 * s, cb * BK, px0 + cg.sign * (kx - cg.pl),
+                                    py0 + cg.sign * (ky - cg.pt), pimg);
+                        const int kB = cb * BK + (cg.b_tap_on_k ? tp * cg.b_tap_stride : 0);
+                        const int nB = n0 + (cg.b_tap_on_k ? 0 : tp * cg.b_tap_stride);
+                        if (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j)
+                                tma_load_2d(sb + j * (BK * 128), &tmB, full0 + 8 * s, nB + 64 * j, kB);
+                        } else {
+                            tma_load_2d(sb, &tmB, full0 + 8 * s, kB, nB);
+                        }
+                    } else if (CONV == 2) {
+                        const int pb = kb_begin + i, t2 = pb / cg.tiles_w;
+                        const int x0 = (pb - t2 * cg.tiles_w) << cg.lw, y0 = (t2 % cg.tiles_h) << cg.lh;
+                        const int img = (t2 / cg.tiles_h) << (6 - cg.lw - cg.lh);
+                        const int ky = tap / cg.KW, kx = tap - ky * cg.KW;
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j)
+                            tma_load_4d(sa + j * (BK * 128), &tmA, full0 + 8 * s, m0 + 64 * j, x0 + kx - cg.pl,
+                                        y0 + ky - cg.pt, img);
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_4d(sb + j * (BK * 128), &tmB, full0 + 8 * s, n0 + 64 * j, x0, y0, img);
+                    } else {
                     if (A_MN) {
 #pragma unroll
                         for (int j = 0; j < BM / 64; ++j)
@@ -218,6 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                             tma_load_2d_mc(sb + r0 * 128, &tmB, full0 + 8 * s, k0, n0 + r0, kMask);
                         }
                     }
+                    }
                 }
                 __syncwarp();
             }
@@ -238,7 +302,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         constexpr uint32_t STAGE_STEP = STAGE_BYTES >> 4;
         uint32_t s = 0, ph = 0, u = 0;
         for (int unit = cluster_id; unit < n_units; unit += n_clusters, ++u) {
-            const int kb_begin = (unit / (tiles_n * tiles_m)) * kb_per_split;
+            int rest = unit / (tiles_n * tiles_m);
+            if (CONV == 2) rest /= cg.ntaps;
+            const int kb_begin = rest * kb_per_split;
             const int nkb = min(total_kb, kb_begin + kb_per_split) - kb_begin;
             const uint32_t as = u & 1u;
             mbar_wait(tempty0 + 8 * as, ((u >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
@@ -285,7 +351,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         uint32_t u = 0;
         for (int unit = cluster_id; unit < n_units; unit += n_clusters, ++u) {
             const int n0 = (unit % tiles_n) * BN;
-            const int m0 = (((unit / tiles_n) % tiles_m) * CL + (int)crank) * BM;
+            const int mt = (unit / tiles_n) % tiles_m;
+            const int m0 = (mt * CL + (int)crank) * BM;
+            // where this warp's 32 rows go: GEMM rows, pixels of the tile's box (CONV 1), rows of the tap's
+            // [Cin, Cout] gradient slab (CONV 2)
+            int drow = m0 + q * 32, dx = 0, dy = 0, dimg = 0;
+            uint32_t rowmask = 0xffffffffu;  // CONV 1: rows of this warp's box that are real output pixels
+            if (CONV == 2) drow += ((unit / (tiles_n * tiles_m)) % cg.ntaps) * M;
+            if (CONV == 1) {
+                const int t2 = mt / cg.tiles_w, lwh = cg.lw + cg.lh;
+                const int x0 = (mt - t2 * cg.tiles_w) << cg.lw, y0 = (t2 % cg.tiles_h) << cg.lh;
+                const int i0 = (t2 / cg.tiles_h) << (7 - lwh);
+                const int r0 = q * 32, r = r0 + lane;
+                dx = x0 + (r0 & ((1 << cg.lw) - 1));
+                dy = y0 + ((r0 >> cg.lw) & ((1 << cg.lh) - 1));
+                dimg = i0 + (r0 >> lwh);
+                const bool ok = (x0 + (r & ((1 << cg.lw) - 1))) < cg.OW &&
+                                (y0 + ((r >> cg.lw) & ((1 << cg.lh) - 1))) < cg.OH && (i0 + (r >> lwh)) < cg.NB;
+                rowmask = __ballot_sync(0xffffffffu, ok);
+            }
+            const bool rows_live = CONV == 1 ? rowmask != 0u : (m0 + q * 32 < M);  // warp-uniform
             const uint32_t as = u & 1u;
             mbar_wait(tfull0 + 8 * as, (u >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -306,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     // registers -> swizzled staging box -> one TMA store per 32 x 32 chunk: the row-per-lane
                     // global stores this replaces cost 32 LSU cycles each (32 different lines per instruction);
                     // rows >= M and columns >= N are clipped by the TMA unit
-                    if (col0 < N && m0 + q * 32 < M) {  // warp-uniform
+                    if (col0 < N && rows_live) {  // warp-uniform
                         const uint32_t stg = stage_out0 + ((uint32_t)(warp - 2) * SD + sbox) * 2048u;
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SD - 1) : "memory");  // this box was read out
                         __syncwarp();
@@ -320,9 +405,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) {
-                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmD),
-                                         "r"(stg), "r"(col0), "r"(m0 + q * 32)
-                                         : "memory");
+                            if (CONV == 1)
+                                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmD),
+                                             "r"(stg), "r"(col0), "r"(dx), "r"(dy), "r"(dimg)
+                                             : "memory");
+                            else
+                                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmD),
+                                             "r"(stg), "r"(col0), "r"(drow)
+                                             : "memory");
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
                         last_box = stg;
@@ -333,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                     // fp32 store / split-K accumulation through the same 2 KB staging box, 16 columns (64-byte
                     // rows) at a time: TMA store, or TMA reduce-add into the fp32 gradient for OUT_ATOMIC_F32
-                    if (m0 + q * 32 < M) {  // warp-uniform
+                    if (CONV != 1 && rows_live) {  // warp-uniform (the convolution forward / data gradient store bf16 only)
                         const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
@@ -354,11 +444,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                             if (lane == 0) {
                                 if (epi.mode == OUT_F32)
                                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmD),
-                                                 "r"(stg), "r"(col0 + 16 * h), "r"(m0 + q * 32)
+                                                 "r"(stg), "r"(col0 + 16 * h), "r"(drow)
                                                  : "memory");
                                 else
                                     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmD),
-                                                 "r"(stg), "r"(col0 + 16 * h), "r"(m0 + q * 32)
+                                                 "r"(stg), "r"(col0 + 16 * h), "r"(drow)
                                                  : "memory");
                                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                             }
@@ -373,14 +463,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         // tried instead of the per-unit barrier below and were slower: 94 vs 81 us on
                         // 744000 x 128 x 128.)
                         float sx = 0.f, sy = 0.f, qx = 0.f, qy = 0.f;
-                        if (col0 < N && m0 + q * 32 < M) {
+                        if (col0 < N && rows_live) {
                             const uint32_t half = (uint32_t)lane >> 4, p = (uint32_t)lane & 15u;
                             const uint32_t base = last_box + half * 1024u + (p & 3u) * 4u;
                             const uint32_t jb = (p >> 2) << 4;
+                            const uint32_t mybits = rowmask >> (half * 16u);
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
                                 uint32_t w;
                                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + i * 64 + (jb ^ (((i >> 1) & 3) << 4))));
+                                if (CONV == 1 && !((mybits >> i) & 1u)) w = 0u;  // pixel outside the output: not a sample
                                 const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
                                 sx += lo; sy += hi;
                                 qx = fmaf(lo, lo, qx); qy = fmaf(hi, hi, qy);
@@ -464,12 +556,14 @@ int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long lon
     return SPNET_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, int CL>
+// CONV 0: tiles_m_conv / ntaps unused. CONV 1: tiles_m_conv = number of pixel tiles. CONV 2: ntaps = cg.ntaps.
+template <int BN, bool A_MN, bool B_MN, int CL, int CONV = 0>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, GemmEpi epi, int M, int N, int K,
-                int splits, cudaStream_t stream) {
-    constexpr int STAGES = (BN <= 128) ? 5 : 4;  // BN = 128: one ring stage traded for the second staging box
+                int splits, cudaStream_t stream, ConvGeom cg = ConvGeom(), int tiles_m_conv = 0) {
+    // BN = 128: one ring stage traded for the second staging box; BN = 64 (narrow convolutions): deep ring
+    constexpr int STAGES = BN <= 64 ? 7 : (BN <= 128) ? 5 : 4;
     constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + kEpiWarps * 2048 * (BN <= 128 ? 2 : 1);
-    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, CL>;
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, CL, CONV>;
     static bool configured = false;
     static int num_sms = 148;
     if (!configured) {
@@ -488,9 +582,9 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     if (splits > total_kb) splits = total_kb;
     const int kbps = (total_kb + splits - 1) / splits;
     splits = (total_kb + kbps - 1) / kbps;  // no empty splits
-    const int tiles_m = ((M + BM - 1) / BM + CL - 1) / CL;  // m-tile groups of CL
+    const int tiles_m = CONV == 1 ? tiles_m_conv : ((M + BM - 1) / BM + CL - 1) / CL;  // m-tile groups of CL
     const int tiles_n = (N + BN - 1) / BN;
-    const long long units = (long long)tiles_m * tiles_n * splits;
+    const long long units = (long long)tiles_m * tiles_n * splits * (CONV == 2 ? cg.ntaps : 1);
     if (units > 0x7fffffffLL) {
         spnet_set_error("gemm_bf16: too many tiles");
         return SPNET_ERR_ARG;
@@ -498,7 +592,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     const int max_clusters = num_sms / CL;
     const int grid = (int)(units < max_clusters ? units : max_clusters) * CL;
     cudaError_t e = spnet_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, CL, ta, tb, td, epi, M, N, K, kbps,
-                                     tiles_m, tiles_n, (int)units);
+                                     tiles_m, tiles_n, (int)units, cg);
     if (e != cudaSuccess) {
         spnet_set_error("gemm_bf16: launch: %s", cudaGetErrorString(e));
         return SPNET_ERR_CUDA;
@@ -580,6 +674,171 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
     if (wide) SPNET_GEMM_DISPATCH(256, 1);
     SPNET_GEMM_DISPATCH(128, 1);
 #undef SPNET_GEMM_DISPATCH
+}
+
+// ---------------------------------------------------------------------------------
+// implicit-GEMM convolutions (stride 1, any kernel size / padding, NHWC bf16)
+// ---------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+// pixel box (2^lw x 2^lh x 2^(log_rows-lw-lh) images) that wastes the fewest rows on overhang
+void pick_pixel_box(int log_rows, int OW, int OH, int NB, int* lw_out, int* lh_out) {
+    double best = -1.0;
+    for (int lw = 0; lw <= log_rows; ++lw)
+        for (int lh = 0; lw + lh <= log_rows; ++lh) {
+            const long long TW = 1 << lw, TH = 1 << lh, TN = 1 << (log_rows - lw - lh);
+            const long long cover = ((OW + TW - 1) / TW * TW) * ((OH + TH - 1) / TH * TH) * ((NB + TN - 1) / TN * TN);
+            const double util = (double)OW * OH * NB / (double)cover + 1e-6 * lw;  // ties: wider boxes
+            if (util > best) { best = util; *lw_out = lw; *lh_out = lh; }
+        }
+}
+
+// NHWC activation [NB, H, W, C] with pixel stride ld (elements): 4-D map, box = 64 channels x pixel box
+int make_pixel_map(CUtensorMap* map, const void* ptr, int NB, int H, int W, int C, long long ld, int lw, int lh, int ln,
+                   int box_c, CUtensorMapSwizzle swz, CUtensorMapL2promotion prom) {
+    PFN_cuTensorMapEncodeTiled enc = spnet_get_tensormap_encoder();
+    if (!enc) {
+        spnet_set_error("conv_tc: cuTensorMapEncodeTiled entry point not available");
+        return SPNET_ERR_CUDA;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, 1u << lw, 1u << lh, 1u << ln}, estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, prom, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        spnet_set_error("conv_tc: cuTensorMapEncodeTiled failed (%d) NB=%d H=%d W=%d C=%d ld=%lld box=%d,%d,%d,%d", (int)r, NB,
+                        H, W, C, ld, box_c, 1 << lw, 1 << lh, 1 << ln);
+        return SPNET_ERR_CUDA;
+    }
+    return SPNET_OK;
+}
+
+// forward (dgrad = 0): out[n, y, x, :] = sum_taps in[n, y + ky - pt, x + kx - pl, :] . Wt[ky, kx, :, :]
+// data gradient (dgrad = 1): out = dX [NB, OH, OW, Cin] from in = dY [NB, IH, IW, Cout]:
+//                            out[n, y, x, ci] = sum_taps in[n, y - ky + pt, x - kx + pl, :] . Wt[ky, kx, ci, :]
+// Wt is the Keras kernel [KH, KW, Cin, Cout]; c_in / c_out are the channel counts of `in` / `out`.
+int conv_tc_fwd_like(bool dgrad, const void* in, long long ld_in, int NB, int IH, int IW, int c_in, const void* Wt,
+                     int Cin, int Cout, void* out, long long ld_out, int OH, int OW, int c_out, int KH, int KW, int pt,
+                     int pl, double* colstats, cudaStream_t stream) {
+    ConvGeom cg = {};
+    pick_pixel_box(7, OW, OH, NB, &cg.lw, &cg.lh);
+    const int ln = 7 - cg.lw - cg.lh;
+    cg.tiles_w = (OW + (1 << cg.lw) - 1) >> cg.lw;
+    cg.tiles_h = (OH + (1 << cg.lh) - 1) >> cg.lh;
+    const int groups = (NB + (1 << ln) - 1) >> ln;
+    cg.OW = OW; cg.OH = OH; cg.NB = NB;
+    cg.KW = KW; cg.ntaps = KH * KW;
+    cg.cin_blocks = (c_in + BK - 1) / BK;
+    cg.pt = pt; cg.pl = pl; cg.sign = dgrad ? -1 : 1;
+    cg.b_tap_stride = Cin;
+    cg.b_tap_on_k = dgrad ? 0 : 1;
+    const long long tiles_m = (long long)cg.tiles_w * cg.tiles_h * groups;
+    SPNET_REQUIRE(tiles_m < (1 << 24), "conv_tc: too many pixel tiles");
+    const int N = c_out, K = cg.ntaps * cg.cin_blocks * BK;
+    const int bn = N <= 64 ? 64 : 128;
+    CUtensorMap ta, tb, td;
+    cg.split_a = getenv("SPNET_CONV_SPLIT_A") != nullptr && cg.lw == 7;
+    int rc = make_pixel_map(&ta, in, NB, IH, IW, c_in, ld_in, cg.split_a ? 6 : cg.lw, cg.lh, ln, BK, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+    // weights as one 2-D matrix: forward [taps*Cin (k), Cout (n)] MN-major; data gradient: rows (n) = tap*Cin + ci,
+    // k = Cout contiguous, K-major
+    if (!dgrad) rc = make_operand_map(&tb, Wt, Cout, (long long)cg.ntaps * Cin, Cout, true, bn);
+    else rc = make_operand_map(&tb, Wt, (long long)cg.ntaps * Cin, Cout, Cout, false, bn);
+    if (rc) return rc;
+    {   // output boxes: this epilogue warp's 32 rows of the tile = a (bw x bh x bn) sub-box of pixels
+        const int lbw = cg.lw < 5 ? cg.lw : 5, lbh = cg.lh < 5 - lbw ? cg.lh : 5 - lbw, lbn = 5 - lbw - lbh;
+        rc = make_pixel_map(&td, out, NB, OH, OW, c_out, ld_out, lbw, lbh, lbn, 32, CU_TENSOR_MAP_SWIZZLE_64B,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE);
+        if (rc) return rc;
+    }
+    GemmEpi epi = {out, ld_out, OUT_BF16, colstats};
+    const int M = (int)(tiles_m * BM);
+    if (!dgrad) {
+        if (bn == 64) return launch_gemm<64, false, true, 1, 1>(ta, tb, td, epi, M, N, K, 1, stream, cg, (int)tiles_m);
+        return launch_gemm<128, false, true, 1, 1>(ta, tb, td, epi, M, N, K, 1, stream, cg, (int)tiles_m);
+    }
+    if (bn == 64) return launch_gemm<64, false, false, 1, 1>(ta, tb, td, epi, M, N, K, 1, stream, cg, (int)tiles_m);
+    return launch_gemm<128, false, false, 1, 1>(ta, tb, td, epi, M, N, K, 1, stream, cg, (int)tiles_m);
+}
+
+}  // namespace
+
+extern "C" {
+
+#define SPNET_CONV_TC_CHECKS(X, ldx, Wt, Y, ldy, Cin, Cout)                                                          \
+    SPNET_REQUIRE(X && Wt && Y, "conv_tc: null pointer");                                                            \
+    SPNET_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= Cin && ldy >= Cout,        \
+                  "conv_tc: channel counts and pixel strides must be multiples of 8 (Cin %d Cout %d)", Cin, Cout);   \
+    SPNET_REQUIRE(((uintptr_t)X % 16 == 0) && ((uintptr_t)Wt % 16 == 0) && ((uintptr_t)Y % 16 == 0),                 \
+                  "conv_tc: pointers must be 16-byte aligned")
+
+// Y[NB, OH, OW, Cout] = conv(X[NB, H, W, Cin], Wt[KH, KW, Cin, Cout]), stride 1, top / left padding pt / pl
+// (bottom / right padding is whatever OH / OW imply), bf16 in / out, fp32 accumulation; optional fused
+// per-channel sum / sum of squares of Y as stored (fp64 [2*Cout], atomically added).
+int spnet_conv_tc_fwd(const void* X, long long ldx, int NB, int H, int W, int Cin, const void* Wt, void* Y, long long ldy,
+                      int OH, int OW, int Cout, int KH, int KW, int pt, int pl, double* colstats, cudaStream_t stream) {
+    SPNET_CONV_TC_CHECKS(X, ldx, Wt, Y, ldy, Cin, Cout);
+    SPNET_REQUIRE(NB > 0 && OH > 0 && OW > 0 && KH > 0 && KW > 0, "conv_tc_fwd: bad shape");
+    return conv_tc_fwd_like(false, X, ldx, NB, H, W, Cin, Wt, Cin, Cout, Y, ldy, OH, OW, Cout, KH, KW, pt, pl, colstats,
+                            stream);
+}
+
+// dX[NB, H, W, Cin] = data gradient of the convolution above from dY[NB, OH, OW, Cout] (overwrites dX)
+int spnet_conv_tc_dgrad(const void* dY, long long ldy, int NB, int OH, int OW, int Cout, const void* Wt, void* dX,
+                        long long ldx, int H, int W, int Cin, int KH, int KW, int pt, int pl, cudaStream_t stream) {
+    SPNET_CONV_TC_CHECKS(dX, ldx, Wt, dY, ldy, Cin, Cout);
+    SPNET_REQUIRE(NB > 0 && OH > 0 && OW > 0 && KH > 0 && KW > 0, "conv_tc_dgrad: bad shape");
+    return conv_tc_fwd_like(true, dY, ldy, NB, OH, OW, Cout, Wt, Cin, Cout, dX, ldx, H, W, Cin, KH, KW, pt, pl, nullptr,
+                            stream);
+}
+
+// dW[KH, KW, Cin, Cout] (fp32) += sum over pixels X[n, y + ky - pt, x + kx - pl, ci] * dY[n, y, x, co]
+// (TMA reduce-add: the caller zeroes dW or accumulates into it on purpose).
+int spnet_conv_tc_wgrad(const void* X, long long ldx, int NB, int H, int W, int Cin, const void* dY, long long ldy, int OH,
+                        int OW, int Cout, float* dW, int KH, int KW, int pt, int pl, cudaStream_t stream) {
+    SPNET_CONV_TC_CHECKS(X, ldx, dW, dY, ldy, Cin, Cout);
+    SPNET_REQUIRE(NB > 0 && OH > 0 && OW > 0 && KH > 0 && KW > 0, "conv_tc_wgrad: bad shape");
+    ConvGeom cg = {};
+    pick_pixel_box(6, OW, OH, NB, &cg.lw, &cg.lh);
+    const int ln = 6 - cg.lw - cg.lh;
+    cg.tiles_w = (OW + (1 << cg.lw) - 1) >> cg.lw;
+    cg.tiles_h = (OH + (1 << cg.lh) - 1) >> cg.lh;
+    const int groups = (NB + (1 << ln) - 1) >> ln;
+    cg.OW = OW; cg.OH = OH; cg.NB = NB;
+    cg.KW = KW; cg.ntaps = KH * KW;
+    cg.cin_blocks = 1;
+    cg.pt = pt; cg.pl = pl; cg.sign = 1;
+    const long long pixel_blocks = (long long)cg.tiles_w * cg.tiles_h * groups;
+    SPNET_REQUIRE(pixel_blocks < (1 << 24), "conv_tc_wgrad: too many pixel blocks");
+    const int M = Cin, N = Cout, K = (int)pixel_blocks * BK;
+    const int bn = N <= 64 ? 64 : 128;
+    CUtensorMap ta, tb, td;
+    int rc = make_pixel_map(&ta, X, NB, H, W, Cin, ldx, cg.lw, cg.lh, ln, 64, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+    rc = make_pixel_map(&tb, dY, NB, OH, OW, Cout, ldy, cg.lw, cg.lh, ln, 64, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+    {
+        PFN_cuTensorMapEncodeTiled enc = spnet_get_tensormap_encoder();
+        cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)cg.ntaps * M}, strides[1] = {(cuuint64_t)N * 4};
+        cuuint32_t box[2] = {16u, 32u}, estr[2] = {1, 1};
+        CUresult r = enc(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dW, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SPNET_REQUIRE(r == CUDA_SUCCESS, "conv_tc_wgrad: cuTensorMapEncodeTiled (output) failed (%d)", (int)r);
+    }
+    // split the pixel reduction so that taps x tiles x splits fills the SMs about once; >= 4 pixel blocks per split
+    const long long tiles = (long long)((M + BM - 1) / BM) * ((N + bn - 1) / bn) * cg.ntaps;
+    long long sp = tiles >= 148 ? 1 : 148 / tiles;
+    if (sp > pixel_blocks / 4) sp = pixel_blocks / 4;
+    const int splits = (int)(sp < 1 ? 1 : sp);
+    GemmEpi epi = {dW, N, OUT_ATOMIC_F32, nullptr};
+    if (bn == 64) return launch_gemm<64, true, true, 1, 2>(ta, tb, td, epi, M, N, K, splits, stream, cg, 0);
+    return launch_gemm<128, true, true, 1, 2>(ta, tb, td, epi, M, N, K, splits, stream, cg, 0);
 }
 
 }  // extern "C"

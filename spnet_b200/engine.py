@@ -824,7 +824,7 @@ class InceptionResNetV2SPNetEngine(SPNetEngineBase):
             o = op["out"]
             if op["kind"] == "conv_bn":
                 op["z"] = A(B, o.h, o.w, o.c)
-                if not (op["kh"] == 1 and op["kw"] == 1 and op["stride"] == 1) and op["cin"] != 3:
+                if not (op["kh"] == 1 and op["kw"] == 1 and op["stride"] == 1) and op["cin"] != 3 and not self._implicit(op):
                     col_el = max(col_el, B * o.h * o.w * op["kh"] * op["kw"] * op["cin"])
             elif op["kind"] == "maxpool":
                 op["argmax"] = A(B, o.h, o.w, o.c, dtype=torch.uint8) if train else None
@@ -844,6 +844,11 @@ class InceptionResNetV2SPNetEngine(SPNetEngineBase):
             self.grad[out.idx] = self.gfeat.view(B, out.h, out.w, out.c)
 
     # ---- helpers
+    def _implicit(self, op):
+        """k x k stride-1 convolutions of the bf16 engine run as implicit GEMM (csrc/gemm_tc.cu CONV modes): no
+        im2col / col2im buffers. fp32 and the few stride-2 convolutions keep the im2col + GEMM route."""
+        return self.lowp and op["stride"] == 1 and (op["kh"] > 1 or op["kw"] > 1) and op["cin"] != 3
+
     def _conv_operand(self, op, x):
         """GEMM A operand [M, K] of a convolution: the activation itself for 1x1, an im2col buffer otherwise."""
         o = op["out"]
@@ -865,6 +870,10 @@ class InceptionResNetV2SPNetEngine(SPNetEngineBase):
                 M = B * o.h * o.w
                 if op["cin"] == 3:  # first convolution: 3x3 stride 2 'valid' on the 3-channel stem output
                     ops.conv_small_fwd(2, xs[0], w[op["name"] + "/kernel"], z, stats=bn.stats if training else None)
+                    self._bn_ready(bn, M, training)
+                elif self._implicit(op):
+                    ops.conv_tc_fwd(xs[0], wl[op["name"] + "/kernel"], z, op["pt"], op["pl"],
+                                    colstats=bn.stats if training else None)
                     self._bn_ready(bn, M, training)
                 else:
                     A_, M, K = self._conv_operand(op, xs[0])
@@ -918,6 +927,12 @@ class InceptionResNetV2SPNetEngine(SPNetEngineBase):
                 if op["cin"] == 3:
                     ops.conv_small_wgrad(2, xs[0], dz, gW)
                     ops.conv_small_dgrad(2, dz, w[op["name"] + "/kernel"], ga)
+                    continue
+                if self._implicit(op):
+                    ops.conv_tc_wgrad(xs[0], dz, gW, op["pt"], op["pl"])
+                    tgt = self._into(ins[0], op["first"][0])
+                    ops.conv_tc_dgrad(dz, wl[op["name"] + "/kernel"], tgt, op["pt"], op["pl"])
+                    self._merge(ins[0], op["first"][0])
                     continue
                 A_, M, K = self._conv_operand(op, xs[0])
                 Wl = wl[op["name"] + "/kernel"].view(K, o.c)

@@ -154,6 +154,38 @@ def gemm_simt(A, a_mn, B, b_mn, D, M, N, K, out_mode=OUT_T, splits=1, colstats=N
     return D
 
 
+def conv_tc_fwd(x, wt, y, pt, pl, colstats=None, ldx=None, ldy=None):
+    """y[B,OH,OW,Cout] = conv(x[B,H,W,Cin], wt[KH,KW,Cin,Cout]), stride 1, bf16, implicit GEMM on tcgen05.
+    x / y may be channel slices of wider NHWC buffers (ldx / ldy = pixel stride in elements)."""
+    _chk(wt, colstats)
+    assert x.is_cuda and y.is_cuda and (ldx is not None or x.is_contiguous()) and (ldy is not None or y.is_contiguous())
+    B, H, W, Cin = x.shape
+    KH, KW, _, Cout = wt.shape
+    lib().conv_tc_fwd(_p(x), ldx or Cin, B, H, W, Cin, _p(wt), _p(y), ldy or Cout, y.shape[1], y.shape[2], Cout, KH, KW,
+                      pt, pl, _p(colstats), _s())
+    return y
+
+
+def conv_tc_dgrad(gy, wt, gx, pt, pl, ldy=None, ldx=None):
+    """gx[B,H,W,Cin] = data gradient of conv_tc_fwd from gy[B,OH,OW,Cout] (overwrites gx)."""
+    _chk(gy, wt, gx)
+    B, OH, OW, Cout = gy.shape
+    KH, KW, Cin, _ = wt.shape
+    lib().conv_tc_dgrad(_p(gy), ldy or Cout, B, OH, OW, Cout, _p(wt), _p(gx), ldx or Cin, gx.shape[1], gx.shape[2], Cin,
+                        KH, KW, pt, pl, _s())
+    return gx
+
+
+def conv_tc_wgrad(x, gy, gw, pt, pl, ldx=None, ldy=None):
+    """gw[KH,KW,Cin,Cout] (fp32) += x (*) gy."""
+    _chk(x, gy, gw)
+    B, H, W, Cin = x.shape
+    _, OH, OW, Cout = gy.shape
+    KH, KW = gw.shape[0], gw.shape[1]
+    lib().conv_tc_wgrad(_p(x), ldx or Cin, B, H, W, Cin, _p(gy), ldy or Cout, OH, OW, Cout, _p(gw), KH, KW, pt, pl, _s())
+    return gw
+
+
 # ----------------------------------------------------------------------------- batch norm
 def bn_finalize(stats, count, gamma, beta, a, b, save_mean, save_rstd, moving_mean=None, moving_var=None,
                 eps=1e-3, momentum=0.99, unbiased=True):

@@ -579,3 +579,90 @@ def test_fullsize_depthwise_adjoint_identities(shape):
     y2 = ops.dwconv3x3_fwd(2.0 * x + 1.0, k)
     ones = ops.dwconv3x3_fwd(torch.ones_like(x), k)
     torch.testing.assert_close(y2, 2.0 * y + ones, rtol=1e-4, atol=1e-4)
+
+
+# ----------------------------------------------------------------------------- implicit-GEMM convolutions
+# (B, H, W, Cin, Cout, KH, KW, pad): Xception block1_conv2 ('valid' 3x3, 32 -> 64), InceptionResNetV2 branch
+# shapes (3x3 / 5x5 'same', 1x7, 7x1, 1x3, 3x1; ragged channel counts; tiny feature maps spanning images)
+CONV_TC_CASES = [
+    (2, 31, 43, 32, 64, 3, 3, "valid"),
+    (3, 21, 29, 48, 64, 5, 5, "same"),
+    (2, 21, 29, 64, 96, 3, 3, "same"),
+    (5, 10, 14, 128, 160, 1, 7, "same"),
+    (5, 10, 14, 160, 192, 7, 1, "same"),
+    (9, 4, 6, 192, 224, 1, 3, "same"),
+    (9, 4, 6, 224, 256, 3, 1, "same"),
+    (2, 46, 62, 80, 192, 3, 3, "valid"),
+    (1, 9, 140, 32, 32, 3, 3, "same"),
+]
+
+
+def _conv_tc_inputs(case, seed=0):
+    B, H, W, Cin, Cout, KH, KW, pad = case
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(B, H, W, Cin, generator=g).to(dev()).bfloat16()
+    wt = (torch.randn(KH, KW, Cin, Cout, generator=g) / (KH * KW * Cin) ** 0.5).to(dev()).bfloat16()
+    if pad == "same":
+        OH, OW, pt, pl = H, W, (KH - 1) // 2, (KW - 1) // 2
+    else:
+        OH, OW, pt, pl = H - KH + 1, W - KW + 1, 0, 0
+    return x, wt, OH, OW, pt, pl
+
+
+def _conv_ref(x, wt, pad, KH, KW):
+    p = ((KH - 1) // 2, (KW - 1) // 2) if pad == "same" else 0
+    return F.conv2d(nchw(x), wt.float().permute(3, 2, 0, 1).contiguous(), padding=p)
+
+
+@pytest.mark.parametrize("case", CONV_TC_CASES)
+def test_conv_tc_fwd_and_stats(case):
+    ops = _ops()
+    B, H, W, Cin, Cout, KH, KW, pad = case
+    x, wt, OH, OW, pt, pl = _conv_tc_inputs(case)
+    ref = nhwc(_conv_ref(x, wt, pad, KH, KW))
+    y = torch.full((B, OH, OW, Cout), float("nan"), device=dev(), dtype=torch.bfloat16)
+    stats = torch.zeros(2 * Cout, device=dev(), dtype=torch.float64)
+    ops.conv_tc_fwd(x, wt, y, pt, pl, colstats=stats)
+    torch.testing.assert_close(y.float(), ref, rtol=2e-2, atol=2e-2)
+    yf = y.double().view(-1, Cout)
+    torch.testing.assert_close(stats[:Cout], yf.sum(0), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(stats[Cout:], (yf * yf).sum(0), rtol=1e-5, atol=1e-3)
+
+
+def test_conv_tc_fwd_channel_slices():
+    """Input and output as channel slices of wider NHWC buffers (concat targets), untouched neighbours."""
+    ops = _ops()
+    case = (3, 21, 29, 64, 96, 3, 3, "same")
+    B, H, W, Cin, Cout, KH, KW, pad = case
+    x, wt, OH, OW, pt, pl = _conv_tc_inputs(case, seed=3)
+    xw = torch.randn(B, H, W, Cin + 40, device=dev()).bfloat16()
+    xw[..., 8:8 + Cin] = x
+    yw = torch.full((B, OH, OW, Cout + 64), 7.0, device=dev(), dtype=torch.bfloat16)
+    ops.conv_tc_fwd(xw[..., 8:8 + Cin], wt, yw[..., 32:32 + Cout], pt, pl, ldx=Cin + 40, ldy=Cout + 64)
+    ref = nhwc(_conv_ref(x, wt, pad, KH, KW))
+    torch.testing.assert_close(yw[..., 32:32 + Cout].float(), ref, rtol=2e-2, atol=2e-2)
+    assert bool((yw[..., :32] == 7.0).all()) and bool((yw[..., 32 + Cout:] == 7.0).all())
+
+
+@pytest.mark.parametrize("case", CONV_TC_CASES)
+def test_conv_tc_dgrad_wgrad(case):
+    ops = _ops()
+    B, H, W, Cin, Cout, KH, KW, pad = case
+    x, wt, OH, OW, pt, pl = _conv_tc_inputs(case, seed=1)
+    g = torch.Generator(device="cpu").manual_seed(2)
+    gy = torch.randn(B, OH, OW, Cout, generator=g).to(dev()).bfloat16()
+    # exact reference: fp64 on the CPU (cuDNN's fp32 weight-gradient algorithms are themselves ~1e-3 of the scale)
+    xr = nchw(x).double().cpu().requires_grad_(True)
+    wr = wt.double().permute(3, 2, 0, 1).contiguous().cpu().requires_grad_(True)
+    p = ((KH - 1) // 2, (KW - 1) // 2) if pad == "same" else 0
+    F.conv2d(xr, wr, padding=p).backward(nchw(gy).double().cpu())
+    gx = torch.full((B, H, W, Cin), float("nan"), device=dev(), dtype=torch.bfloat16)
+    ops.conv_tc_dgrad(gy, wt, gx, pt, pl)
+    torch.testing.assert_close(gx.float(), nhwc(xr.grad).float().to(dev()), rtol=2e-2, atol=2e-2)
+    gw = torch.zeros(KH, KW, Cin, Cout, device=dev())
+    ops.conv_tc_wgrad(x, gy, gw, pt, pl)
+    ref_w = wr.grad.permute(2, 3, 1, 0).contiguous().float().to(dev())
+    scale = float(ref_w.abs().max())
+    torch.testing.assert_close(gw, ref_w, rtol=2e-3, atol=2e-3 * scale)
+    ops.conv_tc_wgrad(x, gy, gw, pt, pl)  # reduce-add: a second call accumulates
+    torch.testing.assert_close(gw, 2 * ref_w, rtol=2e-3, atol=4e-3 * scale)
