@@ -25,7 +25,13 @@ constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;    // two per TMEM lane quadrant, each draining half of the columns
-constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA warp, MMA warp, epilogue warps
+// The producer's per-k-block instruction stream (barrier poll, coordinates, expect_tx, one issue sequence per
+// box) is a single-warp dependent chain of a few hundred cycles; the convolution modes, whose k-blocks are
+// short (N <= 128) and carry 2..4 boxes with 4-D coordinates, spread the boxes over kConvProducers warps.
+// The plain GEMM is not producer-bound (its producer finds the ring full) and keeps one.
+constexpr int kConvProducers = 4;
+__host__ __device__ constexpr int n_producers(int conv) { return conv ? kConvProducers : 1; }
+__host__ __device__ constexpr int n_threads(int conv) { return 64 + 32 * kEpiWarps + 32 * (n_producers(conv) - 1); }  // TMA, MMA, epilogue, extra TMA warps
 
 enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_ATOMIC_F32 = 2 };
 
@@ -52,7 +58,6 @@ struct ConvGeom {
     int pt, pl, sign;      // A-box origin = pixel + sign * (tap - pad)
     int b_tap_stride;      // rows between taps in the 2-D weight map
     int b_tap_on_k;        // 1: taps advance B's K coordinate (forward), 0: its N coordinate (data gradient)
-    int split_a;
 };
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -134,15 +139,24 @@ __device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the four e
 // n-tile and k-range with adjacent m-tiles; each loads its own A tile and HALF of the shared B tile,
 // multicast by TMA into both CTAs' shared memory, so the pair reads B from L2 once.
 template <int BN, bool A_MN, bool B_MN, int STAGES, int CL, int CONV>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmD, GemmEpi epi,
                                                               int M, int N, int K, int kb_per_split, int tiles_m,
                                                               int tiles_n, int n_units, ConvGeom cg) {
     static_assert(CONV == 0 || CL == 1, "convolution modes run without CTA pairs");
+    constexpr int kProducers = n_producers(CONV);
     constexpr uint32_t A_BYTES = BM * BK * 2;
     constexpr uint32_t B_BYTES = BN * BK * 2;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    // TMA boxes per k-block issued by THIS CTA: A is one 128-row box (K-major) or BM/64 atoms (MN-major);
+    // B one box (K-major) or BN/64 atoms (MN-major), of which a CTA of a pair issues 1/CL (multicast)
+    constexpr int NA_BOX = (A_MN || CONV == 2) ? BM / 64 : 1;
+    constexpr int NB_BOX = (B_MN || CONV == 2) ? BN / 64 / CL : 1;
+    constexpr int N_BOX = NA_BOX + NB_BOX;
+    constexpr int kActiveProducers = N_BOX < kProducers ? N_BOX : kProducers;
+    constexpr uint32_t A_BOX_BYTES = A_BYTES / NA_BOX;
+    constexpr uint32_t B_BOX_BYTES = B_BYTES / (NB_BOX * CL);  // what one of this CTA's B boxes lands (in each CTA of the pair)
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -168,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, 1);
+            mbar_init(full0 + 8 * s, kActiveProducers);  // one arrive.expect_tx per producer warp that owns boxes
             mbar_init(empty0 + 8 * s, CL);  // every CTA of the cluster must have consumed the stage
         }
         for (int a = 0; a < 2; ++a) {
@@ -192,9 +206,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     pdl_wait();  // the set-up above overlapped the previous kernel's tail; global memory from here on
     // with CL = 2, tiles_m counts m-tile PAIRS; this CTA owns m-tile 2*pair + rank
 
-    if (warp == 0) {
-        // ---------------- TMA producer ----------------
+    // producer index of this warp: warp 0 and the warps after the epilogue group
+    const int prod = warp == 0 ? 0 : (warp >= 2 + kEpiWarps ? warp - (1 + kEpiWarps) : -1);
+    if (prod >= 0) {
+        // ---------------- TMA producers ----------------
+        // producer p issues boxes p, p + kProducers, ... of every k-block and announces their bytes on the
+        // stage's full barrier (B boxes of a CTA pair land in both CTAs: each CTA expects CL x its own)
+        uint32_t my_bytes = 0;
+#pragma unroll
+        for (int j = 0; j < N_BOX; ++j)
+            if (j % kProducers == prod) my_bytes += j < NA_BOX ? A_BOX_BYTES : B_BOX_BYTES * CL;
         uint32_t ps = 0, pph = 0;  // running stage / phase across units
+        if (prod < kActiveProducers)
         for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
             const int n0 = (unit % tiles_n) * BN;
             const int mt = (unit / tiles_n) % tiles_m;
@@ -203,84 +226,82 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             if (CONV == 2) { tap = rest % cg.ntaps; rest /= cg.ntaps; }
             const int kb_begin = rest * kb_per_split;
             const int nkb = min(total_kb, kb_begin + kb_per_split) - kb_begin;
+            // convolution modes: the k-block -> (tap, channel block) / pixel-box decode runs on counters; a
+            // division per k-block made this single-warp instruction stream (~800 cycles per k-block) the
+            // bottleneck of the whole kernel
             int px0 = 0, py0 = 0, pimg = 0;  // CONV 1: origin of this tile's pixel box
+            int c_cb = 0, c_kx = 0, c_ky = 0, c_tp = 0;  // CONV 1: channel block, tap of the next k-block
+            int c_tx = 0, c_ty = 0, c_g = 0, w_kx = 0, w_ky = 0;  // CONV 2: pixel box of the next k-block; this unit's tap
             if (CONV == 1) {
                 const int t2 = mt / cg.tiles_w;
                 px0 = (mt - t2 * cg.tiles_w) << cg.lw;
                 py0 = (t2 % cg.tiles_h) << cg.lh;
                 pimg = (t2 / cg.tiles_h) << (7 - cg.lw - cg.lh);
+                c_tp = kb_begin / cg.cin_blocks; c_cb = kb_begin - c_tp * cg.cin_blocks;
+                c_ky = c_tp / cg.KW; c_kx = c_tp - c_ky * cg.KW;
+            }
+            if (CONV == 2) {
+                const int t2 = kb_begin / cg.tiles_w;
+                c_tx = kb_begin - t2 * cg.tiles_w; c_ty = t2 % cg.tiles_h; c_g = t2 / cg.tiles_h;
+                w_ky = tap / cg.KW; w_kx = tap - w_ky * cg.KW;
             }
             for (int i = 0; i < nkb; ++i) {
                 const uint32_t s = ps, ph = pph;
                 if (++ps == STAGES) { ps = 0; pph ^= 1u; }
+                // coordinates that depend on the mode (warp-uniform, computed before the wait)
+                const int k0 = (kb_begin + i) * BK;
+                int ax = 0, ay = 0, aimg = 0, bx = 0, by = 0, kA = k0, kB = k0, nB = n0;
+                if (CONV == 1) {
+                    kA = c_cb * BK;
+                    ax = px0 + cg.sign * (c_kx - cg.pl); ay = py0 + cg.sign * (c_ky - cg.pt); aimg = pimg;
+                    kB = kA + (cg.b_tap_on_k ? c_tp * cg.b_tap_stride : 0);
+                    nB = n0 + (cg.b_tap_on_k ? 0 : c_tp * cg.b_tap_stride);
+                    if (++c_cb == cg.cin_blocks) {
+                        c_cb = 0; ++c_tp;
+                        if (++c_kx == cg.KW) { c_kx = 0; ++c_ky; }
+                    }
+                } else if (CONV == 2) {
+                    bx = c_tx << cg.lw; by = c_ty << cg.lh;
+                    aimg = c_g << (6 - cg.lw - cg.lh);
+                    ax = bx + w_kx - cg.pl; ay = by + w_ky - cg.pt;
+                    if (++c_tx == cg.tiles_w) {
+                        c_tx = 0;
+                        if (++c_ty == cg.tiles_h) { c_ty = 0; ++c_g; }
+                    }
+                }
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
                     const uint32_t sb = sa + A_BYTES;
-                    const int k0 = (kb_begin + i) * BK;
-                    mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
-                    if (CONV == 1) {
-                        const int kb = kb_begin + i, tp = kb / cg.cin_blocks, cb = kb - tp * cg.cin_blocks;
-                        const int ky = tp / cg.KW, kx = tp - ky * cg.KW;
-                        if (cg.split_a) {  // experiment: the pixel box as two half-boxes
-                            tma_load_4d(sa, &tmA, full0 + 8 * s, cb * BK, px0 + cg.sign * (kx - cg.pl),
-                                        py0 + cg.sign * (ky - cg.pt), pimg);
-                            tma_load_4d(sa + A_BYTES / 2, &tmA, full0 + 8 * s, cb * BK, px0 + 64 + cg.sign * (kx - cg.pl),
-                                        py0 + cg.sign * (ky - cg.pt), pimg);
-                        } else
-                        tma_load_4d(sa, &tmA, full0 + 8 * s, cb * BK, px0 + cg.sign * (kx - cg.pl),
-                                    py0 + cg.sign * (ky - cg.pt), pimg);
-                        const int kB = cb * BK + (cg.b_tap_on_k ? tp * cg.b_tap_stride : 0);
-                        const int nB = n0 + (cg.b_tap_on_k ? 0 : tp * cg.b_tap_stride);
-                        if (B_MN) {
+                    const uint32_t bar = full0 + 8 * s;
+                    mbar_expect_tx(bar, my_bytes);
 #pragma unroll
-                            for (int j = 0; j < BN / 64; ++j)
-                                tma_load_2d(sb + j * (BK * 128), &tmB, full0 + 8 * s, nB + 64 * j, kB);
+                    for (int j = 0; j < N_BOX; ++j) {
+                        if (j % kProducers != prod) continue;
+                        if (j < NA_BOX) {
+                            if (CONV == 1) tma_load_4d(sa, &tmA, bar, kA, ax, ay, aimg);
+                            else if (CONV == 2) tma_load_4d(sa + j * (BK * 128), &tmA, bar, m0 + 64 * j, ax, ay, aimg);
+                            else if (A_MN) tma_load_2d(sa + j * (BK * 128), &tmA, bar, m0 + 64 * j, k0);
+                            else tma_load_2d(sa, &tmA, bar, k0, m0);
                         } else {
-                            tma_load_2d(sb, &tmB, full0 + 8 * s, kB, nB);
-                        }
-                    } else if (CONV == 2) {
-                        const int pb = kb_begin + i, t2 = pb / cg.tiles_w;
-                        const int x0 = (pb - t2 * cg.tiles_w) << cg.lw, y0 = (t2 % cg.tiles_h) << cg.lh;
-                        const int img = (t2 / cg.tiles_h) << (6 - cg.lw - cg.lh);
-                        const int ky = tap / cg.KW, kx = tap - ky * cg.KW;
-#pragma unroll
-                        for (int j = 0; j < BM / 64; ++j)
-                            tma_load_4d(sa + j * (BK * 128), &tmA, full0 + 8 * s, m0 + 64 * j, x0 + kx - cg.pl,
-                                        y0 + ky - cg.pt, img);
-#pragma unroll
-                        for (int j = 0; j < BN / 64; ++j)
-                            tma_load_4d(sb + j * (BK * 128), &tmB, full0 + 8 * s, n0 + 64 * j, x0, y0, img);
-                    } else {
-                    if (A_MN) {
-#pragma unroll
-                        for (int j = 0; j < BM / 64; ++j)
-                            tma_load_2d(sa + j * (BK * 128), &tmA, full0 + 8 * s, m0 + 64 * j, k0);
-                    } else {
-                        tma_load_2d(sa, &tmA, full0 + 8 * s, k0, m0);
-                    }
-                    if (CL == 1) {
-                        if (B_MN) {
-#pragma unroll
-                            for (int j = 0; j < BN / 64; ++j)
-                                tma_load_2d(sb + j * (BK * 128), &tmB, full0 + 8 * s, n0 + 64 * j, k0);
-                        } else {
-                            tma_load_2d(sb, &tmB, full0 + 8 * s, k0, n0);
-                        }
-                    } else {
-                        // this CTA's half of the B tile, written into BOTH CTAs' stage (same smem offset,
-                        // completing on the same barrier offset in each destination CTA)
-                        if (B_MN) {
-#pragma unroll
-                            for (int j = 0; j < BN / 64 / CL; ++j) {
-                                const int jj = (int)crank * (BN / 64 / CL) + j;
-                                tma_load_2d_mc(sb + jj * (BK * 128), &tmB, full0 + 8 * s, n0 + 64 * jj, k0, kMask);
+                            const int jb = j - NA_BOX;
+                            if (CONV == 2) {
+                                tma_load_4d(sb + jb * (BK * 128), &tmB, bar, n0 + 64 * jb, bx, by, aimg);
+                            } else if (CL == 1) {
+                                if (B_MN) tma_load_2d(sb + jb * (BK * 128), &tmB, bar, nB + 64 * jb, kB);
+                                else tma_load_2d(sb, &tmB, bar, kB, nB);
+                            } else {
+                                // this CTA's half of the B tile, written into BOTH CTAs' stage (same smem offset,
+                                // completing on the same barrier offset in each destination CTA)
+                                if (B_MN) {
+                                    const int jj = (int)crank * NB_BOX + jb;
+                                    tma_load_2d_mc(sb + jj * (BK * 128), &tmB, bar, n0 + 64 * jj, k0, kMask);
+                                } else {
+                                    const int r0 = (int)crank * (BN / CL);
+                                    tma_load_2d_mc(sb + r0 * 128, &tmB, bar, k0, n0 + r0, kMask);
+                                }
                             }
-                        } else {
-                            const int r0 = (int)crank * (BN / CL);
-                            tma_load_2d_mc(sb + r0 * 128, &tmB, full0 + 8 * s, k0, n0 + r0, kMask);
                         }
-                    }
                     }
                 }
                 __syncwarp();
@@ -591,7 +612,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     }
     const int max_clusters = num_sms / CL;
     const int grid = (int)(units < max_clusters ? units : max_clusters) * CL;
-    cudaError_t e = spnet_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, CL, ta, tb, td, epi, M, N, K, kbps,
+    cudaError_t e = spnet_launch_pdl(kern, dim3(grid), dim3(n_threads(CONV)), smem, stream, CL, ta, tb, td, epi, M, N, K, kbps,
                                      tiles_m, tiles_n, (int)units, cg);
     if (e != cudaSuccess) {
         spnet_set_error("gemm_bf16: launch: %s", cudaGetErrorString(e));
@@ -740,8 +761,7 @@ int conv_tc_fwd_like(bool dgrad, const void* in, long long ld_in, int NB, int IH
     const int N = c_out, K = cg.ntaps * cg.cin_blocks * BK;
     const int bn = N <= 64 ? 64 : 128;
     CUtensorMap ta, tb, td;
-    cg.split_a = getenv("SPNET_CONV_SPLIT_A") != nullptr && cg.lw == 7;
-    int rc = make_pixel_map(&ta, in, NB, IH, IW, c_in, ld_in, cg.split_a ? 6 : cg.lw, cg.lh, ln, BK, CU_TENSOR_MAP_SWIZZLE_128B,
+    int rc = make_pixel_map(&ta, in, NB, IH, IW, c_in, ld_in, cg.lw, cg.lh, ln, BK, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (rc) return rc;
     // weights as one 2-D matrix: forward [taps*Cin (k), Cout (n)] MN-major; data gradient: rows (n) = tap*Cin + ci,

@@ -17,6 +17,8 @@ import math
 from collections import OrderedDict
 
 import numpy as np
+import os
+
 import torch
 
 from . import arch, irv2, ops
@@ -164,7 +166,10 @@ class SPNetEngineBase:
         self.l2_out = self._f32(1)
 
     def _act(self, *shape, dtype=None):
-        return torch.empty(*shape, device=self.device, dtype=dtype or self.adt)
+        t = torch.empty(*shape, device=self.device, dtype=dtype or self.adt)
+        if os.environ.get("SPNET_B200_POISON") and t.is_floating_point():
+            t.fill_(float("nan"))  # debug: a kernel that reads a buffer before anything wrote it now fails loudly
+        return t
 
     def _alloc_activations(self):
         B, sh, A = self.B, self.shapes, self._act
