@@ -180,6 +180,11 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
     const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]);
     const uint32_t tempty0 = smem_u32(&bars[2 * STAGES + 2]);
 
+    if (threadIdx.x == 32) {  // descriptor fetch overlaps the barrier / TMEM set-up
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full0 + 8 * s, kActiveProducers);  // one arrive.expect_tx per producer warp that owns boxes
