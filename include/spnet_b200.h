@@ -52,6 +52,11 @@ int spnet_selective_sigmoid_bwd(const float* y, const float* dy, float* dx, int 
  * exists [n,ncols/8] u8. */
 int spnet_decode_detections(const float* y, const float* means, const float* ranges, int n, int ncols, float* denorm, int* ints, unsigned char* exists, cudaStream_t stream);
 
+/* ---- AugmentOnTheFly on the device (spnet/callbacks.py:272-341; cutout_inplace / salt_n_pepa_inplace of
+ *      spnet/augmentation.py:117-135,159-180): x = augmented copy of the pristine frames x_orig, fp32 [n,H,W,C],
+ *      one launch per epoch, counter-based random draws keyed by (seed, frame). ---- */
+int spnet_augment_on_the_fly(const float* x_orig, float* x, int n, int H, int W, int C, long long seed, int max_regions, int minsize, int maxsize, float sp_prob, float sp_amount, float salt_vs_pepper, cudaStream_t stream);
+
 /* ---- SeparableConv2D depthwise half (keras.applications.Xception; spnet/models.py:359) ---- */
 int spnet_dwconv3x3_fwd(const void* in, const float* k, const float* in_a, const float* in_b, int relu, void* out, int dtype, int B, int H, int W, int C, cudaStream_t stream);
 int spnet_dwconv3x3_dgrad(const void* gout, const float* k, void* gin, const void* mask_src, const float* mask_a, const float* mask_b, const void* add_src, const void* add_strided, int dtype, int B, int H, int W, int C, cudaStream_t stream);

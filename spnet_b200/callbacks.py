@@ -127,27 +127,57 @@ class MyProgressCallback(Callback):
 
 
 class AugmentOnTheFly(Callback):
-    """Each aug_every epochs rewrite X in place from a pristine copy: cutout (<= 6 rectangles of
-    11..75 px) and salt-and-pepper (50 % chance, 0.4 % of the pixels); the reference's blur is a no-op
-    (spnet/callbacks.py:272-341, spnet/augmentation.py:66-71,117-180). Labels are untouched."""
+    """Each aug_every epochs rewrite the training frames X in place from a pristine copy with the reference's two
+    live augmentations (spnet/callbacks.py:272-341): cutout_inplace (spnet/augmentation.py:117-135: 0..6
+    rectangles, corner in [0, dim-11), extents 11..74 clipped to dim-1, filled with one grey value drawn between
+    the frame's min and max) and salt_n_pepa_inplace (:159-180: with probability 1/2, ceil(0.004*size*0.2) pixels
+    set to the frame's max, then ceil(0.004*size*0.8) to its min, coordinates in [0, dim-1)). blur_inplace
+    (:66-71) discards its result, i.e. is a no-op, and bp_mixup is commented out at the call site. Labels are
+    untouched (they are already grid-assigned and normalised).
 
-    def __init__(self, X, Y, aug_every=1):
+    X may be a numpy array (host path, numpy's global RNG like the reference) or a CUDA tensor: then the pristine
+    copy stays in HBM too and one kernel launch per epoch does the rewrite (csrc/augment.cu,
+    spnet_augment_on_the_fly) - the device-resident input path of SPNetModel.fit."""
+
+    def __init__(self, X, Y, orig_img_shape=(384, 512), aug_every=1, seed=None):
         super().__init__()
-        self.X, self.Y, self.aug_every = X, Y, aug_every
-        self.X_orig = np.copy(X)
+        self.X, self.Y, self.aug_every, self.orig_img_shape = X, Y, aug_every, orig_img_shape
+        self.on_device = not isinstance(X, np.ndarray)
+        self.X_orig = X.clone() if self.on_device else np.copy(X)
+        self.seed = random.getrandbits(62) if seed is None else int(seed)
+
+    @staticmethod
+    def cutout(img, max_regions=6, minsize=11, maxsize=75):
+        n = np.random.randint(0, max_regions + 1)
+        if n == 0:
+            return
+        lo, hi = np.min(img), np.max(img)
+        for _ in range(n):
+            y0, x0 = np.random.randint(0, img.shape[0] - minsize), np.random.randint(0, img.shape[1] - minsize)
+            eh, ew = np.random.randint(minsize, maxsize), np.random.randint(minsize, maxsize)
+            y1, x1 = min(y0 + eh, img.shape[0] - 1), min(x0 + ew, img.shape[1] - 1)
+            img[y0:y1, x0:x1, :] = np.random.uniform(lo, hi)
+
+    @staticmethod
+    def salt_n_pepa(img, salt_vs_pepper=0.2, amount=0.004):
+        if np.random.rand() >= 0.5:
+            return
+        salt, pepper = np.max(img), np.min(img)
+        for count, value in ((int(np.ceil(amount * img.size * salt_vs_pepper)), salt),
+                             (int(np.ceil(amount * img.size * (1.0 - salt_vs_pepper))), pepper)):
+            ys = np.random.randint(0, img.shape[0] - 1, count)
+            xs = np.random.randint(0, img.shape[1] - 1, count)
+            img[ys, xs, :] = value
 
     def on_epoch_begin(self, epoch, logs=None):
         if epoch % self.aug_every != 0:
             return
+        if self.on_device:
+            from . import ops
+            ops.augment_on_the_fly(self.X_orig, self.X, self.seed + 0x9E3779B97F4A7C15 * (epoch + 1))
+            return
         X = self.X
         X[...] = self.X_orig
-        n, H, W = X.shape[0], X.shape[1], X.shape[2]
-        for i in range(n):
-            for _ in range(random.randint(0, 6)):
-                h, w = random.randint(11, 75), random.randint(11, 75)
-                y0, x0 = random.randint(0, max(0, H - h)), random.randint(0, max(0, W - w))
-                X[i, y0:y0 + h, x0:x0 + w, :] = 0.0
-            if random.random() < 0.5:
-                k = int(0.004 * H * W)
-                ys, xs = np.random.randint(0, H, k), np.random.randint(0, W, k)
-                X[i, ys, xs, :] = np.where(np.random.rand(k, 1) < 0.5, -1.0, 1.0)
+        for i in range(X.shape[0]):
+            self.cutout(X[i])
+            self.salt_n_pepa(X[i])

@@ -316,8 +316,16 @@ class SPNetModel:
         torch = _torch()
         if self.optimizer is None:
             raise RuntimeError("You must compile a model before training/testing. Use `model.compile(optimizer, loss)`.")
-        X = np.asarray(X, dtype=np.float32)
-        Y = np.asarray(Y, dtype=np.float32)
+        # Device-resident input path: X (and optionally Y) given as CUDA tensors stay in HBM for the whole fit;
+        # batches are gathered on the device (no host staging, no H2D copy) and callbacks.AugmentOnTheFly
+        # rewrites X there once per epoch. The host path below is the reference's numpy interface.
+        on_device = torch.is_tensor(X) and X.is_cuda
+        if on_device:
+            X = X.float().contiguous() if X.dtype != torch.float32 or not X.is_contiguous() else X
+            Y = (Y if torch.is_tensor(Y) else torch.from_numpy(np.asarray(Y, dtype=np.float32))).to(X.device).float().contiguous()
+        else:
+            X = np.asarray(X, dtype=np.float32)
+            Y = np.asarray(Y, dtype=np.float32)
         if X.shape[0] != Y.shape[0]:
             raise ValueError("Input arrays should have the same number of samples as target arrays. Found %d input samples and %d target samples." % (X.shape[0], Y.shape[0]))
         if Y.shape[1] != self.Y0size:
@@ -345,8 +353,9 @@ class SPNetModel:
                 cb.set_params({"batch_size": batch_size, "epochs": epochs, "steps": steps, "samples": n, "verbose": verbose})
         self.stop_training = False
         _call(callbacks, "on_train_begin", {})
-        xpin = [torch.empty((local_bs,) + X.shape[1:], dtype=torch.float32).pin_memory() for _ in range(2)]
-        ypin = [torch.empty((local_bs, self.Y0size), dtype=torch.float32).pin_memory() for _ in range(2)]
+        if not on_device:
+            xpin = [torch.empty((local_bs,) + X.shape[1:], dtype=torch.float32).pin_memory() for _ in range(2)]
+            ypin = [torch.empty((local_bs, self.Y0size), dtype=torch.float32).pin_memory() for _ in range(2)]
         loss_acc = torch.zeros(6, device=eng.device)
         rng = np.random.RandomState(np.random.randint(0, 2 ** 31 - 1))
         captured = False
@@ -367,12 +376,23 @@ class SPNetModel:
                 ypin[k].copy_(torch.from_numpy(Y[idx]))
                 pin_free[k] = eng.prefetch_batch(xpin[k], ypin[k])
 
+            def gather_on_device(b):
+                idx = order[b * batch_size:(b + 1) * batch_size]
+                lo, hi = multi_gpu.batch_slice(batch_size, rank, world)
+                idx_t = torch.from_numpy(np.ascontiguousarray(idx[lo:hi])).to(X.device, non_blocking=True)
+                torch.index_select(X, 0, idx_t, out=eng.x0)
+                torch.index_select(Y, 0, idx_t, out=eng.y_true)
+
             pin_free = [None, None]
-            stage(0)
+            if not on_device:
+                stage(0)
             for b in range(steps):
                 _call(callbacks, "on_batch_begin", b, {"batch": b, "size": batch_size})
-                eng.take_prefetched()
-                if b + 1 < steps:
+                if on_device:
+                    gather_on_device(b)
+                else:
+                    eng.take_prefetched()
+                if not on_device and b + 1 < steps:
                     stage(b + 1)  # host gather + H2D of the next batch overlap this step's kernels
                 loss6 = eng.train_step(float(self.optimizer.lr))
                 loss_acc += loss6
@@ -491,7 +511,8 @@ def setup_model(X, Y0size=576, try_checkpoint=True, no_cp_fatal=False, weights_f
 def unfreeze_model(model, X, Y, parallel=False):
     """New identical model with every layer trainable and the old weights (spnet/models.py:510-552)."""
     print("Unfreezing Model: make a new identical model, then copy the layer weights.")
-    new_model = create_model_functional(X, Y[0].size, freeze_fac=0)
+    y0size = int(Y[0].numel()) if hasattr(Y[0], "numel") else int(Y[0].size)  # device-resident targets are tensors
+    new_model = create_model_functional(X, y0size, freeze_fac=0)
     new_model.set_weights(multi_gpu.get_serial_part(model, parallel=parallel).get_weights())
     if parallel:
         new_model = multi_gpu.make_parallel(new_model)

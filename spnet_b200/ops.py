@@ -231,6 +231,17 @@ def bn_bwd_dz(g, z, a, save_mean, save_rstd, c1, c2, out=None):
     return out
 
 
+def augment_on_the_fly(x_orig, x, seed, max_regions=6, minsize=11, maxsize=75, sp_prob=0.5, sp_amount=0.004,
+                       salt_vs_pepper=0.2):
+    """x[n,H,W,C] = cutout + salt-and-pepper copy of the pristine frames x_orig (fp32, on the device)."""
+    _chk(x_orig, x)
+    assert x_orig.dtype == torch.float32 and x.dtype == torch.float32 and x.shape == x_orig.shape
+    n, H, W, C = x.shape
+    lib().augment_on_the_fly(_p(x_orig), _p(x), n, H, W, C, int(seed) & (2 ** 63 - 1), max_regions, minsize, maxsize,
+                             sp_prob, sp_amount, salt_vs_pepper, _s())
+    return x
+
+
 # ----------------------------------------------------------------------------- pooling
 def maxpool3s2_add_fwd(z, a=None, b=None, res=None, ra=None, rb=None, out=None, argmax=None):
     _chk(z, res, out, argmax)

@@ -16,7 +16,7 @@ from predict_spnet import predict_network
 
 def train_network(weights_file="weights.hdf5", datapath=".", fraction=1.0, batch_size=32, epochs=30, pred_grid=[6, 6, 2],
                   noaugment=False, log_dir=".", lr_max=4e-5, freeze_fac=0.7, frozen_epochs=4, random_seed=1,
-                  parallel=False):
+                  parallel=False, device_data=False):
     np.random.seed(random_seed)
     print("pred_grid = ", pred_grid)
     trainpath = datapath + "/Train/"
@@ -34,6 +34,11 @@ def train_network(weights_file="weights.hdf5", datapath=".", fraction=1.0, batch
     lr_sched = callbacks.OneCycleScheduler(lr_max=lr_max, n_data_points=X_train.shape[0], epochs=epochs,
                                            batch_size=batch_size, verbose=1)
     callback_list = [myprogress, checkpointer, lr_sched]
+    if device_data:
+        # B200 build only: the training set (and AugmentOnTheFly's pristine copy) stay in HBM for the whole run;
+        # batches are gathered on the device and the per-epoch augmentation is one kernel launch
+        import torch
+        X_train, Y_train = torch.from_numpy(X_train).cuda(), torch.from_numpy(Y_train).cuda()
     if not noaugment:
         print("Adding callback for augment on the fly")
         callback_list.append(callbacks.AugmentOnTheFly(X_train, Y_train, aug_every=1))
@@ -70,6 +75,7 @@ if __name__ == "__main__":
     parser.add_argument("--dtype", choices=["bf16", "fp32"], default=cf.compute_dtype, help="compute precision (B200 build only)")
     parser.add_argument("--model_type", default=cf.model_type, help="'big' keeps 384x512 input, default resizes to 331x331")
     parser.add_argument("--parallel", action="store_true", help="shard each batch over the ranks of a torchrun launch")
+    parser.add_argument("--device_data", action="store_true", help="keep the training set in GPU memory and augment it there (B200 build only)")
     args = parser.parse_args()
     print("Command line ~= \n", " ".join(s for s in sys.argv))
     print("args = ", args)
@@ -87,7 +93,7 @@ if __name__ == "__main__":
     print("Logging will go to ", log_dir)
     print("\n----------------------------\nStarting training...")
     model = train_network(weights_file=args.weights, datapath=args.datapath, fraction=args.fraction,
-                          batch_size=args.batch_size, epochs=args.epochs, pred_grid=pred_grid, noaugment=args.noaugment,
+                          batch_size=args.batch_size, epochs=args.epochs, pred_grid=pred_grid, noaugment=args.noaugment, device_data=args.device_data,
                           log_dir=log_dir, lr_max=args.lrmax, freeze_fac=args.freeze_fac,
                           frozen_epochs=args.frozen_epochs, random_seed=args.random_seed, parallel=args.parallel)
     if multi_gpu.world()[0] == 0:
