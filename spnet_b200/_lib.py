@@ -103,4 +103,9 @@ def lib():
     global _lib
     if _lib is None:
         _lib = _Lib()
+        import torch
+        if torch.cuda.is_available():  # refuse anything but sm_100a up front (the library carries no other code)
+            rc = _lib._dll.spnet_check_device()
+            if rc != 0:
+                raise SpnetError("spnet_check_device failed (%d): %s" % (rc, _lib.last_error()))
     return _lib
