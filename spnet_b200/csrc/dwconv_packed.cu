@@ -127,7 +127,9 @@ dw3x3_fwd_packed_kernel(const __grid_constant__ CUtensorMap tm_in, const float* 
     __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES];
     const uint32_t sbase = (smem_u32(dwp_smem) + 127u) & ~127u;
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[MAX_STAGES]);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // through a shuffle so that the compiler knows the warp index is warp-uniform (uniform-datapath address math,
+    // no ELECT / R2UR loops around the TMA issue)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int ncons = blockDim.x >> 5;
     const int cbase = blockIdx.y * CB;
     const int TWH = TW + 2;
@@ -270,7 +272,9 @@ dw3x3_bwd_packed_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_c
     __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES];
     const uint32_t sbase = (smem_u32(dwp_smem) + 127u) & ~127u;
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[MAX_STAGES]);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // through a shuffle so that the compiler knows the warp index is warp-uniform (uniform-datapath address math,
+    // no ELECT / R2UR loops around the TMA issue)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int ncons = blockDim.x >> 5;
     const int cbase = blockIdx.y * CB;
     const int TWH = TW + 2;

@@ -60,18 +60,26 @@ struct ConvGeom {
     int b_tap_on_k;        // 1: taps advance B's K coordinate (forward), 0: its N coordinate (data gradient)
 };
 
+// The MMA warp runs its loop CONVERGED: every lane computes the (warp-uniform) descriptors and the instruction
+// itself is guarded by a predicate that is true in lane 0 only. Inside an `if (lane == 0)` block ptxas cannot
+// keep the descriptors in uniform registers and wraps every tcgen05.mma in an ELECT / 5 x R2UR.BROADCAST /
+// BRA.U.ANY loop: ~110 dependent instructions (~600 cycles) per k-block, more than the MMAs of a narrow tile.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
+                                          uint32_t accumulate, uint32_t leader) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-                 : "memory");
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(leader)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -109,10 +117,13 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"(cta_mask)
-                 : "memory");
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %2, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar),
+        "h"(cta_mask), "r"(leader)
+        : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -154,7 +165,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
     constexpr int NA_BOX = (A_MN || CONV == 2) ? BM / 64 : 1;
     constexpr int NB_BOX = (B_MN || CONV == 2) ? BN / 64 / CL : 1;
     constexpr int N_BOX = NA_BOX + NB_BOX;
-    constexpr int kActiveProducers = N_BOX < kProducers ? N_BOX : kProducers;
+    constexpr int kActiveProducers = 1;  // every k-block (all of its boxes) is issued by ONE producer warp
     constexpr uint32_t A_BOX_BYTES = A_BYTES / NA_BOX;
     constexpr uint32_t B_BOX_BYTES = B_BYTES / (NB_BOX * CL);  // what one of this CTA's B boxes lands (in each CTA of the pair)
     extern __shared__ uint8_t smem_raw[];
@@ -164,7 +175,9 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
     __shared__ uint32_t tmem_base_holder;
     __shared__ float sstat[2][2][4][BN];  // [accumulator parity][sum | sumsq][lane quadrant][column]
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then KNOWS it is warp-uniform, keeps the role branches and everything
+    // derived from uniform values in the uniform datapath (no ELECT / R2UR.BROADCAST loops around TMA and MMA issue)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     // output staging for the TMA-store epilogue: SD boxes of 32 rows x 64 bytes (SWIZZLE_64B) per epilogue warp;
     // two where shared memory allows (BN = 128: the HBM-bound shapes), so a box is filled while the previous
     // one is still being read out
@@ -187,7 +200,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, kActiveProducers);  // one arrive.expect_tx per producer warp that owns boxes
+            mbar_init(full0 + 8 * s, kActiveProducers);  // one arrive.expect_tx per k-block
             mbar_init(empty0 + 8 * s, CL);  // every CTA of the cluster must have consumed the stage
         }
         for (int a = 0; a < 2; ++a) {
@@ -215,14 +228,14 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
     const int prod = warp == 0 ? 0 : (warp >= 2 + kEpiWarps ? warp - (1 + kEpiWarps) : -1);
     if (prod >= 0) {
         // ---------------- TMA producers ----------------
-        // producer p issues boxes p, p + kProducers, ... of every k-block and announces their bytes on the
-        // stage's full barrier (B boxes of a CTA pair land in both CTAs: each CTA expects CL x its own)
-        uint32_t my_bytes = 0;
-#pragma unroll
-        for (int j = 0; j < N_BOX; ++j)
-            if (j % kProducers == prod) my_bytes += j < NA_BOX ? A_BOX_BYTES : B_BOX_BYTES * CL;
-        uint32_t ps = 0, pph = 0;  // running stage / phase across units
-        if (prod < kActiveProducers)
+        // k-blocks are striped over the producer warps: warp p issues every box of k-blocks p, p + kProducers, ...
+        // (of the CTA's running k-block count) and announces the whole stage on its full barrier. One warp's
+        // per-k-block instruction stream (barrier poll, coordinates, expect_tx, 2-4 TMA issue sequences) is a
+        // dependent chain of several hundred cycles - longer than the MMAs of a narrow (N <= 128) k-block -
+        // so the convolution modes run kConvProducers of them side by side; the GEMM keeps one.
+        // (B boxes of a CTA pair land in both CTAs: each CTA expects CL x its own.)
+        constexpr uint32_t my_bytes = NA_BOX * A_BOX_BYTES + NB_BOX * B_BOX_BYTES * CL;
+        uint32_t g0 = 0;  // k-blocks of the units before this one
         for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
             const int n0 = (unit % tiles_n) * BN;
             const int mt = (unit / tiles_n) % tiles_m;
@@ -235,24 +248,25 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
             // division per k-block made this single-warp instruction stream (~800 cycles per k-block) the
             // bottleneck of the whole kernel
             int px0 = 0, py0 = 0, pimg = 0;  // CONV 1: origin of this tile's pixel box
-            int c_cb = 0, c_kx = 0, c_ky = 0, c_tp = 0;  // CONV 1: channel block, tap of the next k-block
+            int c_cb = 0, c_kx = 0, c_ky = 0, c_tp = 0;  // CONV 1: channel block, tap of this warp's next k-block
             int c_tx = 0, c_ty = 0, c_g = 0, w_kx = 0, w_ky = 0;  // CONV 2: pixel box of the next k-block; this unit's tap
+            const int kb_first = kb_begin + prod;  // this warp's first k-block of the unit
             if (CONV == 1) {
                 const int t2 = mt / cg.tiles_w;
                 px0 = (mt - t2 * cg.tiles_w) << cg.lw;
                 py0 = (t2 % cg.tiles_h) << cg.lh;
                 pimg = (t2 / cg.tiles_h) << (7 - cg.lw - cg.lh);
-                c_tp = kb_begin / cg.cin_blocks; c_cb = kb_begin - c_tp * cg.cin_blocks;
+                c_tp = kb_first / cg.cin_blocks; c_cb = kb_first - c_tp * cg.cin_blocks;
                 c_ky = c_tp / cg.KW; c_kx = c_tp - c_ky * cg.KW;
             }
             if (CONV == 2) {
-                const int t2 = kb_begin / cg.tiles_w;
-                c_tx = kb_begin - t2 * cg.tiles_w; c_ty = t2 % cg.tiles_h; c_g = t2 / cg.tiles_h;
+                const int t2 = kb_first / cg.tiles_w;
+                c_tx = kb_first - t2 * cg.tiles_w; c_ty = t2 % cg.tiles_h; c_g = t2 / cg.tiles_h;
                 w_ky = tap / cg.KW; w_kx = tap - w_ky * cg.KW;
             }
-            for (int i = 0; i < nkb; ++i) {
-                const uint32_t s = ps, ph = pph;
-                if (++ps == STAGES) { ps = 0; pph ^= 1u; }
+            for (int i = prod; i < nkb; i += kProducers) {
+                const uint32_t g = g0 + (uint32_t)i;  // running k-block index of this CTA -> ring stage and phase
+                const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
                 // coordinates that depend on the mode (warp-uniform, computed before the wait)
                 const int k0 = (kb_begin + i) * BK;
                 int ax = 0, ay = 0, aimg = 0, bx = 0, by = 0, kA = k0, kB = k0, nB = n0;
@@ -261,18 +275,22 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
                     ax = px0 + cg.sign * (c_kx - cg.pl); ay = py0 + cg.sign * (c_ky - cg.pt); aimg = pimg;
                     kB = kA + (cg.b_tap_on_k ? c_tp * cg.b_tap_stride : 0);
                     nB = n0 + (cg.b_tap_on_k ? 0 : c_tp * cg.b_tap_stride);
-                    if (++c_cb == cg.cin_blocks) {
-                        c_cb = 0; ++c_tp;
-                        if (++c_kx == cg.KW) { c_kx = 0; ++c_ky; }
-                    }
+#pragma unroll
+                    for (int t = 0; t < kProducers; ++t)  // advance to this warp's next k-block
+                        if (++c_cb == cg.cin_blocks) {
+                            c_cb = 0; ++c_tp;
+                            if (++c_kx == cg.KW) { c_kx = 0; ++c_ky; }
+                        }
                 } else if (CONV == 2) {
                     bx = c_tx << cg.lw; by = c_ty << cg.lh;
                     aimg = c_g << (6 - cg.lw - cg.lh);
                     ax = bx + w_kx - cg.pl; ay = by + w_ky - cg.pt;
-                    if (++c_tx == cg.tiles_w) {
-                        c_tx = 0;
-                        if (++c_ty == cg.tiles_h) { c_ty = 0; ++c_g; }
-                    }
+#pragma unroll
+                    for (int t = 0; t < kProducers; ++t)
+                        if (++c_tx == cg.tiles_w) {
+                            c_tx = 0;
+                            if (++c_ty == cg.tiles_h) { c_ty = 0; ++c_g; }
+                        }
                 }
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 if (lane == 0) {
@@ -282,7 +300,6 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
                     mbar_expect_tx(bar, my_bytes);
 #pragma unroll
                     for (int j = 0; j < N_BOX; ++j) {
-                        if (j % kProducers != prod) continue;
                         if (j < NA_BOX) {
                             if (CONV == 1) tma_load_4d(sa, &tmA, bar, kA, ax, ay, aimg);
                             else if (CONV == 2) tma_load_4d(sa + j * (BK * 128), &tmA, bar, m0 + 64 * j, ax, ay, aimg);
@@ -311,6 +328,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
                 }
                 __syncwarp();
             }
+            g0 += (uint32_t)nkb;
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
@@ -326,6 +344,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
         constexpr uint32_t A_KSTEP = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
         constexpr uint32_t B_KSTEP = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
         constexpr uint32_t STAGE_STEP = STAGE_BYTES >> 4;
+        const uint32_t leader = lane == 0 ? 1u : 0u;  // the one thread that issues (and commits) every MMA
         uint32_t s = 0, ph = 0, u = 0;
         for (int unit = cluster_id; unit < n_units; unit += n_clusters, ++u) {
             int rest = unit / (tiles_n * tiles_m);
@@ -339,17 +358,17 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
             for (int i = 0; i < nkb; ++i) {
                 mbar_wait(full0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
+                {
                     const uint32_t a_lo = a_lo_base + s * STAGE_STEP, b_lo = b_lo_base + s * STAGE_STEP;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * A_KSTEP);
                         const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * B_KSTEP);
-                        umma_bf16(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        umma_bf16(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u, leader);
                     }
                     // frees the smem stage (in every CTA of the cluster) when these MMAs retire
-                    if (CL > 1) umma_commit_mc(empty0 + 8 * s, kMask); else umma_commit(empty0 + 8 * s);
-                    if (i == nkb - 1) umma_commit(tfull0 + 8 * as);  // accumulator complete
+                    if (CL > 1) umma_commit_mc(empty0 + 8 * s, kMask, leader); else umma_commit(empty0 + 8 * s, leader);
+                    if (i == nkb - 1) umma_commit(tfull0 + 8 * as, leader);  // accumulator complete
                 }
                 __syncwarp();
                 if (++s == STAGES) { s = 0; ph ^= 1u; }

@@ -18,10 +18,10 @@ def graph_us(fn, reps=20):
     return e0.elapsed_time(e1) * 1e3 / (2 * reps)
 
 
-M, N = 12288, 728
+M, N = (int(sys.argv[1]) if len(sys.argv) > 1 else 12288), (int(sys.argv[2]) if len(sys.argv) > 2 else 728)
 for name, a_mn, b_mn, mode, stats in (("fwd+stats", False, True, ops.OUT_T, True), ("fwd", False, True, ops.OUT_T, False),
                                       ("dgrad", False, False, ops.OUT_T, False)):
-    for K in (64, 128, 256, 728, 1456, 2912):
+    for K in ((64, 728) if len(sys.argv) > 1 else (64, 128, 256, 728, 1456, 2912)):
         A = torch.randn(M, K, device=dev).bfloat16()
         B = torch.randn((K, N) if b_mn else (N, K), device=dev).bfloat16()
         D = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
