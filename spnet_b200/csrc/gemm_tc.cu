@@ -25,11 +25,11 @@ constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;    // two per TMEM lane quadrant, each draining half of the columns
-// The producer's per-k-block instruction stream (barrier poll, coordinates, expect_tx, one issue sequence per
-// box) is a single-warp dependent chain of a few hundred cycles; the convolution modes, whose k-blocks are
-// short (N <= 128) and carry 2..4 boxes with 4-D coordinates, spread the boxes over kConvProducers warps.
-// The plain GEMM is not producer-bound (its producer finds the ring full) and keeps one.
-constexpr int kConvProducers = 4;
+// Producer warps. More than one is only safe if every producer waits on EVERY stage's empty barrier (parity waits
+// tell adjacent phases apart, not a producer that ran two ring rounds ahead): striping k-blocks over four warps
+// passed the unit tests and then trapped at full InceptionResNetV2 size for exactly that reason. With the warp
+// index made compiler-visibly uniform (see the kernel) one producer's per-k-block stream is short enough.
+constexpr int kConvProducers = 1;
 __host__ __device__ constexpr int n_producers(int conv) { return conv ? kConvProducers : 1; }
 __host__ __device__ constexpr int n_threads(int conv) { return 64 + 32 * kEpiWarps + 32 * (n_producers(conv) - 1); }  // TMA, MMA, epilogue, extra TMA warps
 
@@ -73,6 +73,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
         : "memory");
+}
+// one lane of a converged warp (always the same one), in a form the compiler recognises as "one thread"
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    return leader;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t leader) {
     asm volatile(
@@ -236,6 +242,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
         // (B boxes of a CTA pair land in both CTAs: each CTA expects CL x its own.)
         constexpr uint32_t my_bytes = NA_BOX * A_BOX_BYTES + NB_BOX * B_BOX_BYTES * CL;
         uint32_t g0 = 0;  // k-blocks of the units before this one
+        const uint32_t issuer = elect_one();
         for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
             const int n0 = (unit % tiles_n) * BN;
             const int mt = (unit / tiles_n) % tiles_m;
@@ -293,7 +300,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
                         }
                 }
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                if (lane == 0) {
+                if (issuer) {
                     const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
                     const uint32_t sb = sa + A_BYTES;
                     const uint32_t bar = full0 + 8 * s;
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
         constexpr uint32_t A_KSTEP = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
         constexpr uint32_t B_KSTEP = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
         constexpr uint32_t STAGE_STEP = STAGE_BYTES >> 4;
-        const uint32_t leader = lane == 0 ? 1u : 0u;  // the one thread that issues (and commits) every MMA
+        const uint32_t leader = elect_one();  // the one thread that issues (and commits) every MMA
         uint32_t s = 0, ph = 0, u = 0;
         for (int unit = cluster_id; unit < n_units; unit += n_clusters, ++u) {
             int rest = unit / (tiles_n * tiles_m);
@@ -358,17 +365,17 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
             for (int i = 0; i < nkb; ++i) {
                 mbar_wait(full0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                {
+                if (leader) {
                     const uint32_t a_lo = a_lo_base + s * STAGE_STEP, b_lo = b_lo_base + s * STAGE_STEP;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * A_KSTEP);
                         const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * B_KSTEP);
-                        umma_bf16(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u, leader);
+                        umma_bf16(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u, 1u);
                     }
                     // frees the smem stage (in every CTA of the cluster) when these MMAs retire
-                    if (CL > 1) umma_commit_mc(empty0 + 8 * s, kMask, leader); else umma_commit(empty0 + 8 * s, leader);
-                    if (i == nkb - 1) umma_commit(tfull0 + 8 * as, leader);  // accumulator complete
+                    if (CL > 1) umma_commit_mc(empty0 + 8 * s, kMask, 1u); else umma_commit(empty0 + 8 * s, 1u);
+                    if (i == nkb - 1) umma_commit(tfull0 + 8 * as, 1u);  // accumulator complete
                 }
                 __syncwarp();
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
