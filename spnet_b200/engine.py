@@ -576,7 +576,7 @@ class XceptionSPNetEngine(SPNetEngineBase):
             s.z = A(B, fh, fw, s.cout)
         self.feat_dims = (fh, fw, 2048)
         if train:
-            self.gcol = A(B * h2 * w2, 288)
+            self.gcol = None if self.lowp else A(B * h2 * w2, 288)  # bf16: the data gradient is an implicit GEMM
             self.scratch = [A(maxel) for _ in range(6)]
 
     def _backbone_fwd(self, training):
@@ -666,10 +666,18 @@ class XceptionSPNetEngine(SPNetEngineBase):
         M2 = B * h2 * w2
         g_z12 = self._bn_bwd(g_x, self.z12, self.b1_bn2, M2, relu_mask=True)
         W2l = self.wl["block1_conv2/kernel"].view(288, 64)
-        self._pw_bwd(self.col, W2l, g["block1_conv2/kernel"].view(288, 64), g_z12.view(M2, 64), self.gcol, M2, 288, 64)
         g_y11 = self._view(G1, B, h1, w1, 32)
-        ops.col2im3x3(self.gcol, g_y11, z=self.z11, a=self.b1_bn1.a, b=self.b1_bn1.b, relu=True)
-        g_z11 = self._bn_bwd(g_y11, self.z11, self.b1_bn1, B * h1 * w1)
+        if self.lowp:
+            # weight gradient from the forward's im2col buffer; data gradient as implicit GEMM (csrc/gemm_tc.cu
+            # CONV mode: 95 us instead of a 120 us GEMM into a 428 MB column-gradient buffer + 97 us col2im),
+            # the ReLU mask of block1_conv1_act is applied by the BatchNorm-backward reduction that follows
+            self._pw_bwd(self.col, W2l, g["block1_conv2/kernel"].view(288, 64), g_z12.view(M2, 64), None, M2, 288, 64)
+            ops.conv_tc_dgrad(g_z12.view(B, h2, w2, 64), self.wl["block1_conv2/kernel"], g_y11, 0, 0)
+            g_z11 = self._bn_bwd(g_y11, self.z11, self.b1_bn1, B * h1 * w1, relu_mask=True)
+        else:
+            self._pw_bwd(self.col, W2l, g["block1_conv2/kernel"].view(288, 64), g_z12.view(M2, 64), self.gcol, M2, 288, 64)
+            ops.col2im3x3(self.gcol, g_y11, z=self.z11, a=self.b1_bn1.a, b=self.b1_bn1.b, relu=True)
+            g_z11 = self._bn_bwd(g_y11, self.z11, self.b1_bn1, B * h1 * w1)
         ops.conv_small_wgrad(2, self.d, g_z11, g["block1_conv1/kernel"])
         ops.conv_small_dgrad(2, g_z11, w["block1_conv1/kernel"], ga)
 
