@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
         }
     } else {
         // ---------------- epilogue warps ----------------
+        const uint32_t e_leader = elect_one();  // this warp's TMA-store / barrier thread (always the same lane)
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
         const int chalf = (warp - 2) >> 2;      // which half of the column chunks this warp drains
         const int et = (warp - 2) * 32 + lane;  // 0..255 within the epilogue group
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
                     // rows >= M and columns >= N are clipped by the TMA unit
                     if (col0 < N && rows_live) {  // warp-uniform
                         const uint32_t stg = stage_out0 + ((uint32_t)(warp - 2) * SD + sbox) * 2048u;
-                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SD - 1) : "memory");  // this box was read out
+                        if (e_leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SD - 1) : "memory");  // this box was read out
                         __syncwarp();
                         const uint32_t rowaddr = stg + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
 #pragma unroll
@@ -456,7 +457,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
                                          : "memory");
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
-                        if (lane == 0) {
+                        if (e_leader) {
                             if (CONV == 1)
                                 asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmD),
                                              "r"(stg), "r"(col0), "r"(dx), "r"(dy), "r"(dimg)
@@ -483,7 +484,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
                             const uint32_t stg = stage_out0 + ((uint32_t)(warp - 2) * SD + sbox) * 2048u;
                             const uint32_t rowaddr = stg + (uint32_t)lane * 64u;
                             if (SD > 1) sbox ^= 1u;
-                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SD - 1) : "memory");
+                            if (e_leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SD - 1) : "memory");
                             __syncwarp();
 #pragma unroll
                             for (int g = 0; g < 4; ++g)
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
                                              : "memory");
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                             __syncwarp();
-                            if (lane == 0) {
+                            if (e_leader) {
                                 if (epi.mode == OUT_F32)
                                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmD),
                                                  "r"(stg), "r"(col0 + 16 * h), "r"(drow)
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
             // accumulator fully read: hand it back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+            if (e_leader) mbar_arrive(tempty0 + 8 * as);
             if (epi.colstats) {
                 // partial sums of this unit are visible after the barrier; the buffer alternates with the
                 // accumulator parity, so the next unit's writers never race with these reads
@@ -566,7 +567,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
             }
         }
         if (epi.colstats) flush_stats();
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging may not die under a store
+        if (e_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging may not die under a store
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     if (CL > 1) cluster_sync_all(); else __syncthreads();  // no CTA may exit while its peer still multicasts into it
