@@ -115,6 +115,13 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_w, int tiles
 // CTA = TW/NC warps; blockIdx.y = 64-channel chunk, blockIdx.x walks
 // (image, row-tile, col-tile) tiles round-robin.
 // =================================================================================================
+// one lane of a converged warp, always the same one, in a form the compiler treats as a single thread
+__device__ __forceinline__ uint32_t elect_one_lane() {
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    return leader;
+}
+
 template <typename T, int NC, bool AFFINE, int RELU>
 __global__ void __launch_bounds__(256, 2)
 dw3x3_fwd_packed_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ k,
@@ -173,16 +180,21 @@ dw3x3_fwd_packed_kernel(const __grid_constant__ CUtensorMap tm_in, const float* 
 #pragma unroll
     for (int oc = 0; oc < NC; ++oc) A_[oc] = B_[oc] = C_[oc] = make_float2(0.f, 0.f);
 
-    int s = 0, n = 0;
+    // Producer duty rotates over the warps (tile i of this CTA is refilled by warp i % ncons): the refill has to
+    // wait until EVERY warp has released the stage and then costs a few hundred cycles of coordinate decode + TMA
+    // issue; pinned to warp 0 that made warp 0 the last one through every tile and the pace of the whole CTA.
+    const uint32_t issuer_lane = elect_one_lane();
+    int s = 0, n = 0, duty = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (threadIdx.x == 0) {
+        if (warp == duty) {  // warp-uniform
             const int nt = tile + (S - 1) * (int)gridDim.x;
             if (nt < n_tiles) {
                 const int sp = s == 0 ? S - 1 : s - 1;  // the stage the previous tile used
                 if (tile != (int)blockIdx.x) mbar_wait(empty0 + 8 * sp, (uint32_t)(s == 0 ? n - 1 : n) & 1u);
-                issue(nt, sp);
+                if (issuer_lane) issue(nt, sp);
             }
         }
+        if (++duty == ncons) duty = 0;
         const TileCoord tc = tile_coord(tile, tiles_w, tiles_h, TH, TW);
         const int h0 = tc.h0, w0 = tc.w0;
         mbar_wait(full0 + 8 * s, (uint32_t)n & 1u);
@@ -325,16 +337,21 @@ dw3x3_bwd_packed_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_c
     const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
     float2 G0[NC + 2], G1[NC + 2], G2[NC + 2];
 
-    int s = 0, n = 0;
+    // Producer duty rotates over the warps (tile i of this CTA is refilled by warp i % ncons): the refill has to
+    // wait until EVERY warp has released the stage and then costs a few hundred cycles of coordinate decode + TMA
+    // issue; pinned to warp 0 that made warp 0 the last one through every tile and the pace of the whole CTA.
+    const uint32_t issuer_lane = elect_one_lane();
+    int s = 0, n = 0, duty = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (threadIdx.x == 0) {
+        if (warp == duty) {  // warp-uniform
             const int nt = tile + (S - 1) * (int)gridDim.x;
             if (nt < n_tiles) {
                 const int sp = s == 0 ? S - 1 : s - 1;  // the stage the previous tile used
                 if (tile != (int)blockIdx.x) mbar_wait(empty0 + 8 * sp, (uint32_t)(s == 0 ? n - 1 : n) & 1u);
-                issue(nt, sp);
+                if (issuer_lane) issue(nt, sp);
             }
         }
+        if (++duty == ncons) duty = 0;
         const TileCoord tc = tile_coord(tile, tiles_w, tiles_h, TH, TW);
         const int h0 = tc.h0, w0 = tc.w0;
         mbar_wait(full0 + 8 * s, (uint32_t)n & 1u);
