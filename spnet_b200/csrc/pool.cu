@@ -16,6 +16,20 @@ __host__ __device__ inline int same_pad_before(int in) {
     return total / 2;
 }
 
+// per-channel coefficients of one channel vector with 16-byte loads
+template <int V> __device__ __forceinline__ void load_coef(const float* __restrict__ p, int c0, float (&v)[V]) {
+#pragma unroll
+    for (int i = 0; i < V; i += 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p + c0 + i));
+        v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
+    }
+}
+
+// Both pooling kernels: blockIdx.x = one row of the tensor the kernel WRITES (image, output row), the threads
+// walk that row's (column, channel vector) items; the image / row split is per CTA and one division per item
+// is left (the one-thread-per-item versions spent three 32-bit divisions and eight single-byte argmax stores
+// per item and ran at 30-40 % of the HBM roofline).
+//
 // out = max_{3x3,s2}(a*z+b) + (ra*res+rb);  argmax (optional) = kh*3+kw of the first maximum
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_add_fwd_kernel(const T* __restrict__ z, const float* __restrict__ a,
@@ -27,61 +41,81 @@ __global__ void __launch_bounds__(256) maxpool_add_fwd_kernel(const T* __restric
                                                               int W, int C, int OH, int OW, int pt, int pl) {
     constexpr int V = VecN<T>::N;
     const int CV = C / V;
-    const long long n = (long long)B * OH * OW * CV;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
-    const unsigned uidx = (unsigned)idx;  // host guarantees < 2^31 items: 32-bit div/mod only
-    const int cv = (int)(uidx % CV);
-    unsigned r = uidx / CV;
-    const int ow = (int)(r % OW);
-    r /= OW;
-    const int oh = (int)(r % OH);
-    const int bi = (int)(r / OH);
-    const int c0 = cv * V;
-    float av[V], bv[V], best[V];
-    int arg[V];
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-        av[i] = a ? a[c0 + i] : 1.f;
-        bv[i] = a ? b[c0 + i] : 0.f;
-        best[i] = -INFINITY;
-        arg[i] = 0;
-    }
-    // all nine loads are issued before the first compare (clamped addresses + validity flags): the
-    // kernel is latency-bound, branches around the loads would serialise them
-    float v[9][V];
-    bool ok[9];
+    const int row = blockIdx.x;  // bi * OH + oh
+    const int bi = row / OH, oh = row - bi * OH;
+    const int items = OW * CV;
+    // the three input rows of this output row (clamped; flagged when they are padding)
+    int ihc[3];
+    bool okh[3];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
         const int ih = oh * 2 - pt + kh;
-        const int ihc = min(max(ih, 0), H - 1);
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-            const int iw = ow * 2 - pl + kw;
-            const int iwc = min(max(iw, 0), W - 1);
-            ok[kh * 3 + kw] = ih == ihc && iw == iwc;
-            load_vec(z + (((size_t)bi * H + ihc) * W + iwc) * C + c0, v[kh * 3 + kw]);
-        }
+        ihc[kh] = min(max(ih, 0), H - 1);
+        okh[kh] = ih == ihc[kh];
     }
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        if (!ok[t]) continue;
+    for (int it = blockIdx.y * blockDim.x + threadIdx.x; it < items; it += blockDim.x * gridDim.y) {
+        const int ow = it / CV, cv = it - ow * CV;
+        const int c0 = cv * V;
+        const size_t idx = (size_t)row * items + it;
+        float av[V], bv[V], best[V];
+        int arg[V];
+        if (a) {
+            load_coef<V>(a, c0, av);
+            load_coef<V>(b, c0, bv);
+        }
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const float y = fmaf(v[t][i], av[i], bv[i]);
-            if (y > best[i]) { best[i] = y; arg[i] = t; }
+            if (!a) { av[i] = 1.f; bv[i] = 0.f; }
+            best[i] = -INFINITY;
+            arg[i] = 0;
         }
-    }
-    if (res) {
-        float v[V];
-        load_vec(res + idx * V, v);
+        // all nine loads are issued before the first compare (clamped addresses + validity flags): the
+        // kernel is latency-bound, branches around the loads would serialise them
+        float v[9][V];
+        bool ok[9];
 #pragma unroll
-        for (int i = 0; i < V; ++i) best[i] += ra ? fmaf(v[i], ra[c0 + i], rb[c0 + i]) : v[i];
-    }
-    store_vec(out + idx * V, best);
-    if (argmax) {
+        for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) argmax[idx * V + i] = (unsigned char)arg[i];
+            for (int kw = 0; kw < 3; ++kw) {
+                const int iw = ow * 2 - pl + kw;
+                const int iwc = min(max(iw, 0), W - 1);
+                ok[kh * 3 + kw] = okh[kh] && iw == iwc;
+                load_vec(z + (((size_t)bi * H + ihc[kh]) * W + iwc) * C + c0, v[kh * 3 + kw]);
+            }
+        }
+        float rv[V];
+        if (res) load_vec(res + idx * V, rv);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            if (!ok[t]) continue;
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const float y = fmaf(v[t][i], av[i], bv[i]);
+                if (y > best[i]) { best[i] = y; arg[i] = t; }
+            }
+        }
+        if (res) {
+            if (ra) {
+                float rav[V], rbv[V];
+                load_coef<V>(ra, c0, rav);
+                load_coef<V>(rb, c0, rbv);
+#pragma unroll
+                for (int i = 0; i < V; ++i) best[i] += fmaf(rv[i], rav[i], rbv[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < V; ++i) best[i] += rv[i];
+            }
+        }
+        store_vec(out + idx * V, best);
+        if (argmax) {  // V codes in one store
+            uint32_t w[V / 4];
+#pragma unroll
+            for (int i = 0; i < V / 4; ++i)
+                w[i] = (uint32_t)arg[4 * i] | ((uint32_t)arg[4 * i + 1] << 8) | ((uint32_t)arg[4 * i + 2] << 16) |
+                       ((uint32_t)arg[4 * i + 3] << 24);
+            if (V == 8) *reinterpret_cast<uint2*>(argmax + idx * V) = make_uint2(w[0], w[V / 4 - 1]);
+            else *reinterpret_cast<uint32_t*>(argmax + idx * V) = w[0];
+        }
     }
 }
 
@@ -93,61 +127,63 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ 
                                                           int OW, int pt, int pl) {
     constexpr int V = VecN<T>::N;
     const int CV = C / V;
-    const long long n = (long long)B * H * W * CV;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
-    const unsigned uidx = (unsigned)idx;
-    const int cv = (int)(uidx % CV);
-    unsigned r = uidx / CV;
-    const int w = (int)(r % W);
-    r /= W;
-    const int h = (int)(r % H);
-    const int bi = (int)(r / H);
-    const int c0 = cv * V;
-    float acc[V];
-#pragma unroll
-    for (int i = 0; i < V; ++i) acc[i] = 0.f;
-    // candidate windows: oh in {(h+pt-kh)/2} for the kh that make it integral (at most two), same for ow;
-    // loads first (clamped, flagged), compares after
-    float g[4][V];
-    uint32_t am[4][2];
-    int code[4];
-    bool ok[4];
-    int nc = 0;
+    const int row = blockIdx.x;  // bi * H + h
+    const int bi = row / H, h = row - bi * H;
+    const int items = W * CV;
+    // candidate window rows: kh with (h + pt - kh) even: kh = (h+pt)&1, and that + 2 (if <= 2) -- per CTA
+    int ohc[2], khc[2];
+    bool okh[2];
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
-        // kh candidates with (h + pt - kh) even: kh = (h+pt)&1, and that + 2 (if <= 2)
         const int kh = ((h + pt) & 1) + 2 * a;
         const int t = h + pt - kh;
         const int oh = t >> 1;
-        const bool okh = kh <= 2 && t >= 0 && oh < OH;
+        okh[a] = kh <= 2 && t >= 0 && oh < OH;
+        ohc[a] = okh[a] ? oh : 0;
+        khc[a] = kh;
+    }
+    for (int it = blockIdx.y * blockDim.x + threadIdx.x; it < items; it += blockDim.x * gridDim.y) {
+        const int w = it / CV, cv = it - w * CV;
+        const int c0 = cv * V;
+        float acc[V];
 #pragma unroll
-        for (int bb = 0; bb < 2; ++bb) {
-            const int kw = ((w + pl) & 1) + 2 * bb;
-            const int u = w + pl - kw;
-            const int ow = u >> 1;
-            const bool okw = kw <= 2 && u >= 0 && ow < OW;
-            ok[nc] = okh && okw;
-            code[nc] = kh * 3 + kw;
-            const size_t o = (((size_t)bi * OH + (okh ? oh : 0)) * OW + (okw ? ow : 0)) * C + c0;
-            load_vec(gout + o, g[nc]);
-            if (V == 8) {
-                const uint2 q = *reinterpret_cast<const uint2*>(argmax + o);
-                am[nc][0] = q.x; am[nc][1] = q.y;
-            } else {
-                am[nc][0] = *reinterpret_cast<const uint32_t*>(argmax + o); am[nc][1] = 0;
+        for (int i = 0; i < V; ++i) acc[i] = 0.f;
+        // loads first (clamped, flagged), compares after
+        float g[4][V];
+        uint32_t am[4][2];
+        int code[4];
+        bool ok[4];
+        int nc = 0;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) {
+                const int kw = ((w + pl) & 1) + 2 * bb;
+                const int u = w + pl - kw;
+                const int ow = u >> 1;
+                const bool okw = kw <= 2 && u >= 0 && ow < OW;
+                ok[nc] = okh[a] && okw;
+                code[nc] = khc[a] * 3 + kw;
+                const size_t o = (((size_t)bi * OH + ohc[a]) * OW + (okw ? ow : 0)) * C + c0;
+                load_vec(gout + o, g[nc]);
+                if (V == 8) {
+                    const uint2 q = *reinterpret_cast<const uint2*>(argmax + o);
+                    am[nc][0] = q.x; am[nc][1] = q.y;
+                } else {
+                    am[nc][0] = *reinterpret_cast<const uint32_t*>(argmax + o); am[nc][1] = 0;
+                }
+                ++nc;
             }
-            ++nc;
         }
-    }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (!ok[k]) continue;
+        for (int k = 0; k < 4; ++k) {
+            if (!ok[k]) continue;
 #pragma unroll
-        for (int i = 0; i < V; ++i)
-            if ((int)((am[k][i >> 2] >> (8 * (i & 3))) & 0xffu) == code[k]) acc[i] += g[k][i];
+            for (int i = 0; i < V; ++i)
+                if ((int)((am[k][i >> 2] >> (8 * (i & 3))) & 0xffu) == code[k]) acc[i] += g[k][i];
+        }
+        store_vec(gin + ((size_t)row * items + it) * V, acc);
     }
-    store_vec(gin + idx * V, acc);
 }
 
 // out[b,oh,ow,:] = in[b,2oh+off_h,2ow+off_w,:]   (off 0: what a 1x1 stride-2 'same' convolution reads, and a 3x3
@@ -198,6 +234,14 @@ __global__ void __launch_bounds__(256) scatter_s2_kernel(const T* __restrict__ i
     store_vec(out + idx * V, v);
 }
 
+// grid of the row-per-CTA pooling kernels: x = rows, y = chunks of a row so that a thread handles ~2 items
+dim3 row_grid(int rows, int items) {
+    int gy = (items + 511) / 512;
+    if (gy < 1) gy = 1;
+    if (gy > 16) gy = 16;
+    return dim3((unsigned)rows, (unsigned)gy);
+}
+
 int check_pool(const char* who, int dtype, int B, int H, int W, int C) {
     SPNET_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "%s: bad shape", who);
     SPNET_REQUIRE((long long)B * H * W * C < 0x7fffffffLL, "%s: tensor too large for 32-bit indexing", who);
@@ -220,8 +264,7 @@ int spnet_maxpool3s2_add_fwd(const void* z, const float* a, const float* b, cons
                   "maxpool3s2_add_fwd: affine parameters come in pairs");
     const int OH = (H + 1) / 2, OW = (W + 1) / 2;
     const int V = dtype == SPNET_BF16 ? 8 : 4;
-    const long long n = (long long)B * OH * OW * (C / V);
-    SPNET_DISPATCH_DTYPE(dtype, (maxpool_add_fwd_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(
+    SPNET_DISPATCH_DTYPE(dtype, (maxpool_add_fwd_kernel<T><<<row_grid(B * OH, OW * (C / V)), 256, 0, stream>>>(
                                     reinterpret_cast<const T*>(z), a, b, reinterpret_cast<const T*>(res), ra, rb,
                                     reinterpret_cast<T*>(out), argmax, B, H, W, C, OH, OW, same_pad_before(H),
                                     same_pad_before(W))));
@@ -235,8 +278,7 @@ int spnet_maxpool3s2_bwd(const void* gout, const unsigned char* argmax, void* gi
     SPNET_REQUIRE(gout && argmax && gin, "maxpool3s2_bwd: null pointer");
     const int OH = (H + 1) / 2, OW = (W + 1) / 2;
     const int V = dtype == SPNET_BF16 ? 8 : 4;
-    const long long n = (long long)B * H * W * (C / V);
-    SPNET_DISPATCH_DTYPE(dtype, (maxpool_bwd_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(
+    SPNET_DISPATCH_DTYPE(dtype, (maxpool_bwd_kernel<T><<<row_grid(B * H, W * (C / V)), 256, 0, stream>>>(
                                     reinterpret_cast<const T*>(gout), argmax, reinterpret_cast<T*>(gin), B, H, W, C,
                                     OH, OW, same_pad_before(H), same_pad_before(W))));
     return spnet_check_launch("maxpool3s2_bwd");
@@ -251,8 +293,7 @@ int spnet_maxpool3s2_valid_fwd(const void* z, void* out, unsigned char* argmax, 
     SPNET_REQUIRE(z && out && H >= 3 && W >= 3, "maxpool3s2_valid_fwd: bad args");
     const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
     const int V = dtype == SPNET_BF16 ? 8 : 4;
-    const long long n = (long long)B * OH * OW * (C / V);
-    SPNET_DISPATCH_DTYPE(dtype, (maxpool_add_fwd_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(
+    SPNET_DISPATCH_DTYPE(dtype, (maxpool_add_fwd_kernel<T><<<row_grid(B * OH, OW * (C / V)), 256, 0, stream>>>(
                                     reinterpret_cast<const T*>(z), nullptr, nullptr, nullptr, nullptr, nullptr,
                                     reinterpret_cast<T*>(out), argmax, B, H, W, C, OH, OW, 0, 0)));
     return spnet_check_launch("maxpool3s2_valid_fwd");
@@ -265,8 +306,7 @@ int spnet_maxpool3s2_valid_bwd(const void* gout, const unsigned char* argmax, vo
     SPNET_REQUIRE(gout && argmax && gin && H >= 3 && W >= 3, "maxpool3s2_valid_bwd: bad args");
     const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
     const int V = dtype == SPNET_BF16 ? 8 : 4;
-    const long long n = (long long)B * H * W * (C / V);
-    SPNET_DISPATCH_DTYPE(dtype, (maxpool_bwd_kernel<T><<<ceil_div(n, 256), 256, 0, stream>>>(
+    SPNET_DISPATCH_DTYPE(dtype, (maxpool_bwd_kernel<T><<<row_grid(B * H, W * (C / V)), 256, 0, stream>>>(
                                     reinterpret_cast<const T*>(gout), argmax, reinterpret_cast<T*>(gin), B, H, W, C, OH, OW,
                                     0, 0)));
     return spnet_check_launch("maxpool3s2_valid_bwd");
