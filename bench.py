@@ -229,6 +229,20 @@ def run_ours(args, rank, world):
     barrier()
     ms_dev = ev0.elapsed_time(ev1)
 
+    # the box's pinned host->device rate for one batch of frames, measured alone (not part of any timed region):
+    # the end-to-end figure below cannot exceed batch / (this copy's time) and single-GPU boxes differ a lot here
+    hb0, hb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scratch_dev = torch.empty_like(Xd[:B])
+    scratch_dev.copy_(Xp[:B], non_blocking=True)
+    torch.cuda.synchronize()
+    hb0.record()
+    for _ in range(3):
+        scratch_dev.copy_(Xp[:B], non_blocking=True)
+    hb1.record()
+    torch.cuda.synchronize()
+    h2d_gbps = 3 * scratch_dev.numel() * 4 / (hb0.elapsed_time(hb1) * 1e-3) / 1e9
+    del scratch_dev
+
     # ---- timed region 2: end to end from host buffers (pinned H2D + loss D2H every step)
     loss_host = torch.zeros(6).pin_memory()
     barrier()
@@ -384,7 +398,9 @@ def run_ours(args, rank, world):
                       "cuda_graph": True, "loss_last": last},
            "clocks": clocks,
            "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
-                   "h2d_bytes_per_step": int(B * (H * W * 4 + N_OUT * 4)), "d2h_bytes_per_step": 24},
+                   "h2d_bytes_per_step": int(B * (H * W * 4 + N_OUT * 4)), "d2h_bytes_per_step": 24,
+                   "h2d_gb_per_s_of_this_box": round(h2d_gbps, 2),
+                   "h2d_bound_images_per_s": round(B * world / (B * H * W * 4 / (h2d_gbps * 1e9)), 1)},
            "gpu_launches": int(launches_per_step * args.steps * 2),
            "roofline": dominant, "roofline_other": other, "kernel_breakdown": breakdown, "eager_step_ms": total_ms / psteps, "gemm_shapes": gemm_shapes,
            "peaks": peaks, "inference": infer, "cpu_baseline": cpu}
