@@ -1,9 +1,11 @@
 // bf16 GEMM on the 5th-generation tensor cores: TMA (cp.async.bulk.tensor) feeds a
 // shared-memory ring, one elected thread issues tcgen05.mma with the fp32 accumulator
-// in TMEM, four warps drain it with tcgen05.ld. Serves the pointwise 1x1 convolutions
+// in TMEM, eight warps drain it with tcgen05.ld. Serves the pointwise 1x1 convolutions
 // of SeparableConv2D, the strided 1x1 residual convolutions, block1_conv2 (as an
 // im2col GEMM) and the Dense head of the reference model (spnet/models.py:359,388),
-// forward, data-gradient and weight-gradient:
+// forward, data-gradient and weight-gradient, and - as implicit GEMM, template parameter
+// CONV - the k x k stride-1 convolutions of the InceptionResNetV2 backbone
+// (spnet/models.py:18,357-359) and block1_conv2's data gradient:
 //
 //     D[M,N] (op)= A[M,K] * B[K,N]
 //
@@ -25,13 +27,11 @@ constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;    // two per TMEM lane quadrant, each draining half of the columns
-// Producer warps. More than one is only safe if every producer waits on EVERY stage's empty barrier (parity waits
-// tell adjacent phases apart, not a producer that ran two ring rounds ahead): striping k-blocks over four warps
-// passed the unit tests and then trapped at full InceptionResNetV2 size for exactly that reason. With the warp
-// index made compiler-visibly uniform (see the kernel) one producer's per-k-block stream is short enough.
-constexpr int kConvProducers = 1;
-__host__ __device__ constexpr int n_producers(int conv) { return conv ? kConvProducers : 1; }
-__host__ __device__ constexpr int n_threads(int conv) { return 64 + 32 * kEpiWarps + 32 * (n_producers(conv) - 1); }  // TMA, MMA, epilogue, extra TMA warps
+// ONE producer warp. (Several were tried for the convolution modes: striping k-blocks over four warps is unsafe -
+// an mbarrier parity wait tells adjacent phases apart, not a producer that ran two ring rounds ahead; it passed the
+// unit tests and trapped at full InceptionResNetV2 size - and striping the boxes of a k-block was not faster once
+// the issue path ran on the uniform datapath.)
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA warp, MMA warp, epilogue warps
 
 enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_ATOMIC_F32 = 2 };
 
@@ -101,19 +101,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Shared-memory matrix descriptor (sm_100 version 1), SWIZZLE_128B.
+// Shared-memory matrix descriptors (sm_100 version 1, SWIZZLE_128B) are assembled in the MMA warp:
 //  K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused.
 //  MN-major: atoms of 64 elements (128 B) x 8 k-rows; SBO = distance between 8-k-row
 //            groups (1024 B), LBO = distance between 64-element atoms along M/N.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
-    d |= (uint64_t)1 << 46;  // descriptor version
-    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
-    return d;
-}
 
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
                                                uint16_t cta_mask) {
@@ -150,19 +141,18 @@ __device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the four e
 // Persistent, warp-specialised kernel. One CTA per SM walks work units (split, m-tile, n-tile):
 //   warp 0      TMA producer   : fills the STAGES-deep smem ring
 //   warp 1      MMA issuer     : one elected lane issues tcgen05.mma into one of TWO TMEM accumulators
-//   warps 2..5  epilogue       : drain the other accumulator (tcgen05.ld -> convert -> global, fused
-//                                BatchNorm column statistics) while the next unit's MMAs run
+//   warps 2..9  epilogue       : drain the other accumulator (tcgen05.ld -> convert -> staging box -> TMA store,
+//                                fused BatchNorm column statistics) while the next unit's MMAs run
 // CL = 2: CTA pairs (thread-block cluster of 2 along M). Both CTAs of a pair work on the same
 // n-tile and k-range with adjacent m-tiles; each loads its own A tile and HALF of the shared B tile,
 // multicast by TMA into both CTAs' shared memory, so the pair reads B from L2 once.
 template <int BN, bool A_MN, bool B_MN, int STAGES, int CL, int CONV>
-__global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmD, GemmEpi epi,
                                                               int M, int N, int K, int kb_per_split, int tiles_m,
                                                               int tiles_n, int n_units, ConvGeom cg) {
     static_assert(CONV == 0 || CL == 1, "convolution modes run without CTA pairs");
-    constexpr int kProducers = n_producers(CONV);
     constexpr uint32_t A_BYTES = BM * BK * 2;
     constexpr uint32_t B_BYTES = BN * BK * 2;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -171,7 +161,6 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
     constexpr int NA_BOX = (A_MN || CONV == 2) ? BM / 64 : 1;
     constexpr int NB_BOX = (B_MN || CONV == 2) ? BN / 64 / CL : 1;
     constexpr int N_BOX = NA_BOX + NB_BOX;
-    constexpr int kActiveProducers = 1;  // every k-block (all of its boxes) is issued by ONE producer warp
     constexpr uint32_t A_BOX_BYTES = A_BYTES / NA_BOX;
     constexpr uint32_t B_BOX_BYTES = B_BYTES / (NB_BOX * CL);  // what one of this CTA's B boxes lands (in each CTA of the pair)
     extern __shared__ uint8_t smem_raw[];
@@ -206,7 +195,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, kActiveProducers);  // one arrive.expect_tx per k-block
+            mbar_init(full0 + 8 * s, 1);  // one arrive.expect_tx per k-block
             mbar_init(empty0 + 8 * s, CL);  // every CTA of the cluster must have consumed the stage
         }
         for (int a = 0; a < 2; ++a) {
@@ -230,16 +219,10 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
     pdl_wait();  // the set-up above overlapped the previous kernel's tail; global memory from here on
     // with CL = 2, tiles_m counts m-tile PAIRS; this CTA owns m-tile 2*pair + rank
 
-    // producer index of this warp: warp 0 and the warps after the epilogue group
-    const int prod = warp == 0 ? 0 : (warp >= 2 + kEpiWarps ? warp - (1 + kEpiWarps) : -1);
-    if (prod >= 0) {
-        // ---------------- TMA producers ----------------
-        // k-blocks are striped over the producer warps: warp p issues every box of k-blocks p, p + kProducers, ...
-        // (of the CTA's running k-block count) and announces the whole stage on its full barrier. One warp's
-        // per-k-block instruction stream (barrier poll, coordinates, expect_tx, 2-4 TMA issue sequences) is a
-        // dependent chain of several hundred cycles - longer than the MMAs of a narrow (N <= 128) k-block -
-        // so the convolution modes run kConvProducers of them side by side; the GEMM keeps one.
-        // (B boxes of a CTA pair land in both CTAs: each CTA expects CL x its own.)
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        // every box of a k-block is issued by one elected thread, which announces the stage's bytes on its full
+        // barrier (B boxes of a CTA pair land in both CTAs: each CTA expects CL x its own)
         constexpr uint32_t my_bytes = NA_BOX * A_BOX_BYTES + NB_BOX * B_BOX_BYTES * CL;
         uint32_t g0 = 0;  // k-blocks of the units before this one
         const uint32_t issuer = elect_one();
@@ -257,7 +240,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
             int px0 = 0, py0 = 0, pimg = 0;  // CONV 1: origin of this tile's pixel box
             int c_cb = 0, c_kx = 0, c_ky = 0, c_tp = 0;  // CONV 1: channel block, tap of this warp's next k-block
             int c_tx = 0, c_ty = 0, c_g = 0, w_kx = 0, w_ky = 0;  // CONV 2: pixel box of the next k-block; this unit's tap
-            const int kb_first = kb_begin + prod;  // this warp's first k-block of the unit
+            const int kb_first = kb_begin;
             if (CONV == 1) {
                 const int t2 = mt / cg.tiles_w;
                 px0 = (mt - t2 * cg.tiles_w) << cg.lw;
@@ -271,7 +254,7 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
                 c_tx = kb_first - t2 * cg.tiles_w; c_ty = t2 % cg.tiles_h; c_g = t2 / cg.tiles_h;
                 w_ky = tap / cg.KW; w_kx = tap - w_ky * cg.KW;
             }
-            for (int i = prod; i < nkb; i += kProducers) {
+            for (int i = 0; i < nkb; ++i) {
                 const uint32_t g = g0 + (uint32_t)i;  // running k-block index of this CTA -> ring stage and phase
                 const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
                 // coordinates that depend on the mode (warp-uniform, computed before the wait)
@@ -282,22 +265,18 @@ __global__ void __launch_bounds__(n_threads(CONV), 1) gemm_tc_kernel(const __gri
                     ax = px0 + cg.sign * (c_kx - cg.pl); ay = py0 + cg.sign * (c_ky - cg.pt); aimg = pimg;
                     kB = kA + (cg.b_tap_on_k ? c_tp * cg.b_tap_stride : 0);
                     nB = n0 + (cg.b_tap_on_k ? 0 : c_tp * cg.b_tap_stride);
-#pragma unroll
-                    for (int t = 0; t < kProducers; ++t)  // advance to this warp's next k-block
-                        if (++c_cb == cg.cin_blocks) {
-                            c_cb = 0; ++c_tp;
-                            if (++c_kx == cg.KW) { c_kx = 0; ++c_ky; }
-                        }
+                    if (++c_cb == cg.cin_blocks) {  // advance to the next k-block
+                        c_cb = 0; ++c_tp;
+                        if (++c_kx == cg.KW) { c_kx = 0; ++c_ky; }
+                    }
                 } else if (CONV == 2) {
                     bx = c_tx << cg.lw; by = c_ty << cg.lh;
                     aimg = c_g << (6 - cg.lw - cg.lh);
                     ax = bx + w_kx - cg.pl; ay = by + w_ky - cg.pt;
-#pragma unroll
-                    for (int t = 0; t < kProducers; ++t)
-                        if (++c_tx == cg.tiles_w) {
-                            c_tx = 0;
-                            if (++c_ty == cg.tiles_h) { c_ty = 0; ++c_g; }
-                        }
+                    if (++c_tx == cg.tiles_w) {
+                        c_tx = 0;
+                        if (++c_ty == cg.tiles_h) { c_ty = 0; ++c_g; }
+                    }
                 }
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 if (issuer) {
@@ -644,7 +623,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     }
     const int max_clusters = num_sms / CL;
     const int grid = (int)(units < max_clusters ? units : max_clusters) * CL;
-    cudaError_t e = spnet_launch_pdl(kern, dim3(grid), dim3(n_threads(CONV)), smem, stream, CL, ta, tb, td, epi, M, N, K, kbps,
+    cudaError_t e = spnet_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, CL, ta, tb, td, epi, M, N, K, kbps,
                                      tiles_m, tiles_n, (int)units, cg);
     if (e != cudaSuccess) {
         spnet_set_error("gemm_bf16: launch: %s", cudaGetErrorString(e));
