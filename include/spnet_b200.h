@@ -52,6 +52,13 @@ int spnet_selective_sigmoid_bwd(const float* y, const float* dy, float* dx, int 
  * exists [n,ncols/8] u8. */
 int spnet_decode_detections(const float* y, const float* means, const float* ranges, int n, int ncols, float* denorm, int* ints, unsigned char* exists, cudaStream_t stream);
 
+/* ---- Evaluation metrics (spnet/diagnostics.py: calc_errors :13-60; compute_iou :85-120 for every (image, slot)
+ *      pair, analytic ellipse raster with an anti-aliasing margin instead of cv2). yp / yt: denormalised fp32
+ *      [n, ncols]; counters int32 [7] (caller zeroes), pix_err fp32 [n]; iou fp32 [n, ncols/8] (-1 = skipped pair),
+ *      counts nullable int32 [n, ncols/8, 2]. ---- */
+int spnet_calc_errors(const float* yp, const float* yt, int n, int ncols, int* counters, float* pix_err, cudaStream_t stream);
+int spnet_ellipse_iou(const float* yp, const float* yt, int n, int ncols, int nx, int ny, float margin, float* iou, int* counts, cudaStream_t stream);
+
 /* ---- AugmentOnTheFly on the device (spnet/callbacks.py:272-341; cutout_inplace / salt_n_pepa_inplace of
  *      spnet/augmentation.py:117-135,159-180): x = augmented copy of the pristine frames x_orig, fp32 [n,H,W,C],
  *      one launch per epoch, counter-based random draws keyed by (seed, frame). ---- */

@@ -242,6 +242,26 @@ def augment_on_the_fly(x_orig, x, seed, max_regions=6, minsize=11, maxsize=75, s
     return x
 
 
+def calc_errors(yp, yt):
+    """-> (counters int32 [7], pix_err fp32 [n]); yp / yt denormalised fp32 [n, ncols] on the device."""
+    _chk(yp, yt)
+    n, ncols = yp.shape
+    counters = torch.zeros(7, device=yp.device, dtype=torch.int32)
+    pix_err = torch.empty(n, device=yp.device, dtype=torch.float32)
+    lib().calc_errors(_p(yp), _p(yt), n, ncols, _p(counters), _p(pix_err), _s())
+    return counters, pix_err
+
+
+def ellipse_iou(yp, yt, nx=512, ny=384, margin=1.35, counts=False):
+    """-> iou fp32 [n, ncols/8] (-1 = pair skipped by the reference); counts=True also returns int32 [n, ncols/8, 2]."""
+    _chk(yp, yt)
+    n, ncols = yp.shape
+    iou = torch.empty(n, ncols // 8, device=yp.device, dtype=torch.float32)
+    cnt = torch.empty(n, ncols // 8, 2, device=yp.device, dtype=torch.int32) if counts else None
+    lib().ellipse_iou(_p(yp), _p(yt), n, ncols, nx, ny, margin, _p(iou), _p(cnt), _s())
+    return (iou, cnt) if counts else iou
+
+
 # ----------------------------------------------------------------------------- pooling
 def maxpool3s2_add_fwd(z, a=None, b=None, res=None, ra=None, rb=None, out=None, argmax=None):
     _chk(z, res, out, argmax)
