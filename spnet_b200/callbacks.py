@@ -94,13 +94,16 @@ class ParallelCheckpointCallback(Callback):
 class MyProgressCallback(Callback):
     """Text part of the reference's progress callback (spnet/callbacks.py:58-265): per epoch,
     predict on the validation set, append `epoch train val center size angle noobj class` to
-    losses.dat and print the FPS line. The plots / sample PNGs are out of scope (SURVEY.md §2 #12)."""
+    losses.dat, print the FPS line, and compute the ring-count / existence accuracy the reference plots
+    (diagnostics.calc_errors on the de-normalised predictions, :156-165; kept in self.acc_hist and printed).
+    The plots / sample PNGs are out of scope (SURVEY.md §2 #12)."""
 
     def __init__(self, X_val=None, Y_val=None, val_file_list=None, log_dir="./logs", pred_shape=None, **kwargs):
         super().__init__()
         self.X_val, self.Y_val, self.val_file_list = X_val, Y_val, val_file_list
         self.log_dir, self.pred_shape = log_dir, pred_shape
         self.batch_size = kwargs.get("batch_size", 32)
+        self.acc_hist = []
 
     def on_train_begin(self, logs=None):
         from . import multi_gpu
@@ -124,6 +127,20 @@ class MyProgressCallback(Callback):
         with open(os.path.join(self.log_dir, "losses.dat"), "a") as f:
             f.write("%d %g %g %s\n" % (epoch + 1, logs.get("loss", float("nan")), logs.get("val_loss", total),
                                        " ".join("%g" % p for p in parts)))
+        # ring-count / existence accuracy on world values (spnet/callbacks.py:152-165)
+        from . import diagnostics
+        if len(utils.means) == 0:
+            utils.setup_means_and_ranges(self.pred_shape or [6, 6, 2, cf.vars_per_pred])
+        Yp = np.array(Y_pred, dtype=np.float32, copy=True)
+        if cf.loss_type != "same":  # logits -> probabilities
+            Yp[:, cf.ind_noobj::cf.vars_per_pred] = 1.0 / (1.0 + np.exp(-Yp[:, cf.ind_noobj::cf.vars_per_pred]))
+        r = diagnostics.calc_errors(utils.denorm_Y(Yp), utils.denorm_Y(np.asarray(self.Y_val, dtype=np.float32)))
+        ring_miscounts, total_obj, false_obj_pos, false_obj_neg = r[0], r[2], r[3], r[4]
+        mistakes = ring_miscounts + false_obj_pos + false_obj_neg
+        class_acc = (total_obj - mistakes) * 1.0 / total_obj * 100 if total_obj else float("nan")
+        self.acc_hist.append(class_acc)
+        print("  diagnostics: ring_miscounts, total_obj, false_obj_pos, false_obj_neg = %d %d %d %d   class accuracy = %.2f %%"
+              % (ring_miscounts, total_obj, false_obj_pos, false_obj_neg, class_acc))
 
 
 class AugmentOnTheFly(Callback):

@@ -69,6 +69,7 @@ def test_fit_loop_reduces_loss_and_checkpoints(tmp_path):
     loss = hist.history["loss"]
     assert len(loss) == 12 and np.isfinite(loss).all() and min(loss[6:]) < loss[0], loss
     assert os.path.exists(tmp_path / "weights.hdf5") and os.path.exists(tmp_path / "losses.dat")
+    assert len(prog.acc_hist) == 12 and all(a <= 100.0 for a in prog.acc_hist)  # calc_errors ran every epoch
     again, _ = models.setup_model(X, 576, try_checkpoint=True, no_cp_fatal=True, weights_file=str(tmp_path / "weights.hdf5"),
                                   freeze_fac=0.0)
     assert len(again.get_weights()) == len(model.get_weights())
