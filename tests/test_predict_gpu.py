@@ -126,3 +126,42 @@ def test_irv2_backbone_through_the_model_surface(tmp_path):
     finally:
         cf.basemodel = "Xception"
         cf.model_type = "monolithic"
+
+
+def test_evaluate_cli_path(tmp_path, capsys):
+    """evaluate_spnet.evaluate_network on a small Test/ directory (PNG + metadata CSV pairs): predict ->
+    de-normalise -> mAP + error summary on the device -> hawley_spnet.csv."""
+    from PIL import Image
+    import spnet.config as cf
+    from spnet import models
+    import evaluate_spnet
+    from spnet_b200 import fake_espi
+
+    cf.model_type = "big"
+    cf.compute_dtype = "bf16"
+    test_dir = tmp_path / "Test"
+    test_dir.mkdir()
+    from spnet import utils
+    n, i, seed = 4, 0, 300
+    while i < n:
+        img, rows = fake_espi.make_frame(seed)
+        seed += 1
+        try:
+            utils.build_Y_from_rows([rows], pred_grid=[6, 6, 2])  # labels that overflow a grid cell are redrawn
+        except AssertionError:
+            continue
+        Image.fromarray(img.reshape(img.shape[0], img.shape[1])).save(test_dir / ("steelpan_%07d.png" % i))
+        with open(test_dir / ("steelpan_%07d.csv" % i), "w") as f:
+            f.write("\n".join(",".join(str(v) for v in r) for r in rows))
+        i += 1
+    X = np.zeros((2, 384, 512, 1), np.float32)
+    model, _ = models.setup_model(X, 576, try_checkpoint=False, freeze_fac=0.0, quick_setup=True)
+    log_dir = str(tmp_path / "out") + "/"
+    evaluate_spnet.evaluate_network(model=model, datapath=str(test_dir) + "/", fraction=1.0, log_dir=log_dir, batch_size=2,
+                                    draw_images=False)
+    out = capsys.readouterr().out
+    assert "mAP = " in out and "Total Mistakes = " in out and "Mean pixel error =" in out
+    last = evaluate_spnet.evaluate_network.last
+    assert 0.0 <= last["mAP"] <= 1.0 and last["total_obj"] >= n  # every frame holds at least one antinode
+    assert os.path.exists(log_dir + "hawley_spnet.csv")
+    cf.model_type = "monolithic"
