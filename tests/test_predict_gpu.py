@@ -155,13 +155,24 @@ def test_evaluate_cli_path(tmp_path, capsys):
             f.write("\n".join(",".join(str(v) for v in r) for r in rows))
         i += 1
     X = np.zeros((2, 384, 512, 1), np.float32)
-    model, _ = models.setup_model(X, 576, try_checkpoint=False, freeze_fac=0.0, quick_setup=True)
+    engine_model, _ = models.setup_model(X, 576, try_checkpoint=False, freeze_fac=0.0, quick_setup=True)
+    _, Y_lab, _, _ = utils.build_dataset(path=str(test_dir) + "/", load_frac=1.0, set_means_ranges=True, batch_size=2,
+                                         shuffle=False, pred_grid=[6, 6, 2])
+
+    class NearTruth:
+        """The engine's forward pass stays in the path, but a random-initialised network finds no ellipse at all
+        (the reference's precision() then divides by zero, and so does ours): predictions = labels + a small
+        bounded function of the network output."""
+
+        def predict(self, Xb, batch_size=None):
+            return (Y_lab + 0.05 * np.tanh(engine_model.predict(Xb, batch_size=batch_size))).astype(np.float32)
+
     log_dir = str(tmp_path / "out") + "/"
-    evaluate_spnet.evaluate_network(model=model, datapath=str(test_dir) + "/", fraction=1.0, log_dir=log_dir, batch_size=2,
-                                    draw_images=False)
+    evaluate_spnet.evaluate_network(model=NearTruth(), datapath=str(test_dir) + "/", fraction=1.0, log_dir=log_dir,
+                                    batch_size=2, draw_images=False)
     out = capsys.readouterr().out
     assert "mAP = " in out and "Total Mistakes = " in out and "Mean pixel error =" in out
     last = evaluate_spnet.evaluate_network.last
-    assert 0.0 <= last["mAP"] <= 1.0 and last["total_obj"] >= n  # every frame holds at least one antinode
+    assert 0.5 <= last["mAP"] <= 1.0 and last["total_obj"] >= n  # every frame holds at least one antinode
     assert os.path.exists(log_dir + "hawley_spnet.csv")
     cf.model_type = "monolithic"
