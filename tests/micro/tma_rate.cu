@@ -1,5 +1,10 @@
-// How fast can one SM's TMA unit land tiles from L2? 1 CTA per SM, no consumer: thread(s) keep S boxes in
-// flight and re-issue as each lands. Prints bytes/clk/SM and clk per box row for several box shapes.
+// How fast can one SM land TMA tiles from L2? 1 CTA per SM, no consumer: thread(s) keep S boxes in flight and
+// re-issue as each lands. Prints bytes/clk/SM and clk per box row for several box shapes.
+// READ THE RESULT WITH CARE: one issuing thread shows ~420 cycles per box whatever the box size and two issuing
+// warps show half of that - this is the cost of THIS LOOP's single-thread instruction stream (integer
+// divisions, an ELECT / R2UR.BROADCAST sequence around every UTMALDG because the operands live in vector
+// registers), not a limit of the TMA unit: with four issuers the SM lands ~74 B/clk. The same effect bounded the
+// narrow GEMM / convolution tiles until the issue threads moved to the uniform datapath.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -o tma_rate tma_rate.cu
 #include <cuda.h>
 #include <cudaTypedefs.h>
