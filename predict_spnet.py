@@ -17,8 +17,11 @@ default_image_dir = "/home/shawley/datasets/zooniverse_steelpan/"
 
 
 def predict_network(weights_file="spnet.model", datapath=default_image_dir, fraction=1.0, log_dir="logs/Predicting/",
-                    batch_size=16, model=None, X_pred="", draw_images=True):
+                    batch_size=16, model=None, X_pred="", draw_images=True, stream_chunk=None):
+    """stream_chunk (B200 build only): decode / predict the directory in chunks of that many frames, decoding chunk
+    k+1 on the host threads while chunk k is on the GPU, instead of loading every frame into memory first."""
     img_file_list = None
+    streaming = stream_chunk is not None and isinstance(X_pred, str) and "" == X_pred
     if isinstance(X_pred, str) and "" == X_pred:
         print(f"Getting data from {datapath}, fraction = {fraction}.")
         if cf.model_type == "simple":
@@ -35,7 +38,12 @@ def predict_network(weights_file="spnet.model", datapath=default_image_dir, frac
         if batch_size is not None:
             total_load = utils.nearest_multiple(total_load, batch_size)
         print("      Total files = ", total_files, ", going to load total_load = ", total_load)
-        X_pred, img_dims = utils.build_X(total_load, img_file_list, force_dim=force_dim, grayscale=grayscale)
+        if streaming:
+            img_file_list = img_file_list[:total_load]
+            chunks = utils.stream_X(img_file_list, int(stream_chunk), force_dim=force_dim, grayscale=grayscale)
+            first_lo, X_pred = next(chunks)  # the model is set up from the first chunk's frame shape
+        else:
+            X_pred, img_dims = utils.build_X(total_load, img_file_list, force_dim=force_dim, grayscale=grayscale)
         print("")
     if model is None:
         print("Loading model from", weights_file)
@@ -47,10 +55,16 @@ def predict_network(weights_file="spnet.model", datapath=default_image_dir, frac
         else:
             print("   Loading whole model")
             model = models.load_model(weights_file)
-    m = X_pred.shape[0]
+    m = len(img_file_list) if streaming else X_pred.shape[0]
     print("    Predicting... (m = ", m, " frames in dataset)", sep="")
     start_time = time.time()
-    Y_pred = model.predict(X_pred, batch_size=batch_size)
+    if streaming:
+        parts = [model.predict(X_pred, batch_size=batch_size)]
+        for _, Xc in chunks:
+            parts.append(model.predict(Xc, batch_size=batch_size))
+        Y_pred = np.concatenate(parts, axis=0)
+    else:
+        Y_pred = model.predict(X_pred, batch_size=batch_size)
     elapsed = time.time() - start_time
     print("    ...elapsed time to predict = ", elapsed, "s.   FPS = ", m * 1.0 / elapsed)
 
@@ -89,10 +103,13 @@ if __name__ == "__main__":
     parser.add_argument("-l", "--logdir", help="Directory of log/output files", default="logs/Predicting/")
     parser.add_argument("-b", "--batch_size", type=int, help="Batch size to use", default=16)
     parser.add_argument("--no-png", action="store_true", help="write only hawley_spnet.csv, skip the per-image PNGs")
+    parser.add_argument("--stream", type=int, default=None, metavar="N",
+                        help="decode and predict N frames at a time (next chunk decoded while this one is on the GPU)")
     parser.add_argument("--dtype", choices=["bf16", "fp32"], default=cf.compute_dtype)
     parser.add_argument("--model_type", default=cf.model_type, help="'big' keeps 384x512 input, default resizes to 331x331")
     args = parser.parse_args()
     cf.compute_dtype = args.dtype
     cf.model_type = args.model_type
     model = predict_network(weights_file=args.weights, datapath=args.datapath, fraction=args.fraction,
-                            log_dir=args.logdir, batch_size=args.batch_size, draw_images=not args.no_png)
+                            log_dir=args.logdir, batch_size=args.batch_size, draw_images=not args.no_png,
+                            stream_chunk=args.stream)

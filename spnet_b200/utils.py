@@ -171,6 +171,30 @@ def build_X(total_load, img_file_list, force_dim=224, grayscale=False):
     return X, img_dims
 
 
+def stream_X(img_file_list, chunk, force_dim=224, grayscale=False):
+    """Generator over (start, X_chunk): the frames of build_X in chunks of `chunk` files, the NEXT chunk being
+    decoded by the worker threads while the caller consumes the current one (at
+    B200 inference rates PIL decode, not the network, bounds predict_spnet over tens of thousands of frames, and
+    the whole set no longer has to fit in host memory). Values are identical to build_X's."""
+    nproc = os.cpu_count() or 1
+    n = len(img_file_list)
+
+    def decode(lo):
+        files = img_file_list[lo:lo + chunk]
+        with ThreadPoolExecutor(nproc) as ex:
+            return np.stack(list(ex.map(_load_one, [(f, force_dim, grayscale) for f in files]))).astype(cf.dtype)
+
+    with ThreadPoolExecutor(1) as bg:
+        fut = bg.submit(decode, 0) if n else None
+        lo = 0
+        while lo < n:
+            X = fut.result()
+            nxt = lo + chunk
+            fut = bg.submit(decode, nxt) if nxt < n else None
+            yield lo, X
+            lo = nxt
+
+
 def build_dataset(path="Train/", load_frac=1.0, set_means_ranges=False, pred_grid=[6, 6, 2], batch_size=None,
                   shuffle=True):
     """spnet/utils.py:425-482."""

@@ -241,3 +241,26 @@ def test_data_parallel_host_logic_gloo_world2(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                          capture_output=True, text=True, env=env, timeout=240)
     assert "DP_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_stream_X_yields_build_X_in_chunks(tmp_path):
+    """utils.stream_X: same values as build_X (spnet/utils.py:325-421), chunked, next chunk decoded in the
+    background; ragged last chunk; both the native-size grayscale path and the LANCZOS-resize path."""
+    from PIL import Image
+    from spnet_b200 import utils
+    rng = np.random.RandomState(4)
+    files = []
+    for i in range(7):
+        img = rng.randint(0, 256, (48, 64), dtype=np.uint8)
+        f = str(tmp_path / ("f_%02d.png" % i))
+        Image.fromarray(img).save(f)
+        files.append(f)
+    for force_dim, gray in ((None, True), (32, True), (32, False)):
+        X, _ = utils.build_X(len(files), files, force_dim=force_dim, grayscale=gray)
+        got, starts = [], []
+        for lo, Xc in utils.stream_X(files, 3, force_dim=force_dim, grayscale=gray):
+            starts.append(lo)
+            got.append(Xc)
+        assert starts == [0, 3, 6] and [g.shape[0] for g in got] == [3, 3, 1]
+        np.testing.assert_array_equal(np.concatenate(got, axis=0), X)
+    assert list(utils.stream_X([], 3)) == []

@@ -176,3 +176,4 @@ def test_evaluate_cli_path(tmp_path, capsys):
     assert 0.5 <= last["mAP"] <= 1.0 and last["total_obj"] >= n  # every frame holds at least one antinode
     assert os.path.exists(log_dir + "hawley_spnet.csv")
     cf.model_type = "monolithic"
+
