@@ -177,3 +177,37 @@ def test_evaluate_cli_path(tmp_path, capsys):
     assert os.path.exists(log_dir + "hawley_spnet.csv")
     cf.model_type = "monolithic"
 
+
+
+def test_predict_streaming_matches_whole_set(tmp_path):
+    """predict_network(stream_chunk=...) = the same CSV as loading every frame first (up to the last bits of the
+    Dense head's split-K accumulation, which can move a rounded integer by one)."""
+    from PIL import Image
+    import spnet.config as cf
+    from spnet import models
+    import predict_spnet
+    from spnet_b200 import fake_espi
+
+    cf.model_type = "big"
+    cf.compute_dtype = "bf16"
+    n = 6
+    for i in range(n):
+        img, _ = fake_espi.make_frame(500 + i)
+        Image.fromarray(img).save(tmp_path / ("steelpan_%07d.png" % i))
+    X = np.zeros((2, 384, 512, 1), np.float32)
+    model, _ = models.setup_model(X, 576, try_checkpoint=False, freeze_fac=0.0, quick_setup=True)
+    a_dir, b_dir = str(tmp_path / "whole") + "/", str(tmp_path / "stream") + "/"
+    predict_spnet.predict_network(model=model, datapath=str(tmp_path), log_dir=a_dir, batch_size=2, draw_images=False)
+    predict_spnet.predict_network(model=model, datapath=str(tmp_path), log_dir=b_dir, batch_size=2, draw_images=False,
+                                  stream_chunk=4)
+    a = open(a_dir + "hawley_spnet.csv").read().strip().splitlines()
+    b = open(b_dir + "hawley_spnet.csv").read().strip().splitlines()
+    cf.model_type = "monolithic"
+    assert len(a) == len(b) and a[0] == b[0]  # header + one row per detection (or per empty frame)
+    for x, y in zip(a[1:], b[1:]):
+        fx, fy = x.split(","), y.split(",")
+        assert fx[2] == fy[2]  # file name
+        for k in (0, 1, 4, 5):  # cx, cy, a, b: rounded integers
+            assert abs(int(fx[k]) - int(fy[k])) <= 1
+        for k in (3, 6):  # rings, angle: floats printed at full precision
+            assert abs(float(fx[k]) - float(fy[k])) <= 1e-3 * max(1.0, abs(float(fx[k])))
