@@ -264,3 +264,20 @@ def test_stream_X_yields_build_X_in_chunks(tmp_path):
         assert starts == [0, 3, 6] and [g.shape[0] for g in got] == [3, 3, 1]
         np.testing.assert_array_equal(np.concatenate(got, axis=0), X)
     assert list(utils.stream_X([], 3)) == []
+
+
+def test_every_exported_entry_point_is_documented():
+    """INTEGRATION.md is the map from reference operations to C-ABI entry points: nothing the header exports may
+    be missing from it (names may be written with {a,b} alternations)."""
+    import re
+    from spnet_b200._lib import parse_header
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    expanded = set(re.findall(r"spnet_\w+", text))
+    for stem, alts, tail in re.findall(r"(spnet_\w*?)\{([^}]*)\}(\w*)", text):
+        for a in alts.split(","):
+            expanded.add(stem + a.strip() + tail)
+    for stem in re.findall(r"(spnet_\w+_)\*", text):
+        expanded.update(n for n in parse_header() if n.startswith(stem))
+    missing = sorted(n for n in parse_header() if n not in expanded)
+    assert not missing, missing
