@@ -152,7 +152,8 @@ class AugmentOnTheFly(Callback):
     (:66-71) discards its result, i.e. is a no-op, and bp_mixup is commented out at the call site. Labels are
     untouched (they are already grid-assigned and normalised).
 
-    X may be a numpy array (host path, numpy's global RNG like the reference) or a CUDA tensor: then the pristine
+    X may be a numpy array (host path: numpy's global RNG consumed in the reference's order, so the same seed gives
+    the reference's frames bit for bit) or a CUDA tensor: then the pristine
     copy stays in HBM too and one kernel launch per epoch does the rewrite (csrc/augment.cu,
     spnet_augment_on_the_fly) - the device-resident input path of SPNetModel.fit."""
 
@@ -177,7 +178,7 @@ class AugmentOnTheFly(Callback):
 
     @staticmethod
     def salt_n_pepa(img, salt_vs_pepper=0.2, amount=0.004):
-        if np.random.rand() >= 0.5:
+        if np.random.choice(["good", "not good"]) != "good":  # the reference's coin, same draw from numpy's stream
             return
         salt, pepper = np.max(img), np.min(img)
         for count, value in ((int(np.ceil(amount * img.size * salt_vs_pepper)), salt),
@@ -198,3 +199,8 @@ class AugmentOnTheFly(Callback):
         for i in range(X.shape[0]):
             self.cutout(X[i])
             self.salt_n_pepa(X[i])
+            # blur() / blur_inplace() (callbacks.py:303-305, augmentation.py:66-71) change nothing - GaussianBlur's
+            # result is dropped - but they draw from the generators; the same draws keep this loop on the
+            # reference's random stream (same seed -> same augmented frames, tests/golden/ref_augment.npz)
+            if np.random.rand() < 0.4 and np.random.random() <= 0.3:
+                random.choice([3, 7])

@@ -111,3 +111,22 @@ def test_fit_with_device_resident_dataset_and_augmentation():
     h2 = m2.fit(torch.from_numpy(X).cuda(), torch.from_numpy(Y).cuda(), batch_size=8, epochs=1, shuffle=False, verbose=0)
     assert abs(h1.history["loss"][0] - h2.history["loss"][0]) <= 2e-2 * abs(h1.history["loss"][0])
     cf.model_type = "monolithic"
+
+
+def test_host_callback_reproduces_the_reference_bit_for_bit():
+    """Same numpy seed -> the same augmented frames as the reference's own AugmentOnTheFly.on_epoch_begin
+    (tests/golden/ref_augment.npz, written by oracle/make_goldens_augment.py running the reference's code): the host
+    path draws from numpy's global stream in the reference's order, including the draws of its no-op blur."""
+    import os
+    import random
+    from spnet_b200.callbacks import AugmentOnTheFly
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_augment.npz"))
+    X, Y = g["X0"].copy(), g["Y0"].copy()
+    cb = AugmentOnTheFly(X, Y, aug_every=1)
+    np.random.seed(123)
+    random.seed(123)
+    cb.on_epoch_begin(0)
+    np.testing.assert_array_equal(X, g["epoch0"])
+    cb.on_epoch_begin(1)
+    np.testing.assert_array_equal(X, g["epoch1"])
+    np.testing.assert_array_equal(Y, g["Y_after"])
