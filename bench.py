@@ -152,17 +152,10 @@ def algorithmic_work(name, a):
     if name == "spnet_dwconv3x3_fwd":      # in,k,a,b,relu,out,dtype,B,H,W,C,stream
         n = a[7] * a[8] * a[9] * a[10]
         return 2 * n * es(a[6]), 18 * n
-    if name == "spnet_dwconv3x3_dgrad":    # gout,k,gin,mask,ma,mb,add,adds,dtype,B,H,W,C
-        n = a[9] * a[10] * a[11] * a[12]
-        t = 2 + (1 if a[3] else 0) + (1 if a[6] else 0)
-        return t * n * es(a[8]), 18 * n
     if name == "spnet_dwconv3x3_bwd_fused":  # gout,in,k,a,b,relu,mean,rstd,stats,add,adds,gin,dk,dtype,B,H,W,C
         n = a[14] * a[15] * a[16] * a[17]
         t = 3 + (1 if a[9] else 0)
         return t * n * es(a[13]), 36 * n
-    if name == "spnet_dwconv3x3_wgrad":    # in,g,a,b,relu,dk,dtype,B,H,W,C
-        n = a[7] * a[8] * a[9] * a[10]
-        return 2 * n * es(a[6]), 18 * n
     if name == "spnet_gemm_bf16":          # A,lda,amn,B,ldb,bmn,D,ldd,mode,M,N,K,splits,...
         M, N, K = a[9], a[10], a[11]
         return 2 * (M * K + N * K) + (2 if a[8] == 0 else 4) * M * N, 2 * M * N * K

@@ -332,6 +332,139 @@ class OracleSPNet:
 
 
 # =================================================================================================
+# Storage-faithful mode: the same networks with every tensor the B200 engine keeps in HBM rounded to bf16
+# at the point where the engine stores it (spnet_b200/engine.py):
+#   * every convolution output z (pre-BatchNorm) is stored as bf16, and its BatchNorm batch statistics are
+#     taken over the STORED values;
+#   * BatchNorm (+ReLU) is applied by the consumer in fp32 as y = a*z + b and is NOT rounded when the consumer
+#     is a depthwise / small convolution (on-load transform); it IS rounded where the engine materialises the
+#     tensor: GEMM A operands (im2col of block1, MobileNet's relu6(BN(dw)), every conv+BN+ReLU of
+#     InceptionResNetV2), block inputs / outputs (x + BN(z), maxpool(BN(z)) + BN(res)), the flattened features;
+#   * weights of the tensor-core GEMMs (pointwise 1x1, residual 1x1, block1_conv2, Dense, every
+#     InceptionResNetV2 convolution but the first) are the bf16 working copy; depthwise and stem / first-layer
+#     kernels stay fp32.
+# With storage="fp32" every rounding is the identity and these classes compute exactly what the plain oracles
+# above compute (tests/test_oracle_goldens.py checks that), so the bf16 comparison separates the error of the
+# KERNELS (accumulation order, a few flipped roundings) from the amplification of bf16 storage itself, which
+# any implementation that stores bf16 activations shares.
+# Backward: straight-through (the rounding has gradient 1), i.e. exact gradients of the rounded forward pass.
+# =================================================================================================
+def bf16_round(x):
+    r = x.detach().to(torch.bfloat16).to(x.dtype)
+    return x + (r - x.detach())
+
+
+class _StoredMixin:
+    storage = "bf16"
+
+    def q(self, x):
+        return bf16_round(x) if self.storage == "bf16" else x
+
+    def wq(self, key):
+        return self.q(self.p[key])
+
+    def bn_ab(self, z, name, training):
+        """(a, b) of y = a*z + b per channel, fp32, from fp64 statistics of the stored z (NCHW)."""
+        g = self.p[name + "/gamma"] if (name + "/gamma") in self.p else None
+        b = self.p[name + "/beta"]
+        mm, mv = self.p[name + "/moving_mean"], self.p[name + "/moving_variance"]
+        if training:
+            zd = z.double()
+            mean = zd.mean((0, 2, 3))
+            var = zd.var((0, 2, 3), unbiased=False)
+            n = z.numel() // z.shape[1]
+            with torch.no_grad():
+                uv = var * n / max(n - 1, 1) if self.unbiased else var
+                mm.mul_(BN_MOMENTUM).add_(((1 - BN_MOMENTUM) * mean).to(mm.dtype))
+                mv.mul_(BN_MOMENTUM).add_(((1 - BN_MOMENTUM) * uv).to(mv.dtype))
+            rstd = (1.0 / torch.sqrt(var + BN_EPS)).to(z.dtype)
+            mean = mean.to(z.dtype)
+        else:
+            rstd = 1.0 / torch.sqrt(mv + BN_EPS)
+            mean = mm
+        a = rstd if g is None else g * rstd
+        return a, b - mean * a
+
+    def bnz(self, z, name, training):
+        a, b = self.bn_ab(z, name, training)
+        return z * a[None, :, None, None] + b[None, :, None, None]
+
+    def stem(self, x_nhwc, training, dropout_mask):
+        p = self.p
+        x0 = torch.as_tensor(np.asarray(x_nhwc), dtype=self.dtype).permute(0, 3, 1, 2)
+        p1 = self.q(F.avg_pool2d(conv2d_tf(x0, p["conv2d_1/kernel"], 1, "same"), 2))
+        s0 = self.q(F.avg_pool2d(x0, 2))
+        x = F.leaky_relu(self.bnz(p1, "batch_normalization_1", training), 0.1)
+        c2 = self.q(conv2d_tf(x, p["conv2d_2/kernel"], 1, "same"))
+        x = F.leaky_relu(self.bnz(c2, "batch_normalization_2", training), 0.1)
+        c3 = self.q(conv2d_tf(x, p["conv2d_3/kernel"], 1, "same"))
+        x = self.bnz(c3, "batch_normalization_3", training) + s0
+        if training and dropout_mask is not None:
+            m = torch.as_tensor(np.asarray(dropout_mask), dtype=self.dtype).permute(0, 3, 1, 2)
+            x = x * m / 0.9
+        return self.q(x)
+
+    def forward(self, x_nhwc, training=False, dropout_mask=None, taps=False):
+        self.taps = {}
+        d = self.stem(x_nhwc, training, dropout_mask)
+        if taps:
+            self.taps["stem"] = d
+        feat = self.backbone(d, training, taps)  # already materialised (rounded) by the backbone
+        flat = feat.permute(0, 2, 3, 1).reshape(feat.shape[0], -1)
+        return flat @ self.wq("FinalOutput/kernel") + self.p["FinalOutput/bias"]
+
+
+class OracleSPNetStored(_StoredMixin, OracleSPNet):
+    """Xception-SPNet with the engine's storage points (XceptionSPNetEngine._backbone_fwd)."""
+
+    def __init__(self, weights, H, W, n_out=576, dtype=torch.float32, unbiased_moving_var=True, storage="bf16"):
+        OracleSPNet.__init__(self, weights, H, W, n_out, dtype, unbiased_moving_var)
+        self.storage = storage
+
+    def sepz(self, x, name):
+        """x: the depthwise input AFTER the on-load transform (fp32, not rounded) -> stored z of the pointwise."""
+        t = self.q(conv2d_tf(x, self.p[name + "/depthwise_kernel"], 1, "same", groups=x.shape[1]))
+        return self.q(conv2d_tf(t, self.wq(name + "/pointwise_kernel"), 1, "valid"))
+
+    def entry(self, x, blk, nres, relu_in, training):
+        xs = x[:, :, ::2, ::2]  # 1x1 stride 2 'same' reads the even pixels
+        zr = self.q(conv2d_tf(xs, self.wq("conv2d_%d/kernel" % nres), 1, "valid"))
+        z1 = self.sepz(torch.relu(x) if relu_in else x, "block%d_sepconv1" % blk)
+        z2 = self.sepz(torch.relu(self.bnz(z1, "block%d_sepconv1_bn" % blk, training)), "block%d_sepconv2" % blk)
+        y = maxpool3s2_same(self.bnz(z2, "block%d_sepconv2_bn" % blk, training))
+        return self.q(y + self.bnz(zr, "batch_normalization_%d" % nres, training))
+
+    def backbone(self, x, training, taps=False):
+        p = self.p
+        z11 = self.q(conv2d_tf(x, p["block1_conv1/kernel"], 2, "valid"))
+        col = self.q(torch.relu(self.bnz(z11, "block1_conv1_bn", training)))          # im2col operand
+        z12 = self.q(conv2d_tf(col, self.wq("block1_conv2/kernel"), 1, "valid"))
+        x = self.q(torch.relu(self.bnz(z12, "block1_conv2_bn", training)))            # x2
+        if taps:
+            self.taps["block1"] = x
+        for blk, nres in ((2, 4), (3, 5), (4, 6)):
+            x = self.entry(x, blk, nres, blk != 2, training)
+            if taps:
+                self.taps["block%d" % blk] = x
+        for blk in range(5, 13):
+            z = self.sepz(torch.relu(x), "block%d_sepconv1" % blk)
+            z = self.sepz(torch.relu(self.bnz(z, "block%d_sepconv1_bn" % blk, training)), "block%d_sepconv2" % blk)
+            z = self.sepz(torch.relu(self.bnz(z, "block%d_sepconv2_bn" % blk, training)), "block%d_sepconv3" % blk)
+            x = self.q(self.bnz(z, "block%d_sepconv3_bn" % blk, training) + x)
+            if taps:
+                self.taps["block%d" % blk] = x
+        x = self.entry(x, 13, 7, True, training)
+        if taps:
+            self.taps["block13"] = x
+        z = self.sepz(x, "block14_sepconv1")
+        z = self.sepz(torch.relu(self.bnz(z, "block14_sepconv1_bn", training)), "block14_sepconv2")
+        x = self.q(torch.relu(self.bnz(z, "block14_sepconv2_bn", training)))
+        if taps:
+            self.taps["block14"] = x
+        return x
+
+
+# =================================================================================================
 # MobileNet backbone (BASELINE configs[2]): keras.applications.mobilenet.MobileNet @ Keras 2.1.3,
 # alpha = 1, depth_multiplier = 1, include_top=False (reference call site spnet/models.py:349-355).
 # Not in the reference tree either; restated from its published architecture (SURVEY.md §2.2):
@@ -544,6 +677,67 @@ class OracleIRv2SPNet(OracleSPNet):
         def residual(t, up, scale, relu):
             y = t + scale * up
             return torch.relu(y) if relu else y
+
+        w = _IRv2Walker(conv_bn, conv_bias, lambda t: F.max_pool2d(t, 3, 2), avgpool, lambda ts: torch.cat(ts, 1), residual)
+        return w.run(x)
+
+
+class OracleMobileNetSPNetStored(_StoredMixin, OracleMobileNetSPNet):
+    """MobileNet-SPNet with the engine's storage points (MobileNetSPNetEngine._backbone_fwd)."""
+
+    def __init__(self, weights, H, W, n_out=576, dtype=torch.float32, unbiased_moving_var=True, storage="bf16"):
+        OracleMobileNetSPNet.__init__(self, weights, H, W, n_out, dtype, unbiased_moving_var)
+        self.storage = storage
+
+    def backbone(self, x, training, taps=False):
+        p = self.p
+        relu6 = lambda v: torch.clamp(v, 0.0, 6.0)  # noqa: E731
+        z, zbn = self.q(conv2d_tf(x, p["conv1/kernel"], 2, "same")), "conv1_bn"
+        for i, (cin, cout, stride) in enumerate(MOBILENET_BLOCKS, start=1):
+            y = relu6(self.bnz(z, zbn, training))                                      # on load, not rounded
+            zd = self.q(conv2d_tf(y, p["conv_dw_%d/depthwise_kernel" % i], stride, "same", groups=cin))
+            t = self.q(relu6(self.bnz(zd, "conv_dw_%d_bn" % i, training)))             # GEMM operand: materialised
+            z, zbn = self.q(conv2d_tf(t, self.wq("conv_pw_%d/kernel" % i), 1, "valid")), "conv_pw_%d_bn" % i
+            if taps:
+                self.taps["block%d" % i] = relu6(self.bnz(z, zbn, False)) if not training else z
+        return self.q(relu6(self.bnz(z, zbn, training)))
+
+
+class OracleIRv2SPNetStored(_StoredMixin, OracleIRv2SPNet):
+    """InceptionResNetV2-SPNet with the engine's storage points (InceptionResNetV2SPNetEngine._backbone_fwd): every
+    conv output z and every conv+BN+ReLU output, pool, residual sum is a stored tensor."""
+
+    def __init__(self, weights, H, W, n_out=576, dtype=torch.float32, unbiased_moving_var=True, storage="bf16"):
+        OracleIRv2SPNet.__init__(self, weights, H, W, n_out, dtype, unbiased_moving_var)
+        self.storage = storage
+
+    def backbone(self, x, training, taps=False):
+        p = self.p
+        cnt = [4, 4]
+        first = [True]
+
+        def conv_bn(t, cout, k, s, pad, name=None):
+            if name is None:
+                name, bname = "conv2d_%d" % cnt[0], "batch_normalization_%d" % cnt[1]
+                cnt[0] += 1
+                cnt[1] += 1
+            else:
+                bname = name + "_bn"
+            w = p[name + "/kernel"] if first[0] else self.wq(name + "/kernel")  # the 3-channel first layer keeps fp32 weights
+            first[0] = False
+            z = self.q(conv2d_tf(t, w, s, pad))
+            return self.q(torch.relu(self.bnz(z, bname, training)))
+
+        def conv_bias(t, name):
+            return self.q(conv2d_tf(t, self.wq(name + "/kernel"), 1, "valid")), p[name + "/bias"]
+
+        def avgpool(t):
+            return self.q(F.avg_pool2d(t, 3, 1, padding=1, count_include_pad=False))
+
+        def residual(t, up, scale, relu):
+            u, bias = up
+            y = t + scale * (u + bias[None, :, None, None])
+            return self.q(torch.relu(y) if relu else y)
 
         w = _IRv2Walker(conv_bn, conv_bias, lambda t: F.max_pool2d(t, 3, 2), avgpool, lambda ts: torch.cat(ts, 1), residual)
         return w.run(x)

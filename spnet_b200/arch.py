@@ -164,3 +164,69 @@ def glorot_init(spec, seed=1):
         else:
             out[key] = np.zeros(shape, np.float32)
     return out
+
+
+# ---- Keras `base_model.layers` order (what `base_model.layers[:N].trainable = False` freezes, spnet/models.py:361-372)
+# Keras 2.1.3 sorts Model.layers by depth (distance to the output, largest first) and breaks ties by the order of a
+# depth-first walk from the output that follows each layer's inputs in call order (topology.Container.__init__).
+# For `add([main, residual])` the main branch is walked first, so a residual branch's layers sit next to the main
+# branch's layers of the same depth, main first. Weight-less layers are listed too: they count towards N.
+def _stem_layers():
+    return ["input_1", "conv2d_1", "average_pooling2d_1", "batch_normalization_1", "leaky_re_lu_1", "conv2d_2",
+            "batch_normalization_2", "leaky_re_lu_2", "conv2d_3", "batch_normalization_3", "average_pooling2d_2", "add_1",
+            "dropout_1"]
+
+
+def xception_keras_layers():
+    """The 144 layers of Xception-SPNet's base_model (paper/run_logs/log_DatasetA_*.txt:95) in Keras order."""
+    L = _stem_layers()
+    L += ["block1_conv1", "block1_conv1_bn", "block1_conv1_act", "block1_conv2", "block1_conv2_bn", "block1_conv2_act"]
+    nadd = 2
+    for n, blk in enumerate((2, 3, 4, 13)):
+        res = "conv2d_%d" % (4 + n)
+        res_bn = "batch_normalization_%d" % (4 + n)
+        if blk == 13:
+            for b in MIDDLE_BLOCKS:
+                for j in (1, 2, 3):
+                    L += ["block%d_sepconv%d_act" % (b, j), "block%d_sepconv%d" % (b, j), "block%d_sepconv%d_bn" % (b, j)]
+                L.append("add_%d" % nadd)
+                nadd += 1
+        if blk != 2:
+            L.append("block%d_sepconv1_act" % blk)
+        L += ["block%d_sepconv1" % blk, "block%d_sepconv1_bn" % blk, "block%d_sepconv2_act" % blk, "block%d_sepconv2" % blk,
+              "block%d_sepconv2_bn" % blk, res, "block%d_pool" % blk, res_bn, "add_%d" % nadd]
+        nadd += 1
+    L += ["block14_sepconv1", "block14_sepconv1_bn", "block14_sepconv1_act", "block14_sepconv2", "block14_sepconv2_bn",
+          "block14_sepconv2_act"]
+    assert len(L) == 144, len(L)
+    return L
+
+
+def mobilenet_keras_layers():
+    """1 Input + 12 stem layers + 81 MobileNet layers (conv1, conv1_bn, conv1_relu, 13 x 6)."""
+    L = _stem_layers() + ["conv1", "conv1_bn", "conv1_relu"]
+    for i in range(1, 14):
+        L += ["conv_dw_%d" % i, "conv_dw_%d_bn" % i, "conv_dw_%d_relu" % i, "conv_pw_%d" % i, "conv_pw_%d_bn" % i,
+              "conv_pw_%d_relu" % i]
+    assert len(L) == 94, len(L)
+    return L
+
+
+def frozen_layer_names(backbone, freeze_fac, spec):
+    """Names of the layers WITH WEIGHTS that `for i in range(int(num_layers * freeze_fac)): base_model.layers[i].trainable
+    = False` freezes (spnet/models.py:361-372). Returns (names, n_frozen_layers, n_layers)."""
+    if backbone == "InceptionResNetV2":
+        # 792 layers with 3-4-way concatenations: the order of the weight-carrying layers is the construction order
+        # (each branch is a chain), the cut is scaled from Keras layers to layers with weights
+        total = 792
+        nfreeze = int(total * freeze_fac)
+        names = []
+        for k, _, _, _ in spec:
+            n = k.split("/")[0]
+            if n != "FinalOutput" and n not in names:
+                names.append(n)
+        return names[:int(round(len(names) * nfreeze / float(total)))], nfreeze, total
+    layers = mobilenet_keras_layers() if backbone == "MobileNet" else xception_keras_layers()
+    nfreeze = int(len(layers) * freeze_fac)
+    with_weights = set(k.split("/")[0] for k, _, _, _ in spec)
+    return [n for n in layers[:nfreeze] if n in with_weights], nfreeze, len(layers)

@@ -68,6 +68,20 @@ class OneCycleScheduler(Callback):
             print("\nLearning rate =", lr)
 
 
+def _splitmix64(x):
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return x ^ (x >> 31)
+
+
+def _epoch_seed(seed, epoch):
+    """Per-epoch key of the device augmentation. The kernel keys every draw as seed + G*(frame+1) + ...; an ADDITIVE
+    per-epoch offset with the same constant made (epoch e, frame f) and (epoch e+1, frame f-1) share their draws, so
+    the epoch goes through a proper mix instead: splitmix64(seed ^ splitmix64(epoch))."""
+    return _splitmix64((seed & 0xFFFFFFFFFFFFFFFF) ^ _splitmix64(epoch))
+
+
 class ParallelCheckpointCallback(Callback):
     """Every save_every epochs: weights of the serial model -> dir/<filepath>, full model ->
     dir/spnet.model (spnet/callbacks.py:20-41). Rank 0 only under data parallelism."""
@@ -75,20 +89,24 @@ class ParallelCheckpointCallback(Callback):
     def __init__(self, model, filepath="weights.hdf5", save_every=1, dir="."):
         super().__init__()
         self.model_to_save = model
-        self.filepath = filepath
         self.save_every = save_every
         self.dir = dir
+        self.weights_path = dir + "/" + filepath        # spnet/callbacks.py:31-32
+        self.model_path = dir + "/" + "spnet.model"
 
     def on_epoch_end(self, epoch, logs=None):
         from . import multi_gpu
         if multi_gpu.world()[0] != 0:
             return
-        if epoch % self.save_every == 0:
-            utils.make_sure_path_exists(self.dir)
+        # epoch + 1 agrees with Keras' "Epoch 1/20" display: after the 5th, 10th, ... epoch for save_every = 5
+        if (1 == self.save_every) or ((0 == ((epoch + 1) % self.save_every)) and (epoch > 0)):
+            utils.make_sure_path_exists(os.path.dirname(self.weights_path) or ".")
+            # the model being trained right now (after unfreeze_model it is a new object), else the one given at set-up
             target = multi_gpu.get_serial_part(self.model if self.model is not None else self.model_to_save)
-            print("Saving checkpoint to", os.path.join(self.dir, os.path.basename(self.filepath)))
-            target.save_weights(os.path.join(self.dir, os.path.basename(self.filepath)))
-            target.save(os.path.join(self.dir, "spnet.model"))
+            print("Saving weights checkpoint to", self.weights_path)
+            target.save_weights(self.weights_path)
+            print("Saving entire model checkpoint to", self.model_path)
+            target.save(self.model_path)
 
 
 class MyProgressCallback(Callback):
@@ -110,8 +128,11 @@ class MyProgressCallback(Callback):
         self.rank0 = multi_gpu.world()[0] == 0
         if self.rank0:
             utils.make_sure_path_exists(self.log_dir)
-            with open(os.path.join(self.log_dir, "losses.dat"), "w") as f:
-                f.write("# epoch Train_total Val_total center size angle noobj class\n")
+            path = os.path.join(self.log_dir, "losses.dat")
+            if not getattr(self, "_header_written", False):  # a second fit() (after unfreeze_model) keeps the frozen-phase log
+                with open(path, "w") as f:
+                    f.write("# epoch Train_total Val_total center size angle noobj class\n")
+                self._header_written = True
 
     def on_epoch_end(self, epoch, logs=None):
         from . import models
@@ -192,7 +213,7 @@ class AugmentOnTheFly(Callback):
             return
         if self.on_device:
             from . import ops
-            ops.augment_on_the_fly(self.X_orig, self.X, self.seed + 0x9E3779B97F4A7C15 * (epoch + 1))
+            ops.augment_on_the_fly(self.X_orig, self.X, _epoch_seed(self.seed, epoch))
             return
         X = self.X
         X[...] = self.X_orig

@@ -10,7 +10,7 @@
 
 namespace {
 
-__global__ void bn_finalize_kernel(double* __restrict__ stats, double count, const float* __restrict__ gamma,
+__global__ void bn_finalize_kernel(long long* __restrict__ stats, double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum, int unbiased,
                                    float* __restrict__ a, float* __restrict__ b, float* __restrict__ save_mean,
                                    float* __restrict__ save_rstd, float* __restrict__ moving_mean,
@@ -19,11 +19,11 @@ __global__ void bn_finalize_kernel(double* __restrict__ stats, double count, con
     pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    const double mean = stats[c] / count;
-    double var = stats[C + c] / count - mean * mean;
+    const double mean = stat_get(stats, c) / count;
+    double var = stat_get(stats, C + c) / count - mean * mean;
     if (var < 0.0) var = 0.0;
-    stats[c] = 0.0;
-    stats[C + c] = 0.0;
+    stat_clear(stats, c);
+    stat_clear(stats, C + c);
     const float rstd = (float)(1.0 / sqrt(var + (double)eps));
     const float g = gamma ? gamma[c] : 1.0f;
     const float aa = g * rstd;
@@ -40,12 +40,17 @@ __global__ void bn_finalize_kernel(double* __restrict__ stats, double count, con
 
 __global__ void bn_inference_affine_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                            const float* __restrict__ mm, const float* __restrict__ mv, float eps,
-                                           float* __restrict__ a, float* __restrict__ b, int C) {
+                                           float* __restrict__ a, float* __restrict__ b, float* __restrict__ save_mean,
+                                           float* __restrict__ save_rstd, int C) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float aa = (gamma ? gamma[c] : 1.0f) / sqrtf(mv[c] + eps);
     a[c] = aa;
     b[c] = (beta ? beta[c] : 0.0f) - mm[c] * aa;
+    if (save_mean) {  // a BatchNorm that normalises with its moving statistics inside a TRAINING step: backward needs them
+        save_mean[c] = mm[c];
+        save_rstd[c] = 1.0f / sqrtf(mv[c] + eps);
+    }
 }
 
 // Channel-stationary mapping shared by the element-wise kernels below: a thread keeps one
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(512, 1) bn_bwd_reduce_kernel(T* __restrict__ g
                                                                const float* __restrict__ rstd,
                                                                const float* __restrict__ relu_a,
                                                                const float* __restrict__ relu_b, int act,
-                                                               double* __restrict__ stats, long long rows, int C,
+                                                               long long* __restrict__ stats, long long rows, int C,
                                                                int cvb, int krows) {
     constexpr int V = VecN<T>::N, NP = RawVec<T>::NP;
     pdl_trigger();
@@ -266,8 +271,8 @@ __global__ void __launch_bounds__(512, 1) bn_bwd_reduce_kernel(T* __restrict__ g
                 t1 += red[0][(j * cvb + cvl) * V + i];
                 t2 += red[1][(j * cvb + cvl) * V + i];
             }
-            atomicAdd(stats + c0 + i, (double)t1);
-            atomicAdd(stats + C + c0 + i, (double)t2);
+            stat_add(stats, c0 + i, (double)t1);
+            stat_add(stats, C + c0 + i, (double)t2);
         }
     }
 }
@@ -275,7 +280,7 @@ __global__ void __launch_bounds__(512, 1) bn_bwd_reduce_kernel(T* __restrict__ g
 // stats[c] += sum z, stats[C+c] += sum z^2 over the rows (batch statistics of a tensor whose producer
 // has no statistics epilogue)
 template <typename T>
-__global__ void __launch_bounds__(512, 1) colstats_kernel(const T* __restrict__ z, double* __restrict__ stats,
+__global__ void __launch_bounds__(512, 1) colstats_kernel(const T* __restrict__ z, long long* __restrict__ stats,
                                                           long long rows, int C, int cvb, int krows) {
     constexpr int V = VecN<T>::N, NP = RawVec<T>::NP;
     pdl_trigger();
@@ -326,26 +331,27 @@ __global__ void __launch_bounds__(512, 1) colstats_kernel(const T* __restrict__ 
                 t1 += red[0][(j * cvb + cvl) * V + i];
                 t2 += red[1][(j * cvb + cvl) * V + i];
             }
-            atomicAdd(stats + c0 + i, (double)t1);
-            atomicAdd(stats + C + c0 + i, (double)t2);
+            stat_add(stats, c0 + i, (double)t1);
+            stat_add(stats, C + c0 + i, (double)t2);
         }
     }
 }
 
-__global__ void bn_bwd_finalize_kernel(double* __restrict__ stats, double count, float* __restrict__ dgamma,
+__global__ void bn_bwd_finalize_kernel(long long* __restrict__ stats, double count, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ c1, float* __restrict__ c2,
                                        int C) {
     pdl_trigger();
     pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    const double sg = stats[c], sgx = stats[C + c];
-    stats[c] = 0.0;
-    stats[C + c] = 0.0;
+    const double sg = stat_get(stats, c), sgx = stat_get(stats, C + c);
+    stat_clear(stats, c);
+    stat_clear(stats, C + c);
     if (dgamma) dgamma[c] = (float)sgx;
     if (dbeta) dbeta[c] = (float)sg;
-    c1[c] = (float)(sg / count);
-    c2[c] = (float)(sgx / count);
+    // count <= 0: the BatchNorm normalised with fixed (moving) statistics in this step - no batch-statistics terms
+    c1[c] = count > 0.0 ? (float)(sg / count) : 0.f;
+    c2[c] = count > 0.0 ? (float)(sgx / count) : 0.f;
 }
 
 // out = a * (g - c1 - xhat*c2) = A*g + Bz*z + D with per-channel A = a, Bz = -a*rstd*c2,
@@ -449,7 +455,7 @@ int check_rc(const char* who, int dtype, long long rows, int C) {
 
 extern "C" {
 
-int spnet_bn_finalize(double* stats, long long count, const float* gamma, const float* beta, float eps,
+int spnet_bn_finalize(long long* stats, long long count, const float* gamma, const float* beta, float eps,
                       float momentum, int unbiased_moving_var, float* a, float* b, float* save_mean,
                       float* save_rstd, float* moving_mean, float* moving_var, int C, cudaStream_t stream) {
     SPNET_REQUIRE(stats && a && b && save_mean && save_rstd && C > 0 && count > 0, "bn_finalize: bad args");
@@ -462,11 +468,12 @@ int spnet_bn_finalize(double* stats, long long count, const float* gamma, const 
 }
 
 int spnet_bn_inference_affine(const float* gamma, const float* beta, const float* moving_mean,
-                              const float* moving_var, float eps, float* a, float* b, int C,
-                              cudaStream_t stream) {
+                              const float* moving_var, float eps, float* a, float* b, float* save_mean,
+                              float* save_rstd, int C, cudaStream_t stream) {
     SPNET_REQUIRE(moving_mean && moving_var && a && b && C > 0, "bn_inference_affine: bad args");
+    SPNET_REQUIRE((save_mean == nullptr) == (save_rstd == nullptr), "bn_inference_affine: save_mean and save_rstd go together");
     bn_inference_affine_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(gamma, beta, moving_mean, moving_var, eps, a,
-                                                                     b, C);
+                                                                     b, save_mean, save_rstd, C);
     return spnet_check_launch("bn_inference_affine");
 }
 
@@ -484,7 +491,7 @@ int spnet_bn_apply(const void* z, const float* a, const float* b, int act, const
 }
 
 int spnet_bn_bwd_reduce(void* g, const void* z, const float* save_mean, const float* save_rstd,
-                        const float* relu_a, const float* relu_b, int act, double* stats, int dtype,
+                        const float* relu_a, const float* relu_b, int act, long long* stats, int dtype,
                         long long rows, int C, cudaStream_t stream) {
     int rc = check_rc("bn_bwd_reduce", dtype, rows, C);
     if (rc) return rc;
@@ -506,7 +513,7 @@ int spnet_bn_bwd_reduce(void* g, const void* z, const float* save_mean, const fl
 }
 
 // stats[2*C] += (sum, sum of squares) per channel of z [rows, C]
-int spnet_colstats(const void* z, double* stats, int dtype, long long rows, int C, cudaStream_t stream) {
+int spnet_colstats(const void* z, long long* stats, int dtype, long long rows, int C, cudaStream_t stream) {
     int rc = check_rc("colstats", dtype, rows, C);
     if (rc) return rc;
     SPNET_REQUIRE(z && stats, "colstats: null pointer");
@@ -516,9 +523,9 @@ int spnet_colstats(const void* z, double* stats, int dtype, long long rows, int 
     return spnet_check_launch("colstats");
 }
 
-int spnet_bn_bwd_finalize(double* stats, long long count, float* dgamma, float* dbeta, float* c1, float* c2,
+int spnet_bn_bwd_finalize(long long* stats, long long count, float* dgamma, float* dbeta, float* c1, float* c2,
                           int C, cudaStream_t stream) {
-    SPNET_REQUIRE(stats && c1 && c2 && C > 0 && count > 0, "bn_bwd_finalize: bad args");
+    SPNET_REQUIRE(stats && c1 && c2 && C > 0 && count >= 0, "bn_bwd_finalize: bad args");
     cudaError_t e = spnet_launch_pdl(bn_bwd_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, stream, 1, stats,
                                      (double)count, dgamma, dbeta, c1, c2, C);
     SPNET_REQUIRE(e == cudaSuccess, "bn_bwd_finalize: launch: %s", cudaGetErrorString(e));

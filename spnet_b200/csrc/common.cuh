@@ -96,6 +96,30 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
     return v[0];
 }
 
+// ---- order-independent accumulators for cross-CTA sums (BatchNorm statistics, loss terms) -----
+// A sum that many CTAs contribute to must not depend on the order in which they arrive, or two runs of
+// the same step differ in the last bits and the network amplifies that (3e-5 at the MobileNet head).
+// Floating-point atomics are not associative; 64-bit integer atomics are. Every contribution is split
+// into two fixed-point limbs  v = (hi * 2^32 + lo) * 2^-56  (quantum 2^-56 = 1.4e-17, |v| < 2^39) and
+// added with integer atomics: exact for any fp32 partial of magnitude >= 2^-32, rounded down to the
+// quantum below that, and bit-identical for every arrival order. Entry i occupies words [2i, 2i+1] of
+// a zero-initialised int64 buffer; stat_get() reassembles the double.
+__device__ __forceinline__ void stat_add(long long* acc, long long i, double v) {
+    const double t = v * 16777216.0;  // units of 2^-24
+    const double fh = floor(t);
+    const long long hi = __double2ll_rd(t);
+    const unsigned long long lo = __double2ull_rz((t - fh) * 4294967296.0);  // [0, 2^32)
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(acc) + 2 * i;
+    atomicAdd(p, (unsigned long long)hi);
+    if (lo) atomicAdd(p + 1, lo);
+}
+__device__ __forceinline__ double stat_get(const long long* acc, long long i) {
+    const long long hi = acc[2 * i];
+    const unsigned long long lo = (unsigned long long)acc[2 * i + 1];
+    return ((double)hi + (double)lo * (1.0 / 4294967296.0)) * (1.0 / 16777216.0);
+}
+__device__ __forceinline__ void stat_clear(long long* acc, long long i) { acc[2 * i] = 0; acc[2 * i + 1] = 0; }
+
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------
 // The step is a chain of ~400 short kernels; with PDL (opt-in: SPNET_B200_PDL=1) a kernel's CTAs are
 // scheduled and run their prologue (barrier init, TMEM allocation, index math) while the previous

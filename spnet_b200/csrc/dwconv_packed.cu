@@ -274,9 +274,9 @@ __global__ void __launch_bounds__(512, 1)
 dw3x3_bwd_packed_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x,
                         const __grid_constant__ CUtensorMap tm_add, const float* __restrict__ k,
                         const float* __restrict__ in_a, const float* __restrict__ in_b,
-                        const float* __restrict__ bn_mean, const float* __restrict__ bn_rstd, double* __restrict__ stats,
-                        const T* __restrict__ add_strided, T* __restrict__ gin, float* __restrict__ dk, int B, int H,
-                        int W, int C, int TH, int TW, int tiles_h, int tiles_w, int S) {
+                        const float* __restrict__ bn_mean, const float* __restrict__ bn_rstd, long long* __restrict__ stats,
+                        const T* __restrict__ add_strided, T* __restrict__ gin, float* __restrict__ dk,
+                        long long* __restrict__ dk_acc, int B, int H, int W, int C, int TH, int TW, int tiles_h, int tiles_w, int S) {
     constexpr int NC = 2;
     constexpr uint32_t PB = PairOf<T>::bytes, PIX = 32 * PB;
     typedef typename PairOf<T>::raw raw_t;
@@ -456,15 +456,16 @@ dw3x3_bwd_packed_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_c
         float sum = 0.f;
         for (int w = 0; w < ncons; ++w) sum += red[((size_t)w * NQ + q) * CB + ch];
         if (q < 9) {
-            atomicAdd(dk + (size_t)(8 - q) * C + c, sum);  // un-flip the tap index
+            if (dk_acc) stat_add(dk_acc, (long long)(8 - q) * C + c, (double)sum);  // order-independent (run-to-run identical)
+            else atomicAdd(dk + (size_t)(8 - q) * C + c, sum);  // un-flip the tap index
         } else if (stats) {
             if (q == 9) {
-                atomicAdd(stats + c, (double)sum);  // sum g
+                stat_add(stats, c, (double)sum);  // sum g
             } else {
                 // sum g*xhat = rstd * (sum g*in - mean * sum g)
                 float sg = 0.f;
                 for (int w = 0; w < ncons; ++w) sg += red[((size_t)w * NQ + 9) * CB + ch];
-                atomicAdd(stats + (size_t)C + c, (double)bn_rstd[c] * ((double)sum - (double)bn_mean[c] * (double)sg));
+                stat_add(stats, (long long)C + c, (double)bn_rstd[c] * ((double)sum - (double)bn_mean[c] * (double)sg));
             }
         }
     }
@@ -587,8 +588,8 @@ int launch_fwd(const void* in, const float* k, const float* a, const float* b, i
 
 template <typename T, bool AF, int RL, int EPI>
 int launch_bwd_inst(const CUtensorMap& tg, const CUtensorMap& tx, const CUtensorMap& ta, const float* k, const float* a,
-                    const float* b, const float* mean, const float* rstd, double* stats, const T* sadd, T* gin,
-                    float* dk, int B, int H, int W, int C, const Tiling& t, cudaStream_t stream) {
+                    const float* b, const float* mean, const float* rstd, long long* stats, const T* sadd, T* gin,
+                    float* dk, long long* dk_acc, int B, int H, int W, int C, const Tiling& t, cudaStream_t stream) {
     auto kern = dw3x3_bwd_packed_kernel<T, AF, RL, EPI>;
     static bool configured = false;
     if (!configured) {
@@ -600,7 +601,7 @@ int launch_bwd_inst(const CUtensorMap& tg, const CUtensorMap& tx, const CUtensor
         configured = true;
     }
     cudaError_t e = spnet_launch_pdl(kern, dim3(t.grid_x, t.chunks), dim3(t.threads), t.smem, stream, 1, tg, tx, ta, k, a,
-                                     b, mean, rstd, stats, sadd, gin, dk, B, H, W, C, t.TH, t.TW, t.tiles_h, t.tiles_w,
+                                     b, mean, rstd, stats, sadd, gin, dk, dk_acc, B, H, W, C, t.TH, t.TW, t.tiles_h, t.tiles_w,
                                      t.S);
     SPNET_REQUIRE(e == cudaSuccess, "dwconv3x3_bwd_fused: launch: %s", cudaGetErrorString(e));
     return spnet_check_launch("dw3x3_bwd_fused");
@@ -608,8 +609,8 @@ int launch_bwd_inst(const CUtensorMap& tg, const CUtensorMap& tx, const CUtensor
 
 template <typename T>
 int launch_bwd(const void* gout, const void* in, const float* k, const float* a, const float* b, int relu,
-               const float* mean, const float* rstd, double* stats, const void* add_src, const void* add_strided,
-               void* gin, float* dk, int dtype, int B, int H, int W, int C, cudaStream_t stream) {
+               const float* mean, const float* rstd, long long* stats, const void* add_src, const void* add_strided,
+               void* gin, float* dk, long long* dk_acc, int dtype, int B, int H, int W, int C, cudaStream_t stream) {
     const int epi = add_src ? 1 : (add_strided ? 2 : 0);
     Tiling t = pick_tiling(epi == 1 ? 2 : 1, dtype, B, H, W, C);
     SPNET_REQUIRE(t.TH > 0, "dwconv3x3_bwd: no tile fits shared memory");
@@ -626,9 +627,9 @@ int launch_bwd(const void* gout, const void* in, const float* k, const float* a,
     T* y = reinterpret_cast<T*>(gin);
 #define DWB(AF, RL)                                                                                                    \
     do {                                                                                                               \
-        if (epi == 1) return launch_bwd_inst<T, AF, RL, 1>(tg, tx, ta, k, a, b, mean, rstd, stats, sadd, y, dk, B, H, W, C, t, stream); \
-        if (epi == 2) return launch_bwd_inst<T, AF, RL, 2>(tg, tx, ta, k, a, b, mean, rstd, stats, sadd, y, dk, B, H, W, C, t, stream); \
-        return launch_bwd_inst<T, AF, RL, 0>(tg, tx, ta, k, a, b, mean, rstd, stats, sadd, y, dk, B, H, W, C, t, stream);   \
+        if (epi == 1) return launch_bwd_inst<T, AF, RL, 1>(tg, tx, ta, k, a, b, mean, rstd, stats, sadd, y, dk, dk_acc, B, H, W, C, t, stream); \
+        if (epi == 2) return launch_bwd_inst<T, AF, RL, 2>(tg, tx, ta, k, a, b, mean, rstd, stats, sadd, y, dk, dk_acc, B, H, W, C, t, stream); \
+        return launch_bwd_inst<T, AF, RL, 0>(tg, tx, ta, k, a, b, mean, rstd, stats, sadd, y, dk, dk_acc, B, H, W, C, t, stream);   \
     } while (0)
     if (a && relu == 2) DWB(true, 2);
     if (a && relu) DWB(true, 1);
@@ -664,19 +665,21 @@ int spnet_dwconv3x3_fwd(const void* in, const float* k, const float* in_a, const
 // Fused backward (see dw3x3_bwd_packed_kernel): gin, dk (+=) and optional BatchNorm-backward sums.
 //   in          : the tensor the forward depthwise read (raw), transformed on load by
 //                 act(v) = relu?(in_a*v+in_b)
-//   stats       : nullable fp64 [2*C]; += (sum gin, sum gin*xhat) with xhat = (in-bn_mean)*bn_rstd
+//   stats       : nullable accumulators, 2*C entries; += (sum gin, sum gin*xhat) with xhat = (in-bn_mean)*bn_rstd
+//   dk_acc      : nullable accumulators, 9*C entries: the kernel-gradient partial sums of the CTAs go there (order-
+//                 independent, spnet_acc_to_f32 adds them into dk) instead of fp32 atomics on dk
 //   add_src / add_strided : optional residual-path gradients added to gin (at most one of them)
 int spnet_dwconv3x3_bwd_fused(const void* gout, const void* in, const float* k, const float* in_a, const float* in_b,
-                              int relu, const float* bn_mean, const float* bn_rstd, double* stats, const void* add_src,
-                              const void* add_strided, void* gin, float* dk, int dtype, int B, int H, int W, int C,
-                              cudaStream_t stream) {
+                              int relu, const float* bn_mean, const float* bn_rstd, long long* stats, const void* add_src,
+                              const void* add_strided, void* gin, float* dk, long long* dk_acc, int dtype, int B, int H,
+                              int W, int C, cudaStream_t stream) {
     int rc = check_args("dwconv3x3_bwd_fused", gout, gin, dtype, B, H, W, C);
     if (rc) return rc;
     SPNET_REQUIRE(in && k && dk && ((in_a == nullptr) == (in_b == nullptr)) && relu >= 0 && relu <= 2, "dwconv3x3_bwd_fused: bad pointers or relu code");
     SPNET_REQUIRE(!stats || (bn_mean && bn_rstd), "dwconv3x3_bwd_fused: stats need bn_mean / bn_rstd");
     SPNET_REQUIRE(!(add_src && add_strided), "dwconv3x3_bwd_fused: add_src and add_strided are exclusive");
     SPNET_DISPATCH_DTYPE(dtype, return launch_bwd<T>(gout, in, k, in_a, in_b, relu, bn_mean, bn_rstd, stats, add_src,
-                                                     add_strided, gin, dk, dtype, B, H, W, C, stream));
+                                                     add_strided, gin, dk, dk_acc, dtype, B, H, W, C, stream));
 }
 
 }  // extern "C"

@@ -11,17 +11,17 @@ namespace {
 
 constexpr int TM = 64, TN = 64, TK = 16, PAD = 4;
 
-enum { OUT_T = 0, OUT_F32 = 1, OUT_ATOMIC_F32 = 2 };
+enum { OUT_T = 0, OUT_F32 = 1, OUT_ATOMIC_F32 = 2, OUT_SLAB_F32 = 3 };
 
 template <typename T>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A, long long sa_r, long long sa_k,
                                                         const T* __restrict__ B, long long sb_r, long long sb_k,
                                                         void* __restrict__ D, long long ldd, int out_mode, int M,
                                                         int N, int K, int k_per_split,
-                                                        double* __restrict__ colstats) {
+                                                        long long* __restrict__ colstats) {
     __shared__ float As[TK][TM + PAD];
     __shared__ float Bs[TK][TN + PAD];
-    __shared__ float cs[2][TN];
+    __shared__ float cs[16][2][TN];  // per thread-row partial column sums, added in row order (run-to-run identical)
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
     const int kbeg = blockIdx.z * k_per_split;
@@ -63,10 +63,6 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
         __syncthreads();
     }
 
-    if (colstats) {
-        if (tid < TN) { cs[0][tid] = 0.f; cs[1][tid] = 0.f; }
-        __syncthreads();
-    }
     float csum[4] = {0.f, 0.f, 0.f, 0.f}, csq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -83,6 +79,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
                 v = round_to<T>(v);
             } else if (out_mode == OUT_F32) {
                 reinterpret_cast<float*>(D)[(long long)r * ldd + c] = v;
+            } else if (out_mode == OUT_SLAB_F32) {  // split z keeps its partial in its own slab (fixed-order split-K)
+                reinterpret_cast<float*>(D)[((long long)blockIdx.z * ((M + 255) / 256 * 256) + r) * ldd + c] = v;
             } else {
                 atomicAdd(reinterpret_cast<float*>(D) + (long long)r * ldd + c, v);
             }
@@ -93,13 +91,15 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
     if (colstats) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            atomicAdd(&cs[0][tx * 4 + j], csum[j]);
-            atomicAdd(&cs[1][tx * 4 + j], csq[j]);
+            cs[ty][0][tx * 4 + j] = csum[j];
+            cs[ty][1][tx * 4 + j] = csq[j];
         }
         __syncthreads();
         if (tid < TN && n0 + tid < N) {
-            atomicAdd(colstats + n0 + tid, (double)cs[0][tid]);
-            atomicAdd(colstats + N + n0 + tid, (double)cs[1][tid]);
+            float t0 = 0.f, t1 = 0.f;
+            for (int r_ = 0; r_ < 16; ++r_) { t0 += cs[r_][0][tid]; t1 += cs[r_][1][tid]; }
+            stat_add(colstats, n0 + tid, (double)t0);
+            stat_add(colstats, N + n0 + tid, (double)t1);
         }
     }
 }
@@ -111,11 +111,11 @@ extern "C" {
 // dtype: element type of A and B (0 fp32, 1 bf16). out_mode 0 stores D in that same type.
 int spnet_gemm_simt(const void* A, long long sa_r, long long sa_k, const void* B, long long sb_r, long long sb_k,
                     void* D, long long ldd, int dtype, int out_mode, int M, int N, int K, int splits,
-                    double* colstats, cudaStream_t stream) {
+                    long long* colstats, cudaStream_t stream) {
     SPNET_REQUIRE(A && B && D, "gemm_simt: null pointer");
     SPNET_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_simt: bad shape %d %d %d", M, N, K);
-    SPNET_REQUIRE(out_mode >= 0 && out_mode <= 2, "gemm_simt: bad out_mode");
-    SPNET_REQUIRE(splits <= 1 || out_mode == OUT_ATOMIC_F32, "gemm_simt: split-K needs out_mode 2");
+    SPNET_REQUIRE(out_mode >= 0 && out_mode <= 3, "gemm_simt: bad out_mode");
+    SPNET_REQUIRE(splits <= 1 || out_mode == OUT_ATOMIC_F32 || out_mode == OUT_SLAB_F32, "gemm_simt: split-K needs out_mode 2 or 3");
     SPNET_REQUIRE(!(colstats && splits > 1), "gemm_simt: column statistics are not defined for split-K partials");
     if (splits < 1) splits = 1;
     int kps = ceil_div(ceil_div(K, splits), TK) * TK;

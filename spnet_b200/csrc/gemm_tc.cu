@@ -33,13 +33,14 @@ constexpr int kEpiWarps = 8;    // two per TMEM lane quadrant, each draining hal
 // the issue path ran on the uniform datapath.)
 constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA warp, MMA warp, epilogue warps
 
-enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_ATOMIC_F32 = 2 };
+enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_ATOMIC_F32 = 2, OUT_SLAB_F32 = 3 };
 
 struct GemmEpi {
     void* out;
     long long ldc;
     int mode;
-    double* colstats;  // [2*N] (sum, sumsq) or nullptr
+    int slab_rows;     // OUT_SLAB_F32: split s stores its fp32 partial at row offset s * slab_rows of D
+    long long* colstats;  // order-independent accumulators (common.cuh stat_add), 2*N entries (sum, sumsq), or nullptr
 };
 
 // Implicit-GEMM convolution on the same kernel (template parameter CONV). The activation operand is a 4-D
@@ -367,15 +368,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int chalf = (warp - 2) >> 2;      // which half of the column chunks this warp drains
         const int et = (warp - 2) * 32 + lane;  // 0..255 within the epilogue group
         // BatchNorm column statistics: thread `et` owns column `et` of the tile and keeps fp64 running
-        // sums across the units this CTA walks; they go to global memory (fp64 atomics) only when the
+        // sums across the units this CTA walks; they go to global memory (fixed-point integer atomics) only when the
         // n-tile changes or the CTA is done. Per-unit atomics to the same few addresses from every CTA
         // were 36 % of a skinny GEMM (744000 x 128 x 128: 125 us -> 80 us without them).
         double acc_s = 0.0, acc_q = 0.0;
         int acc_n0 = -1;
         auto flush_stats = [&]() {
             if (acc_n0 >= 0 && et < BN && acc_n0 + et < N) {
-                atomicAdd(epi.colstats + (acc_n0 + et), acc_s);
-                atomicAdd(epi.colstats + N + (acc_n0 + et), acc_q);
+                stat_add(epi.colstats, acc_n0 + et, acc_s);
+                stat_add(epi.colstats, N + (acc_n0 + et), acc_q);
             }
             acc_s = 0.0;
             acc_q = 0.0;
@@ -390,6 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             int drow = m0 + q * 32, dx = 0, dy = 0, dimg = 0;
             uint32_t rowmask = 0xffffffffu;  // CONV 1: rows of this warp's box that are real output pixels
             if (CONV == 2) drow += ((unit / (tiles_n * tiles_m)) % cg.ntaps) * M;
+            if (CONV == 0 && epi.mode == OUT_SLAB_F32) drow += (unit / (tiles_n * tiles_m)) * epi.slab_rows;
             if (CONV == 1) {
                 const int t2 = mt / cg.tiles_w, lwh = cg.lw + cg.lh;
                 const int x0 = (mt - t2 * cg.tiles_w) << cg.lw, y0 = (t2 % cg.tiles_h) << cg.lh;
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                             __syncwarp();
                             if (e_leader) {
-                                if (epi.mode == OUT_F32)
+                                if (epi.mode != OUT_ATOMIC_F32)
                                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmD),
                                                  "r"(stg), "r"(col0 + 16 * h), "r"(drow)
                                                  : "memory");
@@ -638,20 +640,23 @@ extern "C" {
 
 // D[M,N] (op)= A[M,K] * B[K,N], bf16 operands, fp32 accumulation in TMEM.
 //   a_mn / b_mn : 0 = K-major (ptr[r*ld + k]), 1 = MN-major (ptr[k*ld + r])
-//   out_mode    : 0 store bf16, 1 store fp32, 2 atomic-add fp32 (required when splits > 1)
+//   out_mode    : 0 store bf16, 1 store fp32, 2 reduce-add fp32 (split-K, order of the adds not fixed), 3 fp32
+//                 SLABS (split-K with a fixed summation order): split s stores its partial product at rows
+//                 [s * R, s * R + M) of D, R = M rounded up to 256; the effective number of splits is
+//                 ceil(kb / ceil(kb / splits)) with kb = ceil(K / 64); spnet_slab_reduce adds the slabs in order
 //   colstats    : nullable fp64 [2*N]; per-column sum and sum of squares of the values as
 //                 stored (after bf16 rounding in mode 0) are atomically added
 //   Requirements: pointers 16-byte aligned, lda/ldb multiples of 8, N % 8 == 0 (bf16 out)
 //                 or N % 4 == 0 (fp32 store).
 int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* D,
-                    long long ldd, int out_mode, int M, int N, int K, int splits, double* colstats,
+                    long long ldd, int out_mode, int M, int N, int K, int splits, long long* colstats,
                     cudaStream_t stream) {
     SPNET_REQUIRE(A && B && D, "gemm_bf16: null pointer");
     SPNET_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16: bad shape %d %d %d", M, N, K);
     SPNET_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm_bf16: lda/ldb must be multiples of 8 elements");
     SPNET_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)D % 16 == 0),
                   "gemm_bf16: pointers must be 16-byte aligned");
-    SPNET_REQUIRE(out_mode >= 0 && out_mode <= 2, "gemm_bf16: bad out_mode %d", out_mode);
+    SPNET_REQUIRE(out_mode >= 0 && out_mode <= 3, "gemm_bf16: bad out_mode %d", out_mode);
     SPNET_REQUIRE(out_mode != OUT_BF16 || (N % 8 == 0 && ldd % 8 == 0), "gemm_bf16: bf16 output needs N, ldd %% 8 == 0");
     SPNET_REQUIRE(out_mode == OUT_BF16 || ldd % 4 == 0, "gemm_bf16: fp32 output needs ldd %% 4 == 0");
     const bool wide_ = N >= 512 && getenv("SPNET_GEMM_FORCE_NARROW") == nullptr, pair_ = wide_ && M > BM && getenv("SPNET_B200_NO_CLUSTER") == nullptr;
@@ -669,7 +674,16 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
             splits = (int)(sp < 1 ? 1 : sp);
         }
     }
-    SPNET_REQUIRE(splits <= 1 || out_mode == OUT_ATOMIC_F32, "gemm_bf16: split-K needs out_mode 2");
+    SPNET_REQUIRE(splits <= 1 || out_mode == OUT_ATOMIC_F32 || out_mode == OUT_SLAB_F32, "gemm_bf16: split-K needs out_mode 2 or 3");
+    const int slab_rows = (M + 255) / 256 * 256;
+    long long out_rows = M;
+    if (out_mode == OUT_SLAB_F32) {
+        const int kb = (K + BK - 1) / BK;
+        int sp = splits < 1 ? 1 : (splits > kb ? kb : splits);
+        const int kbps = (kb + sp - 1) / sp;
+        sp = (kb + kbps - 1) / kbps;
+        out_rows = (long long)sp * slab_rows;
+    }
     SPNET_REQUIRE(!(colstats && splits > 1), "gemm_bf16: column statistics are not defined for split-K partials");
     // 128x256 tiles when N is wide: one A tile then feeds 256 output columns, which cuts the
     // L2->SM operand traffic per FLOP by a third (the 128x128 kernel is L2-bandwidth bound).
@@ -685,14 +699,14 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
     {
         PFN_cuTensorMapEncodeTiled enc = spnet_get_tensormap_encoder();
         const bool ob = out_mode == OUT_BF16;
-        cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M}, strides[1] = {(cuuint64_t)ldd * (ob ? 2 : 4)};
+        cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)out_rows}, strides[1] = {(cuuint64_t)ldd * (ob ? 2 : 4)};
         cuuint32_t box[2] = {ob ? 32u : 16u, 32u}, estr[2] = {1, 1};
         CUresult r = enc(&td, ob ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, D, dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SPNET_REQUIRE(r == CUDA_SUCCESS, "gemm_bf16: cuTensorMapEncodeTiled (output) failed (%d) M=%d N=%d ldd=%lld", (int)r, M, N, ldd);
     }
-    GemmEpi epi = {D, ldd, out_mode, colstats};
+    GemmEpi epi = {D, ldd, out_mode, slab_rows, colstats};
 #define SPNET_GEMM_DISPATCH(BN_, CL_)                                                                    \
     do {                                                                                                 \
         if (a_mn) {                                                                                      \
@@ -754,7 +768,7 @@ int make_pixel_map(CUtensorMap* map, const void* ptr, int NB, int H, int W, int 
 // Wt is the Keras kernel [KH, KW, Cin, Cout]; c_in / c_out are the channel counts of `in` / `out`.
 int conv_tc_fwd_like(bool dgrad, const void* in, long long ld_in, int NB, int IH, int IW, int c_in, const void* Wt,
                      int Cin, int Cout, void* out, long long ld_out, int OH, int OW, int c_out, int KH, int KW, int pt,
-                     int pl, double* colstats, cudaStream_t stream) {
+                     int pl, long long* colstats, cudaStream_t stream) {
     ConvGeom cg = {};
     pick_pixel_box(7, OW, OH, NB, &cg.lw, &cg.lh);
     const int ln = 7 - cg.lw - cg.lh;
@@ -786,7 +800,7 @@ int conv_tc_fwd_like(bool dgrad, const void* in, long long ld_in, int NB, int IH
                             CU_TENSOR_MAP_L2_PROMOTION_NONE);
         if (rc) return rc;
     }
-    GemmEpi epi = {out, ld_out, OUT_BF16, colstats};
+    GemmEpi epi = {out, ld_out, OUT_BF16, 0, colstats};
     const int M = (int)(tiles_m * BM);
     if (!dgrad) {
         if (bn == 64) return launch_gemm<64, false, true, 1, 1>(ta, tb, td, epi, M, N, K, 1, stream, cg, (int)tiles_m);
@@ -811,7 +825,7 @@ extern "C" {
 // (bottom / right padding is whatever OH / OW imply), bf16 in / out, fp32 accumulation; optional fused
 // per-channel sum / sum of squares of Y as stored (fp64 [2*Cout], atomically added).
 int spnet_conv_tc_fwd(const void* X, long long ldx, int NB, int H, int W, int Cin, const void* Wt, void* Y, long long ldy,
-                      int OH, int OW, int Cout, int KH, int KW, int pt, int pl, double* colstats, cudaStream_t stream) {
+                      int OH, int OW, int Cout, int KH, int KW, int pt, int pl, long long* colstats, cudaStream_t stream) {
     SPNET_CONV_TC_CHECKS(X, ldx, Wt, Y, ldy, Cin, Cout);
     SPNET_REQUIRE(NB > 0 && OH > 0 && OW > 0 && KH > 0 && KW > 0, "conv_tc_fwd: bad shape");
     return conv_tc_fwd_like(false, X, ldx, NB, H, W, Cin, Wt, Cin, Cout, Y, ldy, OH, OW, Cout, KH, KW, pt, pl, colstats,
@@ -867,7 +881,7 @@ int spnet_conv_tc_wgrad(const void* X, long long ldx, int NB, int H, int W, int 
     long long sp = tiles >= 148 ? 1 : 148 / tiles;
     if (sp > pixel_blocks / 4) sp = pixel_blocks / 4;
     const int splits = (int)(sp < 1 ? 1 : sp);
-    GemmEpi epi = {dW, N, OUT_ATOMIC_F32, nullptr};
+    GemmEpi epi = {dW, N, OUT_ATOMIC_F32, 0, nullptr};
     if (bn == 64) return launch_gemm<64, true, true, 1, 2>(ta, tb, td, epi, M, N, K, splits, stream, cg, 0);
     return launch_gemm<128, true, true, 1, 2>(ta, tb, td, epi, M, N, K, splits, stream, cg, 0);
 }

@@ -28,7 +28,12 @@ __global__ void __launch_bounds__(256) adam_keras_kernel(float* __restrict__ p, 
                                                          long long n, long long n_l2, float l2,
                                                          const float* __restrict__ lr_t_ptr, float beta1,
                                                          float beta2, float eps, float grad_scale,
-                                                         bf16* __restrict__ p_bf16) {
+                                                         bf16* __restrict__ p_bf16,
+                                                         const unsigned char* __restrict__ frozen8,
+                                                         const bf16* __restrict__ g_bf16) {
+    // frozen8 (nullable): one byte per 8 parameters (every tensor is padded to 8), non-zero = the tensor is not
+    // trainable (layer.trainable = False, spnet/models.py:361-372): no update, no L2 pull, moments untouched.
+    // g_bf16 (nullable): the gradients come from this bf16 buffer (data-parallel all-reduce in bf16) instead of g.
     const float lr_t = *lr_t_ptr;
     const float l2x2 = 2.0f * l2;
     const long long nv = n >> 2;  // float4 vectors
@@ -39,10 +44,16 @@ __global__ void __launch_bounds__(256) adam_keras_kernel(float* __restrict__ p, 
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const long long i = i0 + u * stride;
-            ok[u] = i < nv;
+            ok[u] = i < nv && !(frozen8 && frozen8[i >> 1]);
             if (ok[u]) {
                 pv[u] = reinterpret_cast<const float4*>(p)[i];
-                gv[u] = __ldcs(reinterpret_cast<const float4*>(g) + i);  // gradients are dead after this read
+                if (g_bf16) {
+                    const uint2 w = __ldcs(reinterpret_cast<const uint2*>(g_bf16) + i);
+                    gv[u] = make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u),
+                                        __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xffff0000u));
+                } else {
+                    gv[u] = __ldcs(reinterpret_cast<const float4*>(g) + i);  // gradients are dead after this read
+                }
                 mv[u] = reinterpret_cast<const float4*>(m)[i];
                 vv[u] = reinterpret_cast<const float4*>(v)[i];
             }
@@ -65,15 +76,16 @@ __global__ void __launch_bounds__(256) adam_keras_kernel(float* __restrict__ p, 
     }
     // tail (n not a multiple of 4: never the case for the engine's padded buffers)
     for (long long i = 4 * nv + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (frozen8 && frozen8[i >> 3]) continue;
         float pi = p[i], mi = m[i], vi = v[i];
-        adam_one(pi, g[i], mi, vi, i < n_l2, l2x2, lr_t, beta1, beta2, eps, grad_scale);
+        adam_one(pi, g_bf16 ? __bfloat162float(g_bf16[i]) : g[i], mi, vi, i < n_l2, l2x2, lr_t, beta1, beta2, eps, grad_scale);
         p[i] = pi; m[i] = mi; v[i] = vi;
         if (p_bf16) p_bf16[i] = __float2bfloat16_rn(pi);
     }
 }
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ p, long long n, float scale,
-                                                    float* __restrict__ out) {
+                                                    long long* __restrict__ out) {
     float s = 0.f;
     const long long nv = n >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
@@ -90,8 +102,37 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ p,
     if (threadIdx.x == 0) {
         float t = 0.f;
         for (int w = 0; w < 8; ++w) t += red[w];
-        atomicAdd(out, t * scale);
+        stat_add(out, 0, (double)t * (double)scale);  // order-independent across CTAs (common.cuh)
     }
+}
+
+// out[i] (+)= value of accumulator i (common.cuh stat_get); optionally clears the accumulators for the next step
+__global__ void acc_to_f32_kernel(long long* __restrict__ acc, float* __restrict__ out, long long n, int accumulate, int clear) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = (float)stat_get(acc, i);
+    out[i] = accumulate ? out[i] + v : v;
+    if (clear) stat_clear(acc, i);
+}
+
+// out[r, c] = (accumulate ? out[r, c] : 0) + bias[c] + slab_0[r, c] + slab_1[r, c] + ... (that order): the second half
+// of a split-K GEMM whose result must not depend on which split finished first (spnet_gemm_bf16 out_mode 3)
+__global__ void __launch_bounds__(256) slab_reduce_kernel(const float* __restrict__ slabs, int nslabs, long long slab_stride,
+                                                          long long lds, const float* __restrict__ bias, float* __restrict__ out,
+                                                          long long ldo, int rows, int cols4, int accumulate) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)rows * cols4) return;
+    const int r = (int)(i / cols4), c = (int)(i % cols4) * 4;
+    float4 a = accumulate ? *reinterpret_cast<const float4*>(out + r * ldo + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + c);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    for (int s = 0; s < nslabs; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(slabs + s * slab_stride + r * lds + c);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + r * ldo + c) = a;
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
@@ -131,17 +172,19 @@ extern "C" {
 
 int spnet_adam_keras_step(float* p, const float* g, float* m, float* v, long long n, long long n_l2, float l2,
                           const float* lr_t_dev, float beta1, float beta2, float eps, float grad_scale,
-                          void* p_bf16, cudaStream_t stream) {
-    SPNET_REQUIRE(p && g && m && v && lr_t_dev && n > 0 && n_l2 >= 0 && n_l2 <= n, "adam_keras_step: bad args");
-    SPNET_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0 && ((uintptr_t)p_bf16 & 7) == 0,
+                          void* p_bf16, const unsigned char* frozen8, const void* g_bf16, cudaStream_t stream) {
+    SPNET_REQUIRE(p && (g || g_bf16) && m && v && lr_t_dev && n > 0 && n_l2 >= 0 && n_l2 <= n, "adam_keras_step: bad args");
+    SPNET_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0 && ((uintptr_t)p_bf16 & 7) == 0 &&
+                      ((uintptr_t)g_bf16 & 7) == 0,
                   "adam_keras_step: buffers must be 16-byte aligned");
     adam_keras_kernel<<<grid_for(n), 256, 0, stream>>>(p, g, m, v, n, n_l2, l2, lr_t_dev, beta1, beta2, eps,
-                                                      grad_scale, reinterpret_cast<bf16*>(p_bf16));
+                                                      grad_scale, reinterpret_cast<bf16*>(p_bf16), frozen8,
+                                                      reinterpret_cast<const bf16*>(g_bf16));
     return spnet_check_launch("adam_keras_step");
 }
 
 // *out += scale * sum(p^2)
-int spnet_sumsq(const float* p, long long n, float scale, float* out, cudaStream_t stream) {
+int spnet_sumsq(const float* p, long long n, float scale, long long* out, cudaStream_t stream) {
     SPNET_REQUIRE(p && out && n > 0 && ((uintptr_t)p & 15) == 0, "sumsq: bad args (p must be 16-byte aligned)");
     sumsq_kernel<<<grid_for(n), 256, 0, stream>>>(p, n, scale, out);
     return spnet_check_launch("sumsq");
@@ -167,6 +210,24 @@ int spnet_colsum(const float* g, float* out, int rows, int cols, cudaStream_t st
     SPNET_REQUIRE(g && out && rows > 0 && cols > 0, "colsum: bad args");
     colsum_kernel<<<ceil_div(cols, 128), 128, 0, stream>>>(g, out, rows, cols);
     return spnet_check_launch("colsum");
+}
+
+
+int spnet_acc_to_f32(long long* acc, float* out, long long n, int accumulate, int clear, cudaStream_t stream) {
+    SPNET_REQUIRE(acc && out && n > 0, "acc_to_f32: bad args");
+    acc_to_f32_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(acc, out, n, accumulate, clear);
+    return spnet_check_launch("acc_to_f32");
+}
+
+int spnet_slab_reduce(const float* slabs, int nslabs, long long slab_stride, long long lds, const float* bias, float* out,
+                      long long ldo, int rows, int cols, int accumulate, cudaStream_t stream) {
+    SPNET_REQUIRE(slabs && out && nslabs > 0 && rows > 0 && cols > 0, "slab_reduce: bad args");
+    SPNET_REQUIRE(cols % 4 == 0 && lds % 4 == 0 && ldo % 4 == 0 && slab_stride % 4 == 0, "slab_reduce: cols / strides must be multiples of 4");
+    SPNET_REQUIRE(((uintptr_t)slabs % 16 == 0) && ((uintptr_t)out % 16 == 0) && (!bias || (uintptr_t)bias % 16 == 0),
+                  "slab_reduce: pointers must be 16-byte aligned");
+    slab_reduce_kernel<<<ceil_div((long long)rows * (cols / 4), 256), 256, 0, stream>>>(slabs, nslabs, slab_stride, lds, bias, out,
+                                                                                      ldo, rows, cols / 4, accumulate);
+    return spnet_check_launch("slab_reduce");
 }
 
 }  // extern "C"

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_kernel(const TI* __restr
                                                                const float* __restrict__ in_a,
                                                                const float* __restrict__ in_b, int act,
                                                                TO* __restrict__ out, TO* __restrict__ skip,
-                                                               double* __restrict__ stats,
+                                                               long long* __restrict__ stats,
                                                                const TO* __restrict__ mask_z,
                                                                const float* __restrict__ mask_a,
                                                                const float* __restrict__ mask_b, int B, int H, int W,
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_kernel(const TI* __restr
     __shared__ float sab[2 * CIN + 2 * COUT];
     __shared__ TO s_out[TH * TW * COUT];
     __shared__ TO s_skip[MODE == 1 ? TH * TW : 1];
-    __shared__ float sred[2 * COUT];
+    __shared__ float sred[(kThreads / 32) * 2 * COUT];  // per-warp partials, summed in warp order (run-to-run identical)
     for (int i = threadIdx.x; i < NW; i += kThreads) {
         const int t = i / (CIN * COUT), rem = i % (CIN * COUT);
         const int cin_here = rem / COUT, cout_here = rem % COUT;
@@ -141,7 +141,6 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_kernel(const TI* __restr
         sab[2 * CIN + threadIdx.x] = mask_z ? mask_a[threadIdx.x] : 1.f;
         sab[2 * CIN + COUT + threadIdx.x] = mask_z ? mask_b[threadIdx.x] : 0.f;
     }
-    if (threadIdx.x < 2 * COUT) sred[threadIdx.x] = 0.f;
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     float ssum[COUT] = {0.f, 0.f, 0.f}, ssq[COUT] = {0.f, 0.f, 0.f};
     const int n_tiles = B * tiles_h * tiles_w;
@@ -221,10 +220,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_kernel(const TI* __restr
 #pragma unroll
         for (int co = 0; co < COUT; ++co) {
             const float s = warp_sum(ssum[co]), q = warp_sum(ssq[co]);
-            if ((threadIdx.x & 31) == 0) { atomicAdd(&sred[co], s); atomicAdd(&sred[COUT + co], q); }
+            if ((threadIdx.x & 31) == 0) {
+                sred[(threadIdx.x >> 5) * 2 * COUT + co] = s;
+                sred[(threadIdx.x >> 5) * 2 * COUT + COUT + co] = q;
+            }
         }
         __syncthreads();
-        if (threadIdx.x < 2 * COUT) atomicAdd(stats + threadIdx.x, (double)sred[threadIdx.x]);
+        if (threadIdx.x < 2 * COUT) {
+            float t = 0.f;
+            for (int w_ = 0; w_ < kThreads / 32; ++w_) t += sred[w_ * 2 * COUT + threadIdx.x];
+            stat_add(stats, threadIdx.x, (double)t);
+        }
     }
 }
 
@@ -236,7 +242,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads, 2) conv_b1c1_fwd_kernel(const T* __restrict__ in, const float* __restrict__ w,
                                                                     const float* __restrict__ in_a,
                                                                     const float* __restrict__ in_b, int act,
-                                                                    T* __restrict__ out, double* __restrict__ stats,
+                                                                    T* __restrict__ out, long long* __restrict__ stats,
                                                                     int B, int H, int W, int OH, int OW, int pt, int pl,
                                                                     int tiles_h, int tiles_w) {
     constexpr int CIN = 3, COUT = 32, KS = 3, S = 2, TH = 4, TW = 64;
@@ -246,13 +252,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_b1c1_fwd_kernel(const T* __r
     __shared__ float s_in[IH_T * ROWP];
     __shared__ __align__(16) float ws[KS * KS * CIN * COUT];
     __shared__ float sab[2 * CIN];
-    __shared__ float sred[2 * COUT];
+    __shared__ float sred[(kThreads / 32) * 2 * COUT];  // per-warp partials, summed in warp order
     for (int i = threadIdx.x; i < KS * KS * CIN * COUT; i += kThreads) ws[i] = w[i];
     if (threadIdx.x < CIN) {
         sab[threadIdx.x] = in_a ? in_a[threadIdx.x] : 1.f;
         sab[CIN + threadIdx.x] = in_a ? in_b[threadIdx.x] : 0.f;
     }
-    if (threadIdx.x < 2 * COUT) sred[threadIdx.x] = 0.f;
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6, lane = threadIdx.x & 31;
     float cs = 0.f, cq = 0.f;  // running per-channel sums: channel = lane
     const int n_tiles = B * tiles_h * tiles_w;
@@ -321,10 +326,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv_b1c1_fwd_kernel(const T* __r
     }
     if (stats) {
         __syncthreads();
-        atomicAdd(&sred[lane], cs);
-        atomicAdd(&sred[COUT + lane], cq);
+        sred[(threadIdx.x >> 5) * 2 * COUT + lane] = cs;
+        sred[(threadIdx.x >> 5) * 2 * COUT + COUT + lane] = cq;
         __syncthreads();
-        if (threadIdx.x < 2 * COUT) atomicAdd(stats + threadIdx.x, (double)sred[threadIdx.x]);
+        if (threadIdx.x < 2 * COUT) {
+            float t = 0.f;
+            for (int w_ = 0; w_ < kThreads / 32; ++w_) t += sred[w_ * 2 * COUT + threadIdx.x];
+            stat_add(stats, threadIdx.x, (double)t);
+        }
     }
 }
 
@@ -439,6 +448,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_wgrad_kernel(const TI* _
                                                                      const float* __restrict__ in_a,
                                                                      const float* __restrict__ in_b, int act,
                                                                      const TG* __restrict__ g, float* __restrict__ dw,
+                                                                     long long* __restrict__ dw_acc,
                                                                      int B, int H, int W, int OH, int OW, int pt,
                                                                      int pl, int tiles_h, int tiles_w) {
     constexpr int COUT = 3, TH = C3W_TH, TW = C3_TW;
@@ -509,12 +519,20 @@ __global__ void __launch_bounds__(kThreads, 2) conv3out_wgrad_kernel(const TI* _
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < NW; ++i) {
-        const float s = warp_sum(acc[i]);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[i], s);
+    for (int i = 0; i < NW; ++i) acc[i] = warp_sum(acc[i]);
+    // the warps add their sums one after the other (fixed order: the CTA's partial is the same in every run)
+    for (int w_ = 0; w_ < kThreads / 32; ++w_) {
+        if ((threadIdx.x >> 5) == w_ && (threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) sacc[i] += acc[i];
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < NW; i += kThreads) atomicAdd(dw + i, sacc[i]);
+    // across CTAs: fp32 atomics (fast, order of the adds not fixed) or the order-independent accumulators
+    for (int i = threadIdx.x; i < NW; i += kThreads) {
+        if (dw_acc) stat_add(dw_acc, i, (double)sacc[i]);
+        else atomicAdd(dw + i, sacc[i]);
+    }
 }
 
 // =================================================================================================
@@ -526,6 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_b1c1_wgrad_kernel(const T* _
                                                                       const float* __restrict__ in_a,
                                                                       const float* __restrict__ in_b, int act,
                                                                       const T* __restrict__ g, float* __restrict__ dw,
+                                                                      long long* __restrict__ dw_acc,
                                                                       int B, int H, int W, int OH, int OW, int pt, int pl,
                                                                       int tiles_h, int tiles_w) {
     constexpr int CIN = 3, COUT = 32, KS = 3, S = 2, TH = 4, TW = 32;
@@ -601,7 +620,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_b1c1_wgrad_kernel(const T* _
         }
     }
     __syncthreads();
-    // reduce the 4 pixel slots of a warp, then the 8 warps through shared memory
+    // reduce the 4 pixel slots of a warp, then the 8 warps through shared memory, one warp after the other (fixed
+    // order: the CTA's partial is the same in every run)
 #pragma unroll
     for (int t = 0; t < NT; ++t)
 #pragma unroll
@@ -609,10 +629,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_b1c1_wgrad_kernel(const T* _
             float s = acc[t][j];
             s += __shfl_xor_sync(0xffffffffu, s, 8);
             s += __shfl_xor_sync(0xffffffffu, s, 16);
-            if (ps == 0) atomicAdd(&sacc[t * COUT + 4 * cg + j], s);
+            acc[t][j] = s;
         }
-    __syncthreads();
-    for (int i = threadIdx.x; i < NT * COUT; i += kThreads) atomicAdd(dw + i, sacc[i]);
+    for (int w_ = 0; w_ < kThreads / 32; ++w_) {
+        if (warp == w_ && ps == 0) {
+#pragma unroll
+            for (int t = 0; t < NT; ++t)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sacc[t * COUT + 4 * cg + j] += acc[t][j];
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < NT * COUT; i += kThreads) {
+        if (dw_acc) stat_add(dw_acc, i, (double)sacc[i]);
+        else atomicAdd(dw + i, sacc[i]);
+    }
 }
 
 int persist_grid_tiles(long long n_tiles, int ctas_per_sm) {
@@ -633,7 +664,7 @@ extern "C" {
 // in_a/in_b (nullable) + act (0 none, 1 relu, 2 leaky 0.1) transform the input on load.
 // stats (nullable): fp64 [2*Cout] batch-norm accumulators.
 int spnet_conv_small_fwd(int which, const void* in, const float* w, const float* in_a, const float* in_b, int act,
-                         void* out, void* skip, double* stats, int dtype, int B, int H, int W, cudaStream_t stream) {
+                         void* out, void* skip, long long* stats, int dtype, int B, int H, int W, cudaStream_t stream) {
     SPNET_REQUIRE(in && w && out && B > 0 && H > 2 && W > 2, "conv_small_fwd: bad args");
     SPNET_REQUIRE((in_a == nullptr) == (in_b == nullptr), "conv_small_fwd: affine parameters come in pairs");
     if (which == 0) {
@@ -669,8 +700,10 @@ int spnet_conv_small_fwd(int which, const void* in, const float* w, const float*
 
 // dw += weight gradient of the same three convolutions (dw zeroed by the caller).
 // For which == 0, dw is the K4 gradient [4,4,1,3]; fold it with spnet_stem_k4grad_to_k3grad.
+// dw_acc (nullable): order-independent accumulators (one entry per weight, spnet_acc_to_f32 adds them into dw): the
+// cross-CTA sums are then bit-identical run to run instead of fp32 atomics whose order is not fixed
 int spnet_conv_small_wgrad(int which, const void* in, const float* in_a, const float* in_b, int act, const void* g,
-                           float* dw, int dtype, int B, int H, int W, cudaStream_t stream) {
+                           float* dw, long long* dw_acc, int dtype, int B, int H, int W, cudaStream_t stream) {
     SPNET_REQUIRE(in && g && dw && B > 0 && H > 2 && W > 2, "conv_small_wgrad: bad args");
     SPNET_REQUIRE((in_a == nullptr) == (in_b == nullptr), "conv_small_wgrad: affine parameters come in pairs");
     if (which == 0) {
@@ -679,13 +712,13 @@ int spnet_conv_small_wgrad(int which, const void* in, const float* in_a, const f
         const int grid = persist_grid_tiles((long long)B * th * tw, 2);
         SPNET_DISPATCH_DTYPE(dtype, (conv3out_wgrad_kernel<float, T, 1, 4, 2><<<grid, kThreads, 0, stream>>>(
                                         reinterpret_cast<const float*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g),
-                                        dw, B, H, W, OH, OW, 1, 1, th, tw)));
+                                        dw, dw_acc, B, H, W, OH, OW, 1, 1, th, tw)));
     } else if (which == 1) {
         const int th = ceil_div(H, C3W_TH), tw = ceil_div(W, C3_TW);
         const int grid = persist_grid_tiles((long long)B * th * tw, 2);
         SPNET_DISPATCH_DTYPE(dtype, (conv3out_wgrad_kernel<T, T, 3, 3, 1><<<grid, kThreads, 0, stream>>>(
                                         reinterpret_cast<const T*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g), dw,
-                                        B, H, W, H, W, 1, 1, th, tw)));
+                                        dw_acc, B, H, W, H, W, 1, 1, th, tw)));
     } else if (which == 2 || which == 3) {
         const int OH = which == 2 ? (H - 3) / 2 + 1 : (H + 1) / 2, OW = which == 2 ? (W - 3) / 2 + 1 : (W + 1) / 2;
         const int pt = which == 3 ? (H & 1) : 0, pl = which == 3 ? (W & 1) : 0;
@@ -693,7 +726,7 @@ int spnet_conv_small_wgrad(int which, const void* in, const float* in_a, const f
         const int grid = persist_grid_tiles((long long)B * th * tw, 1);  // 134 registers x 256 threads: one CTA per SM
         SPNET_DISPATCH_DTYPE(dtype, (conv_b1c1_wgrad_kernel<T><<<grid, kThreads, 0, stream>>>(
                                         reinterpret_cast<const T*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g), dw,
-                                        B, H, W, OH, OW, pt, pl, th, tw)));
+                                        dw_acc, B, H, W, OH, OW, pt, pl, th, tw)));
     } else {
         spnet_set_error("conv_small_wgrad: unknown conv id %d", which);
         return SPNET_ERR_ARG;

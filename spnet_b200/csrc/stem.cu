@@ -124,7 +124,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn3_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ z,
                                                              const float* __restrict__ mean,
                                                              const float* __restrict__ rstd,
-                                                             double* __restrict__ stats, long long pixels) {
+                                                             long long* __restrict__ stats, long long pixels) {
     float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < pixels;
          p += (long long)gridDim.x * blockDim.x) {
@@ -135,16 +135,18 @@ __global__ void __launch_bounds__(256) bn3_bwd_reduce_kernel(const T* __restrict
             s[3 + c] = fmaf(gv, (to_f32(z[p * 3 + c]) - mean[c]) * rstd[c], s[3 + c]);
         }
     }
-    __shared__ float red[6];
-    if (threadIdx.x < 6) red[threadIdx.x] = 0.f;
-    __syncthreads();
+    __shared__ float red[8][6];  // per-warp partials, summed in warp order (run-to-run identical)
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         const float v = warp_sum(s[i]);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&red[i], v);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
     }
     __syncthreads();
-    if (threadIdx.x < 6) atomicAdd(stats + threadIdx.x, (double)red[threadIdx.x]);
+    if (threadIdx.x < 6) {
+        float t = 0.f;
+        for (int w_ = 0; w_ < (int)(blockDim.x >> 5); ++w_) t += red[w_][threadIdx.x];
+        stat_add(stats, threadIdx.x, (double)t);
+    }
 }
 template <typename T>
 __global__ void bn3_bwd_dz_kernel(const T* g, const T* __restrict__ z, const float* __restrict__ a,
@@ -287,7 +289,7 @@ int spnet_stem_out_bwd(const void* g, void* gout, int dtype, long long pixels, f
     return spnet_check_launch("stem_out_bwd");
 }
 
-int spnet_bn3_bwd_reduce(const void* g, const void* z, const float* save_mean, const float* save_rstd, double* stats,
+int spnet_bn3_bwd_reduce(const void* g, const void* z, const float* save_mean, const float* save_rstd, long long* stats,
                          int dtype, long long pixels, cudaStream_t stream) {
     SPNET_REQUIRE(g && z && save_mean && save_rstd && stats && pixels > 0, "bn3_bwd_reduce: bad args");
     SPNET_DISPATCH_DTYPE(dtype, (bn3_bwd_reduce_kernel<T><<<persist_grid(pixels), 256, 0, stream>>>(

@@ -42,8 +42,15 @@ class SPNetEngineBase:
 
     def __init__(self, H, W, batch, n_out=576, dtype="bf16", device="cuda:0", weights=None, seed=1,
                  loss_type="same", dropout_rate=arch.DROPOUT_RATE, use_l2=True, unbiased_moving_var=True,
-                 training=True):
+                 training=True, deterministic=False):
+        """deterministic: also make the WEIGHT GRADIENTS bit-identical from run to run (split-K partial products go to
+        slabs that are added in a fixed order instead of fp32 reduce-adds). The forward pass, the BatchNorm
+        statistics, the loss and the predictions are order-independent in either mode."""
         assert dtype in ("bf16", "fp32")
+        self.deterministic = bool(deterministic)
+        self._slabs = None
+        self._affine_fixed = False
+        self._gacc = None  # accumulator scratch of the deterministic weight-gradient paths (allocated with the activations)
         rc = lib().check_device  # noqa: F841  (resolved lazily below, after the device is selected)
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
@@ -68,6 +75,11 @@ class SPNetEngineBase:
         self.seed_dev = torch.zeros(1, device=self.device, dtype=torch.int64)
         self.base_seed = int(seed)
         self.grad_hook = None  # called between backward and the optimiser (data-parallel all-reduce)
+        # which BatchNorms normalise with their moving statistics inside a training step: "none" (Keras 2.1.3: even a
+        # frozen BN uses the batch statistics in the training phase), "frozen" (modern tf.keras semantics), "all"
+        self.bn_use_moving = "none"
+        self.frozen8 = None    # uint8 per 8 parameters: non-zero = frozen (set_frozen)
+        self.frozen_layers = frozenset()
 
     # ------------------------------------------------------------------ parameters
     def _alloc_params(self, weights):
@@ -123,6 +135,7 @@ class SPNetEngineBase:
         return out
 
     def refresh_lowp(self):
+        self._affine_fixed = False  # the weights changed: inference-mode BatchNorm affines must be rebuilt
         if self.lowp:
             ops.cast_f32_to_bf16(self.params, self.params_lp)
 
@@ -140,7 +153,7 @@ class SPNetEngineBase:
             bn.ggamma = bn.gbeta = None
         bn.mm, bn.mv = self.nt[name + "/moving_mean"], self.nt[name + "/moving_variance"]
         bn.a, bn.b, bn.mean, bn.rstd, bn.c1, bn.c2 = (self._f32(C) for _ in range(6))
-        bn.stats = torch.zeros(2 * C, device=self.device, dtype=torch.float64)
+        bn.stats = ops.stats_alloc(2 * C, self.device)  # order-independent accumulators (sum | sum of squares)
         self.bns.append(bn)
         return bn
 
@@ -164,6 +177,7 @@ class SPNetEngineBase:
         self.k4 = self._f32(48).view(4, 4, 1, 3)
         self.gk4 = self._f32(48).view(4, 4, 1, 3)
         self.l2_out = self._f32(1)
+        self.l2_acc = ops.stats_alloc(1, self.device)
 
     def _act(self, *shape, dtype=None):
         t = torch.empty(*shape, device=self.device, dtype=dtype or self.adt)
@@ -190,7 +204,10 @@ class SPNetEngineBase:
             self.gfeat = A(B, fh * fw * fc)
             sp = B * sh["stem"][0] * sh["stem"][1] * 3
             self.gstem = [A(sp) for _ in range(2)]
+        if self.deterministic and self.can_train:
+            self._gacc = ops.stats_alloc(9 * 2048, self.device)
         self.dense_splits = max(1, min(64, (2 * 148) // max(1, -(-self.n_out // 128))))
+        self.head_slabs = torch.zeros(self.dense_splits, ops.slab_rows(B), self.n_out, device=self.device, dtype=torch.float32)
 
     # ------------------------------------------------------------------ helpers
     def _view(self, buf, *shape):
@@ -199,9 +216,21 @@ class SPNetEngineBase:
 
     def _bn_ready(self, bn, count, training):
         if training:
-            ops.bn_finalize(bn.stats, count, bn.gamma, bn.beta, bn.a, bn.b, bn.mean, bn.rstd, bn.mm, bn.mv,
-                            eps=arch.BN_EPS, momentum=arch.BN_MOMENTUM, unbiased=self.unbiased)
-        else:
+            # a frozen BatchNormalization (layer.trainable = False under Keras 2.1.3) still normalises with the batch
+            # statistics in the training phase; what stops is the update of its moving averages (Layer.updates is
+            # empty for a non-trainable layer) and of gamma / beta (Adam mask)
+            frozen = bn.name in self.frozen_layers
+            moving = self.bn_use_moving == "all" or (frozen and self.bn_use_moving == "frozen")
+            ops.bn_finalize(bn.stats, count, bn.gamma, bn.beta, bn.a, bn.b, bn.mean, bn.rstd, None if (frozen or moving) else bn.mm,
+                            None if (frozen or moving) else bn.mv, eps=arch.BN_EPS, momentum=arch.BN_MOMENTUM, unbiased=self.unbiased)
+            if moving:
+                # this BatchNorm normalises with its MOVING statistics inside the training step (modern-Keras frozen-BN
+                # semantics, and the N-GPU == 1-GPU gradient test where the batch must not couple the samples): the
+                # affine and the statistics saved for backward come from the moving averages; backward then runs with
+                # count = 0, which drops the batch-statistics terms (c1 = c2 = 0) and leaves dz = a * g
+                ops.bn_inference_affine(bn.gamma, bn.beta, bn.mm, bn.mv, bn.a, bn.b, eps=arch.BN_EPS, save_mean=bn.mean,
+                                        save_rstd=bn.rstd)
+        elif not self._affine_fixed:
             ops.bn_inference_affine(bn.gamma, bn.beta, bn.mm, bn.mv, bn.a, bn.b, eps=arch.BN_EPS)
 
     def _pw_fwd(self, A, Wl, D, M, K, N, bn, training):
@@ -214,10 +243,26 @@ class SPNetEngineBase:
         kb = max(1, K // (64 if self.lowp else 16))
         return int(max(1, min(kb // 4 if kb >= 8 else 1, -(-(2 * 148) // tiles))))
 
+    def _slab_buf(self, nslabs, rows, cols):
+        n = nslabs * ops.slab_rows(rows) * cols
+        if self._slabs is None or self._slabs.numel() < n:
+            assert not torch.cuda.is_current_stream_capturing(), "slab scratch must be sized by an eager warm-up step"
+            self._slabs = torch.zeros(n, device=self.device, dtype=torch.float32)
+        return self._slabs
+
     def _pw_bwd(self, A, Wl, gW, gz, gA, M, K, N):
         """gz [M,N] -> gW [K,N] += A^T gz ;  gA [M,K] = gz W^T."""
-        sp = 0 if self.lowp else self._wgrad_splits(K, N, M)  # 0 = let the tcgen05 GEMM pick (fills the SMs once)
-        ops.gemm(A, True, gz, True, gW, K, N, M, out_mode=ops.OUT_ATOMIC, splits=sp, lda=K, ldb=N)
+        if self.deterministic:
+            # fixed-order split-K: partial products to slabs, added in split order (bit-identical run to run)
+            sp = self._wgrad_splits(K, N, M)
+            slabs = self._slab_buf(sp, K, N)
+            if sp > 1:
+                slabs[:sp * ops.slab_rows(K) * N].zero_()  # a slab the GEMM does not need must read as zero
+            ops.gemm(A, True, gz, True, slabs, K, N, M, out_mode=ops.OUT_SLAB, splits=sp, lda=K, ldb=N)
+            ops.slab_reduce(slabs, sp, K, N, gW, accumulate=True)
+        else:
+            sp = 0 if self.lowp else self._wgrad_splits(K, N, M)  # 0 = let the tcgen05 GEMM pick (fills the SMs once)
+            ops.gemm(A, True, gz, True, gW, K, N, M, out_mode=ops.OUT_ATOMIC, splits=sp, lda=K, ldb=N)
         if gA is not None:
             ops.gemm(gz, False, Wl, False, gA, M, K, N, out_mode=ops.OUT_T, ldb=N)
 
@@ -227,13 +272,17 @@ class SPNetEngineBase:
         M = B * s.H * s.W
         self._pw_fwd(s.t, s.pwl, s.z, M, s.cin, s.cout, s.bn, training)
 
+    def _bwd_count(self, bn, rows):
+        moving = self.bn_use_moving == "all" or (self.bn_use_moving == "frozen" and bn.name in self.frozen_layers)
+        return 0 if moving else rows  # count 0: bn_bwd_finalize drops the batch-statistics terms (c1 = c2 = 0)
+
     def _bn_bwd(self, g, z, bn, rows, relu_mask=False, out=None, reduced=False):
         """g = grad wrt BN output (or wrt relu(BN output) when relu_mask) -> grad wrt z.
         reduced=True: the sums were already accumulated into bn.stats by the producer of g."""
         if not reduced:
             ops.bn_bwd_reduce(g, z, bn.mean, bn.rstd, bn.stats, relu_a=bn.a if relu_mask else None,
                               relu_b=bn.b if relu_mask else None, act=1)
-        ops.bn_bwd_finalize(bn.stats, rows, bn.ggamma, bn.gbeta, bn.c1, bn.c2)
+        ops.bn_bwd_finalize(bn.stats, self._bwd_count(bn, rows), bn.ggamma, bn.gbeta, bn.c1, bn.c2)
         return ops.bn_bwd_dz(g, z, bn.a, bn.mean, bn.rstd, bn.c1, bn.c2, out=out if out is not None else g)
 
     # ------------------------------------------------------------------ forward
@@ -258,9 +307,11 @@ class SPNetEngineBase:
                          seed=self.seed_dev if drop else None)
         self._backbone_fwd(training)
         F = self.feat.shape[1]
-        ops.bias_fill(w["FinalOutput/bias"], self.y_pred)
-        ops.gemm(self.feat, False, self.wl["FinalOutput/kernel"], True, self.y_pred, B, self.n_out, F,
-                 out_mode=ops.OUT_ATOMIC, splits=self.dense_splits)
+        # split-K over the 98,304 features with a FIXED summation order: every split stores its partial product in its
+        # own slab, one small kernel adds bias + slabs in order -> two predict() calls give bit-identical outputs
+        ops.gemm(self.feat, False, self.wl["FinalOutput/kernel"], True, self.head_slabs, B, self.n_out, F,
+                 out_mode=ops.OUT_SLAB, splits=self.dense_splits)
+        ops.slab_reduce(self.head_slabs, self.dense_splits, B, self.n_out, self.y_pred, bias=w["FinalOutput/bias"])
         return self.y_pred
 
     def _entry_fwd(self, e, x, training):
@@ -280,9 +331,9 @@ class SPNetEngineBase:
     def loss(self, with_grad):
         ops.yolo_ellipse_loss(self.y_true, self.y_pred, hybrid=(self.loss_type != "same"), out6=self.loss6,
                               grad=self.gy if with_grad else None)
-        self.l2_out.zero_()
         if self.use_l2:
-            ops.sumsq(self.params, self.n_l2, arch.L2_COEF, self.l2_out)
+            ops.sumsq(self.params, self.n_l2, arch.L2_COEF, self.l2_acc)
+            ops.acc_to_f32(self.l2_acc, self.l2_out)
 
     # ------------------------------------------------------------------ backward
     def _sep_bwd(self, s, gz, x, in_bn, relu, g_t, g_in, add_src=None, add_strided=None):
@@ -296,7 +347,7 @@ class SPNetEngineBase:
         ops.dwconv3x3_bwd_fused(gt4, x, s.dwk, s.gdwk, in_a=in_bn.a if in_bn else None, in_b=in_bn.b if in_bn else None,
                                 relu=relu, bn_mean=in_bn.mean if in_bn else None, bn_rstd=in_bn.rstd if in_bn else None,
                                 stats=in_bn.stats if in_bn else None, add_src=add_src, add_strided=add_strided,
-                                out=g_in.view(B, s.H, s.W, s.cin))
+                                out=g_in.view(B, s.H, s.W, s.cin), acc=self._gacc)
 
     def _entry_bwd(self, e, x, g_out, bufs):
         """g_out: grad wrt block output [B,oh,ow,c]. Returns grad wrt block input x."""
@@ -332,8 +383,11 @@ class SPNetEngineBase:
         if self.lowp:
             ops.cast_f32_to_bf16(self.gy, self.gyl)
         ops.colsum(self.gy, g["FinalOutput/bias"])
-        ops.gemm(self.feat, True, self.gyl, True, g["FinalOutput/kernel"], F, self.n_out, B, out_mode=ops.OUT_F32,
-                 lda=F, ldb=self.n_out)
+        # under bf16 data-parallel communication the 226 MB fp32 weight gradient of the head is written as bf16
+        # straight into the all-reduce buffer (multi_gpu.GradAllReduce sets head_grad_lp); Adam reads it from there
+        gk = getattr(self, "head_grad_lp", None)
+        ops.gemm(self.feat, True, self.gyl, True, gk if gk is not None else g["FinalOutput/kernel"], F, self.n_out, B,
+                 out_mode=ops.OUT_T if gk is not None else ops.OUT_F32, lda=F, ldb=self.n_out)
         ops.gemm(self.gyl, False, self.wl["FinalOutput/kernel"], False, self.gfeat, B, F, self.n_out,
                  out_mode=ops.OUT_T, ldb=self.n_out)
 
@@ -371,25 +425,45 @@ class SPNetEngineBase:
         drop = self.dropout_rate > 0
         ops.stem_out_bwd(ga, gb, rate=self.dropout_rate if drop else 0.0, seed=self.seed_dev if drop else None)
         self._bn3_bwd(gb, self.c3, bn3, npx)                      # gb = grad wrt c3
-        ops.conv_small_wgrad(1, self.c2, gb, g["conv2d_3/kernel"], in_a=bn2.a, in_b=bn2.b, act=2)
+        ops.conv_small_wgrad(1, self.c2, gb, g["conv2d_3/kernel"], in_a=bn2.a, in_b=bn2.b, act=2, acc=self._gacc)
         ops.conv_small_dgrad(1, gb, w["conv2d_3/kernel"], ga, mask_z=self.c2, mask_a=bn2.a, mask_b=bn2.b, act=2)
         self._bn3_bwd(ga, self.c2, bn2, npx)                      # ga = grad wrt c2
-        ops.conv_small_wgrad(1, self.p1, ga, g["conv2d_2/kernel"], in_a=bn1.a, in_b=bn1.b, act=2)
+        ops.conv_small_wgrad(1, self.p1, ga, g["conv2d_2/kernel"], in_a=bn1.a, in_b=bn1.b, act=2, acc=self._gacc)
         ops.conv_small_dgrad(1, ga, w["conv2d_2/kernel"], gb, mask_z=self.p1, mask_a=bn1.a, mask_b=bn1.b, act=2)
         self._bn3_bwd(gb, self.p1, bn1, npx)                      # gb = grad wrt p1
         self.gk4.zero_()
-        ops.conv_small_wgrad(0, self.x0, gb, self.gk4)
+        ops.conv_small_wgrad(0, self.x0, gb, self.gk4, acc=self._gacc)
         ops.stem_k4grad_to_k3grad(self.gk4, g["conv2d_1/kernel"])
 
     def _bn3_bwd(self, gbuf, z, bn, npx):
         ops.bn3_bwd_reduce(gbuf, z, bn.mean, bn.rstd, bn.stats)
-        ops.bn_bwd_finalize(bn.stats, npx, bn.ggamma, bn.gbeta, bn.c1, bn.c2)
+        ops.bn_bwd_finalize(bn.stats, self._bwd_count(bn, npx), bn.ggamma, bn.gbeta, bn.c1, bn.c2)
         ops.bn3_bwd_dz(gbuf, z, bn.a, bn.mean, bn.rstd, bn.c1, bn.c2, gbuf)
 
     # ------------------------------------------------------------------ optimiser / step
-    def optimizer_step(self, grad_scale=1.0):
-        ops.adam_keras_step(self.params, self.grads, self.adam_m, self.adam_v, self.lr_t_dev, n_l2=self.n_l2 if self.use_l2 else 0,
-                            l2=arch.L2_COEF, grad_scale=grad_scale, p_bf16=self.params_lp)
+    def set_frozen(self, layer_names):
+        """Layers whose weights must not train (Keras layer.trainable = False; spnet/models.py:361-372): Adam skips
+        every tensor of those layers (no update, no L2 pull) and their BatchNormalization moving averages stop."""
+        self.frozen_layers = frozenset(layer_names or ())
+        if not self.frozen_layers:
+            self.frozen8 = None
+            return
+        mask = np.zeros(self.n_params_padded // 8, np.uint8)
+        for k, (o, n, _) in self.offsets.items():
+            if k.split("/")[0] in self.frozen_layers:
+                mask[o // 8:(o + n + 7) // 8] = 1
+        self.frozen8 = torch.from_numpy(mask).to(self.device)
+        self.graph = None  # the mask pointer is baked into a captured step
+
+    def optimizer_step(self, grad_scale=1.0, lo=0, hi=None, g_bf16=None):
+        """Keras Adam (+ L2 pull) on the flat parameter range [lo, hi) (multiples of 8; default: everything)."""
+        hi = self.n_params_padded if hi is None else hi
+        n_l2 = min(max((self.n_l2 if self.use_l2 else 0) - lo, 0), hi - lo)
+        ops.adam_keras_step(self.params[lo:hi], self.grads[lo:hi], self.adam_m[lo:hi], self.adam_v[lo:hi], self.lr_t_dev,
+                            n_l2=n_l2, l2=arch.L2_COEF, grad_scale=grad_scale,
+                            p_bf16=self.params_lp[lo:hi] if self.params_lp is not None else None,
+                            frozen8=self.frozen8[lo // 8:] if self.frozen8 is not None else None,
+                            g_bf16=g_bf16[lo:hi] if g_bf16 is not None else None)
 
     def _step_part1(self):
         # the Dense-head weight gradient (73 % of the buffer, at offset 0) is written in overwrite mode
@@ -452,6 +526,9 @@ class SPNetEngineBase:
         Returns the device tensor [total, center, size, angle, noobj, class] (data loss) —
         the L2 term is in self.l2_out."""
         self.set_lr(lr)
+        fn = getattr(self.grad_hook, "step_begin", None)
+        if fn is not None:
+            fn(self)
         if self.graph is not None:
             self.graph[0].replay()
             if len(self.graph) > 1:
@@ -474,45 +551,89 @@ class SPNetEngineBase:
     def _ensure_stage(self):
         if getattr(self, "_copy_stream", None) is None:
             self._xs = torch.empty_like(self.x0)
+            self._xs_u8 = None
             self._ys = torch.empty_like(self.y_true)
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._stage_ready = torch.cuda.Event()
             self._stage_free = torch.cuda.Event()
             self._stage_free.record()
             self._h2d_done = torch.cuda.Event()
+            self._staged_u8 = False
 
     def prefetch_batch(self, x_host, y_host=None):
         """Start the H2D copy of a batch (pinned torch tensors) without blocking the compute stream.
-        Returns an event that fires when the host buffers may be reused."""
+        uint8 frames (raw pixel values 0..255) travel as bytes - a quarter of the PCIe traffic of fp32 - and are
+        normalised on the device by take_prefetched(). Returns an event that fires when the host buffers may be reused."""
         self._ensure_stage()
         cs = self._copy_stream
+        u8 = x_host.dtype == torch.uint8
+        if u8 and self._xs_u8 is None:
+            self._xs_u8 = torch.empty(self.x0.shape, device=self.device, dtype=torch.uint8)
         with torch.cuda.stream(cs):
             cs.wait_event(self._stage_free)  # the previous staged batch has been taken
-            self._xs.copy_(x_host.view(self._xs.shape), non_blocking=True)
+            if u8:
+                self._xs_u8.copy_(x_host.view(self._xs_u8.shape), non_blocking=True)
+            else:
+                self._xs.copy_(x_host.view(self._xs.shape), non_blocking=True)
             if y_host is not None:
                 self._ys.copy_(y_host.view(self._ys.shape), non_blocking=True)
             done = torch.cuda.Event()
             done.record(cs)
             self._stage_ready.record(cs)
         self._has_y = y_host is not None
+        self._staged_u8 = u8
         return done
 
     def take_prefetched(self):
         """Make the staged batch the current one (compute stream waits for its H2D copy only)."""
         main = torch.cuda.current_stream()
         main.wait_event(self._stage_ready)
-        self.x0.copy_(self._xs)
+        if self._staged_u8:
+            ops.normalize_u8(self._xs_u8, self.x0)  # (v/255 - 0.5)*2, spnet/utils.py:340-342
+        else:
+            self.x0.copy_(self._xs)
         if self._has_y:
             self.y_true.copy_(self._ys)
         self._stage_free.record(main)
 
     def load_batch(self, x_host, y_host=None):
-        """H2D copy of one batch (numpy or pinned torch tensors)."""
-        xt = x_host if torch.is_tensor(x_host) else torch.from_numpy(np.ascontiguousarray(x_host, dtype=np.float32))
-        self.x0.copy_(xt.view(self.x0.shape), non_blocking=True)
+        """H2D copy of one batch (numpy or pinned torch tensors; uint8 frames are normalised on the device)."""
+        if (torch.is_tensor(x_host) and x_host.dtype == torch.uint8) or (not torch.is_tensor(x_host) and np.asarray(x_host).dtype == np.uint8):
+            xt = x_host if torch.is_tensor(x_host) else torch.from_numpy(np.ascontiguousarray(x_host))
+            ops.normalize_u8(xt.view(self.x0.shape).to(self.device, non_blocking=True), self.x0)
+        else:
+            xt = x_host if torch.is_tensor(x_host) else torch.from_numpy(np.ascontiguousarray(x_host, dtype=np.float32))
+            self.x0.copy_(xt.view(self.x0.shape), non_blocking=True)
         if y_host is not None:
             yt = y_host if torch.is_tensor(y_host) else torch.from_numpy(np.ascontiguousarray(y_host, dtype=np.float32))
             self.y_true.copy_(yt.view(self.y_true.shape), non_blocking=True)
+
+    # ---- inference: the forward pass as one CUDA graph
+    def capture_forward(self):
+        """Capture forward(training=False) into a CUDA graph (call after one eager forward)."""
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward(training=False)
+        self.fwd_graph = g
+
+    def prepare_inference(self):
+        """Inference-only engines: build every BatchNorm's moving-statistics affine once per set of weights instead of
+        once per forward pass (about a hundred tiny launches per batch)."""
+        self._affine_fixed = False
+        for bn in self.bns:
+            self._bn_ready(bn, 0, False)
+        self._affine_fixed = not self.can_train  # a training step overwrites bn.a / bn.b with batch-statistics affines
+
+    def infer(self):
+        """Inference-mode forward on the batch in self.x0 (graph replay once captured). Result in self.y_pred."""
+        if not self._affine_fixed and not self.can_train:
+            self.prepare_inference()
+        g = getattr(self, "fwd_graph", None)
+        if g is not None:
+            g.replay()
+        else:
+            self.forward(training=False)
+        return self.y_pred
 
 
 class XceptionSPNetEngine(SPNetEngineBase):
@@ -678,7 +799,7 @@ class XceptionSPNetEngine(SPNetEngineBase):
             self._pw_bwd(self.col, W2l, g["block1_conv2/kernel"].view(288, 64), g_z12.view(M2, 64), self.gcol, M2, 288, 64)
             ops.col2im3x3(self.gcol, g_y11, z=self.z11, a=self.b1_bn1.a, b=self.b1_bn1.b, relu=True)
             g_z11 = self._bn_bwd(g_y11, self.z11, self.b1_bn1, B * h1 * w1)
-        ops.conv_small_wgrad(2, self.d, g_z11, g["block1_conv1/kernel"])
+        ops.conv_small_wgrad(2, self.d, g_z11, g["block1_conv1/kernel"], acc=self._gacc)
         ops.conv_small_dgrad(2, g_z11, w["block1_conv1/kernel"], ga)
 
 
@@ -783,11 +904,11 @@ class MobileNetSPNetEngine(SPNetEngineBase):
             # depthwise 3x3: gradient w.r.t. relu6(BN_prev(x)) (masked) + BN_prev backward sums + dk
             g_y = self._view(bufs[nb], B, h, wd, cin)
             ops.dwconv3x3_bwd_fused(g_full, x, b["dwk"], b["gdwk"], in_a=xbn.a, in_b=xbn.b, relu=2, bn_mean=xbn.mean,
-                                    bn_rstd=xbn.rstd, stats=xbn.stats, out=g_y)
+                                    bn_rstd=xbn.rstd, stats=xbn.stats, out=g_y, acc=self._gacc)
             cur = nb
         h, wd = self.shapes["conv1"]
         g_zc1 = self._bn_bwd(g_y, self.zc1, self.c1_bn, B * h * wd, reduced=True)
-        ops.conv_small_wgrad(3, self.d, g_zc1, g["conv1/kernel"])
+        ops.conv_small_wgrad(3, self.d, g_zc1, g["conv1/kernel"], acc=self._gacc)
         ops.conv_small_dgrad(3, g_zc1, w["conv1/kernel"], ga)
 
 
@@ -938,7 +1059,7 @@ class InceptionResNetV2SPNetEngine(SPNetEngineBase):
                 dz = self._bn_bwd(gy, z, bn, M, reduced=True)
                 gW = g_[op["name"] + "/kernel"]
                 if op["cin"] == 3:
-                    ops.conv_small_wgrad(2, xs[0], dz, gW)
+                    ops.conv_small_wgrad(2, xs[0], dz, gW, acc=self._gacc)
                     ops.conv_small_dgrad(2, dz, w[op["name"] + "/kernel"], ga)
                     continue
                 if self._implicit(op):

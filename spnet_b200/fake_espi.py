@@ -100,23 +100,58 @@ def make_frame(seed):
     return (img.reshape(IM_H, IM_W) * mask.reshape(IM_H, IM_W)).astype(np.uint8), rows
 
 
-def make_dataset(n, base_seed=0, pred_grid=(6, 6, 2)):
+def _frame_job(args):
+    seed, pred_grid = args
+    from . import utils
+    img, rows = make_frame(seed)
+    try:
+        y, _ = utils.build_Y_from_rows([rows], pred_grid=list(pred_grid))
+    except AssertionError:   # labels overflow a grid cell (the reference asserts, spnet/utils.py:240): frame is redrawn
+        return None
+    return img, y[0], rows
+
+
+def make_frames_u8(n, base_seed=0, pred_grid=(6, 6, 2), workers=1):
+    """n frames as uint8 (n,384,512,1) pixel values, Y float32 (n,576) normalised targets, rows. Frame i is drawn from
+    seed base_seed + i + (number of earlier frames that were redrawn), exactly as the sequential loop would; with
+    workers > 1 the seeds are drawn in parallel processes (call BEFORE CUDA is initialised) and consumed in seed order."""
+    X = np.zeros((n, IM_H, IM_W, 1), np.uint8)
+    Ys, all_rows = [], []
+    seed, i = base_seed, 0
+    pool = None
+    if workers > 1:
+        import multiprocessing as mp
+        pool = mp.get_context("fork").Pool(workers)
+    try:
+        while i < n:
+            chunk = list(range(seed, seed + max(n - i, 1)))
+            jobs = [(sd, tuple(pred_grid)) for sd in chunk]
+            results = pool.map(_frame_job, jobs, chunksize=max(1, len(jobs) // (4 * workers))) if pool else map(_frame_job, jobs)
+            for r in results:
+                seed += 1
+                if r is None:
+                    continue
+                if i < n:
+                    X[i, :, :, 0] = r[0]
+                    Ys.append(r[1])
+                    all_rows.append(r[2])
+                    i += 1
+                else:
+                    seed -= 1  # not consumed
+                    break
+    finally:
+        if pool is not None:
+            pool.close()
+            pool.join()
+    return X, np.stack(Ys).astype(np.float32), all_rows
+
+
+def make_dataset(n, base_seed=0, pred_grid=(6, 6, 2), workers=1):
     """n frames -> X float32 (n,384,512,1) in [-1,1], Y float32 (n,576) normalised targets, rows.
     Frames whose labels overflow a grid cell (the reference asserts, spnet/utils.py:240) are redrawn."""
-    from . import utils
-    X = np.zeros((n, IM_H, IM_W, 1), np.float32)
-    Ys, all_rows = [], []
-    seed = base_seed
-    i = 0
-    while i < n:
-        img, rows = make_frame(seed)
-        seed += 1
-        try:
-            y, _ = utils.build_Y_from_rows([rows], pred_grid=list(pred_grid))
-        except AssertionError:
-            continue
-        X[i, :, :, 0] = (img.astype(np.float32) / 255.0 - 0.5) * 2.0
-        Ys.append(y[0])
-        all_rows.append(rows)
-        i += 1
-    return X, np.stack(Ys).astype(np.float32), all_rows
+    Xu, Y, rows = make_frames_u8(n, base_seed, pred_grid, workers)
+    X = Xu.astype(np.float32)
+    X = X / 255.0      # spnet/utils.py:340-342
+    X -= 0.5
+    X *= 2.0
+    return X, Y, rows

@@ -183,6 +183,12 @@ class SPNetModel:
     def count_params(self):
         return arch.count_params(self.spec)[0]
 
+    def _count_trainable(self):
+        """(trainable, non-trainable) parameter counts as Keras reports them: weights of frozen layers count as
+        non-trainable (spnet/models.py:415-423)."""
+        tr = sum(int(np.prod(self._shape[k])) for k in self.trainable_weights)
+        return tr, arch.count_params(self.spec)[0] - tr
+
     def _weights_dict(self):
         if self._master is not None:
             self._host_weights = self._master.get_weights()
@@ -236,6 +242,7 @@ class SPNetModel:
         w = self._weights_dict()
         with open(filepath, "wb") as f:
             np.savez(f, __config__=np.array([self.H, self.W, self.Y0size, int(self.use_l2)]),
+                     __backbone__=np.array(self.backbone), __loss_type__=np.array(cf.loss_type),
                      **{k.replace("/", "::"): v for k, v in w.items()})
 
     def summary(self):
@@ -268,36 +275,88 @@ class SPNetModel:
                 eng.refresh_lowp()
             eng._version = self._version
         eng.loss_type = cf.loss_type
+        if training and eng.frozen_layers != frozenset(self.frozen_layers):
+            eng.set_frozen(self.frozen_layers)
         return eng
 
     # ---- inference ----------------------------------------------------------------------------
     def predict(self, X, batch_size=32, verbose=0):
+        """Keras Model.predict (reference call site predict_spnet.py:85): inference-mode forward over X in batches.
+        X: numpy / torch array (n, H, W, 1), float32 already normalised, or uint8 raw pixel values (normalised on the
+        device, (v/255 - 0.5)*2 of spnet/utils.py:340-342 bit for bit; a quarter of the host->device bytes).
+        The forward pass of a batch is one CUDA-graph replay; batch k+1 travels host -> device on a copy stream
+        (from X itself when X is a pinned torch tensor, through a pinned staging pair filled by a helper thread
+        otherwise) while batch k computes, and the results come back through one pinned buffer."""
         torch = _torch()
-        X = np.asarray(X, dtype=np.float32)
-        n = X.shape[0]
+        if torch.is_tensor(X):
+            Xt = X if X.dtype in (torch.uint8, torch.float32) else X.float()
+        else:
+            Xn = np.asarray(X)
+            if Xn.dtype not in (np.uint8, np.float32):
+                Xn = Xn.astype(np.float32)
+            Xt = torch.from_numpy(np.ascontiguousarray(Xn))
+        n = Xt.shape[0]
         out = np.empty((n, self.Y0size), np.float32)
         if n == 0:
             return out
         bs = min(batch_size, n)
         eng = self._engine(bs, False)
-        pin = [torch.empty((bs,) + X.shape[1:], dtype=torch.float32).pin_memory() for _ in range(2)]
-        res = torch.empty((n, self.Y0size), dtype=torch.float32).pin_memory()
-        i, k = 0, 0
-        while i < n:
-            m = min(bs, n - i)
-            buf = pin[k % 2]
-            buf[:m].copy_(torch.from_numpy(X[i:i + m]))
-            if m < bs:
-                buf[m:].zero_()
-            eng.load_batch(buf)
-            y = eng.forward(training=False)
-            res[i:i + m].copy_(y[:m], non_blocking=True)
-            i += m
-            k += 1
-            if k % 2 == 0:
-                torch.cuda.current_stream().synchronize()  # the pinned staging buffers are reused
+        nb = -(-n // bs)
+        frame = tuple(Xt.shape[1:])
+        res = torch.empty((nb * bs, self.Y0size), dtype=torch.float32).pin_memory()
+        if os.environ.get("SPNET_B200_NO_GRAPH") is None and getattr(eng, "fwd_graph", None) is None:
+            eng.x0.zero_()
+            eng.prepare_inference()
+            eng.forward(training=False)   # eager warm-up (sizes every lazily allocated buffer), then capture
+            torch.cuda.synchronize()
+            eng.capture_forward()
+        if Xt.is_cuda:
+            for j in range(nb):
+                m = min(bs, n - j * bs)
+                if m < bs:
+                    eng.x0.zero_()
+                src = Xt[j * bs:j * bs + m]
+                if src.dtype == torch.uint8:
+                    from . import ops
+                    if m == bs:
+                        ops.normalize_u8(src.contiguous().view(eng.x0.shape), eng.x0)
+                    else:
+                        eng.x0[:m].copy_(ops.normalize_u8(src.contiguous()).view((m,) + tuple(eng.x0.shape[1:])))
+                else:
+                    eng.x0[:m].copy_(src.reshape((m,) + tuple(eng.x0.shape[1:])))
+                res[j * bs:(j + 1) * bs].copy_(eng.infer(), non_blocking=True)
+        else:
+            direct = Xt.is_pinned() and Xt.is_contiguous()
+            pin = None if direct else [torch.empty((bs,) + frame, dtype=Xt.dtype).pin_memory() for _ in range(2)]
+            pin_free = [None, None]
+
+            def fill(j):
+                """Host side of batch j: a full pinned batch to copy from (X itself, or a staging buffer)."""
+                m = min(bs, n - j * bs)
+                if direct and m == bs:
+                    return Xt[j * bs:(j + 1) * bs]
+                k = j % 2
+                if pin is None:
+                    return torch.cat([Xt[j * bs:j * bs + m], torch.zeros((bs - m,) + frame, dtype=Xt.dtype)]).pin_memory()
+                if pin_free[k] is not None:
+                    pin_free[k].synchronize()  # the H2D copy that last read this staging buffer is done
+                pin[k][:m].copy_(Xt[j * bs:j * bs + m])
+                if m < bs:
+                    pin[k][m:].zero_()
+                return pin[k]
+
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=1) as pool:  # staging memcpy of batch j+1 overlaps the launches of batch j
+                nxt = pool.submit(fill, 0)
+                for j in range(nb):
+                    buf = nxt.result()
+                    pin_free[j % 2] = eng.prefetch_batch(buf)
+                    if j + 1 < nb:
+                        nxt = pool.submit(fill, j + 1)
+                    eng.take_prefetched()
+                    res[j * bs:(j + 1) * bs].copy_(eng.infer(), non_blocking=True)
         torch.cuda.synchronize()
-        out[:] = res.numpy()
+        out[:] = res.numpy()[:n]
         return out
 
     def evaluate(self, X, Y, batch_size=32, verbose=0):
@@ -463,20 +522,15 @@ def create_model_functional(X, Y0size=576, freeze_fac=0.75, quick_setup=False):
         raise NotImplementedError("cf.basemodel = %r: the Xception (reference default, spnet/config.py:52), MobileNet and "
                                   "InceptionResNetV2 backbones are built" % cf.basemodel)
     model = SPNetModel(X[0].shape, Y0size=Y0size, quick_setup=quick_setup, backbone=cf.basemodel)
-    # Keras layer count of base_model: 144 for Xception (paper/run_logs/log_DatasetA_*.txt:95);
-    # MobileNet: 1 Input + 12 stem layers + 81 backbone layers (3 + 13 x 6)
-    # InceptionResNetV2: 1 Input + 12 stem layers + 779 backbone layers after its input
-    num_layers = {"Xception": 144, "MobileNet": 94}.get(cf.basemodel, 792)
-    freeze_layers = int(num_layers * freeze_fac)
+    # base_model.layers[:int(num_layers * freeze_fac)].trainable = False (spnet/models.py:361-372), on the exact Keras
+    # layer order for Xception (144 layers, paper/run_logs/log_DatasetA_*.txt:95) and MobileNet (94)
+    names, freeze_layers, num_layers = arch.frozen_layer_names(cf.basemodel, freeze_fac, model.spec)
     print("Freezing ", freeze_layers, "/", num_layers, " layers of base_model")
-    if freeze_layers > 0:
-        names = [l.name for l in model.layers if l.name != "FinalOutput"]
-        # the 144 Keras layers include weight-less ones; scale the cut to the layers that carry weights
-        model.frozen_layers = set(names[:int(round(len(names) * freeze_layers / float(num_layers)))])
-    tot, tr, nt = arch.count_params(model.spec)
+    model.frozen_layers = set(names)
     if not quick_setup:
+        tr, nt = model._count_trainable()
         print("After adding l2 regularization, model.losses =", model.losses)
-        print("create_model_functional: Total params: {:,}".format(tot))
+        print("create_model_functional: Total params: {:,}".format(tr + nt))
         print("create_model_functional: Trainable params: {:,}".format(tr))
         print("create_model_functional: Non-trainable params: {:,}".format(nt))
     return model
@@ -518,7 +572,8 @@ def unfreeze_model(model, X, Y, parallel=False):
         new_model = multi_gpu.make_parallel(new_model)
     new_model.compile(loss=custom_loss, optimizer=Adam(lr=0.00001))
     print("  ...finished un-freezing model")
-    tot, tr, nt = arch.count_params(new_model.spec)
+    tr, nt = new_model._count_trainable()
+    tot = tr + nt
     print("post-unfreeze_model: Total params: {:,}".format(tot))
     print("post-unfreeze_model: Trainable params: {:,}".format(tr))
     print("post-unfreeze_model: Non-trainable params: {:,}".format(nt))
@@ -529,7 +584,15 @@ def load_model(filepath):
     """keras.models.load_model counterpart for files written by SPNetModel.save."""
     z = np.load(filepath)
     H, W, Y0, use_l2 = (int(v) for v in z["__config__"])
-    m = SPNetModel((H, W, 1), Y0size=Y0, quick_setup=not use_l2)
-    m._load_dict({k.replace("::", "/"): z[k] for k in z.files if not k.startswith("__")})
+    backbone = str(z["__backbone__"]) if "__backbone__" in z.files else "Xception"
+    if "__loss_type__" in z.files:
+        cf.loss_type = str(z["__loss_type__"])   # the reference's load_model restores the compiled loss with the model
+    m = SPNetModel((H, W, 1), Y0size=Y0, quick_setup=not use_l2, backbone=backbone)
+    d = {k.replace("::", "/"): z[k] for k in z.files if not k.startswith("__")}
+    missing = [k for k, _, _, _ in m.spec if k not in d]
+    if missing:
+        raise ValueError("load_model: %s does not hold a %s-SPNet for %dx%d input (%d tensors missing, first: %s)"
+                         % (filepath, backbone, H, W, len(missing), missing[0]))
+    m._load_dict(d)
     m.compile(loss=custom_loss, optimizer=Adam(lr=0.00001))
     return m

@@ -83,39 +83,37 @@ def dwconv3x3_fwd(x, k, in_a=None, in_b=None, relu=False, out=None):
     return out
 
 
-def dwconv3x3_dgrad(gout, k, mask_src=None, mask_a=None, mask_b=None, add_src=None, add_strided=None, out=None):
-    _chk(gout, k, mask_src, mask_a, mask_b, add_src, add_strided, out)
-    B, H, W, C = gout.shape
-    if out is None:
-        out = torch.empty_like(gout)
-    lib().dwconv3x3_dgrad(_p(gout), _p(k), _p(out), _p(mask_src), _p(mask_a), _p(mask_b), _p(add_src),
-                          _p(add_strided), dtype_code(gout), B, H, W, C, _s())
-    return out
-
-
 def dwconv3x3_bwd_fused(gout, x, k, dk, in_a=None, in_b=None, relu=False, bn_mean=None, bn_rstd=None, stats=None,
-                        add_src=None, add_strided=None, out=None):
-    """gin, dk (+=) and optional BatchNorm-backward sums in one pass (see dwconv.cu)."""
+                        add_src=None, add_strided=None, out=None, acc=None):
+    """gin, dk (+=) and optional BatchNorm-backward sums in one pass (see dwconv_packed.cu)."""
     _chk(gout, x, k, dk, in_a, in_b, stats, add_src, add_strided, out)
     B, H, W, C = gout.shape
     if out is None:
         out = torch.empty_like(gout)
     lib().dwconv3x3_bwd_fused(_p(gout), _p(x), _p(k), _p(in_a), _p(in_b), int(relu), _p(bn_mean), _p(bn_rstd),
-                              _p(stats), _p(add_src), _p(add_strided), _p(out), _p(dk), dtype_code(gout), B, H, W, C,
+                              _p(stats), _p(add_src), _p(add_strided), _p(out), _p(dk), _p(acc), dtype_code(gout), B, H, W, C,
                               _s())
+    if acc is not None:  # order-independent kernel gradient: accumulators -> dk (+=), accumulators cleared
+        lib().acc_to_f32(_p(acc), _p(dk), dk.numel(), 1, 1, _s())
     return out
 
 
-def dwconv3x3_wgrad(x, gout, dk, in_a=None, in_b=None, relu=False):
-    """dk (fp32 [3,3,C]) is accumulated into: zero it first."""
-    _chk(x, gout, dk, in_a, in_b)
-    B, H, W, C = x.shape
-    lib().dwconv3x3_wgrad(_p(x), _p(gout), _p(in_a), _p(in_b), int(relu), _p(dk), dtype_code(x), B, H, W, C, _s())
-    return dk
-
-
 # ----------------------------------------------------------------------------- GEMM
-OUT_T, OUT_F32, OUT_ATOMIC = 0, 1, 2
+OUT_T, OUT_F32, OUT_ATOMIC, OUT_SLAB = 0, 1, 2, 3
+
+
+def slab_rows(M):
+    """Row stride between the split-K slabs of gemm(..., out_mode=OUT_SLAB)."""
+    return (M + 255) // 256 * 256
+
+
+def slab_reduce(slabs, nslabs, M, N, out, bias=None, accumulate=False, ldo=None):
+    """out[M,N] = [out +] bias + slab_0 + slab_1 + ... in that order (slabs: zero-initialised [nslabs, slab_rows(M), N]
+    fp32 buffer written by gemm(..., out_mode=OUT_SLAB, splits=nslabs); slabs the GEMM did not need stay zero)."""
+    _chk(slabs, out, bias)
+    lib().slab_reduce(_p(slabs), nslabs, slab_rows(M) * N, N, _p(bias), _p(out), ldo if ldo is not None else N, M, N,
+                      int(accumulate), _s())
+    return out
 
 
 def gemm(A, a_mn, B, b_mn, D, M, N, K, out_mode=OUT_T, splits=1, colstats=None, lda=None, ldb=None, ldd=None):
@@ -194,8 +192,9 @@ def bn_finalize(stats, count, gamma, beta, a, b, save_mean, save_rstd, moving_me
                       _p(save_mean), _p(save_rstd), _p(moving_mean), _p(moving_var), C, _s())
 
 
-def bn_inference_affine(gamma, beta, moving_mean, moving_var, a, b, eps=1e-3):
-    lib().bn_inference_affine(_p(gamma), _p(beta), _p(moving_mean), _p(moving_var), eps, _p(a), _p(b), a.numel(), _s())
+def bn_inference_affine(gamma, beta, moving_mean, moving_var, a, b, eps=1e-3, save_mean=None, save_rstd=None):
+    lib().bn_inference_affine(_p(gamma), _p(beta), _p(moving_mean), _p(moving_var), eps, _p(a), _p(b), _p(save_mean),
+                              _p(save_rstd), a.numel(), _s())
 
 
 def bn_apply(z, a, b, act=0, x=None, out=None):
@@ -321,10 +320,14 @@ def conv_small_fwd(which, x, w, out, skip=None, in_a=None, in_b=None, act=0, sta
     return out
 
 
-def conv_small_wgrad(which, x, g, dw, in_a=None, in_b=None, act=0):
-    _chk(x, g, dw)
+def conv_small_wgrad(which, x, g, dw, in_a=None, in_b=None, act=0, acc=None):
+    """dw += weight gradient. acc: accumulator scratch (stats_alloc, >= dw.numel() entries, all zero): the cross-CTA sums
+    then go through the order-independent accumulators (bit-identical run to run) and are added into dw afterwards."""
+    _chk(x, g, dw, acc)
     B, H, W = x.shape[0], x.shape[1], x.shape[2]
-    lib().conv_small_wgrad(which, _p(x), _p(in_a), _p(in_b), act, _p(g), _p(dw), dtype_code(g), B, H, W, _s())
+    lib().conv_small_wgrad(which, _p(x), _p(in_a), _p(in_b), act, _p(g), _p(dw), _p(acc), dtype_code(g), B, H, W, _s())
+    if acc is not None:
+        lib().acc_to_f32(_p(acc), _p(dw), dw.numel(), 1, 1, _s())
     return dw
 
 
@@ -380,13 +383,91 @@ def col2im3x3(gcol, gin, z=None, a=None, b=None, relu=False):
 
 # ----------------------------------------------------------------------------- optimiser
 def adam_keras_step(p, g, m, v, lr_t_dev, n_l2=0, l2=1e-4, beta1=0.9, beta2=0.999, eps=1e-7, grad_scale=1.0,
-                    p_bf16=None):
+                    p_bf16=None, frozen8=None, g_bf16=None):
+    """Keras-2.1.3 Adam on a flat range. frozen8: uint8 per 8 parameters (non-zero = not trainable);
+    g_bf16: read the gradients from this bf16 buffer instead of g."""
     lib().adam_keras_step(_p(p), _p(g), _p(m), _p(v), p.numel(), n_l2, l2, _p(lr_t_dev), beta1, beta2, eps,
-                          grad_scale, _p(p_bf16), _s())
+                          grad_scale, _p(p_bf16), _p(frozen8), _p(g_bf16), _s())
 
 
-def sumsq(p, n, scale, out):
-    lib().sumsq(_p(p), n, scale, _p(out), _s())
+def sumsq(p, n, scale, acc):
+    """acc (stats accumulator, 1 entry) += scale * sum(p[:n]^2); read it with acc_to_f32."""
+    lib().sumsq(_p(p), n, scale, _p(acc), _s())
+
+
+def acc_to_f32(acc, out, accumulate=False, clear=True):
+    lib().acc_to_f32(_p(acc), _p(out), out.numel(), int(accumulate), int(clear), _s())
+    return out
+
+
+# ---- order-independent accumulators (csrc/common.cuh stat_add / stat_get): 2 int64 words per entry
+def stats_alloc(n_entries, device):
+    return torch.zeros(2 * n_entries, device=device, dtype=torch.int64)
+
+
+def stats_values(st):
+    """Decode an accumulator buffer into float64 values (host-side helper for tests / diagnostics)."""
+    w = st.detach().cpu().view(-1, 2)
+    return (w[:, 0].double() + w[:, 1].double() / 4294967296.0) / 16777216.0
+
+
+def stats_from_values(vals, device):
+    """Encode float64 values as accumulators (tests feed bn_finalize directly)."""
+    t = vals.detach().cpu().double() * 16777216.0
+    hi = torch.floor(t)
+    lo = torch.floor((t - hi) * 4294967296.0)
+    return torch.stack([hi.long(), lo.long()], 1).reshape(-1).contiguous().to(device)
+
+
+# ----------------------------------------------------------------------------- host-path kernels
+def assign_grid(ann, counts, defaults, means, ranges, nx=6, ny=6, ppc=2):
+    """true_to_pred_grid + norm_Y on the device. ann [n, max_obj, 8] float64, counts [n] int32.
+    Returns (Y [n, nx*ny*ppc*8] fp32, err [n] int32)."""
+    _chk(ann, counts, defaults, means, ranges)
+    assert ann.dtype == torch.float64 and counts.dtype == torch.int32
+    n, max_obj = ann.shape[0], ann.shape[1]
+    Y = torch.empty(n, nx * ny * ppc * 8, device=ann.device, dtype=torch.float32)
+    err = torch.zeros(n, device=ann.device, dtype=torch.int32)
+    lib().assign_grid(_p(ann), _p(counts), n, max_obj, nx, ny, ppc, _p(defaults), _p(means), _p(ranges), _p(Y), _p(err), _s())
+    return Y, err
+
+
+def yolo_ellipse_loss_ann(ann, counts, defaults, means, ranges, y_pred, nx=6, ny=6, ppc=2, hybrid=False, sel_sigmoid=False,
+                          out6=None, grad=None, y_true_out=None):
+    """custom_loss straight from the annotations (assignment + normalisation + loss + gradient in one launch).
+    Returns (out6, err)."""
+    _chk(ann, counts, defaults, means, ranges, y_pred, out6, grad, y_true_out)
+    assert ann.dtype == torch.float64 and counts.dtype == torch.int32
+    B, max_obj = ann.shape[0], ann.shape[1]
+    assert y_pred.shape == (B, nx * ny * ppc * 8)
+    if out6 is None:
+        out6 = torch.empty(6, device=y_pred.device, dtype=torch.float32)
+    err = torch.zeros(B, device=y_pred.device, dtype=torch.int32)
+    lib().yolo_ellipse_loss_ann(_p(ann), _p(counts), max_obj, nx, ny, ppc, _p(defaults), _p(means), _p(ranges), _p(y_pred), B,
+                                int(hybrid), int(sel_sigmoid), _p(y_true_out), _p(out6), _p(grad), _p(err), _s())
+    return out6, err
+
+
+_U8_LUT = {}
+
+
+def normalize_u8(x_u8, out=None):
+    """(v/255 - 0.5)*2 of spnet/utils.py:340-342 on uint8 frames, bit-exact to numpy's fp32 arithmetic (the 256
+    possible results are computed by numpy itself and looked up on the device)."""
+    import numpy as np
+    _chk(x_u8, out)
+    assert x_u8.dtype == torch.uint8
+    key = str(x_u8.device)
+    if key not in _U8_LUT:
+        lut = np.arange(256, dtype=np.float32)
+        lut = lut / 255.0
+        lut -= 0.5
+        lut *= 2.0
+        _U8_LUT[key] = torch.from_numpy(lut.astype(np.float32)).to(x_u8.device)
+    if out is None:
+        out = torch.empty(x_u8.shape, device=x_u8.device, dtype=torch.float32)
+    lib().normalize_u8(_p(x_u8), _p(_U8_LUT[key]), _p(out), x_u8.numel(), _s())
+    return out
 
 
 def cast_f32_to_bf16(src, dst):

@@ -131,6 +131,46 @@ def build_Y_from_rows(list_of_rows, pred_grid=[6, 6, 2]):
     return norm_Y(Y).astype(cf.dtype), pred_shape
 
 
+def pack_annotations(list_of_arrs):
+    """[[8-variable antinode rows] per image] (parse_meta_file / parse_meta_rows output) -> (ann [n, max_obj, 8] float64,
+    counts [n] int32): the device-side input of ops.assign_grid / ops.yolo_ellipse_loss_ann."""
+    n = len(list_of_arrs)
+    max_obj = max([len(a) for a in list_of_arrs] + [1])
+    ann = np.zeros((n, max_obj, cf.vars_per_pred), np.float64)
+    counts = np.zeros(n, np.int32)
+    for i, a in enumerate(list_of_arrs):
+        counts[i] = len(a)
+        if len(a):
+            ann[i, :len(a)] = np.asarray(a, np.float64).reshape(-1, cf.vars_per_pred)
+    return ann, counts
+
+
+def grid_tables(pred_shape, device):
+    """(defaults, means, ranges) of setup_means_and_ranges as flat fp32 device tensors."""
+    import torch
+    _, _, _, _, _, _, defaults = setup_means_and_ranges(pred_shape)
+    mk = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float32).ravel()).to(device)  # noqa: E731
+    return mk(defaults), mk(means), mk(ranges)
+
+
+def build_Y_device(list_of_arrs, pred_grid=[6, 6, 2], device="cuda"):
+    """true_to_pred_grid + norm_Y for a whole dataset in ONE kernel launch (csrc/loss.cu assign_grid_kernel; the
+    reference loops over images and antinodes in Python, spnet/utils.py:191-244,312-318). Returns the normalised
+    targets as a CUDA tensor [n, prod(pred_shape)] (what SPNetModel.fit takes for a device-resident run) and
+    pred_shape. Raises AssertionError exactly where the reference's `assert slot < preds_per_cell` (:240) would."""
+    import torch
+    from . import ops
+    pred_shape = np.array([pred_grid[0], pred_grid[1], pred_grid[2], cf.vars_per_pred], dtype=int)
+    ann, counts = pack_annotations(list_of_arrs)
+    defaults, mean_t, range_t = grid_tables(pred_shape, device)
+    Y, err = ops.assign_grid(torch.from_numpy(ann).to(device), torch.from_numpy(counts).to(device), defaults, mean_t, range_t,
+                             int(pred_grid[0]), int(pred_grid[1]), int(pred_grid[2]))
+    bad = torch.nonzero(err).flatten()
+    assert bad.numel() == 0, "true_to_pred_grid: image %d offers more than %d antinodes to one grid cell (antinode %d)" % (
+        int(bad[0]), int(pred_grid[2]), int(err[bad[0]]) - 1)
+    return Y, pred_shape
+
+
 def build_Y(total_load, meta_file_list, img_file_list, pred_grid=[6, 6, 2], set_means_ranges=False):
     pred_shape = np.array([pred_grid[0], pred_grid[1], pred_grid[2], cf.vars_per_pred], dtype=int)
     Y = np.zeros([total_load, int(np.prod(pred_shape))], dtype=cf.dtype)
@@ -145,11 +185,15 @@ def build_Y(total_load, meta_file_list, img_file_list, pred_grid=[6, 6, 2], set_
 
 # ------------------------------------------------------------------ images
 def _load_one(args):
-    filename, force_dim, grayscale = args
+    filename, force_dim, grayscale = args[:3]
+    raw_u8 = len(args) > 3 and args[3]
     from PIL import Image
     img = Image.open(filename).convert("RGB")
     if force_dim is not None:
         img = img.resize((force_dim, force_dim), Image.LANCZOS)
+    if raw_u8:  # pixel values as decoded (and resized) by PIL: the normalisation below then runs on the device
+        arr = np.asarray(img, dtype=np.uint8)
+        return arr[:, :, 0:1] if grayscale else arr
     arr = np.asarray(img, dtype=np.float32)
     arr = arr / 255.0
     arr -= 0.5
@@ -157,21 +201,23 @@ def _load_one(args):
     return arr[:, :, 0:1] if grayscale else arr
 
 
-def build_X(total_load, img_file_list, force_dim=224, grayscale=False):
+def build_X(total_load, img_file_list, force_dim=224, grayscale=False, raw_u8=False):
     """Images -> X float32 NHWC in [-1,1] (spnet/utils.py:325-421): PIL decode, optional LANCZOS
-    resize to a force_dim square, (v/255 - 0.5)*2, channel 0 only when grayscale."""
+    resize to a force_dim square, (v/255 - 0.5)*2, channel 0 only when grayscale.
+    raw_u8 (B200 build only): return the uint8 pixel values instead; SPNetModel.predict / the engine apply the
+    same normalisation on the device, bit for bit, and a quarter of the bytes cross PCIe."""
     print("      Reading images and assigning as input X...")
-    first = _load_one((img_file_list[0], force_dim, grayscale))
+    first = _load_one((img_file_list[0], force_dim, grayscale, raw_u8))
     img_dims = first.shape if not grayscale else (first.shape[0], first.shape[1], 3)
-    X = np.zeros((total_load,) + first.shape, dtype=cf.dtype)
+    X = np.zeros((total_load,) + first.shape, dtype=np.uint8 if raw_u8 else cf.dtype)
     nproc = os.cpu_count() or 1
     with ThreadPoolExecutor(nproc) as ex:
-        for i, arr in enumerate(ex.map(_load_one, [(f, force_dim, grayscale) for f in img_file_list[:total_load]])):
+        for i, arr in enumerate(ex.map(_load_one, [(f, force_dim, grayscale, raw_u8) for f in img_file_list[:total_load]])):
             X[i] = arr
     return X, img_dims
 
 
-def stream_X(img_file_list, chunk, force_dim=224, grayscale=False):
+def stream_X(img_file_list, chunk, force_dim=224, grayscale=False, raw_u8=False):
     """Generator over (start, X_chunk): the frames of build_X in chunks of `chunk` files, the NEXT chunk being
     decoded by the worker threads while the caller consumes the current one (at
     B200 inference rates PIL decode, not the network, bounds predict_spnet over tens of thousands of frames, and
@@ -182,7 +228,8 @@ def stream_X(img_file_list, chunk, force_dim=224, grayscale=False):
     def decode(lo):
         files = img_file_list[lo:lo + chunk]
         with ThreadPoolExecutor(nproc) as ex:
-            return np.stack(list(ex.map(_load_one, [(f, force_dim, grayscale) for f in files]))).astype(cf.dtype)
+            return np.stack(list(ex.map(_load_one, [(f, force_dim, grayscale, raw_u8) for f in files]))).astype(
+                np.uint8 if raw_u8 else cf.dtype)
 
     with ThreadPoolExecutor(1) as bg:
         fut = bg.submit(decode, 0) if n else None

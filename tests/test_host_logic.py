@@ -209,24 +209,34 @@ lo, hi = multi_gpu.batch_slice(10, rank, world)      # get_slice: size = shape[0
 assert (lo, hi) == (rank * 5, rank * 5 + 5)
 class FakeEngine:
     device = "cpu"
+    lowp = False                         # fp32 engine -> fp32 communication
     def __init__(self, tail_key):
-        self.offsets = OrderedDict([("FinalOutput/kernel", (0, 20, (4, 5))), ("entry", (24, 8, (8,))), ("middle", (32, 16, (16,)))])
+        self.offsets = OrderedDict([("FinalOutput/kernel", (0, 24, (4, 6))), ("entry", (24, 8, (8,))), ("middle", (32, 16, (16,)))])
         self.tail_param_key = tail_key
         self.grads = torch.arange(48, dtype=torch.float32) * (rank + 1)
-        self.scale = None
-    def optimizer_step(self, grad_scale=1.0):
-        self.scale = grad_scale
+        self.steps = []
+    def optimizer_step(self, grad_scale=1.0, lo=0, hi=None, g_bf16=None):
+        # the bucket's gradients must already be the sum over the ranks when its update is launched
+        expect = torch.arange(lo, hi, dtype=torch.float32) * sum(r + 1 for r in range(world))
+        assert torch.equal(self.grads[lo:hi], expect), (lo, hi)
+        assert g_bf16 is None
+        self.steps.append((lo, hi, grad_scale))
 for tail_key in ("middle", None):        # with and without a tail bucket (Xception / MobileNet engines)
     eng = FakeEngine(tail_key)
     hook = multi_gpu.attach_data_parallel(eng)
-    assert hook.buckets["head"].numel() == 24 and hook.buckets["tail"].numel() == (16 if tail_key else 0)
-    assert hook.rest.numel() == (8 if tail_key else 24)
+    assert hook.ranges["head"] == (0, 24) and hook.ranges["tail"] == ((32, 48) if tail_key else (48, 48))
+    assert hook.ranges["rest"] == ((24, 32) if tail_key else (24, 48))
+    hook.step_begin(eng)
     hook.bucket_ready(eng, "head")       # on CPU the buckets are reduced in the final call
     hook.bucket_ready(eng, "tail")
     hook(eng)
     expect = torch.arange(48, dtype=torch.float32) * sum(r + 1 for r in range(world))
     assert torch.equal(eng.grads, expect), (eng.grads, expect)
-    assert eng.scale == 1.0 / world
+    # every parameter updated exactly once, each bucket with the 1/world average
+    covered = sorted((lo, hi) for lo, hi, _ in eng.steps)
+    assert covered == sorted(r for r in hook.ranges.values() if r[1] > r[0]), covered
+    assert all(sc == 1.0 / world for _, _, sc in eng.steps)
+    assert eng.skip_default_optimizer
 dist.barrier()
 if rank == 0:
     print("DP_OK")
@@ -281,3 +291,127 @@ def test_every_exported_entry_point_is_documented():
         expanded.update(n for n in parse_header() if n.startswith(stem))
     missing = sorted(n for n in parse_header() if n not in expanded)
     assert not missing, missing
+
+
+# ------------------------------------------------------------------ round 2: freeze list, checkpoints, sharded CSV merge
+def test_keras_layer_order_and_freeze_cut():
+    """base_model.layers[:int(144 * freeze_fac)].trainable = False (spnet/models.py:361-372) on the Keras layer order:
+    144 layers for Xception-SPNet (paper/run_logs/log_DatasetA_*.txt:95), the 75 % cut ends with block 10."""
+    from spnet_b200 import arch
+    L = arch.xception_keras_layers()
+    assert len(L) == 144 and len(set(L)) == 144 and L[0] == "input_1" and L[12] == "dropout_1"
+    assert L[19:28] == ["block2_sepconv1", "block2_sepconv1_bn", "block2_sepconv2_act", "block2_sepconv2", "block2_sepconv2_bn",
+                        "conv2d_4", "block2_pool", "batch_normalization_4", "add_2"]
+    spec = arch.param_spec(331, 331)
+    with_weights = set(k.split("/")[0] for k, _, _, _ in spec)
+    assert with_weights - {"FinalOutput"} <= set(L)
+    names, nf, nt = arch.frozen_layer_names("Xception", 0.75, spec)
+    assert (nf, nt) == (108, 144) and names[-1] == "block10_sepconv3_bn" and "block11_sepconv1" not in names
+    assert arch.frozen_layer_names("Xception", 0.0, spec)[0] == []
+    assert set(arch.frozen_layer_names("Xception", 1.0, spec)[0]) == with_weights - {"FinalOutput"}
+    assert len(arch.mobilenet_keras_layers()) == 94
+    import spnet.config as cf
+    from spnet import models
+    cf.basemodel = "Xception"
+    m = models.create_model_functional(np.zeros((1, 331, 331, 1), np.float32), 576, freeze_fac=0.75)
+    tr, ntr = m._count_trainable()
+    assert tr + ntr == 50353481 and tr == 39508112
+    m0 = models.create_model_functional(np.zeros((1, 331, 331, 1), np.float32), 576, freeze_fac=0.0)
+    assert m0._count_trainable() == (50298935, 54546)   # log_DatasetA_*.txt:100-101
+
+
+@pytest.mark.parametrize("backbone,hw", [("Xception", (96, 128)), ("MobileNet", (96, 128)), ("InceptionResNetV2", (200, 260))])
+def test_full_model_save_and_load_model_round_trip(tmp_path, backbone, hw):
+    """spnet.model / full_model.h5 (ParallelCheckpointCallback, train_spnet.py:149): load_model rebuilds the backbone
+    that was saved, with its weights and the loss type it was compiled with."""
+    import spnet.config as cf
+    from spnet import models
+    cf.basemodel, old_loss = backbone, cf.loss_type
+    try:
+        cf.loss_type = "hybrid"
+        m = models.create_model_functional(np.zeros((1,) + hw + (1,), np.float32), 576, freeze_fac=0.0, quick_setup=True)
+        path = str(tmp_path / "spnet.model")
+        m.save(path)
+        cf.loss_type = "same"
+        m2 = models.load_model(path)
+        assert m2.backbone == backbone and cf.loss_type == "hybrid" and (m2.H, m2.W) == hw
+        for a, b in zip(m.get_weights(), m2.get_weights()):
+            np.testing.assert_array_equal(a, b)
+        wrong = models.SPNetModel((hw[0] * 2, hw[1], 1), backbone=backbone, quick_setup=True)
+        with pytest.raises(ValueError):
+            wrong.set_weights(m.get_weights())
+    finally:
+        cf.basemodel, cf.loss_type = "Xception", old_loss
+
+
+def test_checkpoint_callback_saves_like_the_reference(tmp_path):
+    """spnet/callbacks.py:35-41: save when save_every == 1, or after the 5th, 10th, ... epoch for save_every = 5; paths
+    are dir + '/' + filepath and dir + '/spnet.model'."""
+    from spnet import callbacks
+
+    class M:
+        saved = []
+
+        def save_weights(self, p):
+            self.saved.append(("w", p))
+
+        def save(self, p):
+            self.saved.append(("m", p))
+
+    m = M()
+    ck = callbacks.ParallelCheckpointCallback(m, filepath="weights.hdf5", save_every=5, dir=str(tmp_path / "logs"))
+    ck.model = None
+    hits = []
+    for epoch in range(12):
+        n0 = len(m.saved)
+        ck.on_epoch_end(epoch)
+        if len(m.saved) > n0:
+            hits.append(epoch)
+    assert hits == [4, 9]
+    assert m.saved[0] == ("w", str(tmp_path / "logs") + "/weights.hdf5") and m.saved[1] == ("m", str(tmp_path / "logs") + "/spnet.model")
+    m.saved.clear()
+    ck1 = callbacks.ParallelCheckpointCallback(m, save_every=1, dir=str(tmp_path))
+    ck1.model = None
+    for epoch in range(3):
+        ck1.on_epoch_end(epoch)
+    assert len(m.saved) == 6
+    # device-augmentation epoch keys: no two (epoch, frame) pairs of neighbouring epochs share a key
+    G = 0x9E3779B97F4A7C15
+    keys = set()
+    for e in range(20):
+        sd = callbacks._epoch_seed(1234, e) & (2 ** 63 - 1)
+        for f in range(50):
+            keys.add((sd + G * (f + 1)) & 0xFFFFFFFFFFFFFFFF)
+    assert len(keys) == 20 * 50
+
+
+def test_sharded_csv_parts_merge_in_rank_order(tmp_path, monkeypatch):
+    import predict_spnet
+    out = str(tmp_path / "hawley_spnet.csv")
+    monkeypatch.setenv("MASTER_PORT", "12345")
+    for r, text in ((2, "c\n"), (1, "b1\nb2\n"), (0, "a\n")):
+        with open(out + ".part%d" % r, "w") as f:
+            f.write(text)
+    predict_spnet.merge_csv_parts(out, 2, 3)
+    predict_spnet.merge_csv_parts(out, 1, 3)
+    assert not os.path.exists(out)
+    predict_spnet.merge_csv_parts(out, 0, 3)
+    assert open(out).read() == "a\nb1\nb2\nc\n"
+    assert os.listdir(str(tmp_path)) == ["hawley_spnet.csv"]
+
+
+def test_stored_oracle_is_the_plain_oracle_without_rounding():
+    """oracle/xception_torch.py Oracle*Stored(storage='fp32') restates the engine's storage points without rounding: it
+    must compute what the plain oracle computes (inference mode: to fp32 rounding)."""
+    import torch
+    from oracle import xception_torch as xt
+    from spnet_b200.selfcheck import make_case
+    for name, plain, stored, (H, W) in (("Xception", xt.OracleSPNet, xt.OracleSPNetStored, (96, 128)),
+                                        ("MobileNet", xt.OracleMobileNetSPNet, xt.OracleMobileNetSPNetStored, (96, 128))):
+        w, x, yt = make_case(H, W, 2, seed=3, backbone=name)
+        with torch.no_grad():
+            ya = plain(w, H, W).forward(x, training=False)
+            yb = stored(w, H, W, storage="fp32").forward(x, training=False)
+            yc = stored(w, H, W, storage="bf16").forward(x, training=False)
+        assert float((ya - yb).abs().max() / ya.abs().max()) < 2e-6
+        assert 1e-4 < float((ya - yc).norm() / ya.norm()) < 2e-2   # bf16 storage is visible, and small in inference mode

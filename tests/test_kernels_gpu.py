@@ -187,7 +187,7 @@ def test_dwconv_bwd_fused(dtype, shape, mode):
         b = torch.randn(C, device=dev()) * 0.2
         mean = torch.randn(C, device=dev()) * 0.1
         rstd = torch.rand(C, device=dev()) + 0.5
-        stats = torch.zeros(2 * C, device=dev(), dtype=torch.float64)
+        stats = ops.stats_alloc(2 * C, dev())
     elif mode == "relu_add":
         add = torch.randn(shape, device=dev()).to(dtype)
     else:
@@ -204,8 +204,9 @@ def test_dwconv_bwd_fused(dtype, shape, mode):
     if stats is not None:
         gq = gin.double()
         xh = (x.double() - mean.double()) * rstd.double()
-        torch.testing.assert_close(stats[:C], gq.sum((0, 1, 2)), rtol=1e-4, atol=1e-3)
-        torch.testing.assert_close(stats[C:], (gq * xh).sum((0, 1, 2)), rtol=1e-4, atol=1e-3)
+        sv = ops.stats_values(stats).to(gq.device)
+        torch.testing.assert_close(sv[:C], gq.sum((0, 1, 2)), rtol=1e-4, atol=1e-3)
+        torch.testing.assert_close(sv[C:], (gq * xh).sum((0, 1, 2)), rtol=1e-4, atol=1e-3)
     if add is not None:
         ref = ref + add.float()
     if sadd is not None:
@@ -230,10 +231,11 @@ def test_subsample_scatter_colstats(dtype, off):
     ref = torch.zeros_like(x)
     ref[:, off[0]::2, off[1]::2, :] = y
     torch.testing.assert_close(back, ref)
-    st = torch.zeros(2 * C, device=dev(), dtype=torch.float64)
+    st = ops.stats_alloc(2 * C, dev())
     ops.colstats(x, st)
-    torch.testing.assert_close(st[:C], x.double().sum((0, 1, 2)), rtol=1e-5, atol=1e-4)
-    torch.testing.assert_close(st[C:], (x.double() ** 2).sum((0, 1, 2)), rtol=1e-5, atol=1e-4)
+    sv = ops.stats_values(st).to(x.device)
+    torch.testing.assert_close(sv[:C], x.double().sum((0, 1, 2)), rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(sv[C:], (x.double() ** 2).sum((0, 1, 2)), rtol=1e-5, atol=1e-4)
 
 
 # ------------------------------------------------------------------ GEMM
@@ -248,14 +250,15 @@ def _gemm_case(M, N, K, a_mn, b_mn, out_mode, splits, stats, dtype):
     B_st = B_l.contiguous() if b_mn else B_l.t().contiguous()          # [K,N] or [N,K]
     out_dtype = dtype if out_mode == ops.OUT_T else torch.float32
     D = torch.zeros(M, N, device=dev(), dtype=out_dtype)
-    cs = torch.zeros(2 * N, device=dev(), dtype=torch.float64) if stats else None
+    cs = ops.stats_alloc(2 * N, dev()) if stats else None
     ops.gemm(A_st, a_mn, B_st, b_mn, D, M, N, K, out_mode=out_mode, splits=splits, colstats=cs)
     t = dict(rtol=2e-2, atol=2e-2 * K ** 0.5) if out_dtype == torch.bfloat16 else dict(rtol=1e-3, atol=1e-3 * K ** 0.5)
     torch.testing.assert_close(D.float(), ref, **t)
     if stats:
         Dd = D.double()
-        torch.testing.assert_close(cs[:N], Dd.sum(0), rtol=1e-4, atol=1e-2)
-        torch.testing.assert_close(cs[N:], (Dd * Dd).sum(0), rtol=1e-4, atol=1e-2)
+        cv = ops.stats_values(cs).to(Dd.device)
+        torch.testing.assert_close(cv[:N], Dd.sum(0), rtol=1e-4, atol=1e-2)
+        torch.testing.assert_close(cv[N:], (Dd * Dd).sum(0), rtol=1e-4, atol=1e-2)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
@@ -287,12 +290,12 @@ def test_bn_train_fwd_bwd(dtype):
     gamma = torch.rand(C, device=dev()) + 0.5
     beta = torch.randn(C, device=dev()) * 0.1
     zf = z.double()
-    stats = torch.cat([zf.sum(0), (zf * zf).sum(0)]).contiguous()
+    stats = ops.stats_from_values(torch.cat([zf.sum(0), (zf * zf).sum(0)]), dev())
     a, b, mean, rstd = (torch.empty(C, device=dev()) for _ in range(4))
     mm = torch.zeros(C, device=dev())
     mv = torch.ones(C, device=dev())
     ops.bn_finalize(stats, rows, gamma, beta, a, b, mean, rstd, mm, mv)
-    assert float(stats.abs().max()) == 0.0
+    assert int(stats.abs().max()) == 0
     zr = z.float().requires_grad_(True)
     gr = gamma.clone().requires_grad_(True)
     br = beta.clone().requires_grad_(True)
@@ -308,7 +311,7 @@ def test_bn_train_fwd_bwd(dtype):
     g = torch.randn(rows, C, device=dev()).to(dtype)
     torch.relu(y).backward(g.float())
     gy = g.clone()
-    bstats = torch.zeros(2 * C, device=dev(), dtype=torch.float64)
+    bstats = ops.stats_alloc(2 * C, dev())
     ops.bn_bwd_reduce(gy, z, mean, rstd, bstats, relu_a=a, relu_b=b, act=1)
     dgamma, dbeta, c1, c2 = (torch.empty(C, device=dev()) for _ in range(4))
     ops.bn_bwd_finalize(bstats, rows, dgamma, dbeta, c1, c2)
@@ -378,7 +381,7 @@ def test_stem_and_block1_convs(dtype, hw):
     H2, W2 = H // 2, W // 2
     p1 = torch.empty(B, H2, W2, 3, device=dev(), dtype=dtype)
     s0 = torch.empty(B, H2, W2, 1, device=dev(), dtype=dtype)
-    st = torch.zeros(6, device=dev(), dtype=torch.float64)
+    st = ops.stats_alloc(6, dev())
     ops.conv_small_fwd(0, x0, k4, p1, skip=s0, stats=st)
     k3r = k3.clone().requires_grad_(True)
     conv = F.conv2d(nchw(x0), k3r.permute(3, 2, 0, 1), padding=1)
@@ -386,8 +389,8 @@ def test_stem_and_block1_convs(dtype, hw):
     ref_s0 = nhwc(F.avg_pool2d(nchw(x0), 2))
     torch.testing.assert_close(p1.float(), ref_p1.detach(), **tol(dtype))
     torch.testing.assert_close(s0.float(), ref_s0, **tol(dtype))
-    torch.testing.assert_close(st[:3], p1.double().sum((0, 1, 2)), rtol=1e-5, atol=1e-3)
-    torch.testing.assert_close(st[3:], (p1.double() ** 2).sum((0, 1, 2)), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(ops.stats_values(st).to(p1.device)[:3], p1.double().sum((0, 1, 2)), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(ops.stats_values(st).to(p1.device)[3:], (p1.double() ** 2).sum((0, 1, 2)), rtol=1e-5, atol=1e-3)
     # conv1 weight gradient through the avgpool fold
     g1 = torch.randn(B, H2, W2, 3, device=dev()).to(dtype)
     ref_p1.backward(g1.float())
@@ -403,7 +406,7 @@ def test_stem_and_block1_convs(dtype, hw):
     b = torch.randn(3, device=dev()) * 0.3
     w33 = (torch.randn(3, 3, 3, 3, device=dev()) * 0.4)
     c2 = torch.empty(B, H2, W2, 3, device=dev(), dtype=dtype)
-    st2 = torch.zeros(6, device=dev(), dtype=torch.float64)
+    st2 = ops.stats_alloc(6, dev())
     ops.conv_small_fwd(1, p1, w33, c2, in_a=a, in_b=b, act=2, stats=st2)
     pr = p1.float().requires_grad_(True)
     wr = w33.clone().requires_grad_(True)
@@ -411,7 +414,7 @@ def test_stem_and_block1_convs(dtype, hw):
     act_leaf = act_in.detach().requires_grad_(True)
     ref_c2 = nhwc(F.conv2d(nchw(act_leaf), wr.permute(3, 2, 0, 1), padding=1))
     torch.testing.assert_close(c2.float(), ref_c2.detach(), **tol(dtype))
-    torch.testing.assert_close(st2[:3], c2.double().sum((0, 1, 2)), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(ops.stats_values(st2).to(c2.device)[:3], c2.double().sum((0, 1, 2)), rtol=1e-5, atol=1e-3)
     g2 = torch.randn(B, H2, W2, 3, device=dev()).to(dtype)
     ref_c2.backward(g2.float())
     dw = torch.zeros(3, 3, 3, 3, device=dev())
@@ -445,13 +448,13 @@ def test_stem_and_block1_convs(dtype, hw):
     w1 = torch.randn(3, 3, 3, 32, device=dev()) * 0.3
     OH, OW = (H2 - 3) // 2 + 1, (W2 - 3) // 2 + 1
     z11 = torch.empty(B, OH, OW, 32, device=dev(), dtype=dtype)
-    st3 = torch.zeros(64, device=dev(), dtype=torch.float64)
+    st3 = ops.stats_alloc(64, dev())
     ops.conv_small_fwd(2, d, w1, z11, stats=st3)
     dr = d.float().requires_grad_(True)
     w1r = w1.clone().requires_grad_(True)
     ref_z = nhwc(F.conv2d(nchw(dr), w1r.permute(3, 2, 0, 1), stride=2))
     torch.testing.assert_close(z11.float(), ref_z.detach(), **tol(dtype))
-    torch.testing.assert_close(st3[:32], z11.double().sum((0, 1, 2)), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(ops.stats_values(st3).to(z11.device)[:32], z11.double().sum((0, 1, 2)), rtol=1e-5, atol=1e-3)
     gz = torch.randn(B, OH, OW, 32, device=dev()).to(dtype)
     ref_z.backward(gz.float())
     dw1 = torch.zeros(3, 3, 3, 32, device=dev())
@@ -467,7 +470,7 @@ def test_stem_and_block1_convs(dtype, hw):
     var = c2.float().var((0, 1, 2), unbiased=False)
     rstd = 1 / torch.sqrt(var + 1e-3)
     gam = torch.rand(3, device=dev()) + 0.5
-    bst = torch.zeros(6, device=dev(), dtype=torch.float64)
+    bst = ops.stats_alloc(6, dev())
     ops.bn3_bwd_reduce(gd, c2, mean, rstd, bst)
     c1, cc2, dg, db = (torch.empty(3, device=dev()) for _ in range(4))
     n = B * H2 * W2
@@ -525,9 +528,26 @@ def test_adam_keras_and_helpers():
     torch.testing.assert_close(m.double(), mr, rtol=1e-5, atol=1e-8)
     torch.testing.assert_close(v.double(), vr, rtol=1e-5, atol=1e-9)
     torch.testing.assert_close(pb, p.to(torch.bfloat16))
+    acc = ops.stats_alloc(1, dev())
     out = torch.zeros(1, device=dev())
-    ops.sumsq(p, n_l2, 1e-4, out)
+    ops.sumsq(p, n_l2, 1e-4, acc)
+    ops.acc_to_f32(acc, out)
     torch.testing.assert_close(out[0].double(), 1e-4 * (p[:n_l2].double() ** 2).sum(), rtol=1e-4, atol=0)
+    assert int(acc.abs().max()) == 0  # acc_to_f32 clears the accumulator for the next step
+    # frozen mask (one byte per 8 parameters) and bf16 gradients
+    p2, m2, v2 = p.clone(), m.clone(), v.clone()
+    mask = torch.zeros(n // 8, device=dev(), dtype=torch.uint8)
+    mask[100:300] = 1
+    gb = g.to(torch.bfloat16)
+    ops.adam_keras_step(p2, g, m2, v2, lr_dev, n_l2=n_l2, l2=1e-4, frozen8=mask, g_bf16=gb)
+    fr = mask.repeat_interleave(8).bool()
+    assert torch.equal(p2[fr], p[fr]) and torch.equal(m2[fr], m[fr]) and torch.equal(v2[fr], v[fr])
+    gg2 = gb.double()
+    gg2[:n_l2] += 2e-4 * p.double()[:n_l2]
+    mr2 = 0.9 * m.double() + 0.1 * gg2
+    vr2 = 0.999 * v.double() + 0.001 * gg2 * gg2
+    pr2 = p.double() - lr_t * mr2 / (vr2.sqrt() + 1e-7)
+    torch.testing.assert_close(p2.double()[~fr], pr2[~fr], rtol=1e-5, atol=1e-7)
     bias = torch.randn(576, device=dev())
     y = torch.empty(5, 576, device=dev())
     ops.bias_fill(bias, y)
@@ -621,12 +641,13 @@ def test_conv_tc_fwd_and_stats(case):
     x, wt, OH, OW, pt, pl = _conv_tc_inputs(case)
     ref = nhwc(_conv_ref(x, wt, pad, KH, KW))
     y = torch.full((B, OH, OW, Cout), float("nan"), device=dev(), dtype=torch.bfloat16)
-    stats = torch.zeros(2 * Cout, device=dev(), dtype=torch.float64)
+    stats = ops.stats_alloc(2 * Cout, dev())
     ops.conv_tc_fwd(x, wt, y, pt, pl, colstats=stats)
     torch.testing.assert_close(y.float(), ref, rtol=2e-2, atol=2e-2)
     yf = y.double().view(-1, Cout)
-    torch.testing.assert_close(stats[:Cout], yf.sum(0), rtol=1e-5, atol=1e-3)
-    torch.testing.assert_close(stats[Cout:], (yf * yf).sum(0), rtol=1e-5, atol=1e-3)
+    sv = ops.stats_values(stats).to(yf.device)
+    torch.testing.assert_close(sv[:Cout], yf.sum(0), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(sv[Cout:], (yf * yf).sum(0), rtol=1e-5, atol=1e-3)
 
 
 def test_conv_tc_fwd_channel_slices():

@@ -36,8 +36,7 @@ def test_predict_cli_path_writes_reference_format_csv(tmp_path):
         assert os.path.basename(f) in text
     assert os.path.exists(log_dir + "steelpan_pred_00000.png")
     # one set of network outputs through (a) device decode + product CSV writer, (b) the oracle's row
-    # formatter, (c) the host numpy decode. (The Dense head accumulates split-K partials with fp32 atomics,
-    # so two predict() calls may differ in the last bits: every path below consumes the SAME Y.)
+    # formatter, (c) the host numpy decode
     Xp, _ = utils.build_X(n, files, force_dim=None, grayscale=True)
     Y = m2.predict(Xp, batch_size=2)
     utils.setup_means_and_ranges([6, 6, 2, 8])
@@ -97,7 +96,7 @@ def test_mobilenet_backbone_through_the_model_surface(tmp_path):
         y1 = model.predict(X[:8], batch_size=8)
         y2 = again.predict(X[:8], batch_size=8)
         assert y1.shape == (8, 576) and np.isfinite(y1).all()
-        np.testing.assert_allclose(y1, y2, rtol=2e-2, atol=2e-2)  # split-K atomics reorder the Dense sums
+        np.testing.assert_array_equal(y1, y2)  # same weights -> bit-identical predictions (fixed-order split-K head)
         cf.basemodel = "NASNetLarge"
         with pytest.raises((NotImplementedError, AttributeError)):
             models.setup_model(X, 576, try_checkpoint=False, freeze_fac=0.0)
@@ -180,8 +179,7 @@ def test_evaluate_cli_path(tmp_path, capsys):
 
 
 def test_predict_streaming_matches_whole_set(tmp_path):
-    """predict_network(stream_chunk=...) = the same CSV as loading every frame first (up to the last bits of the
-    Dense head's split-K accumulation, which can move a rounded integer by one)."""
+    """predict_network(stream_chunk=...) = the same CSV TEXT as loading every frame first."""
     from PIL import Image
     import spnet.config as cf
     from spnet import models
@@ -200,14 +198,86 @@ def test_predict_streaming_matches_whole_set(tmp_path):
     predict_spnet.predict_network(model=model, datapath=str(tmp_path), log_dir=a_dir, batch_size=2, draw_images=False)
     predict_spnet.predict_network(model=model, datapath=str(tmp_path), log_dir=b_dir, batch_size=2, draw_images=False,
                                   stream_chunk=4)
-    a = open(a_dir + "hawley_spnet.csv").read().strip().splitlines()
-    b = open(b_dir + "hawley_spnet.csv").read().strip().splitlines()
+    # raw_u8 (default: frames cross PCIe as bytes, normalised on the device) against the reference's host-side
+    # normalisation, and a second whole-set run: the forward pass has a fixed summation order everywhere, so the
+    # three CSV files are IDENTICAL TEXT
+    c_dir = str(tmp_path / "hostnorm") + "/"
+    predict_spnet.predict_network(model=model, datapath=str(tmp_path), log_dir=c_dir, batch_size=2, draw_images=False,
+                                  raw_u8=False)
+    d_dir = str(tmp_path / "again") + "/"
+    predict_spnet.predict_network(model=model, datapath=str(tmp_path), log_dir=d_dir, batch_size=4, draw_images=False)
+    a = open(a_dir + "hawley_spnet.csv").read()
     cf.model_type = "monolithic"
-    assert len(a) == len(b) and a[0] == b[0]  # header + one row per detection (or per empty frame)
-    for x, y in zip(a[1:], b[1:]):
-        fx, fy = x.split(","), y.split(",")
-        assert fx[2] == fy[2]  # file name
-        for k in (0, 1, 4, 5):  # cx, cy, a, b: rounded integers
-            assert abs(int(fx[k]) - int(fy[k])) <= 1
-        for k in (3, 6):  # rings, angle: floats printed at full precision
-            assert abs(float(fx[k]) - float(fy[k])) <= 1e-3 * max(1.0, abs(float(fx[k])))
+    assert len(a.strip().splitlines()) >= n
+    assert a == open(b_dir + "hawley_spnet.csv").read()
+    assert a == open(c_dir + "hawley_spnet.csv").read()
+    # a different batch size changes nothing either: inference-mode rows are independent of their batch mates
+    assert a == open(d_dir + "hawley_spnet.csv").read()
+
+
+def test_predict_graph_u8_pinned_and_device_inputs_agree():
+    """SPNetModel.predict: numpy fp32, numpy uint8, pinned torch uint8 and CUDA-resident inputs give bit-identical
+    outputs; ragged last batch; graph replay == eager forward."""
+    import torch
+    import spnet.config as cf
+    from spnet import models
+    from spnet_b200 import fake_espi
+    cf.compute_dtype = "bf16"
+    n = 7
+    Xu, _, _ = fake_espi.make_frames_u8(n, base_seed=900)
+    Xf = Xu.astype(np.float32)
+    Xf = Xf / 255.0
+    Xf -= 0.5
+    Xf *= 2.0
+    model, _ = models.setup_model(Xf[:2], 576, try_checkpoint=False, freeze_fac=0.0, quick_setup=True)
+    y_f = model.predict(Xf, batch_size=3)
+    y_u = model.predict(Xu, batch_size=3)
+    y_p = model.predict(torch.from_numpy(Xu).pin_memory(), batch_size=3)
+    y_d = model.predict(torch.from_numpy(Xu).cuda(), batch_size=3)
+    np.testing.assert_array_equal(y_f, y_u)
+    np.testing.assert_array_equal(y_f, y_p)
+    np.testing.assert_array_equal(y_f, y_d)
+    eng = model._engine(3, False)
+    assert getattr(eng, "fwd_graph", None) is not None
+    eng.load_batch(Xf[:3])
+    eager = eng.forward(training=False).cpu().numpy()
+    np.testing.assert_array_equal(eager, y_f[:3])
+
+
+def test_predict_cli_sharded_over_ranks_writes_the_same_csv(tmp_path):
+    """`torchrun --nproc-per-node 2 predict_spnet.py`: the sorted file list is cut into contiguous shards, every rank
+    predicts its shard (no collective on the data path), rank 0 concatenates the per-rank CSV parts in rank order ->
+    the same hawley_spnet.csv, byte for byte, as the single-process run (7 frames: uneven shards)."""
+    import subprocess
+    import sys
+    from PIL import Image
+    import spnet.config as cf
+    from spnet import models
+    from spnet_b200 import fake_espi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    data = tmp_path / "frames"
+    data.mkdir()
+    n = 7
+    for i in range(n):
+        img, _ = fake_espi.make_frame(700 + i)
+        Image.fromarray(img).save(data / ("steelpan_%07d.png" % i))
+    cf.model_type = "big"
+    cf.compute_dtype = "bf16"
+    X = np.zeros((2, 384, 512, 1), np.float32)
+    model, _ = models.setup_model(X, 576, try_checkpoint=False, freeze_fac=0.0, quick_setup=True)
+    wpath = str(tmp_path / "spnet.model")
+    model.save(wpath)
+    cf.model_type = "monolithic"
+    common = ["-w", wpath, "-d", str(data), "-b", "1", "--no-png", "--model_type", "big", "--dtype", "bf16"]
+    env = dict(os.environ, PYTHONPATH=root)
+    one = subprocess.run([sys.executable, os.path.join(root, "predict_spnet.py"), "-l", str(tmp_path / "one") + "/"] + common,
+                         capture_output=True, text=True, env=env, timeout=900)
+    assert one.returncode == 0, one.stdout[-2000:] + one.stderr[-2000:]
+    two = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29571", os.path.join(root, "predict_spnet.py"), "-l",
+                          str(tmp_path / "two") + "/"] + common, capture_output=True, text=True, env=env, timeout=900)
+    assert two.returncode == 0, two.stdout[-2000:] + two.stderr[-2000:]
+    a = open(str(tmp_path / "one") + "/hawley_spnet.csv").read()
+    b = open(str(tmp_path / "two") + "/hawley_spnet.csv").read()
+    assert a == b and len(a.strip().splitlines()) >= n
+    assert not [f for f in os.listdir(str(tmp_path / "two")) if "part" in f]

@@ -11,7 +11,8 @@ import numpy as np
 
 from spnet import callbacks, models, multi_gpu, utils
 import spnet.config as cf
-from predict_spnet import predict_network
+from predict_spnet import predict_network, default_image_dir
+from evaluate_spnet import evaluate_network
 
 
 def train_network(weights_file="weights.hdf5", datapath=".", fraction=1.0, batch_size=32, epochs=30, pred_grid=[6, 6, 2],
@@ -76,6 +77,8 @@ if __name__ == "__main__":
     parser.add_argument("--model_type", default=cf.model_type, help="'big' keeps 384x512 input, default resizes to 331x331")
     parser.add_argument("--parallel", action="store_true", help="shard each batch over the ranks of a torchrun launch")
     parser.add_argument("--device_data", action="store_true", help="keep the training set in GPU memory and augment it there (B200 build only)")
+    parser.add_argument("--predict_path", default=default_image_dir,
+                        help="directory of frames for the post-training predict_network pass (reference: hard-coded Zooniverse path)")
     args = parser.parse_args()
     print("Command line ~= \n", " ".join(s for s in sys.argv))
     print("args = ", args)
@@ -97,6 +100,22 @@ if __name__ == "__main__":
                           log_dir=log_dir, lr_max=args.lrmax, freeze_fac=args.freeze_fac,
                           frozen_epochs=args.frozen_epochs, random_seed=args.random_seed, parallel=args.parallel)
     if multi_gpu.world()[0] == 0:
+        # run model evaluation (train_spnet.py:130-138)
+        print("\n----------------------------\nStarting model evaluation...")
+        testpath = args.datapath + "/Test/"
+        if not os.path.isdir(testpath):
+            testpath = args.datapath + "/Val/"
+        evaluate_network(model=model, weights_file="", datapath=testpath, fraction=1.0, log_dir="logs/Evaluation/",
+                         batch_size=args.batch_size, pred_grid=pred_grid, set_means_ranges=False)
+        # make predictions on the Zooniverse dataset (:140-143); the reference's path is the author's home directory,
+        # so the pass is skipped with a notice where that directory holds no frames (the reference would raise there)
+        print("\n----------------------------\nStarting Zooniverse predictions...")
+        import glob
+        if glob.glob(args.predict_path + "/*.png") or glob.glob(args.predict_path + "/*.bmp"):
+            predict_network(weights_file="", datapath=args.predict_path, fraction=args.fraction, log_dir="logs/Predicting/",
+                            batch_size=args.batch_size, model=model, X_pred="")
+        else:
+            print("    no frames under", args.predict_path, "- skipping (give --predict_path)")
         weights2name = "final_" + args.weights
         print("Just to be sure: Saving model to", weights2name)
         model.save_weights(weights2name)
