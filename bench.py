@@ -90,37 +90,84 @@ def make_pool(n, seed0):
     return X, Y
 
 
+def make_pool_u8(n, seed0, workers=1):
+    """uint8 gen_fake_espi-style frames (n,384,512,1) + normalised targets; parallel worker processes (fork: call before
+    CUDA is initialised in this process)."""
+    from spnet_b200 import fake_espi
+    X, Y, _ = fake_espi.make_frames_u8(n, base_seed=seed0, workers=workers)
+    return X, Y
+
+
+def normalise_host(Xu):
+    X = Xu.astype(np.float32)
+    X = X / 255.0   # spnet/utils.py:340-342
+    X -= 0.5
+    X *= 2.0
+    return X
+
+
 # -------------------------------------------------------------------------------------------------
-def run_reference(args, rank):
-    """CPU arm: oracle restatement of the same training step on the host cores (kind 'port')."""
-    if rank != 0:
-        return
+CPU_BATCH = 32  # BASELINE.md section 3: batch 32, median of >= 5 timed iterations after 2 warm-ups
+
+
+def cpu_train_steps(n_timed, n_warm, budget_s=None):
+    """The oracle restatement's training step (fwd + loss + bwd + Keras Adam, fp32, batch 32, 384x512 gen_fake_espi frames)
+    on all host cores. Returns (median seconds per step, timed steps actually run, cores)."""
     import torch
     from oracle import xception_torch as xt
     ncores = os.cpu_count() or 1
     torch.set_num_threads(ncores)
-    Bs = 4  # bounded sample of the batch-64 workload: 4 images per step
-    X, Y = make_pool(Bs, 10_000)
-    spec = xt.xception_spnet_spec(H, W, N_OUT)
-    model = xt.OracleSPNet(xt.init_weights(spec, seed=1), H, W)
-    times = []
-    for i in range(args.warmup_ref + args.steps_ref):
+    X, Y = make_pool(CPU_BATCH, 10_000)
+    model = xt.OracleSPNet(xt.init_weights(xt.xception_spnet_spec(H, W, N_OUT), seed=1), H, W)
+    ts, t_begin = [], time.perf_counter()
+    for i in range(n_warm + n_timed):
         t0 = time.perf_counter()
         _, _, _, grads = model.loss_and_grads(X, Y)
         model.adam_step(grads, LR)
         dt = time.perf_counter() - t0
-        if i >= args.warmup_ref:
-            times.append(dt)
-    ms = 1e3 * float(np.mean(times))
-    val = Bs / (ms / 1e3)
+        if i >= n_warm:
+            ts.append(dt)
+            if budget_s is not None and len(ts) >= 5 and time.perf_counter() - t_begin > budget_s:
+                break
+    return float(np.median(ts)), len(ts), ncores
+
+
+def cpu_cfg1(n_timed=5, n_warm=2):
+    """BASELINE.json configs[0] on the host cores: forward + YOLO-ellipse loss, batch 32, inference-mode BatchNorm."""
+    import torch
+    from oracle import xception_torch as xt
+    X, Y = make_pool(CPU_BATCH, 10_000)
+    model = xt.OracleSPNet(xt.init_weights(xt.xception_spnet_spec(H, W, N_OUT), seed=1), H, W)
+    yt = torch.as_tensor(Y)
+    ts = []
+    for i in range(n_warm + n_timed):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            float(model.custom_loss(yt, model.forward(X, training=False)))
+        if i >= n_warm:
+            ts.append(time.perf_counter() - t0)
+    return CPU_BATCH / float(np.median(ts))
+
+
+def run_reference(args, rank):
+    """CPU arm: oracle restatement of the same training step on the host cores (kind 'port': TensorFlow 1.14 / Keras 2.1.3
+    cannot run in this image). Batch 32 per step, the driver's --steps timed steps (at least 5,
+    stopping early once 5 are done and 150 s have passed), 2 warm-ups, median."""
+    if rank != 0:
+        return
+    import torch
+    dt, nsteps, ncores = cpu_train_steps(max(5, args.steps), 2, budget_s=150.0)
+    ms = 1e3 * dt
+    val = CPU_BATCH / dt
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
-           "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": ms, "higher_is_better": True,
+           "steps": nsteps, "warmup": 2, "ms_per_step": ms, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "Xception-SPNet train step fwd+bwd+loss+Adam, 384x512x1, batch 64/GPU",
+           "config": {"workload": "Xception-SPNet train step fwd+bwd+YOLO-ellipse loss+Keras Adam, 384x512x1, batch 64/GPU",
+                      "sample": "batch %d per step (bounded sample of the batch-64 workload, BASELINE.md section 3)" % CPU_BATCH,
                       "note": "reference CPU path = oracle restatement (TF1.14/Keras2.1.3 not runnable here)"},
            "cpu_baseline": {"value": val, "unit": "images/s", "cores": ncores, "kind": "port",
-                            "sample": "%d steps of %d images (of the batch-64 workload), torch %s CPU fp32" % (
-                                args.steps_ref, Bs, torch.__version__)},
+                            "sample": "median of %d timed steps (2 warm-ups) of %d images, oracle torch %s CPU fp32, all host cores" % (
+                                nsteps, CPU_BATCH, torch.__version__)},
            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -152,10 +199,10 @@ def algorithmic_work(name, a):
     if name == "spnet_dwconv3x3_fwd":      # in,k,a,b,relu,out,dtype,B,H,W,C,stream
         n = a[7] * a[8] * a[9] * a[10]
         return 2 * n * es(a[6]), 18 * n
-    if name == "spnet_dwconv3x3_bwd_fused":  # gout,in,k,a,b,relu,mean,rstd,stats,add,adds,gin,dk,dtype,B,H,W,C
-        n = a[14] * a[15] * a[16] * a[17]
+    if name == "spnet_dwconv3x3_bwd_fused":  # gout,in,k,a,b,relu,mean,rstd,stats,add,adds,gin,dk,dk_acc,dtype,B,H,W,C
+        n = a[15] * a[16] * a[17] * a[18]
         t = 3 + (1 if a[9] else 0)
-        return t * n * es(a[13]), 36 * n
+        return t * n * es(a[14]), 36 * n
     if name == "spnet_gemm_bf16":          # A,lda,amn,B,ldb,bmn,D,ldd,mode,M,N,K,splits,...
         M, N, K = a[9], a[10], a[11]
         return 2 * (M * K + N * K) + (2 if a[8] == 0 else 4) * M * N, 2 * M * N * K
@@ -181,10 +228,10 @@ def run_ours(args, rank, world):
     lib = get_lib()
     B = BATCH_PER_GPU
     npool = 2 * B
-    X, Y = make_pool(npool, 1_000_000 * rank)
-    Xp = torch.from_numpy(X).pin_memory()
-    Yp = torch.from_numpy(Y).pin_memory()
-    Xd, Yd = Xp.to(dev), Yp.to(dev)
+    Xu, Y, Xu_inf = args.pools           # uint8 frames, generated before CUDA was initialised (main)
+    Xp = torch.from_numpy(Xu[:npool]).pin_memory()            # HOST buffers of the end-to-end legs: uint8 pixel values
+    Yp = torch.from_numpy(Y[:npool]).pin_memory()
+    Xd, Yd = torch.from_numpy(normalise_host(Xu[:npool])).to(dev), Yp.to(dev)   # resident inputs of the HBM-timed leg
 
     eng = Engine(H, W, B, dtype="bf16", device=str(dev), seed=1)
     if world > 1:
@@ -225,15 +272,15 @@ def run_ours(args, rank, world):
     # the box's pinned host->device rate for one batch of frames, measured alone (not part of any timed region):
     # the end-to-end figure below cannot exceed batch / (this copy's time) and single-GPU boxes differ a lot here
     hb0, hb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    scratch_dev = torch.empty_like(Xd[:B])
+    scratch_dev = torch.empty(Xp[:B].shape, device=dev, dtype=torch.uint8)
     scratch_dev.copy_(Xp[:B], non_blocking=True)
     torch.cuda.synchronize()
     hb0.record()
-    for _ in range(3):
+    for _ in range(5):
         scratch_dev.copy_(Xp[:B], non_blocking=True)
     hb1.record()
     torch.cuda.synchronize()
-    h2d_gbps = 3 * scratch_dev.numel() * 4 / (hb0.elapsed_time(hb1) * 1e-3) / 1e9
+    h2d_gbps = 5 * scratch_dev.numel() / (hb0.elapsed_time(hb1) * 1e-3) / 1e9
     del scratch_dev
 
     # ---- timed region 2: end to end from host buffers (pinned H2D + loss D2H every step)
@@ -256,12 +303,27 @@ def run_ours(args, rank, world):
     ms_e2e = ev2.elapsed_time(ev3)
     clocks = sampler.stop()
 
-    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    # ---- timed region 3: inference through the public API (SPNetModel.predict, reference call site
+    #      predict_spnet.py:85) with HOST buffers: a pinned pool of uint8 frames cycled to ~50,000 frames per job
+    #      (BASELINE.json configs[4]), every batch copied host -> device inside the timed region, results copied back,
+    #      then decode + hawley_spnet.csv. Each rank predicts its contiguous share of the job (no collective).
+    hook_obj = eng.grad_hook
+    dp_timeline = None
+    if hook_obj is not None and getattr(hook_obj, "trace", False):
+        torch.cuda.synchronize()
+        dp_timeline = hook_obj.timeline()
+    infer = run_inference(args, rank, world, dev, Xu_inf, barrier)
+
+    t = torch.tensor([ms_dev, ms_e2e, infer["ms_predict"], infer["ms_total"]], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = float(t[0]), float(t[1])
+    infer["ms_predict"], infer["ms_total"] = float(t[2]), float(t[3])
     if rank != 0:
         return
+    frames_job = infer.pop("frames_per_rank") * world
+    infer.update({"value": frames_job / (infer["ms_predict"] / 1e3), "unit": "images/s",
+                  "value_with_decode_and_csv": frames_job / (infer["ms_total"] / 1e3), "frames": frames_job, "n_gpus": world})
 
     total_imgs = B * world * args.steps
     value = total_imgs / (ms_dev / 1e3)
@@ -300,7 +362,7 @@ def run_ours(args, rank, world):
         torch.cuda.synchronize()
         return t0.elapsed_time(t1) * 1e3 / (reps * len(calls))
 
-    RIDGE = peaks["tf_sust"] * 1e12 / (peaks["hbm"] * 1e9)  # FLOP/B above which a GEMM is tensor-bound
+    RIDGE = peaks["tf_burst"] * 1e12 / (peaks["hbm"] * 1e9)  # FLOP/B above which a GEMM is tensor-bound
     one_step = {n: d["items"][:len(d["items"]) // psteps] for n, d in fam.items()}
     fams = {"gemm_tensor": ("tensor", "gemm_tc_kernel (tcgen05), shapes above the ridge (%.0f FLOP/B)" % RIDGE, []),
             "gemm_hbm": ("hbm", "gemm_tc_kernel (tcgen05), shapes below the ridge", []),
@@ -334,8 +396,9 @@ def run_ours(args, rank, world):
                       "algorithmic_bytes_per_step": nb})
         else:
             ach = nf / t_s / 1e12
-            r.update({"achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sust"],
-                      "algorithmic_flops_per_step": nf})
+            # the family is replayed alone for a few milliseconds at full clock: the BURST peak is the denominator
+            r.update({"achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tf_burst"],
+                      "frac_of_sustained_peak": ach / peaks["tf_sust"], "algorithmic_flops_per_step": nf})
         r["share_of_step"] = t_s * 1e3 / (ms_dev / args.steps)
         roofs[key] = r
     # per-shape view of the GEMMs (M,N,K,a_mn,b_mn): eager-event time, TFLOP/s
@@ -351,33 +414,6 @@ def run_ours(args, rank, world):
     dominant = max(roofs.values(), key=lambda r: r["share_of_step"])
     other = [r for r in roofs.values() if r is not dominant]
 
-    # ---- inference throughput (forward only, moving-stat BN), same batch / shape, CUDA-graph replay
-    infer = None
-    try:
-        del eng
-        torch.cuda.empty_cache()
-        ieng = Engine(H, W, B, dtype="bf16", device=str(dev), seed=1, training=False)
-        ieng.x0.copy_(Xd[:B])
-        ieng.forward(training=False)
-        torch.cuda.synchronize()
-        ig = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(ig):
-            ieng.forward(training=False)
-        for _ in range(3):
-            ig.replay()
-        torch.cuda.synchronize()
-        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        i0.record()
-        for i in range(args.steps):
-            ieng.x0.copy_(Xd[(i % 2) * B:(i % 2) * B + B])
-            ig.replay()
-        i1.record()
-        torch.cuda.synchronize()
-        ims = i0.elapsed_time(i1) / args.steps
-        infer = {"value": B / (ims / 1e3), "unit": "images/s (per GPU)", "ms_per_batch": ims, "batch": B}
-    except Exception as e:  # the training numbers above stay valid
-        infer = {"error": str(e)[:200]}
-
     # ---- CPU baseline on this box's host cores: bounded sample of the same workload
     cpu = cpu_baseline()
 
@@ -391,32 +427,63 @@ def run_ours(args, rank, world):
                       "cuda_graph": True, "loss_last": last},
            "clocks": clocks,
            "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
-                   "h2d_bytes_per_step": int(B * (H * W * 4 + N_OUT * 4)), "d2h_bytes_per_step": 24,
+                   "h2d_bytes_per_step": int(B * (H * W * 1 + N_OUT * 4)), "d2h_bytes_per_step": 24,
+                   "input": "uint8 frames from pinned host memory, normalised on the device ((v/255-0.5)*2, bit-exact)",
                    "h2d_gb_per_s_of_this_box": round(h2d_gbps, 2),
-                   "h2d_bound_images_per_s": round(B * world / (B * H * W * 4 / (h2d_gbps * 1e9)), 1)},
+                   "h2d_bound_images_per_s": round(B * world / (B * H * W / (h2d_gbps * 1e9)), 1)},
            "gpu_launches": int(launches_per_step * args.steps * 2),
            "roofline": dominant, "roofline_other": other, "kernel_breakdown": breakdown, "eager_step_ms": total_ms / psteps, "gemm_shapes": gemm_shapes,
-           "peaks": peaks, "inference": infer, "cpu_baseline": cpu}
+           "peaks": peaks, "inference": infer, "cpu_baseline": cpu, "dp_timeline_ms": dp_timeline}
     print(json.dumps(out), flush=True)
 
 
-def cpu_baseline():
+def run_inference(args, rank, world, dev, Xu_inf, barrier):
+    """predict_spnet's hot loop through the public API: SPNetModel.predict over ~50k frames of host memory."""
     import torch
-    from oracle import xception_torch as xt
-    ncores = os.cpu_count() or 1
-    torch.set_num_threads(ncores)
-    Bs = 4
-    X, Y = make_pool(Bs, 10_000)
-    model = xt.OracleSPNet(xt.init_weights(xt.xception_spnet_spec(H, W, N_OUT), seed=1), H, W)
-    ts = []
-    for i in range(3):
-        t0 = time.perf_counter()
-        _, _, _, grads = model.loss_and_grads(X, Y)
-        model.adam_step(grads, LR)
-        ts.append(time.perf_counter() - t0)
-    dt = float(np.mean(ts[1:]))
-    return {"value": Bs / dt, "unit": "images/s", "cores": ncores, "kind": "port",
-            "sample": "2 timed steps (1 warm-up) of %d images of the batch-64 workload, oracle torch-CPU fp32" % Bs}
+    import spnet.config as cf
+    from spnet import models, utils
+    import predict_spnet
+    cf.compute_dtype, cf.basemodel, cf.model_type = "bf16", args.backbone, "big"
+    B = BATCH_PER_GPU
+    pool = torch.from_numpy(Xu_inf).pin_memory()
+    npool = pool.shape[0]
+    per_rank = (args.infer_frames // world + npool - 1) // npool * npool   # whole passes over the pool
+    reps = per_rank // npool
+    model = models.SPNetModel((H, W, 1), Y0size=N_OUT, quick_setup=True, backbone=args.backbone)
+    model.predict(pool[:2 * B], batch_size=B)   # engine set-up + graph capture: not part of the timed region
+    utils.setup_means_and_ranges([6, 6, 2, 8])
+    import tempfile
+    log_dir = tempfile.mkdtemp(prefix="bench_predict_rank%d_" % rank) + "/"   # ~72 rows per frame on random weights: >100 MB
+    barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    parts = [model.predict(pool, batch_size=B) for _ in range(reps)]
+    e1.record()
+    Y_pred = np.concatenate(parts, axis=0)
+    Yp, decoded = predict_spnet.decode_on_device(Y_pred)
+    names = ["frame_%07d.png" % (rank * per_rank + i) for i in range(per_rank)]
+    utils.show_pred_ellipses(Yp, Yp, names, num_draw=per_rank, log_dir=log_dir, out_csv=log_dir + "hawley_spnet.csv",
+                             show_true=False, draw_images=False, decoded=decoded)
+    e2.record()
+    barrier()
+    rows = sum(1 for _ in open(log_dir + "hawley_spnet.csv"))
+    csv_bytes = os.path.getsize(log_dir + "hawley_spnet.csv")
+    import shutil
+    shutil.rmtree(log_dir, ignore_errors=True)
+    return {"ms_predict": e0.elapsed_time(e1), "ms_total": e0.elapsed_time(e2), "frames_per_rank": per_rank, "batch": B,
+            "api": "SPNetModel.predict(pinned uint8 host pool of %d frames, cycled %dx per rank), CUDA-graph forward, "
+                   "H2D of every batch and D2H of every result inside the timed region" % (npool, reps),
+            "h2d_bytes_per_batch": int(B * H * W), "csv_rows_rank0": rows, "csv_bytes_rank0": csv_bytes,
+            "note": "random-initialised weights: ~72 'detections' per frame, so the CSV leg formats millions of rows; a trained "
+                    "model writes a few rows per frame"}
+
+
+def cpu_baseline():
+    """Bounded CPU sample inside the default run: 5 timed training steps (2 warm-ups) of batch 32 + configs[0]."""
+    dt, nsteps, ncores = cpu_train_steps(5, 2)
+    return {"value": CPU_BATCH / dt, "unit": "images/s", "cores": ncores, "kind": "port",
+            "sample": "median of %d timed steps (2 warm-ups) of %d images of the batch-64 workload, oracle torch-CPU fp32" % (nsteps, CPU_BATCH),
+            "cfg1_forward_loss_batch32_images_per_s": cpu_cfg1()}
 
 
 def main():
@@ -426,6 +493,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--backbone", default="Xception", choices=["Xception", "MobileNet", "InceptionResNetV2"])
+    ap.add_argument("--infer-frames", type=int, default=50_000, help="frames of the predict_spnet leg (whole job)")
+    ap.add_argument("--infer-pool", type=int, default=512, help="distinct frames in the inference pool (cycled)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     args.steps_ref = max(1, min(args.steps, 3))
@@ -435,6 +504,11 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    # synthetic frames first: the generator forks worker processes, which must happen before CUDA / NCCL exist here
+    nw = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
+    Xu, Y = make_pool_u8(2 * BATCH_PER_GPU, 1_000_000 * rank, workers=nw)
+    Xu_inf, _ = make_pool_u8(args.infer_pool, 2_000_000 + 1_000_000 * rank, workers=nw)
+    args.pools = (Xu, Y, Xu_inf)
     # keep stdout clean for the single JSON line (NCCL prints its version banner to stdout)
     real_stdout = os.dup(1)
     os.dup2(2, 1)
