@@ -203,9 +203,10 @@ def algorithmic_work(name, a):
         n = a[15] * a[16] * a[17] * a[18]
         t = 3 + (1 if a[9] else 0)
         return t * n * es(a[14]), 36 * n
-    if name == "spnet_gemm_bf16":          # A,lda,amn,B,ldb,bmn,D,ldd,mode,M,N,K,splits,...
-        M, N, K = a[9], a[10], a[11]
-        return 2 * (M * K + N * K) + (2 if a[8] == 0 else 4) * M * N, 2 * M * N * K
+    if name == "spnet_gemm_bf16":          # A,lda,amn,B,ldb,bmn,D,ldd,slab_stride,mode,M,N,K,splits,...
+        M, N, K = a[10], a[11], a[12]
+        nout = (a[13] if a[9] == 3 else 1) * M * N   # slab mode: one [M, N] product per split
+        return 2 * (M * K + N * K) + (2 if a[9] == 0 else 4) * nout, 2 * M * N * K
     return 0, 0
 
 
@@ -404,7 +405,7 @@ def run_ours(args, rank, world):
     # per-shape view of the GEMMs (M,N,K,a_mn,b_mn): eager-event time, TFLOP/s
     shapes = {}
     for a, ms in fam.get("spnet_gemm_bf16", {"items": []})["items"]:
-        key = (a[9], a[10], a[11], a[2], a[5])
+        key = (a[10], a[11], a[12], a[2], a[5])
         d = shapes.setdefault(key, [0, 0.0])
         d[0] += 1
         d[1] += ms

@@ -86,9 +86,12 @@ int spnet_dwconv3x3_fwd(const void* in, const float* k, const float* in_a, const
 int spnet_dwconv3x3_bwd_fused(const void* gout, const void* in, const float* k, const float* in_a, const float* in_b, int relu, const float* bn_mean, const float* bn_rstd, long long* stats, const void* add_src, const void* add_strided, void* gin, float* dk, long long* dk_acc, int dtype, int B, int H, int W, int C, cudaStream_t stream);
 
 /* ---- GEMMs: pointwise 1x1, strided 1x1 residual convs, block1_conv2 (im2col), Dense head
- *      (spnet/models.py:359,388). See gemm_tc.cu / gemm_simt.cu for operand conventions. ---- */
-int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* D, long long ldd, int out_mode, int M, int N, int K, int splits, long long* colstats, cudaStream_t stream);
-int spnet_gemm_simt(const void* A, long long sa_r, long long sa_k, const void* B, long long sb_r, long long sb_k, void* D, long long ldd, int dtype, int out_mode, int M, int N, int K, int splits, long long* colstats, cudaStream_t stream);
+ *      (spnet/models.py:359,388). See gemm_tc.cu / gemm_simt.cu for operand conventions. out_mode 3 (slabs): split s
+ *      of the K range stores its [M, N] partial product at D + s * slab_stride elements - split-K with a fixed
+ *      summation order (spnet_slab_reduce), or a batch of GEMMs stacked along K in ONE launch (the weight gradients
+ *      of Xception's 24 identical middle-flow layers, written straight into the flat gradient buffer). ---- */
+int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* D, long long ldd, long long slab_stride, int out_mode, int M, int N, int K, int splits, long long* colstats, cudaStream_t stream);
+int spnet_gemm_simt(const void* A, long long sa_r, long long sa_k, const void* B, long long sb_r, long long sb_k, void* D, long long ldd, long long slab_stride, int dtype, int out_mode, int M, int N, int K, int splits, long long* colstats, cudaStream_t stream);
 
 /* ---- Conv2D k x k, stride 1, as implicit GEMM on tcgen05 (gemm_tc.cu, no im2col buffer): Xception
  *      block1_conv2 (keras.applications.Xception; spnet/models.py:359) and the InceptionResNetV2 branch

@@ -7,10 +7,10 @@ spnet_b200/csrc/diagnostics.cu:
   against the reference's own output in tests/golden/ref_diagnostics.npz.
 * compute_iou (:85-120): the reference rasterises both ellipses with cv2.ellipse(..., thickness=-1, LINE_AA,
   shift=10) on a 512 x 384 canvas and counts non-zero pixels, i.e. every pixel the ANTI-ALIASED filled polygon
-  touches. cv2's polygon scan converter is not restated; the mask here is the analytic ellipse with both
-  semi-axes enlarged by AA_MARGIN pixels, calibrated against cv2 (mean symmetric difference 1 % of the ellipse
-  area over random ellipses). Parity is therefore approximate and pinned with a tolerance: |IoU - reference|
-  <= 0.04 on the golden pairs, mAP within 0.03 (tests/test_diagnostics.py).
+  touches. That rasteriser (third-party: OpenCV drawing.cpp) is restated in integers in oracle/cv2_raster.py and
+  pinned pixel for pixel against cv2 itself; the IoUs here are therefore the reference's own, bit for bit
+  (tests/test_diagnostics.py compares with tests/golden/ref_diagnostics.npz). The earlier analytic approximation
+  (semi-axes enlarged by AA_MARGIN) is kept as ellipse_mask_analytic for the device kernel's fast mode.
 * precision (:125-150) and calc_map (:153-162): exact restatements on top of the IoU matrix.
 """
 import numpy as np
@@ -53,8 +53,20 @@ def calc_errors(Yp, Yt):
 
 
 def ellipse_mask(args, nx=512, ny=384):
-    """Pixels of the filled, anti-aliased ellipse (create_ellipse_image :68-80; draw_ellipse utils.py:35-53 passes
-    -angle to cv2, whose angles run clockwise on the y-down canvas)."""
+    """EXACT: the pixels the reference's create_ellipse_image (:68-80) leaves non-zero, through the integer restatement
+    of cv2's anti-aliased filled-polygon rasteriser (oracle/cv2_raster.py, pinned pixel for pixel against cv2)."""
+    from . import cv2_raster
+    cx, cy, a, b, c2, s2, noobj = [np.float32(v) for v in args[:7]]
+    if not noobj < 0.5:
+        return np.zeros((ny, nx), bool)
+    angle = np.rad2deg(np.arctan2(s2, c2) / 2.0)   # float32 arithmetic, as the reference's numpy scalars
+    return cv2_raster.ellipse_mask(cx, cy, a, b, angle, nx, ny)
+
+
+def ellipse_mask_analytic(args, nx=512, ny=384):
+    """The analytic approximation (device kernel's `margin >= 0` mode): ellipse test with both semi-axes enlarged by
+    AA_MARGIN pixels standing in for cv2's anti-aliased edge (create_ellipse_image :68-80; draw_ellipse utils.py:35-53
+    passes -angle to cv2, whose angles run clockwise on the y-down canvas)."""
     cx, cy, a, b, c2, s2, noobj = [np.float32(v) for v in args[:7]]
     if not noobj < 0.5:
         return np.zeros((ny, nx), bool)
@@ -67,12 +79,25 @@ def ellipse_mask(args, nx=512, ny=384):
     return (u * u + v * v) <= np.float32(1.0)
 
 
+def ellipse_image(args, nx=512, ny=384):
+    """uint8 canvas with the reference's pixel VALUES (create_ellipse_image :68-80): arguments keep their dtype, exactly as
+    the reference's numpy scalars do (float32 rows of Yp / Yt, or Python floats)."""
+    from . import cv2_raster
+    cx, cy, a, b, c2, s2, noobj = args[:7]
+    if not noobj < 0.5:
+        return np.zeros((ny, nx), np.uint8)
+    angle = np.rad2deg(np.arctan2(s2, c2) / 2.0)
+    return cv2_raster.ellipse_image(cx, cy, a, b, angle, nx, ny)
+
+
 def compute_iou(args_p, args_t):
-    """diagnostics.py:85-120: -1 when the true slot is empty (noobj > 0.99) or neither ellipse is drawn."""
+    """diagnostics.py:85-120: -1 when the true slot is empty (noobj > 0.99) or neither ellipse is drawn. Intersection /
+    union are counted on cv2.bitwise_and / bitwise_or of the pixel VALUES (two partially covered edge pixels can AND to
+    zero), as the reference does."""
     if args_t[6] > 0.99:
         return -1.0
-    mp, mt = ellipse_mask(args_p), ellipse_mask(args_t)
-    ni, nu = int((mp & mt).sum()), int((mp | mt).sum())
+    vp, vt = ellipse_image(args_p), ellipse_image(args_t)
+    ni, nu = int(((vp & vt) != 0).sum()), int(((vp | vt) != 0).sum())
     if ni == 0 and nu == 0:
         return -1.0
     return ni / nu

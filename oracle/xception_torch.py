@@ -676,7 +676,13 @@ class OracleIRv2SPNet(OracleSPNet):
 
         def residual(t, up, scale, relu):
             y = t + scale * up
-            return torch.relu(y) if relu else y
+            y = torch.relu(y) if relu else y
+            if taps:   # debugging aid: (input, up-branch, output) of every Inception-ResNet block, gradients retained
+                for v in (t, up, y):
+                    if v.requires_grad:
+                        v.retain_grad()
+                self.taps.setdefault("residual", []).append((t, up, y))
+            return y
 
         w = _IRv2Walker(conv_bn, conv_bias, lambda t: F.max_pool2d(t, 3, 2), avgpool, lambda ts: torch.cat(ts, 1), residual)
         return w.run(x)

@@ -16,8 +16,8 @@ enum { OUT_T = 0, OUT_F32 = 1, OUT_ATOMIC_F32 = 2, OUT_SLAB_F32 = 3 };
 template <typename T>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A, long long sa_r, long long sa_k,
                                                         const T* __restrict__ B, long long sb_r, long long sb_k,
-                                                        void* __restrict__ D, long long ldd, int out_mode, int M,
-                                                        int N, int K, int k_per_split,
+                                                        void* __restrict__ D, long long ldd, long long slab_stride,
+                                                        int out_mode, int M, int N, int K, int k_per_split,
                                                         long long* __restrict__ colstats) {
     __shared__ float As[TK][TM + PAD];
     __shared__ float Bs[TK][TN + PAD];
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
             } else if (out_mode == OUT_F32) {
                 reinterpret_cast<float*>(D)[(long long)r * ldd + c] = v;
             } else if (out_mode == OUT_SLAB_F32) {  // split z keeps its partial in its own slab (fixed-order split-K)
-                reinterpret_cast<float*>(D)[((long long)blockIdx.z * ((M + 255) / 256 * 256) + r) * ldd + c] = v;
+                reinterpret_cast<float*>(D)[(long long)blockIdx.z * slab_stride + (long long)r * ldd + c] = v;
             } else {
                 atomicAdd(reinterpret_cast<float*>(D) + (long long)r * ldd + c, v);
             }
@@ -110,7 +110,7 @@ extern "C" {
 
 // dtype: element type of A and B (0 fp32, 1 bf16). out_mode 0 stores D in that same type.
 int spnet_gemm_simt(const void* A, long long sa_r, long long sa_k, const void* B, long long sb_r, long long sb_k,
-                    void* D, long long ldd, int dtype, int out_mode, int M, int N, int K, int splits,
+                    void* D, long long ldd, long long slab_stride, int dtype, int out_mode, int M, int N, int K, int splits,
                     long long* colstats, cudaStream_t stream) {
     SPNET_REQUIRE(A && B && D, "gemm_simt: null pointer");
     SPNET_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_simt: bad shape %d %d %d", M, N, K);
@@ -118,13 +118,14 @@ int spnet_gemm_simt(const void* A, long long sa_r, long long sa_k, const void* B
     SPNET_REQUIRE(splits <= 1 || out_mode == OUT_ATOMIC_F32 || out_mode == OUT_SLAB_F32, "gemm_simt: split-K needs out_mode 2 or 3");
     SPNET_REQUIRE(!(colstats && splits > 1), "gemm_simt: column statistics are not defined for split-K partials");
     if (splits < 1) splits = 1;
+    SPNET_REQUIRE(out_mode != OUT_SLAB_F32 || slab_stride > 0, "gemm_simt: out_mode 3 needs slab_stride");
     int kps = ceil_div(ceil_div(K, splits), TK) * TK;
     splits = ceil_div(K, kps);
     dim3 grid(ceil_div(N, TN), ceil_div(M, TM), splits);
     SPNET_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm_simt: grid too large");
     SPNET_DISPATCH_DTYPE(dtype, (gemm_simt_kernel<T><<<grid, 256, 0, stream>>>(
                                     reinterpret_cast<const T*>(A), sa_r, sa_k, reinterpret_cast<const T*>(B), sb_r,
-                                    sb_k, D, ldd, out_mode, M, N, K, kps, colstats)));
+                                    sb_k, D, ldd, slab_stride, out_mode, M, N, K, kps, colstats)));
     return spnet_check_launch("gemm_simt");
 }
 

@@ -39,7 +39,7 @@ struct GemmEpi {
     void* out;
     long long ldc;
     int mode;
-    int slab_rows;     // OUT_SLAB_F32: split s stores its fp32 partial at row offset s * slab_rows of D
+    int slab_rows;     // unused (kept for layout); OUT_SLAB_F32 stores through a 3-D output map {N, M, split}
     long long* colstats;  // order-independent accumulators (common.cuh stat_add), 2*N entries (sum, sumsq), or nullptr
 };
 
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             int drow = m0 + q * 32, dx = 0, dy = 0, dimg = 0;
             uint32_t rowmask = 0xffffffffu;  // CONV 1: rows of this warp's box that are real output pixels
             if (CONV == 2) drow += ((unit / (tiles_n * tiles_m)) % cg.ntaps) * M;
-            if (CONV == 0 && epi.mode == OUT_SLAB_F32) drow += (unit / (tiles_n * tiles_m)) * epi.slab_rows;
+            const int dslab = unit / (tiles_n * tiles_m);  // OUT_SLAB_F32: this unit's split = its output slab
             if (CONV == 1) {
                 const int t2 = mt / cg.tiles_w, lwh = cg.lw + cg.lh;
                 const int x0 = (mt - t2 * cg.tiles_w) << cg.lw, y0 = (t2 % cg.tiles_h) << cg.lh;
@@ -476,7 +476,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                             __syncwarp();
                             if (e_leader) {
-                                if (epi.mode != OUT_ATOMIC_F32)
+                                if (epi.mode == OUT_SLAB_F32)  // rows >= M of the slab are clipped: slabs may sit inside other data
+                                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmD),
+                                                 "r"(stg), "r"(col0 + 16 * h), "r"(drow), "r"(dslab)
+                                                 : "memory");
+                                else if (epi.mode != OUT_ATOMIC_F32)
                                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmD),
                                                  "r"(stg), "r"(col0 + 16 * h), "r"(drow)
                                                  : "memory");
@@ -641,15 +645,18 @@ extern "C" {
 // D[M,N] (op)= A[M,K] * B[K,N], bf16 operands, fp32 accumulation in TMEM.
 //   a_mn / b_mn : 0 = K-major (ptr[r*ld + k]), 1 = MN-major (ptr[k*ld + r])
 //   out_mode    : 0 store bf16, 1 store fp32, 2 reduce-add fp32 (split-K, order of the adds not fixed), 3 fp32
-//                 SLABS (split-K with a fixed summation order): split s stores its partial product at rows
-//                 [s * R, s * R + M) of D, R = M rounded up to 256; the effective number of splits is
-//                 ceil(kb / ceil(kb / splits)) with kb = ceil(K / 64); spnet_slab_reduce adds the slabs in order
+//                 SLABS: split s (k-blocks [s*kbps, (s+1)*kbps), kbps = ceil(ceil(K/64) / splits)) stores its partial
+//                 product as an [M, N] matrix (row stride ldd) at D + s * slab_stride elements. Two uses: split-K with
+//                 a FIXED summation order (spnet_slab_reduce adds the slabs in order), and BATCHED GEMMs whose
+//                 operands are stacked along K - e.g. the weight gradients of the 24 identical middle-flow layers in
+//                 one launch: K = 24 x rows, splits = 24, slab s = dW of layer s, written straight into the flat
+//                 gradient buffer (rows >= M are clipped by the TMA unit, so slabs may be embedded in other data)
 //   colstats    : nullable fp64 [2*N]; per-column sum and sum of squares of the values as
 //                 stored (after bf16 rounding in mode 0) are atomically added
 //   Requirements: pointers 16-byte aligned, lda/ldb multiples of 8, N % 8 == 0 (bf16 out)
 //                 or N % 4 == 0 (fp32 store).
 int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* D,
-                    long long ldd, int out_mode, int M, int N, int K, int splits, long long* colstats,
+                    long long ldd, long long slab_stride, int out_mode, int M, int N, int K, int splits, long long* colstats,
                     cudaStream_t stream) {
     SPNET_REQUIRE(A && B && D, "gemm_bf16: null pointer");
     SPNET_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16: bad shape %d %d %d", M, N, K);
@@ -675,14 +682,13 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
         }
     }
     SPNET_REQUIRE(splits <= 1 || out_mode == OUT_ATOMIC_F32 || out_mode == OUT_SLAB_F32, "gemm_bf16: split-K needs out_mode 2 or 3");
-    const int slab_rows = (M + 255) / 256 * 256;
-    long long out_rows = M;
+    int n_slabs = 1;
     if (out_mode == OUT_SLAB_F32) {
+        SPNET_REQUIRE(slab_stride > 0 && slab_stride % 4 == 0, "gemm_bf16: slab_stride must be a positive multiple of 4 elements");
         const int kb = (K + BK - 1) / BK;
         int sp = splits < 1 ? 1 : (splits > kb ? kb : splits);
         const int kbps = (kb + sp - 1) / sp;
-        sp = (kb + kbps - 1) / kbps;
-        out_rows = (long long)sp * slab_rows;
+        n_slabs = (kb + kbps - 1) / kbps;
     }
     SPNET_REQUIRE(!(colstats && splits > 1), "gemm_bf16: column statistics are not defined for split-K partials");
     // 128x256 tiles when N is wide: one A tile then feeds 256 output columns, which cuts the
@@ -699,14 +705,16 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
     {
         PFN_cuTensorMapEncodeTiled enc = spnet_get_tensormap_encoder();
         const bool ob = out_mode == OUT_BF16;
-        cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)out_rows}, strides[1] = {(cuuint64_t)ldd * (ob ? 2 : 4)};
-        cuuint32_t box[2] = {ob ? 32u : 16u, 32u}, estr[2] = {1, 1};
-        CUresult r = enc(&td, ob ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, D, dims, strides, box,
-                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        const bool slabs = out_mode == OUT_SLAB_F32;
+        cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)n_slabs};
+        cuuint64_t strides[2] = {(cuuint64_t)ldd * (ob ? 2 : 4), (cuuint64_t)slab_stride * 4};
+        cuuint32_t box[3] = {ob ? 32u : 16u, 32u, 1u}, estr[3] = {1, 1, 1};
+        CUresult r = enc(&td, ob ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, slabs ? 3 : 2, D, dims,
+                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SPNET_REQUIRE(r == CUDA_SUCCESS, "gemm_bf16: cuTensorMapEncodeTiled (output) failed (%d) M=%d N=%d ldd=%lld", (int)r, M, N, ldd);
     }
-    GemmEpi epi = {D, ldd, out_mode, slab_rows, colstats};
+    GemmEpi epi = {D, ldd, out_mode, 0, colstats};
 #define SPNET_GEMM_DISPATCH(BN_, CL_)                                                                    \
     do {                                                                                                 \
         if (a_mn) {                                                                                      \

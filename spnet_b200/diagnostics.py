@@ -3,9 +3,11 @@ calc_map - computed on the GPU (csrc/diagnostics.cu through the C ABI; there is 
 
 The reference's calc_map rasterises 2 x 72 x N anti-aliased 512 x 384 ellipse masks with cv2 for EACH of its ten
 thresholds; here every (image, slot) pair's IoU comes out of one kernel launch and the ten precisions are
-counted from that matrix. The ellipse test is analytic with a 1.35-pixel margin standing in for cv2's
-anti-aliased edge (calibrated, oracle/diagnostics_numpy.py): IoUs agree with the reference's to ~0.02, mAP to
-~0.001 on the golden set; calc_errors is exact."""
+counted from that matrix. The rasteriser is an integer port of cv2's own (polygon of the ellipse, anti-aliased
+edges with their pixel values, convex fill): intersection and union are the reference's pixel counts, so IoU,
+precision and mAP are the reference's numbers bit for bit (tests/test_diagnostics.py against
+tests/golden/ref_diagnostics.npz). `fast=True` selects the earlier analytic approximation (ellipse test with a
+1.35-pixel margin; within 0.04 IoU / 0.03 mAP of the reference). calc_errors is exact."""
 import numpy as np
 
 from . import config as cf
@@ -34,10 +36,17 @@ def calc_errors(Yp, Yt):
     return c[0], c[1], c[2], c[3], c[4], c[5], c[6], pe, int(np.argmax(pe))
 
 
-def iou_matrix(Yp, Yt):
-    """IoU of every (image, predictor slot) pair, -1 where the reference's compute_iou returns -1."""
+def iou_matrix(Yp, Yt, fast=False):
+    """IoU of every (image, predictor slot) pair, -1 where the reference's compute_iou returns -1. The exact mode returns
+    intersection / union of the reference's pixel counts in float64."""
     from . import ops
-    return ops.ellipse_iou(_dev(Yp), _dev(Yt), CANVAS[0], CANVAS[1], AA_MARGIN).cpu().numpy().astype(np.float64)
+    if fast:
+        return ops.ellipse_iou(_dev(Yp), _dev(Yt), CANVAS[0], CANVAS[1], AA_MARGIN).cpu().numpy().astype(np.float64)
+    iou, counts = ops.ellipse_iou(_dev(Yp), _dev(Yt), CANVAS[0], CANVAS[1], -1.0, counts=True)
+    iou, counts = iou.cpu().numpy().astype(np.float64), counts.cpu().numpy().astype(np.float64)
+    live = iou >= 0
+    iou[live] = counts[..., 0][live] / counts[..., 1][live]   # num_i / num_u in double, as the reference divides
+    return iou
 
 
 def compute_iou(args_p, args_t, display=False):

@@ -207,7 +207,7 @@ class SPNetEngineBase:
         if self.deterministic and self.can_train:
             self._gacc = ops.stats_alloc(9 * 2048, self.device)
         self.dense_splits = max(1, min(64, (2 * 148) // max(1, -(-self.n_out // 128))))
-        self.head_slabs = torch.zeros(self.dense_splits, ops.slab_rows(B), self.n_out, device=self.device, dtype=torch.float32)
+        self.head_slabs = torch.zeros(self.dense_splits, B, self.n_out, device=self.device, dtype=torch.float32)
 
     # ------------------------------------------------------------------ helpers
     def _view(self, buf, *shape):
@@ -244,20 +244,23 @@ class SPNetEngineBase:
         return int(max(1, min(kb // 4 if kb >= 8 else 1, -(-(2 * 148) // tiles))))
 
     def _slab_buf(self, nslabs, rows, cols):
-        n = nslabs * ops.slab_rows(rows) * cols
+        n = nslabs * rows * cols
         if self._slabs is None or self._slabs.numel() < n:
             assert not torch.cuda.is_current_stream_capturing(), "slab scratch must be sized by an eager warm-up step"
             self._slabs = torch.zeros(n, device=self.device, dtype=torch.float32)
         return self._slabs
 
     def _pw_bwd(self, A, Wl, gW, gz, gA, M, K, N):
-        """gz [M,N] -> gW [K,N] += A^T gz ;  gA [M,K] = gz W^T."""
-        if self.deterministic:
+        """gz [M,N] -> gW [K,N] += A^T gz ;  gA [M,K] = gz W^T. gW None: the weight gradient is computed elsewhere
+        (the batched launch over the middle flow)."""
+        if gW is None:
+            pass
+        elif self.deterministic:
             # fixed-order split-K: partial products to slabs, added in split order (bit-identical run to run)
             sp = self._wgrad_splits(K, N, M)
             slabs = self._slab_buf(sp, K, N)
             if sp > 1:
-                slabs[:sp * ops.slab_rows(K) * N].zero_()  # a slab the GEMM does not need must read as zero
+                slabs[:sp * K * N].zero_()  # a slab the GEMM does not need must read as zero
             ops.gemm(A, True, gz, True, slabs, K, N, M, out_mode=ops.OUT_SLAB, splits=sp, lda=K, ldb=N)
             ops.slab_reduce(slabs, sp, K, N, gW, accumulate=True)
         else:
@@ -336,13 +339,13 @@ class SPNetEngineBase:
             ops.acc_to_f32(self.l2_acc, self.l2_out)
 
     # ------------------------------------------------------------------ backward
-    def _sep_bwd(self, s, gz, x, in_bn, relu, g_t, g_in, add_src=None, add_strided=None):
+    def _sep_bwd(self, s, gz, x, in_bn, relu, g_t, g_in, add_src=None, add_strided=None, wgrad=True):
         """gz: grad wrt s.z [B,H,W,cout]. Produces the gradient wrt the sepconv's input tensor x
         (before its on-load BN/ReLU transform) in g_in; for a BN'd input this is still the grad wrt
         the BN OUTPUT (masked by relu'), to be pushed through _bn_bwd by the caller."""
         B = self.B
         M = B * s.H * s.W
-        self._pw_bwd(s.t, s.pwl, s.gpw, gz, g_t, M, s.cin, s.cout)
+        self._pw_bwd(s.t, s.pwl, s.gpw if wgrad else None, gz, g_t, M, s.cin, s.cout)
         gt4 = g_t.view(B, s.H, s.W, s.cin)
         ops.dwconv3x3_bwd_fused(gt4, x, s.dwk, s.gdwk, in_a=in_bn.a if in_bn else None, in_b=in_bn.b if in_bn else None,
                                 relu=relu, bn_mean=in_bn.mean if in_bn else None, bn_rstd=in_bn.rstd if in_bn else None,
@@ -686,9 +689,16 @@ class XceptionSPNetEngine(SPNetEngineBase):
             e["out"] = A(B, oh, ow, e["c"])
             e["argmax"] = A(B, oh, ow, e["c"], dtype=torch.uint8) if train else None
         mh, mw = sh["middle"]
-        for blk in self.middle:
-            for s in blk:
-                s.t = A(B, mh, mw, 728)
+        # the depthwise outputs t (the A operand of every pointwise weight gradient) of the 24 identical middle-flow
+        # layers are ONE contiguous [24, B*mh*mw, 728] tensor, and so are the gradients dz reaching their pointwise
+        # convolutions: the 24 weight gradients dW_i = t_i^T dz_i are then a single GEMM launch whose K range is cut
+        # into 24 slabs (ops.gemm out_mode OUT_SLAB), each stored straight into the flat gradient buffer
+        nmid = 3 * len(self.middle)
+        self.mid_t = A(nmid, B, mh, mw, 728)
+        self.mid_dz = A(nmid, B, mh, mw, 728) if train else None
+        for bi, blk in enumerate(self.middle):
+            for j, s in enumerate(blk):
+                s.t = self.mid_t[3 * bi + j]
                 s.z = A(B, mh, mw, 728)
         self.mid_out = [A(B, mh, mw, 728) for _ in self.middle]
         fh, fw = sh["out13"]
@@ -699,6 +709,16 @@ class XceptionSPNetEngine(SPNetEngineBase):
         if train:
             self.gcol = None if self.lowp else A(B * h2 * w2, 288)  # bf16: the data gradient is an implicit GEMM
             self.scratch = [A(maxel) for _ in range(6)]
+            # batched middle-flow weight gradient: needs the 24 pointwise kernels equally spaced in the flat gradient
+            # buffer (they are: every layer contributes dw kernel + pw kernel + gamma + beta) and k-blocks that do
+            # not straddle two layers (rows per layer a multiple of the GEMM's 64 / 16-row k-block)
+            o0 = self.offsets["block5_sepconv1/pointwise_kernel"][0]
+            stride = self.offsets["block5_sepconv2/pointwise_kernel"][0] - o0
+            names = ["block%d_sepconv%d/pointwise_kernel" % (b, j) for b in arch.MIDDLE_BLOCKS for j in (1, 2, 3)]
+            even = all(self.offsets[n][0] == o0 + i * stride for i, n in enumerate(names))
+            rows = B * mh * mw
+            self.mid_batched = even and rows % (64 if self.lowp else 16) == 0 and os.environ.get("SPNET_B200_NO_BATCHED_WGRAD") is None
+            self.mid_gw_off, self.mid_gw_stride = o0, stride
 
     def _backbone_fwd(self, training):
         B, sh, w = self.B, self.shapes, self.w
@@ -754,20 +774,31 @@ class XceptionSPNetEngine(SPNetEngineBase):
         # ---- middle blocks 12..5
         mh, mw = sh["middle"]
         M = B * mh * mw
+        bat = self.mid_batched
         for i in range(len(self.middle) - 1, -1, -1):
             blk = self.middle[i]
             x_in = self.mid_out[i - 1] if i > 0 else self.entry[-1]["out"]
-            g3 = self._bn_bwd(g_x, blk[2].z, blk[2].bn, M, out=self._view(G1, B, mh, mw, 728))
+            # with the batched weight gradient every dz is kept (mid_dz) until the end of the middle flow
+            dz3, dz2, dz1 = (self.mid_dz[3 * i + 2], self.mid_dz[3 * i + 1], self.mid_dz[3 * i]) if bat else (None, None, None)
+            g3 = self._bn_bwd(g_x, blk[2].z, blk[2].bn, M, out=dz3 if bat else self._view(G1, B, mh, mw, 728))
             gy2 = self._view(G3, B, mh, mw, 728)
-            self._sep_bwd(blk[2], g3.view(M, 728), blk[1].z, blk[1].bn, True, self._view(G2, M, 728), gy2)
-            g2 = self._bn_bwd(gy2, blk[1].z, blk[1].bn, M, reduced=True)
+            self._sep_bwd(blk[2], g3.view(M, 728), blk[1].z, blk[1].bn, True, self._view(G2, M, 728), gy2, wgrad=not bat)
+            g2 = self._bn_bwd(gy2, blk[1].z, blk[1].bn, M, reduced=True, out=dz2)
             gy1 = self._view(G1, B, mh, mw, 728)
-            self._sep_bwd(blk[1], g2.view(M, 728), blk[0].z, blk[0].bn, True, self._view(G2, M, 728), gy1)
-            g1 = self._bn_bwd(gy1, blk[0].z, blk[0].bn, M, reduced=True)
+            self._sep_bwd(blk[1], g2.view(M, 728), blk[0].z, blk[0].bn, True, self._view(G2, M, 728), gy1, wgrad=not bat)
+            g1 = self._bn_bwd(gy1, blk[0].z, blk[0].bn, M, reduced=True, out=dz1)
             g_new = self._view(R_nxt, B, mh, mw, 728)
-            self._sep_bwd(blk[0], g1.view(M, 728), x_in, None, True, self._view(G2, M, 728), g_new, add_src=g_x)
+            self._sep_bwd(blk[0], g1.view(M, 728), x_in, None, True, self._view(G2, M, 728), g_new, add_src=g_x, wgrad=not bat)
             g_x = g_new
             R_cur, R_nxt = R_nxt, R_cur
+        if bat:
+            # dW_i = t_i^T dz_i for the 24 layers in ONE launch: both operands stacked along K (pixel rows), split s of the
+            # K range = layer s, its [728, 728] product stored at the layer's place in the flat gradient buffer. No
+            # split-K reduce-adds (every output tile has ONE writer: also bit-identical run to run), 192 k-blocks per
+            # tile instead of 24 launches with ~10 k-blocks per CTA each
+            n = len(self.middle) * 3
+            ops.gemm(self.mid_t.view(n * M, 728), True, self.mid_dz.view(n * M, 728), True, self.grads[self.mid_gw_off:], 728, 728,
+                     n * M, out_mode=ops.OUT_SLAB, splits=n, lda=728, ldb=728, ldd=728, slab_stride=self.mid_gw_stride)
         self._bwd_state = (g_x, R_cur, R_nxt)
 
     def _backbone_bwd_b(self, ga):

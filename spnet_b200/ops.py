@@ -102,39 +102,38 @@ def dwconv3x3_bwd_fused(gout, x, k, dk, in_a=None, in_b=None, relu=False, bn_mea
 OUT_T, OUT_F32, OUT_ATOMIC, OUT_SLAB = 0, 1, 2, 3
 
 
-def slab_rows(M):
-    """Row stride between the split-K slabs of gemm(..., out_mode=OUT_SLAB)."""
-    return (M + 255) // 256 * 256
-
-
-def slab_reduce(slabs, nslabs, M, N, out, bias=None, accumulate=False, ldo=None):
-    """out[M,N] = [out +] bias + slab_0 + slab_1 + ... in that order (slabs: zero-initialised [nslabs, slab_rows(M), N]
-    fp32 buffer written by gemm(..., out_mode=OUT_SLAB, splits=nslabs); slabs the GEMM did not need stay zero)."""
+def slab_reduce(slabs, nslabs, M, N, out, bias=None, accumulate=False, ldo=None, slab_stride=None):
+    """out[M,N] = [out +] bias + slab_0 + slab_1 + ... in that order (slabs: zero-initialised [nslabs, M, N] fp32 buffer
+    written by gemm(..., out_mode=OUT_SLAB, splits=nslabs); slabs the GEMM did not need stay zero)."""
     _chk(slabs, out, bias)
-    lib().slab_reduce(_p(slabs), nslabs, slab_rows(M) * N, N, _p(bias), _p(out), ldo if ldo is not None else N, M, N,
-                      int(accumulate), _s())
+    lib().slab_reduce(_p(slabs), nslabs, slab_stride if slab_stride is not None else M * N, N, _p(bias), _p(out),
+                      ldo if ldo is not None else N, M, N, int(accumulate), _s())
     return out
 
 
-def gemm(A, a_mn, B, b_mn, D, M, N, K, out_mode=OUT_T, splits=1, colstats=None, lda=None, ldb=None, ldd=None):
+def gemm(A, a_mn, B, b_mn, D, M, N, K, out_mode=OUT_T, splits=1, colstats=None, lda=None, ldb=None, ldd=None,
+         slab_stride=None):
     """D[M,N] (op)= A[M,K] @ B[K,N].
 
     a_mn / b_mn False: operand stored [rows, K] (K contiguous); True: stored [K, rows].
     bf16 operands run on tcgen05 (gemm_tc.cu), fp32 operands on the exact FFMA kernel.
+    out_mode OUT_SLAB: split s of the K range stores its partial product at D + s * slab_stride elements (default
+    M * N: a dense [splits, M, N] buffer) - fixed-order split-K (slab_reduce) or a batch of GEMMs stacked along K.
     """
     _chk(A, B, D, colstats)
     lda = lda if lda is not None else (M if a_mn else K)
     ldb = ldb if ldb is not None else (N if b_mn else K)
     ldd = ldd if ldd is not None else N
+    ss = (slab_stride if slab_stride is not None else M * ldd) if out_mode == OUT_SLAB else 0
     if A.dtype == torch.bfloat16:
         assert B.dtype == torch.bfloat16
-        lib().gemm_bf16(_p(A), lda, int(a_mn), _p(B), ldb, int(b_mn), _p(D), ldd, out_mode, M, N, K, splits,
+        lib().gemm_bf16(_p(A), lda, int(a_mn), _p(B), ldb, int(b_mn), _p(D), ldd, ss, out_mode, M, N, K, splits,
                         _p(colstats), _s())
     else:
         assert A.dtype == torch.float32 and B.dtype == torch.float32
         sa = (1, lda) if a_mn else (lda, 1)
         sb = (1, ldb) if b_mn else (ldb, 1)
-        lib().gemm_simt(_p(A), sa[0], sa[1], _p(B), sb[0], sb[1], _p(D), ldd, F32, out_mode, M, N, K, splits,
+        lib().gemm_simt(_p(A), sa[0], sa[1], _p(B), sb[0], sb[1], _p(D), ldd, ss, F32, out_mode, M, N, K, splits,
                         _p(colstats), _s())
     return D
 
@@ -147,8 +146,8 @@ def gemm_simt(A, a_mn, B, b_mn, D, M, N, K, out_mode=OUT_T, splits=1, colstats=N
     ldd = ldd if ldd is not None else N
     sa = (1, lda) if a_mn else (lda, 1)
     sb = (1, ldb) if b_mn else (ldb, 1)
-    lib().gemm_simt(_p(A), sa[0], sa[1], _p(B), sb[0], sb[1], _p(D), ldd, dtype_code(A), out_mode, M, N, K, splits,
-                    _p(colstats), _s())
+    lib().gemm_simt(_p(A), sa[0], sa[1], _p(B), sb[0], sb[1], _p(D), ldd, M * ldd if out_mode == OUT_SLAB else 0,
+                    dtype_code(A), out_mode, M, N, K, splits, _p(colstats), _s())
     return D
 
 

@@ -156,15 +156,18 @@ def test_fp32_train_step_every_gradient_against_fp64(case):
     # In training mode the backward pass is chaotic in fp32 (a forward error of 1e-5 flips isolated ReLU / ReLU6 /
     # max-pool decisions, each flip moves a BatchNorm-beta gradient by a few per cent of one channel): the fp32 oracle
     # itself sits at a MEDIAN of 2.8e-3 (Xception) / 5.9e-3 (MobileNet) relative L2 from the fp64 one, with single
-    # tensors at 1.5e-2 ... 1.5e-1. The engine has to be as good as that: per tensor within 1e-3, or 3x the fp32
-    # oracle's error on that tensor, or 3x the fp32 oracle's median error; and its median within 3x the oracle's median.
-    e_all = np.array([v["engine_vs_fp64"] for v in rows.values()])
-    t_all = np.array([v["torch_fp32_vs_fp64"] for v in rows.values()])
-    t_med = float(np.median(t_all))
+    # tensors at 1.5e-2 ... 1.5e-1 (which tensors depends on where an implementation's flips happen to fall). The engine
+    # has to be as good as that: per tensor within 1e-3, or 3x the fp32 oracle's error on that tensor, or 5x the fp32
+    # oracle's median error, or a tenth of the fp32 oracle's own worst tensor; median, 90th percentile and maximum over
+    # the tensors within 3x the fp32 oracle's.
+    e_all = np.array([v["engine_vs_fp64"] for k, v in rows.items() if k != "batch_normalization_3/beta"])
+    t_all = np.array([v["torch_fp32_vs_fp64"] for k, v in rows.items() if k != "batch_normalization_3/beta"])
+    t_med, t_max = float(np.median(t_all)), float(t_all.max())
     bad = [(k, v["engine_vs_fp64"], v["torch_fp32_vs_fp64"]) for k, v in rows.items()
-           if k != "batch_normalization_3/beta" and v["engine_vs_fp64"] > max(1e-3, 3 * v["torch_fp32_vs_fp64"], 5 * t_med)]
-    assert not bad, (t_med, bad[:10])
-    assert float(np.median(e_all)) <= max(1e-3, 3 * t_med), (float(np.median(e_all)), t_med)
+           if k != "batch_normalization_3/beta" and v["engine_vs_fp64"] > max(1e-3, 3 * v["torch_fp32_vs_fp64"], 5 * t_med, 0.1 * t_max)]
+    assert not bad, (t_med, t_max, bad[:10])
+    for q in (50, 90, 100):
+        assert float(np.percentile(e_all, q)) <= max(1e-3, 3 * float(np.percentile(t_all, q))), (q, float(np.percentile(e_all, q)))
     # BatchNorm moving statistics after the step
     ref64.adam_step(g64, 1e-3)
     w_ref, w_got = ref64.weights_numpy(), eng.get_weights()
