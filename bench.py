@@ -416,7 +416,7 @@ def run_ours(args, rank, world):
     other = [r for r in roofs.values() if r is not dominant]
 
     # ---- CPU baseline on this box's host cores: bounded sample of the same workload
-    cpu = cpu_baseline()
+    cpu = cpu_baseline() if not args.quick else None
 
     out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -496,6 +496,7 @@ def main():
     ap.add_argument("--backbone", default="Xception", choices=["Xception", "MobileNet", "InceptionResNetV2"])
     ap.add_argument("--infer-frames", type=int, default=50_000, help="frames of the predict_spnet leg (whole job)")
     ap.add_argument("--infer-pool", type=int, default=512, help="distinct frames in the inference pool (cycled)")
+    ap.add_argument("--quick", action="store_true", help="diagnostic runs: skip the CPU baseline and the per-family roofline legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     args.steps_ref = max(1, min(args.steps, 3))

@@ -31,3 +31,23 @@ for i, (op, (t, up, yy)) in enumerate(zip(res_ops[:4], ref.taps["residual"][:4])
     print("block", i + 1, "fwd x %.2e up %.2e y %.2e" % (rl2(eng.data[op["inputs"][0].idx], nhwc(t.detach())),
           rl2(eng.data[op["inputs"][1].idx] + eng.w[op["bias_name"]], nhwc(up.detach())), rl2(eng.data[op["out"].idx], nhwc(yy.detach()))),
           "| bwd gy %.2e gu %.2e gx %.2e" % (rl2(gy_e, nhwc(yy.grad)), rl2(gu_e, nhwc(up.grad)), rl2(gx_e, nhwc(t.grad))))
+print("---- mask disagreements (engine y > 0 vs oracle y > 0)")
+for i, (op, (t, up, yy)) in enumerate(zip(res_ops[:3], ref.taps["residual"][:3])):
+    ye = eng.data[op["out"].idx].double().cpu()
+    yo = yy.detach().permute(0, 2, 3, 1)
+    pre_o = (t.detach() + op["scale"] * up.detach()).permute(0, 2, 3, 1)
+    dis = (ye > 0) != (yo > 0)
+    print("block", i + 1, "disagree", int(dis.sum()), "of", dis.numel(), "x==0 fraction %.3f" % float((t.detach() == 0).double().mean()),
+          "oracle pre at disagreements:", pre_o[dis][:8].tolist(), "engine y there:", ye[dis][:8].tolist())
+    xe = eng.data[op["inputs"][0].idx].double().cpu()
+    xo = t.detach().permute(0, 2, 3, 1)
+    print("      x zero-pattern disagreements:", int(((xe == 0) != (xo == 0)).sum()), " max|xe-xo| %.3e" % float((xe - xo).abs().max()))
+    gy_e, gy_o = eng.grad[op["out"].idx].double().cpu(), yy.grad.permute(0, 2, 3, 1)
+    gm_o = gy_o * (yo > 0)
+    gu_e = eng.grad[op["inputs"][1].idx].double().cpu()
+    d = (gu_e - op["scale"] * gm_o)
+    idx = torch.nonzero(d.abs() > 10 * d.abs().mean())
+    print("      gu outliers:", idx.shape[0], "top |d|", d.abs().flatten().topk(5).values.tolist(), "typ |gu| %.3e" % float(gu_e.abs().mean()))
+    if idx.shape[0]:
+        j = tuple(idx[0].tolist())
+        print("      at", j, "gu_e", float(gu_e[j]), "scale*gy_o", float(op["scale"] * gy_o[j]), "yo", float(yo[j]), "ye", float(ye[j]), "gy_e", float(gy_e[j]))
