@@ -565,6 +565,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
+int g_cta_cap = 0;  // 0 = every SM
 // operand with `rows` along M/N and `kdim` along K; ld in elements
 int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long long kdim, long long ld, bool mn_major,
                      int tile_rows) {
@@ -602,19 +603,26 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     constexpr int STAGES = BN <= 64 ? 7 : (BN <= 128) ? 5 : 4;
     constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + kEpiWarps * 2048 * (BN <= 128 ? 2 : 1);
     auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, CL, CONV>;
-    static bool configured = false;
-    static int num_sms = 148;
-    if (!configured) {
+    // per (instantiation, device): the dynamic shared-memory opt-in is a per-device function attribute
+    static bool configured[64] = {};
+    static int num_sms_dev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             spnet_set_error("gemm_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return SPNET_ERR_CUDA;
         }
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        configured = true;
+        cudaDeviceGetAttribute(&num_sms_dev[dev], cudaDevAttrMultiProcessorCount, dev);
+        configured[dev] = true;
     }
+    // persistent grid: one CTA per SM, or fewer when the caller reserves SMs for a concurrent collective
+    // (spnet_gemm_set_cta_cap: NCCL's CTAs hold their SMs for the whole all-reduce, and a 148-CTA persistent GEMM
+    // would leave its last CTAs waiting for them)
+    int num_sms = num_sms_dev[dev];
+    if (g_cta_cap > 0 && g_cta_cap < num_sms) num_sms = g_cta_cap;
     const int total_kb = (K + BK - 1) / BK;
     if (splits < 1) splits = 1;
     if (splits > total_kb) splits = total_kb;
@@ -642,6 +650,13 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
 
 extern "C" {
 
+// Upper bound on the CTAs of the persistent tensor-core GEMM (0 = one per SM). The data-parallel engine lowers it while
+// a gradient all-reduce is in flight so that NCCL's resident CTAs and the GEMM never queue behind each other.
+int spnet_gemm_set_cta_cap(int max_ctas) {
+    g_cta_cap = max_ctas > 0 ? max_ctas : 0;
+    return SPNET_OK;
+}
+
 // D[M,N] (op)= A[M,K] * B[K,N], bf16 operands, fp32 accumulation in TMEM.
 //   a_mn / b_mn : 0 = K-major (ptr[r*ld + k]), 1 = MN-major (ptr[k*ld + r])
 //   out_mode    : 0 store bf16, 1 store fp32, 2 reduce-add fp32 (split-K, order of the adds not fixed), 3 fp32
@@ -666,7 +681,8 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
     SPNET_REQUIRE(out_mode >= 0 && out_mode <= 3, "gemm_bf16: bad out_mode %d", out_mode);
     SPNET_REQUIRE(out_mode != OUT_BF16 || (N % 8 == 0 && ldd % 8 == 0), "gemm_bf16: bf16 output needs N, ldd %% 8 == 0");
     SPNET_REQUIRE(out_mode == OUT_BF16 || ldd % 4 == 0, "gemm_bf16: fp32 output needs ldd %% 4 == 0");
-    const bool wide_ = N >= 512 && getenv("SPNET_GEMM_FORCE_NARROW") == nullptr, pair_ = wide_ && M > BM && getenv("SPNET_B200_NO_CLUSTER") == nullptr;
+    static const bool force_narrow = getenv("SPNET_GEMM_FORCE_NARROW") != nullptr, no_cluster = getenv("SPNET_B200_NO_CLUSTER") != nullptr;
+    const bool wide_ = N >= 512 && !force_narrow, pair_ = wide_ && M > BM && !no_cluster;
     if (splits <= 0) {
         // auto split-K (atomic output only): fill the SMs (or SM pairs) once without spilling into a
         // second, nearly empty round; keep at least 4 k-blocks per split
@@ -674,7 +690,10 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
         if (out_mode == OUT_ATOMIC_F32) {
             const int bn = wide_ ? 256 : 128, cl = pair_ ? 2 : 1;
             const long long tiles = (long long)(((M + BM - 1) / BM + cl - 1) / cl) * ((N + bn - 1) / bn);
-            const long long slots = 148 / cl;
+            int nsm = 148;
+            { int d_ = 0; cudaGetDevice(&d_); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d_); }
+            if (g_cta_cap > 0 && g_cta_cap < nsm) nsm = g_cta_cap;
+            const long long slots = nsm / cl;
             long long sp = tiles >= slots ? 1 : slots / tiles;
             const long long kb = (K + BK - 1) / BK;
             if (sp > kb / 4) sp = kb / 4;

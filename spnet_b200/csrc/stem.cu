@@ -88,34 +88,92 @@ __device__ __forceinline__ bool dropout_keep(unsigned long long seed, long long 
     return (float)(r >> 8) * (1.0f / 16777216.0f) >= rate;
 }
 
+// The 3-channel tensors of the stem are walked as flat arrays, G pixels (= 3 sixteen-byte vectors: 24 bf16 or 12 fp32
+// elements) per thread and step: element e of a group belongs to channel e % 3 and pixel e / 3 whatever the group, so
+// the per-channel coefficients index statically and every access is a full 16-byte vector. (One thread per pixel with
+// three 2-byte accesses ran these passes at 1.5 TB/s.) The pixels past the last full group are handled one by one.
+template <typename T> struct Tri { static constexpr int G = VecN<T>::N, E = 3 * VecN<T>::N; };
+
+template <typename T> __device__ __forceinline__ void load_tri(const T* __restrict__ p, float (&v)[Tri<T>::E]) {
+    constexpr int V = VecN<T>::N;
+    float t[V];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        load_vec(p + k * V, t);
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[k * V + i] = t[i];
+    }
+}
+template <typename T> __device__ __forceinline__ void store_tri(T* __restrict__ p, const float (&v)[Tri<T>::E]) {
+    constexpr int V = VecN<T>::N;
+    float t[V];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) t[i] = v[k * V + i];
+        store_vec(p + k * V, t);
+    }
+}
+
 template <typename T>
-__global__ void stem_out_fwd_kernel(const T* __restrict__ c3, const float* __restrict__ a,
-                                    const float* __restrict__ b, const T* __restrict__ skip, T* __restrict__ out,
-                                    long long pixels, float rate, const unsigned long long* __restrict__ seed) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= pixels) return;
-    const float s = to_f32(skip[p]);
+__global__ void __launch_bounds__(256) stem_out_fwd_kernel(const T* __restrict__ c3, const float* __restrict__ a,
+                                                           const float* __restrict__ b, const T* __restrict__ skip,
+                                                           T* __restrict__ out, long long pixels, float rate,
+                                                           const unsigned long long* __restrict__ seed) {
+    constexpr int G = Tri<T>::G, E = Tri<T>::E;
     const unsigned long long sd = seed ? *seed : 0ULL;
     const float scale = 1.0f / (1.0f - rate);
+    const float av[3] = {a[0], a[1], a[2]}, bv[3] = {b[0], b[1], b[2]};
+    const long long groups = pixels / G;
+    for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += (long long)gridDim.x * blockDim.x) {
+        float v[E], s[G];
+        load_tri(c3 + gi * E, v);
+        load_vec(skip + gi * G, s);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float y = fmaf(to_f32(c3[p * 3 + c]), a[c], b[c]) + s;
-        if (seed) y = dropout_keep(sd, p * 3 + c, rate) ? y * scale : 0.f;
-        out[p * 3 + c] = from_f32<T>(y);
+        for (int e = 0; e < E; ++e) {
+            float y = fmaf(v[e], av[e % 3], bv[e % 3]) + s[e / 3];
+            if (seed) y = dropout_keep(sd, gi * E + e, rate) ? y * scale : 0.f;
+            v[e] = y;
+        }
+        store_tri(out + gi * E, v);
+    }
+    if (blockIdx.x == 0) {  // the last pixels % G pixels
+        for (long long p = groups * G + threadIdx.x; p < pixels; p += blockDim.x) {
+            const float s = to_f32(skip[p]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float y = fmaf(to_f32(c3[p * 3 + c]), av[c], bv[c]) + s;
+                if (seed) y = dropout_keep(sd, p * 3 + c, rate) ? y * scale : 0.f;
+                out[p * 3 + c] = from_f32<T>(y);
+            }
+        }
     }
 }
 template <typename T>
-__global__ void stem_out_bwd_kernel(const T* g, T* gout, long long pixels, float rate,
-                                    const unsigned long long* __restrict__ seed) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= pixels) return;
+__global__ void __launch_bounds__(256) stem_out_bwd_kernel(const T* g, T* gout, long long pixels, float rate,
+                                                           const unsigned long long* __restrict__ seed) {
+    constexpr int G = Tri<T>::G, E = Tri<T>::E;
     const unsigned long long sd = seed ? *seed : 0ULL;
     const float scale = 1.0f / (1.0f - rate);
+    const long long groups = pixels / G;
+    for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += (long long)gridDim.x * blockDim.x) {
+        float v[E];
+        load_tri(g + gi * E, v);
+        if (seed) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float v = to_f32(g[p * 3 + c]);
-        if (seed) v = dropout_keep(sd, p * 3 + c, rate) ? v * scale : 0.f;
-        gout[p * 3 + c] = from_f32<T>(v);
+            for (int e = 0; e < E; ++e) v[e] = dropout_keep(sd, gi * E + e, rate) ? v[e] * scale : 0.f;
+        }
+        store_tri(gout + gi * E, v);
+    }
+    if (blockIdx.x == 0) {
+        for (long long p = groups * G + threadIdx.x; p < pixels; p += blockDim.x) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float v = to_f32(g[p * 3 + c]);
+                if (seed) v = dropout_keep(sd, p * 3 + c, rate) ? v * scale : 0.f;
+                gout[p * 3 + c] = from_f32<T>(v);
+            }
+        }
     }
 }
 
@@ -125,14 +183,28 @@ __global__ void __launch_bounds__(256) bn3_bwd_reduce_kernel(const T* __restrict
                                                              const float* __restrict__ mean,
                                                              const float* __restrict__ rstd,
                                                              long long* __restrict__ stats, long long pixels) {
+    constexpr int G = Tri<T>::G, E = Tri<T>::E;
     float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < pixels;
-         p += (long long)gridDim.x * blockDim.x) {
+    const float mv[3] = {mean[0], mean[1], mean[2]}, rv[3] = {rstd[0], rstd[1], rstd[2]};
+    const long long groups = pixels / G;
+    for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += (long long)gridDim.x * blockDim.x) {
+        float gv[E], zv[E];
+        load_tri(g + gi * E, gv);
+        load_tri(z + gi * E, zv);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float gv = to_f32(g[p * 3 + c]);
-            s[c] += gv;
-            s[3 + c] = fmaf(gv, (to_f32(z[p * 3 + c]) - mean[c]) * rstd[c], s[3 + c]);
+        for (int e = 0; e < E; ++e) {
+            s[e % 3] += gv[e];
+            s[3 + e % 3] = fmaf(gv[e], (zv[e] - mv[e % 3]) * rv[e % 3], s[3 + e % 3]);
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (long long p = groups * G + threadIdx.x; p < pixels; p += blockDim.x) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float gv = to_f32(g[p * 3 + c]);
+                s[c] += gv;
+                s[3 + c] = fmaf(gv, (to_f32(z[p * 3 + c]) - mv[c]) * rv[c], s[3 + c]);
+            }
         }
     }
     __shared__ float red[8][6];  // per-warp partials, summed in warp order (run-to-run identical)
@@ -149,16 +221,34 @@ __global__ void __launch_bounds__(256) bn3_bwd_reduce_kernel(const T* __restrict
     }
 }
 template <typename T>
-__global__ void bn3_bwd_dz_kernel(const T* g, const T* __restrict__ z, const float* __restrict__ a,
-                                  const float* __restrict__ mean, const float* __restrict__ rstd,
-                                  const float* __restrict__ c1, const float* __restrict__ c2, T* out,
-                                  long long pixels) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= pixels) return;
+__global__ void __launch_bounds__(256) bn3_bwd_dz_kernel(const T* g, const T* __restrict__ z, const float* __restrict__ a,
+                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                         const float* __restrict__ c1, const float* __restrict__ c2, T* out,
+                                                         long long pixels) {
+    constexpr int G = Tri<T>::G, E = Tri<T>::E;
+    float av[3], mv[3], rv[3], c1v[3], c2v[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float xh = (to_f32(z[p * 3 + c]) - mean[c]) * rstd[c];
-        out[p * 3 + c] = from_f32<T>(a[c] * (to_f32(g[p * 3 + c]) - c1[c] - xh * c2[c]));
+    for (int c = 0; c < 3; ++c) { av[c] = a[c]; mv[c] = mean[c]; rv[c] = rstd[c]; c1v[c] = c1[c]; c2v[c] = c2[c]; }
+    const long long groups = pixels / G;
+    for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += (long long)gridDim.x * blockDim.x) {
+        float gv[E], zv[E];
+        load_tri(g + gi * E, gv);
+        load_tri(z + gi * E, zv);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const float xh = (zv[e] - mv[e % 3]) * rv[e % 3];
+            gv[e] = av[e % 3] * (gv[e] - c1v[e % 3] - xh * c2v[e % 3]);
+        }
+        store_tri(out + gi * E, gv);
+    }
+    if (blockIdx.x == 0) {
+        for (long long p = groups * G + threadIdx.x; p < pixels; p += blockDim.x) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float xh = (to_f32(z[p * 3 + c]) - mv[c]) * rv[c];
+                out[p * 3 + c] = from_f32<T>(av[c] * (to_f32(g[p * 3 + c]) - c1v[c] - xh * c2v[c]));
+            }
+        }
     }
 }
 
@@ -255,6 +345,13 @@ int persist_grid(long long n) {
     const long long cap = 148LL * 4;
     return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
+// one thread per group of 8 (bf16) / 4 (fp32) pixels; at most one resident wave (the kernels stride over the groups)
+int tri_grid(long long pixels, int dtype) {
+    const long long groups = pixels / (dtype == SPNET_BF16 ? 8 : 4);
+    long long g = (groups + 255) / 256;
+    const long long cap = 148LL * 8;
+    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
 
 }  // namespace
 
@@ -276,7 +373,7 @@ int spnet_stem_k4grad_to_k3grad(const float* g4, float* g3, int cout, cudaStream
 int spnet_stem_out_fwd(const void* c3, const float* a, const float* b, const void* skip, void* out, int dtype,
                        long long pixels, float rate, const unsigned long long* seed, cudaStream_t stream) {
     SPNET_REQUIRE(c3 && a && b && skip && out && pixels > 0 && rate >= 0.f && rate < 1.f, "stem_out_fwd: bad args");
-    SPNET_DISPATCH_DTYPE(dtype, (stem_out_fwd_kernel<T><<<ceil_div(pixels, 256), 256, 0, stream>>>(
+    SPNET_DISPATCH_DTYPE(dtype, (stem_out_fwd_kernel<T><<<tri_grid(pixels, dtype), 256, 0, stream>>>(
                                     reinterpret_cast<const T*>(c3), a, b, reinterpret_cast<const T*>(skip),
                                     reinterpret_cast<T*>(out), pixels, rate, seed)));
     return spnet_check_launch("stem_out_fwd");
@@ -284,7 +381,7 @@ int spnet_stem_out_fwd(const void* c3, const float* a, const float* b, const voi
 int spnet_stem_out_bwd(const void* g, void* gout, int dtype, long long pixels, float rate,
                        const unsigned long long* seed, cudaStream_t stream) {
     SPNET_REQUIRE(g && gout && pixels > 0 && rate >= 0.f && rate < 1.f, "stem_out_bwd: bad args");
-    SPNET_DISPATCH_DTYPE(dtype, (stem_out_bwd_kernel<T><<<ceil_div(pixels, 256), 256, 0, stream>>>(
+    SPNET_DISPATCH_DTYPE(dtype, (stem_out_bwd_kernel<T><<<tri_grid(pixels, dtype), 256, 0, stream>>>(
                                     reinterpret_cast<const T*>(g), reinterpret_cast<T*>(gout), pixels, rate, seed)));
     return spnet_check_launch("stem_out_bwd");
 }
@@ -300,7 +397,7 @@ int spnet_bn3_bwd_reduce(const void* g, const void* z, const float* save_mean, c
 int spnet_bn3_bwd_dz(const void* g, const void* z, const float* a, const float* save_mean, const float* save_rstd,
                      const float* c1, const float* c2, void* out, int dtype, long long pixels, cudaStream_t stream) {
     SPNET_REQUIRE(g && z && a && save_mean && save_rstd && c1 && c2 && out && pixels > 0, "bn3_bwd_dz: bad args");
-    SPNET_DISPATCH_DTYPE(dtype, (bn3_bwd_dz_kernel<T><<<ceil_div(pixels, 256), 256, 0, stream>>>(
+    SPNET_DISPATCH_DTYPE(dtype, (bn3_bwd_dz_kernel<T><<<tri_grid(pixels, dtype), 256, 0, stream>>>(
                                     reinterpret_cast<const T*>(g), reinterpret_cast<const T*>(z), a, save_mean, save_rstd,
                                     c1, c2, reinterpret_cast<T*>(out), pixels)));
     return spnet_check_launch("bn3_bwd_dz");

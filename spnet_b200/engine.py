@@ -477,11 +477,22 @@ class SPNetEngineBase:
         self.loss(with_grad=True)
         self.backward_head()
 
+    def _reserve_sms(self, on):
+        """Data parallelism: while a gradient all-reduce is in flight the persistent GEMMs leave the SMs NCCL holds alone
+        (grid = dp_gemm_cap CTAs instead of one per SM; the grid is baked into the captured graph)."""
+        cap = getattr(self, "dp_gemm_cap", 0)
+        if cap:
+            lib().gemm_set_cta_cap(cap if on else 0)
+
     def _step_part2a(self):
+        self._reserve_sms(True)
         self.backward_body_a()
+        self._reserve_sms(False)
 
     def _step_part2b(self):
+        self._reserve_sms(True)
         self.backward_body_b()
+        self._reserve_sms(False)
         if self.grad_hook is None:
             self.optimizer_step()
 

@@ -73,6 +73,11 @@ class GradAllReduce:
             self.ready = {k: torch.cuda.Event() for k in ("head", "tail")}
             self.done = {k: torch.cuda.Event() for k in ("head", "tail")}
         self.in_flight = set()
+        # diagnostic knobs (profiles/r2/dp_timeline.md): skip the collectives / run every Adam after backward
+        self.no_comm = os.environ.get("SPNET_B200_DP_NOCOMM") is not None
+        self.adam_late = os.environ.get("SPNET_B200_DP_ADAM_LATE") is not None
+        cap = os.environ.get("SPNET_B200_DP_GEMM_CTAS")
+        engine.dp_gemm_cap = int(cap) if cap else 0
         self.trace = bool(int(os.environ.get("SPNET_B200_DP_TRACE", "0"))) if trace is None else trace
         self.trace_log, self._ev = [], None
 
@@ -89,13 +94,14 @@ class GradAllReduce:
             self._mark("step_begin")
 
     def timeline(self):
-        """Mean offset (ms) of every mark from step_begin over the traced steps (call after a synchronize)."""
+        """Median offset (ms) of every mark from step_begin over the traced steps (call after a synchronize); the median
+        ignores the first steps (NCCL set-up, eager warm-up before the graph capture)."""
         acc = {}
         for ev in self.trace_log:
             t0 = ev[0][1]
             for name, e in ev[1:]:
                 acc.setdefault(name, []).append(t0.elapsed_time(e))
-        return {k: sum(v) / len(v) for k, v in acc.items()}
+        return {k: sorted(v)[len(v) // 2] for k, v in acc.items()}
 
     def _reduce_and_step(self, engine, which, stream=None):
         """all-reduce bucket `which` and apply Adam to it, on the current stream."""
@@ -107,11 +113,13 @@ class GradAllReduce:
             from . import ops
             if not (which == "head" and engine.head_grad_lp is not None):
                 ops.cast_f32_to_bf16(engine.grads[lo:hi], self.glp[lo:hi])
-            self.dist.all_reduce(self.glp[lo:hi], group=self.group)
-        else:
+            if not self.no_comm:
+                self.dist.all_reduce(self.glp[lo:hi], group=self.group)
+        elif not self.no_comm:
             self.dist.all_reduce(engine.grads[lo:hi], group=self.group)
         self._mark(which + "_ar_end", stream)
-        engine.optimizer_step(grad_scale=1.0 / self.world, lo=lo, hi=hi, g_bf16=self.glp)
+        if not self.adam_late:
+            engine.optimizer_step(grad_scale=1.0 / self.world, lo=lo, hi=hi, g_bf16=self.glp)
         self._mark(which + "_adam_end", stream)
 
     def bucket_ready(self, engine, which):
@@ -136,6 +144,8 @@ class GradAllReduce:
         for which in self.in_flight:
             torch.cuda.current_stream().wait_event(self.done[which])
         self.in_flight.clear()
+        if self.adam_late:
+            engine.optimizer_step(grad_scale=1.0 / self.world, g_bf16=self.glp)
         self._mark("step_end")
         if self._ev is not None:
             self.trace_log.append(self._ev)

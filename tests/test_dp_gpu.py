@@ -26,14 +26,15 @@ from spnet_b200 import multi_gpu
 from spnet_b200.engine import XceptionSPNetEngine
 from spnet_b200.selfcheck import make_case
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dev = "cuda:" + os.environ["LOCAL_RANK"]
+torch.cuda.set_device(dev)
 dist.init_process_group("nccl")
 H, W, Bg = 96, 128, 8
 w, x, yt = make_case(H, W, Bg, seed=61)
 lo, hi = multi_gpu.batch_slice(Bg, rank, world)
 report = {}
 for dtype, comm, tol in (("fp32", "fp32", 2e-4), ("bf16", "fp32", 3e-2), ("bf16", "bf16", 3e-2)):
-    eng = XceptionSPNetEngine(H, W, hi - lo, dtype=dtype, weights=w, dropout_rate=0.0, deterministic=True)
+    eng = XceptionSPNetEngine(H, W, hi - lo, dtype=dtype, weights=w, dropout_rate=0.0, deterministic=True, device=dev)
     eng.bn_use_moving = "all"
     hook = multi_gpu.attach_data_parallel(eng, comm_dtype=comm)
     eng.load_batch(x[lo:hi], yt[lo:hi])
@@ -48,7 +49,7 @@ for dtype, comm, tol in (("fp32", "fp32", 2e-4), ("bf16", "fp32", 3e-2), ("bf16"
     dist.all_gather(gathered, chk)
     assert all(torch.equal(gathered[0], t) for t in gathered), gathered
     if rank == 0:
-        one = XceptionSPNetEngine(H, W, Bg, dtype=dtype, weights=w, dropout_rate=0.0, deterministic=True)
+        one = XceptionSPNetEngine(H, W, Bg, dtype=dtype, weights=w, dropout_rate=0.0, deterministic=True, device=dev)
         one.bn_use_moving = "all"
         one.load_batch(x, yt)
         one.grad_hook = lambda e: None
