@@ -206,7 +206,8 @@ class SPNetEngineBase:
             self.gstem = [A(sp) for _ in range(2)]
         if self.deterministic and self.can_train:
             self._gacc = ops.stats_alloc(9 * 2048, self.device)
-        self.dense_splits = max(1, min(64, (2 * 148) // max(1, -(-self.n_out // 128))))
+        self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.dense_splits = max(1, min(64, (2 * self.n_sms) // max(1, -(-self.n_out // 128))))
         self.head_slabs = torch.zeros(self.dense_splits, B, self.n_out, device=self.device, dtype=torch.float32)
 
     # ------------------------------------------------------------------ helpers
@@ -241,7 +242,7 @@ class SPNetEngineBase:
         tile = 128 if self.lowp else 64
         tiles = -(-rows_out // tile) * -(-cols_out // tile)
         kb = max(1, K // (64 if self.lowp else 16))
-        return int(max(1, min(kb // 4 if kb >= 8 else 1, -(-(2 * 148) // tiles))))
+        return int(max(1, min(kb // 4 if kb >= 8 else 1, -(-(2 * self.n_sms) // tiles))))
 
     def _slab_buf(self, nslabs, rows, cols):
         n = nslabs * rows * cols

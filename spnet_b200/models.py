@@ -217,29 +217,78 @@ class SPNetModel:
             eng.set_weights(self._host_weights)
             eng._version = self._version
 
+    # ---- checkpoint files -------------------------------------------------------------------------
+    # The reference's checkpoints are Keras HDF5 files (weights.hdf5 / spnet.model / full_model.h5: spnet/models.py:
+    # 475-485, spnet/callbacks.py:35-41, train_spnet.py:145-150). Files whose name ends in .h5 / .hdf5 / .model are
+    # written in that format (spnet_b200/hdf5_min.py: h5py is not in this image); any other name gets an .npz container
+    # keyed by the Keras weight names. Reading sniffs the file's magic bytes, whatever its name.
+    def _keras_layers(self):
+        by_layer = OrderedDict()
+        for k, _, _, _ in self.spec:
+            by_layer.setdefault(k.split("/")[0], []).append(k)
+        order = {"Xception": arch.xception_keras_layers, "MobileNet": arch.mobilenet_keras_layers}.get(self.backbone)
+        names = (order() + ["flatten_1", "FinalOutput"]) if order else list(by_layer)
+        names += [n for n in by_layer if n not in names]
+        return [(n, by_layer.get(n, [])) for n in names]
+
+    @staticmethod
+    def _is_hdf5_name(filepath):
+        return str(filepath).lower().endswith((".h5", ".hdf5", ".model"))
+
     def save_weights(self, filepath):
         w = self._weights_dict()
+        if self._is_hdf5_name(filepath):
+            from . import hdf5_min
+            hdf5_min.write_keras_weights(filepath, self._keras_layers(), w)
+            return
         with open(filepath, "wb") as f:
             np.savez(f, **{k.replace("/", "::"): v for k, v in w.items()})
 
-    def load_weights(self, filepath, by_name=False):
+    @staticmethod
+    def _read_weight_file(filepath):
+        """-> ({key: array}, config dict or None) from an HDF5 (Keras) or .npz file."""
         with open(filepath, "rb") as f:
             magic = f.read(8)
         if magic.startswith(b"\x89HDF"):
-            raise IOError("%s is a Keras HDF5 file; this build reads the .npz weight files it writes itself "
-                          "(h5py is not available in this image — INTEGRATION.md describes the converter)" % filepath)
+            import json
+            from . import hdf5_min
+            d, attrs = hdf5_min.read_keras_weights(filepath)
+            cfg = attrs.get("model_config")
+            if cfg is not None:
+                cfg = json.loads(cfg.decode("utf8") if isinstance(cfg, bytes) else cfg)
+            return d, cfg
         z = np.load(filepath)
         d = {k.replace("::", "/"): z[k] for k in z.files if not k.startswith("__")}
+        cfg = None
+        if "__config__" in z.files:
+            H, W, Y0, use_l2 = (int(v) for v in z["__config__"])
+            cfg = {"spnet_b200": {"H": H, "W": W, "Y0size": Y0, "use_l2": bool(use_l2),
+                                  "backbone": str(z["__backbone__"]) if "__backbone__" in z.files else "Xception",
+                                  "loss_type": str(z["__loss_type__"]) if "__loss_type__" in z.files else None}}
+        return d, cfg
+
+    def load_weights(self, filepath, by_name=False):
+        d, _ = self._read_weight_file(filepath)
         missing = [k for k, _, _, _ in self.spec if k not in d]
         if missing and not by_name:
             raise ValueError("load_weights: %d tensors missing from %s (first: %s)" % (len(missing), filepath, missing[0]))
+        for k, shp, _, _ in self.spec:
+            if k in d and tuple(d[k].shape) != tuple(shp):
+                raise ValueError("load_weights: %s has shape %s in %s, the model expects %s" % (k, tuple(d[k].shape), filepath, tuple(shp)))
         cur = self._weights_dict()
         self._load_dict({k: d.get(k, cur[k]) for k, _, _, _ in self.spec})
 
     def save(self, filepath):
-        """Full-model save: weights + architecture config (+ Adam state is not stored by the reference's
-        resume path either: spnet/models.py:475-485 reloads weights only)."""
+        """Full-model save: weights + architecture config (+ Adam state is not stored by the reference's resume path either:
+        spnet/models.py:475-485 reloads weights only)."""
         w = self._weights_dict()
+        cfg = {"H": self.H, "W": self.W, "Y0size": self.Y0size, "use_l2": bool(self.use_l2), "backbone": self.backbone,
+               "loss_type": cf.loss_type}
+        if self._is_hdf5_name(filepath):
+            import json
+            from . import hdf5_min
+            hdf5_min.write_keras_weights(filepath, self._keras_layers(), w, full_model_config=json.dumps({"spnet_b200": cfg}))
+            return
         with open(filepath, "wb") as f:
             np.savez(f, __config__=np.array([self.H, self.W, self.Y0size, int(self.use_l2)]),
                      __backbone__=np.array(self.backbone), __loss_type__=np.array(cf.loss_type),
@@ -581,14 +630,29 @@ def unfreeze_model(model, X, Y, parallel=False):
 
 
 def load_model(filepath):
-    """keras.models.load_model counterpart for files written by SPNetModel.save."""
-    z = np.load(filepath)
-    H, W, Y0, use_l2 = (int(v) for v in z["__config__"])
-    backbone = str(z["__backbone__"]) if "__backbone__" in z.files else "Xception"
-    if "__loss_type__" in z.files:
-        cf.loss_type = str(z["__loss_type__"])   # the reference's load_model restores the compiled loss with the model
-    m = SPNetModel((H, W, 1), Y0size=Y0, quick_setup=not use_l2, backbone=backbone)
-    d = {k.replace("::", "/"): z[k] for k in z.files if not k.startswith("__")}
+    """keras.models.load_model counterpart (reference call sites: predict_spnet.py:77-79, evaluate_spnet.py). Reads files
+    written by SPNetModel.save (HDF5 or .npz) and Keras `model.save` HDF5 files: the weights come from /model_weights,
+    the backbone from the layer names, the input size from the Keras model_config's InputLayer."""
+    d, cfg = SPNetModel._read_weight_file(filepath)
+    own = (cfg or {}).get("spnet_b200")
+    if own is not None:
+        H, W, Y0, use_l2, backbone = own["H"], own["W"], own["Y0size"], own["use_l2"], own.get("backbone") or "Xception"
+        if own.get("loss_type"):
+            cf.loss_type = own["loss_type"]   # the reference's load_model restores the compiled loss with the model
+    else:
+        backbone = "MobileNet" if "conv_pw_13/kernel" in d else ("InceptionResNetV2" if "conv_7b/kernel" in d else "Xception")
+        Y0, use_l2 = int(d["FinalOutput/kernel"].shape[1]), True
+        H = W = None
+        try:   # Keras model_config: {"class_name": "Model", "config": {"layers": [{"class_name": "InputLayer", "config": {...}}]}}
+            for layer in cfg["config"]["layers"]:
+                if layer["class_name"] == "InputLayer":
+                    _, H, W = layer["config"]["batch_input_shape"][:3]
+                    break
+        except Exception:
+            pass
+        if H is None:
+            raise ValueError("load_model: %s carries no input size (neither an spnet_b200 config nor a Keras model_config)" % filepath)
+    m = SPNetModel((int(H), int(W), 1), Y0size=int(Y0), quick_setup=not use_l2, backbone=backbone)
     missing = [k for k, _, _, _ in m.spec if k not in d]
     if missing:
         raise ValueError("load_model: %s does not hold a %s-SPNet for %dx%d input (%d tensors missing, first: %s)"

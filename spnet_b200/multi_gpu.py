@@ -76,6 +76,10 @@ class GradAllReduce:
         # diagnostic knobs (profiles/r2/dp_timeline.md): skip the collectives / run every Adam after backward
         self.no_comm = os.environ.get("SPNET_B200_DP_NOCOMM") is not None
         self.adam_late = os.environ.get("SPNET_B200_DP_ADAM_LATE") is not None
+        # when the head bucket's all-reduce starts: "early" = as soon as it is final (it then overlaps the GEMM-heavy
+        # exit / middle-flow backward), "late" = together with the tail bucket (it overlaps the bandwidth-bound entry flow)
+        self.head_late = os.environ.get("SPNET_B200_DP_HEAD", "early") == "late"
+        self._deferred = None
         cap = os.environ.get("SPNET_B200_DP_GEMM_CTAS")
         engine.dp_gemm_cap = int(cap) if cap else 0
         self.trace = bool(int(os.environ.get("SPNET_B200_DP_TRACE", "0"))) if trace is None else trace
@@ -128,9 +132,17 @@ class GradAllReduce:
         if not self.on_cuda or hi <= lo:
             return
         self._mark(which + "_ready")
+        if which == "head" and self.head_late and self.ranges["tail"][1] > self.ranges["tail"][0]:
+            self._deferred = "head"      # launched when the tail bucket is ready
+            return
         self.ready[which].record()
         with torch.cuda.stream(self.side):
             self.side.wait_event(self.ready[which])
+            if self._deferred:
+                self._reduce_and_step(engine, self._deferred, self.side)
+                self.done[self._deferred].record(self.side)
+                self.in_flight.add(self._deferred)
+                self._deferred = None
             self._reduce_and_step(engine, which, self.side)
             self.done[which].record(self.side)
         self.in_flight.add(which)

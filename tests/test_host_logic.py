@@ -415,3 +415,64 @@ def test_stored_oracle_is_the_plain_oracle_without_rounding():
             yc = stored(w, H, W, storage="bf16").forward(x, training=False)
         assert float((ya - yb).abs().max() / ya.abs().max()) < 2e-6
         assert 1e-4 < float((ya - yc).norm() / ya.norm()) < 2e-2   # bf16 storage is visible, and small in inference mode
+
+
+# ------------------------------------------------------------------ Keras HDF5 checkpoints (spnet_b200/hdf5_min.py)
+def test_hdf5_reader_on_a_file_written_by_libhdf5():
+    """The reader against a GENUINE HDF5 file (MATLAB v7.3 = libhdf5, shipped with scipy's test data: 512-byte user
+    block, superblock 0, symbol-table group, B-tree + local heap, version-1 object header, attribute, dataset)."""
+    import scipy.io
+    from spnet_b200 import hdf5_min
+    path = os.path.join(os.path.dirname(scipy.io.__file__), "matlab", "tests", "data", "testhdf5_7.4_GLNX86.mat")
+    if not os.path.exists(path):
+        pytest.skip("scipy's HDF5 test file is not installed")
+    r = hdf5_min.Reader(path)
+    assert r.base == 512 and list(r.links(r.root)) == ["testdouble"]
+    a = r.resolve("testdouble")
+    assert r.attrs(a) == {"MATLAB_class": b"double"}
+    np.testing.assert_allclose(r.dataset(a).ravel(), np.arange(0, 2 * np.pi + 1e-9, np.pi / 4), rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("backbone,hw", [("Xception", (96, 128)), ("InceptionResNetV2", (200, 260))])
+def test_keras_hdf5_weight_files_round_trip(tmp_path, backbone, hw):
+    """weights.hdf5 / full_model.h5 in the Keras layout (layer_names / weight_names attributes, datasets at
+    /<layer>/<layer>/<weight>:0, /model_weights for full models): written and read back bit for bit; a 450-group root
+    (InceptionResNetV2) exercises the multi-level B-tree."""
+    import spnet.config as cf
+    from spnet import models
+    from spnet_b200 import hdf5_min
+    cf.basemodel = backbone
+    try:
+        m = models.create_model_functional(np.zeros((1,) + hw + (1,), np.float32), 576, freeze_fac=0.0, quick_setup=True)
+        wpath, fpath = str(tmp_path / "weights.hdf5"), str(tmp_path / "full_model.h5")
+        m.save_weights(wpath)
+        m.save(fpath)
+        assert open(wpath, "rb").read(8) == b"\x89HDF\r\n\x1a\n"
+        d, attrs = hdf5_min.read_keras_weights(wpath)
+        assert attrs["keras_version"] == b"2.1.3" and attrs["backend"] == b"tensorflow"
+        r = hdf5_min.Reader(wpath)
+        names = [n.decode() for n in r.attrs(r.root)["layer_names"]]
+        assert "FinalOutput" in names and len(names) == len(set(names)) and set(r.links(r.root)) == set(names)
+        if backbone == "Xception":
+            assert names[:3] == ["input_1", "conv2d_1", "average_pooling2d_1"] and len(names) == 146
+            assert [w.decode() for w in r.attrs(r.resolve("block5_sepconv1"))["weight_names"]] == [
+                "block5_sepconv1/depthwise_kernel:0", "block5_sepconv1/pointwise_kernel:0"]
+            assert r.dataset(r.resolve("block5_sepconv1/block5_sepconv1/pointwise_kernel:0")).shape == (1, 1, 728, 728)
+        w0 = m.get_weights()
+        m2 = models.create_model_functional(np.zeros((1,) + hw + (1,), np.float32), 576, freeze_fac=0.0, quick_setup=True)
+        m2._load_dict({k: np.zeros_like(v) for k, v in m._weights_dict().items()})
+        m2.load_weights(wpath)
+        for a, b in zip(w0, m2.get_weights()):
+            np.testing.assert_array_equal(a, b)
+        m3 = models.load_model(fpath)
+        assert m3.backbone == backbone and (m3.H, m3.W) == hw
+        for a, b in zip(w0, m3.get_weights()):
+            np.testing.assert_array_equal(a, b)
+        # the .npz container (any other file name) still works, and a file of the wrong size is refused
+        m.save_weights(str(tmp_path / "weights.npz"))
+        m2.load_weights(str(tmp_path / "weights.npz"))
+        other = models.SPNetModel((hw[0] * 2, hw[1], 1), backbone=backbone, quick_setup=True)
+        with pytest.raises(ValueError):
+            other.load_weights(wpath)
+    finally:
+        cf.basemodel = "Xception"
