@@ -425,7 +425,7 @@ def run_ours(args, rank, world):
     other = [r for r in roofs.values() if r is not dominant]
 
     # ---- CPU baseline on this box's host cores: bounded sample of the same workload
-    cpu = cpu_baseline() if not args.quick else None
+    cpu = cpu_baseline() if (not args.quick and world == 1) else None   # N = 1 only (bench contract)
 
     out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
