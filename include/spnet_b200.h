@@ -104,6 +104,13 @@ int spnet_gemm_simt(const void* A, long long sa_r, long long sa_k, const void* B
 int spnet_conv_tc_fwd(const void* X, long long ldx, int NB, int H, int W, int Cin, const void* Wt, void* Y, long long ldy, int OH, int OW, int Cout, int KH, int KW, int pt, int pl, long long* colstats, cudaStream_t stream);
 int spnet_conv_tc_dgrad(const void* dY, long long ldy, int NB, int OH, int OW, int Cout, const void* Wt, void* dX, long long ldx, int H, int W, int Cin, int KH, int KW, int pt, int pl, cudaStream_t stream);
 int spnet_conv_tc_wgrad(const void* X, long long ldx, int NB, int H, int W, int Cin, const void* dY, long long ldy, int OH, int OW, int Cout, float* dW, int KH, int KW, int pt, int pl, cudaStream_t stream);
+/* 'valid' stride-1 convolution of a DENSE NHWC bf16 tensor (pixel stride = Cin) with the KW taps of a filter row folded
+ * into the channel axis (they are KW*Cin contiguous elements): KH * ceil(KW*Cin/64) k-blocks per tile and no im2col buffer.
+ * Replaces the im2col + GEMM route of Xception's block1_conv2 (3x3, 32 -> 64; keras.applications.xception, called from
+ * spnet/models.py:359). Y [NB, H-KH+1, W-KW+1, Cout] bf16 (pixel stride ldy), Wt the Keras kernel [KH, KW, Cin, Cout];
+ * colstats as for spnet_conv_tc_fwd. The weight gradient is reduce-added into dW (fp32, caller zeroes it). */
+int spnet_conv_tc_fwd_kwfold(const void* X, int NB, int H, int W, int Cin, const void* Wt, void* Y, long long ldy, int Cout, int KH, int KW, long long* colstats, cudaStream_t stream);
+int spnet_conv_tc_wgrad_kwfold(const void* X, int NB, int H, int W, int Cin, const void* dY, long long ldy, int Cout, float* dW, int KH, int KW, cudaStream_t stream);
 
 /* ---- BatchNormalization (43 layers; spnet/models.py:326-336 + Xception) ---- */
 int spnet_bn_finalize(long long* stats, long long count, const float* gamma, const float* beta, float eps, float momentum, int unbiased_moving_var, float* a, float* b, float* save_mean, float* save_rstd, float* moving_mean, float* moving_var, int C, cudaStream_t stream);

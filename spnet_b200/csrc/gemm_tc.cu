@@ -769,15 +769,18 @@ void pick_pixel_box(int log_rows, int OW, int OH, int NB, int* lw_out, int* lh_o
 }
 
 // NHWC activation [NB, H, W, C] with pixel stride ld (elements): 4-D map, box = 64 channels x pixel box
+// row_ld: elements between image rows (W * ld for a dense image; larger when W is a clipped extent, see the kw-fold
+// entry points below)
 int make_pixel_map(CUtensorMap* map, const void* ptr, int NB, int H, int W, int C, long long ld, int lw, int lh, int ln,
-                   int box_c, CUtensorMapSwizzle swz, CUtensorMapL2promotion prom) {
+                   int box_c, CUtensorMapSwizzle swz, CUtensorMapL2promotion prom, long long row_ld = 0) {
+    if (row_ld <= 0) row_ld = (long long)W * ld;
     PFN_cuTensorMapEncodeTiled enc = spnet_get_tensormap_encoder();
     if (!enc) {
         spnet_set_error("conv_tc: cuTensorMapEncodeTiled entry point not available");
         return SPNET_ERR_CUDA;
     }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
-    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)row_ld * 2, (cuuint64_t)H * row_ld * 2};
     cuuint32_t box[4] = {(cuuint32_t)box_c, 1u << lw, 1u << lh, 1u << ln}, estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, prom, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -795,7 +798,7 @@ int make_pixel_map(CUtensorMap* map, const void* ptr, int NB, int H, int W, int 
 // Wt is the Keras kernel [KH, KW, Cin, Cout]; c_in / c_out are the channel counts of `in` / `out`.
 int conv_tc_fwd_like(bool dgrad, const void* in, long long ld_in, int NB, int IH, int IW, int c_in, const void* Wt,
                      int Cin, int Cout, void* out, long long ld_out, int OH, int OW, int c_out, int KH, int KW, int pt,
-                     int pl, long long* colstats, cudaStream_t stream) {
+                     int pl, long long* colstats, cudaStream_t stream, long long row_ld_in = 0) {
     ConvGeom cg = {};
     pick_pixel_box(7, OW, OH, NB, &cg.lw, &cg.lh);
     const int ln = 7 - cg.lw - cg.lh;
@@ -814,7 +817,7 @@ int conv_tc_fwd_like(bool dgrad, const void* in, long long ld_in, int NB, int IH
     const int bn = N <= 64 ? 64 : 128;
     CUtensorMap ta, tb, td;
     int rc = make_pixel_map(&ta, in, NB, IH, IW, c_in, ld_in, cg.lw, cg.lh, ln, BK, CU_TENSOR_MAP_SWIZZLE_128B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, row_ld_in);
     if (rc) return rc;
     // weights as one 2-D matrix: forward [taps*Cin (k), Cout (n)] MN-major; data gradient: rows (n) = tap*Cin + ci,
     // k = Cout contiguous, K-major
@@ -835,6 +838,47 @@ int conv_tc_fwd_like(bool dgrad, const void* in, long long ld_in, int NB, int IH
     }
     if (bn == 64) return launch_gemm<64, false, false, 1, 1>(ta, tb, td, epi, M, N, K, 1, stream, cg, (int)tiles_m);
     return launch_gemm<128, false, false, 1, 1>(ta, tb, td, epi, M, N, K, 1, stream, cg, (int)tiles_m);
+}
+
+int conv_tc_wgrad_impl(const void* X, long long ldx, int NB, int H, int W, int Cin, const void* dY, long long ldy, int OH,
+                       int OW, int Cout, float* dW, int KH, int KW, int pt, int pl, cudaStream_t stream, long long row_ld_x) {
+    ConvGeom cg = {};
+    pick_pixel_box(6, OW, OH, NB, &cg.lw, &cg.lh);
+    const int ln = 6 - cg.lw - cg.lh;
+    cg.tiles_w = (OW + (1 << cg.lw) - 1) >> cg.lw;
+    cg.tiles_h = (OH + (1 << cg.lh) - 1) >> cg.lh;
+    const int groups = (NB + (1 << ln) - 1) >> ln;
+    cg.OW = OW; cg.OH = OH; cg.NB = NB;
+    cg.KW = KW; cg.ntaps = KH * KW;
+    cg.cin_blocks = 1;
+    cg.pt = pt; cg.pl = pl; cg.sign = 1;
+    const long long pixel_blocks = (long long)cg.tiles_w * cg.tiles_h * groups;
+    SPNET_REQUIRE(pixel_blocks < (1 << 24), "conv_tc_wgrad: too many pixel blocks");
+    const int M = Cin, N = Cout, K = (int)pixel_blocks * BK;
+    const int bn = N <= 64 ? 64 : 128;
+    CUtensorMap ta, tb, td;
+    int rc = make_pixel_map(&ta, X, NB, H, W, Cin, ldx, cg.lw, cg.lh, ln, 64, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, row_ld_x);
+    if (rc) return rc;
+    rc = make_pixel_map(&tb, dY, NB, OH, OW, Cout, ldy, cg.lw, cg.lh, ln, 64, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+    {
+        PFN_cuTensorMapEncodeTiled enc = spnet_get_tensormap_encoder();
+        cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)cg.ntaps * M}, strides[1] = {(cuuint64_t)N * 4};
+        cuuint32_t box[2] = {16u, 32u}, estr[2] = {1, 1};
+        CUresult r = enc(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dW, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SPNET_REQUIRE(r == CUDA_SUCCESS, "conv_tc_wgrad: cuTensorMapEncodeTiled (output) failed (%d)", (int)r);
+    }
+    // split the pixel reduction so that taps x tiles x splits fills the SMs about once; >= 4 pixel blocks per split
+    const long long tiles = (long long)((M + BM - 1) / BM) * ((N + bn - 1) / bn) * cg.ntaps;
+    long long sp = tiles >= 148 ? 1 : 148 / tiles;
+    if (sp > pixel_blocks / 4) sp = pixel_blocks / 4;
+    const int splits = (int)(sp < 1 ? 1 : sp);
+    GemmEpi epi = {dW, N, OUT_ATOMIC_F32, 0, nullptr};
+    if (bn == 64) return launch_gemm<64, true, true, 1, 2>(ta, tb, td, epi, M, N, K, splits, stream, cg, 0);
+    return launch_gemm<128, true, true, 1, 2>(ta, tb, td, epi, M, N, K, splits, stream, cg, 0);
 }
 
 }  // namespace
@@ -874,43 +918,33 @@ int spnet_conv_tc_wgrad(const void* X, long long ldx, int NB, int H, int W, int 
                         int OW, int Cout, float* dW, int KH, int KW, int pt, int pl, cudaStream_t stream) {
     SPNET_CONV_TC_CHECKS(X, ldx, dW, dY, ldy, Cin, Cout);
     SPNET_REQUIRE(NB > 0 && OH > 0 && OW > 0 && KH > 0 && KW > 0, "conv_tc_wgrad: bad shape");
-    ConvGeom cg = {};
-    pick_pixel_box(6, OW, OH, NB, &cg.lw, &cg.lh);
-    const int ln = 6 - cg.lw - cg.lh;
-    cg.tiles_w = (OW + (1 << cg.lw) - 1) >> cg.lw;
-    cg.tiles_h = (OH + (1 << cg.lh) - 1) >> cg.lh;
-    const int groups = (NB + (1 << ln) - 1) >> ln;
-    cg.OW = OW; cg.OH = OH; cg.NB = NB;
-    cg.KW = KW; cg.ntaps = KH * KW;
-    cg.cin_blocks = 1;
-    cg.pt = pt; cg.pl = pl; cg.sign = 1;
-    const long long pixel_blocks = (long long)cg.tiles_w * cg.tiles_h * groups;
-    SPNET_REQUIRE(pixel_blocks < (1 << 24), "conv_tc_wgrad: too many pixel blocks");
-    const int M = Cin, N = Cout, K = (int)pixel_blocks * BK;
-    const int bn = N <= 64 ? 64 : 128;
-    CUtensorMap ta, tb, td;
-    int rc = make_pixel_map(&ta, X, NB, H, W, Cin, ldx, cg.lw, cg.lh, ln, 64, CU_TENSOR_MAP_SWIZZLE_128B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
-    if (rc) return rc;
-    rc = make_pixel_map(&tb, dY, NB, OH, OW, Cout, ldy, cg.lw, cg.lh, ln, 64, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
-    if (rc) return rc;
-    {
-        PFN_cuTensorMapEncodeTiled enc = spnet_get_tensormap_encoder();
-        cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)cg.ntaps * M}, strides[1] = {(cuuint64_t)N * 4};
-        cuuint32_t box[2] = {16u, 32u}, estr[2] = {1, 1};
-        CUresult r = enc(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dW, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        SPNET_REQUIRE(r == CUDA_SUCCESS, "conv_tc_wgrad: cuTensorMapEncodeTiled (output) failed (%d)", (int)r);
-    }
-    // split the pixel reduction so that taps x tiles x splits fills the SMs about once; >= 4 pixel blocks per split
-    const long long tiles = (long long)((M + BM - 1) / BM) * ((N + bn - 1) / bn) * cg.ntaps;
-    long long sp = tiles >= 148 ? 1 : 148 / tiles;
-    if (sp > pixel_blocks / 4) sp = pixel_blocks / 4;
-    const int splits = (int)(sp < 1 ? 1 : sp);
-    GemmEpi epi = {dW, N, OUT_ATOMIC_F32, 0, nullptr};
-    if (bn == 64) return launch_gemm<64, true, true, 1, 2>(ta, tb, td, epi, M, N, K, splits, stream, cg, 0);
-    return launch_gemm<128, true, true, 1, 2>(ta, tb, td, epi, M, N, K, splits, stream, cg, 0);
+    return conv_tc_wgrad_impl(X, ldx, NB, H, W, Cin, dY, ldy, OH, OW, Cout, dW, KH, KW, pt, pl, stream, 0);
+}
+
+// ---- 'valid' convolutions of a DENSE NHWC tensor with the KW taps folded into the channel axis ----------------
+// The KW taps of one filter row read KW * Cin CONTIGUOUS elements of X (pixels x .. x+KW-1 of one image row), so
+// X is described to the TMA unit as [NB, H, W-KW+1, KW*Cin] with a pixel stride of Cin elements (rows of the map
+// overlap) and the convolution runs as a KH x 1 one over KW*Cin channels: KH * ceil(KW*Cin/64) k-blocks per tile
+// instead of KH*KW half-empty ones when Cin = 32 (block1_conv2 of the reference's Xception: 3x3, 32 -> 64,
+// spnet/models.py:359 via keras.applications.xception), and no im2col buffer. The Keras kernel [KH, KW, Cin, Cout]
+// is already the [KH, 1, KW*Cin, Cout] kernel of the folded problem.
+int spnet_conv_tc_fwd_kwfold(const void* X, int NB, int H, int W, int Cin, const void* Wt, void* Y, long long ldy, int Cout,
+                             int KH, int KW, long long* colstats, cudaStream_t stream) {
+    SPNET_CONV_TC_CHECKS(X, (long long)Cin, Wt, Y, ldy, Cin, Cout);
+    const int OH = H - KH + 1, OW = W - KW + 1;
+    SPNET_REQUIRE(NB > 0 && OH > 0 && OW > 0 && KH > 0 && KW > 0, "conv_tc_fwd_kwfold: bad shape");
+    return conv_tc_fwd_like(false, X, Cin, NB, H, OW, KW * Cin, Wt, KW * Cin, Cout, Y, ldy, OH, OW, Cout, KH, 1, 0, 0,
+                            colstats, stream, (long long)W * Cin);
+}
+
+// dW[KH, KW, Cin, Cout] (fp32) += weight gradient of the convolution above (TMA reduce-add)
+int spnet_conv_tc_wgrad_kwfold(const void* X, int NB, int H, int W, int Cin, const void* dY, long long ldy, int Cout,
+                               float* dW, int KH, int KW, cudaStream_t stream) {
+    SPNET_CONV_TC_CHECKS(X, (long long)Cin, dW, dY, ldy, Cin, Cout);
+    const int OH = H - KH + 1, OW = W - KW + 1;
+    SPNET_REQUIRE(NB > 0 && OH > 0 && OW > 0 && KH > 0 && KW > 0, "conv_tc_wgrad_kwfold: bad shape");
+    return conv_tc_wgrad_impl(X, Cin, NB, H, OW, KW * Cin, dY, ldy, OH, OW, Cout, dW, KH, 1, 0, 0, stream,
+                              (long long)W * Cin);
 }
 
 }  // extern "C"

@@ -163,6 +163,29 @@ def conv_tc_fwd(x, wt, y, pt, pl, colstats=None, ldx=None, ldy=None):
     return y
 
 
+def conv_tc_fwd_kwfold(x, wt, y, colstats=None):
+    """'valid' convolution of a dense NHWC tensor, the KW taps of a filter row folded into the channel axis
+    (csrc/gemm_tc.cu spnet_conv_tc_fwd_kwfold): y[B,H-KH+1,W-KW+1,Cout]."""
+    _chk(x, wt, y, colstats)
+    assert x.is_contiguous() and y.is_contiguous()
+    B, H, W, Cin = x.shape
+    KH, KW, _, Cout = wt.shape
+    assert tuple(y.shape) == (B, H - KH + 1, W - KW + 1, Cout)
+    lib().conv_tc_fwd_kwfold(_p(x), B, H, W, Cin, _p(wt), _p(y), Cout, Cout, KH, KW, _p(colstats), _s())
+    return y
+
+
+def conv_tc_wgrad_kwfold(x, gy, gw):
+    """gw[KH,KW,Cin,Cout] (fp32) += weight gradient of conv_tc_fwd_kwfold."""
+    _chk(x, gy, gw)
+    assert x.is_contiguous() and gy.is_contiguous() and gw.is_contiguous()
+    B, H, W, Cin = x.shape
+    KH, KW, _, Cout = gw.shape
+    assert tuple(gy.shape) == (B, H - KH + 1, W - KW + 1, Cout)
+    lib().conv_tc_wgrad_kwfold(_p(x), B, H, W, Cin, _p(gy), Cout, Cout, _p(gw), KH, KW, _s())
+    return gw
+
+
 def conv_tc_dgrad(gy, wt, gx, pt, pl, ldy=None, ldx=None):
     """gx[B,H,W,Cin] = data gradient of conv_tc_fwd from gy[B,OH,OW,Cout] (overwrites gx)."""
     _chk(gy, wt, gx)

@@ -614,6 +614,38 @@ def test_conv_tc_fwd_and_stats(case):
     torch.testing.assert_close(sv[Cout:], (yf * yf).sum(0), rtol=1e-5, atol=1e-3)
 
 
+KWFOLD_CASES = [(2, 46, 62, 32, 64, 3, 3), (3, 21, 141, 32, 64, 3, 3), (5, 9, 70, 16, 24, 3, 3), (2, 12, 40, 32, 128, 2, 5),
+                (1, 30, 131, 64, 64, 3, 3)]
+
+
+@pytest.mark.parametrize("case", KWFOLD_CASES)
+def test_conv_tc_kwfold_fwd_wgrad(case):
+    """'valid' convolution with the KW taps folded into the channel axis (overlapping-row tensor map): block1_conv2's
+    route. Forward + fused statistics against torch, weight gradient against fp64."""
+    ops = _ops()
+    B, H, W, Cin, Cout, KH, KW = case
+    x, wt, OH, OW, _, _ = _conv_tc_inputs((B, H, W, Cin, Cout, KH, KW, "valid"), seed=5)
+    ref = nhwc(_conv_ref(x, wt, "valid", KH, KW))
+    y = torch.full((B, OH, OW, Cout), float("nan"), device=dev(), dtype=torch.bfloat16)
+    stats = ops.stats_alloc(2 * Cout, dev())
+    ops.conv_tc_fwd_kwfold(x, wt, y, colstats=stats)
+    torch.testing.assert_close(y.float(), ref, rtol=2e-2, atol=2e-2)
+    yf = y.double().view(-1, Cout)
+    sv = ops.stats_values(stats).to(yf.device)
+    torch.testing.assert_close(sv[:Cout], yf.sum(0), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(sv[Cout:], (yf * yf).sum(0), rtol=1e-5, atol=1e-3)
+    g = torch.Generator(device="cpu").manual_seed(6)
+    gy = torch.randn(B, OH, OW, Cout, generator=g).to(dev()).bfloat16()
+    xr = nchw(x).double().cpu()
+    wr = wt.double().permute(3, 2, 0, 1).contiguous().cpu().requires_grad_(True)
+    F.conv2d(xr, wr).backward(nchw(gy).double().cpu())
+    ref_w = wr.grad.permute(2, 3, 1, 0).contiguous().float().to(dev())
+    gw = torch.zeros(KH, KW, Cin, Cout, device=dev())
+    ops.conv_tc_wgrad_kwfold(x, gy, gw)
+    scale = float(ref_w.abs().max())
+    torch.testing.assert_close(gw, ref_w, rtol=2e-3, atol=2e-3 * scale)
+
+
 def test_conv_tc_fwd_channel_slices():
     """Input and output as channel slices of wider NHWC buffers (concat targets), untouched neighbours."""
     ops = _ops()
