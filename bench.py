@@ -152,22 +152,23 @@ def cpu_cfg1(n_timed=5, n_warm=2):
 def run_reference(args, rank):
     """CPU arm: oracle restatement of the same training step on the host cores (kind 'port': TensorFlow 1.14 / Keras 2.1.3
     cannot run in this image). Batch 32 per step, the driver's --steps timed steps (at least 5,
-    stopping early once 5 are done and 150 s have passed), 2 warm-ups, median."""
+    stopping early once 5 are done and 150 s have passed), the driver's --warmup untimed steps (1..5), median."""
     if rank != 0:
         return
     import torch
-    dt, nsteps, ncores = cpu_train_steps(max(5, args.steps), 2, budget_s=150.0)
+    nwarm = min(5, max(1, args.warmup))
+    dt, nsteps, ncores = cpu_train_steps(max(5, args.steps), nwarm, budget_s=150.0)
     ms = 1e3 * dt
     val = CPU_BATCH / dt
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
-           "steps": nsteps, "warmup": 2, "ms_per_step": ms, "higher_is_better": True,
+           "steps": nsteps, "warmup": nwarm, "ms_per_step": ms, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "Xception-SPNet train step fwd+bwd+YOLO-ellipse loss+Keras Adam, 384x512x1, batch 64/GPU",
                       "sample": "batch %d per step (bounded sample of the batch-64 workload, BASELINE.md section 3)" % CPU_BATCH,
                       "note": "reference CPU path = oracle restatement (TF1.14/Keras2.1.3 not runnable here)"},
            "cpu_baseline": {"value": val, "unit": "images/s", "cores": ncores, "kind": "port",
-                            "sample": "median of %d timed steps (2 warm-ups) of %d images, oracle torch %s CPU fp32, all host cores" % (
-                                nsteps, CPU_BATCH, torch.__version__)},
+                            "sample": "median of %d timed steps (%d warm-ups) of %d images, oracle torch %s CPU fp32, all host cores" % (
+                                nsteps, nwarm, CPU_BATCH, torch.__version__)},
            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
