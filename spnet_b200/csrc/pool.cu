@@ -119,70 +119,184 @@ __global__ void __launch_bounds__(256) maxpool_add_fwd_kernel(const T* __restric
     }
 }
 
-// gin[b,h,w,c] = sum over the (<= 2x2) windows containing (h,w) whose argmax is (h,w)
+// bf16 forward: the same result bit for bit with a third of the instructions (the kernel above is issue-bound in
+// bf16: 9 taps x 8 channels x (unpack, FMA, compare, two selects)). y = fma(v, a, b) is monotone in v for a fixed
+// channel (rounding is monotone), so max_t y_t = fma(max_t v_t, a, b) for a > 0, fma(min_t v_t, a, b) for a < 0 and
+// b for a = 0: the window maximum is taken on the raw bf16 pairs with packed max instructions on the KEY
+// (v & zmask) ^ smask (sign flipped where a < 0, zero where a = 0), and the affine runs once per output.
+// Padding: a padded tap is read from its clamped address, which is another tap of the same window (TF 'SAME'
+// pads at most one row / column per side), so it can never change the maximum; it carries the CODE of the tap
+// it duplicates, so that the first-maximum scan below lands on a real position. argmax = first tap, in kh*3+kw
+// order, whose key equals the maximum (the fp32 kernel compares y instead of v: the two differ only where two
+// different bf16 inputs round to the same fp32 y, and then both are maxima of y).
+__global__ void __launch_bounds__(256) maxpool_add_fwd_bf16_kernel(const bf16* __restrict__ z, const float* __restrict__ a,
+                                                                   const float* __restrict__ b,
+                                                                   const bf16* __restrict__ res,
+                                                                   const float* __restrict__ ra,
+                                                                   const float* __restrict__ rb, bf16* __restrict__ out,
+                                                                   unsigned char* __restrict__ argmax, int B, int H,
+                                                                   int W, int C, int OH, int OW, int pt, int pl) {
+    constexpr int V = 8;
+    const int CV = C / V;
+    const int row = blockIdx.x;  // bi * OH + oh
+    const int bi = row / OH, oh = row - bi * OH;
+    const int items = OW * CV;
+    int ihc[3];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) ihc[kh] = min(max(oh * 2 - pt + kh, 0), H - 1);
+    const int ih0 = oh * 2 - pt;
+    for (int it = blockIdx.y * blockDim.x + threadIdx.x; it < items; it += blockDim.x * gridDim.y) {
+        const int ow = it / CV, cv = it - ow * CV;
+        const int c0 = cv * V;
+        const size_t idx = (size_t)row * items + it;
+        const int iw0 = ow * 2 - pl;
+        uint4 raw[9];
+        uint32_t code[9];  // kh*3+kw of the position actually read, in both halves of the word
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int iwc = min(max(iw0 + kw, 0), W - 1);
+                raw[kh * 3 + kw] = *reinterpret_cast<const uint4*>(z + (((size_t)bi * H + ihc[kh]) * W + iwc) * C + c0);
+                code[kh * 3 + kw] = (uint32_t)((ihc[kh] - ih0) * 3 + (iwc - iw0)) * 0x00010001u;
+            }
+        }
+        float av[V], bv[V];
+        uint32_t zm[4], sm[4];
+        if (a) {
+            load_coef<V>(a, c0, av);
+            load_coef<V>(b, c0, bv);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                zm[p] = (av[2 * p] != 0.f ? 0x0000ffffu : 0u) | (av[2 * p + 1] != 0.f ? 0xffff0000u : 0u);
+                sm[p] = (av[2 * p] < 0.f ? 0x00008000u : 0u) | (av[2 * p + 1] < 0.f ? 0x80000000u : 0u);
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) { zm[p] = 0xffffffffu; sm[p] = 0u; }
+#pragma unroll
+            for (int i = 0; i < V; ++i) { av[i] = 1.f; bv[i] = 0.f; }
+        }
+        uint32_t key[9][4], best[4], arg[4];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const uint32_t w[4] = {raw[t].x, raw[t].y, raw[t].z, raw[t].w};
+#pragma unroll
+            for (int p = 0; p < 4; ++p) key[t][p] = (w[p] & zm[p]) ^ sm[p];
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            __nv_bfloat162 m = *reinterpret_cast<const __nv_bfloat162*>(&key[0][p]);
+#pragma unroll
+            for (int t = 1; t < 9; ++t) m = __hmax2(m, *reinterpret_cast<const __nv_bfloat162*>(&key[t][p]));
+            best[p] = *reinterpret_cast<const uint32_t*>(&m);
+            arg[p] = 0u;
+#pragma unroll
+            for (int t = 8; t >= 0; --t) {  // last write wins = the first tap that holds the maximum
+                const uint32_t eq = __heq2_mask(*reinterpret_cast<const __nv_bfloat162*>(&key[t][p]), m);
+                arg[p] = (arg[p] & ~eq) | (code[t] & eq);
+            }
+        }
+        float y[V];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const uint32_t v = best[p] ^ sm[p];
+            y[2 * p] = fmaf(__uint_as_float(v << 16), av[2 * p], bv[2 * p]);
+            y[2 * p + 1] = fmaf(__uint_as_float(v & 0xffff0000u), av[2 * p + 1], bv[2 * p + 1]);
+        }
+        if (res) {
+            float rv[V];
+            load_vec(res + idx * V, rv);
+            if (ra) {
+                float rav[V], rbv[V];
+                load_coef<V>(ra, c0, rav);
+                load_coef<V>(rb, c0, rbv);
+#pragma unroll
+                for (int i = 0; i < V; ++i) y[i] += fmaf(rv[i], rav[i], rbv[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < V; ++i) y[i] += rv[i];
+            }
+        }
+        store_vec(out + idx * V, y);
+        if (argmax) {
+            const uint32_t w0 = (arg[0] & 0xffu) | ((arg[0] >> 8) & 0xff00u) | ((arg[1] & 0xffu) << 16) | ((arg[1] << 8) & 0xff000000u);
+            const uint32_t w1 = (arg[2] & 0xffu) | ((arg[2] >> 8) & 0xff00u) | ((arg[3] & 0xffu) << 16) | ((arg[3] << 8) & 0xff000000u);
+            *reinterpret_cast<uint2*>(argmax + idx * V) = make_uint2(w0, w1);
+        }
+    }
+}
+
+// gin[b,h,w,c] = sum over the (<= 2x2) windows containing (h,w) whose argmax is (h,w).
+// One item = a 2 x 2 block of input positions (rows 2j-pt, 2j-pt+1; columns 2i-pl, 2i-pl+1) x one channel vector:
+// the block lies inside window (j, i) - taps (0..1, 0..1) - and its first row / column are taps 2 of windows
+// j-1 / i-1, so FOUR (gout, argmax) loads serve four outputs (one item per input position needed four loads
+// each, 7 of every 16 of them for windows that cannot contain the position). The sums run in the order
+// (j,i), (j,i-1), (j-1,i), (j-1,i-1).
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ gout,
                                                           const unsigned char* __restrict__ argmax,
                                                           T* __restrict__ gin, int B, int H, int W, int C, int OH,
-                                                          int OW, int pt, int pl) {
+                                                          int OW, int pt, int pl, int HP, int WP) {
     constexpr int V = VecN<T>::N;
     const int CV = C / V;
-    const int row = blockIdx.x;  // bi * H + h
-    const int bi = row / H, h = row - bi * H;
-    const int items = W * CV;
-    // candidate window rows: kh with (h + pt - kh) even: kh = (h+pt)&1, and that + 2 (if <= 2) -- per CTA
-    int ohc[2], khc[2];
-    bool okh[2];
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        const int kh = ((h + pt) & 1) + 2 * a;
-        const int t = h + pt - kh;
-        const int oh = t >> 1;
-        okh[a] = kh <= 2 && t >= 0 && oh < OH;
-        ohc[a] = okh[a] ? oh : 0;
-        khc[a] = kh;
-    }
+    const int row = blockIdx.x;  // bi * HP + j
+    const int bi = row / HP, j = row - bi * HP;
+    const int items = WP * CV;
+    const int r0 = 2 * j - pt, r1 = r0 + 1;
+    const bool okr0 = r0 >= 0, okr1 = r1 < H;             // r0 < H and r1 >= 0 by construction of HP
+    const bool okj0 = j < OH, okj1 = j >= 1 && j - 1 < OH;  // windows j and j-1 exist
     for (int it = blockIdx.y * blockDim.x + threadIdx.x; it < items; it += blockDim.x * gridDim.y) {
-        const int w = it / CV, cv = it - w * CV;
+        const int i = it / CV, cv = it - i * CV;
         const int c0 = cv * V;
-        float acc[V];
-#pragma unroll
-        for (int i = 0; i < V; ++i) acc[i] = 0.f;
-        // loads first (clamped, flagged), compares after
+        const int q0 = 2 * i - pl, q1 = q0 + 1;
+        const bool okq0 = q0 >= 0, okq1 = q1 < W;
+        const bool oki0 = i < OW, oki1 = i >= 1 && i - 1 < OW;
+        // windows in summation order: (j,i) (j,i-1) (j-1,i) (j-1,i-1)
+        const bool okw[4] = {okj0 && oki0, okj0 && oki1, okj1 && oki0, okj1 && oki1};
         float g[4][V];
         uint32_t am[4][2];
-        int code[4];
-        bool ok[4];
-        int nc = 0;
-#pragma unroll
-        for (int a = 0; a < 2; ++a) {
-#pragma unroll
-            for (int bb = 0; bb < 2; ++bb) {
-                const int kw = ((w + pl) & 1) + 2 * bb;
-                const int u = w + pl - kw;
-                const int ow = u >> 1;
-                const bool okw = kw <= 2 && u >= 0 && ow < OW;
-                ok[nc] = okh[a] && okw;
-                code[nc] = khc[a] * 3 + kw;
-                const size_t o = (((size_t)bi * OH + ohc[a]) * OW + (okw ? ow : 0)) * C + c0;
-                load_vec(gout + o, g[nc]);
-                if (V == 8) {
-                    const uint2 q = *reinterpret_cast<const uint2*>(argmax + o);
-                    am[nc][0] = q.x; am[nc][1] = q.y;
-                } else {
-                    am[nc][0] = *reinterpret_cast<const uint32_t*>(argmax + o); am[nc][1] = 0;
-                }
-                ++nc;
-            }
-        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (!ok[k]) continue;
-#pragma unroll
-            for (int i = 0; i < V; ++i)
-                if ((int)((am[k][i >> 2] >> (8 * (i & 3))) & 0xffu) == code[k]) acc[i] += g[k][i];
+            const int oh = (k < 2) ? (okj0 ? j : 0) : (okj1 ? j - 1 : 0);
+            const int ow = (k & 1) ? (oki1 ? i - 1 : 0) : (oki0 ? i : 0);
+            const size_t o = (((size_t)bi * OH + oh) * OW + ow) * C + c0;
+            load_vec(gout + o, g[k]);
+            if (V == 8) {
+                const uint2 q = *reinterpret_cast<const uint2*>(argmax + o);
+                am[k][0] = q.x; am[k][1] = q.y;
+            } else {
+                am[k][0] = *reinterpret_cast<const uint32_t*>(argmax + o); am[k][1] = 0;
+            }
+            if (!okw[k]) { am[k][0] = 0xffffffffu; am[k][1] = 0xffffffffu; }  // code 255: matches no tap
         }
-        store_vec(gin + ((size_t)row * items + it) * V, acc);
+        float a00[V], a01[V], a10[V], a11[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const int sh = 8 * (e & 3), wd = e >> 2;
+            const uint32_t k0 = (am[0][wd] >> sh) & 0xffu, k1 = (am[1][wd] >> sh) & 0xffu;
+            const uint32_t k2 = (am[2][wd] >> sh) & 0xffu, k3 = (am[3][wd] >> sh) & 0xffu;
+            float s = 0.f;
+            if (k0 == 0u) s += g[0][e];
+            if (k1 == 2u) s += g[1][e];
+            if (k2 == 6u) s += g[2][e];
+            if (k3 == 8u) s += g[3][e];
+            a00[e] = s;
+            s = 0.f;
+            if (k0 == 1u) s += g[0][e];
+            if (k2 == 7u) s += g[2][e];
+            a01[e] = s;
+            s = 0.f;
+            if (k0 == 3u) s += g[0][e];
+            if (k1 == 5u) s += g[1][e];
+            a10[e] = s;
+            a11[e] = (k0 == 4u) ? g[0][e] : 0.f;
+        }
+        T* base = gin + (((size_t)bi * H + r0) * W + q0) * C + c0;
+        if (okr0 && okq0) store_vec(base, a00);
+        if (okr0 && okq1) store_vec(base + C, a01);
+        if (okr1 && okq0) store_vec(base + (size_t)W * C, a10);
+        if (okr1 && okq1) store_vec(base + (size_t)W * C + C, a11);
     }
 }
 
@@ -264,10 +378,14 @@ int spnet_maxpool3s2_add_fwd(const void* z, const float* a, const float* b, cons
                   "maxpool3s2_add_fwd: affine parameters come in pairs");
     const int OH = (H + 1) / 2, OW = (W + 1) / 2;
     const int V = dtype == SPNET_BF16 ? 8 : 4;
-    SPNET_DISPATCH_DTYPE(dtype, (maxpool_add_fwd_kernel<T><<<row_grid(B * OH, OW * (C / V)), 256, 0, stream>>>(
-                                    reinterpret_cast<const T*>(z), a, b, reinterpret_cast<const T*>(res), ra, rb,
-                                    reinterpret_cast<T*>(out), argmax, B, H, W, C, OH, OW, same_pad_before(H),
-                                    same_pad_before(W))));
+    if (dtype == SPNET_BF16)
+        maxpool_add_fwd_bf16_kernel<<<row_grid(B * OH, OW * (C / V)), 256, 0, stream>>>(
+            reinterpret_cast<const bf16*>(z), a, b, reinterpret_cast<const bf16*>(res), ra, rb, reinterpret_cast<bf16*>(out),
+            argmax, B, H, W, C, OH, OW, same_pad_before(H), same_pad_before(W));
+    else
+        maxpool_add_fwd_kernel<float><<<row_grid(B * OH, OW * (C / V)), 256, 0, stream>>>(
+            reinterpret_cast<const float*>(z), a, b, reinterpret_cast<const float*>(res), ra, rb,
+            reinterpret_cast<float*>(out), argmax, B, H, W, C, OH, OW, same_pad_before(H), same_pad_before(W));
     return spnet_check_launch("maxpool3s2_add_fwd");
 }
 
@@ -278,9 +396,11 @@ int spnet_maxpool3s2_bwd(const void* gout, const unsigned char* argmax, void* gi
     SPNET_REQUIRE(gout && argmax && gin, "maxpool3s2_bwd: null pointer");
     const int OH = (H + 1) / 2, OW = (W + 1) / 2;
     const int V = dtype == SPNET_BF16 ? 8 : 4;
-    SPNET_DISPATCH_DTYPE(dtype, (maxpool_bwd_kernel<T><<<row_grid(B * H, W * (C / V)), 256, 0, stream>>>(
+    const int pt = same_pad_before(H), pl = same_pad_before(W);
+    const int HP = (H - 1 + pt) / 2 + 1, WP = (W - 1 + pl) / 2 + 1;  // 2 x 2 blocks of input positions
+    SPNET_DISPATCH_DTYPE(dtype, (maxpool_bwd_kernel<T><<<row_grid(B * HP, WP * (C / V)), 256, 0, stream>>>(
                                     reinterpret_cast<const T*>(gout), argmax, reinterpret_cast<T*>(gin), B, H, W, C,
-                                    OH, OW, same_pad_before(H), same_pad_before(W))));
+                                    OH, OW, pt, pl, HP, WP)));
     return spnet_check_launch("maxpool3s2_bwd");
 }
 
@@ -293,9 +413,14 @@ int spnet_maxpool3s2_valid_fwd(const void* z, void* out, unsigned char* argmax, 
     SPNET_REQUIRE(z && out && H >= 3 && W >= 3, "maxpool3s2_valid_fwd: bad args");
     const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
     const int V = dtype == SPNET_BF16 ? 8 : 4;
-    SPNET_DISPATCH_DTYPE(dtype, (maxpool_add_fwd_kernel<T><<<row_grid(B * OH, OW * (C / V)), 256, 0, stream>>>(
-                                    reinterpret_cast<const T*>(z), nullptr, nullptr, nullptr, nullptr, nullptr,
-                                    reinterpret_cast<T*>(out), argmax, B, H, W, C, OH, OW, 0, 0)));
+    if (dtype == SPNET_BF16)
+        maxpool_add_fwd_bf16_kernel<<<row_grid(B * OH, OW * (C / V)), 256, 0, stream>>>(
+            reinterpret_cast<const bf16*>(z), nullptr, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<bf16*>(out), argmax,
+            B, H, W, C, OH, OW, 0, 0);
+    else
+        maxpool_add_fwd_kernel<float><<<row_grid(B * OH, OW * (C / V)), 256, 0, stream>>>(
+            reinterpret_cast<const float*>(z), nullptr, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<float*>(out),
+            argmax, B, H, W, C, OH, OW, 0, 0);
     return spnet_check_launch("maxpool3s2_valid_fwd");
 }
 
@@ -306,9 +431,10 @@ int spnet_maxpool3s2_valid_bwd(const void* gout, const unsigned char* argmax, vo
     SPNET_REQUIRE(gout && argmax && gin && H >= 3 && W >= 3, "maxpool3s2_valid_bwd: bad args");
     const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
     const int V = dtype == SPNET_BF16 ? 8 : 4;
-    SPNET_DISPATCH_DTYPE(dtype, (maxpool_bwd_kernel<T><<<row_grid(B * H, W * (C / V)), 256, 0, stream>>>(
+    const int HP = (H - 1) / 2 + 1, WP = (W - 1) / 2 + 1;
+    SPNET_DISPATCH_DTYPE(dtype, (maxpool_bwd_kernel<T><<<row_grid(B * HP, WP * (C / V)), 256, 0, stream>>>(
                                     reinterpret_cast<const T*>(gout), argmax, reinterpret_cast<T*>(gin), B, H, W, C, OH, OW,
-                                    0, 0)));
+                                    0, 0, HP, WP)));
     return spnet_check_launch("maxpool3s2_valid_bwd");
 }
 

@@ -327,6 +327,54 @@ def test_maxpool_add_fwd_bwd(dtype, shape):
     torch.testing.assert_close(sub, z[:, ::2, ::2, :].contiguous())
 
 
+@pytest.mark.parametrize("shape", [(2, 24, 32, 64), (2, 23, 31, 64), (1, 7, 9, 128)])
+def test_maxpool_bf16_exact_and_ties(shape):
+    """bf16 pooling takes the maximum on the raw inputs (monotone affine): the output must equal the fp32 formula bit
+    for bit, also with zero / negative scales and with many equal inputs, and the gradient must go to the FIRST
+    maximum of every window (torch's rule as well)."""
+    ops = _ops()
+    torch.manual_seed(9)
+    B, H, W, C = shape
+    z = torch.randint(-3, 4, shape, device=dev()).float().bfloat16()       # seven distinct values: ties everywhere
+    a = torch.randn(C, device=dev())
+    a[::5] = 0.0
+    b = torch.randn(C, device=dev()) * 0.2
+    OH, OW = (H + 1) // 2, (W + 1) // 2
+    argmax = torch.empty(B, OH, OW, C, device=dev(), dtype=torch.uint8)
+    out = ops.maxpool3s2_add_fwd(z, a, b, argmax=argmax)
+    yr = torch.addcmul(b, z.float(), a).requires_grad_(True)                # fma(v, a, b) like the kernel
+    ref = tf_same_maxpool_ref(yr)
+    assert torch.equal(out, ref.detach().bfloat16())
+    g = torch.randn(B, OH, OW, C, device=dev()).bfloat16()
+    ref.backward(g.float())
+    gin = ops.maxpool3s2_bwd(g, argmax, H, W)
+    live = (a != 0).view(1, 1, 1, C)     # a = 0: every tap is a maximum; both pick the first, but y is constant
+    torch.testing.assert_close((gin.float() * live), (yr.grad * live).bfloat16().float(), rtol=1e-2, atol=1e-2)
+    # gradient mass is conserved per channel whatever the tie rule
+    torch.testing.assert_close(gin.float().sum((0, 1, 2)), g.float().sum((0, 1, 2)), rtol=2e-2, atol=0.3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 35, 35, 64), (1, 17, 20, 128), (2, 8, 9, 32)])
+def test_maxpool_valid_fwd_bwd(dtype, shape):
+    ops = _ops()
+    torch.manual_seed(10)
+    B, H, W, C = shape
+    x = torch.randn(shape, device=dev()).to(dtype)
+    OH, OW = (H - 3) // 2 + 1, (W - 3) // 2 + 1
+    out = torch.empty(B, OH, OW, C, device=dev(), dtype=dtype)
+    argmax = torch.empty(B, OH, OW, C, device=dev(), dtype=torch.uint8)
+    ops.maxpool3s2_valid_fwd(x, out, argmax)
+    xr = x.float().requires_grad_(True)
+    ref = nhwc(F.max_pool2d(nchw(xr), 3, 2))
+    assert torch.equal(out.float(), ref.detach())
+    g = torch.randn(B, OH, OW, C, device=dev()).to(dtype)
+    ref.backward(g.float())
+    gin = torch.full(shape, float("nan"), device=dev(), dtype=dtype)
+    ops.maxpool3s2_valid_bwd(g, argmax, gin)
+    torch.testing.assert_close(gin.float(), xr.grad, **tol(dtype))
+
+
 # ------------------------------------------------------------------ stem / block1
 def leaky(v):
     return F.leaky_relu(v, 0.1)
