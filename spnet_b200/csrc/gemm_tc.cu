@@ -21,6 +21,16 @@
 #include "tma.cuh"
 #include <stdlib.h>
 
+#ifdef SPNET_GEMM_TRACE
+// diagnostic build only (tests/micro/gemm_trace.py): per-CTA cycle stamps of the kernel's phases
+__device__ unsigned long long g_gemm_trace[256 * 16];
+#define TRACE(slot) do { g_gemm_trace[blockIdx.x * 16 + (slot)] = (unsigned long long)clock64(); } while (0)
+#define TRACE_G(slot) do { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_gemm_trace[blockIdx.x * 16 + (slot)] = t_; } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#define TRACE_G(slot) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int BM = 128;          // UMMA M (cta_group::1)
@@ -189,6 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]);
     const uint32_t tempty0 = smem_u32(&bars[2 * STAGES + 2]);
 
+    if (threadIdx.x == 0) { TRACE(0); TRACE_G(8); }
     if (threadIdx.x == 32) {  // descriptor fetch overlaps the barrier / TMEM set-up
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -217,6 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (CL > 1) cluster_sync_all(); else __syncthreads();  // barrier inits visible cluster-wide
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_holder;
+    if (threadIdx.x == 0) TRACE(1);
     pdl_wait();  // the set-up above overlapped the previous kernel's tail; global memory from here on
     // with CL = 2, tiles_m counts m-tile PAIRS; this CTA owns m-tile 2*pair + rank
 
@@ -345,6 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             for (int i = 0; i < nkb; ++i) {
                 mbar_wait(full0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (leader && u == 0 && i == 0) TRACE(2);
                 if (leader) {
                     const uint32_t a_lo = a_lo_base + s * STAGE_STEP, b_lo = b_lo_base + s * STAGE_STEP;
 #pragma unroll
@@ -356,6 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     // frees the smem stage (in every CTA of the cluster) when these MMAs retire
                     if (CL > 1) umma_commit_mc(empty0 + 8 * s, kMask, 1u); else umma_commit(empty0 + 8 * s, 1u);
                     if (i == nkb - 1) umma_commit(tfull0 + 8 * as, 1u);  // accumulator complete
+                    if (i == nkb - 1) { if (u == 0) TRACE(3); TRACE(4); }
                 }
                 __syncwarp();
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -408,6 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const uint32_t as = u & 1u;
             mbar_wait(tfull0 + 8 * as, (u >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (threadIdx.x == 64) { if (u == 0) TRACE(5); TRACE(6); }
 #pragma unroll 1
             for (int c = chalf; c < BN / 32; c += kEpiWarps / 4) {
                 uint32_t v[32];
@@ -537,6 +552,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (e_leader) mbar_arrive(tempty0 + 8 * as);
+            if (threadIdx.x == 64) { if (u == 0) TRACE(7); TRACE(9); }
             if (epi.colstats) {
                 // partial sums of this unit are visible after the barrier; the buffer alternates with the
                 // accumulator parity, so the next unit's writers never race with these reads
@@ -553,9 +569,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
         if (epi.colstats) flush_stats();
         if (e_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging may not die under a store
+        if (threadIdx.x == 64) TRACE(10);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     if (CL > 1) cluster_sync_all(); else __syncthreads();  // no CTA may exit while its peer still multicasts into it
+    if (threadIdx.x == 0) { TRACE(11); TRACE_G(12); }
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN))
                      : "memory");
@@ -649,6 +667,12 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
 }  // namespace
 
 extern "C" {
+
+#ifdef SPNET_GEMM_TRACE
+int spnet_gemm_trace_read(unsigned long long* host) {
+    return cudaMemcpyFromSymbol(host, g_gemm_trace, sizeof(g_gemm_trace)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 // Upper bound on the CTAs of the persistent tensor-core GEMM (0 = one per SM). The data-parallel engine lowers it while
 // a gradient all-reduce is in flight so that NCCL's resident CTAs and the GEMM never queue behind each other.
