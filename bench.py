@@ -421,7 +421,7 @@ def run_ours(args, rank, world):
         d[1] += ms
     gemm_shapes = [{"M": k[0], "N": k[1], "K": k[2], "a_mn": k[3], "b_mn": k[4], "launches_per_step": v[0] // psteps,
                     "us_each_eager": round(1e3 * v[1] / v[0], 1), "tflops": round(2.0 * k[0] * k[1] * k[2] / (v[1] / v[0] * 1e-3) / 1e12, 1)}
-                   for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:10]]
+                   for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:args.gemm_shapes]]
     dominant = max(roofs.values(), key=lambda r: r["share_of_step"])
     other = [r for r in roofs.values() if r is not dominant]
 
@@ -507,6 +507,7 @@ def main():
     ap.add_argument("--infer-frames", type=int, default=50_000, help="frames of the predict_spnet leg (whole job)")
     ap.add_argument("--infer-pool", type=int, default=512, help="distinct frames in the inference pool (cycled)")
     ap.add_argument("--quick", action="store_true", help="diagnostic runs: skip the CPU baseline and the per-family roofline legs")
+    ap.add_argument("--gemm-shapes", type=int, default=10, dest="gemm_shapes", help="how many GEMM shapes the per-shape table lists")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     args.steps_ref = max(1, min(args.steps, 3))

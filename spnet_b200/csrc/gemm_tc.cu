@@ -742,7 +742,7 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
     CUtensorMap ta, tb;
     int rc = make_operand_map(&ta, A, M, K, lda, a_mn != 0, BM);
     if (rc) return rc;
-    rc = make_operand_map(&tb, B, N, K, ldb, b_mn != 0, wide ? (pair ? 128 : 256) : 128);
+    rc = make_operand_map(&tb, B, N, K, ldb, b_mn != 0, wide ? (pair ? 128 : 256) : (N <= 64 ? 64 : 128));
     if (rc) return rc;
     CUtensorMap td;  // output boxes of the TMA-store epilogue: 32 x 32 bf16 or 32 x 16 fp32 (64-byte rows, SWIZZLE_64B)
     {
@@ -769,6 +769,9 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
     } while (0)
     if (pair) SPNET_GEMM_DISPATCH(256, 2);
     if (wide) SPNET_GEMM_DISPATCH(256, 1);
+    // N <= 64 (the data gradients into Xception's 64-channel block 1 output): 64-wide tiles - a 128-wide tile would
+    // spend half of its B traffic, MMA columns and epilogue on columns that do not exist
+    if (N <= 64) SPNET_GEMM_DISPATCH(64, 1);
     SPNET_GEMM_DISPATCH(128, 1);
 #undef SPNET_GEMM_DISPATCH
 }

@@ -227,7 +227,8 @@ def _gemm_case(M, N, K, a_mn, b_mn, out_mode, splits, stats, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
-@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (300, 728, 728), (1000, 256, 128), (64, 576, 1024), (128, 128, 2048)])
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (300, 728, 728), (1000, 256, 128), (64, 576, 1024), (128, 128, 2048),
+                                   (5000, 64, 128), (264, 32, 200)])
 def test_gemm_store(dtype, a_mn, b_mn, M, N, K):
     if a_mn and M % 8:
         pytest.skip("MN-major A needs M % 8 == 0 (TMA 16-byte stride)")
@@ -242,6 +243,8 @@ def test_gemm_splitk_atomic_and_f32_store(dtype):
     _gemm_case(728, 728, 3000 if dtype == torch.float32 else 3072, True, True, ops.OUT_ATOMIC, 4, False, dtype)
     _gemm_case(512, 576, 64, True, True, ops.OUT_F32, 1, False, dtype)
     _gemm_case(200, 264, 72, False, False, ops.OUT_F32, 1, True, dtype)
+    _gemm_case(128, 64, 4000, True, True, ops.OUT_ATOMIC, 5, False, dtype)     # 64-wide tiles, split-K
+    _gemm_case(288, 64, 520, True, True, ops.OUT_F32, 1, True, dtype)
 
 
 # ------------------------------------------------------------------ batch norm pieces
