@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(256) slab_reduce_kernel(const float* __restric
         const float4 b = *reinterpret_cast<const float4*>(bias + c);
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
-    for (int s = 0; s < nslabs; ++s) {
+#pragma unroll 8
+    for (int s = 0; s < nslabs; ++s) {  // the loads of eight slabs in flight, the adds in slab order
         const float4 v = *reinterpret_cast<const float4*>(slabs + s * slab_stride + r * lds + c);
         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }

@@ -207,7 +207,14 @@ class SPNetEngineBase:
         if self.deterministic and self.can_train:
             self._gacc = ops.stats_alloc(9 * 2048, self.device)
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-        self.dense_splits = max(1, min(64, (2 * self.n_sms) // max(1, -(-self.n_out // 128))))
+        # Dense head forward = split-K over the features: ONE wave of the persistent GEMM (bf16: 128 x 256 tiles when
+        # n_out >= 512, else 128 x 128 / 128 x 64) - a second, nearly empty wave doubled its time
+        if self.lowp:
+            tile_n = 256 if self.n_out >= 512 else (64 if self.n_out <= 64 else 128)
+            tiles = -(-self.n_out // tile_n) * -(-B // 128)
+            self.dense_splits = max(1, min(64, self.n_sms // max(1, tiles)))
+        else:  # the fp32 kernel is not persistent: a few CTAs per SM hide its latency
+            self.dense_splits = max(1, min(64, (2 * self.n_sms) // max(1, -(-self.n_out // 128))))
         self.head_slabs = torch.zeros(self.dense_splits, B, self.n_out, device=self.device, dtype=torch.float32)
 
     # ------------------------------------------------------------------ helpers
