@@ -13,6 +13,7 @@
 // through shared memory so that global stores are contiguous too. BatchNorm statistics and weight
 // gradients are accumulated in registers across all tiles of a CTA and reduced once at the end.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -646,10 +647,353 @@ __global__ void __launch_bounds__(kThreads, 1) conv_b1c1_wgrad_kernel(const T* _
     }
 }
 
+// =================================================================================================
+// Strip kernels for the 3 -> 3, 3x3 'same' stem convolutions (which 1) when W % 8 == 0: a thread owns a strip of
+// 8 consecutive output pixels of one row. The kernels above read one shared-memory word per multiply-add operand
+// (27 input reads + weight reads for 81 FMAs: bound by the shared-memory pipe, 15-25 % of the FP32 peak); here a
+// thread reads the 10-pixel x 3-channel input run of its strip once per filter row with eight 16-byte loads and
+// keeps it in registers: 24 loads for 648 FMAs. Same arithmetic (fp32 FMA in (ky, kx, ci) order per output) and
+// same results as the pixel-per-thread kernels.
+//   tile = 16 rows x 128 pixels, 256 threads = 16 rows x 16 strips; window = 18 rows x 130 pixels x 3, fp32,
+//   pixel x0-1 at float 0 of a row so that strip j starts at float 24*j (16-byte aligned)
+// Global memory is moved in aligned 16-byte chunks (W % 8 == 0 makes every row 16-byte aligned and every chunk
+// entirely inside or outside its row); the next tile's chunks are in flight while the current tile is computed.
+// =================================================================================================
+constexpr int SK_TH = 16, SK_TW = 128, SK_WR = SK_TH + 2, SK_WE = (SK_TW + 2) * 3, SK_RP = 392;
+
+template <typename T>
+struct StripWindow {
+    static constexpr int EPC = 16 / (int)sizeof(T);          // elements per 16-byte chunk
+    static constexpr int NCH = 3 * SK_TW / EPC + 2;           // chunks per window row (one before, one after the tile's 384)
+    static constexpr int PER = (SK_WR * NCH + kThreads - 1) / kThreads;
+    static constexpr int STAGE_BYTES = SK_WR * NCH * 16;      // raw window of one tile
+    static constexpr int STAGES = sizeof(T) == 2 ? 3 : 2;     // tiles in flight (cp.async groups)
+    static __device__ __forceinline__ bool inside(int idx, int H, int W, int y0, int x0, int* y, int* e0) {
+        const int wr = idx / NCH, m = idx - wr * NCH;
+        *y = y0 - 1 + wr;
+        *e0 = 3 * x0 + (m - 1) * EPC;
+        return idx < SK_WR * NCH && *y >= 0 && *y < H && *e0 >= 0 && *e0 + EPC <= 3 * W;
+    }
+    // raw 16-byte chunks of one tile's window, global -> shared, asynchronously (one cp.async group per call)
+    static __device__ __forceinline__ void issue(uint32_t stage, const T* __restrict__ img, int H, int W, int y0, int x0) {
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int idx = threadIdx.x + k * kThreads;
+            int y, e0;
+            if (inside(idx, H, W, y0, x0, &y, &e0))
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage + (uint32_t)idx * 16u),
+                             "l"(img + ((size_t)y * W) * 3 + e0)
+                             : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // the thread's own chunks (same index map as issue(): visible after its cp.async.wait_group) -> affine +
+    // activation (zero outside the image: padding follows the activation) -> fp32 window
+    static __device__ __forceinline__ void transform(const uint8_t* __restrict__ stage, float* __restrict__ sm, const float* sab,
+                                                     bool affine, int act, int H, int W, int y0, int x0) {
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int idx = threadIdx.x + k * kThreads;
+            if (idx >= SK_WR * NCH) break;
+            int y, e0;
+            const bool live = inside(idx, H, W, y0, x0, &y, &e0);
+            const int wr = idx / NCH, m = idx - wr * NCH;
+            const int w0 = (m - 1) * EPC + 3;      // window float index of the chunk's first element
+            int ch = ((m + 2) * EPC) % 3;          // channel of the chunk's first element (x0 * 3 is a multiple of 3)
+            float v[EPC];
+            const uint4 raw = live ? *reinterpret_cast<const uint4*>(stage + (size_t)idx * 16) : make_uint4(0u, 0u, 0u, 0u);
+            if (sizeof(T) == 2) {
+                const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    v[(2 * i) % EPC] = __uint_as_float(w[i] << 16);
+                    v[(2 * i + 1) % EPC] = __uint_as_float(w[i] & 0xffff0000u);
+                }
+            } else {
+                v[0] = __uint_as_float(raw.x); v[1 % EPC] = __uint_as_float(raw.y);
+                v[2 % EPC] = __uint_as_float(raw.z); v[3 % EPC] = __uint_as_float(raw.w);
+            }
+#pragma unroll
+            for (int i = 0; i < EPC; ++i) {
+                float x = 0.f;
+                if (live) {
+                    x = v[i];
+                    if (affine) x = apply_act(fmaf(x, sab[ch], sab[3 + ch]), act);
+                }
+                const int wi = w0 + i;
+                if (wi >= 0 && wi < SK_WE) sm[wr * SK_RP + wi] = x;
+                ch = ch == 2 ? 0 : ch + 1;
+            }
+        }
+    }
+    static constexpr size_t smem_bytes() { return (size_t)SK_WR * SK_RP * 4 + (size_t)STAGES * STAGE_BYTES; }
+};
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 24 consecutive elements (8 pixels x 3 channels) of a 16-byte aligned strip <-> fp32 registers
+template <typename T> __device__ __forceinline__ void load_strip(const T* p, float (&v)[24]) {
+    if (sizeof(T) == 2) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const uint4 r = reinterpret_cast<const uint4*>(p)[q];
+            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                v[8 * q + 2 * i] = __uint_as_float(w[i] << 16);
+                v[8 * q + 2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const float4 r = reinterpret_cast<const float4*>(p)[q];
+            v[4 * q] = r.x; v[4 * q + 1] = r.y; v[4 * q + 2] = r.z; v[4 * q + 3] = r.w;
+        }
+    }
+}
+template <typename T> __device__ __forceinline__ void store_strip(T* p, const float (&v)[24]) {
+    if (sizeof(T) == 2) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            reinterpret_cast<uint4*>(p)[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                                        pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+    } else {
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+            reinterpret_cast<float4*>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+}
+
+// MODE 0: forward (+ BatchNorm statistics of the output as stored)   MODE 2: data gradient (flipped, transposed
+// kernel; times act'(mask_a * mask_z + mask_b) when mask_z is given)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreads, 2) conv3c3_strip_kernel(const T* __restrict__ in, const float* __restrict__ w,
+                                                                    const float* __restrict__ in_a,
+                                                                    const float* __restrict__ in_b, int act,
+                                                                    T* __restrict__ out, long long* __restrict__ stats,
+                                                                    const T* __restrict__ mask_z,
+                                                                    const float* __restrict__ mask_a,
+                                                                    const float* __restrict__ mask_b, int B, int H, int W,
+                                                                    int tiles_h, int tiles_w) {
+    typedef StripWindow<T> Win;
+    extern __shared__ __align__(16) uint8_t sk_smem[];
+    float* s_in = reinterpret_cast<float*>(sk_smem);
+    uint8_t* stages = sk_smem + (size_t)SK_WR * SK_RP * 4;
+    __shared__ __align__(16) float ws[27 * 4];  // [tap][ci][co padded to 4]
+    __shared__ float sab[12];
+    __shared__ float sred[(kThreads / 32) * 6];
+    for (int i = threadIdx.x; i < 81; i += kThreads) {
+        const int t = i / 9, rem = i % 9, ci = rem / 3, co = rem % 3;
+        ws[(t * 3 + ci) * 4 + co] = MODE == 2 ? w[((8 - t) * 3 + co) * 3 + ci] : w[i];
+    }
+    if (threadIdx.x < 3) {
+        sab[threadIdx.x] = in_a ? in_a[threadIdx.x] : 1.f;
+        sab[3 + threadIdx.x] = in_a ? in_b[threadIdx.x] : 0.f;
+        sab[6 + threadIdx.x] = (MODE == 2 && mask_z) ? mask_a[threadIdx.x] : 1.f;
+        sab[9 + threadIdx.x] = (MODE == 2 && mask_z) ? mask_b[threadIdx.x] : 0.f;
+    }
+    const int j = threadIdx.x & 15, r = threadIdx.x >> 4;
+    float ssum[3] = {0.f, 0.f, 0.f}, ssq[3] = {0.f, 0.f, 0.f};
+    const int n_tiles = B * tiles_h * tiles_w;
+    const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(stages);
+    // STAGES - 1 tiles ahead: one cp.async group per tile slot (empty groups past the end keep the count uniform)
+    auto issue = [&](int tile, int slot) {
+        if (tile < n_tiles) {
+            const TileXY t = tile_xy(tile, tiles_h, tiles_w, SK_TH, SK_TW);
+            Win::issue(stage0 + (uint32_t)slot * Win::STAGE_BYTES, in + (size_t)t.b * H * W * 3, H, W, t.r0, t.c0);
+        } else {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    };
+#pragma unroll
+    for (int p = 0; p < Win::STAGES - 1; ++p) issue(blockIdx.x + p * gridDim.x, p);
+    int slot = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const TileXY tc = tile_xy(tile, tiles_h, tiles_w, SK_TH, SK_TW);
+        cp_async_wait<Win::STAGES - 2>();  // this thread's chunks of `tile` have landed
+        __syncthreads();                   // the previous tile's readers are done with s_in
+        Win::transform(stages + (size_t)slot * Win::STAGE_BYTES, s_in, sab, in_a != nullptr, act, H, W, tc.r0, tc.c0);
+        __syncthreads();
+        {   // refill the slot the PREVIOUS iteration consumed (every thread is past that transform)
+            int ps = slot + Win::STAGES - 1;
+            if (ps >= Win::STAGES) ps -= Win::STAGES;
+            issue(tile + (Win::STAGES - 1) * (int)gridDim.x, ps);
+        }
+        if (++slot == Win::STAGES) slot = 0;
+        const int y = tc.r0 + r, x = tc.c0 + 8 * j;
+        if (y >= H || x >= W) continue;  // whole strip outside (W % 8 == 0): nothing to compute or count
+        float acc[24];
+#pragma unroll
+        for (int i = 0; i < 24; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            float xin[32];
+            const float4* rp = reinterpret_cast<const float4*>(&s_in[(r + ky) * SK_RP + 24 * j]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 t4 = rp[q];
+                xin[4 * q] = t4.x; xin[4 * q + 1] = t4.y; xin[4 * q + 2] = t4.z; xin[4 * q + 3] = t4.w;
+            }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    const float4 wv = *reinterpret_cast<const float4*>(&ws[((ky * 3 + kx) * 3 + ci) * 4]);
+#pragma unroll
+                    for (int px = 0; px < 8; ++px) {
+                        const float v = xin[3 * (px + kx) + ci];
+                        acc[3 * px] = fmaf(v, wv.x, acc[3 * px]);
+                        acc[3 * px + 1] = fmaf(v, wv.y, acc[3 * px + 1]);
+                        acc[3 * px + 2] = fmaf(v, wv.z, acc[3 * px + 2]);
+                    }
+                }
+        }
+        const size_t o = (((size_t)tc.b * H + y) * W + x) * 3;
+        if (MODE == 2 && mask_z) {
+            float mz[24];
+            load_strip(mask_z + o, mz);
+#pragma unroll
+            for (int i = 0; i < 24; ++i) {
+                const float pre = fmaf(mz[i], sab[6 + i % 3], sab[9 + i % 3]);
+                if (!(pre > 0.f)) acc[i] = (act == 2) ? 0.1f * acc[i] : (act == 1 ? 0.f : acc[i]);
+            }
+        }
+        store_strip(out + o, acc);
+        if (MODE == 0 && stats) {
+#pragma unroll
+            for (int i = 0; i < 24; ++i) {
+                const float rr = round_to<T>(acc[i]);
+                ssum[i % 3] += rr;
+                ssq[i % 3] = fmaf(rr, rr, ssq[i % 3]);
+            }
+        }
+    }
+    if (MODE == 0 && stats) {
+        __syncthreads();
+#pragma unroll
+        for (int co = 0; co < 3; ++co) {
+            const float s_ = warp_sum(ssum[co]), q_ = warp_sum(ssq[co]);
+            if ((threadIdx.x & 31) == 0) {
+                sred[(threadIdx.x >> 5) * 6 + co] = s_;
+                sred[(threadIdx.x >> 5) * 6 + 3 + co] = q_;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            float t = 0.f;
+            for (int w_ = 0; w_ < kThreads / 32; ++w_) t += sred[w_ * 6 + threadIdx.x];
+            stat_add(stats, threadIdx.x, (double)t);
+        }
+    }
+}
+
+// weight gradient of the same convolution: 81 partial sums per thread, the strip's input run from shared memory
+// (8 x 16-byte loads per filter row), its 8 x 3 output gradients straight from global memory
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1) conv3c3_wgrad_strip_kernel(const T* __restrict__ in,
+                                                                          const float* __restrict__ in_a,
+                                                                          const float* __restrict__ in_b, int act,
+                                                                          const T* __restrict__ g, float* __restrict__ dw,
+                                                                          long long* __restrict__ dw_acc, int B, int H,
+                                                                          int W, int tiles_h, int tiles_w) {
+    typedef StripWindow<T> Win;
+    extern __shared__ __align__(16) uint8_t sk_smem[];
+    float* s_in = reinterpret_cast<float*>(sk_smem);
+    uint8_t* stages = sk_smem + (size_t)SK_WR * SK_RP * 4;
+    __shared__ float sab[6];
+    __shared__ float sacc[81];
+    if (threadIdx.x < 3) {
+        sab[threadIdx.x] = in_a ? in_a[threadIdx.x] : 1.f;
+        sab[3 + threadIdx.x] = in_a ? in_b[threadIdx.x] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 81; i += kThreads) sacc[i] = 0.f;
+    const int j = threadIdx.x & 15, r = threadIdx.x >> 4;
+    float acc[81];
+#pragma unroll
+    for (int i = 0; i < 81; ++i) acc[i] = 0.f;
+    const int n_tiles = B * tiles_h * tiles_w;
+    const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(stages);
+    float gv[24];
+    auto issue = [&](int tile, int slot) {
+        if (tile < n_tiles) {
+            const TileXY t = tile_xy(tile, tiles_h, tiles_w, SK_TH, SK_TW);
+            Win::issue(stage0 + (uint32_t)slot * Win::STAGE_BYTES, in + (size_t)t.b * H * W * 3, H, W, t.r0, t.c0);
+        } else {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    };
+#pragma unroll
+    for (int p = 0; p < Win::STAGES - 1; ++p) issue(blockIdx.x + p * gridDim.x, p);
+    int slot = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const TileXY tc = tile_xy(tile, tiles_h, tiles_w, SK_TH, SK_TW);
+        const int y = tc.r0 + r, x = tc.c0 + 8 * j;
+        const bool live = y < H && x < W;
+        if (live) load_strip(g + (((size_t)tc.b * H + y) * W + x) * 3, gv);  // in flight across the two barriers
+        cp_async_wait<Win::STAGES - 2>();
+        __syncthreads();
+        Win::transform(stages + (size_t)slot * Win::STAGE_BYTES, s_in, sab, in_a != nullptr, act, H, W, tc.r0, tc.c0);
+        __syncthreads();
+        {
+            int ps = slot + Win::STAGES - 1;
+            if (ps >= Win::STAGES) ps -= Win::STAGES;
+            issue(tile + (Win::STAGES - 1) * (int)gridDim.x, ps);
+        }
+        if (++slot == Win::STAGES) slot = 0;
+        if (!live) continue;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            float xin[32];
+            const float4* rp = reinterpret_cast<const float4*>(&s_in[(r + ky) * SK_RP + 24 * j]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 t4 = rp[q];
+                xin[4 * q] = t4.x; xin[4 * q + 1] = t4.y; xin[4 * q + 2] = t4.z; xin[4 * q + 3] = t4.w;
+            }
+#pragma unroll
+            for (int px = 0; px < 8; ++px)   // pixels in order: every partial sum adds its pixels left to right
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int ci = 0; ci < 3; ++ci) {
+                        const float v = xin[3 * (px + kx) + ci];
+#pragma unroll
+                        for (int co = 0; co < 3; ++co)
+                            acc[((ky * 3 + kx) * 3 + ci) * 3 + co] = fmaf(v, gv[3 * px + co], acc[((ky * 3 + kx) * 3 + ci) * 3 + co]);
+                    }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 81; ++i) acc[i] = warp_sum(acc[i]);
+    // the warps add their sums one after the other (fixed order: the CTA's partial is the same in every run)
+    for (int w_ = 0; w_ < kThreads / 32; ++w_) {
+        if ((threadIdx.x >> 5) == w_ && (threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int i = 0; i < 81; ++i) sacc[i] += acc[i];
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < 81; i += kThreads) {
+        if (dw_acc) stat_add(dw_acc, i, (double)sacc[i]);
+        else atomicAdd(dw + i, sacc[i]);
+    }
+}
+
 int persist_grid_tiles(long long n_tiles, int ctas_per_sm) {
     const long long cap = 148LL * ctas_per_sm;
     return (int)(n_tiles < cap ? n_tiles : cap);
 }
+
+// dynamic shared memory above 48 KB is a per-device opt-in of the function
+// (set on every call: the kernels share one function-pointer type, so a per-type "done" flag would be wrong, and the
+// call is host-side only)
+template <typename K> void strip_smem_optin(K kern, size_t bytes) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// SPNET_B200_NO_STRIP=1: the pixel-per-thread kernels for every width (comparison runs)
+const bool g_no_strip = getenv("SPNET_B200_NO_STRIP") != nullptr;
 
 }  // namespace
 
@@ -676,6 +1020,13 @@ int spnet_conv_small_fwd(int which, const void* in, const float* w, const float*
                                         reinterpret_cast<const float*>(in), w, in_a, in_b, act, reinterpret_cast<T*>(out),
                                         reinterpret_cast<T*>(skip), stats, nullptr, nullptr, nullptr, B, H, W, OH, OW, 1,
                                         1, th, tw)));
+    } else if (which == 1 && W % 8 == 0 && !g_no_strip) {
+        const int th = ceil_div(H, SK_TH), tw = ceil_div(W, SK_TW);
+        const int grid = persist_grid_tiles((long long)B * th * tw, 2);
+        SPNET_DISPATCH_DTYPE(dtype, (strip_smem_optin(conv3c3_strip_kernel<T, 0>, StripWindow<T>::smem_bytes()),
+                                     conv3c3_strip_kernel<T, 0><<<grid, kThreads, StripWindow<T>::smem_bytes(), stream>>>(
+                                        reinterpret_cast<const T*>(in), w, in_a, in_b, act, reinterpret_cast<T*>(out), stats,
+                                        nullptr, nullptr, nullptr, B, H, W, th, tw)));
     } else if (which == 1) {
         const int th = ceil_div(H, C3_TH), tw = ceil_div(W, C3_TW);
         const int grid = persist_grid_tiles((long long)B * th * tw, 2);
@@ -713,6 +1064,13 @@ int spnet_conv_small_wgrad(int which, const void* in, const float* in_a, const f
         SPNET_DISPATCH_DTYPE(dtype, (conv3out_wgrad_kernel<float, T, 1, 4, 2><<<grid, kThreads, 0, stream>>>(
                                         reinterpret_cast<const float*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g),
                                         dw, dw_acc, B, H, W, OH, OW, 1, 1, th, tw)));
+    } else if (which == 1 && W % 8 == 0 && !g_no_strip) {
+        const int th = ceil_div(H, SK_TH), tw = ceil_div(W, SK_TW);
+        const int grid = persist_grid_tiles((long long)B * th * tw, 1);
+        SPNET_DISPATCH_DTYPE(dtype, (strip_smem_optin(conv3c3_wgrad_strip_kernel<T>, StripWindow<T>::smem_bytes()),
+                                     conv3c3_wgrad_strip_kernel<T><<<grid, kThreads, StripWindow<T>::smem_bytes(), stream>>>(
+                                        reinterpret_cast<const T*>(in), in_a, in_b, act, reinterpret_cast<const T*>(g), dw,
+                                        dw_acc, B, H, W, th, tw)));
     } else if (which == 1) {
         const int th = ceil_div(H, C3W_TH), tw = ceil_div(W, C3_TW);
         const int grid = persist_grid_tiles((long long)B * th * tw, 2);
@@ -741,7 +1099,14 @@ int spnet_conv_small_dgrad(int which, const void* g, const float* w, const void*
                            cudaStream_t stream) {
     SPNET_REQUIRE(g && w && gin && B > 0 && H > 2 && W > 2, "conv_small_dgrad: bad args");
     SPNET_REQUIRE(!mask_z || (mask_a && mask_b), "conv_small_dgrad: mask needs its affine");
-    if (which == 1) {
+    if (which == 1 && W % 8 == 0 && !g_no_strip) {
+        const int th = ceil_div(H, SK_TH), tw = ceil_div(W, SK_TW);
+        const int grid = persist_grid_tiles((long long)B * th * tw, 2);
+        SPNET_DISPATCH_DTYPE(dtype, (strip_smem_optin(conv3c3_strip_kernel<T, 2>, StripWindow<T>::smem_bytes()),
+                                     conv3c3_strip_kernel<T, 2><<<grid, kThreads, StripWindow<T>::smem_bytes(), stream>>>(
+                                        reinterpret_cast<const T*>(g), w, nullptr, nullptr, act, reinterpret_cast<T*>(gin),
+                                        nullptr, reinterpret_cast<const T*>(mask_z), mask_a, mask_b, B, H, W, th, tw)));
+    } else if (which == 1) {
         // 'same' 3x3 stride 1: the data gradient is the convolution of g with the flipped, transposed kernel
         const int th = ceil_div(H, C3_TH), tw = ceil_div(W, C3_TW);
         const int grid = persist_grid_tiles((long long)B * th * tw, 2);
