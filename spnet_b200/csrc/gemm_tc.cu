@@ -133,6 +133,38 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask, 
         "h"(cta_mask), "r"(leader)
         : "memory");
 }
+// ---- CTA-pair MMA (cta_group::2): one thread of the pair's EVEN CTA issues a 256-row MMA over both CTAs' shared memory
+// (A: 128 rows from each CTA; B: half of the N columns from each), each CTA's TMEM receives its 128 rows. Both CTAs'
+// TMA loads complete on the even CTA's "full" barrier: in the shared::cluster window bit 24 of a CTA-local address
+// selects the CTA of the pair, clearing it addresses the even CTA (cute::Sm100MmaPeerBitMask).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint32_t leader) {  // arrives on `bar` in BOTH CTAs
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n\t}" ::"r"(bar),
+        "r"(leader), "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_even_cta, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_even_cta), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -157,23 +189,27 @@ __device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the four e
 // CL = 2: CTA pairs (thread-block cluster of 2 along M). Both CTAs of a pair work on the same
 // n-tile and k-range with adjacent m-tiles; each loads its own A tile and HALF of the shared B tile,
 // multicast by TMA into both CTAs' shared memory, so the pair reads B from L2 once.
-template <int BN, bool A_MN, bool B_MN, int STAGES, int CL, int CONV>
+// P2 (with CL = 2): the pair runs ONE cta_group::2 MMA per k-step instead of one cta_group::1 MMA per CTA over a
+// multicast copy of B: each CTA keeps only its half of the B tile (16 KB instead of 32 KB per stage: six ring stages
+// instead of four, a third less shared-memory traffic per k-block).
+template <int BN, bool A_MN, bool B_MN, int STAGES, int CL, int CONV, bool P2 = false>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmD, GemmEpi epi,
                                                               int M, int N, int K, int kb_per_split, int tiles_m,
                                                               int tiles_n, int n_units, ConvGeom cg) {
     static_assert(CONV == 0 || CL == 1, "convolution modes run without CTA pairs");
+    static_assert(!P2 || CL == 2, "pair MMA needs the CTA pair");
     constexpr uint32_t A_BYTES = BM * BK * 2;
-    constexpr uint32_t B_BYTES = BN * BK * 2;
+    constexpr uint32_t B_BYTES = (P2 ? BN / 2 : BN) * BK * 2;  // P2: this CTA's half of the N columns
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     // TMA boxes per k-block issued by THIS CTA: A is one 128-row box (K-major) or BM/64 atoms (MN-major);
     // B one box (K-major) or BN/64 atoms (MN-major), of which a CTA of a pair issues 1/CL (multicast)
     constexpr int NA_BOX = (A_MN || CONV == 2) ? BM / 64 : 1;
-    constexpr int NB_BOX = (B_MN || CONV == 2) ? BN / 64 / CL : 1;
+    constexpr int NB_BOX = (B_MN || CONV == 2) ? BN / 64 / CL : 1;  // (P2: BN / 2 columns = BN / 64 / 2 atoms)
     constexpr int N_BOX = NA_BOX + NB_BOX;
     constexpr uint32_t A_BOX_BYTES = A_BYTES / NA_BOX;
-    constexpr uint32_t B_BOX_BYTES = B_BYTES / (NB_BOX * CL);  // what one of this CTA's B boxes lands (in each CTA of the pair)
+    constexpr uint32_t B_BOX_BYTES = P2 ? B_BYTES / NB_BOX : B_BYTES / (NB_BOX * CL);  // what one of this CTA's B boxes lands
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -208,20 +244,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);  // one arrive.expect_tx per k-block
-            mbar_init(empty0 + 8 * s, CL);  // every CTA of the cluster must have consumed the stage
+            mbar_init(empty0 + 8 * s, P2 ? 1 : CL);  // every CTA's MMAs (P2: the pair's MMAs) must have consumed the stage
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull0 + 8 * a, 1);
-            mbar_init(tempty0 + 8 * a, kEpiWarps);  // one arrive per epilogue warp
+            mbar_init(tempty0 + 8 * a, P2 ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (P2: of both CTAs)
         }
         mbar_fence_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(&tmem_base_holder)),
-                     "r"((uint32_t)(2 * BN))
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (P2) {  // the same warp of both CTAs, same destination offset
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(&tmem_base_holder)),
+                         "r"((uint32_t)(2 * BN))
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(&tmem_base_holder)),
+                         "r"((uint32_t)(2 * BN))
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     pdl_trigger();
@@ -236,7 +280,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         // ---------------- TMA producer ----------------
         // every box of a k-block is issued by one elected thread, which announces the stage's bytes on its full
         // barrier (B boxes of a CTA pair land in both CTAs: each CTA expects CL x its own)
-        constexpr uint32_t my_bytes = NA_BOX * A_BOX_BYTES + NB_BOX * B_BOX_BYTES * CL;
+        // (P2: the even CTA announces the bytes landing in BOTH CTAs on its barrier; the odd CTA only issues its loads)
+        constexpr uint32_t my_bytes = P2 ? 2 * (A_BYTES + B_BYTES) : NA_BOX * A_BOX_BYTES + NB_BOX * B_BOX_BYTES * CL;
         uint32_t g0 = 0;  // k-blocks of the units before this one
         const uint32_t issuer = elect_one();
         for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
@@ -296,9 +341,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
                     const uint32_t sb = sa + A_BYTES;
                     const uint32_t bar = full0 + 8 * s;
-                    mbar_expect_tx(bar, my_bytes);
+                    if (!P2 || crank == 0) mbar_expect_tx(bar, my_bytes);
+                    if (P2) {
+                        const uint32_t fbar = bar & kPeerBitMask;  // the even CTA's barrier
+                        const int nh = n0 + (int)crank * (BN / 2);
 #pragma unroll
-                    for (int j = 0; j < N_BOX; ++j) {
+                        for (int j = 0; j < NA_BOX; ++j) {
+                            if (A_MN) tma_load_2d_2sm(sa + j * (BK * 128), &tmA, fbar, m0 + 64 * j, k0);
+                            else tma_load_2d_2sm(sa, &tmA, fbar, k0, m0);
+                        }
+#pragma unroll
+                        for (int jb = 0; jb < NB_BOX; ++jb) {
+                            if (B_MN) tma_load_2d_2sm(sb + jb * (BK * 128), &tmB, fbar, nh + 64 * jb, k0);
+                            else tma_load_2d_2sm(sb, &tmB, fbar, k0, nh);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < (P2 ? 0 : N_BOX); ++j) {
                         if (j < NA_BOX) {
                             if (CONV == 1) tma_load_4d(sa, &tmA, bar, kA, ax, ay, aimg);
                             else if (CONV == 2) tma_load_4d(sa + j * (BK * 128), &tmA, bar, m0 + 64 * j, ax, ay, aimg);
@@ -329,11 +388,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
             g0 += (uint32_t)nkb;
         }
-    } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        // instruction descriptor: fp32 accumulate, bf16 x bf16, majors, N>>3, M>>4
+    } else if (warp == 1 && (!P2 || crank == 0)) {
+        // ---------------- MMA issuer (P2: of the pair, in its even CTA) ----------------
+        // instruction descriptor: fp32 accumulate, bf16 x bf16, majors, N>>3, M>>4 (P2: 256 rows over the two CTAs)
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
-                               ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                               ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)((P2 ? 2 * BM : BM) >> 4) << 24);
         // Shared-memory descriptors differ between stages / k-steps only in the 14-bit address field of
         // the low word: build the constant parts once so the per-MMA issue cost is a couple of adds.
         const uint32_t a_lbo = A_MN ? (uint32_t)(BK * 128) : 0u, b_lbo = B_MN ? (uint32_t)(BK * 128) : 0u;
@@ -364,18 +424,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * A_KSTEP);
                         const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * B_KSTEP);
-                        umma_bf16(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u, 1u);
+                        if (P2) umma_bf16_2sm(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u, 1u);
+                        else umma_bf16(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u, 1u);
                     }
                     // frees the smem stage (in every CTA of the cluster) when these MMAs retire
-                    if (CL > 1) umma_commit_mc(empty0 + 8 * s, kMask, 1u); else umma_commit(empty0 + 8 * s, 1u);
-                    if (i == nkb - 1) umma_commit(tfull0 + 8 * as, 1u);  // accumulator complete
+                    if (P2) umma_commit_2sm(empty0 + 8 * s, 1u);
+                    else if (CL > 1) umma_commit_mc(empty0 + 8 * s, kMask, 1u);
+                    else umma_commit(empty0 + 8 * s, 1u);
+                    if (i == nkb - 1) {  // accumulator complete (P2: in both CTAs' TMEM)
+                        if (P2) umma_commit_2sm(tfull0 + 8 * as, 1u); else umma_commit(tfull0 + 8 * as, 1u);
+                    }
                     if (i == nkb - 1) { if (u == 0) TRACE(3); TRACE(4); }
                 }
                 __syncwarp();
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
-    } else {
+    } else if (warp >= 2) {
         // ---------------- epilogue warps ----------------
         const uint32_t e_leader = elect_one();  // this warp's TMA-store / barrier thread (always the same lane)
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -551,7 +616,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             // accumulator fully read: hand it back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (e_leader) mbar_arrive(tempty0 + 8 * as);
+            if (e_leader) {
+                if (P2) mbar_arrive_cluster((tempty0 + 8 * as) & kPeerBitMask);  // the even CTA's MMA warp waits for both
+                else mbar_arrive(tempty0 + 8 * as);
+            }
             if (threadIdx.x == 64) { if (u == 0) TRACE(7); TRACE(9); }
             if (epi.colstats) {
                 // partial sums of this unit are visible after the barrier; the buffer alternates with the
@@ -575,8 +643,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (CL > 1) cluster_sync_all(); else __syncthreads();  // no CTA may exit while its peer still multicasts into it
     if (threadIdx.x == 0) { TRACE(11); TRACE_G(12); }
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN))
-                     : "memory");
+        if (P2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN))
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN))
+                         : "memory");
     }
 }
 
@@ -614,13 +686,14 @@ int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long lon
 }
 
 // CONV 0: tiles_m_conv / ntaps unused. CONV 1: tiles_m_conv = number of pixel tiles. CONV 2: ntaps = cg.ntaps.
-template <int BN, bool A_MN, bool B_MN, int CL, int CONV = 0>
+template <int BN, bool A_MN, bool B_MN, int CL, int CONV = 0, bool P2 = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, GemmEpi epi, int M, int N, int K,
                 int splits, cudaStream_t stream, ConvGeom cg = ConvGeom(), int tiles_m_conv = 0) {
     // BN = 128: one ring stage traded for the second staging box; BN = 64 (narrow convolutions): deep ring
-    constexpr int STAGES = BN <= 64 ? 7 : (BN <= 128) ? 5 : 4;
-    constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + kEpiWarps * 2048 * (BN <= 128 ? 2 : 1);
-    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, CL, CONV>;
+    // (pair MMA: a CTA holds half of the B tile - six stages in the space of four)
+    constexpr int STAGES = P2 ? 6 : BN <= 64 ? 7 : (BN <= 128) ? 5 : 4;
+    constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (P2 ? BN / 2 : BN) * BK * 2) + 1024 + kEpiWarps * 2048 * (BN <= 128 ? 2 : 1);
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, CL, CONV, P2>;
     // per (instantiation, device): the dynamic shared-memory opt-in is a per-device function attribute
     static bool configured[64] = {};
     static int num_sms_dev[64] = {};
@@ -758,21 +831,30 @@ int spnet_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long 
         SPNET_REQUIRE(r == CUDA_SUCCESS, "gemm_bf16: cuTensorMapEncodeTiled (output) failed (%d) M=%d N=%d ldd=%lld", (int)r, M, N, ldd);
     }
     GemmEpi epi = {D, ldd, out_mode, 0, colstats};
-#define SPNET_GEMM_DISPATCH(BN_, CL_)                                                                    \
-    do {                                                                                                 \
-        if (a_mn) {                                                                                      \
-            if (b_mn) return launch_gemm<BN_, true, true, CL_>(ta, tb, td, epi, M, N, K, splits, stream);    \
-            return launch_gemm<BN_, true, false, CL_>(ta, tb, td, epi, M, N, K, splits, stream);             \
-        }                                                                                                \
-        if (b_mn) return launch_gemm<BN_, false, true, CL_>(ta, tb, td, epi, M, N, K, splits, stream);       \
-        return launch_gemm<BN_, false, false, CL_>(ta, tb, td, epi, M, N, K, splits, stream);                \
+#define SPNET_GEMM_DISPATCH(BN_, CL_, P2_)                                                                                  \
+    do {                                                                                                                    \
+        if (a_mn) {                                                                                                         \
+            if (b_mn) return launch_gemm<BN_, true, true, CL_, 0, P2_>(ta, tb, td, epi, M, N, K, splits, stream);          \
+            return launch_gemm<BN_, true, false, CL_, 0, P2_>(ta, tb, td, epi, M, N, K, splits, stream);                   \
+        }                                                                                                                   \
+        if (b_mn) return launch_gemm<BN_, false, true, CL_, 0, P2_>(ta, tb, td, epi, M, N, K, splits, stream);             \
+        return launch_gemm<BN_, false, false, CL_, 0, P2_>(ta, tb, td, epi, M, N, K, splits, stream);                      \
     } while (0)
-    if (pair) SPNET_GEMM_DISPATCH(256, 2);
-    if (wide) SPNET_GEMM_DISPATCH(256, 1);
+    // CTA pairs: by default one cta_group::1 MMA per CTA over a multicast copy of B. SPNET_B200_PAIR_MMA=1 selects the
+    // cta_group::2 form (one 256-row MMA per k-step over both CTAs' shared memory, half of B per CTA, six ring stages).
+    // Measured on B200 (round 2): the cta_group::2 form is SLOWER on every shape of this network - 12288x728x728
+    // 18.4-20.1 us against 17.5-18.2 us, the K-stacked weight gradient 333 against 294 us (938 / 1062 TFLOP/s),
+    // 49152x728x728 66-73 against 62-64 us, step 7.32 against 7.16 ms: the M = 128, N = 256 single-CTA MMA already runs
+    // at the cuBLAS-peak rate, shared-memory bandwidth was not the limiter, and the pair now advances in lock step
+    // (one "full" barrier for both CTAs' loads, +1.5 us of set-up).
+    static const bool pair_mma = getenv("SPNET_B200_PAIR_MMA") != nullptr;
+    if (pair && pair_mma) SPNET_GEMM_DISPATCH(256, 2, true);
+    if (pair) SPNET_GEMM_DISPATCH(256, 2, false);
+    if (wide) SPNET_GEMM_DISPATCH(256, 1, false);
     // N <= 64 (the data gradients into Xception's 64-channel block 1 output): 64-wide tiles - a 128-wide tile would
     // spend half of its B traffic, MMA columns and epilogue on columns that do not exist
-    if (N <= 64) SPNET_GEMM_DISPATCH(64, 1);
-    SPNET_GEMM_DISPATCH(128, 1);
+    if (N <= 64) SPNET_GEMM_DISPATCH(64, 1, false);
+    SPNET_GEMM_DISPATCH(128, 1, false);
 #undef SPNET_GEMM_DISPATCH
 }
 
