@@ -286,11 +286,13 @@ def run_ours(args, rank, world):
     del scratch_dev
 
     # ---- timed region 2: end to end from host buffers (pinned H2D of every batch + D2H of every step's loss).
-    #      The loss of step i is copied to pinned host memory asynchronously and read on the host while step i+1
-    #      runs (one step of pipelining, as a training loop that logs every step would do): every step's result still
-    #      reaches the host inside the timed region, the last one before the closing event.
-    loss_host = [torch.zeros(6).pin_memory() for _ in range(2)]
-    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    #      The loss of step i is copied to pinned host memory asynchronously and read on the host while steps i+1 and
+    #      i+2 are queued (a training loop that logs every step two steps late): every step's result still reaches the
+    #      host inside the timed region, the last ones before the closing event.
+    DEPTH = 3   # losses in flight: the host reads step i-2's loss while steps i-1 and i are queued, so one host hiccup
+    #             (the clock sampler forks nvidia-smi from this process) does not drain the GPU's queue
+    loss_host = [torch.zeros(6).pin_memory() for _ in range(DEPTH)]
+    loss_ev = [torch.cuda.Event() for _ in range(DEPTH)]
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
@@ -302,13 +304,15 @@ def run_ours(args, rank, world):
             o = ((i + 1) % 2) * B
             eng.prefetch_batch(Xp[o:o + B], Yp[o:o + B])  # next batch travels while this step computes (as Model.fit does)
         loss6 = eng.train_step(LR)
-        loss_host[i % 2].copy_(loss6, non_blocking=True)
-        loss_ev[i % 2].record()
-        if i > 0:
-            loss_ev[(i - 1) % 2].synchronize()
-            last = float(loss_host[(i - 1) % 2][0])
-    loss_ev[(args.steps - 1) % 2].synchronize()
-    last = float(loss_host[(args.steps - 1) % 2][0])
+        loss_host[i % DEPTH].copy_(loss6, non_blocking=True)
+        loss_ev[i % DEPTH].record()
+        if i >= DEPTH - 1:
+            j = i - (DEPTH - 1)
+            loss_ev[j % DEPTH].synchronize()
+            last = float(loss_host[j % DEPTH][0])
+    for j in range(max(0, args.steps - (DEPTH - 1)), args.steps):   # the remaining losses, before the closing event
+        loss_ev[j % DEPTH].synchronize()
+        last = float(loss_host[j % DEPTH][0])
     ev3.record()
     barrier()
     ms_e2e = ev2.elapsed_time(ev3)
@@ -427,6 +431,13 @@ def run_ours(args, rank, world):
 
     # ---- CPU baseline on this box's host cores: bounded sample of the same workload
     cpu = cpu_baseline() if (not args.quick and world == 1) else None   # N = 1 only (bench contract)
+    fit_leg = None
+    if world == 1 and not args.quick:
+        del eng
+        torch.cuda.empty_cache()
+        nfit = min(512, Xu_inf.shape[0]) // BATCH_PER_GPU * BATCH_PER_GPU
+        if nfit:
+            fit_leg = run_fit(args, dev, Xu_inf[:nfit], args.fit_Y[:nfit])
 
     out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -444,7 +455,7 @@ def run_ours(args, rank, world):
                    "h2d_bound_images_per_s": round(B * world / (B * H * W / (h2d_gbps * 1e9)), 1)},
            "gpu_launches": int(launches_per_step * args.steps * 2),
            "roofline": dominant, "roofline_other": other, "kernel_breakdown": breakdown, "eager_step_ms": total_ms / psteps, "gemm_shapes": gemm_shapes,
-           "peaks": peaks, "inference": infer, "cpu_baseline": cpu, "dp_timeline_ms": dp_timeline}
+           "peaks": peaks, "inference": infer, "fit": fit_leg, "cpu_baseline": cpu, "dp_timeline_ms": dp_timeline}
     print(json.dumps(out), flush=True)
 
 
@@ -489,6 +500,32 @@ def run_inference(args, rank, world, dev, Xu_inf, barrier):
                     "model writes a few rows per frame"}
 
 
+def run_fit(args, dev, Xu, Y):
+    """The training loop a user runs: SPNetModel.fit (reference call site train_spnet.py:118-128) on HOST arrays -
+    shuffled batches gathered on the host, pinned staging, H2D on the copy stream one batch ahead, CUDA-graph step,
+    epoch loss read back. Two passes over a pool of host frames; the second epoch (graph already captured) is timed
+    with the host clock around fit()."""
+    import torch
+    import spnet.config as cf
+    from spnet import models
+    cf.compute_dtype, cf.basemodel, cf.model_type = "bf16", args.backbone, "big"
+    B = BATCH_PER_GPU
+    model = models.SPNetModel((H, W, 1), Y0size=N_OUT, quick_setup=True, backbone=args.backbone)
+    model.compile(optimizer=models.Adam(lr=LR))
+    out = {}
+    for label, X in (("uint8_frames", Xu), ("float32_frames", normalise_host(Xu))):
+        steps = X.shape[0] // B
+        model.fit(X, Y, batch_size=B, epochs=1, verbose=0)           # engine set-up, warm-up, graph capture
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.fit(X, Y, batch_size=B, epochs=2, verbose=0)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out[label] = {"images_per_s": 2 * steps * B / dt, "ms_per_step": 1e3 * dt / (2 * steps), "steps_timed": 2 * steps}
+    out["api"] = "SPNetModel.fit(X, Y, batch_size=%d) on host numpy arrays of %d frames, shuffled, host wall clock" % (B, Xu.shape[0])
+    return out
+
+
 def cpu_baseline():
     """Bounded CPU sample inside the default run: 5 timed training steps (2 warm-ups) of batch 32 + configs[0]."""
     dt, nsteps, ncores = cpu_train_steps(5, 2)
@@ -520,8 +557,9 @@ def main():
     # synthetic frames first: the generator forks worker processes, which must happen before CUDA / NCCL exist here
     nw = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
     Xu, Y = make_pool_u8(2 * BATCH_PER_GPU, 1_000_000 * rank, workers=nw)
-    Xu_inf, _ = make_pool_u8(args.infer_pool, 2_000_000 + 1_000_000 * rank, workers=nw)
+    Xu_inf, Y_inf = make_pool_u8(args.infer_pool, 2_000_000 + 1_000_000 * rank, workers=nw)
     args.pools = (Xu, Y, Xu_inf)
+    args.fit_Y = Y_inf
     # keep stdout clean for the single JSON line (NCCL prints its version banner to stdout)
     real_stdout = os.dup(1)
     os.dup2(2, 1)

@@ -69,8 +69,6 @@ class SPNetEngineBase:
         self._alloc_activations()
         self.step_count = 0
         self.graph = None
-        self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
-        self._seed_host = torch.zeros(1, dtype=torch.int64).pin_memory()
         self.lr_t_dev = torch.zeros(1, device=self.device, dtype=torch.float32)
         self.seed_dev = torch.zeros(1, device=self.device, dtype=torch.int64)
         self.base_seed = int(seed)
@@ -520,10 +518,10 @@ class SPNetEngineBase:
         """Host side of Keras Adam: t += 1, lr_t = lr*sqrt(1-b2^t)/(1-b1^t) -> device scalar."""
         self.step_count += 1
         t = self.step_count
-        self._lr_host[0] = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
-        self.lr_t_dev.copy_(self._lr_host, non_blocking=True)
-        self._seed_host[0] = (self.base_seed * 1000003 + t) & 0x7FFFFFFFFFFFFFFF
-        self.seed_dev.copy_(self._seed_host, non_blocking=True)
+        # by-value kernel arguments (fill), not asynchronous copies from a reused pinned scalar: the host may be several
+        # steps ahead of the GPU, and a pinned buffer is read when the copy EXECUTES
+        self.lr_t_dev.fill_(lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t))
+        self.seed_dev.fill_((self.base_seed * 1000003 + t) & 0x7FFFFFFFFFFFFFFF)
 
     def capture(self):
         """Capture fwd+loss+bwd(+Adam) into one CUDA graph (call after one eager warm-up step)."""
