@@ -43,8 +43,57 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback (B200_PROFILING.md)")
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+class ClockSampler:
+    """SM clock / throttle reasons while the timed region runs, sampled by a SEPARATE nvidia-smi process every 100 ms
+    (the profiling recipe's clocks line). An in-process NVML poll takes driver locks that kernel launches from this
+    process need: the end-to-end leg, whose host thread must keep the GPU's queue fed step by step, lost up to 40 % in
+    some runs to exactly that; the in-process poll is only the fallback when nvidia-smi cannot be started."""
+    FIELDS = ["clocks.sm", "clocks.max.sm", "clocks_event_reasons.hw_slowdown", "clocks_event_reasons.hw_thermal_slowdown",
+              "clocks_event_reasons.sw_thermal_slowdown", "clocks_event_reasons.sw_power_cap"]
+
+    def __init__(self, index):
+        vis = [t.strip() for t in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if t.strip()]
+        self.smi_id = vis[index] if index < len(vis) else str(index)   # nvidia-smi counts physical devices
+        self.index, self.proc, self.thread = index, None, None
+
+    def start(self):
+        import subprocess
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.smi_id, "--query-gpu=" + ",".join(self.FIELDS),
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            self.thread = _NvmlPoll(self.index)
+            self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return self.thread.stop() if self.thread is not None else {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        import signal
+        self.proc.send_signal(signal.SIGINT)
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        mhz, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in (out or "").splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 6 or not f[0].isdigit():
+                continue
+            mhz.append(int(f[0]))
+            mx = int(f[1]) if f[1].isdigit() else mx
+            for k, v in zip(names, f[2:6]):
+                if v == "Active":
+                    reasons.add(k)
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "sampler": "nvidia-smi -lms 100 (separate process), %d samples" % len(mhz)}
+
+
+class _NvmlPoll(threading.Thread):
+    """Fallback: in-process NVML poll, twice a second."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -75,13 +124,13 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.5)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "sampler": "in-process NVML poll"}
 
 
 def make_pool(n, seed0):

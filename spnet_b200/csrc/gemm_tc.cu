@@ -192,7 +192,11 @@ __device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the four e
 // P2 (with CL = 2): the pair runs ONE cta_group::2 MMA per k-step instead of one cta_group::1 MMA per CTA over a
 // multicast copy of B: each CTA keeps only its half of the B tile (16 KB instead of 32 KB per stage: six ring stages
 // instead of four, a third less shared-memory traffic per k-block).
-template <int BN, bool A_MN, bool B_MN, int STAGES, int CL, int CONV, bool P2 = false>
+// BRES (CONV 1, one n-tile, few k-blocks): the whole B operand (the convolution's weights, <= 72 KB) is loaded into
+// shared memory ONCE per CTA and stays there for all of its pixel tiles; the ring then carries A boxes only. Narrow
+// convolutions are bound by L2 -> SM delivery (a 128x64x64 k-block is 0.09 us of MMA), and re-fetching the weights for
+// every tile was a third of that traffic.
+template <int BN, bool A_MN, bool B_MN, int STAGES, int CL, int CONV, bool P2 = false, bool BRES = false>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmD, GemmEpi epi,
@@ -202,7 +206,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     static_assert(!P2 || CL == 2, "pair MMA needs the CTA pair");
     constexpr uint32_t A_BYTES = BM * BK * 2;
     constexpr uint32_t B_BYTES = (P2 ? BN / 2 : BN) * BK * 2;  // P2: this CTA's half of the N columns
-    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    static_assert(!BRES || (CONV == 1 && CL == 1), "resident B is a mode of the forward-type implicit convolution");
+    constexpr uint32_t STAGE_BYTES = A_BYTES + (BRES ? 0u : B_BYTES);
     // TMA boxes per k-block issued by THIS CTA: A is one 128-row box (K-major) or BM/64 atoms (MN-major);
     // B one box (K-major) or BN/64 atoms (MN-major), of which a CTA of a pair issues 1/CL (multicast)
     constexpr int NA_BOX = (A_MN || CONV == 2) ? BM / 64 : 1;
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES + 5];
     __shared__ uint32_t tmem_base_holder;
     __shared__ float sstat[2][2][4][BN];  // [accumulator parity][sum | sumsq][lane quadrant][column]
 
@@ -224,9 +229,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // two where shared memory allows (BN = 128: the HBM-bound shapes), so a box is filled while the previous
     // one is still being read out
     constexpr int SD = BN <= 128 ? 2 : 1;
-    const uint32_t stage_out0 = smem_u32(smem) + STAGES * STAGE_BYTES;
-    uint32_t sbox = 0, last_box = 0;  // staging box this warp fills next; address of the one it filled last
     const int total_kb = (K + BK - 1) / BK;
+    const uint32_t resb0 = smem_u32(smem) + STAGES * STAGE_BYTES;  // BRES: total_kb B tiles, k-block after k-block
+    const uint32_t stage_out0 = resb0 + (BRES ? (uint32_t)total_kb * B_BYTES : 0u);
+    uint32_t sbox = 0, last_box = 0;  // staging box this warp fills next; address of the one it filled last
     const uint32_t crank = CL > 1 ? cluster_cta_rank() : 0u;
     const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
     constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
@@ -234,6 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const uint32_t empty0 = smem_u32(&bars[STAGES]);
     const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]);
     const uint32_t tempty0 = smem_u32(&bars[2 * STAGES + 2]);
+    const uint32_t bres_bar = smem_u32(&bars[2 * STAGES + 4]);
 
     if (threadIdx.x == 0) { TRACE(0); TRACE_G(8); }
     if (threadIdx.x == 32) {  // descriptor fetch overlaps the barrier / TMEM set-up
@@ -246,6 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             mbar_init(full0 + 8 * s, 1);  // one arrive.expect_tx per k-block
             mbar_init(empty0 + 8 * s, P2 ? 1 : CL);  // every CTA's MMAs (P2: the pair's MMAs) must have consumed the stage
         }
+        mbar_init(bres_bar, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull0 + 8 * a, 1);
             mbar_init(tempty0 + 8 * a, P2 ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (P2: of both CTAs)
@@ -281,9 +289,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         // every box of a k-block is issued by one elected thread, which announces the stage's bytes on its full
         // barrier (B boxes of a CTA pair land in both CTAs: each CTA expects CL x its own)
         // (P2: the even CTA announces the bytes landing in BOTH CTAs on its barrier; the odd CTA only issues its loads)
-        constexpr uint32_t my_bytes = P2 ? 2 * (A_BYTES + B_BYTES) : NA_BOX * A_BOX_BYTES + NB_BOX * B_BOX_BYTES * CL;
+        constexpr uint32_t my_bytes = P2 ? 2 * (A_BYTES + B_BYTES)
+                                         : NA_BOX * A_BOX_BYTES + (BRES ? 0u : NB_BOX * B_BOX_BYTES * CL);
         uint32_t g0 = 0;  // k-blocks of the units before this one
         const uint32_t issuer = elect_one();
+        if (BRES && issuer && cluster_id < n_units) {  // the weights, once: k-block kb = (tap, channel block)
+            mbar_expect_tx(bres_bar, (uint32_t)total_kb * B_BYTES);
+            int tp = 0, cb = 0;
+            for (int kb = 0; kb < total_kb; ++kb) {
+                const int kA = cb * BK;
+                const int kB = kA + (cg.b_tap_on_k ? tp * cg.b_tap_stride : 0);
+                const int nB = cg.b_tap_on_k ? 0 : tp * cg.b_tap_stride;
+                const uint32_t dst = resb0 + (uint32_t)kb * B_BYTES;
+#pragma unroll
+                for (int jb = 0; jb < NB_BOX; ++jb) {
+                    if (B_MN) tma_load_2d(dst + jb * (BK * 128), &tmB, bres_bar, nB + 64 * jb, kB);
+                    else tma_load_2d(dst, &tmB, bres_bar, kB, nB);
+                }
+                if (++cb == cg.cin_blocks) { cb = 0; ++tp; }
+            }
+        }
         for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
             const int n0 = (unit % tiles_n) * BN;
             const int mt = (unit / tiles_n) % tiles_m;
@@ -357,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         }
                     }
 #pragma unroll
-                    for (int j = 0; j < (P2 ? 0 : N_BOX); ++j) {
+                    for (int j = 0; j < (P2 ? 0 : BRES ? NA_BOX : N_BOX); ++j) {
                         if (j < NA_BOX) {
                             if (CONV == 1) tma_load_4d(sa, &tmA, bar, kA, ax, ay, aimg);
                             else if (CONV == 2) tma_load_4d(sa + j * (BK * 128), &tmA, bar, m0 + 64 * j, ax, ay, aimg);
@@ -399,12 +424,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const uint32_t a_lbo = A_MN ? (uint32_t)(BK * 128) : 0u, b_lbo = B_MN ? (uint32_t)(BK * 128) : 0u;
         const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B, version 1, SWIZZLE_128B
         const uint32_t a_lo_base = ((a_lbo >> 4) << 16) + ((smem_u32(smem) & 0x3ffffu) >> 4);
-        const uint32_t b_lo_base = ((b_lbo >> 4) << 16) + (((smem_u32(smem) + A_BYTES) & 0x3ffffu) >> 4);
+        const uint32_t b_lo_base = ((b_lbo >> 4) << 16) + (((BRES ? resb0 : smem_u32(smem) + A_BYTES) & 0x3ffffu) >> 4);
         constexpr uint32_t A_KSTEP = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
         constexpr uint32_t B_KSTEP = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
         constexpr uint32_t STAGE_STEP = STAGE_BYTES >> 4;
         const uint32_t leader = elect_one();  // the one thread that issues (and commits) every MMA
         uint32_t s = 0, ph = 0, u = 0;
+        if (BRES && cluster_id < n_units) mbar_wait(bres_bar, 0u);  // the resident weights have landed
         for (int unit = cluster_id; unit < n_units; unit += n_clusters, ++u) {
             int rest = unit / (tiles_n * tiles_m);
             if (CONV == 2) rest /= cg.ntaps;
@@ -419,7 +445,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (leader && u == 0 && i == 0) TRACE(2);
                 if (leader) {
-                    const uint32_t a_lo = a_lo_base + s * STAGE_STEP, b_lo = b_lo_base + s * STAGE_STEP;
+                    const uint32_t a_lo = a_lo_base + s * STAGE_STEP;
+                    const uint32_t b_lo = b_lo_base + (BRES ? (uint32_t)(kb_begin + i) * (B_BYTES >> 4) : s * STAGE_STEP);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * A_KSTEP);
@@ -656,6 +683,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 // host side
 // ---------------------------------------------------------------------------------
 int g_cta_cap = 0;  // 0 = every SM
+constexpr int kMaxResidentKb = 9;  // resident-B convolutions: at most 9 k-blocks of 64-wide weights (72 KB)
 // operand with `rows` along M/N and `kdim` along K; ld in elements
 int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long long kdim, long long ld, bool mn_major,
                      int tile_rows) {
@@ -686,14 +714,16 @@ int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long lon
 }
 
 // CONV 0: tiles_m_conv / ntaps unused. CONV 1: tiles_m_conv = number of pixel tiles. CONV 2: ntaps = cg.ntaps.
-template <int BN, bool A_MN, bool B_MN, int CL, int CONV = 0, bool P2 = false>
+template <int BN, bool A_MN, bool B_MN, int CL, int CONV = 0, bool P2 = false, bool BRES = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, GemmEpi epi, int M, int N, int K,
                 int splits, cudaStream_t stream, ConvGeom cg = ConvGeom(), int tiles_m_conv = 0) {
     // BN = 128: one ring stage traded for the second staging box; BN = 64 (narrow convolutions): deep ring
     // (pair MMA: a CTA holds half of the B tile - six stages in the space of four)
     constexpr int STAGES = P2 ? 6 : BN <= 64 ? 7 : (BN <= 128) ? 5 : 4;
-    constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (P2 ? BN / 2 : BN) * BK * 2) + 1024 + kEpiWarps * 2048 * (BN <= 128 ? 2 : 1);
-    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, CL, CONV, P2>;
+    // (resident B: the ring carries A only; the weights take ceil(K/64) tiles of BN x 64 next to it)
+    const size_t smem = (size_t)STAGES * (BM * BK * 2 + (BRES ? 0 : (P2 ? BN / 2 : BN) * BK * 2)) +
+                        (BRES ? (size_t)((K + BK - 1) / BK) * BN * BK * 2 : 0) + 1024 + kEpiWarps * 2048 * (BN <= 128 ? 2 : 1);
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, CL, CONV, P2, BRES>;
     // per (instantiation, device): the dynamic shared-memory opt-in is a per-device function attribute
     static bool configured[64] = {};
     static int num_sms_dev[64] = {};
@@ -701,7 +731,9 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     cudaGetDevice(&dev);
     dev &= 63;
     if (!configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // (resident B: the size depends on K; opt in to the largest this mode is dispatched with)
+        const size_t smem_max = BRES ? (size_t)STAGES * BM * BK * 2 + (size_t)kMaxResidentKb * BN * BK * 2 + 1024 + kEpiWarps * 2048 * 2 : smem;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) {
             spnet_set_error("gemm_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return SPNET_ERR_CUDA;
@@ -941,10 +973,15 @@ int conv_tc_fwd_like(bool dgrad, const void* in, long long ld_in, int NB, int IH
     }
     GemmEpi epi = {out, ld_out, OUT_BF16, 0, colstats};
     const int M = (int)(tiles_m * BM);
+    // one 64-wide n-tile and at most kMaxResidentKb k-blocks: the weights stay in shared memory (BRES)
+    static const bool no_bres = getenv("SPNET_B200_NO_RESIDENT_B") != nullptr;
+    const bool bres = bn == 64 && K / BK <= kMaxResidentKb && !no_bres;
     if (!dgrad) {
+        if (bres) return launch_gemm<64, false, true, 1, 1, false, true>(ta, tb, td, epi, M, N, K, 1, stream, cg, (int)tiles_m);
         if (bn == 64) return launch_gemm<64, false, true, 1, 1>(ta, tb, td, epi, M, N, K, 1, stream, cg, (int)tiles_m);
         return launch_gemm<128, false, true, 1, 1>(ta, tb, td, epi, M, N, K, 1, stream, cg, (int)tiles_m);
     }
+    if (bres) return launch_gemm<64, false, false, 1, 1, false, true>(ta, tb, td, epi, M, N, K, 1, stream, cg, (int)tiles_m);
     if (bn == 64) return launch_gemm<64, false, false, 1, 1>(ta, tb, td, epi, M, N, K, 1, stream, cg, (int)tiles_m);
     return launch_gemm<128, false, false, 1, 1>(ta, tb, td, epi, M, N, K, 1, stream, cg, (int)tiles_m);
 }
