@@ -562,6 +562,10 @@ def run_fit(args, dev, Xu, Y):
     model = models.SPNetModel((H, W, 1), Y0size=N_OUT, quick_setup=True, backbone=args.backbone)
     model.compile(optimizer=models.Adam(lr=LR))
     out = {}
+    # the pool is repeated to 2,048 frames (32 steps per epoch) so that the once-per-epoch work of fit() - loss
+    # read-back, history, callbacks - weighs as little as in a real epoch of hundreds of steps
+    rep = max(1, 2048 // Xu.shape[0])
+    Xu, Y = np.concatenate([Xu] * rep), np.concatenate([Y] * rep)
     for label, X in (("uint8_frames", Xu), ("float32_frames", normalise_host(Xu))):
         steps = X.shape[0] // B
         model.fit(X, Y, batch_size=B, epochs=1, verbose=0)           # engine set-up, warm-up, graph capture
