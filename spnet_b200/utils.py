@@ -300,22 +300,28 @@ def decode_host(Yp):
 
 def csv_rows(Yp, ints, exists, file_list):
     """One text block per image, rows in predictor order: cx,cy,filename,rings,a,b,angle
-    (spnet/utils.py:122-126)."""
+    (spnet/utils.py:122-126). The reference formats numpy float32 scalars with "{}".format, which prints the value as a
+    Python float (shortest repr of the double): the columns are converted to Python lists once and formatted with %r /
+    %d - the same text, without a numpy scalar per field."""
     v = cf.vars_per_pred
     ang = _angles(Yp)
     rings = Yp[:, cf.ind_rings::v]
-    out = []
-    for j in range(Yp.shape[0]):
+    n = Yp.shape[0]
+    jj, aa = np.nonzero(np.asarray(exists)[:n])
+    sel = np.asarray(ints)[jj, aa]
+    c0, c1, c4, c5 = (sel[:, i].tolist() for i in range(4))
+    r = np.asarray(rings[jj, aa], dtype=np.float64).tolist()
+    g = np.asarray(ang[jj, aa], dtype=np.float64).tolist()
+    counts = np.bincount(jj, minlength=n).tolist()
+    out, k = [], 0
+    for j in range(n):
         base = os.path.basename(file_list[j])
-        idx = np.nonzero(exists[j])[0]
-        if idx.size == 0:
+        m = counts[j]
+        if m == 0:
             out.append("0,0," + base + ",0,0,0,0\n")
             continue
-        s = ""
-        for an in idx:
-            s += "{},{},{},{},{},{},{}".format(int(ints[j, an, 0]), int(ints[j, an, 1]), base, rings[j, an],
-                                                 int(ints[j, an, 2]), int(ints[j, an, 3]), ang[j, an]) + "\n"
-        out.append(s)
+        out.append("".join(["%d,%d,%s,%r,%d,%d,%r\n" % (c0[i], c1[i], base, r[i], c4[i], c5[i], g[i]) for i in range(k, k + m)]))
+        k += m
     return out
 
 
