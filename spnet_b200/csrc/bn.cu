@@ -420,7 +420,7 @@ static ChanGrid chan_grid(int CV, long long rows, int ctas_per_sm) {
     if (c.krows < 1) c.krows = 1;
     // one resident wave; at least 2*UNROLL rows per thread so the coefficient prologue is amortised
     long long gx = (rows + (long long)c.krows * 2 * UNROLL - 1) / ((long long)c.krows * 2 * UNROLL);
-    const long long cap = (148LL * ctas_per_sm) / nchunks;
+    const long long cap = ((long long)spnet_num_sms() * ctas_per_sm) / nchunks;
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     c.grid = dim3((unsigned)gx, nchunks);
@@ -437,7 +437,7 @@ static ChanGrid chan_grid_reduce(int CV, long long rows) {
     c.krows = 512 / c.cvb;
     if (c.krows < 1) c.krows = 1;
     long long gx = (rows + (long long)c.krows * 2 * UNROLL - 1) / ((long long)c.krows * 2 * UNROLL);
-    const long long cap = 148 / nchunks > 0 ? 148 / nchunks : 1;
+    const long long cap = spnet_num_sms() / nchunks > 0 ? spnet_num_sms() / nchunks : 1;
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     c.grid = dim3((unsigned)gx, nchunks);

@@ -167,6 +167,31 @@ static inline cudaError_t spnet_launch_pdl(void (*kern)(KArgs...), dim3 grid, di
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncSetAttribute (the dynamic shared-memory opt-in) is per DEVICE: one flag per device for a launcher's
+// "configured once" state. Returns true the first time it is called for the current device with these flags.
+static inline bool spnet_first_use_on_device(bool (&flags)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (flags[dev]) return false;
+    flags[dev] = true;
+    return true;
+}
+
+// SM count of the current device (148 on B200), cached per device: persistent grids are sized from it.
+static inline int spnet_num_sms() {
+    static int cached[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
 // dispatch on activation dtype code
 #define SPNET_DISPATCH_DTYPE(dtype, ...)                                   \
     do {                                                                   \

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kT) colsum_rows_kernel(const T* __restrict__ g
 
 int grid_for_n(long long n) {
     long long g = (n + kT - 1) / kT;
-    const long long cap = 148LL * 16;
+    const long long cap = (long long)spnet_num_sms() * 16;
     return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 

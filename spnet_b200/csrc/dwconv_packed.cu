@@ -533,13 +533,13 @@ Tiling pick_tiling(int kind, int dtype, int B, int H, int W, int C) {
         if (force_s && S > force_s) S = force_s;
         if (S < 2) continue;
         const long long n = (long long)B * ceil_div(H, th) * t.tiles_w;
-        long long gx = (148LL * ctas) / t.chunks;
+        long long gx = ((long long)spnet_num_sms() * ctas) / t.chunks;
         if (gx < 1) gx = 1;
         if (gx > n) gx = n;
         const long long per = (n + gx - 1) / gx;
         if (S > per + 1) S = (int)per + 1;
         // rows a CTA walks (+2 halo rows and ~1 row of per-tile overhead each), scaled by the share of an SM it gets
-        const double waves = (double)ceil_div(gx * t.chunks, 148LL * ctas);
+        const double waves = (double)ceil_div(gx * t.chunks, (long long)spnet_num_sms() * ctas);
         const double cost = (double)per * ((th < H ? th : H) + 3.0) * waves;
         if (cost < best) {
             best = cost;
@@ -554,14 +554,13 @@ template <typename T, int NC, bool AF, int RL>
 int launch_fwd_inst(const CUtensorMap& tm, const float* k, const float* a, const float* b, T* y, int B, int H, int W,
                     int C, const Tiling& t, cudaStream_t stream) {
     auto kern = dw3x3_fwd_packed_kernel<T, NC, AF, RL>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (spnet_first_use_on_device(configured)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) {
             spnet_set_error("dwconv3x3_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return SPNET_ERR_CUDA;
         }
-        configured = true;
     }
     cudaError_t e = spnet_launch_pdl(kern, dim3(t.grid_x, t.chunks), dim3(t.threads), t.smem, stream, 1, tm, k, a, b, y, B,
                                      H, W, C, t.TH, t.TW, t.tiles_h, t.tiles_w, t.S);
@@ -591,14 +590,13 @@ int launch_bwd_inst(const CUtensorMap& tg, const CUtensorMap& tx, const CUtensor
                     const float* b, const float* mean, const float* rstd, long long* stats, const T* sadd, T* gin,
                     float* dk, long long* dk_acc, int B, int H, int W, int C, const Tiling& t, cudaStream_t stream) {
     auto kern = dw3x3_bwd_packed_kernel<T, AF, RL, EPI>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (spnet_first_use_on_device(configured)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) {
             spnet_set_error("dwconv3x3_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return SPNET_ERR_CUDA;
         }
-        configured = true;
     }
     cudaError_t e = spnet_launch_pdl(kern, dim3(t.grid_x, t.chunks), dim3(t.threads), t.smem, stream, 1, tg, tx, ta, k, a,
                                      b, mean, rstd, stats, sadd, gin, dk, dk_acc, B, H, W, C, t.TH, t.TW, t.tiles_h, t.tiles_w,

@@ -1019,7 +1019,8 @@ int conv_tc_wgrad_impl(const void* X, long long ldx, int NB, int H, int W, int C
     }
     // split the pixel reduction so that taps x tiles x splits fills the SMs about once; >= 4 pixel blocks per split
     const long long tiles = (long long)((M + BM - 1) / BM) * ((N + bn - 1) / bn) * cg.ntaps;
-    long long sp = tiles >= 148 ? 1 : 148 / tiles;
+    const long long nsm_ = spnet_num_sms();
+    long long sp = tiles >= nsm_ ? 1 : nsm_ / tiles;
     if (sp > pixel_blocks / 4) sp = pixel_blocks / 4;
     const int splits = (int)(sp < 1 ? 1 : sp);
     GemmEpi epi = {dW, N, OUT_ATOMIC_F32, 0, nullptr};

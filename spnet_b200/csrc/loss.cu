@@ -353,7 +353,7 @@ int spnet_normalize_u8(const unsigned char* in, const float* lut, float* out, lo
     const long long n16 = n / 16;
     const int ntail = (int)(n - n16 * 16);
     long long blocks = (n16 + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > spnet_num_sms() * 8) blocks = spnet_num_sms() * 8;
     if (blocks < 1) blocks = 1;
     normalize_u8_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), lut,
                                                               reinterpret_cast<float4*>(out), n16, in + n16 * 16, out + n16 * 16,

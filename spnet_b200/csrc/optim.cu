@@ -163,7 +163,7 @@ __global__ void colsum_kernel(const float* __restrict__ g, float* __restrict__ o
 
 int grid_for(long long n) {
     long long g = (n + 255) / 256;
-    const long long cap = 148LL * 8;
+    const long long cap = (long long)spnet_num_sms() * 8;
     return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 

@@ -981,7 +981,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3c3_wgrad_strip_kernel(const 
 }
 
 int persist_grid_tiles(long long n_tiles, int ctas_per_sm) {
-    const long long cap = 148LL * ctas_per_sm;
+    const long long cap = (long long)spnet_num_sms() * ctas_per_sm;
     return (int)(n_tiles < cap ? n_tiles : cap);
 }
 

@@ -342,14 +342,14 @@ __global__ void __launch_bounds__(256) col2im3x3_kernel(const T* __restrict__ gc
 
 int persist_grid(long long n) {
     long long g = (n + 255) / 256;
-    const long long cap = 148LL * 4;
+    const long long cap = (long long)spnet_num_sms() * 4;
     return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 // one thread per group of 8 (bf16) / 4 (fp32) pixels; at most one resident wave (the kernels stride over the groups)
 int tri_grid(long long pixels, int dtype) {
     const long long groups = pixels / (dtype == SPNET_BF16 ? 8 : 4);
     long long g = (groups + 255) / 256;
-    const long long cap = 148LL * 8;
+    const long long cap = (long long)spnet_num_sms() * 8;
     return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
