@@ -515,7 +515,7 @@ def run_inference(args, rank, world, dev, Xu_inf, barrier):
     from spnet import models, utils
     import predict_spnet
     cf.compute_dtype, cf.basemodel, cf.model_type = "bf16", args.backbone, "big"
-    B = BATCH_PER_GPU
+    B = args.infer_batch
     pool = torch.from_numpy(Xu_inf).pin_memory()
     npool = pool.shape[0]
     per_rank = (args.infer_frames // world + npool - 1) // npool * npool   # whole passes over the pool
@@ -596,6 +596,7 @@ def main():
     ap.add_argument("--backbone", default="Xception", choices=["Xception", "MobileNet", "InceptionResNetV2"])
     ap.add_argument("--infer-frames", type=int, default=50_000, help="frames of the predict_spnet leg (whole job)")
     ap.add_argument("--infer-pool", type=int, default=512, help="distinct frames in the inference pool (cycled)")
+    ap.add_argument("--infer-batch", type=int, default=BATCH_PER_GPU, dest="infer_batch", help="batch_size passed to SPNetModel.predict")
     ap.add_argument("--quick", action="store_true", help="diagnostic runs: skip the CPU baseline and the per-family roofline legs")
     ap.add_argument("--gemm-shapes", type=int, default=10, dest="gemm_shapes", help="how many GEMM shapes the per-shape table lists")
     args = ap.parse_args()
