@@ -88,6 +88,14 @@ class ClockSampler:
             for k, v in zip(names, f[2:6]):
                 if v == "Active":
                     reasons.add(k)
+        if not mhz:  # nvidia-smi produced nothing in time: one in-process reading now rather than no clocks at all
+            poll = _NvmlPoll(self.index)
+            if poll.nv is not None:
+                try:
+                    return {"sm_mhz": float(poll.nv.nvmlDeviceGetClockInfo(poll.h, poll.nv.NVML_CLOCK_SM)), "sm_max_mhz": poll.max_mhz,
+                            "reasons": [], "sampler": "single NVML reading after the timed region (nvidia-smi gave no samples)"}
+                except Exception:
+                    pass
         return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "sampler": "nvidia-smi -lms 100 (separate process), %d samples" % len(mhz)}
 
