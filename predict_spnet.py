@@ -23,7 +23,7 @@ def _ranks():
 
 
 def predict_network(weights_file="spnet.model", datapath=default_image_dir, fraction=1.0, log_dir="logs/Predicting/",
-                    batch_size=16, model=None, X_pred="", draw_images=True, stream_chunk=None, raw_u8=True):
+                    batch_size=16, model=None, X_pred="", draw_images=True, stream_chunk=None, raw_u8=True, ranks=None):
     """stream_chunk (B200 build only): decode / predict the directory in chunks of that many frames, decoding chunk
     k+1 on the host threads while chunk k is on the GPU, instead of loading every frame into memory first.
     raw_u8: frames read from `datapath` travel to the GPU as uint8 and are normalised there (same values bit for bit).
@@ -32,7 +32,9 @@ def predict_network(weights_file="spnet.model", datapath=default_image_dir, frac
     GPU r (no collective on the data path) and writes hawley_spnet.csv.part<r>; rank 0 then concatenates the parts in
     rank order, so the rows of hawley_spnet.csv are in sorted-file order exactly as in a single-process run."""
     img_file_list = None
-    rank, world = _ranks()
+    # ranks = (rank, world) overrides the torchrun environment: train_spnet.py's post-training pass runs on rank 0
+    # ALONE (the other ranks have left), so it must not wait for their CSV parts
+    rank, world = ranks if ranks is not None else _ranks()
     shard_lo = 0
     streaming = stream_chunk is not None and isinstance(X_pred, str) and "" == X_pred
     if isinstance(X_pred, str) and "" == X_pred:

@@ -282,3 +282,31 @@ def test_predict_cli_sharded_over_ranks_writes_the_same_csv(tmp_path):
     b = open(str(tmp_path / "two") + "/hawley_spnet.csv").read()
     assert a == b and len(a.strip().splitlines()) >= n
     assert not [f for f in os.listdir(str(tmp_path / "two")) if "part" in f]
+
+
+def test_predict_network_ranks_override_ignores_the_torchrun_environment(tmp_path, monkeypatch):
+    """train_spnet.py's post-training prediction pass runs on rank 0 alone while WORLD_SIZE is still 2: with
+    ranks=(0, 1) predict_network must predict every frame and not wait for the other rank's CSV part (it used to
+    block for merge_csv_parts' ten-minute timeout)."""
+    from PIL import Image
+    import spnet.config as cf
+    from spnet import models
+    import predict_spnet
+    from spnet_b200 import fake_espi
+    cf.model_type, cf.compute_dtype = "big", "bf16"
+    n = 5
+    for i in range(n):
+        img, _ = fake_espi.make_frame(900 + i)
+        Image.fromarray(img).save(tmp_path / ("steelpan_%07d.png" % i))
+    X = np.zeros((2, 384, 512, 1), np.float32)
+    model, _ = models.setup_model(X, 576, try_checkpoint=False, freeze_fac=0.0, quick_setup=True)
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setenv("RANK", "0")
+    log_dir = str(tmp_path / "out") + "/"
+    predict_spnet.predict_network(weights_file="", datapath=str(tmp_path), fraction=1.0, log_dir=log_dir, batch_size=1,
+                                  model=model, X_pred="", draw_images=False, ranks=(0, 1))
+    text = open(log_dir + "hawley_spnet.csv").read()
+    for i in range(n):
+        assert ("steelpan_%07d.png" % i) in text
+    assert not [f for f in os.listdir(log_dir) if "part" in f]
+    cf.model_type = "monolithic"
