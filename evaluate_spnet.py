@@ -37,7 +37,13 @@ def evaluate_network(model=None, weights_file="", datapath="Test/", fraction=1.0
     if cf.loss_type != "same":  # convert from logits if needed
         Y_pred[:, cf.ind_noobj::cf.vars_per_pred] = 1.0 / (1.0 + np.exp(-Y_pred[:, cf.ind_noobj::cf.vars_per_pred]))
     Yt, Yp = utils.denorm_Y(Y_test), utils.denorm_Y(Y_pred)  # normalised -> 'world' values
-    mean_ap = diagnostics.calc_map(Yp, Yt)
+    try:
+        mean_ap = diagnostics.calc_map(Yp, Yt)
+    except ZeroDivisionError:
+        # no (prediction, label) pair with both ellipses present: tp = fp = fn = 0 and precision() divides by zero -
+        # the reference's precision() does the same and the script dies there; here the summary goes on without a mAP
+        mean_ap = float("nan")
+        print("    no detections at all: mean average precision is undefined (the reference raises ZeroDivisionError here)")
     print("mAP = ", mean_ap)
     (ring_miscounts, ring_truecounts, total_obj, false_obj_pos, false_obj_neg, true_obj_pos, true_obj_neg, pix_err,
      ipem) = diagnostics.calc_errors(Yp, Yt)

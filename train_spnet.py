@@ -105,13 +105,8 @@ if __name__ == "__main__":
         testpath = args.datapath + "/Test/"
         if not os.path.isdir(testpath):
             testpath = args.datapath + "/Val/"
-        try:
-            evaluate_network(model=model, weights_file="", datapath=testpath, fraction=1.0, log_dir="logs/Evaluation/",
-                             batch_size=args.batch_size, pred_grid=pred_grid, set_means_ranges=False)
-        except ZeroDivisionError:
-            # a network that detects nothing yet (a few epochs on a small set) has tp = fp = fn = 0 and precision()
-            # divides by zero, here as in the reference (spnet/diagnostics.py); the run's weights are still saved below
-            print("    no detections at all: mean average precision is undefined (the reference raises here)")
+        evaluate_network(model=model, weights_file="", datapath=testpath, fraction=1.0, log_dir="logs/Evaluation/",
+                         batch_size=args.batch_size, pred_grid=pred_grid, set_means_ranges=False)
         # make predictions on the Zooniverse dataset (:140-143); the reference's path is the author's home directory,
         # so the pass is skipped with a notice where that directory holds no frames (the reference would raise there)
         print("\n----------------------------\nStarting Zooniverse predictions...")
