@@ -447,10 +447,13 @@ def run_ours(args, rank, world):
         fams["dwconv_fwd"][2].append(("spnet_dwconv3x3_fwd", a))
     for a, _ in one_step.get("spnet_dwconv3x3_bwd_fused", []):
         fams["dwconv_bwd"][2].append(("spnet_dwconv3x3_bwd_fused", a))
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1", "traffic.json")))
-    except Exception:
-        traffic = {}
+    traffic = {}
+    for rnd in ("r2", "r1"):   # per-launch DRAM traffic of one representative launch per family, from ncu --set full
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", rnd, "traffic.json")))
+            break
+        except Exception:
+            pass
     roofs = {}
     for key, (bound, label, calls) in fams.items():
         if not calls:
