@@ -476,3 +476,34 @@ def test_keras_hdf5_weight_files_round_trip(tmp_path, backbone, hw):
             other.load_weights(wpath)
     finally:
         cf.basemodel = "Xception"
+
+
+def test_csv_rows_text_equals_the_reference_row_format_on_awkward_values():
+    """csv_rows formats from Python lists (%r / %d); the reference formats numpy float32 scalars with "{}".format
+    (spnet/utils.py:122-126). Same text for integral values, tiny / huge magnitudes, negatives and empty images."""
+    import spnet.config as cf
+    from spnet_b200 import utils
+    utils.setup_means_and_ranges([6, 6, 2, 8])
+    rng = np.random.default_rng(3)
+    n, v = 7, cf.vars_per_pred
+    Yp = (rng.standard_normal((n, 576)) * 60 + 120).astype(np.float32)
+    Yp[:, cf.ind_noobj::v] = 0.0                        # every predictor "exists" ...
+    Yp[2, cf.ind_noobj::v] = 1.0                        # ... except in image 2 (the "0,0,name,0,0,0,0" row)
+    Yp[0, cf.ind_rings::v] = np.float32(3.0)            # integral float -> "3.0"
+    Yp[1, cf.ind_rings::v] = np.float32(1e-5)           # -> "9.999999747378752e-06"
+    Yp[3, cf.ind_rings::v] = np.float32(-0.1)
+    Yp[4, cf.ind_rings::v] = np.float32(1.5e9)
+    ints, exists = utils.decode_host(Yp)
+    names = ["some/dir/frame_%03d.png" % i for i in range(n)]
+    got = utils.csv_rows(Yp, ints, exists, names)
+    ang, rings = utils._angles(Yp), Yp[:, cf.ind_rings::v]
+    want = []
+    for j in range(n):
+        base, idx = os.path.basename(names[j]), np.nonzero(exists[j])[0]
+        if idx.size == 0:
+            want.append("0,0," + base + ",0,0,0,0\n")
+            continue
+        want.append("".join("{},{},{},{},{},{},{}".format(int(ints[j, an, 0]), int(ints[j, an, 1]), base, rings[j, an],
+                                                          int(ints[j, an, 2]), int(ints[j, an, 3]), ang[j, an]) + "\n" for an in idx))
+    assert got == want
+    assert want[2] == "0,0,frame_002.png,0,0,0,0\n" and ",3.0," in want[0]
